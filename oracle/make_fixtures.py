@@ -1,0 +1,247 @@
+"""Mint golden vectors by EXECUTING THE REFERENCE'S OWN FUNCTIONS (build container only).
+
+    python -m oracle.make_fixtures            # G1-G5 (seconds)
+    python -m oracle.make_fixtures --config1  # BASELINE.json configs[0]: 7B shapes, fp32 CPU (minutes, ~30 GB)
+
+Outputs: tests/golden/*.npz.  Everything here comes from /root/reference/src code
+(VLDPOTrainer.get_batch_logps / dpo_loss, diff_lib.get_diff_ids, LlavaForRL.forward) except
+the trl-0.8.1 glue (concatenated_inputs / get_batch_loss_metrics), which is not on disk.
+Inputs are regenerated from seeds by `oracle.restate` (hash-based, device independent).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim, restate as R  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def hf_config(cfg: R.LlavaCfg):
+    from transformers import CLIPVisionConfig, LlamaConfig, LlavaConfig
+    v = CLIPVisionConfig(hidden_size=cfg.v_hidden, intermediate_size=cfg.v_ff, num_hidden_layers=cfg.v_layers,
+                         num_attention_heads=cfg.v_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                         hidden_act="quick_gelu", layer_norm_eps=cfg.v_eps, projection_dim=cfg.v_hidden)
+    t = LlamaConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.ff,
+                    num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads,
+                    rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
+                    attention_bias=False, mlp_bias=False, tie_word_embeddings=False)
+    c = LlavaConfig(vision_config=v, text_config=t, image_token_index=cfg.image_token_index,
+                    projector_hidden_act="gelu", vision_feature_select_strategy="default",
+                    vision_feature_layer=cfg.vision_feature_layer, tie_word_embeddings=False)
+    c.pad_token_id = cfg.pad_token_id
+    c.ignore_index = cfg.ignore_index
+    c._attn_implementation = "eager"
+    return c
+
+
+def hf_name(name: str) -> str:
+    """transformers-4.41 parameter name -> transformers-5.5 LlavaForConditionalGeneration name."""
+    if name == "language_model.lm_head.weight":
+        return "lm_head.weight"
+    if name.startswith("language_model.model."):
+        return "model.language_model." + name[len("language_model.model."):]
+    return "model." + name
+
+
+def build_reference_model(cfg: R.LlavaCfg, weights):
+    _, _, LlavaShim = ref_shim.reference_symbols()
+    hc = hf_config(cfg)
+    with torch.device("meta"):
+        m = LlavaShim(hc)
+    m = m.to_empty(device="cpu")
+    sd = m.state_dict()
+    missing = []
+    with torch.no_grad():
+        for n, t in weights.items():
+            k = hf_name(n)
+            if k not in sd:
+                missing.append(k)
+                continue
+            sd[k].copy_(t)
+    assert not missing, missing[:5]
+    loaded = {hf_name(n) for n in weights}
+    not_set = [k for k in sd if k not in loaded and "post_layernorm" not in k]
+    assert not not_set, not_set[:5]
+    for k in sd:  # post_layernorm is unused by the path (hidden_states[-2]); make it finite
+        if "post_layernorm" in k:
+            sd[k].fill_(1.0 if k.endswith("weight") else 0.0)
+    # non-persistent buffers (position_ids, rotary inv_freq) are lost by to_empty(): rebuild them
+    emb = m.model.vision_tower.vision_model.embeddings
+    emb.position_ids = torch.arange(emb.num_positions).expand((1, -1))
+    rot = m.model.language_model.rotary_emb
+    inv, scale = rot.compute_default_rope_parameters(rot.config, "cpu") if hasattr(rot, "compute_default_rope_parameters") \
+        else rot.rope_init_fn(rot.config, "cpu")
+    rot.inv_freq = inv
+    rot.original_inv_freq = inv
+    rot.attention_scaling = scale
+    m.eval()
+    return m
+
+
+def reference_concatenated_forward(model, cfg, batch, loss_type="sigmoid"):
+    """The reference's VLDPOTrainer.concatenated_forward body (base/trainer.py:204-242) driven with
+    the restated trl concatenated_inputs; model(...) and get_batch_logps are the reference's own."""
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    cb = R.concatenated_inputs(batch, -100, 0)
+    with torch.no_grad():
+        out = model(input_ids=cb["concatenated_input_ids"], attention_mask=cb["concatenated_attention_mask"],
+                    labels=cb["concatenated_labels"], use_cache=False, **cb["concatenated_img_input_dict"])
+    logps = VLDPOTrainer.get_batch_logps(out.logits, out.labels, average_log_prob=False, is_encoder_decoder=False,
+                                         label_pad_token_id=-100, mask_shared_tokens=(loss_type == "ddpo"))
+    return logps, out
+
+
+def ref_dpo_loss(pc, pr, rc, rr, beta, ls, loss_type, reference_free=False):
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    self = SimpleNamespace(beta=beta, label_smoothing=ls, loss_type=loss_type, reference_free=reference_free,
+                           accelerator=SimpleNamespace(device="cpu"))
+    return VLDPOTrainer.dpo_loss(self, pc, pr, rc, rr)
+
+
+def g1_logps():
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    out = {}
+    g = torch.Generator().manual_seed(1)
+    for tag, (B2, S, V) in {"a": (4, 37, 320), "b": (2, 200, 2048), "c": (6, 16, 32064)}.items():
+        logits = torch.randn(B2, S, V, generator=g) * 3.0
+        labels = torch.randint(0, V, (B2, S), generator=g)
+        for b in range(B2):
+            p = int(torch.randint(1, S // 2, (1,), generator=g))
+            e = int(torch.randint(S // 2 + 1, S + 1, (1,), generator=g))
+            labels[b, :p] = -100
+            labels[b, e:] = -100
+        out[f"{tag}_logits"] = logits.numpy()
+        out[f"{tag}_labels"] = labels.numpy()
+        out[f"{tag}_sum"] = VLDPOTrainer.get_batch_logps(logits, labels).numpy()
+        out[f"{tag}_avg"] = VLDPOTrainer.get_batch_logps(logits, labels, average_log_prob=True).numpy()
+        bl = logits.to(torch.bfloat16)
+        out[f"{tag}_sum_bf16in_refdtype"] = VLDPOTrainer.get_batch_logps(bl, labels).float().numpy()
+        out[f"{tag}_sum_bf16in_fp32math"] = VLDPOTrainer.get_batch_logps(bl.float(), labels).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "g1_logps.npz"), **out)
+
+
+def g2_loss():
+    out = {}
+    g = torch.Generator().manual_seed(2)
+    pc, pr, rc, rr = [(-torch.rand(5, generator=g) * 400 - 20) for _ in range(4)]
+    rc = pc + torch.randn(5, generator=g) * 4
+    rr = pr + torch.randn(5, generator=g) * 4
+    out.update(pc=pc.numpy(), pr=pr.numpy(), rc=rc.numpy(), rr=rr.numpy())
+    for lt in ("sigmoid", "ddpo", "hinge", "ipo", "kto_pair"):
+        for ls in (0.0, 0.1):
+            for rf in (False, True):
+                l, c, r = ref_dpo_loss(pc, pr, rc, rr, 0.1, ls, lt, rf)
+                k = f"{lt}_ls{ls}_rf{int(rf)}"
+                out[k + "_losses"], out[k + "_cr"], out[k + "_rr"] = l.numpy(), c.numpy(), r.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "g2_loss.npz"), **out)
+
+
+def g3_ddpo():
+    _, get_diff_ids, _ = ref_shim.reference_symbols()
+    rs = np.random.RandomState(3)
+    cases = {}
+    # (a) single substitution inside shared text
+    a = rs.randint(3, 30000, size=1598).tolist()
+    b = list(a)
+    b[740:745] = rs.randint(3, 30000, size=3).tolist()
+    cases["subst"] = (a, b)
+    # (b) repetitive response triggering autojunk (len >= 200, a token > 1% + 1 times)
+    a = ([5, 6, 7, 8] * 250)[:1000]
+    a[100:103] = [11, 12, 13]
+    b = list(a)
+    b[900:905] = [21, 22]
+    cases["autojunk"] = (a, b)
+    # (c) identical
+    a = rs.randint(3, 30000, size=300).tolist()
+    cases["identical"] = (a, list(a))
+    # (d) pure insertion (not counted: both-sides-non-empty rule)
+    b = list(a)
+    b[150:150] = [7, 7, 7, 7]
+    cases["insertion"] = (a, b)
+    # (e) masked-label style: zeros prefix + zeros suffix (labels==-100 rewritten to 0), several edits
+    a = [0] * 600 + rs.randint(3, 30000, size=700).tolist() + [0] * 298
+    b = list(a)
+    for s in (650, 800, 1000, 1200):
+        b[s:s + 4] = rs.randint(3, 30000, size=rs.randint(1, 8)).tolist()
+    b = (b + [0] * 1598)[:1598]
+    cases["masked"] = (a, b)
+    # (f) short blocks below min_match_size
+    a = rs.randint(3, 50, size=120).tolist()
+    b = rs.randint(3, 50, size=110).tolist()
+    cases["noisy_small_vocab"] = (a, b)
+    # (g) random small-alphabet long sequences (autojunk + many blocks)
+    a = rs.randint(3, 40, size=900).tolist()
+    b = list(a)
+    for s in range(50, 850, 90):
+        b[s:s + 5] = rs.randint(3, 40, size=4).tolist()
+    cases["small_alpha_long"] = (a, b)
+    out = {}
+    for k, (a, b) in cases.items():
+        ia, ib = get_diff_ids(a, b, min_match_size=3)
+        out[k + "_a"], out[k + "_b"] = np.array(a, dtype=np.int64), np.array(b, dtype=np.int64)
+        out[k + "_ia"], out[k + "_ib"] = np.array(ia, dtype=np.int64), np.array(ib, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "g3_ddpo.npz"), **out)
+
+
+def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed: int, ddpo: bool):
+    wp, wr = R.make_policy_and_ref(cfg, seed)
+    batch = R.make_batch(cfg, n_pairs, text_len, prompt_len, seed, ddpo_like=ddpo)
+    out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
+    res = {}
+    for who, w in (("policy", wp), ("ref", wr)):
+        t0 = time.time()
+        m = build_reference_model(cfg, w)
+        logps, o = reference_concatenated_forward(m, cfg, batch, "sigmoid")
+        res[who] = logps
+        out[f"{who}_logps"] = logps.numpy()
+        if ddpo:
+            dl, _ = reference_concatenated_forward(m, cfg, batch, "ddpo")
+            out[f"{who}_logps_ddpo"] = dl.numpy()
+            res[who + "_ddpo"] = dl
+        if who == "policy":
+            out["labels"] = o.labels.numpy()
+            out["image_position_map"] = o.image_position_map.numpy()
+            if o.logits.numel() < 4_000_000:
+                out["policy_logits"] = o.logits.numpy()
+            out["policy_logits_mean_chosen"] = o.logits[:n_pairs].mean().numpy()
+            out["policy_logits_mean_rejected"] = o.logits[n_pairs:].mean().numpy()
+        print(f"[{tag}] {who} forward {time.time() - t0:.1f}s", flush=True)
+        del m, o
+    n = n_pairs
+    for lt in ("sigmoid", "ipo", "hinge", "kto_pair") + (("ddpo",) if ddpo else ()):
+        sfx = "_ddpo" if lt == "ddpo" else ""
+        pl, rl = res["policy" + sfx], res["ref" + sfx]
+        l, c, r = ref_dpo_loss(pl[:n], pl[n:], rl[:n], rl[n:], 0.1, 0.0, lt)
+        out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
+    print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "sigmoid_losses"}, flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config1", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    if args.config1:
+        # BASELINE.json configs[0]: LLaVA-1.5-7B shapes, 2 pairs, text 128 (+575 -> 703), fp32 CPU
+        g45_llava("g5_config1_7b", R.LLAVA15_7B, 2, 128, 32, 0, ddpo=False)
+        return
+    g1_logps()
+    g2_loss()
+    g3_ddpo()
+    g45_llava("g4_tiny", R.TINY, 2, 24, 8, 0, ddpo=True)
+    g45_llava("g4_small", R.SMALL, 2, 96, 24, 0, ddpo=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""oracle/restate.py (CPU restatement) vs golden vectors minted from the reference's own functions."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_g1_get_batch_logps_matches_reference():
+    d = load("g1_logps.npz")
+    for tag in "abc":
+        logits, labels = torch.from_numpy(d[f"{tag}_logits"]), torch.from_numpy(d[f"{tag}_labels"])
+        np.testing.assert_allclose(R.get_batch_logps(logits, labels).numpy(), d[f"{tag}_sum"], rtol=1e-6, atol=1e-4)
+        np.testing.assert_allclose(R.get_batch_logps(logits, labels, average_log_prob=True).numpy(), d[f"{tag}_avg"],
+                                   rtol=1e-6, atol=1e-5)
+        # the reference-dtype (bf16 log_softmax + bf16 sum) path is itself ~1e-3..1e-2 off the fp32 math
+        ref32, refbf = d[f"{tag}_sum_bf16in_fp32math"], d[f"{tag}_sum_bf16in_refdtype"]
+        assert np.max(np.abs(refbf - ref32) / np.abs(ref32)) < 2e-2
+
+
+def test_g1_shape_mismatch_raises():
+    with pytest.raises(ValueError):
+        R.get_batch_logps(torch.zeros(2, 5, 7), torch.zeros(2, 4, dtype=torch.long))
+
+
+def test_g2_dpo_loss_matches_reference():
+    d = load("g2_loss.npz")
+    pc, pr, rc, rr = (torch.from_numpy(d[k]) for k in ("pc", "pr", "rc", "rr"))
+    for lt in ("sigmoid", "ddpo", "hinge", "ipo", "kto_pair"):
+        for ls in (0.0, 0.1):
+            for rf in (False, True):
+                l, c, r = R.dpo_loss(pc, pr, rc, rr, 0.1, ls, lt, rf)
+                k = f"{lt}_ls{ls}_rf{int(rf)}"
+                np.testing.assert_allclose(l.numpy(), d[k + "_losses"], rtol=1e-6, atol=1e-6)
+                np.testing.assert_allclose(c.numpy(), d[k + "_cr"], rtol=1e-6, atol=1e-6)
+                np.testing.assert_allclose(r.numpy(), d[k + "_rr"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        R.dpo_loss(pc, pr, rc, rr, loss_type="nope")
+
+
+def test_g3_ddpo_diff_ids_matches_reference():
+    d = load("g3_ddpo.npz")
+    cases = sorted({k[:-2] for k in d.files if k.endswith("_a")})
+    assert len(cases) >= 7
+    for c in cases:
+        ia, ib = R.get_diff_ids(d[c + "_a"].tolist(), d[c + "_b"].tolist(), 3)
+        assert ia == d[c + "_ia"].tolist(), c
+        assert ib == d[c + "_ib"].tolist(), c
+    assert d["identical_ia"].size == 0 and d["insertion_ia"].size == 0
+
+
+@pytest.mark.parametrize("tag,cfg,npairs,tl,pl", [("g4_tiny", R.TINY, 2, 24, 8), ("g4_small", R.SMALL, 2, 96, 24)])
+def test_g4_llava_forward_matches_reference(tag, cfg, npairs, tl, pl):
+    d = load(tag + ".npz")
+    wp, wr = R.make_policy_and_ref(cfg, int(d["seed"]))
+    batch = R.make_batch(cfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True)
+    cb = R.concatenated_inputs(batch)
+    with torch.no_grad():
+        logits, labels, img_map = R.llava_forward(cfg, wp, cb["concatenated_input_ids"],
+                                                  cb["concatenated_attention_mask"], cb["concatenated_labels"],
+                                                  **cb["concatenated_img_input_dict"])
+    assert np.array_equal(labels.numpy(), d["labels"])
+    assert np.array_equal(img_map.numpy(), d["image_position_map"])
+    if "policy_logits" in d.files:
+        np.testing.assert_allclose(logits.numpy(), d["policy_logits"], rtol=2e-4, atol=2e-4)
+    with torch.no_grad():
+        loss, metrics, aux = R.get_batch_loss_metrics(cfg, wp, wr, batch)
+    pol = torch.cat([aux["policy_chosen_logps"], aux["policy_rejected_logps"]]).numpy()
+    ref = torch.cat([aux["reference_chosen_logps"], aux["reference_rejected_logps"]]).numpy()
+    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(aux["losses"].numpy(), d["sigmoid_losses"], rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        _, _, aux = R.get_batch_loss_metrics(cfg, wp, wr, batch, loss_type="ddpo")
+    pol = torch.cat([aux["policy_chosen_logps"], aux["policy_rejected_logps"]]).numpy()
+    np.testing.assert_allclose(pol, d["policy_logps_ddpo"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(aux["losses"].numpy(), d["ddpo_losses"], rtol=1e-4, atol=1e-5)
+    assert np.abs(d["policy_logps_ddpo"]).max() > 0  # the DDPO mask is non-trivial
+
+
+def test_hash_uniform_known_values():
+    # pins the generator the CUDA init kernel must reproduce bit-for-bit
+    t = R.hash_uniform(5, 1234, 1.0)
+    assert t.dtype == torch.float32
+    assert np.all(np.abs(t.numpy()) <= 1.0)
+    t2 = R.hash_uniform(5, 1234, 1.0)
+    assert torch.equal(t, t2)
+    big = R.hash_uniform(1 << 16, 7, 1.0).numpy()
+    assert abs(big.mean()) < 0.02 and abs(big.std() - 1 / np.sqrt(3)) < 0.01
