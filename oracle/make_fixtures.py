@@ -111,7 +111,7 @@ def g1_logps():
     VLDPOTrainer, _, _ = ref_shim.reference_symbols()
     out = {}
     g = torch.Generator().manual_seed(1)
-    for tag, (B2, S, V) in {"a": (4, 37, 320), "b": (2, 200, 2048), "c": (6, 16, 32064)}.items():
+    for tag, (B2, S, V) in {"a": (4, 37, 320), "b": (2, 200, 2048), "c": (2, 12, 32064)}.items():
         logits = torch.randn(B2, S, V, generator=g) * 3.0
         labels = torch.randint(0, V, (B2, S), generator=g)
         for b in range(B2):
@@ -210,7 +210,7 @@ def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len
         if who == "policy":
             out["labels"] = o.labels.numpy()
             out["image_position_map"] = o.image_position_map.numpy()
-            if o.logits.numel() < 4_000_000:
+            if o.logits.numel() < 1_000_000:
                 out["policy_logits"] = o.logits.numpy()
             out["policy_logits_mean_chosen"] = o.logits[:n_pairs].mean().numpy()
             out["policy_logits_mean_rejected"] = o.logits[n_pairs:].mean().numpy()
