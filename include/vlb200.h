@@ -1,0 +1,192 @@
+/* libvlb200 -- C ABI of the B200-native VL-DPO hot path.
+ *
+ * The reference (TideDra/VL-RLHF) has no FFI of its own: its hot path is Python calling
+ * transformers/trl/torch.  The entry points below are what a binding for that path needs:
+ * plain device pointers + sizes + a cudaStream_t (as void*), no torch types.  Each block cites
+ * the reference code it replaces (paths relative to the reference repo root, or the
+ * transformers module the reference delegates to).  INTEGRATION.md shows the ctypes stub and
+ * the ModelCoreMapper plug-in a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (VLB200_OK) or a VLB200_ERR_* code; vlb200_last_error() gives
+ *     the message (thread-local).  Asynchronous CUDA faults surface at the next sync.
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host.
+ *   - work is enqueued on `stream` (cudaStream_t); nothing synchronises unless stated.
+ *   - bf16 = __nv_bfloat16 storage; accumulation is always fp32.
+ *   - no hidden allocations after the first call of a given shape (TMA descriptor cache only).
+ */
+#ifndef VLB200_H
+#define VLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLB200_OK 0
+#define VLB200_ERR_INVALID 1 /* bad argument (maps to Python ValueError, like base/trainer.py:157-158) */
+#define VLB200_ERR_CUDA 2    /* CUDA runtime/driver failure (maps to RuntimeError) */
+#define VLB200_ERR_UNSUPPORTED 3
+
+#define VLB200_ABI_VERSION 1
+
+int vlb200_abi_version(void);
+const char* vlb200_last_error(void);
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+uint64_t vlb200_launch_count(void);
+
+/* ---- dtype tags ---------------------------------------------------------------------- */
+#define VLB200_BF16 0
+#define VLB200_F32 1
+
+/* ---- deterministic synthetic init (twin of oracle/restate.py::hash_uniform) -----------
+ * dst[i] = bf16( shift + scale * (2 * (lowbias32(i ^ lowbias32(seed)) >> 8) * 2^-24 - 1) )   */
+int vlb200_init_uniform(void* dst, int dtype, uint64_t n, uint32_t seed, float scale, float shift, void* stream);
+/* dst = bf16( base + alpha * (other - shift) )  (reference-model perturbation, oracle make_policy_and_ref) */
+int vlb200_perturb_bf16(void* dst, const void* base, const void* other, uint64_t n, float alpha, float shift,
+                        void* stream);
+
+/* ---- GEMM (tcgen05 / TMEM / TMA) --------------------------------------------------------
+ * Replaces every nn.Linear / Conv2d-as-GEMM the reference reaches through transformers:
+ * CLIP q/k/v/out/fc1/fc2 (modeling_clip.py), LlavaMultiModalProjector (modeling_llava.py:87-107),
+ * Llama q/k/v/o/gate/up/down/lm_head (modeling_llama.py), and their autograd backward.
+ *
+ *   D[M,N] = epilogue( sum_k opA(A)[m,k] * opB(B)[n,k] )
+ *   opA: a_kmajor=1 -> A is row-major [M,K] (lda >= K);  a_kmajor=0 -> A is row-major [K,M] (lda >= M)
+ *   opB: b_kmajor=1 -> B is row-major [N,K] (ldb >= K)   (nn.Linear weight layout: y = x W^T)
+ *        b_kmajor=0 -> B is row-major [K,N] (ldb >= N)
+ *   epilogue: + bias[n] (bf16 or NULL), activation, + residual[m,n] (bf16, ldr, or NULL),
+ *             accumulate=1 adds the previous contents of D (gradient accumulation).
+ *   out_dtype: VLB200_BF16 or VLB200_F32.   All leading dimensions in elements; pointers 16-byte
+ *   aligned; lda/ldb multiples of 8.                                                         */
+#define VLB200_ACT_NONE 0
+#define VLB200_ACT_QUICK_GELU 1 /* x * sigmoid(1.702 x)   (CLIP MLP) */
+#define VLB200_ACT_GELU_ERF 2   /* projector */
+int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D, int ldd,
+                     int out_dtype, int M, int N, int K, const void* bias, int act, const void* residual, int ldr,
+                     int accumulate, void* stream);
+
+/* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
+ * logits: [rows, V] (dtype bf16|f32, row stride ld_logits elements).  Row r predicts target[r];
+ * target[r] < 0 (label_pad) rows are skipped without being read.  rows = n_seq * rows_per_seq
+ * (row r belongs to sequence r / rows_per_seq).
+ * weight[r] (u8, optional) is the DDPO shared-token mask (trainer.py:169-184): 0 drops the row.
+ * Outputs: per_token_logp[r] (f32, 0 for skipped rows), lse[r] (f32), logps[n_seq] (f32; sum, or
+ * mean over counted rows when average_log_prob).  Deterministic (two-stage reduction).        */
+int vlb200_logps_fwd(const void* logits, int logits_dtype, int64_t ld_logits, const int64_t* target,
+                     const uint8_t* weight, int rows, int rows_per_seq, int n_seq, int V, int average_log_prob,
+                     float* per_token_logp, float* lse, float* logps, void* stream);
+/* dlogits[r, v] = g[seq(r)] * w[r] * (onehot(target[r]) - softmax(logits[r])) (bf16 out, may alias
+ * bf16 logits).  Skipped rows are written as zeros.                                          */
+int vlb200_logps_bwd(const void* logits, int logits_dtype, int64_t ld_logits, const int64_t* target,
+                     const uint8_t* weight, const float* lse, const float* grad_logps, int rows, int rows_per_seq,
+                     int n_seq, int V, int average_log_prob, void* dlogits, int64_t ld_dlogits, void* stream);
+
+/* ---- preference loss (K18) -- base/trainer.py:244-301 VLDPOTrainer.dpo_loss -------------
+ * loss_type: sigmoid / hinge / ipo / kto_pair / ddpo (ddpo == sigmoid on DDPO-masked logps).
+ * Inputs policy_logps / ref_logps are [2*n_pairs] (chosen first, like concatenated_forward).
+ * losses has n_pairs entries (2*n_pairs for kto_pair, chosen half then rejected half).
+ * stats[0..5] = mean loss, reward accuracy, mean chosen reward, mean rejected reward, mean margin, n_losses
+ * grad_policy_logps (optional) = d(mean(losses) * loss_scale)/d policy_logps.                */
+#define VLB200_LOSS_SIGMOID 0
+#define VLB200_LOSS_HINGE 1
+#define VLB200_LOSS_IPO 2
+#define VLB200_LOSS_KTO_PAIR 3
+#define VLB200_LOSS_DDPO 4
+int vlb200_dpo_loss(const float* policy_logps, const float* ref_logps, int n_pairs, float beta,
+                    float label_smoothing, int loss_type, int reference_free, float loss_scale, float* losses,
+                    float* chosen_rewards, float* rejected_rewards, float* stats, float* grad_policy_logps,
+                    void* stream);
+
+/* ---- norms ----------------------------------------------------------------------------
+ * RMSNorm = LlamaRMSNorm (transformers modeling_llama.py:53-67); LayerNorm = CLIP pre/layer norms
+ * (modeling_clip.py).  x,y,w,b bf16; statistics fp32.  cols % 8 == 0, cols <= 8192.            */
+int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int rows, int cols,
+                       float eps, void* stream);
+/* dx = d(rmsnorm)/dx (+ dres), dw (+)= sum_rows dy * xhat.  x/dy/dx/dres contiguous [rows, cols].
+ * workspace: vlb200_norm_bwd_workspace_floats(cols) floats.                                    */
+int vlb200_norm_bwd_workspace_floats(int cols);
+int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                       void* dw, int dw_accumulate, float* workspace, int rows, int cols, void* stream);
+int vlb200_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows,
+                         int cols, float eps, void* stream);
+/* out[c] (bf16) (+)= sum_r a[r, c]  (bias gradients).  workspace as for rmsnorm_bwd.            */
+int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, void* out, int accumulate, float* workspace,
+                  void* stream);
+
+/* ---- RoPE / SwiGLU / GELU (modeling_llama.py:146-184, modeling_llava.py:87-107) -----------
+ * rope: rotate-half in place on the first n_rot_heads heads (q heads then k heads) of each row of qkv;
+ * pos[rows] int32 indexes cos/sin tables [max_pos, head_dim/2] fp32; inverse=1 applies the transpose.   */
+int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int rows,
+                int n_rot_heads, int head_dim, int inverse, void* stream);
+/* gate_up = [gate | up] per row (2*ff columns); act = silu(gate) * up                           */
+int vlb200_swiglu_fwd(const void* gate_up, int64_t ld_gu, void* act, int64_t ld_act, int rows, int ff, void* stream);
+int vlb200_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_dact, void* dgate_up,
+                      int64_t ld_dgu, int rows, int ff, void* stream);
+int vlb200_gelu_fwd(const void* z, void* h, uint64_t n, void* stream);
+int vlb200_gelu_bwd(const void* z, const void* dh, void* dz, uint64_t n, void* stream);
+
+/* ---- CLIP patch embedding helpers (modeling_clip.py:138-219) -------------------------------
+ * im2col: pixels [B,3,H,W] (f32|bf16) -> patches [B*(H/p)*(W/p), ld_out] bf16, column = c*p*p + ky*p + kx.
+ * cls_rows: x[b*tokens_per_img, :] = class_embedding + position_embedding[0].                      */
+int vlb200_clip_im2col(const void* pixels, int pixel_dtype, void* patches, int64_t ld_out, int batch, int height,
+                       int width, int patch, void* stream);
+int vlb200_clip_cls_rows(void* x, const void* cls, const void* pos0, int batch, int tokens_per_img, int d, void* stream);
+
+/* ---- row movers (bf16, 16-byte granularity) -------------------------------------------------- */
+int vlb200_copy_rows(const void* src, int64_t src_group_stride, int64_t src_row_stride, int src_row0, void* dst,
+                     int64_t dst_group_stride, int64_t dst_row_stride, int groups, int rows_per_group, int cols,
+                     void* stream);
+int vlb200_gather_rows(const void* src, int64_t ld_src, const int* index, void* dst, int64_t ld_dst, int n, int cols,
+                       void* stream);
+int vlb200_scatter_rows(const void* src, int64_t ld_src, const int* index, void* dst, int64_t ld_dst, int n, int cols,
+                        void* stream);
+int vlb200_memset_zero(void* dst, uint64_t bytes, void* stream);
+
+/* ---- LLaVA text/image merge (K7+K8) -- models/Llava/__init__.py:36-109 ---------------------
+ * merge_index: integer pass (one thread per sequence).  Outputs, all device:
+ *   src_map[n_seq*S] (>=0 embed row, -1-k image feature row k, INT_MIN zero row), labels_merged[n_seq*S] i64,
+ *   mask_merged / position_ids [n_seq*S] i32, seqlens[n_seq], img_pos[n_seq*imgs_per_seq*P],
+ *   row_of_text[n_seq*(L-1)] (flat merged row whose logits predict text token j), target[n_seq*(L-1)] i64,
+ *   status: 0 ok, 1 too many image tokens, 2 ragged image counts, 3 attention mask is not a prefix.
+ * Sequence b uses images (b % n_img_batch)*imgs_per_seq ... (the reference duplicates pixel_values [v, v]).  */
+int vlb200_llava_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels, int n_seq,
+                             int text_len, int merged_len, int n_patches, int n_img_batch, int imgs_per_seq,
+                             int image_token, int pad_token, int ignore_index, int* src_map, int64_t* labels_merged,
+                             int* mask_merged, int* position_ids, int* seqlens, int* img_pos, int* row_of_text,
+                             int64_t* target, int* status, void* stream);
+int vlb200_llava_merge_embed(const int* src_map, const void* embed_tokens, const void* image_features, void* out,
+                             int rows, int d, void* stream);
+/* dembed_f32[V,d] += text-row grads (fp32 atomics); dimage_features = sum over sequences sharing the image */
+int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
+                           void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq, int d,
+                           void* stream);
+
+/* ---- attention (K4, K12) -- CLIPAttention (modeling_clip.py:261-334), LlamaAttention
+ * (modeling_llama.py:199-290).  q/k/v/out rows are tokens (row = b*S + t), head h at column h*head_dim.
+ * causal + key-padding via seqlens[B] (attended prefix length; NULL = S).  lse/delta: [B,H,S] f32.
+ * head_dim 64 or 128; H % KVH == 0 (GQA).                                                          */
+int vlb200_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                    int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH, int head_dim, int causal,
+                    float scale, void* stream);
+int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
+                    int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
+                    void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,
+                    int head_dim, int causal, float scale, void* stream);
+
+/* ---- optimizer (K24: torch.optim.AdamW semantics, HF Trainer max_grad_norm clipping) ---------
+ * sumsq: out[0] (+)= sum x^2 (deterministic two-stage; workspace 1024 floats).
+ * adamw: bf16 param/grad, fp32 master + moments; grads are multiplied by grad_scale and by the clip
+ * coefficient min(1, max_grad_norm / (sqrt(grad_sumsq[0])*grad_scale + 1e-6)) when grad_sumsq != NULL.  */
+int vlb200_sumsq_bf16(const void* x, uint64_t n, float* workspace_1024, float* out, int accumulate, void* stream);
+int vlb200_adamw(void* param_bf16, const void* grad_bf16, float* master, float* exp_avg, float* exp_avg_sq, uint64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                 const float* grad_sumsq, float max_grad_norm, void* stream);
+int vlb200_cast_f32_to_bf16(const float* src, void* dst, uint64_t n, float scale, void* stream);
+int vlb200_cast_bf16_to_f32(const void* src, float* dst, uint64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLB200_H */

@@ -72,7 +72,7 @@ class LlavaCfg:
 
 LLAVA15_7B = LlavaCfg()
 
-TINY = LlavaCfg(image_size=28, patch_size=14, v_hidden=64, v_layers=3, v_heads=2, v_ff=128,
+TINY = LlavaCfg(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_heads=2, v_ff=256,
                 hidden=128, layers=2, heads=2, kv_heads=2, ff=256, vocab=320,
                 image_token_index=300, pad_token_id=301)
 

@@ -1,0 +1,444 @@
+"""TEST-ONLY stand-in for `vlrlhf_b200.ops` built from plain PyTorch CPU ops (fp32 math, bf16 storage).
+
+Purpose: run the engine's host-side orchestration (buffer plumbing, GEMM orientations, backward formulas,
+optimizer sequencing, data-parallel all-reduce over gloo) on the CPU-only build box, against the oracle.
+It is never importable from the product package and never used on a GPU box."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1, 2
+LOSS_TYPES = {"sigmoid": 0, "hinge": 1, "ipo": 2, "kto_pair": 3, "ddpo": 4}
+_launches = [0]
+
+
+def launch_count():
+    return _launches[0]
+
+
+def _c(n=1):
+    _launches[0] += n
+
+
+def _lowbias32(x):
+    x = x.clone()
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def init_uniform_(t, seed, scale, shift=0.0):
+    from oracle.restate import hash_uniform
+    t.copy_(hash_uniform(t.numel(), seed, scale, shift).to(t.dtype))
+    _c()
+    return t
+
+
+def perturb_(dst, base, other, alpha, shift):
+    dst.copy_((base.float() + alpha * (other.float() - shift)).to(torch.bfloat16))
+    _c()
+    return dst
+
+
+def gemm(a, b, *, a_kmajor=True, b_kmajor=True, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
+         residual=None, accumulate=False):
+    A = a.float() if a_kmajor else a.float().t()
+    B = b.float() if b_kmajor else b.float().t()
+    if A.shape[1] != B.shape[1]:
+        raise ValueError("gemm: contraction mismatch")
+    y = A @ B.t()
+    if bias is not None:
+        y = y + bias.float()
+    if act == ACT_QUICK_GELU:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == ACT_GELU_ERF:
+        y = F.gelu(y)
+    if residual is not None:
+        y = y + residual.float()
+    if out is None:
+        out = torch.empty(y.shape, dtype=out_dtype)
+    if accumulate:
+        y = y + out.float()
+    out.copy_(y.to(out.dtype))
+    _c()
+    return out
+
+
+def logps_fwd(logits, target, n_seq, weight=None, average_log_prob=False):
+    rows, V = logits.shape
+    if target.numel() != rows or rows % n_seq != 0:
+        raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+    on = target >= 0
+    if weight is not None:
+        on = on & (weight != 0)
+    lse = torch.logsumexp(logits.float(), -1)
+    pick = logits.float().gather(1, target.clamp(min=0)[:, None])[:, 0]
+    per = torch.where(on, pick - lse, torch.zeros_like(lse))
+    s = per.view(n_seq, -1).sum(-1)
+    if average_log_prob:
+        s = s / on.view(n_seq, -1).sum(-1)
+    _c(2)
+    return s, per, torch.where(on, lse, torch.zeros_like(lse))
+
+
+def logps_bwd(logits, target, n_seq, lse, grad_logps, weight=None, average_log_prob=False, out=None):
+    rows, V = logits.shape
+    on = target >= 0
+    if weight is not None:
+        on = on & (weight != 0)
+    g = grad_logps.repeat_interleave(rows // n_seq)
+    if average_log_prob:
+        g = g / on.view(n_seq, -1).sum(-1).repeat_interleave(rows // n_seq)
+    p = torch.exp(logits.float() - lse[:, None])
+    d = -g[:, None] * p
+    d[torch.arange(rows), target.clamp(min=0)] += g
+    d = d * on[:, None]
+    if out is None:
+        out = torch.empty(rows, V, dtype=torch.bfloat16)
+    out.copy_(d.to(torch.bfloat16))
+    _c()
+    return out
+
+
+def dpo_loss(policy_logps, ref_logps, beta, label_smoothing=0.0, loss_type="sigmoid", reference_free=False,
+             loss_scale=1.0, want_grad=True):
+    from oracle.restate import dpo_loss as oracle_loss  # test-only module: the oracle is allowed here
+    if loss_type not in LOSS_TYPES:
+        raise ValueError(f"Unknown loss type: {loss_type}. Should be one of ['sigmoid', 'hinge', 'ipo', 'kto_pair']")
+    n = policy_logps.numel() // 2
+    p = policy_logps.detach().float().clone().requires_grad_(True)
+    losses, cr, rr = oracle_loss(p[:n], p[n:], ref_logps[:n].float(), ref_logps[n:].float(), beta, label_smoothing, loss_type,
+                                 reference_free)
+    grad = None
+    if want_grad:
+        (losses.mean() * loss_scale).backward()
+        grad = p.grad
+    stats = torch.stack([losses.mean().detach(), (cr > rr).float().mean(), cr.mean(), rr.mean(), (cr - rr).mean(),
+                         torch.tensor(float(losses.numel()))])
+    _c()
+    return losses.detach(), cr, rr, stats, grad
+
+
+def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
+    xf = x.float()
+    r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    if rstd is not None:
+        rstd.copy_(r[:, 0])
+    if out is None:
+        out = torch.empty_like(x)
+    out.copy_((w.float() * (xf * r)).to(out.dtype))
+    _c()
+    return out
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dw, dres=None, out=None, dw_accumulate=False):
+    xf, g, wf = x.float(), dy.float(), w.float()
+    xh = xf * rstd[:, None]
+    dot = (wf * g * xh).mean(-1, keepdim=True)
+    dx = rstd[:, None] * (wf * g - xh * dot)
+    if dres is not None:
+        dx = dx + dres.float()
+    dwv = (g * xh).sum(0)
+    if dw_accumulate:
+        dwv = dwv + dw.float()
+    dw.copy_(dwv.to(dw.dtype))
+    if out is None:
+        out = torch.empty_like(x)
+    out.copy_(dx.to(out.dtype))
+    _c(2)
+    return out
+
+
+def layernorm_fwd(x, w, b, eps, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    out.copy_(F.layer_norm(x.float(), (x.shape[1],), w.float(), b.float(), eps).to(out.dtype))
+    _c()
+    return out
+
+
+def colsum(a, out, accumulate=False):
+    s = a.float().sum(0)
+    if accumulate:
+        s = s + out.float()
+    out.copy_(s.to(out.dtype))
+    _c(2)
+    return out
+
+
+def rope_(qkv, pos, cos_t, sin_t, n_rot_heads, head_dim, inverse=False):
+    T = qkv.shape[0]
+    x = qkv[:, :n_rot_heads * head_dim].float().view(T, n_rot_heads, head_dim)
+    c = torch.cat([cos_t, cos_t], -1)[pos.long()][:, None]
+    s = torch.cat([sin_t, sin_t], -1)[pos.long()][:, None]
+    if inverse:
+        s = -s
+    rot = torch.cat([-x[..., head_dim // 2:], x[..., :head_dim // 2]], -1)
+    qkv[:, :n_rot_heads * head_dim] = (x * c + rot * s).reshape(T, -1).to(qkv.dtype)
+    _c()
+    return qkv
+
+
+def swiglu_fwd(gate_up, out=None):
+    ff = gate_up.shape[1] // 2
+    y = F.silu(gate_up[:, :ff].float()) * gate_up[:, ff:].float()
+    if out is None:
+        out = torch.empty(y.shape, dtype=torch.bfloat16)
+    out.copy_(y.to(out.dtype))
+    _c()
+    return out
+
+
+def swiglu_bwd(gate_up, dact, out=None):
+    ff = gate_up.shape[1] // 2
+    g, u, d = gate_up[:, :ff].float(), gate_up[:, ff:].float(), dact.float()
+    s = torch.sigmoid(g)
+    res = torch.cat([d * u * s * (1 + g * (1 - s)), d * g * s], 1)
+    if out is None:
+        out = torch.empty_like(gate_up)
+    out.copy_(res.to(out.dtype))
+    _c()
+    return out
+
+
+def gelu_fwd(z, out=None):
+    if out is None:
+        out = torch.empty_like(z)
+    out.copy_(F.gelu(z.float()).to(out.dtype))
+    _c()
+    return out
+
+
+def gelu_bwd(z, dh, out=None):
+    x = z.float()
+    cdf = 0.5 * (1 + torch.erf(x / math.sqrt(2)))
+    pdf = torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    res = dh.float() * (cdf + x * pdf)
+    if out is None:
+        out = torch.empty_like(z)
+    out.copy_(res.to(out.dtype))
+    _c()
+    return out
+
+
+def clip_im2col(pixels, patch, out):
+    B = pixels.shape[0]
+    cols = F.unfold(pixels.float(), kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, 3 * patch * patch)
+    out[:, :cols.shape[1]] = cols.to(out.dtype)
+    _c()
+    return out
+
+
+def clip_cls_rows_(x, cls, pos0, batch, tokens_per_img):
+    x.view(batch, tokens_per_img, -1)[:, 0] = (cls.float() + pos0.float()).to(x.dtype)
+    _c()
+    return x
+
+
+def copy_rows(src, src_group_stride, src_row_stride, src_row0, dst, dst_group_stride, dst_row_stride, groups,
+              rows_per_group, cols):
+    s = torch.as_strided(src, (groups, rows_per_group, cols), (src_group_stride, src_row_stride, 1),
+                         src.storage_offset() + src_row0 * src_row_stride)
+    d = torch.as_strided(dst, (groups, rows_per_group, cols), (dst_group_stride, dst_row_stride, 1), dst.storage_offset())
+    d.copy_(s)
+    _c()
+    return dst
+
+
+def gather_rows(src, index, out):
+    idx = index.long()
+    out.copy_(torch.where((idx >= 0)[:, None], src[idx.clamp(min=0)], torch.zeros_like(out)))
+    _c()
+    return out
+
+
+def scatter_rows(src, index, out):
+    idx = index.long()
+    ok = idx >= 0
+    out[idx[ok]] = src[ok]
+    _c()
+    return out
+
+
+def zero_(t):
+    t.zero_()
+    return t
+
+
+class MergeIndex:
+    pass
+
+
+def llava_merge_index(input_ids, attention_mask, labels, n_patches, n_img_batch, imgs_per_seq, image_token, pad_token,
+                      ignore_index=-100):
+    INT_MIN = -(2 ** 31)
+    n_seq, L = input_ids.shape
+    P = n_patches
+    S = L + imgs_per_seq * (P - 1)
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, S, P, n_img_batch, imgs_per_seq
+    m.src_map = torch.full((n_seq * S,), INT_MIN, dtype=torch.int32)
+    m.labels = torch.full((n_seq, S), ignore_index, dtype=torch.int64)
+    m.mask = torch.zeros(n_seq, S, dtype=torch.int32)
+    m.pos = torch.ones(n_seq * S, dtype=torch.int32)
+    m.seqlens = torch.zeros(n_seq, dtype=torch.int32)
+    m.img_pos = torch.zeros(n_seq * imgs_per_seq * P, dtype=torch.int32)
+    m.row_of_text = torch.zeros(n_seq * (L - 1), dtype=torch.int32)
+    m.target = torch.full((n_seq * (L - 1),), -100, dtype=torch.int64)
+    m.status = torch.zeros(1, dtype=torch.int32)
+    for b in range(n_seq):
+        p = slot = 0
+        base = (b % n_img_batch) * imgs_per_seq
+        for j in range(L):
+            t = int(input_ids[b, j])
+            if t == image_token:
+                if slot < imgs_per_seq and p + P <= S:
+                    for i in range(P):
+                        m.src_map[b * S + p + i] = -1 - ((base + slot) * P + i)
+                        m.mask[b, p + i] = 1
+                        m.img_pos[(b * imgs_per_seq + slot) * P + i] = p + i
+                else:
+                    m.status[0] = 1
+                if j >= 1:
+                    m.row_of_text[b * (L - 1) + j - 1] = b * S + p - 1
+                p += P
+                slot += 1
+            else:
+                if p < S:
+                    m.src_map[b * S + p] = INT_MIN if t == pad_token else t
+                    m.mask[b, p] = int(attention_mask[b, j])
+                    m.labels[b, p] = int(labels[b, j])
+                else:
+                    m.status[0] = 1
+                if j >= 1:
+                    m.row_of_text[b * (L - 1) + j - 1] = b * S + p - 1
+                    lv = int(labels[b, j])
+                    m.target[b * (L - 1) + j - 1] = -100 if lv == ignore_index else lv
+                p += 1
+        if slot != imgs_per_seq or p != S:
+            m.status[0] = 2
+        run = 0
+        prefix = True
+        for q in range(S):
+            if m.mask[b, q]:
+                m.pos[b * S + q] = run
+                run += 1
+                if not prefix:
+                    m.status[0] = 3
+                m.seqlens[b] = q + 1
+            else:
+                prefix = False
+    _c()
+    return m
+
+
+def llava_merge_embed(m, embed_tokens, image_features, out):
+    INT_MIN = -(2 ** 31)
+    s = m.src_map.long()
+    out.zero_()
+    t = s >= 0
+    out[t] = embed_tokens[s[t]]
+    im = (s < 0) & (s != INT_MIN)
+    out[im] = image_features[-1 - s[im]]
+    _c()
+    return out
+
+
+def llava_merge_bwd(m, dx, dembed_f32, dimage_features):
+    INT_MIN = -(2 ** 31)
+    s = m.src_map.long()
+    t = s >= 0
+    dembed_f32.index_add_(0, s[t], dx[t].float())
+    im = (s < 0) & (s != INT_MIN)
+    acc = torch.zeros(dimage_features.shape, dtype=torch.float32)
+    acc.index_add_(0, -1 - s[im], dx[im].float())
+    dimage_features.copy_(acc.to(dimage_features.dtype))
+    _c(2)
+
+
+def _attn_ref(q, k, v, seqlens, B, S, H, KVH, dh, causal, scale):
+    qf = q.float().reshape(B, S, H, dh)
+    kf = k.float().reshape(B, S, KVH, dh).repeat_interleave(H // KVH, 2)
+    vf = v.float().reshape(B, S, KVH, dh).repeat_interleave(H // KVH, 2)
+    s = torch.einsum("bqhd,bkhd->bhqk", qf, kf) * scale
+    mask = torch.zeros(B, 1, S, S, dtype=torch.bool)
+    if causal:
+        mask = mask | torch.ones(S, S, dtype=torch.bool).triu(1)[None, None]
+    if seqlens is not None:
+        mask = mask | (torch.arange(S)[None, :] >= seqlens[:, None].long())[:, None, None, :]
+    s = s.masked_fill(mask, float("-inf"))
+    return qf, kf, vf, s
+
+
+def attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale):
+    qf, kf, vf, s = _attn_ref(q, k, v, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    p = torch.softmax(s, -1)
+    o = torch.einsum("bhqk,bkhd->bqhd", p, vf).reshape(B * S, H * head_dim)
+    out.copy_(o.to(out.dtype))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1))
+    _c()
+    return out
+
+
+def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
+    qq = q.float().reshape(B, S, H, head_dim).clone().requires_grad_(True)
+    kk = k.float().reshape(B, S, KVH, head_dim).clone().requires_grad_(True)
+    vv = v.float().reshape(B, S, KVH, head_dim).clone().requires_grad_(True)
+    kf = kk.repeat_interleave(H // KVH, 2)
+    vf = vv.repeat_interleave(H // KVH, 2)
+    s = torch.einsum("bqhd,bkhd->bhqk", qq, kf) * scale
+    mask = torch.zeros(B, 1, S, S, dtype=torch.bool)
+    if causal:
+        mask = mask | torch.ones(S, S, dtype=torch.bool).triu(1)[None, None]
+    if seqlens is not None:
+        mask = mask | (torch.arange(S)[None, :] >= seqlens[:, None].long())[:, None, None, :]
+    o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s.masked_fill(mask, float("-inf")), -1), vf)
+    (o * dout.float().reshape(B, S, H, head_dim)).sum().backward()
+    dq.copy_(qq.grad.reshape(B * S, -1).to(dq.dtype))
+    dk.copy_(kk.grad.reshape(B * S, -1).to(dk.dtype))
+    dv.copy_(vv.grad.reshape(B * S, -1).to(dv.dtype))
+    _c(3)
+
+
+def sumsq(x, out, workspace, accumulate=False):
+    s = x.float().pow(2).sum()
+    out[0] = out[0] + s if accumulate else s
+    _c(2)
+    return out
+
+
+def adamw_(param, grad, master, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+           grad_sumsq=None, max_grad_norm=0.0):
+    gs = grad_scale
+    if grad_sumsq is not None and max_grad_norm > 0:
+        norm = float(grad_sumsq[0].sqrt()) * grad_scale
+        gs *= min(1.0, max_grad_norm / (norm + 1e-6))
+    g = grad.float() * gs
+    exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2s = math.sqrt(1 - beta2 ** step)
+    master.mul_(1 - lr * weight_decay).addcdiv_(exp_avg, exp_avg_sq.sqrt() / bc2s + eps, value=-lr / bc1)
+    param.copy_(master.to(param.dtype))
+    _c()
+
+
+def cast_f32_to_bf16(src, dst, scale=1.0):
+    dst.copy_((src * scale).to(dst.dtype))
+    _c()
+    return dst
+
+
+def cast_bf16_to_f32(src, dst):
+    dst.copy_(src.float())
+    _c()
+    return dst

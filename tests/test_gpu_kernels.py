@@ -1,0 +1,309 @@
+"""GPU numerics of the individual sm_100a kernels vs plain PyTorch fp32 references of the same op.
+(bf16 storage, fp32 math: tolerances are bf16 rounding of the outputs.)"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ops
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def close(got, want, rtol=1.6e-2, atol=1e-3):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4g} (want absmax {want.abs().max().item():.4g}), " \
+                                     f"bad {(err > tol).sum().item()}/{err.numel()}"
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,ak,bk", [(128, 256, 64, 1, 1), (300, 320, 200, 1, 1), (257, 136, 72, 1, 1),
+                                         (256, 512, 256, 1, 0), (256, 512, 256, 0, 1), (200, 264, 136, 0, 0),
+                                         (576, 1024, 588, 1, 1), (1000, 32064, 128, 1, 1)])
+def test_gemm_variants(ops, M, N, K, ak, bk):
+    torch.manual_seed(M + N + K)
+    lda = (K if ak else M) + 8  # padded leading dimensions: views, not contiguous tensors
+    ldb = (K if bk else N) + 16
+    a_full = bf(torch.randn((M if ak else K), lda, device="cuda") * 0.5)
+    b_full = bf(torch.randn((N if bk else K), ldb, device="cuda") * 0.5)
+    a = a_full[:, :(K if ak else M)]
+    b = b_full[:, :(K if bk else N)]
+    A = a.float() if ak else a.float().t()
+    B = b.float() if bk else b.float().t()
+    want = A @ B.t()
+    got = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out_dtype=torch.float32)
+    close(got, want, rtol=1e-3, atol=1e-3)
+    got16 = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk))
+    close(got16, want, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(1)
+    M, N, K = 384, 768, 320
+    a, b = bf(torch.randn(M, K, device="cuda") * 0.3), bf(torch.randn(N, K, device="cuda") * 0.3)
+    bias, res = bf(torch.randn(N, device="cuda")), bf(torch.randn(M, N, device="cuda"))
+    base = a.float() @ b.float().t()
+    x = base + bias.float()
+    close(ops.gemm(a, b, bias=bias, out_dtype=torch.float32), x, 1e-3, 1e-3)
+    close(ops.gemm(a, b, bias=bias, act=ops.ACT_QUICK_GELU, out_dtype=torch.float32), x * torch.sigmoid(1.702 * x), 1e-3, 2e-3)
+    close(ops.gemm(a, b, bias=bias, act=ops.ACT_GELU_ERF, out_dtype=torch.float32), F.gelu(x), 1e-3, 2e-3)
+    close(ops.gemm(a, b, residual=res, out_dtype=torch.float32), base + res.float(), 1e-3, 1e-3)
+    # in-place residual (out aliases residual) and accumulate
+    r2 = res.clone()
+    ops.gemm(a, b, out=r2, residual=r2)
+    close(r2, base + res.float(), 1e-2, 2e-2)
+    acc = torch.ones(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(a, b, out=acc, accumulate=True)
+    close(acc, base + 1.0, 1e-3, 1e-3)
+    with pytest.raises(ValueError):
+        ops.gemm(a, bf(torch.randn(N, K + 8, device="cuda")))
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("rows,cols", [(37, 128), (1000, 4096), (5, 1024)])
+def test_rmsnorm_fwd_bwd(ops, rows, cols):
+    torch.manual_seed(rows)
+    x = bf(torch.randn(rows, cols, device="cuda"))
+    w = bf(1 + 0.1 * torch.randn(cols, device="cuda"))
+    dy = bf(torch.randn(rows, cols, device="cuda"))
+    dres = bf(torch.randn(rows, cols, device="cuda"))
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    y = wf * (xf * torch.rsqrt(var + 1e-5))
+    rstd = torch.empty(rows, dtype=torch.float32, device="cuda")
+    got = ops.rmsnorm_fwd(x, w, 1e-5, rstd=rstd)
+    close(got, y.detach())
+    close(rstd, torch.rsqrt(var + 1e-5).flatten().detach(), 1e-5, 1e-6)
+    y.backward(dy.float())
+    dw = torch.zeros(cols, dtype=torch.bfloat16, device="cuda")
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dw, dres=dres)
+    close(dx, xf.grad + dres.float(), 1.6e-2, 2e-2)
+    close(dw, wf.grad, 2e-2, 2e-2 * math.sqrt(rows))
+
+
+def test_layernorm_and_colsum(ops):
+    torch.manual_seed(0)
+    x = bf(torch.randn(300, 1024, device="cuda") * 2 + 0.5)
+    w, b = bf(1 + 0.1 * torch.randn(1024, device="cuda")), bf(0.1 * torch.randn(1024, device="cuda"))
+    close(ops.layernorm_fwd(x, w, b, 1e-5), F.layer_norm(x.float(), (1024,), w.float(), b.float(), 1e-5))
+    out = torch.zeros(1024, dtype=torch.bfloat16, device="cuda")
+    ops.colsum(x, out)
+    close(out, x.float().sum(0), 1e-2, 0.2)
+
+
+# ------------------------------------------------------------------ rope / swiglu / gelu
+def test_rope_roundtrip_and_reference(ops):
+    torch.manual_seed(0)
+    T, H, KV, dh = 50, 4, 2, 128
+    qkv = bf(torch.randn(T, (H + 2 * KV) * dh, device="cuda"))
+    pos = torch.randint(0, 2000, (T,), device="cuda", dtype=torch.int32)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))
+    fr = torch.arange(2048, dtype=torch.float32)[:, None] * inv[None]
+    cos_t, sin_t = fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+    x = qkv.float().view(T, H + 2 * KV, dh)
+    c = torch.cat([cos_t, cos_t], -1)[pos.long()][:, None]
+    s = torch.cat([sin_t, sin_t], -1)[pos.long()][:, None]
+    rot = torch.cat([-x[..., dh // 2:], x[..., :dh // 2]], -1)
+    want = x.clone()
+    want[:, :H + KV] = (x * c + rot * s)[:, :H + KV]
+    got = qkv.clone()
+    ops.rope_(got, pos, cos_t, sin_t, H + KV, dh)
+    close(got.view(T, H + 2 * KV, dh), want)
+    assert torch.equal(got[:, (H + KV) * dh:], qkv[:, (H + KV) * dh:])  # v untouched
+    ops.rope_(got, pos, cos_t, sin_t, H + KV, dh, inverse=True)
+    close(got, qkv, 2e-2, 2e-2)
+
+
+def test_swiglu_gelu(ops):
+    torch.manual_seed(0)
+    T, ff = 77, 256
+    gu = bf(torch.randn(T, 2 * ff, device="cuda") * 2)
+    d = bf(torch.randn(T, ff, device="cuda"))
+    g = gu[:, :ff].float().requires_grad_(True)
+    u = gu[:, ff:].float().requires_grad_(True)
+    y = F.silu(g) * u
+    close(ops.swiglu_fwd(gu), y.detach())
+    y.backward(d.float())
+    close(ops.swiglu_bwd(gu, d), torch.cat([g.grad, u.grad], 1), 1.6e-2, 1e-2)
+    z = bf(torch.randn(T, ff, device="cuda") * 2)
+    zf = z.float().requires_grad_(True)
+    h = F.gelu(zf)
+    close(ops.gelu_fwd(z), h.detach())
+    h.backward(d.float())
+    close(ops.gelu_bwd(z, d), zf.grad, 1.6e-2, 1e-2)
+
+
+# ------------------------------------------------------------------ attention
+def ref_attention(q, k, v, causal, seqlens, scale):
+    """q [B,S,H,dh], k/v [B,S,KV,dh] fp32 -> out, lse"""
+    B, S, H, dh = q.shape
+    KV = k.shape[2]
+    kk = k.repeat_interleave(H // KV, dim=2)
+    vv = v.repeat_interleave(H // KV, dim=2)
+    s = torch.einsum("bqhd,bkhd->bhqk", q, kk) * scale
+    mask = torch.zeros(B, 1, S, S, device=q.device, dtype=torch.bool)
+    if causal:
+        mask |= torch.ones(S, S, device=q.device, dtype=torch.bool).triu(1)[None, None]
+    if seqlens is not None:
+        mask |= (torch.arange(S, device=q.device)[None, :] >= seqlens[:, None].long())[:, None, None, :]
+    s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bkhd->bqhd", p, vv), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,S,H,KV,dh,causal,lens", [
+    (2, 577, 4, 4, 64, False, None),          # ViT shape
+    (2, 200, 2, 2, 128, True, [200, 131]),    # decoder MHA with right padding
+    (3, 130, 4, 2, 128, True, [130, 64, 1]),  # GQA, ragged
+    (1, 64, 2, 2, 64, True, None),
+])
+def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
+    torch.manual_seed(S + H)
+    dev = "cuda"
+    ld = (H + 2 * KV) * dh
+    qkv = bf(torch.randn(B * S, ld, device=dev))
+    seqlens = torch.tensor(lens, device=dev, dtype=torch.int32) if lens is not None else None
+    scale = 1.0 / math.sqrt(dh)
+    q = qkv[:, :H * dh]
+    k = qkv[:, H * dh:(H + KV) * dh]
+    v = qkv[:, (H + KV) * dh:]
+    out = torch.empty(B * S, H * dh, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+    ops.attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KV, dh, causal, scale)
+    qf = q.float().view(B, S, H, dh).clone().requires_grad_(True)
+    kf = k.float().view(B, S, KV, dh).clone().requires_grad_(True)
+    vf = v.float().view(B, S, KV, dh).clone().requires_grad_(True)
+    want, want_lse = ref_attention(qf, kf, vf, causal, seqlens, scale)
+    valid = torch.ones(B, S, dtype=torch.bool, device=dev)
+    if seqlens is not None:
+        valid = torch.arange(S, device=dev)[None] < seqlens[:, None].long()
+    got = out.view(B, S, H, dh).float()
+    close(got[valid], want.detach()[valid], 1.6e-2, 1e-2)
+    close(lse.permute(0, 2, 1)[valid], want_lse.detach().permute(0, 2, 1)[valid], 1e-3, 1e-3)
+    assert torch.isfinite(got).all()  # padded query rows stay finite
+    # backward: upstream gradient is zero on padded rows (as in the DPO step)
+    dout = bf(torch.randn(B * S, H * dh, device=dev)) * valid.view(-1, 1)
+    (want * dout.float().view(B, S, H, dh)).sum().backward()
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+    ops.attn_bwd(q, k, v, out, dout, lse, delta, dqkv[:, :H * dh], dqkv[:, H * dh:(H + KV) * dh], dqkv[:, (H + KV) * dh:],
+                 seqlens, B, S, H, KV, dh, causal, scale)
+    assert torch.isfinite(dqkv).all()
+    gq = dqkv[:, :H * dh].view(B, S, H, dh)
+    gk = dqkv[:, H * dh:(H + KV) * dh].view(B, S, KV, dh)
+    gv = dqkv[:, (H + KV) * dh:].view(B, S, KV, dh)
+    for name, g, w in (("dq", gq, qf.grad), ("dk", gk, kf.grad), ("dv", gv, vf.grad)):
+        rel = (g.float() - w).norm() / w.norm()
+        assert rel < 2e-2, f"{name} rel l2 err {rel.item():.4g}"
+        close(g, w, 3e-2, 3e-2)
+
+
+# ------------------------------------------------------------------ merge / movers
+def test_merge_index_embed_bwd(ops):
+    from oracle import restate as R
+    cfg = R.TINY
+    batch = R.make_batch(cfg, 3, 20, 6, seed=5)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    P, d = cfg.n_patches, cfg.hidden
+    torch.manual_seed(0)
+    emb = bf(torch.randn(cfg.vocab, d))
+    img = bf(torch.randn(3 * P, d))
+    img2 = torch.cat([img.view(3, P, d), img.view(3, P, d)], 0)  # the reference duplicates the images
+    fe, fm, fl, fp, fmap = R.merge_input_ids_with_image_features(cfg, img2.float(), F.embedding(ids, emb.float()), ids, am, lb)
+    m = ops.llava_merge_index(ids.cuda(), am.cuda(), lb.cuda(), P, 3, 1, cfg.image_token_index, cfg.pad_token_id)
+    assert int(m.status.item()) == 0
+    S = m.S
+    assert torch.equal(m.labels.cpu(), fl)
+    assert torch.equal(m.mask.cpu().long(), fm)
+    assert torch.equal(m.pos.cpu().view(6, S).long(), fp)
+    assert torch.equal(m.seqlens.cpu().long(), fm.sum(-1))
+    assert torch.equal((m.src_map.cpu().view(6, S) < 0) & (m.src_map.cpu().view(6, S) > -(2 ** 31)), fmap)
+    out = torch.empty(6 * S, d, dtype=torch.bfloat16, device="cuda")
+    ops.llava_merge_embed(m, emb.cuda(), img.cuda(), out)
+    assert torch.equal(out.cpu().float().view(6, S, d), fe)
+    # targets / rows: shifted-label semantics of get_batch_logps on the merged sequence
+    tgt = m.target.cpu().view(6, -1)
+    rows = m.row_of_text.cpu().view(6, -1)
+    shift = fl[:, 1:]
+    for b in range(6):
+        want_rows = (shift[b] != -100).nonzero().flatten() + b * S
+        got_rows = rows[b][tgt[b] >= 0]
+        assert torch.equal(got_rows.long(), want_rows)
+        assert torch.equal(tgt[b][tgt[b] >= 0], shift[b][shift[b] != -100])
+    # backward: embedding scatter-add and image-feature gradient (chosen + rejected share the image)
+    dx = bf(torch.randn(6 * S, d))
+    dembed = torch.zeros(cfg.vocab, d, dtype=torch.float32, device="cuda")
+    dimg = torch.empty(3 * P, d, dtype=torch.bfloat16, device="cuda")
+    ops.llava_merge_bwd(m, dx.cuda(), dembed, dimg)
+    e = emb.float().requires_grad_(True)
+    i2 = img.float().requires_grad_(True)
+    fe2, *_ = R.merge_input_ids_with_image_features(cfg, torch.cat([i2.view(3, P, d)] * 2, 0), F.embedding(ids, e), ids, am, lb)
+    (fe2.view(-1, d) * dx.float()).sum().backward()
+    close(dembed, e.grad, 1e-5, 1e-5)
+    close(dimg, i2.grad, 1e-2, 1e-2)
+    # status codes: two image tokens in one sequence -> ragged
+    bad = ids.clone()
+    bad[0, 3] = cfg.image_token_index
+    m2 = ops.llava_merge_index(bad.cuda(), am.cuda(), lb.cuda(), P, 3, 1, cfg.image_token_index, cfg.pad_token_id)
+    assert int(m2.status.item()) != 0
+
+
+def test_gather_scatter_copy_im2col(ops):
+    torch.manual_seed(0)
+    src = bf(torch.randn(50, 64, device="cuda"))
+    idx = torch.tensor([3, -1, 49, 0, 7], device="cuda", dtype=torch.int32)
+    out = torch.full((5, 64), 9.0, dtype=torch.bfloat16, device="cuda")
+    ops.gather_rows(src, idx, out)
+    want = src[idx.clamp(min=0).long()].clone()
+    want[1] = 0
+    assert torch.equal(out, want)
+    dst = torch.zeros(50, 64, dtype=torch.bfloat16, device="cuda")
+    ops.scatter_rows(out, idx, dst)
+    assert torch.equal(dst[3], src[3]) and torch.equal(dst[49], src[49]) and float(dst[1].abs().sum()) == 0
+    x = bf(torch.randn(3 * 5, 16, device="cuda"))
+    y = torch.empty(3 * 4, 16, dtype=torch.bfloat16, device="cuda")
+    ops.copy_rows(x, 5 * 16, 16, 1, y, 4 * 16, 16, 3, 4, 16)
+    assert torch.equal(y.view(3, 4, 16), x.view(3, 5, 16)[:, 1:])
+    pix = torch.randn(2, 3, 28, 28, device="cuda")
+    pat = torch.zeros(2 * 4, 592, dtype=torch.bfloat16, device="cuda")
+    ops.clip_im2col(pix, 14, pat)
+    want = F.unfold(pix, kernel_size=14, stride=14).transpose(1, 2).reshape(8, 588)
+    assert torch.equal(pat[:, :588], bf(want))
+
+
+# ------------------------------------------------------------------ optimizer
+def test_adamw_matches_torch(ops):
+    torch.manual_seed(0)
+    n = 4096 * 3
+    p0 = torch.randn(n, device="cuda") * 0.05
+    master = bf(p0).float()
+    param = bf(p0).clone()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ref_p = master.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+    ws, ss = torch.zeros(1024, device="cuda"), torch.zeros(1, device="cuda")
+    for step in range(1, 4):
+        g = bf(torch.randn(n, device="cuda") * (10.0 if step == 2 else 0.01))
+        ops.sumsq(g, ss, ws)
+        torch.testing.assert_close(ss[0], g.float().pow(2).sum(), rtol=1e-5, atol=1e-5)
+        ref_p.grad = g.float().clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        ops.adamw_(param, g, master, m, v, 1e-3, 0.9, 0.98, 1e-6, 0.01, step, grad_scale=1.0, grad_sumsq=ss, max_grad_norm=1.0)
+        torch.testing.assert_close(master, ref_p.detach(), rtol=2e-5, atol=1e-7)
+        assert torch.equal(param, bf(master))

@@ -1,0 +1,147 @@
+"""CPU tests of the host logic: the engine's orchestration (run over tests/mock_ops.py, a plain-PyTorch
+stand-in for the C ABI) against the oracle + golden vectors, the host-side DDPO mask, concatenated_inputs,
+and the 2-rank gloo data-parallel path.  No CUDA kernel runs here."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def cpu_pkg():
+    """vlrlhf_b200 with `ops` replaced by the PyTorch mock (CPU)."""
+    import vlrlhf_b200  # noqa: F401
+    from tests import mock_ops
+    saved = {k: sys.modules.get(k) for k in ("vlrlhf_b200.ops", "vlrlhf_b200.engine")}
+    sys.modules["vlrlhf_b200.ops"] = mock_ops
+    sys.modules.pop("vlrlhf_b200.engine", None)
+    engine = importlib.import_module("vlrlhf_b200.engine")
+    from vlrlhf_b200 import config, host
+    yield config, engine, host, mock_ops
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+def _setup(cpu_pkg, tag="g4_tiny", loss_type="sigmoid", with_optimizer=False):
+    config, engine, host, ops = cpu_pkg
+    name, rcfg, npairs, tl, pl = {"g4_tiny": ("TINY", R.TINY, 2, 24, 8), "g4_small": ("SMALL", R.SMALL, 2, 96, 24)}[tag]
+    d = np.load(os.path.join(G, tag + ".npz"))
+    eng = engine.LlavaDPOEngine(getattr(config, name), config.TrainConfig(loss_type=loss_type, learning_rate=1e-3),
+                                device="cpu", with_optimizer=with_optimizer)
+    eng.init_synthetic(int(d["seed"]))
+    batch = R.make_batch(rcfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True)
+    cb = host.concatenated_inputs(batch)
+    return eng, rcfg, d, batch, cb
+
+
+def test_config_mirrors_oracle_specs(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    for a, b in ((config.TINY, R.TINY), (config.SMALL, R.SMALL), (config.LLAVA15_7B, R.LLAVA15_7B)):
+        assert config.weight_specs(a) == R.weight_specs(b)
+        assert a.n_patches == b.n_patches and a.v_used_layers == b.v_used_layers
+    assert config.tensor_seed("x.y", 3) == R.tensor_seed("x.y", 3)
+
+
+def test_concatenated_inputs_matches_oracle(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    batch = R.make_batch(R.TINY, 3, 20, 6, seed=1)
+    batch["rejected_input_ids"] = batch["rejected_input_ids"][:, :17]  # ragged chosen/rejected lengths
+    batch["rejected_attention_mask"] = batch["rejected_attention_mask"][:, :17]
+    batch["rejected_labels"] = batch["rejected_labels"][:, :17]
+    a, b = host.concatenated_inputs(batch, padding_value=7), R.concatenated_inputs(batch, padding_value=7)
+    for k in ("concatenated_input_ids", "concatenated_attention_mask", "concatenated_labels"):
+        assert torch.equal(a[k], b[k])
+    assert torch.equal(a["concatenated_img_input_dict"]["pixel_values"], b["concatenated_img_input_dict"]["pixel_values"])
+    with pytest.raises(ValueError):
+        host.concatenated_inputs({**batch, "img_input_dict": {"x": 3}})
+
+
+def test_get_diff_ids_golden(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    d = np.load(os.path.join(G, "g3_ddpo.npz"))
+    for c in sorted({k[:-2] for k in d.files if k.endswith("_a")}):
+        ia, ib = host.get_diff_ids(d[c + "_a"].tolist(), d[c + "_b"].tolist(), 3)
+        assert ia == d[c + "_ia"].tolist() and ib == d[c + "_ib"].tolist(), c
+
+
+def test_ddpo_row_weights_equal_reference_mask(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    cfg = R.TINY
+    batch = R.make_batch(cfg, 3, 40, 8, seed=2, ddpo_like=True)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    w = host.ddpo_row_weights(ids, lb, cfg.image_token_index, cfg.n_patches)
+    # reference semantics: mask over the merged shifted labels (trainer.py:161-184)
+    emb = torch.zeros(cfg.vocab, 8)
+    img = torch.ones(6, cfg.n_patches, 8)
+    _, _, fl, _, _ = R.merge_input_ids_with_image_features(cfg, img, torch.nn.functional.embedding(ids, emb) + 1, ids, am, lb)
+    shift = fl[:, 1:].clone()
+    shift[shift == -100] = 0
+    mask = R.ddpo_shared_mask(shift)
+    m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, 3, 1, cfg.image_token_index, cfg.pad_token_id)
+    rows = m.row_of_text.view(6, -1).long() - (torch.arange(6) * m.S)[:, None]
+    want = torch.gather(mask, 1, rows.clamp(min=0)).to(torch.uint8)
+    tgt = m.target.view(6, -1)
+    assert torch.equal(w[tgt >= 0], want[tgt >= 0])
+    assert int(w.sum()) > 0
+
+
+@pytest.mark.parametrize("tag", ["g4_tiny", "g4_small"])
+def test_engine_forward_parity_cpu_mock(cpu_pkg, tag):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, tag)
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    pol = eng.hf_state("policy")
+    for k, v in wp.items():
+        if k in pol:
+            assert torch.equal(pol[k].float().reshape(v.shape), v), k
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    a = eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"])
+    out = eng.step(*a[:4], train=False)
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps"], rtol=1e-3)
+    np.testing.assert_allclose(out.ref_logps.numpy(), d["ref_logps"], rtol=1e-3)
+    # DDPO path
+    wt = host.ddpo_row_weights(ids, lb, rcfg.image_token_index, rcfg.n_patches)
+    out = eng.step(*a[:4], ddpo_weight=wt.reshape(-1), train=False)
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps_ddpo"], rtol=1e-3, atol=1e-2)
+
+
+def test_engine_backward_parity_cpu_mock(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    a = eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"])
+    eng.step(*a[:4], train=True)
+    got = {k: v.float() for k, v in eng.hf_state("grad").items()}
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in wp.items() if not k.startswith("vision_tower.")}
+    w = dict(wp)
+    w.update(leaves)
+    loss, _, _ = R.get_batch_loss_metrics(rcfg, w, wr, batch)
+    loss.backward()
+    for k, leaf in leaves.items():
+        g, want = got[k].reshape(leaf.shape), leaf.grad
+        rel = (g - want).norm().item() / max(want.norm().item(), 1e-12)
+        assert rel < 5e-2, f"{k}: rel {rel}"
+
+
+def test_engine_optimizer_cpu_mock(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny", with_optimizer=True)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    a = eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"])
+    l0 = float(eng.step(*a[:4], train=True).stats[0])
+    for _ in range(3):
+        l1 = float(eng.step(*a[:4], train=True).stats[0])
+    assert l1 < l0
+    assert torch.equal(eng.params, eng.master.to(torch.bfloat16))

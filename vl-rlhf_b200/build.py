@@ -1,0 +1,72 @@
+"""Build libvlb200.so (sm_100a only) in-tree with nvcc.  `python vl-rlhf_b200/build.py [--force]`.
+
+The .so stays in-tree (git-ignored, NOT gpurun-ignored) so it travels to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libvlb200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"] if os.environ.get("VLB_PTXAS_V") else \
+         ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
+
+
+def _headers_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "vlb200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src: str, force: bool) -> str:
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+    sp = os.path.join(CSRC, src)
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), _headers_mtime()):
+        return obj
+    cmd = [NVCC, *ARCH, *CFLAGS, "-c", sp, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if os.environ.get("VLB_PTXAS_V"):
+        sys.stderr.write(r.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force), srcs))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        rpaths = ["/usr/local/cuda/lib64"]
+        try:
+            import nvidia.cuda_runtime  # torch's bundled runtime
+            rpaths.insert(0, os.path.join(os.path.dirname(nvidia.cuda_runtime.__file__), "lib"))
+        except Exception:
+            pass
+        cmd = [NVCC, *ARCH, "-shared", "-cudart", "shared", "-o", LIB, *objs]
+        for rp in rpaths:
+            cmd += ["-Xlinker", "-rpath", "-Xlinker", rp]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[vlb200] built {LIB} from {len(objs)} objects")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,138 @@
+"""Model / training configuration of the hot path (LLaVA-1.5 family).
+
+Parameter names follow transformers-4.41 `LlavaForConditionalGeneration` (what the reference's
+`LlavaForRL` subclasses, models/Llava/__init__.py:35) so state dicts map 1:1.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from dataclasses import dataclass
+from typing import List, Tuple
+
+
+@dataclass
+class ModelConfig:
+    # vision tower (CLIP ViT)
+    image_size: int = 336
+    patch_size: int = 14
+    v_hidden: int = 1024
+    v_layers: int = 24
+    v_heads: int = 16
+    v_ff: int = 4096
+    v_eps: float = 1e-5
+    vision_feature_layer: int = -2
+    # decoder (Llama / Mistral style)
+    hidden: int = 4096
+    layers: int = 32
+    heads: int = 32
+    kv_heads: int = 32
+    ff: int = 11008
+    vocab: int = 32064
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    image_token_index: int = 32000
+    pad_token_id: int = 32001
+    ignore_index: int = -100
+    max_positions: int = 4096
+
+    @property
+    def n_patches(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
+
+    @property
+    def v_used_layers(self) -> int:
+        n = self.v_layers
+        return self.vision_feature_layer if self.vision_feature_layer >= 0 else n + 1 + self.vision_feature_layer
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+    @property
+    def v_head_dim(self) -> int:
+        return self.v_hidden // self.v_heads
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.heads + 2 * self.kv_heads) * self.head_dim
+
+    @property
+    def patch_k(self) -> int:
+        return 3 * self.patch_size * self.patch_size
+
+    @property
+    def patch_k_padded(self) -> int:
+        return (self.patch_k + 7) // 8 * 8
+
+
+LLAVA15_7B = ModelConfig()
+TINY = ModelConfig(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_heads=2, v_ff=256, hidden=128, layers=2,
+                   heads=2, kv_heads=2, ff=256, vocab=320, image_token_index=300, pad_token_id=301)
+# exercises the production tile shapes (head dims 64 / 128, several tiles per GEMM)
+SMALL = ModelConfig(image_size=112, patch_size=14, v_hidden=256, v_layers=3, v_heads=4, v_ff=512, hidden=512, layers=2,
+                    heads=4, kv_heads=4, ff=1024, vocab=2048, image_token_index=2000, pad_token_id=2001)
+
+
+@dataclass
+class TrainConfig:
+    """Hot-path knobs of the reference's TrainingArguments / VLDPOTrainer (dpo.py:16-86, base/trainer.py:38-67)."""
+    beta: float = 0.1
+    label_smoothing: float = 0.0
+    loss_type: str = "sigmoid"  # sigmoid | hinge | ipo | kto_pair | ddpo
+    reference_free: bool = False
+    label_pad_token_id: int = -100
+    padding_value: int = 0
+    # optimizer (scripts/dpo_llava.sh:35-42; HF Trainer defaults)
+    learning_rate: float = 1e-6
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.98
+    adam_eps: float = 1e-6
+    weight_decay: float = 0.0
+    max_grad_norm: float = 1.0
+
+
+def tensor_seed(name: str, base_seed: int) -> int:
+    return (zlib.crc32(name.encode()) ^ (base_seed * 0x9E3779B1)) & 0xFFFFFFFF
+
+
+def weight_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    """(HF-4.41 name, shape, uniform half-width, shift) -- the synthetic-init recipe (random-init weights of
+    the named architecture; there are no checkpoints on the box)."""
+    a = 0.02 * math.sqrt(3.0)
+    s: List[Tuple[str, Tuple[int, ...], float, float]] = []
+    vp = "vision_tower.vision_model."
+    s += [(vp + "embeddings.class_embedding", (cfg.v_hidden,), a, 0.0),
+          (vp + "embeddings.patch_embedding.weight", (cfg.v_hidden, 3, cfg.patch_size, cfg.patch_size), a, 0.0),
+          (vp + "embeddings.position_embedding.weight", (cfg.n_patches + 1, cfg.v_hidden), a, 0.0),
+          (vp + "pre_layrnorm.weight", (cfg.v_hidden,), 0.1, 1.0),
+          (vp + "pre_layrnorm.bias", (cfg.v_hidden,), 0.02, 0.0)]
+    for i in range(cfg.v_layers):
+        p = f"{vp}encoder.layers.{i}."
+        for ln in ("layer_norm1", "layer_norm2"):
+            s += [(p + ln + ".weight", (cfg.v_hidden,), 0.1, 1.0), (p + ln + ".bias", (cfg.v_hidden,), 0.02, 0.0)]
+        for pr in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s += [(p + f"self_attn.{pr}.weight", (cfg.v_hidden, cfg.v_hidden), a, 0.0),
+                  (p + f"self_attn.{pr}.bias", (cfg.v_hidden,), 0.02, 0.0)]
+        s += [(p + "mlp.fc1.weight", (cfg.v_ff, cfg.v_hidden), a, 0.0), (p + "mlp.fc1.bias", (cfg.v_ff,), 0.02, 0.0),
+              (p + "mlp.fc2.weight", (cfg.v_hidden, cfg.v_ff), a, 0.0), (p + "mlp.fc2.bias", (cfg.v_hidden,), 0.02, 0.0)]
+    s += [("multi_modal_projector.linear_1.weight", (cfg.hidden, cfg.v_hidden), a, 0.0),
+          ("multi_modal_projector.linear_1.bias", (cfg.hidden,), 0.02, 0.0),
+          ("multi_modal_projector.linear_2.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+          ("multi_modal_projector.linear_2.bias", (cfg.hidden,), 0.02, 0.0),
+          ("language_model.model.embed_tokens.weight", (cfg.vocab, cfg.hidden), a, 0.0)]
+    kv = cfg.kv_heads * cfg.head_dim
+    for i in range(cfg.layers):
+        p = f"language_model.model.layers.{i}."
+        s += [(p + "input_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
+              (p + "self_attn.q_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+              (p + "self_attn.k_proj.weight", (kv, cfg.hidden), a, 0.0),
+              (p + "self_attn.v_proj.weight", (kv, cfg.hidden), a, 0.0),
+              (p + "self_attn.o_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+              (p + "post_attention_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
+              (p + "mlp.gate_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),
+              (p + "mlp.up_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),
+              (p + "mlp.down_proj.weight", (cfg.hidden, cfg.ff), a, 0.0)]
+    s += [("language_model.model.norm.weight", (cfg.hidden,), 0.1, 1.0),
+          ("language_model.lm_head.weight", (cfg.vocab, cfg.hidden), 3.0 * a, 0.0)]
+    return s

@@ -1,0 +1,422 @@
+// bf16 GEMM on the 5th-gen tensor cores: TMA -> 128B-swizzled smem ring -> tcgen05.mma (TMEM
+// accumulators, double buffered) -> tcgen05.ld epilogue (bias / activation / residual / accumulate).
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2-5 = epilogue (TMEM lane quadrant = warp_idx % 4).  One CTA per SM, grid = #SMs.
+//
+// Replaces every nn.Linear the reference reaches through transformers (see include/vlb200.h).
+#include <mutex>
+#include <unordered_map>
+
+#include "ptx.cuh"
+
+namespace vlb {
+namespace gemm {
+
+using namespace ptx;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+struct Params {
+    int M, N, K;
+    int num_m_blocks, num_n_blocks, num_tiles, num_k_blocks;
+    void* D;
+    long long ldd;
+    int out_f32;
+    const __nv_bfloat16* bias;
+    int act;
+    const __nv_bfloat16* residual;
+    long long ldr;
+    int accumulate;
+};
+
+__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
+    // grouped rasterisation: 8 M-blocks share each B tile while it is hot in L2
+    constexpr int GROUP_M = 8;
+    const int tiles_per_group = GROUP_M * p.num_n_blocks;
+    const int group = tile / tiles_per_group;
+    const int first_m = group * GROUP_M;
+    const int group_m = min(p.num_m_blocks - first_m, GROUP_M);
+    const int in_group = tile - group * tiles_per_group;
+    m_blk = first_m + in_group % group_m;
+    n_blk = in_group / group_m;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == VLB200_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+    if (act == VLB200_ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+template <int BLOCK_N, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+    constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_TX_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
+    static_assert(TMEM_COLS == 512 || TMEM_COLS == 256 || TMEM_COLS == 128, "TMEM allocation must be a power of two");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // manual 1024-byte alignment (SWIZZLE_128B atoms are 1024 B)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_TILE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane_idx = threadIdx.x & 31;
+
+    if (warp_idx == 0 && lane_idx == 0) {
+        prefetch_tensormap(&tma_a);
+        prefetch_tensormap(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane_idx == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(p, tile, m_blk, n_blk);
+                const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX_BYTES);
+                    uint8_t* sa = smem_a + stage * A_TILE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_TILE_BYTES;
+                    const int k0 = kb * BLOCK_K;
+                    if constexpr (A_KMAJOR) {
+                        tma_load_2d(&tma_a, &full_bar[stage], sa, k0, m0);  // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 64; ++i)  // box {64 m, 64 k}
+                            tma_load_2d(&tma_a, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
+                    }
+                    if constexpr (B_KMAJOR) {
+                        tma_load_2d(&tma_b, &full_bar[stage], sb, k0, n0);  // box {64 k, BLOCK_N n}
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_N / 64; ++i)  // box {64 n, 64 k}
+                            tma_load_2d(&tma_b, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (lane_idx == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N, !A_KMAJOR, !B_KMAJOR);
+            // K-major: SBO = 8 rows * 128 B; advance 32 B per UMMA_K.  MN-major: LBO = chunk pitch,
+            // SBO = 8 k-rows * 128 B; advance 16 k-rows * 128 B per UMMA_K.
+            constexpr uint32_t LBO = BLOCK_K * 128;
+            constexpr uint32_t A_KADV = A_KMAJOR ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+            constexpr uint32_t B_KADV = B_KMAJOR ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 200 + acc);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 300 + stage);
+                    tcgen05_fence_after();
+                    const uint64_t a_desc =
+                        make_smem_desc_sw128(smem_u32(smem_a + stage * A_TILE_BYTES), 1024, A_KMAJOR ? 0 : LBO);
+                    const uint64_t b_desc =
+                        make_smem_desc_sw128(smem_u32(smem_b + stage * B_TILE_BYTES), 1024, B_KMAJOR ? 0 : LBO);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * A_KADV), b_desc + (uint64_t)(k * B_KADV), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps) =====================
+        const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may touch
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords(p, tile, m_blk, n_blk);
+            const int row = m_blk * BLOCK_M + quad * 32 + lane_idx;
+            const int n0 = n_blk * BLOCK_N;
+            mbar_wait(&tmem_full_bar[acc], acc_phase, 400 + acc);
+            tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr0 + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row < p.M && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j8 * 8);
+                                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f = unpack_bf16x2(bw[q]);
+                                    v[j8 * 8 + 2 * q] += f.x;
+                                    v[j8 * 8 + 2 * q + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.act != VLB200_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                    }
+                    if (p.residual != nullptr) {
+                        const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+                                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f = unpack_bf16x2(bw[q]);
+                                    v[j8 * 8 + 2 * q] += f.x;
+                                    v[j8 * 8 + 2 * q + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            if (col0 + j4 * 4 < p.N) {
+                                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                if (p.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(dp + j4 * 4);
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(dp + j4 * 4) = o;
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                if (p.accumulate) {
+                                    const uint4 b = *reinterpret_cast<const uint4*>(dp + j8 * 8);
+                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f = unpack_bf16x2(bw[q]);
+                                        v[j8 * 8 + 2 * q] += f.x;
+                                        v[j8 * 8 + 2 * q + 1] += f.y;
+                                    }
+                                }
+                                uint4 o;
+                                o.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+                                o.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                                o.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+                                o.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                                *reinterpret_cast<uint4*>(dp + j8 * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane_idx == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: TMA descriptor cache + dispatch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t inner, outer, ld;
+    uint32_t box_inner, box_outer;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+               box_outer == o.box_outer;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 tensor map, 128B swizzle; inner = contiguous dimension
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    static std::mutex mu;
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return VLB200_OK; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return VLB200_ERR_CUDA; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+        return VLB200_ERR_CUDA;
+    }
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 65536) cache.clear();
+        cache[key] = m;
+    }
+    *out = m;
+    return VLB200_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+    constexpr int smem_bytes = STAGES * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 1024;
+    auto kern = gemm_bf16_kernel<BLOCK_N, STAGES, A_KMAJOR, B_KMAJOR>;
+    static bool configured = false;
+    if (!configured) {
+        VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
+                          cudaStream_t s) {
+    if (ak && bk) return launch<BLOCK_N, STAGES, true, true>(ta, tb, p, s);
+    if (ak && !bk) return launch<BLOCK_N, STAGES, true, false>(ta, tb, p, s);
+    if (!ak && bk) return launch<BLOCK_N, STAGES, false, true>(ta, tb, p, s);
+    return launch<BLOCK_N, STAGES, false, false>(ta, tb, p, s);
+}
+
+}  // namespace gemm
+}  // namespace vlb
+
+extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D,
+                                int ldd, int out_dtype, int M, int N, int K, const void* bias, int act,
+                                const void* residual, int ldr, int accumulate, void* stream) {
+    using namespace vlb;
+    using namespace vlb::gemm;
+    VLB_REQUIRE(A && B && D, "gemm: null pointer");
+    VLB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    VLB_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+    VLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%d / ldb=%d must be multiples of 8 elements (TMA 16 B strides)",
+                lda, ldb);
+    VLB_REQUIRE(ldd % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "gemm: ldd/ldr must be multiples of 8");
+    VLB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+                "gemm: pointers must be 16-byte aligned");
+    VLB_REQUIRE(out_dtype == VLB200_BF16 || out_dtype == VLB200_F32, "gemm: bad out_dtype %d", out_dtype);
+    VLB_REQUIRE(a_kmajor ? lda >= K : lda >= M, "gemm: lda too small");
+    VLB_REQUIRE(b_kmajor ? ldb >= K : ldb >= N, "gemm: ldb too small");
+    const bool big_n = N > 128;
+    const int BN = big_n ? 256 : 128;
+
+    CUtensorMap ta, tb;
+    int rc;
+    if (a_kmajor) rc = get_tensor_map(A, K, M, lda, BLOCK_K, BLOCK_M, &ta);
+    else rc = get_tensor_map(A, M, K, lda, 64, BLOCK_K, &ta);
+    if (rc) return rc;
+    if (b_kmajor) rc = get_tensor_map(B, K, N, ldb, BLOCK_K, BN, &tb);
+    else rc = get_tensor_map(B, N, K, ldb, 64, BLOCK_K, &tb);
+    if (rc) return rc;
+
+    Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_blocks = (N + BN - 1) / BN;
+    p.num_tiles = p.num_m_blocks * p.num_n_blocks;
+    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.D = D; p.ldd = ldd; p.out_f32 = out_dtype == VLB200_F32;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.act = act;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    p.ldr = ldr;
+    p.accumulate = accumulate;
+    cudaStream_t s = as_stream(stream);
+    if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
+    return dispatch_major<128, 6>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
+}

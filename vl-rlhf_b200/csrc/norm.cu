@@ -1,0 +1,295 @@
+// RMSNorm (Llama, modeling_llama.py:53-67) forward/backward and LayerNorm (CLIP, modeling_clip.py) forward.
+// HBM-bound row kernels: 16-byte loads, fp32 statistics, one CTA (128 threads) per row in forward;
+// backward is a persistent grid that also produces the weight gradient (two-stage, deterministic).
+#include "common.cuh"
+
+namespace vlb {
+
+constexpr int NORM_THREADS = 128;
+constexpr int NORM_MAX_VEC = 8;  // supports cols <= 128 * 8 * 8 = 8192
+
+__device__ __forceinline__ float block_sum_128(float v, float* sm) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float t = sm[0] + sm[1] + sm[2] + sm[3];
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = unpack_bf16x2(w[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// y = w * (x * rsqrt(mean(x^2) + eps))            (fp32 math, one rounding at the end)
+__global__ void __launch_bounds__(NORM_THREADS)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                   __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ rstd_out, int cols, float eps) {
+    __shared__ float sm[4];
+    const int row = blockIdx.x;
+    const int nvec = cols >> 3;
+    const __nv_bfloat16* xr = x + (size_t)row * ldx;
+    uint4 xv[NORM_MAX_VEC];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+            xv[k] = *reinterpret_cast<const uint4*>(xr + (size_t)i * 8);
+            float f[8];
+            unpack8(xv[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+        }
+    }
+    ss = block_sum_128(ss, sm);
+    const float rstd = rsqrtf(ss / (float)cols + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+    __nv_bfloat16* yr = y + (size_t)row * ldy;
+#pragma unroll
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+            float f[8], g[8];
+            unpack8(xv[k], f);
+            unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = g[j] * (f[j] * rstd);
+            *reinterpret_cast<uint4*>(yr + (size_t)i * 8) = pack8(f);
+        }
+    }
+}
+
+// dx = rstd * (w*dy - xhat * mean(w*dy*xhat)) (+ dres);   dw_partial[cta] += dy * xhat
+template <int VPT>
+__global__ void __launch_bounds__(NORM_THREADS)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
+                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial,
+                   int rows, int cols) {
+    __shared__ float sm[4];
+    const int nvec = cols >> 3;
+    float dw[VPT][8];
+    float wv[VPT][8];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
+        if (i < nvec) unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), wv[k]);
+    }
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float rstd = rstd_in[row];
+        const size_t off = (size_t)row * cols;
+        uint4 xv[VPT], gv[VPT];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int i = threadIdx.x + k * NORM_THREADS;
+            if (i < nvec) {
+                xv[k] = *reinterpret_cast<const uint4*>(x + off + (size_t)i * 8);
+                gv[k] = *reinterpret_cast<const uint4*>(dy + off + (size_t)i * 8);
+                float xf[8], gf[8];
+                unpack8(xv[k], xf);
+                unpack8(gv[k], gf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = xf[j] * rstd;
+                    dot += wv[k][j] * gf[j] * xh;
+                    dw[k][j] += gf[j] * xh;
+                }
+            }
+        }
+        dot = block_sum_128(dot, sm) / (float)cols;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int i = threadIdx.x + k * NORM_THREADS;
+            if (i < nvec) {
+                float xf[8], gf[8], o[8];
+                unpack8(xv[k], xf);
+                unpack8(gv[k], gf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (wv[k][j] * gf[j] - xf[j] * rstd * dot);
+                if (dres) {
+                    float rf[8];
+                    unpack8(*reinterpret_cast<const uint4*>(dres + off + (size_t)i * 8), rf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += rf[j];
+                }
+                *reinterpret_cast<uint4*>(dx + off + (size_t)i * 8) = pack8(o);
+            }
+        }
+    }
+    float* out = dw_partial + (size_t)blockIdx.x * cols;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[(size_t)i * 8 + j] = dw[k][j];
+        }
+    }
+}
+
+// out[c] (bf16) (+)= sum_p partial[p, c]
+__global__ void colsum_partials_kernel(const float* __restrict__ partial, int nparts, int cols,
+                                       __nv_bfloat16* __restrict__ out, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * cols + c];
+    if (accumulate) s += __bfloat162float(out[c]);
+    out[c] = __float2bfloat16(s);
+}
+
+// column sums of a bf16 matrix (bias gradients): partial[cta, c] = sum over the CTA's rows
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const __nv_bfloat16* __restrict__ a, long long lda, int rows, int cols, float* __restrict__ partial) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) s += __bfloat162float(a[(size_t)r * lda + c]);
+    partial[(size_t)blockIdx.x * cols + c] = s;
+}
+
+// LayerNorm forward (CLIP): y = (x - mean) * rsqrt(var + eps) * w + b
+__global__ void __launch_bounds__(NORM_THREADS)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+                     const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long ldy, int cols,
+                     float eps) {
+    __shared__ float sm[4];
+    const int row = blockIdx.x;
+    const int nvec = cols >> 3;
+    const __nv_bfloat16* xr = x + (size_t)row * ldx;
+    uint4 xv[NORM_MAX_VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+            xv[k] = *reinterpret_cast<const uint4*>(xr + (size_t)i * 8);
+            float f[8];
+            unpack8(xv[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[j];
+        }
+    }
+    const float mean = block_sum_128(s, sm) / (float)cols;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+            float f[8];
+            unpack8(xv[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; v += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(block_sum_128(v, sm) / (float)cols + eps);
+    __nv_bfloat16* yr = y + (size_t)row * ldy;
+#pragma unroll
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+        const int i = threadIdx.x + k * NORM_THREADS;
+        if (i < nvec) {
+            float f[8], g[8], h[8];
+            unpack8(xv[k], f);
+            unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), g);
+            unpack8(*reinterpret_cast<const uint4*>(b + (size_t)i * 8), h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[j] + h[j];
+            *reinterpret_cast<uint4*>(yr + (size_t)i * 8) = pack8(f);
+        }
+    }
+}
+
+}  // namespace vlb
+
+using namespace vlb;
+
+static int check_cols(int cols, const char* who) {
+    VLB_REQUIRE(cols > 0 && cols % 8 == 0 && cols <= NORM_THREADS * NORM_MAX_VEC * 8, "%s: cols=%d must be a multiple of 8 and <= %d",
+                who, cols, NORM_THREADS * NORM_MAX_VEC * 8);
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int rows,
+                                  int cols, float eps, void* stream) {
+    VLB_REQUIRE(x && w && y, "rmsnorm_fwd: null pointer");
+    if (int rc = check_cols(cols, "rmsnorm_fwd")) return rc;
+    VLB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "rmsnorm_fwd: row strides must be multiples of 8");
+    if (rows <= 0) return VLB200_OK;
+    rmsnorm_fwd_kernel<<<rows, NORM_THREADS, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
+                                                                    (__nv_bfloat16*)y, ldy, rstd, cols, eps);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_norm_bwd_workspace_floats(int cols) { return 2 * num_sms() * cols; }
+
+extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+                                  void* dx, void* dw, int dw_accumulate, float* workspace, int rows, int cols,
+                                  void* stream) {
+    VLB_REQUIRE(dy && x && w && rstd && dx && dw && workspace, "rmsnorm_bwd: null pointer");
+    if (int rc = check_cols(cols, "rmsnorm_bwd")) return rc;
+    if (rows <= 0) return VLB200_OK;
+    const int grid = rows < 2 * num_sms() ? rows : 2 * num_sms();
+    cudaStream_t s = as_stream(stream);
+    const int vpt = ((cols >> 3) + NORM_THREADS - 1) / NORM_THREADS;
+#define VLB_RMS_BWD(V)                                                                                         \
+    rmsnorm_bwd_kernel<V><<<grid, NORM_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,     \
+                                                        (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres, \
+                                                        (__nv_bfloat16*)dx, workspace, rows, cols)
+    if (vpt <= 1) VLB_RMS_BWD(1);
+    else if (vpt <= 2) VLB_RMS_BWD(2);
+    else if (vpt <= 4) VLB_RMS_BWD(4);
+    else VLB_RMS_BWD(8);
+#undef VLB_RMS_BWD
+    VLB_LAUNCH_CHECK();
+    colsum_partials_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, grid, cols, (__nv_bfloat16*)dw, dw_accumulate);
+    count_launch(2);
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, void* out, int accumulate, float* workspace,
+                             void* stream) {
+    VLB_REQUIRE(a && out && workspace, "colsum: null pointer");
+    VLB_REQUIRE(cols <= NORM_THREADS * NORM_MAX_VEC * 8 * 4, "colsum: cols too large for the workspace contract");
+    if (rows <= 0 || cols <= 0) return VLB200_OK;
+    const int gx = rows < 2 * num_sms() ? rows : 2 * num_sms();
+    dim3 grid(gx, (cols + 255) / 256);
+    cudaStream_t s = as_stream(stream);
+    colsum_rows_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, lda, rows, cols, workspace);
+    VLB_LAUNCH_CHECK();
+    colsum_partials_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, gx, cols, (__nv_bfloat16*)out, accumulate);
+    count_launch(2);
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                                    int rows, int cols, float eps, void* stream) {
+    VLB_REQUIRE(x && w && b && y, "layernorm_fwd: null pointer");
+    if (int rc = check_cols(cols, "layernorm_fwd")) return rc;
+    if (rows <= 0) return VLB200_OK;
+    layernorm_fwd_kernel<<<rows, NORM_THREADS, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ldx,
+                                                                      (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,
+                                                                      (__nv_bfloat16*)y, ldy, cols, eps);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}

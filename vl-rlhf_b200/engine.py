@@ -1,0 +1,479 @@
+"""The B200-native DPO step for the LLaVA-1.5 family.
+
+Replaces, behind the reference's own interfaces (see plugin.py):
+  * `LlavaForRL.forward` incl. `_merge_input_ids_with_image_features`   (models/Llava/__init__.py:36-271)
+  * `VLDPOTrainer.concatenated_forward / get_batch_logps / dpo_loss`      (base/trainer.py:148-301)
+  * trl `DPOTrainer.get_batch_loss_metrics` (policy pass, no-grad reference pass, loss, reward stats)
+  * autograd backward + AdamW + the data-parallel gradient all-reduce (accelerate/DeepSpeed in the reference)
+
+Every FLOP/byte of device work is a libvlb200 kernel (ops.py -> C ABI).  torch provides device memory,
+the CUDA stream and torch.distributed (NCCL) only.  Differences from the reference that do not change
+results: the frozen vision tower runs once per pair (the reference runs it 4x on identical pixels), the
+full-vocab logits are computed only for rows that can carry a label, the discarded CE loss
+(Llava/__init__.py:245-257) is not computed, and there is no per-step empty_cache()/gc (trainer.py:303-308).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .config import ModelConfig, TrainConfig, tensor_seed, weight_specs
+
+ALIGN = 128  # elements (256 B): keeps every tensor TMA/16-byte aligned inside the flat arenas
+
+
+class Arena:
+    """Flat bf16 buffer with named row-major tensors carved out of it."""
+
+    def __init__(self):
+        self.shapes: Dict[str, Tuple[int, ...]] = {}
+        self.offsets: Dict[str, int] = {}
+        self.size = 0
+        self.flat: Optional[torch.Tensor] = None
+
+    def add(self, name: str, shape: Tuple[int, ...]):
+        assert name not in self.shapes
+        n = 1
+        for s in shape:
+            n *= s
+        self.shapes[name] = shape
+        self.offsets[name] = self.size
+        self.size += (n + ALIGN - 1) // ALIGN * ALIGN
+
+    def allocate(self, device, dtype=torch.bfloat16):
+        self.flat = torch.zeros(self.size, dtype=dtype, device=device)
+        return self
+
+    def view_of(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        shape = self.shapes[name]
+        n = 1
+        for s in shape:
+            n *= s
+        off = self.offsets[name]
+        return flat[off:off + n].view(shape)
+
+    def __getitem__(self, name: str) -> torch.Tensor:
+        return self.view_of(self.flat, name)
+
+
+class Weights:
+    """Name -> tensor view for one copy of the model (policy, reference) in engine layout."""
+
+    def __init__(self, arena: Arena, flat: torch.Tensor):
+        self.t = {n: arena.view_of(flat, n) for n in arena.shapes}
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+
+def _trainable_layout(cfg: ModelConfig) -> Arena:
+    a = Arena()
+    d = cfg.hidden
+    a.add("proj.w1", (d, cfg.v_hidden)); a.add("proj.b1", (d,)); a.add("proj.w2", (d, d)); a.add("proj.b2", (d,))
+    a.add("embed", (cfg.vocab, d))
+    for i in range(cfg.layers):
+        a.add(f"L{i}.ln1", (d,)); a.add(f"L{i}.wqkv", (cfg.qkv_dim, d)); a.add(f"L{i}.wo", (d, cfg.heads * cfg.head_dim))
+        a.add(f"L{i}.ln2", (d,)); a.add(f"L{i}.wgu", (2 * cfg.ff, d)); a.add(f"L{i}.wd", (d, cfg.ff))
+    a.add("norm", (d,)); a.add("lm_head", (cfg.vocab, d))
+    return a
+
+
+def _vision_layout(cfg: ModelConfig) -> Arena:
+    a = Arena()
+    dv = cfg.v_hidden
+    a.add("v.cls", (dv,)); a.add("v.patch", (dv, cfg.patch_k_padded)); a.add("v.pos", (cfg.n_patches + 1, dv))
+    a.add("v.pre.w", (dv,)); a.add("v.pre.b", (dv,))
+    for i in range(cfg.v_used_layers):
+        a.add(f"v{i}.ln1.w", (dv,)); a.add(f"v{i}.ln1.b", (dv,)); a.add(f"v{i}.wqkv", (3 * dv, dv)); a.add(f"v{i}.bqkv", (3 * dv,))
+        a.add(f"v{i}.wo", (dv, dv)); a.add(f"v{i}.bo", (dv,)); a.add(f"v{i}.ln2.w", (dv,)); a.add(f"v{i}.ln2.b", (dv,))
+        a.add(f"v{i}.w1", (cfg.v_ff, dv)); a.add(f"v{i}.b1", (cfg.v_ff,)); a.add(f"v{i}.w2", (dv, cfg.v_ff)); a.add(f"v{i}.b2", (dv,))
+    return a
+
+
+def hf_views(cfg: ModelConfig, w: Dict[str, torch.Tensor], vision: Optional[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """HF-4.41-named views into the engine's (fused) storage: q/k/v_proj and gate/up_proj are row slices."""
+    out: Dict[str, torch.Tensor] = {}
+    hd = cfg.heads * cfg.head_dim
+    kvd = cfg.kv_heads * cfg.head_dim
+    out["multi_modal_projector.linear_1.weight"] = w["proj.w1"]; out["multi_modal_projector.linear_1.bias"] = w["proj.b1"]
+    out["multi_modal_projector.linear_2.weight"] = w["proj.w2"]; out["multi_modal_projector.linear_2.bias"] = w["proj.b2"]
+    out["language_model.model.embed_tokens.weight"] = w["embed"]
+    for i in range(cfg.layers):
+        p = f"language_model.model.layers.{i}."
+        qkv, gu = w[f"L{i}.wqkv"], w[f"L{i}.wgu"]
+        out[p + "input_layernorm.weight"] = w[f"L{i}.ln1"]
+        out[p + "self_attn.q_proj.weight"] = qkv[:hd]
+        out[p + "self_attn.k_proj.weight"] = qkv[hd:hd + kvd]
+        out[p + "self_attn.v_proj.weight"] = qkv[hd + kvd:]
+        out[p + "self_attn.o_proj.weight"] = w[f"L{i}.wo"]
+        out[p + "post_attention_layernorm.weight"] = w[f"L{i}.ln2"]
+        out[p + "mlp.gate_proj.weight"] = gu[:cfg.ff]
+        out[p + "mlp.up_proj.weight"] = gu[cfg.ff:]
+        out[p + "mlp.down_proj.weight"] = w[f"L{i}.wd"]
+    out["language_model.model.norm.weight"] = w["norm"]
+    out["language_model.lm_head.weight"] = w["lm_head"]
+    if vision is not None:
+        v = vision
+        vp = "vision_tower.vision_model."
+        dv = cfg.v_hidden
+        out[vp + "embeddings.class_embedding"] = v["v.cls"]
+        out[vp + "embeddings.patch_embedding.weight"] = v["v.patch"][:, :cfg.patch_k]  # [dv, 3*p*p] strided view
+        out[vp + "embeddings.position_embedding.weight"] = v["v.pos"]
+        out[vp + "pre_layrnorm.weight"] = v["v.pre.w"]; out[vp + "pre_layrnorm.bias"] = v["v.pre.b"]
+        for i in range(cfg.v_used_layers):
+            p = f"{vp}encoder.layers.{i}."
+            out[p + "layer_norm1.weight"] = v[f"v{i}.ln1.w"]; out[p + "layer_norm1.bias"] = v[f"v{i}.ln1.b"]
+            out[p + "layer_norm2.weight"] = v[f"v{i}.ln2.w"]; out[p + "layer_norm2.bias"] = v[f"v{i}.ln2.b"]
+            for j, pr in enumerate(("q_proj", "k_proj", "v_proj")):
+                out[p + f"self_attn.{pr}.weight"] = v[f"v{i}.wqkv"][j * dv:(j + 1) * dv]
+                out[p + f"self_attn.{pr}.bias"] = v[f"v{i}.bqkv"][j * dv:(j + 1) * dv]
+            out[p + "self_attn.out_proj.weight"] = v[f"v{i}.wo"]; out[p + "self_attn.out_proj.bias"] = v[f"v{i}.bo"]
+            out[p + "mlp.fc1.weight"] = v[f"v{i}.w1"]; out[p + "mlp.fc1.bias"] = v[f"v{i}.b1"]
+            out[p + "mlp.fc2.weight"] = v[f"v{i}.w2"]; out[p + "mlp.fc2.bias"] = v[f"v{i}.b2"]
+    return out
+
+
+class StepOutput:
+    __slots__ = ("loss", "losses", "chosen_rewards", "rejected_rewards", "stats", "policy_logps", "ref_logps", "grad_norm")
+
+
+class LlavaDPOEngine:
+    def __init__(self, cfg: ModelConfig, train: Optional[TrainConfig] = None, device: str = "cuda",
+                 with_optimizer: bool = True, process_group=None):
+        self.cfg, self.tc = cfg, train or TrainConfig()
+        self.device = torch.device(device)
+        self.pg = process_group
+        self.layout = _trainable_layout(cfg)
+        self.vlayout = _vision_layout(cfg)
+        n = self.layout.size
+        self.params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)      # policy (projector + LLM)
+        self.ref_params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)  # frozen reference copy
+        self.grads = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.vparams = torch.zeros(self.vlayout.size, dtype=torch.bfloat16, device=self.device)  # frozen vision tower
+        self.policy = Weights(self.layout, self.params)
+        self.ref = Weights(self.layout, self.ref_params)
+        self.g = Weights(self.layout, self.grads)
+        self.vis = Weights(self.vlayout, self.vparams)
+        self.with_optimizer = with_optimizer
+        if with_optimizer:
+            self.master = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.dembed_f32 = torch.zeros(cfg.vocab, cfg.hidden, dtype=torch.float32, device=self.device)
+        self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
+        self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.opt_step = 0
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._build_rope_tables()
+
+    # ------------------------------------------------------------------ weights
+    def _build_rope_tables(self):
+        # identical arithmetic to LlamaRotaryEmbedding (modeling_llama.py:138-168): fp32 inv_freq, fp32 angles
+        cfg = self.cfg
+        dh = cfg.head_dim
+        inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))
+        t = torch.arange(cfg.max_positions, dtype=torch.float32)
+        freqs = t[:, None] * inv_freq[None, :]
+        self.rope_cos = freqs.cos().contiguous().to(self.device)
+        self.rope_sin = freqs.sin().contiguous().to(self.device)
+
+    def hf_state(self, which: str = "policy") -> Dict[str, torch.Tensor]:
+        w = {"policy": self.policy, "ref": self.ref, "grad": self.g}[which]
+        return hf_views(self.cfg, w.t, self.vis.t if which != "grad" else None)
+
+    def init_synthetic(self, seed: int, ref_alpha: float = 0.05):
+        """Seeded random-init weights of the architecture (bit-identical to oracle.restate.make_policy_and_ref)."""
+        cfg = self.cfg
+        pol, ref = self.hf_state("policy"), self.hf_state("ref")
+        tmp_cache: Dict[int, torch.Tensor] = {}
+
+        def tmp(n):
+            if n not in tmp_cache:
+                tmp_cache[n] = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            return tmp_cache[n]
+
+        for name, shape, scale, shift in weight_specs(cfg):
+            if name not in pol:
+                continue  # vision layers above vision_feature_layer are never used by the path
+            dst = pol[name]
+            n = dst.numel()
+            if dst.is_contiguous():
+                ops.init_uniform_(dst.view(-1), tensor_seed(name, seed), scale, shift)
+            else:  # padded patch-embedding weight
+                t = tmp(n)
+                ops.init_uniform_(t, tensor_seed(name, seed), scale, shift)
+                dst.copy_(t.view(dst.shape))
+            if name.startswith("vision_tower."):
+                continue
+            other = tmp(n)
+            ops.init_uniform_(other, tensor_seed(name, seed + 1), scale, shift)
+            ops.perturb_(ref[name].view(-1), dst.view(-1), other, ref_alpha, 1.0 if name.endswith("norm.weight") else 0.0)
+        if self.with_optimizer:
+            ops.cast_bf16_to_f32(self.params, self.master)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], which: str = "policy"):
+        dst = self.hf_state(which)
+        for k, v in sd.items():
+            if k in dst:
+                dst[k].copy_(v.to(device=self.device, dtype=torch.bfloat16).view(dst[k].shape))
+        if which == "policy" and self.with_optimizer:
+            ops.cast_bf16_to_f32(self.params, self.master)
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        t = self._bufs.get(name)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    # ------------------------------------------------------------------ vision tower (frozen, once per pair)
+    def vision_features(self, pixels: torch.Tensor) -> torch.Tensor:
+        cfg, v = self.cfg, self.vis
+        Bv = pixels.shape[0]
+        P, Sv, dv = cfg.n_patches, cfg.n_patches + 1, cfg.v_hidden
+        K, Kp = cfg.patch_k, cfg.patch_k_padded
+        patches = self.buf("v.patches", (Bv * P, Kp))
+        ops.clip_im2col(pixels, cfg.patch_size, patches)
+        x = self.buf("v.x", (Bv * Sv, dv))
+        wpatch = v["v.patch"][:, :K]
+        pos = v["v.pos"]
+        for b in range(Bv):  # conv-as-GEMM; epilogue adds the position embedding (K1)
+            ops.gemm(patches[b * P:(b + 1) * P, :K], wpatch, out=x[b * Sv + 1:(b + 1) * Sv], residual=pos[1:])
+        ops.clip_cls_rows_(x, v["v.cls"], pos[0], Bv, Sv)
+        h = self.buf("v.h", (Bv * Sv, dv))
+        ops.layernorm_fwd(x, v["v.pre.w"], v["v.pre.b"], cfg.v_eps, out=h)
+        x, h = h, x
+        qkv = self.buf("v.qkv", (Bv * Sv, 3 * dv))
+        att = self.buf("v.att", (Bv * Sv, dv))
+        f = self.buf("v.f", (Bv * Sv, cfg.v_ff))
+        scale = cfg.v_head_dim ** -0.5
+        for i in range(cfg.v_used_layers):
+            ops.layernorm_fwd(x, v[f"v{i}.ln1.w"], v[f"v{i}.ln1.b"], cfg.v_eps, out=h)
+            ops.gemm(h, v[f"v{i}.wqkv"], out=qkv, bias=v[f"v{i}.bqkv"])
+            ops.attn_fwd(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, None, None, Bv, Sv, cfg.v_heads, cfg.v_heads,
+                         cfg.v_head_dim, False, scale)
+            ops.gemm(att, v[f"v{i}.wo"], out=x, bias=v[f"v{i}.bo"], residual=x)
+            ops.layernorm_fwd(x, v[f"v{i}.ln2.w"], v[f"v{i}.ln2.b"], cfg.v_eps, out=h)
+            ops.gemm(h, v[f"v{i}.w1"], out=f, bias=v[f"v{i}.b1"], act=ops.ACT_QUICK_GELU)
+            ops.gemm(f, v[f"v{i}.w2"], out=x, bias=v[f"v{i}.b2"], residual=x)
+        feats = self.buf("v.feats", (Bv * P, dv))  # drop CLS (Llava/__init__.py:182-183)
+        ops.copy_rows(x, Sv * dv, dv, 1, feats, P * dv, dv, Bv, P, dv)
+        return feats
+
+    # ------------------------------------------------------------------ forward of one model copy
+    def _forward(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, tag: str, save: bool,
+                 ddpo_weight: Optional[torch.Tensor]):
+        cfg = self.cfg
+        d, T = cfg.hidden, m.n_seq * m.S
+        H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
+        hd, kvd = H * dh, KV * dh
+        nimg = feats.shape[0]
+        # projector (K6)
+        if save:
+            z = self.buf("p.z", (nimg, d)); ph = self.buf("p.h", (nimg, d))
+            ops.gemm(feats, w["proj.w1"], out=z, bias=w["proj.b1"])
+            ops.gelu_fwd(z, ph)
+        else:
+            ph = self.buf("p.h_ref", (nimg, d))
+            ops.gemm(feats, w["proj.w1"], out=ph, bias=w["proj.b1"], act=ops.ACT_GELU_ERF)
+        img = self.buf("p.img", (nimg, d))
+        ops.gemm(ph, w["proj.w2"], out=img, bias=w["proj.b2"])
+        # embed + merge (K7, K8)
+        L = cfg.layers
+        x = self.buf("x.0" if save else "s.x0", (T, d))
+        ops.llava_merge_embed(m, w["embed"], img, x)
+        h = self.buf("s.h", (T, d))
+        act = self.buf("s.act", (T, cfg.ff))
+        scale = 1.0 / math.sqrt(dh)
+        for i in range(L):
+            sfx = f".{i}" if save else ""
+            pre = "a" if save else "s"
+            rstd1 = self.buf(f"{pre}.rstd1{sfx}", (T,), torch.float32)
+            rstd2 = self.buf(f"{pre}.rstd2{sfx}", (T,), torch.float32)
+            qkv = self.buf(f"{pre}.qkv{sfx}", (T, cfg.qkv_dim))
+            att = self.buf(f"{pre}.att{sfx}", (T, hd))
+            lse = self.buf(f"{pre}.lse{sfx}", (m.n_seq, H, m.S), torch.float32)
+            xmid = self.buf(f"{pre}.xmid{sfx}", (T, d))
+            gu = self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff))
+            xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d))
+            ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=rstd1)
+            ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
+            ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
+            ops.attn_fwd(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, lse, m.seqlens, m.n_seq, m.S, H, KV, dh,
+                         True, scale)
+            ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
+            ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=rstd2)
+            ops.gemm(h, w[f"L{i}.wgu"], out=gu)
+            ops.swiglu_fwd(gu, act)
+            ops.gemm(act, w[f"L{i}.wd"], out=xn, residual=xmid)
+            x = xn
+        rstd_f = self.buf("a.rstd_f" if save else "s.rstd_f", (T,), torch.float32)
+        ops.rmsnorm_fwd(x, w["norm"], cfg.rms_eps, out=h, rstd=rstd_f)
+        # lm_head only on rows that can carry a label (K15) + fused log-prob gather (K16)
+        R = m.n_seq * (m.L - 1)
+        hsel = self.buf("a.hsel" if save else "s.hsel", (R, d))
+        ops.gather_rows(h, m.row_of_text, hsel)
+        logits = self.buf("a.logits" if save else "s.logits", (R, cfg.vocab), torch.float32)
+        ops.gemm(hsel, w["lm_head"], out=logits)
+        logps, per_tok, lse_v = ops.logps_fwd(logits, m.target, m.n_seq, weight=ddpo_weight)
+        if save:
+            self._saved = dict(m=m, feats=feats, x_last=x, lse_v=lse_v, ddpo_weight=ddpo_weight)
+        return logps
+
+    # ------------------------------------------------------------------ backward of the policy copy
+    def _backward(self, grad_logps: torch.Tensor):
+        cfg, w, g = self.cfg, self.policy, self.g
+        sv = self._saved
+        m: ops.MergeIndex = sv["m"]
+        d, T = cfg.hidden, m.n_seq * m.S
+        H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
+        hd, kvd = H * dh, KV * dh
+        R = m.n_seq * (m.L - 1)
+        logits = self._bufs["a.logits"]
+        hsel = self._bufs["a.hsel"]
+        dlogits = self.buf("b.dlogits", (R, cfg.vocab))
+        ops.logps_bwd(logits, m.target, m.n_seq, sv["lse_v"], grad_logps, weight=sv["ddpo_weight"], out=dlogits)
+        ops.gemm(dlogits, hsel, a_kmajor=False, b_kmajor=False, out=g["lm_head"])            # dW = dlogits^T hsel
+        dhsel = self.buf("b.dhsel", (R, d))
+        ops.gemm(dlogits, w["lm_head"], b_kmajor=False, out=dhsel)                           # dh = dlogits W
+        dxf = self.buf("b.dxf", (T, d))
+        ops.zero_(dxf)
+        ops.scatter_rows(dhsel, m.row_of_text, dxf)
+        dx = self.buf("b.dx0", (T, d))
+        dx2 = self.buf("b.dx1", (T, d))
+        ops.rmsnorm_bwd(dxf, sv["x_last"], w["norm"], self._bufs["a.rstd_f"], g["norm"], out=dx)
+        h = self.buf("s.h", (T, d))
+        act = self.buf("s.act", (T, cfg.ff))
+        dact = self.buf("b.dact", (T, cfg.ff))
+        dnorm = dxf  # reuse: [T, d] scratch for the gradients of the normed activations
+        dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
+        datt = self.buf("b.datt", (T, hd))
+        delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
+        scale = 1.0 / math.sqrt(dh)
+        for i in reversed(range(cfg.layers)):
+            x_in = self._bufs[f"x.{i}"]
+            xmid, gu, qkv, att = (self._bufs[f"a.{k}.{i}"] for k in ("xmid", "gu", "qkv", "att"))
+            rstd1, rstd2, lse = (self._bufs[f"a.{k}.{i}"] for k in ("rstd1", "rstd2", "lse"))
+            # ---- MLP
+            ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h)                         # recompute h2
+            ops.swiglu_fwd(gu, act)                                                           # recompute act
+            ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"])              # dWd = dx^T act
+            ops.gemm(dx, w[f"L{i}.wd"], b_kmajor=False, out=dact)                             # dact = dx Wd
+            ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
+            ops.gemm(gu, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wgu"])               # dWgu = dgu^T h2
+            ops.gemm(gu, w[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                           # dh2 = dgu Wgu
+            ops.rmsnorm_bwd(dnorm, xmid, w[f"L{i}.ln2"], rstd2, g[f"L{i}.ln2"], dres=dx, out=dx2)  # dxmid
+            # ---- attention
+            ops.gemm(dx2, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wo"])             # dWo = dxmid^T att
+            ops.gemm(dx2, w[f"L{i}.wo"], b_kmajor=False, out=datt)                            # datt = dxmid Wo
+            ops.attn_bwd(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
+                         dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh,
+                         True, scale)
+            ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
+            ops.rmsnorm_fwd(x_in, w[f"L{i}.ln1"], cfg.rms_eps, out=h)                         # recompute h1
+            ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"])            # dWqkv = dqkv^T h1
+            ops.gemm(dqkv, w[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)                        # dh1 = dqkv Wqkv
+            ops.rmsnorm_bwd(dnorm, x_in, w[f"L{i}.ln1"], rstd1, g[f"L{i}.ln1"], dres=dx2, out=dx)
+        # ---- embedding / merge / projector
+        feats = sv["feats"]
+        nimg = feats.shape[0]
+        dimg = self.buf("b.dimg", (nimg, d))
+        ops.zero_(self.dembed_f32)
+        ops.llava_merge_bwd(m, dx, self.dembed_f32, dimg)
+        ops.cast_f32_to_bf16(self.dembed_f32.view(-1), g["embed"].view(-1))
+        ph, z = self._bufs["p.h"], self._bufs["p.z"]
+        ops.gemm(dimg, ph, a_kmajor=False, b_kmajor=False, out=g["proj.w2"])
+        ops.colsum(dimg, g["proj.b2"])
+        dph = self.buf("b.dph", (nimg, d))
+        ops.gemm(dimg, w["proj.w2"], b_kmajor=False, out=dph)
+        ops.gelu_bwd(z, dph, out=dph)
+        ops.gemm(dph, feats, a_kmajor=False, b_kmajor=False, out=g["proj.w1"])
+        ops.colsum(dph, g["proj.b1"])
+
+    # ------------------------------------------------------------------ optimizer + data parallel
+    def allreduce_grads(self):
+        """ONE NCCL all-reduce over the flat bf16 gradient buffer (sum; the 1/world scale is folded into AdamW)."""
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                   and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def world_size(self) -> int:
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(self.pg)
+        return 1
+
+    def optimizer_step(self):
+        tc = self.tc
+        self.opt_step += 1
+        ops.sumsq(self.grads, self.grad_sumsq, self.sumsq_ws)
+        ops.adamw_(self.params, self.grads, self.master, self.exp_avg, self.exp_avg_sq, tc.learning_rate, tc.adam_beta1,
+                   tc.adam_beta2, tc.adam_eps, tc.weight_decay, self.opt_step, grad_scale=1.0 / self.world_size(),
+                   grad_sumsq=self.grad_sumsq, max_grad_norm=tc.max_grad_norm)
+
+    # ------------------------------------------------------------------ the step
+    def prepare_inputs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
+                       pixel_values: torch.Tensor, ddpo_weight: Optional[torch.Tensor] = None):
+        """Host -> device staging of one concatenated batch (the H2D copies of the step).  Inputs may be CPU
+        (pinned or not) or CUDA tensors.  pixel_values may be [B,...] or the reference's duplicated [2B,...]."""
+        dev = self.device
+        n_seq = input_ids.shape[0]
+        ids = input_ids.to(dev, non_blocking=True).contiguous()
+        am = attention_mask.to(dev, non_blocking=True).contiguous()
+        lb = labels.to(dev, non_blocking=True).contiguous()
+        if pixel_values.shape[0] == n_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
+            pixel_values = pixel_values[: n_seq // 2]
+        px = pixel_values.to(dev, non_blocking=True).contiguous()
+        if px.dtype not in (torch.float32, torch.bfloat16):
+            px = px.float()
+        wt = ddpo_weight.to(dev, non_blocking=True).reshape(-1).contiguous() if ddpo_weight is not None else None
+        return ids, am, lb, px, wt
+
+    def forward_logps(self, ids, am, lb, px, ddpo_weight=None, which: str = "policy", save: bool = False,
+                      feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None):
+        cfg = self.cfg
+        if m is None:
+            imgs_per_seq = 1
+            m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0], imgs_per_seq, cfg.image_token_index,
+                                      cfg.pad_token_id, cfg.ignore_index)
+        if feats is None:
+            feats = self.vision_features(px)
+        w = self.policy if which == "policy" else self.ref
+        return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
+
+    def step(self, ids, am, lb, px, ddpo_weight=None, train: bool = True) -> StepOutput:
+        """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
+        backward + gradient all-reduce + AdamW."""
+        tc = self.tc
+        pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, "policy", save=train)
+        ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, "ref", save=False, feats=feats, m=m)
+        losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
+                                                   1.0, want_grad=train)
+        out = StepOutput()
+        out.losses, out.chosen_rewards, out.rejected_rewards, out.stats = losses, cr, rr, stats
+        out.policy_logps, out.ref_logps = pol, ref
+        out.loss = stats[0:1]
+        out.grad_norm = None
+        if train:
+            self._backward(grad)
+            self.allreduce_grads()
+            if self.with_optimizer:
+                self.optimizer_step()
+                out.grad_norm = self.grad_sumsq
+        return out
+
+    def check_merge_status(self, m: "ops.MergeIndex"):
+        """Synchronising validity check mirroring the reference's ValueError (Llava/__init__.py:90-94)."""
+        st = int(m.status.item())
+        if st == 1 or st == 2:
+            raise ValueError("The input provided to the model are wrong. The number of image tokens does not match the "
+                             "number of images given to the model (every sequence must hold the same number of <image> "
+                             "tokens in this build).")
+        if st == 3:
+            raise ValueError("attention_mask must be a right-padded prefix mask (left padding is not supported yet)")

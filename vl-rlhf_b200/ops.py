@@ -1,0 +1,356 @@
+"""Tensor-level wrappers over the C ABI.  torch is only the memory/stream plumbing here: every
+function hands raw device pointers of CUDA tensors to libvlb200 on the current torch stream."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1, 2
+LOSS_TYPES = {"sigmoid": 0, "hinge": 1, "ipo": 2, "kto_pair": 3, "ddpo": 4}
+
+_L = _lib.load()  # raises ImportError when the extension is missing: no fallback
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "vlb200 ops take CUDA tensors only (there is no CPU path)"
+    return t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def _rowmajor_ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D view"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def launch_count() -> int:
+    return int(_L.vlb200_launch_count())
+
+
+def init_uniform_(t: torch.Tensor, seed: int, scale: float, shift: float = 0.0) -> torch.Tensor:
+    assert t.is_contiguous()
+    check(_L.vlb200_init_uniform(_ptr(t), _dt(t), t.numel(), seed & 0xFFFFFFFF, scale, shift, _stream()))
+    return t
+
+
+def perturb_(dst: torch.Tensor, base: torch.Tensor, other: torch.Tensor, alpha: float, shift: float) -> torch.Tensor:
+    assert dst.dtype == base.dtype == other.dtype == torch.bfloat16
+    assert dst.is_contiguous() and base.is_contiguous() and other.is_contiguous()
+    check(_L.vlb200_perturb_bf16(_ptr(dst), _ptr(base), _ptr(other), dst.numel(), alpha, shift, _stream()))
+    return dst
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
+         accumulate: bool = False) -> torch.Tensor:
+    """D[M,N] = epilogue(opA(a) @ opB(b)^T).
+
+    a: [M,K] if a_kmajor else [K,M];  b: [N,K] if b_kmajor (nn.Linear weight) else [K,N]."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
+    N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
+    if K != Kb:
+        raise ValueError(f"gemm: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N)
+    check(_L.vlb200_gemm_bf16(_ptr(a), _rowmajor_ld(a), int(a_kmajor), _ptr(b), _rowmajor_ld(b), int(b_kmajor),
+                              _ptr(out), _rowmajor_ld(out), _dt(out), M, N, K, _ptr(bias), act, _ptr(residual),
+                              _rowmajor_ld(residual) if residual is not None else 0, int(accumulate), _stream()))
+    return out
+
+
+def logps_fwd(logits: torch.Tensor, target: torch.Tensor, n_seq: int, weight: Optional[torch.Tensor] = None,
+              average_log_prob: bool = False):
+    """logits [rows, V] (bf16|f32); target [rows] int64 (<0 = skip).  -> (logps[n_seq], per_token[rows], lse[rows])"""
+    rows, V = logits.shape
+    if target.numel() != rows or rows % n_seq != 0:
+        raise ValueError("Logits (batch and sequence length dim) and labels must have the same shape.")
+    assert target.dtype == torch.int64 and target.is_contiguous()
+    if weight is not None:
+        assert weight.dtype == torch.uint8 and weight.is_contiguous() and weight.numel() == rows
+    per_token = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    logps = torch.empty(n_seq, dtype=torch.float32, device=logits.device)
+    check(_L.vlb200_logps_fwd(_ptr(logits), _dt(logits), _rowmajor_ld(logits), _ptr(target), _ptr(weight), rows,
+                              rows // n_seq, n_seq, V, int(average_log_prob), _ptr(per_token), _ptr(lse), _ptr(logps),
+                              _stream()))
+    return logps, per_token, lse
+
+
+def logps_bwd(logits: torch.Tensor, target: torch.Tensor, n_seq: int, lse: torch.Tensor, grad_logps: torch.Tensor,
+              weight: Optional[torch.Tensor] = None, average_log_prob: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, V = logits.shape
+    if out is None:
+        out = torch.empty(rows, V, dtype=torch.bfloat16, device=logits.device)
+    assert grad_logps.dtype == torch.float32 and grad_logps.numel() == n_seq
+    check(_L.vlb200_logps_bwd(_ptr(logits), _dt(logits), _rowmajor_ld(logits), _ptr(target), _ptr(weight), _ptr(lse),
+                              _ptr(grad_logps), rows, rows // n_seq, n_seq, V, int(average_log_prob), _ptr(out),
+                              _rowmajor_ld(out), _stream()))
+    return out
+
+
+def dpo_loss(policy_logps: torch.Tensor, ref_logps: torch.Tensor, beta: float, label_smoothing: float = 0.0,
+             loss_type: str = "sigmoid", reference_free: bool = False, loss_scale: float = 1.0, want_grad: bool = True):
+    """policy_logps/ref_logps: f32 [2*n_pairs] (chosen first).
+    -> (losses, chosen_rewards, rejected_rewards, stats[6], grad_policy_logps|None)"""
+    if loss_type not in LOSS_TYPES:
+        raise ValueError(f"Unknown loss type: {loss_type}. Should be one of ['sigmoid', 'hinge', 'ipo', 'kto_pair']")
+    n2 = policy_logps.numel()
+    assert n2 % 2 == 0 and ref_logps.numel() == n2
+    n = n2 // 2
+    dev = policy_logps.device
+    policy_logps = policy_logps.float().contiguous()
+    ref_logps = ref_logps.float().contiguous()
+    losses = torch.empty(2 * n if loss_type == "kto_pair" else n, dtype=torch.float32, device=dev)
+    cr = torch.empty(n, dtype=torch.float32, device=dev)
+    rr = torch.empty(n, dtype=torch.float32, device=dev)
+    stats = torch.empty(6, dtype=torch.float32, device=dev)
+    grad = torch.empty(n2, dtype=torch.float32, device=dev) if want_grad else None
+    check(_L.vlb200_dpo_loss(_ptr(policy_logps), _ptr(ref_logps), n, beta, label_smoothing, LOSS_TYPES[loss_type],
+                             int(reference_free), loss_scale, _ptr(losses), _ptr(cr), _ptr(rr), _ptr(stats), _ptr(grad),
+                             _stream()))
+    return losses, cr, rr, stats, grad
+
+
+# ------------------------------------------------------------------------------------------
+# norms / elementwise / movers
+# ------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _workspace(cols: int, device) -> torch.Tensor:
+    n = int(_L.vlb200_norm_bwd_workspace_floats(cols))
+    key = (str(device), n)
+    if key not in _ws_cache:
+        _ws_cache[key] = torch.empty(n, dtype=torch.float32, device=device)
+    return _ws_cache[key]
+
+
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None,
+                rstd: Optional[torch.Tensor] = None):
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L.vlb200_rmsnorm_fwd(_ptr(x), _rowmajor_ld(x), _ptr(w), _ptr(out), _rowmajor_ld(out), _ptr(rstd), rows, cols,
+                                eps, _stream()))
+    return out
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor, dw: torch.Tensor,
+                dres: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, dw_accumulate: bool = False):
+    rows, cols = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L.vlb200_rmsnorm_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(rstd), _ptr(dres), _ptr(out), _ptr(dw),
+                                int(dw_accumulate), _ptr(_workspace(cols, x.device)), rows, cols, _stream()))
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None):
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L.vlb200_layernorm_fwd(_ptr(x), _rowmajor_ld(x), _ptr(w), _ptr(b), _ptr(out), _rowmajor_ld(out), rows, cols,
+                                  eps, _stream()))
+    return out
+
+
+def colsum(a: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
+    rows, cols = a.shape
+    check(_L.vlb200_colsum(_ptr(a), _rowmajor_ld(a), rows, cols, _ptr(out), int(accumulate),
+                           _ptr(_workspace(max(cols, 8), a.device)), _stream()))
+    return out
+
+
+def rope_(qkv: torch.Tensor, pos: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, n_rot_heads: int, head_dim: int,
+          inverse: bool = False):
+    assert pos.dtype == torch.int32 and cos_t.dtype == torch.float32 and sin_t.dtype == torch.float32
+    check(_L.vlb200_rope(_ptr(qkv), _rowmajor_ld(qkv), _ptr(pos), _ptr(cos_t), _ptr(sin_t), qkv.shape[0], n_rot_heads,
+                         head_dim, int(inverse), _stream()))
+    return qkv
+
+
+def swiglu_fwd(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None):
+    rows, ff2 = gate_up.shape
+    ff = ff2 // 2
+    if out is None:
+        out = torch.empty(rows, ff, dtype=torch.bfloat16, device=gate_up.device)
+    check(_L.vlb200_swiglu_fwd(_ptr(gate_up), _rowmajor_ld(gate_up), _ptr(out), _rowmajor_ld(out), rows, ff, _stream()))
+    return out
+
+
+def swiglu_bwd(gate_up: torch.Tensor, dact: torch.Tensor, out: Optional[torch.Tensor] = None):
+    rows, ff2 = gate_up.shape
+    if out is None:
+        out = torch.empty_like(gate_up)
+    check(_L.vlb200_swiglu_bwd(_ptr(gate_up), _rowmajor_ld(gate_up), _ptr(dact), _rowmajor_ld(dact), _ptr(out),
+                               _rowmajor_ld(out), rows, ff2 // 2, _stream()))
+    return out
+
+
+def gelu_fwd(z: torch.Tensor, out: Optional[torch.Tensor] = None):
+    assert z.is_contiguous()
+    if out is None:
+        out = torch.empty_like(z)
+    check(_L.vlb200_gelu_fwd(_ptr(z), _ptr(out), z.numel(), _stream()))
+    return out
+
+
+def gelu_bwd(z: torch.Tensor, dh: torch.Tensor, out: Optional[torch.Tensor] = None):
+    assert z.is_contiguous() and dh.is_contiguous()
+    if out is None:
+        out = torch.empty_like(z)
+    check(_L.vlb200_gelu_bwd(_ptr(z), _ptr(dh), _ptr(out), z.numel(), _stream()))
+    return out
+
+
+def clip_im2col(pixels: torch.Tensor, patch: int, out: torch.Tensor):
+    B, C, H, W = pixels.shape
+    assert C == 3 and pixels.is_contiguous()
+    check(_L.vlb200_clip_im2col(_ptr(pixels), _dt(pixels), _ptr(out), _rowmajor_ld(out), B, H, W, patch, _stream()))
+    return out
+
+
+def clip_cls_rows_(x: torch.Tensor, cls: torch.Tensor, pos0: torch.Tensor, batch: int, tokens_per_img: int):
+    check(_L.vlb200_clip_cls_rows(_ptr(x), _ptr(cls), _ptr(pos0), batch, tokens_per_img, x.shape[1], _stream()))
+    return x
+
+
+def copy_rows(src: torch.Tensor, src_group_stride: int, src_row_stride: int, src_row0: int, dst: torch.Tensor,
+              dst_group_stride: int, dst_row_stride: int, groups: int, rows_per_group: int, cols: int):
+    check(_L.vlb200_copy_rows(_ptr(src), src_group_stride, src_row_stride, src_row0, _ptr(dst), dst_group_stride,
+                              dst_row_stride, groups, rows_per_group, cols, _stream()))
+    return dst
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor):
+    assert index.dtype == torch.int32
+    check(_L.vlb200_gather_rows(_ptr(src), _rowmajor_ld(src), _ptr(index), _ptr(out), _rowmajor_ld(out), index.numel(),
+                                src.shape[1], _stream()))
+    return out
+
+
+def scatter_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor):
+    assert index.dtype == torch.int32
+    check(_L.vlb200_scatter_rows(_ptr(src), _rowmajor_ld(src), _ptr(index), _ptr(out), _rowmajor_ld(out), index.numel(),
+                                 src.shape[1], _stream()))
+    return out
+
+
+def zero_(t: torch.Tensor):
+    assert t.is_contiguous()
+    check(_L.vlb200_memset_zero(_ptr(t), t.numel() * t.element_size(), _stream()))
+    return t
+
+
+# ------------------------------------------------------------------------------------------
+# LLaVA merge
+# ------------------------------------------------------------------------------------------
+class MergeIndex:
+    """Device-side result of the integer merge pass (Llava/__init__.py:36-109)."""
+    __slots__ = ("src_map", "labels", "mask", "pos", "seqlens", "img_pos", "row_of_text", "target", "status",
+                 "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq")
+
+
+def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_patches: int,
+                      n_img_batch: int, imgs_per_seq: int, image_token: int, pad_token: int, ignore_index: int = -100):
+    n_seq, L = input_ids.shape
+    S = L + imgs_per_seq * (n_patches - 1)
+    dev = input_ids.device
+    for t in (input_ids, attention_mask, labels):
+        assert t.dtype == torch.int64 and t.is_contiguous() and t.shape == (n_seq, L)
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, S, n_patches, n_img_batch, imgs_per_seq
+    m.src_map = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
+    m.labels = torch.empty(n_seq, S, dtype=torch.int64, device=dev)
+    m.mask = torch.empty(n_seq, S, dtype=torch.int32, device=dev)
+    m.pos = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
+    m.seqlens = torch.empty(n_seq, dtype=torch.int32, device=dev)
+    m.img_pos = torch.empty(n_seq * imgs_per_seq * n_patches, dtype=torch.int32, device=dev)
+    m.row_of_text = torch.empty(n_seq * (L - 1), dtype=torch.int32, device=dev)
+    m.target = torch.empty(n_seq * (L - 1), dtype=torch.int64, device=dev)
+    m.status = torch.empty(1, dtype=torch.int32, device=dev)
+    check(_L.vlb200_llava_merge_index(_ptr(input_ids), _ptr(attention_mask), _ptr(labels), n_seq, L, S, n_patches,
+                                      n_img_batch, imgs_per_seq, image_token, pad_token, ignore_index, _ptr(m.src_map),
+                                      _ptr(m.labels), _ptr(m.mask), _ptr(m.pos), _ptr(m.seqlens), _ptr(m.img_pos),
+                                      _ptr(m.row_of_text), _ptr(m.target), _ptr(m.status), _stream()))
+    return m
+
+
+def llava_merge_embed(m: MergeIndex, embed_tokens: torch.Tensor, image_features: torch.Tensor, out: torch.Tensor):
+    check(_L.vlb200_llava_merge_embed(_ptr(m.src_map), _ptr(embed_tokens), _ptr(image_features), _ptr(out),
+                                      m.n_seq * m.S, embed_tokens.shape[1], _stream()))
+    return out
+
+
+def llava_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, dimage_features: torch.Tensor):
+    assert dembed_f32.dtype == torch.float32
+    check(_L.vlb200_llava_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32), _ptr(dimage_features),
+                                    m.n_seq, m.n_img_batch, m.S, m.imgs_per_seq * m.P, dx.shape[1], _stream()))
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
+             seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool, scale: float):
+    """q/k/v/out: 2-D row-major views [B*S, >= heads*head_dim] (may be column slices of one qkv buffer)."""
+    check(_L.vlb200_attn_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
+                             _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale, _stream()))
+    return out
+
+
+def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
+    check(_L.vlb200_attn_bwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
+                             _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk),
+                             dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal),
+                             scale, _stream()))
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------
+def sumsq(x: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, accumulate: bool = False):
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and workspace.numel() >= 1024
+    check(_L.vlb200_sumsq_bf16(_ptr(x), x.numel(), _ptr(workspace), _ptr(out), int(accumulate), _stream()))
+    return out
+
+
+def adamw_(param: torch.Tensor, grad: torch.Tensor, master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+           lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0,
+           grad_sumsq: Optional[torch.Tensor] = None, max_grad_norm: float = 0.0):
+    n = param.numel()
+    assert grad.numel() == n and master.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    check(_L.vlb200_adamw(_ptr(param), _ptr(grad), _ptr(master), _ptr(exp_avg), _ptr(exp_avg_sq), n, lr, beta1, beta2,
+                          eps, weight_decay, step, grad_scale, _ptr(grad_sumsq), max_grad_norm, _stream()))
+
+
+def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
+    check(_L.vlb200_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), scale, _stream()))
+    return dst
+
+
+def cast_bf16_to_f32(src: torch.Tensor, dst: torch.Tensor):
+    check(_L.vlb200_cast_bf16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()))
+    return dst
