@@ -35,8 +35,8 @@ def close(got, want, rtol=1.6e-2, atol=1e-3):
                                          (576, 1024, 588, 1, 1), (1000, 32064, 128, 1, 1)])
 def test_gemm_variants(ops, M, N, K, ak, bk):
     torch.manual_seed(M + N + K)
-    lda = (K if ak else M) + 8  # padded leading dimensions: views, not contiguous tensors
-    ldb = (K if bk else N) + 16
+    lda = ((K if ak else M) + 7) // 8 * 8 + 8  # padded leading dimensions: views, not contiguous tensors
+    ldb = ((K if bk else N) + 7) // 8 * 8 + 16
     a_full = bf(torch.randn((M if ak else K), lda, device="cuda") * 0.5)
     b_full = bf(torch.randn((N if bk else K), ldb, device="cuda") * 0.5)
     a = a_full[:, :(K if ak else M)]
@@ -254,8 +254,8 @@ def test_merge_index_embed_bwd(ops):
     i2 = img.float().requires_grad_(True)
     fe2, *_ = R.merge_input_ids_with_image_features(cfg, torch.cat([i2.view(3, P, d)] * 2, 0), F.embedding(ids, e), ids, am, lb)
     (fe2.view(-1, d) * dx.float()).sum().backward()
-    close(dembed, e.grad, 1e-5, 1e-5)
-    close(dimg, i2.grad, 1e-2, 1e-2)
+    close(dembed.cpu(), e.grad, 1e-5, 1e-5)
+    close(dimg.cpu(), i2.grad, 1e-2, 1e-2)
     # status codes: two image tokens in one sequence -> ragged
     bad = ids.clone()
     bad[0, 3] = cfg.image_token_index

@@ -238,7 +238,7 @@ extern "C" int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, voi
     return VLB200_OK;
 }
 
-extern "C" int vlb200_norm_bwd_workspace_floats(int cols) { return 2 * num_sms() * cols; }
+extern "C" int vlb200_norm_bwd_workspace_floats(int cols) { return 8 * num_sms() * cols; }
 
 extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
                                   void* dx, void* dw, int dw_accumulate, float* workspace, int rows, int cols,
@@ -246,7 +246,7 @@ extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, 
     VLB_REQUIRE(dy && x && w && rstd && dx && dw && workspace, "rmsnorm_bwd: null pointer");
     if (int rc = check_cols(cols, "rmsnorm_bwd")) return rc;
     if (rows <= 0) return VLB200_OK;
-    const int grid = rows < 2 * num_sms() ? rows : 2 * num_sms();
+    const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
     cudaStream_t s = as_stream(stream);
     const int vpt = ((cols >> 3) + NORM_THREADS - 1) / NORM_THREADS;
 #define VLB_RMS_BWD(V)                                                                                         \

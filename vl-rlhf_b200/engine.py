@@ -468,6 +468,27 @@ class LlavaDPOEngine:
                 out.grad_norm = self.grad_sumsq
         return out
 
+    def train_step(self, batch: Dict, train: bool = True) -> Dict[str, float]:
+        """Public end-to-end call: one collated host batch (the dict VLDPODataCollatorWithPadding emits) in,
+        the TRL metric dict out.  Includes the H2D staging of the inputs and the D2H read of the results."""
+        from . import host
+        tc = self.tc
+        cb = host.concatenated_inputs(batch, False, tc.label_pad_token_id, tc.padding_value)
+        ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+        px = batch["img_input_dict"]["pixel_values"]  # one copy per pair: the [v, v] duplicate is never shipped
+        wt = None
+        if tc.loss_type == "ddpo":
+            wt = host.ddpo_row_weights(ids, lb, self.cfg.image_token_index, self.cfg.n_patches, tc.label_pad_token_id)
+        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt), train=train)
+        n = out.policy_logps.numel() // 2
+        packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
+                            (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0)]).cpu()  # the D2H read
+        world = self.world_size()
+        return {"loss": float(packed[0]), "rewards/accuracies": float(packed[1]), "rewards/chosen": float(packed[2]),
+                "rewards/rejected": float(packed[3]), "rewards/margins": float(packed[4]),
+                "logps/chosen": float(packed[6]), "logps/rejected": float(packed[7]),
+                "grad_norm": float(packed[8]) ** 0.5 / world}
+
     def check_merge_status(self, m: "ops.MergeIndex"):
         """Synchronising validity check mirroring the reference's ValueError (Llava/__init__.py:90-94)."""
         st = int(m.status.item())

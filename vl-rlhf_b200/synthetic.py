@@ -1,0 +1,47 @@
+"""Synthetic preference batches in the exact format VLDPODataCollatorWithPadding emits
+(base/collator.py:26-68): right-padded chosen_/rejected_ input_ids / attention_mask / labels (int64) and
+img_input_dict.pixel_values (fp32 [B,3,H,W]).  One <image> placeholder after BOS; labels = -100 on prompt
+and padding.  (SURVEY.md §8d "Synthetic inputs".)"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .config import ModelConfig
+
+
+def make_batch(cfg: ModelConfig, n_pairs: int, text_len: int, prompt_len: int, seed: int, pin: bool = False) -> Dict:
+    g = np.random.RandomState(seed)
+    lo, hi = 3, min(cfg.image_token_index, cfg.vocab) - 1
+    B, L = n_pairs, text_len
+    prompt = g.randint(lo, hi, size=(B, prompt_len))
+    prompt[:, 0] = 1
+    prompt[:, 1] = cfg.image_token_index
+    long_len = np.full(B, L)
+    short_len = g.randint(int(0.75 * L), L + 1, size=B)
+    swap = g.rand(B) < 0.5
+    lens = {"chosen": np.where(swap, short_len, long_len), "rejected": np.where(swap, long_len, short_len)}
+    out: Dict = {}
+    for key in ("chosen", "rejected"):
+        ids = np.full((B, L), cfg.pad_token_id, dtype=np.int64)
+        mask = np.zeros((B, L), dtype=np.int64)
+        labels = np.full((B, L), -100, dtype=np.int64)
+        for b in range(B):
+            n = int(lens[key][b])
+            ids[b, :prompt_len] = prompt[b]
+            ids[b, prompt_len:n] = g.randint(lo, hi, size=n - prompt_len)
+            mask[b, :n] = 1
+            labels[b, prompt_len:n] = ids[b, prompt_len:n]
+        out[f"{key}_input_ids"] = torch.from_numpy(ids)
+        out[f"{key}_attention_mask"] = torch.from_numpy(mask)
+        out[f"{key}_labels"] = torch.from_numpy(labels)
+    gen = torch.Generator().manual_seed(seed)
+    out["img_input_dict"] = {"pixel_values": torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=gen)}
+    if pin:
+        for k, v in list(out.items()):
+            if isinstance(v, torch.Tensor):
+                out[k] = v.pin_memory()
+        out["img_input_dict"]["pixel_values"] = out["img_input_dict"]["pixel_values"].pin_memory()
+    return out
