@@ -114,13 +114,14 @@ def dpo_loss(policy_logps, ref_logps, beta, label_smoothing=0.0, loss_type="sigm
     if loss_type not in LOSS_TYPES:
         raise ValueError(f"Unknown loss type: {loss_type}. Should be one of ['sigmoid', 'hinge', 'ipo', 'kto_pair']")
     n = policy_logps.numel() // 2
-    p = policy_logps.detach().float().clone().requires_grad_(True)
-    losses, cr, rr = oracle_loss(p[:n], p[n:], ref_logps[:n].float(), ref_logps[n:].float(), beta, label_smoothing, loss_type,
-                                 reference_free)
     grad = None
-    if want_grad:
-        (losses.mean() * loss_scale).backward()
-        grad = p.grad
+    with torch.enable_grad():
+        p = policy_logps.detach().float().clone().requires_grad_(True)
+        losses, cr, rr = oracle_loss(p[:n], p[n:], ref_logps[:n].detach().float(), ref_logps[n:].detach().float(), beta,
+                                     label_smoothing, loss_type, reference_free)
+        if want_grad:
+            (losses.mean() * loss_scale).backward()
+            grad = p.grad
     stats = torch.stack([losses.mean().detach(), (cr > rr).float().mean(), cr.mean(), rr.mean(), (cr - rr).mean(),
                          torch.tensor(float(losses.numel()))])
     _c()
@@ -390,6 +391,12 @@ def attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale):
 
 
 def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
+    with torch.enable_grad():
+        _attn_bwd_impl(q, k, v, dout, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    _c(3)
+
+
+def _attn_bwd_impl(q, k, v, dout, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
     qq = q.float().reshape(B, S, H, head_dim).clone().requires_grad_(True)
     kk = k.float().reshape(B, S, KVH, head_dim).clone().requires_grad_(True)
     vv = v.float().reshape(B, S, KVH, head_dim).clone().requires_grad_(True)
@@ -406,7 +413,6 @@ def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, 
     dq.copy_(qq.grad.reshape(B * S, -1).to(dq.dtype))
     dk.copy_(kk.grad.reshape(B * S, -1).to(dk.dtype))
     dv.copy_(vv.grad.reshape(B * S, -1).to(dv.dtype))
-    _c(3)
 
 
 def sumsq(x, out, workspace, accumulate=False):

@@ -145,3 +145,93 @@ def test_engine_optimizer_cpu_mock(cpu_pkg):
         l1 = float(eng.step(*a[:4], train=True).stats[0])
     assert l1 < l0
     assert torch.equal(eng.params, eng.master.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------
+# plugin API (the reference's three VLDPOTrainer override points) over the mock ops
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cpu_plugin(cpu_pkg):
+    sys.modules.pop("vlrlhf_b200.plugin", None)
+    return importlib.import_module("vlrlhf_b200.plugin")
+
+
+def _ref_fns():
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        T, _, _ = ref_shim.reference_symbols()
+        return T.get_batch_logps, T.dpo_loss, "reference"
+    return (lambda lg, lb, **kw: R.get_batch_logps(lg, lb, **{k: v for k, v in kw.items() if k != "is_encoder_decoder"}),
+            lambda s, a, b, c, d: R.dpo_loss(a, b, c, d, s.beta, s.label_smoothing, s.loss_type, s.reference_free), "oracle")
+
+
+def test_plugin_get_batch_logps_like_reference(cpu_plugin):
+    ref_logps, _, _ = _ref_fns()
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(4, 30, 97, generator=g) * 2
+    labels = torch.randint(1, 97, (4, 30), generator=g)
+    labels[:, :7] = -100
+    labels[1, 22:] = -100
+    labels[2:] = labels[:2]
+    labels[2, 12:15] = torch.tensor([5, 6, 7])  # a modified span so the DDPO mask is non-trivial
+    for kw in (dict(), dict(average_log_prob=True), dict(mask_shared_tokens=True)):
+        a = logits.clone().requires_grad_(True)
+        b = logits.clone().requires_grad_(True)
+        got = cpu_plugin.get_batch_logps(a, labels, **kw)
+        want = ref_logps(b, labels, **kw)
+        np.testing.assert_allclose(got.detach().numpy(), want.detach().numpy(), rtol=1e-5, atol=1e-4)
+        w = torch.tensor([1.0, -2.0, 0.5, 3.0])
+        (got * w).sum().backward()
+        (want * w).sum().backward()
+        np.testing.assert_allclose(a.grad.numpy(), b.grad.numpy(), rtol=2e-2, atol=2e-3)  # bf16 dlogits
+    with pytest.raises(ValueError):
+        cpu_plugin.get_batch_logps(logits, labels[:, :-1])
+
+
+def test_plugin_dpo_loss_like_reference(cpu_plugin):
+    from types import SimpleNamespace
+    _, ref_loss, _ = _ref_fns()
+    g = torch.Generator().manual_seed(1)
+    pc, pr = -torch.rand(5, generator=g) * 300, -torch.rand(5, generator=g) * 300
+    rc, rr = pc + torch.randn(5, generator=g) * 3, pr + torch.randn(5, generator=g) * 3
+    for lt in ("sigmoid", "ddpo", "hinge", "ipo", "kto_pair"):
+        for ls in (0.0, 0.1):
+            s = SimpleNamespace(beta=0.1, label_smoothing=ls, loss_type=lt, reference_free=False,
+                                accelerator=SimpleNamespace(device="cpu"))
+            a, b = pc.clone().requires_grad_(True), pr.clone().requires_grad_(True)
+            c, d = pc.clone().requires_grad_(True), pr.clone().requires_grad_(True)
+            l1, cr1, rr1 = cpu_plugin.dpo_loss(s, a, b, rc, rr)
+            l2, cr2, rr2 = ref_loss(s, c, d, rc, rr)
+            np.testing.assert_allclose(l1.detach().numpy(), l2.detach().numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(cr1.numpy(), cr2.numpy(), rtol=1e-6)
+            l1.mean().backward()
+            l2.mean().backward()
+            np.testing.assert_allclose(a.grad.numpy(), c.grad.numpy(), rtol=1e-4, atol=1e-7)
+            np.testing.assert_allclose(b.grad.numpy(), d.grad.numpy(), rtol=1e-4, atol=1e-7)
+    with pytest.raises(ValueError):
+        cpu_plugin.dpo_loss(SimpleNamespace(beta=0.1, label_smoothing=0, loss_type="x", reference_free=False), pc, pr, rc, rr)
+
+
+def test_plugin_concatenated_forward_and_module(cpu_plugin, cpu_pkg):
+    from types import SimpleNamespace
+    config, engine, host, ops = cpu_pkg
+    d = np.load(os.path.join(G, "g4_tiny.npz"))
+    model = cpu_plugin.B200LlavaForRL(config.TINY, config.TrainConfig(), device="cpu", with_optimizer=False)
+    model.engine.init_synthetic(int(d["seed"]))
+    names = dict(model.hf_named_parameters())
+    assert "language_model.model.layers.0.self_attn.q_proj.weight" in names
+    assert not names["vision_tower.vision_model.embeddings.class_embedding"].requires_grad
+    batch = R.make_batch(R.TINY, 2, 24, 8, int(d["seed"]), ddpo_like=True)
+    trainer = SimpleNamespace(loss_type="sigmoid", is_encoder_decoder=False, label_pad_token_id=-100, padding_value=0,
+                              beta=0.1, label_smoothing=0.0, reference_free=False)
+    pc, pr, _, _ = cpu_plugin.concatenated_forward(trainer, model, batch)
+    with torch.no_grad():
+        rc, rr, _, _ = cpu_plugin.concatenated_forward(trainer, cpu_plugin.RefView(model), batch)
+    np.testing.assert_allclose(torch.cat([pc, pr]).detach().numpy(), d["policy_logps"], rtol=1e-3)
+    np.testing.assert_allclose(torch.cat([rc, rr]).numpy(), d["ref_logps"], rtol=1e-3)
+    losses, cr, rj = cpu_plugin.dpo_loss(trainer, pc, pr, rc, rr)
+    np.testing.assert_allclose(losses.detach().numpy(), d["sigmoid_losses"], atol=2e-3)
+    losses.mean().backward()  # autograd -> engine backward -> .grad views of the flat gradient buffer
+    gq = names["language_model.model.layers.0.self_attn.q_proj.weight"].grad
+    assert gq is not None and float(gq.float().abs().sum()) > 0
+    assert gq.data_ptr() == model.engine.hf_state("grad")["language_model.model.layers.0.self_attn.q_proj.weight"].data_ptr()
