@@ -238,9 +238,14 @@ def run_b200(args):
         step_dev()
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = ops.launch_count()
+    nvtx = os.environ.get("VLB_NVTX") == "1"  # `ncu --nvtx --nvtx-include "vlb_step/"` profiles only the timed steps
+    if nvtx:
+        torch.cuda.nvtx.range_push("vlb_step")
     ms_dev = timed(step_dev, args.steps)
+    if nvtx:
+        torch.cuda.nvtx.range_pop()
     launches = (ops.launch_count() - n0)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
     clocks = sampler.stop() if sampler else None
 
     # dominant kernel live: the tcgen05 GEMM at its largest forward shape (gate_up: [T,d] x [2ff,d]^T)
@@ -293,6 +298,7 @@ def main():
     ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny"])
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,7 +52,20 @@ def hf_name(name: str) -> str:
     return "model." + name
 
 
+def streamed_weights(cfg: R.LlavaCfg, seed: int, which: str):
+    """Yield (name, tensor) one tensor at a time (7B shapes: never hold two full copies in RAM).
+    Same values as R.make_policy_and_ref(cfg, seed)[0 if which == 'policy' else 1]."""
+    for name, shape, scale, shift in R.weight_specs(cfg):
+        n = int(np.prod(shape))
+        t = R.bf16_round(R.hash_uniform(n, R.tensor_seed(name, seed), scale, shift))
+        if which == "ref" and not name.startswith("vision_tower."):
+            o = R.bf16_round(R.hash_uniform(n, R.tensor_seed(name, seed + 1), scale, shift))
+            t = R.bf16_round(t + 0.05 * (o - (1.0 if name.endswith("norm.weight") else 0.0)))
+        yield name, t.reshape(shape)
+
+
 def build_reference_model(cfg: R.LlavaCfg, weights):
+    """weights: dict name->tensor, or an iterator of (name, tensor)."""
     _, _, LlavaShim = ref_shim.reference_symbols()
     hc = hf_config(cfg)
     with torch.device("meta"):
@@ -60,15 +73,18 @@ def build_reference_model(cfg: R.LlavaCfg, weights):
     m = m.to_empty(device="cpu")
     sd = m.state_dict()
     missing = []
+    names = []
     with torch.no_grad():
-        for n, t in weights.items():
+        for n, t in (weights.items() if isinstance(weights, dict) else weights):
+            names.append(n)
             k = hf_name(n)
             if k not in sd:
                 missing.append(k)
                 continue
             sd[k].copy_(t)
+            del t
     assert not missing, missing[:5]
-    loaded = {hf_name(n) for n in weights}
+    loaded = {hf_name(n) for n in names}
     not_set = [k for k in sd if k not in loaded and "post_layernorm" not in k]
     assert not not_set, not_set[:5]
     for k in sd:  # post_layernorm is unused by the path (hidden_states[-2]); make it finite
@@ -193,13 +209,13 @@ def g3_ddpo():
 
 
 def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed: int, ddpo: bool):
-    wp, wr = R.make_policy_and_ref(cfg, seed)
     batch = R.make_batch(cfg, n_pairs, text_len, prompt_len, seed, ddpo_like=ddpo)
     out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
     res = {}
-    for who, w in (("policy", wp), ("ref", wr)):
+    for who in ("policy", "ref"):
         t0 = time.time()
-        m = build_reference_model(cfg, w)
+        m = build_reference_model(cfg, streamed_weights(cfg, seed, who))
+        print(f"[{tag}] {who} weights ready {time.time() - t0:.1f}s", flush=True)
         logps, o = reference_concatenated_forward(m, cfg, batch, "sigmoid")
         res[who] = logps
         out[f"{who}_logps"] = logps.numpy()
