@@ -170,6 +170,18 @@ int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* d
 int vlb200_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                     int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH, int head_dim, int causal,
                     float scale, void* stream);
+/* tcgen05/TMEM/TMA forward (same contract as vlb200_attn_fwd; S and O accumulate in TMEM, K/V tiles arrive by TMA) */
+int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                       int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH, int head_dim, int causal,
+                       float scale, void* stream);
+/* delta[b,h,t] = sum_d dout[t,h,d] * out[t,h,d]  (softmax-backward row statistic) */
+int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
+                      int head_dim, void* stream);
+/* tcgen05/TMEM/TMA backward (same contract as vlb200_attn_bwd): pass 1 dK,dV (key tile stationary), pass 2 dQ */
+int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
+                       int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
+                       void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,
+                       int head_dim, int causal, float scale, void* stream);
 int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
                     int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
                     void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,

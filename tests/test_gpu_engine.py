@@ -151,6 +151,32 @@ def test_optimizer_step_reduces_loss_and_tracks_master(pkg):
     assert torch.equal(ref[k].float().cpu(), wr[k])
 
 
+def test_config1_7b_shapes_logps_and_loss_parity(pkg):
+    """BASELINE.json configs[0]: LLaVA-1.5-7B shapes, 2 pairs, text 128 (703 merged), loss/logprob parity against the
+    reference's LlavaForRL.forward + get_batch_logps + dpo_loss run in fp32 on CPU (tests/golden/g5_config1_7b.npz).
+    7B-shape weights are regenerated on the GPU by the bit-exact hash twin, so nothing travels."""
+    config, engine, host, ops = pkg
+    d = np.load(os.path.join(G, "g5_config1_7b.npz"))
+    rcfg = R.LLAVA15_7B
+    eng = engine.LlavaDPOEngine(config.LLAVA15_7B, config.TrainConfig(), with_optimizer=False)
+    eng.init_synthetic(int(d["seed"]))
+    batch = R.make_batch(rcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]))
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
+    out = eng.step(ids, am, lb, px, train=False)
+    pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
+    print("config1 policy logps", pol, "golden", d["policy_logps"])
+    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
+    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
+    # per-pair loss / rewards: margins are differences of ~1e3-sized log-probs, each good to 1e-3 relative
+    slack = 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4
+    np.testing.assert_allclose(out.losses.cpu().numpy(), d["sigmoid_losses"], atol=slack)
+    acc_want = (d["sigmoid_cr"] > d["sigmoid_rr"]).mean()
+    assert abs(float(out.stats[1]) - acc_want) < 1e-6
+    del eng
+    torch.cuda.empty_cache()
+
+
 def test_merge_validity_errors(pkg):
     config, engine, host, ops = pkg
     eng, rcfg, d, batch, cb = build(pkg, "g4_tiny", with_optimizer=False)

@@ -171,7 +171,10 @@ def ref_attention(q, k, v, causal, seqlens, scale):
     (3, 130, 4, 2, 128, True, [130, 64, 1]),  # GQA, ragged
     (1, 64, 2, 2, 64, True, None),
 ])
-def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
+@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
+def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens, impl):
+    fwd = ops.attn_fwd if impl == "mma_sync" else ops.attn_fwd_tc
+    bwd = ops.attn_bwd if impl == "mma_sync" else ops.attn_bwd_tc
     torch.manual_seed(S + H)
     dev = "cuda"
     ld = (H + 2 * KV) * dh
@@ -183,7 +186,7 @@ def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
     v = qkv[:, (H + KV) * dh:]
     out = torch.empty(B * S, H * dh, dtype=torch.bfloat16, device=dev)
     lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
-    ops.attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KV, dh, causal, scale)
+    fwd(q, k, v, out, lse, seqlens, B, S, H, KV, dh, causal, scale)
     qf = q.float().view(B, S, H, dh).clone().requires_grad_(True)
     kf = k.float().view(B, S, KV, dh).clone().requires_grad_(True)
     vf = v.float().view(B, S, KV, dh).clone().requires_grad_(True)
@@ -200,8 +203,8 @@ def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
     (want * dout.float().view(B, S, H, dh)).sum().backward()
     dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty(B, H, S, dtype=torch.float32, device=dev)
-    ops.attn_bwd(q, k, v, out, dout, lse, delta, dqkv[:, :H * dh], dqkv[:, H * dh:(H + KV) * dh], dqkv[:, (H + KV) * dh:],
-                 seqlens, B, S, H, KV, dh, causal, scale)
+    bwd(q, k, v, out, dout, lse, delta, dqkv[:, :H * dh], dqkv[:, H * dh:(H + KV) * dh], dqkv[:, (H + KV) * dh:],
+        seqlens, B, S, H, KV, dh, causal, scale)
     assert torch.isfinite(dqkv).all()
     gq = dqkv[:, :H * dh].view(B, S, H, dh)
     gk = dqkv[:, H * dh:(H + KV) * dh].view(B, S, KV, dh)

@@ -571,6 +571,18 @@ extern "C" int vlb200_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
     return attn::launch_fwd<128>(p, causal, as_stream(stream));
 }
 
+extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
+                                 int head_dim, void* stream) {
+    VLB_REQUIRE(out && dout && delta, "attn_delta: null pointer");
+    const size_t nw = (size_t)B * S * H;
+    const int blocks = (int)std::min<size_t>((nw + 7) / 8, (size_t)num_sms() * 16);
+    attn::attn_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                                  delta, B, S, H, head_dim);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
 extern "C" int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta,
                                void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens,

@@ -1,0 +1,416 @@
+// FlashAttention backward on tcgen05 + TMEM + TMA (sm_100a).  Two launches of one templated kernel:
+//
+//   MODE 0 (dK, dV): a CTA keeps a 128-key tile (K_j, V_j) in smem and streams 64-query tiles (Q_i, dO_i):
+//        S^T = K Q^T, dP^T = V dO^T            tcgen05.mma 128x64x16 (scores transposed: TMEM lane = key)
+//        P^T = exp2(S^T*c - lse[q]),  dS^T = scale * P^T o (dP^T - delta[q])      (bf16 -> swizzled smem)
+//        dV += P^T dO,  dK += dS^T Q           tcgen05.mma 128xDHx16, B = streamed tile read MN-major
+//   MODE 1 (dQ):     a CTA keeps a 128-query tile (Q_i, dO_i) and streams 64-key tiles (K_j, V_j):
+//        S = Q K^T, dP = dO V^T;  dS = scale * P o (dP - delta[row]);  dQ += dS K
+//
+// dQ is produced by a second pass (7 tile-GEMMs instead of 5) so no atomics are needed and results are
+// deterministic.  Persistent CTAs, warp 0 = TMA producer (stationary tiles + 3-stage ring of streamed tiles),
+// warp 1 = MMA issuer, warps 2-5 = elementwise/epilogue (one stationary row per thread).  Score tiles are
+// double buffered in TMEM; dK/dV (or dQ) accumulate in TMEM over the whole loop (GQA: over the group's heads).
+//
+// Replaces the autograd backward of LlamaAttention (modeling_llama.py:199-290).
+#include <algorithm>
+
+#include "ptx.cuh"
+
+namespace vlb {
+namespace gemm {
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                   CUtensorMap* out);
+}
+namespace attn_bwd_tc {
+
+using namespace ptx;
+
+constexpr int BX = 128;  // stationary rows
+constexpr int BY = 64;   // streamed rows
+constexpr int NST = 3;   // streamed-tile ring depth
+constexpr int NTHREADS = 192;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+struct Params {
+    const float* lse;    // [B, H, S] natural log
+    const float* delta;  // [B, H, S]
+    const int* seqlens;
+    __nv_bfloat16* out1; long long ld1;  // MODE 0: dV ; MODE 1: unused
+    __nv_bfloat16* out2; long long ld2;  // MODE 0: dK ; MODE 1: dQ
+    int B, S, H, KVH, causal;
+    float scale;
+    int n_xb, n_work;
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+
+template <int MODE>
+__device__ __forceinline__ void item_coords(const Params& p, int w, int& b, int& hx, int& xb) {
+    const int heads = MODE == 0 ? p.KVH : p.H;
+    const int bh = w / p.n_xb;
+    xb = MODE == 0 ? (w - bh * p.n_xb) : (p.n_xb - 1 - (w - bh * p.n_xb));  // heavy tiles first
+    hx = bh % heads;
+    b = bh / heads;
+}
+// streamed-tile range for one item: tiles [y_begin, y_end) of 64 rows, repeated for `reps` heads (GQA group)
+template <int MODE>
+__device__ __forceinline__ void item_range(const Params& p, int b, int xb, int& y_begin, int& y_end, int& reps) {
+    int kv_len = p.seqlens ? p.seqlens[b] : p.S;
+    kv_len = max(min(kv_len, p.S), 0);
+    const int x0 = xb * BX;
+    if (MODE == 0) {  // stationary keys [x0, x0+128); queries beyond kv_len have dO == 0
+        reps = p.H / p.KVH;
+        y_begin = p.causal ? x0 / BY : 0;
+        y_end = x0 < kv_len ? (kv_len + BY - 1) / BY : y_begin;
+    } else {          // stationary queries; keys up to the causal diagonal / kv_len
+        reps = 1;
+        y_begin = 0;
+        int kmax = kv_len;
+        if (p.causal) kmax = min(kmax, x0 + BX);
+        y_end = x0 < kv_len ? (kmax + BY - 1) / BY : 0;
+    }
+    if (y_end < y_begin) y_end = y_begin;
+}
+
+template <int DH, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_constant__ CUtensorMap tma_x2,
+                   const __grid_constant__ CUtensorMap tma_y1, const __grid_constant__ CUtensorMap tma_y2, const Params p) {
+    constexpr int NCH = DH / 64;
+    constexpr int XCH = BX * 128;            // bytes of one [128 x 128 B] chunk
+    constexpr int YCH = BY * 128;            // bytes of one [64 x 128 B] chunk
+    constexpr int X_BYTES = NCH * XCH;       // one stationary tile
+    constexpr int Y_BYTES = NCH * YCH;       // one streamed tile
+    constexpr int E_BYTES = BX * 128;        // [128 rows][64 bf16]
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t TM_T1 = 0, TM_T2 = 128, TM_A1 = 256, TM_A2 = 384;  // T buffers: +64 per stage
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX1 = smem;
+    uint8_t* sX2 = sX1 + X_BYTES;
+    uint8_t* sY = sX2 + X_BYTES;                 // NST stages of (Y1, Y2)
+    uint8_t* sE1 = sY + NST * 2 * Y_BYTES;
+    uint8_t* sE2 = sE1 + E_BYTES;
+    float* sLse = reinterpret_cast<float*>(sE2 + E_BYTES);  // [2][64] (MODE 0)
+    float* sDelta = sLse + 2 * BY;                           // [2][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BY);
+    uint64_t* x_full = bars + 0;
+    uint64_t* x_empty = bars + 1;
+    uint64_t* y_full = bars + 2;             // [NST]
+    uint64_t* y_empty = bars + 2 + NST;      // [NST]
+    uint64_t* t_full = bars + 2 + 2 * NST;   // [2]
+    uint64_t* t_empty = t_full + 2;          // [2]
+    uint64_t* e_full = t_empty + 2;
+    uint64_t* e_done = e_full + 1;
+    uint64_t* acc_free = e_done + 1;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_free + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
+    if (warp_idx == 0 && lane_idx == 0) {
+        prefetch_tensormap(&tma_x1); prefetch_tensormap(&tma_x2); prefetch_tensormap(&tma_y1); prefetch_tensormap(&tma_y2);
+        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        for (int i = 0; i < NST; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        mbar_init(e_full, 4); mbar_init(e_done, 1); mbar_init(acc_free, 4);
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const int group = p.H / p.KVH;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane_idx == 0) {
+            uint32_t item = 0, yc = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                int b, hx, xb, yb, ye, reps;
+                item_coords<MODE>(p, w, b, hx, xb);
+                item_range<MODE>(p, b, xb, yb, ye, reps);
+                const int n = (ye - yb) * reps;
+                if (n == 0) continue;
+                const int row0 = b * p.S;
+                const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
+                mbar_wait(x_empty, (item & 1) ^ 1, 10);
+                mbar_arrive_expect_tx(x_full, 2 * X_BYTES);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    tma_load_2d(&tma_x1, x_full, sX1 + c * XCH, xcol + c * 64, row0 + xb * BX);
+                    tma_load_2d(&tma_x2, x_full, sX2 + c * XCH, xcol + c * 64, row0 + xb * BX);
+                }
+                for (int t = 0; t < n; ++t, ++yc) {
+                    const int st = yc % NST;
+                    const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                    const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
+                    mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
+                    mbar_arrive_expect_tx(&y_full[st], 2 * Y_BYTES);
+                    uint8_t* y1 = sY + st * 2 * Y_BYTES;
+                    uint8_t* y2 = y1 + Y_BYTES;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        tma_load_2d(&tma_y1, &y_full[st], y1 + c * YCH, ycol + c * 64, row0 + yt * BY);
+                        tma_load_2d(&tma_y2, &y_full[st], y2 + c * YCH, ycol + c * 64, row0 + yt * BY);
+                    }
+                }
+                ++item;
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (lane_idx == 0) {
+            constexpr uint32_t idesc_t = make_idesc_bf16_f32(BX, BY, false, false);
+            constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
+            uint32_t item = 0, yc = 0, tc = 0, ec = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                int b, hx, xb, yb, ye, reps;
+                item_coords<MODE>(p, w, b, hx, xb);
+                item_range<MODE>(p, b, xb, yb, ye, reps);
+                const int n = (ye - yb) * reps;
+                if (n == 0) continue;
+                mbar_wait(x_full, item & 1, 30);
+                tcgen05_fence_after();
+                const uint32_t y0 = yc;
+                for (int t = 0; t <= n; ++t) {
+                    if (t < n) {
+                        const uint32_t yi = y0 + t, st = yi % NST, tb = tc & 1;
+                        mbar_wait(&y_full[st], (yi / NST) & 1, 40 + st);
+                        mbar_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1, 50 + tb);
+                        tcgen05_fence_after();
+                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
+                            umma_f16_ss(tmem_base + TM_T1 + tb * BY, make_smem_desc_sw128(smem_u32(sX1) + xo, 1024, 0),
+                                        make_smem_desc_sw128(y1 + yo, 1024, 0), idesc_t, k != 0);
+                        }
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
+                            umma_f16_ss(tmem_base + TM_T2 + tb * BY, make_smem_desc_sw128(smem_u32(sX2) + xo, 1024, 0),
+                                        make_smem_desc_sw128(y2 + yo, 1024, 0), idesc_t, k != 0);
+                        }
+                        umma_commit(&t_full[tb]);
+                        if (t == n - 1) umma_commit(x_empty);
+                        ++tc;
+                    }
+                    if (t >= 1) {
+                        const uint32_t u = t - 1, yi = y0 + u, st = yi % NST;
+                        if (u == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);
+                        mbar_wait(e_full, ec & 1, 70);
+                        tcgen05_fence_after();
+                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BY / 16; ++k) {
+                            if (MODE == 0)  // dV += P^T dO
+                                umma_f16_ss(tmem_base + TM_A1, make_smem_desc_sw128(smem_u32(sE1) + k * 32, 1024, 0),
+                                            make_smem_desc_sw128(y2 + k * 2048, 1024, YCH), idesc_a, (u != 0 || k != 0) ? 1u : 0u);
+                            // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
+                            umma_f16_ss(tmem_base + TM_A2, make_smem_desc_sw128(smem_u32(sE2) + k * 32, 1024, 0),
+                                        make_smem_desc_sw128(y1 + k * 2048, 1024, YCH), idesc_a, (u != 0 || k != 0) ? 1u : 0u);
+                        }
+                        umma_commit(e_done);
+                        umma_commit(&y_empty[st]);
+                        ++ec;
+                    }
+                }
+                yc += n;
+                ++item;
+            }
+        }
+    } else {
+        // ===================== elementwise + epilogue (4 warps, one stationary row per thread) =====================
+        const int quad = warp_idx & 3;
+        const int r = quad * 32 + lane_idx;
+        const int tid_e = threadIdx.x - 64;  // 0..127 inside the elementwise group
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float sl2 = p.scale * LOG2E_F;
+        uint32_t tc = 0, ec = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, hx, xb, yb, ye, reps;
+            item_coords<MODE>(p, w, b, hx, xb);
+            item_range<MODE>(p, b, xb, yb, ye, reps);
+            const int n = (ye - yb) * reps;
+            int kv_len = p.seqlens ? p.seqlens[b] : p.S;
+            kv_len = max(min(kv_len, p.S), 0);
+            const int xrow = xb * BX + r;  // MODE 0: key index ; MODE 1: query index
+            float row_lse2 = 0.f, row_delta = 0.f;
+            if (MODE == 1 && xrow < p.S) {
+                const long long si = ((long long)b * p.H + hx) * p.S + xrow;
+                row_lse2 = p.lse[si] * LOG2E_F;
+                row_delta = p.delta[si];
+            }
+            for (int t = 0; t < n; ++t, ++tc) {
+                const uint32_t tb = tc & 1;
+                const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                const int y0 = yt * BY;
+                if (MODE == 0) {  // per-column (query) statistics of this streamed tile -> smem
+                    if (tid_e < BY) {
+                        const int q = y0 + tid_e;
+                        const int hq = hx * group + rep;
+                        const long long si = ((long long)b * p.H + hq) * p.S + q;
+                        sLse[tb * BY + tid_e] = q < p.S ? p.lse[si] * LOG2E_F : 0.f;
+                        sDelta[tb * BY + tid_e] = q < p.S ? p.delta[si] : 0.f;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
+                tcgen05_fence_after();
+                uint32_t t1[2][32], t2[2][32];
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY, t1[0]);
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + 32, t1[1]);
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY, t2[0]);
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + 32, t2[1]);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(&t_empty[tb]);
+                uint32_t e1[32], e2[32];
+#pragma unroll
+                for (int c = 0; c < BY; c += 2) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = c + e;
+                        const int key = MODE == 0 ? xrow : y0 + col;
+                        const int qi = MODE == 0 ? y0 + col : xrow;
+                        const bool ok = key < kv_len && qi < kv_len && (!p.causal || key <= qi);
+                        const float l2 = MODE == 0 ? sLse[tb * BY + col] : row_lse2;
+                        const float dl = MODE == 0 ? sDelta[tb * BY + col] : row_delta;
+                        const float s = __uint_as_float(t1[col >> 5][col & 31]);
+                        const float dp = __uint_as_float(t2[col >> 5][col & 31]);
+                        const float pr = ok ? exp2f(fmaf(s, sl2, -l2)) : 0.f;
+                        pv[e] = pr;
+                        dv[e] = pr * (dp - dl) * p.scale;
+                    }
+                    e1[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+                    e2[c >> 1] = pack_bf16x2(dv[0], dv[1]);
+                }
+                // E buffers are free once the accumulate MMAs of the previous tile have completed
+                if (ec > 0) mbar_wait(e_done, (ec - 1) & 1, 90);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t off = r * 128 + ((u ^ (r & 7)) << 4);
+                    if (MODE == 0) *reinterpret_cast<uint4*>(sE1 + off) = make_uint4(e1[u * 4], e1[u * 4 + 1], e1[u * 4 + 2], e1[u * 4 + 3]);
+                    *reinterpret_cast<uint4*>(sE2 + off) = make_uint4(e2[u * 4], e2[u * 4 + 1], e2[u * 4 + 2], e2[u * 4 + 3]);
+                }
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(e_full);
+                ++ec;
+            }
+            // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work)
+            if (n > 0) {
+                mbar_wait(e_done, (ec - 1) & 1, 95);
+                tcgen05_fence_after();
+            }
+            const bool valid = xrow < p.S;
+            const long long grow = (long long)b * p.S + xrow;
+#pragma unroll
+            for (int a = (MODE == 0 ? 0 : 1); a < 2; ++a) {
+                __nv_bfloat16* dst = (a == 0 ? p.out1 + grow * p.ld1 : p.out2 + grow * p.ld2) + (long long)hx * DH;
+#pragma unroll
+                for (int c = 0; c < DH / 32; ++c) {
+                    uint32_t acc[32];
+                    if (n > 0) {
+                        tmem_ld_32x32b(tmem_base + lane_addr + (a == 0 ? TM_A1 : TM_A2) + c * 32, acc);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint4 v;
+                            v.x = pack_bf16x2(__uint_as_float(acc[u * 8 + 0]), __uint_as_float(acc[u * 8 + 1]));
+                            v.y = pack_bf16x2(__uint_as_float(acc[u * 8 + 2]), __uint_as_float(acc[u * 8 + 3]));
+                            v.z = pack_bf16x2(__uint_as_float(acc[u * 8 + 4]), __uint_as_float(acc[u * 8 + 5]));
+                            v.w = pack_bf16x2(__uint_as_float(acc[u * 8 + 6]), __uint_as_float(acc[u * 8 + 7]));
+                            *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
+                        }
+                    }
+                }
+            }
+            if (n > 0) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(acc_free);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int DH, int MODE>
+static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, const Params& p,
+                  cudaStream_t s) {
+    constexpr int NCH = DH / 64;
+    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + 2 * BX * 128 + 4 * BY * 4 + 256 + 1024;
+    auto kern = attn_bwd_tc_kernel<DH, MODE>;
+    static bool configured = false;
+    if (!configured) {
+        VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int grid = std::min(p.n_work, num_sms());
+    kern<<<grid, NTHREADS, smem_bytes, s>>>(x1, x2, y1, y2, p);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+}  // namespace attn_bwd_tc
+}  // namespace vlb
+
+extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
+                                 int head_dim, void* stream);
+
+extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta,
+                                  void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens,
+                                  int B, int S, int H, int KVH, int head_dim, int causal, float scale, void* stream) {
+    using namespace vlb;
+    using namespace vlb::attn_bwd_tc;
+    VLB_REQUIRE(q && k && v && out && dout && lse && delta && dq && dk && dv, "attn_bwd_tc: null pointer");
+    VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_bwd_tc: bad B/S/H/KVH");
+    VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_bwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
+    VLB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+                "attn_bwd_tc: row strides must be multiples of 8");
+    if (int rc = vlb200_attn_delta(out, ldo, dout, lddo, delta, B, S, H, head_dim, stream)) return rc;
+    const uint64_t rows = (uint64_t)B * S;
+    const uint64_t qcols = (uint64_t)H * head_dim, kcols = (uint64_t)KVH * head_dim;
+    CUtensorMap xk, xv, yq, ydo, xq, xdo, yk, yv;
+    int rc;
+    if ((rc = gemm::get_tensor_map(k, kcols, rows, ldk, 64, BX, &xk))) return rc;
+    if ((rc = gemm::get_tensor_map(v, kcols, rows, ldv, 64, BX, &xv))) return rc;
+    if ((rc = gemm::get_tensor_map(q, qcols, rows, ldq, 64, BY, &yq))) return rc;
+    if ((rc = gemm::get_tensor_map(dout, qcols, rows, lddo, 64, BY, &ydo))) return rc;
+    if ((rc = gemm::get_tensor_map(q, qcols, rows, ldq, 64, BX, &xq))) return rc;
+    if ((rc = gemm::get_tensor_map(dout, qcols, rows, lddo, 64, BX, &xdo))) return rc;
+    if ((rc = gemm::get_tensor_map(k, kcols, rows, ldk, 64, BY, &yk))) return rc;
+    if ((rc = gemm::get_tensor_map(v, kcols, rows, ldv, 64, BY, &yv))) return rc;
+    Params p{};
+    p.lse = lse; p.delta = delta; p.seqlens = seqlens;
+    p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
+    p.n_xb = (S + BX - 1) / BX;
+    cudaStream_t s = as_stream(stream);
+    // pass 1: dK, dV
+    p.out1 = (__nv_bfloat16*)dv; p.ld1 = lddv; p.out2 = (__nv_bfloat16*)dk; p.ld2 = lddk;
+    p.n_work = p.n_xb * KVH * B;
+    rc = head_dim == 64 ? launch<64, 0>(xk, xv, yq, ydo, p, s) : launch<128, 0>(xk, xv, yq, ydo, p, s);
+    if (rc) return rc;
+    // pass 2: dQ
+    p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq;
+    p.n_work = p.n_xb * H * B;
+    return head_dim == 64 ? launch<64, 1>(xq, xdo, yk, yv, p, s) : launch<128, 1>(xq, xdo, yk, yv, p, s);
+}

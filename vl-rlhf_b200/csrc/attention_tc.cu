@@ -1,0 +1,363 @@
+// FlashAttention forward on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   S = Q K^T            tcgen05.mma 128x128x16, A = Q tile (smem, K-major), B = K tile (smem, K-major), D = TMEM
+//   P = softmax-part(S)  4 softmax warps: thread r owns row r (TMEM lane r): tcgen05.ld, online max/sum in the
+//                        log2 domain, bf16 P written to 128B-swizzled smem (K-major A operand)
+//   O += P V             tcgen05.mma 128xDHx16, B = V tile (smem, MN-major), O accumulates in TMEM across KV tiles;
+//                        rescaled lazily (only when the running max grows by > 2^8), normalised once at the end
+//
+// Persistent CTAs (grid = #SMs), warp 0 = TMA producer (Q tile + 2-stage K/V ring), warp 1 = MMA issuer,
+// warps 2-5 = softmax/epilogue (TMEM lane quadrant = warp_idx % 4).  S is double buffered in TMEM so the
+// QK^T of tile j+1 overlaps the softmax of tile j.
+//
+// Replaces LlamaAttention / CLIPAttention forward (modeling_llama.py:199-290, modeling_clip.py:261-334).
+#include <algorithm>
+
+#include "ptx.cuh"
+
+namespace vlb {
+namespace gemm {
+int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                   CUtensorMap* out);
+}
+namespace attn_tc {
+
+using namespace ptx;
+
+constexpr int BM = 128, BN = 128;
+constexpr int NTHREADS = 192;
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P <= 2^8 before a lazy rescale of O
+
+struct Params {
+    __nv_bfloat16* o; long long ldo;
+    float* lse;          // [B, H, S] or null
+    const int* seqlens;  // [B] or null
+    int B, S, H, KVH, causal;
+    float scale;
+    int n_qb, n_work;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void work_coords(const Params& p, int w, int& b, int& h, int& qb) {
+    const int bh = w / p.n_qb;
+    qb = p.n_qb - 1 - (w - bh * p.n_qb);  // heavy (late) query tiles first within a head
+    h = bh % p.H;
+    b = bh / p.H;
+}
+__device__ __forceinline__ int num_kv_tiles(const Params& p, int b, int qb) {
+    int kv_len = p.seqlens ? p.seqlens[b] : p.S;
+    kv_len = max(kv_len, 1);
+    int kmax = kv_len;
+    if (p.causal) kmax = min(kmax, (qb + 1) * BM);
+    return (kmax + BN - 1) / BN;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                   const __grid_constant__ CUtensorMap tma_v, const Params p) {
+    constexpr int NCH = DH / 64;                 // 64-column (128 B) chunks per row
+    constexpr int CHUNK_BYTES = 128 * 128;       // [128 rows][128 B]
+    constexpr int Q_BYTES = NCH * CHUNK_BYTES;
+    constexpr int KV_BYTES = NCH * CHUNK_BYTES;  // one K or V tile
+    constexpr int P_BYTES = 2 * CHUNK_BYTES;     // [128 q][128 keys] bf16
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t TM_S = 0, TM_O = 256;     // S buffers at columns 0 / 128, O at 256
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + Q_BYTES;            // 2 stages
+    uint8_t* sV = sK + 2 * KV_BYTES;       // 2 stages
+    uint8_t* sP = sV + 2 * KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;   // [2]
+    uint64_t* kv_empty = bars + 4;  // [2]
+    uint64_t* s_full = bars + 6;    // [2]
+    uint64_t* s_empty = bars + 8;   // [2]
+    uint64_t* p_full = bars + 10;
+    uint64_t* pv_done = bars + 11;
+    uint64_t* o_free = bars + 12;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
+
+    if (warp_idx == 0 && lane_idx == 0) {
+        prefetch_tensormap(&tma_q); prefetch_tensormap(&tma_k); prefetch_tensormap(&tma_v);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+        }
+        mbar_init(p_full, 4); mbar_init(pv_done, 1); mbar_init(o_free, 4);
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane_idx == 0) {
+            uint32_t item = 0, kvc = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+                int b, h, qb;
+                work_coords(p, w, b, h, qb);
+                const int kvh = h / (p.H / p.KVH);
+                const int n_tiles = num_kv_tiles(p, b, qb);
+                const int row0 = b * p.S;
+                mbar_wait(q_empty, (item & 1) ^ 1, 10);
+                mbar_arrive_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_q, q_full, sQ + c * CHUNK_BYTES, h * DH + c * 64, row0 + qb * BM);
+                for (int j = 0; j < n_tiles; ++j, ++kvc) {
+                    const int st = kvc & 1;
+                    mbar_wait(&kv_empty[st], ((kvc >> 1) & 1) ^ 1, 20 + st);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        tma_load_2d(&tma_k, &kv_full[st], sK + st * KV_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
+                        tma_load_2d(&tma_v, &kv_full[st], sV + st * KV_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (lane_idx == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
+            constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
+            uint32_t item = 0, kvc = 0, sc = 0, pc = 0;
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+                int b, h, qb;
+                work_coords(p, w, b, h, qb);
+                const int n_tiles = num_kv_tiles(p, b, qb);
+                mbar_wait(q_full, item & 1, 30);
+                tcgen05_fence_after();
+                const uint32_t kv0 = kvc;
+                for (int j = 0; j <= n_tiles; ++j) {
+                    if (j < n_tiles) {
+                        // ---- S_j = Q K_j^T into S buffer (sc & 1)
+                        const uint32_t kvi = kv0 + j, st = kvi & 1, sb = sc & 1;
+                        mbar_wait(&kv_full[st], (kvi >> 1) & 1, 40 + st);
+                        mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1, 50 + sb);
+                        tcgen05_fence_after();
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+                            const uint64_t a = make_smem_desc_sw128(smem_u32(sQ) + off, 1024, 0);
+                            const uint64_t bd = make_smem_desc_sw128(smem_u32(sK + st * KV_BYTES) + off, 1024, 0);
+                            umma_f16_ss(tmem_base + TM_S + sb * BN, a, bd, idesc_s, k != 0);
+                        }
+                        umma_commit(&s_full[sb]);
+                        if (j == n_tiles - 1) umma_commit(q_empty);  // Q tile no longer needed once S of the last tile retires
+                        ++sc;
+                    }
+                    if (j >= 1) {
+                        // ---- O (+)= P_{j-1} V_{j-1}
+                        const uint32_t t = j - 1, kvi = kv0 + t, st = kvi & 1;
+                        if (t == 0) mbar_wait(o_free, (item & 1) ^ 1, 60);  // epilogue of the previous item has read O
+                        mbar_wait(p_full, pc & 1, 70);
+                        tcgen05_fence_after();
+#pragma unroll
+                        for (int k = 0; k < BN / 16; ++k) {
+                            const uint64_t a = make_smem_desc_sw128(smem_u32(sP) + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 1024, 0);
+                            const uint64_t bd = make_smem_desc_sw128(smem_u32(sV + st * KV_BYTES) + k * (16 * 128), 1024, CHUNK_BYTES);
+                            umma_f16_ss(tmem_base + TM_O, a, bd, idesc_o, (t != 0 || k != 0) ? 1u : 0u);
+                        }
+                        umma_commit(pv_done);
+                        umma_commit(&kv_empty[st]);
+                        ++pc;
+                    }
+                }
+                kvc += n_tiles;
+            }
+        }
+    } else {
+        // ===================== softmax + epilogue (4 warps, one row per thread) =====================
+        const int quad = warp_idx & 3;
+        const int r = quad * 32 + lane_idx;  // row inside the Q tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float sl2 = p.scale * LOG2E_F;
+        uint32_t item = 0, sc = 0, pvc = 0;  // pvc = number of PV MMAs whose completion this thread has accounted for
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+            int b, h, qb;
+            work_coords(p, w, b, h, qb);
+            const int n_tiles = num_kv_tiles(p, b, qb);
+            int kv_len = p.seqlens ? p.seqlens[b] : p.S;
+            kv_len = max(kv_len, 1);
+            const int qrow = qb * BM + r;
+            float m_run = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_tiles; ++j, ++sc) {
+                const uint32_t sb = sc & 1;
+                mbar_wait(&s_full[sb], (sc >> 1) & 1, 80 + sb);
+                tcgen05_fence_after();
+                uint32_t sr[4][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_base + lane_addr + TM_S + sb * BN + c * 32, sr[c]);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(&s_empty[sb]);  // S buffer is in registers now
+                const int k0 = j * BN;
+                const bool need_mask = (k0 + BN > kv_len) || (p.causal && k0 + BN > qb * BM);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(sr[c][i]) * sl2;
+                        if (need_mask) {
+                            const int key = k0 + c * 32 + i;
+                            if (key >= kv_len || (p.causal && key > qrow)) x = -INFINITY;
+                        }
+                        sr[c][i] = __float_as_uint(x);
+                        mx = fmaxf(mx, x);
+                    }
+                }
+                // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^RESCALE_THRESHOLD
+                float corr = 1.f;
+                bool need = false;
+                if (mx > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
+                    const float m_new = mx == -INFINITY ? m_run : mx;
+                    if (m_run != -INFINITY && m_new != m_run) { corr = exp2f(m_run - m_new); need = true; }
+                    m_run = m_new;
+                }
+                const float m_use = m_run == -INFINITY ? 0.f : m_run;
+                // the P buffer and O are free once PV of the previous tile has completed
+                if (j > 0) mbar_wait(pv_done, (pvc - 1) & 1, 90);
+                if (j > 0 && __any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int c = 0; c < DH / 32; ++c) {
+                        uint32_t orow[32];
+                        tmem_ld_32x32(tmem_base + lane_addr + TM_O + c * 32, orow);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * corr);
+                        tmem_st_32x32(tmem_base + lane_addr + TM_O + c * 32, orow);
+                    }
+                    tmem_st_wait();
+                }
+                // P = exp2(s - m) (bf16) written as a K-major 128B-swizzled A operand: chunk = 64 keys, row pitch 128 B
+                float rs = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = exp2f(__uint_as_float(sr[c][u * 8 + 2 * e]) - m_use);
+                            const float p1 = exp2f(__uint_as_float(sr[c][u * 8 + 2 * e + 1]) - m_use);
+                            rs += p0 + p1;
+                            w4[e] = pack_bf16x2(p0, p1);
+                        }
+                        const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 64-key chunk (c >> 1)
+                        *reinterpret_cast<uint4*>(sP + (c >> 1) * CHUNK_BYTES + r * 128 + ((unit ^ (r & 7)) << 4)) =
+                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                l_run = l_run * corr + rs;
+                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(p_full);
+                ++pvc;  // PV_j will be issued for this tile
+            }
+            // ---- epilogue: wait for the last PV, normalise, store O and LSE
+            mbar_wait(pv_done, (pvc - 1) & 1, 95);
+            tcgen05_fence_after();
+            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            const bool valid = qrow < p.S;
+            __nv_bfloat16* op = p.o + ((long long)b * p.S + qrow) * p.ldo + (long long)h * DH;
+#pragma unroll
+            for (int c = 0; c < DH / 32; ++c) {
+                uint32_t orow[32];
+                tmem_ld_32x32(tmem_base + lane_addr + TM_O + c * 32, orow);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 v;
+                        v.x = pack_bf16x2(__uint_as_float(orow[u * 8 + 0]) * inv, __uint_as_float(orow[u * 8 + 1]) * inv);
+                        v.y = pack_bf16x2(__uint_as_float(orow[u * 8 + 2]) * inv, __uint_as_float(orow[u * 8 + 3]) * inv);
+                        v.z = pack_bf16x2(__uint_as_float(orow[u * 8 + 4]) * inv, __uint_as_float(orow[u * 8 + 5]) * inv);
+                        v.w = pack_bf16x2(__uint_as_float(orow[u * 8 + 6]) * inv, __uint_as_float(orow[u * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(op + c * 32 + u * 8) = v;
+                    }
+                }
+            }
+            if (valid && p.lse) p.lse[((long long)b * p.H + h) * p.S + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * LN2_F : -INFINITY;
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane_idx == 0) mbar_arrive(o_free);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int DH>
+static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t s) {
+    constexpr int smem_bytes = (DH / 64) * 128 * 128 * 5 + 2 * 128 * 128 + 256 + 1024;
+    auto kern = attn_fwd_tc_kernel<DH>;
+    static bool configured = false;
+    if (!configured) {
+        VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int grid = std::min(p.n_work, num_sms());
+    kern<<<grid, NTHREADS, smem_bytes, s>>>(tq, tk, tv, p);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+}  // namespace attn_tc
+}  // namespace vlb
+
+extern "C" int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  void* out, int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH,
+                                  int head_dim, int causal, float scale, void* stream) {
+    using namespace vlb;
+    VLB_REQUIRE(q && k && v && out, "attn_fwd_tc: null pointer");
+    VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_fwd_tc: bad B/S/H/KVH");
+    VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_fwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
+    VLB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attn_fwd_tc: row strides must be multiples of 8");
+    const uint64_t rows = (uint64_t)B * S;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = gemm::get_tensor_map(q, (uint64_t)H * head_dim, rows, ldq, 64, 128, &tq))) return rc;
+    if ((rc = gemm::get_tensor_map(k, (uint64_t)KVH * head_dim, rows, ldk, 64, 128, &tk))) return rc;
+    if ((rc = gemm::get_tensor_map(v, (uint64_t)KVH * head_dim, rows, ldv, 64, 128, &tv))) return rc;
+    attn_tc::Params p{};
+    p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.seqlens = seqlens;
+    p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
+    p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
+    p.n_work = p.n_qb * H * B;
+    if (head_dim == 64) return attn_tc::launch<64>(tq, tk, tv, p, as_stream(stream));
+    return attn_tc::launch<128>(tq, tk, tv, p, as_stream(stream));
+}

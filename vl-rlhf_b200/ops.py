@@ -321,11 +321,29 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     return out
 
 
+def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
+                seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool,
+                scale: float):
+    """tcgen05/TMEM/TMA forward; same contract as attn_fwd."""
+    check(_L.vlb200_attn_fwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                out.stride(0), _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale,
+                                _stream()))
+    return out
+
+
 def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
     check(_L.vlb200_attn_bwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
                              _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk),
                              dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal),
                              scale, _stream()))
+
+
+def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
+    """tcgen05/TMEM/TMA backward; same contract as attn_bwd."""
+    check(_L.vlb200_attn_bwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
+                                _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim,
+                                int(causal), scale, _stream()))
 
 
 # ------------------------------------------------------------------------------------------
