@@ -31,6 +31,19 @@ elif which == "attn":
         ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, sl, B, S, H, H, dh, True, sc)
         ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, dout, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
                      dqkv[:, 2 * d:], sl, B, S, H, H, dh, True, sc)
+elif which == "attn_tc":
+    qkv = torch.randn(T, 3 * d, device=dev).to(bf)
+    out = torch.empty(T, d, dtype=bf, device=dev)
+    lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+    sl = torch.tensor([1599, 1400, 1599, 1500, 1599, 1300, 1450, 1599], dtype=torch.int32, device=dev)
+    sc = 1 / math.sqrt(dh)
+    dout = torch.randn(T, d, device=dev).to(bf)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    for _ in range(3):
+        ops.attn_fwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, sl, B, S, H, H, dh, True, sc)
+        ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, dout, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
+                        dqkv[:, 2 * d:], sl, B, S, H, H, dh, True, sc)
 elif which == "logps":
     R = 8 * 1023
     logits = torch.randn(R, V, device=dev)
