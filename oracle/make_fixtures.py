@@ -245,9 +245,13 @@ def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config1", action="store_true")
+    ap.add_argument("--config1-bf16", dest="config1_bf16", action="store_true")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if args.config1_bf16:
+        config1_reference_bf16()
+        return
     if args.config1:
         # BASELINE.json configs[0]: LLaVA-1.5-7B shapes, 2 pairs, text 128 (+575 -> 703), fp32 CPU
         g45_llava("g5_config1_7b", R.LLAVA15_7B, 2, 128, 32, 0, ddpo=False)
@@ -257,6 +261,29 @@ def main():
     g3_ddpo()
     g45_llava("g4_tiny", R.TINY, 2, 24, 8, 0, ddpo=True)
     g45_llava("g4_small", R.SMALL, 2, 96, 24, 0, ddpo=True)
+
+
+
+
+def config1_reference_bf16():
+    """The reference's OWN bf16 path (model weights + activations bf16, as `torch_dtype=bfloat16` in
+    utils/auto_load.py:510,535) on the config-1 inputs: its deviation from the fp32 run is the noise floor of the
+    path itself and is stored next to the fp32 golden values."""
+    cfg, seed = R.LLAVA15_7B, 0
+    path = os.path.join(GOLDEN, "g5_config1_7b.npz")
+    d = dict(np.load(path))
+    batch = R.make_batch(cfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), seed)
+    batch["img_input_dict"]["pixel_values"] = batch["img_input_dict"]["pixel_values"].to(torch.bfloat16)
+    t0 = time.time()
+    m = build_reference_model(cfg, streamed_weights(cfg, seed, "policy"))
+    m = m.to(torch.bfloat16)
+    print(f"[config1-bf16] model ready {time.time() - t0:.1f}s", flush=True)
+    logps, o = reference_concatenated_forward(m, cfg, batch, "sigmoid")
+    d["policy_logps_refdtype_bf16"] = logps.float().numpy()
+    print("[config1-bf16] reference bf16 logps", d["policy_logps_refdtype_bf16"], "fp32", d["policy_logps"],
+          f"{time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(path, **d)
+
 
 
 if __name__ == "__main__":

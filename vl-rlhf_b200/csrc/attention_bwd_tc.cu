@@ -44,6 +44,11 @@ struct Params {
 };
 
 __device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int MODE>
 __device__ __forceinline__ void item_coords(const Params& p, int w, int& b, int& hx, int& xb) {
@@ -91,9 +96,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     uint8_t* sX1 = smem;
     uint8_t* sX2 = sX1 + X_BYTES;
     uint8_t* sY = sX2 + X_BYTES;                 // NST stages of (Y1, Y2)
-    uint8_t* sE1 = sY + NST * 2 * Y_BYTES;
-    uint8_t* sE2 = sE1 + E_BYTES;
-    float* sLse = reinterpret_cast<float*>(sE2 + E_BYTES);  // [2][64] (MODE 0)
+    uint8_t* sE = sY + NST * 2 * Y_BYTES;        // 2 buffers of (E1, E2)
+    float* sLse = reinterpret_cast<float*>(sE + 4 * E_BYTES);  // [2][64] (MODE 0)
     float* sDelta = sLse + 2 * BY;                           // [2][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BY);
     uint64_t* x_full = bars + 0;
@@ -102,9 +106,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     uint64_t* y_empty = bars + 2 + NST;      // [NST]
     uint64_t* t_full = bars + 2 + 2 * NST;   // [2]
     uint64_t* t_empty = t_full + 2;          // [2]
-    uint64_t* e_full = t_empty + 2;
-    uint64_t* e_done = e_full + 1;
-    uint64_t* acc_free = e_done + 1;
+    uint64_t* e_full = t_empty + 2;          // [2]
+    uint64_t* e_done = e_full + 2;           // [2]
+    uint64_t* acc_free = e_done + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_free + 1);
 
     const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
@@ -113,7 +117,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int i = 0; i < NST; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        mbar_init(e_full, 4); mbar_init(e_done, 1); mbar_init(acc_free, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], 4); mbar_init(&e_done[i], 1); }
+        mbar_init(acc_free, 4);
         fence_barrier_init();
     }
     if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -174,47 +179,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 mbar_wait(x_full, item & 1, 30);
                 tcgen05_fence_after();
                 const uint32_t y0 = yc;
-                for (int t = 0; t <= n; ++t) {
-                    if (t < n) {
-                        const uint32_t yi = y0 + t, st = yi % NST, tb = tc & 1;
-                        mbar_wait(&y_full[st], (yi / NST) & 1, 40 + st);
-                        mbar_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1, 50 + tb);
-                        tcgen05_fence_after();
-                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                // dynamic issue order (see attention_tc.cu): score MMAs for tile ts as soon as its streamed tile and a
+                // TMEM score buffer are ready, otherwise the accumulate MMAs of tile ta once its E operands are published
+                int ts = 0, ta = 0;
+                long long t_spin = 0;
+                while (ta < n) {
+                    bool progressed = false;
+                    if (ts < n) {
+                        const uint32_t yi = y0 + ts, st = yi % NST, tb = tc & 1;
+                        if (mbar_try_wait(&y_full[st], (yi / NST) & 1) && mbar_try_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1)) {
+                            tcgen05_fence_after();
+                            const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
 #pragma unroll
-                        for (int k = 0; k < DH / 16; ++k) {
-                            const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
-                            umma_f16_ss(tmem_base + TM_T1 + tb * BY, make_smem_desc_sw128(smem_u32(sX1) + xo, 1024, 0),
-                                        make_smem_desc_sw128(y1 + yo, 1024, 0), idesc_t, k != 0);
-                        }
+                            for (int k = 0; k < DH / 16; ++k) {
+                                const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
+                                umma_f16_ss(tmem_base + TM_T1 + tb * BY, make_smem_desc_sw128(smem_u32(sX1) + xo, 1024, 0),
+                                            make_smem_desc_sw128(y1 + yo, 1024, 0), idesc_t, k != 0);
+                            }
 #pragma unroll
-                        for (int k = 0; k < DH / 16; ++k) {
-                            const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
-                            umma_f16_ss(tmem_base + TM_T2 + tb * BY, make_smem_desc_sw128(smem_u32(sX2) + xo, 1024, 0),
-                                        make_smem_desc_sw128(y2 + yo, 1024, 0), idesc_t, k != 0);
+                            for (int k = 0; k < DH / 16; ++k) {
+                                const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
+                                umma_f16_ss(tmem_base + TM_T2 + tb * BY, make_smem_desc_sw128(smem_u32(sX2) + xo, 1024, 0),
+                                            make_smem_desc_sw128(y2 + yo, 1024, 0), idesc_t, k != 0);
+                            }
+                            umma_commit(&t_full[tb]);
+                            if (ts == n - 1) umma_commit(x_empty);
+                            ++tc; ++ts;
+                            progressed = true;
                         }
-                        umma_commit(&t_full[tb]);
-                        if (t == n - 1) umma_commit(x_empty);
-                        ++tc;
                     }
-                    if (t >= 1) {
-                        const uint32_t u = t - 1, yi = y0 + u, st = yi % NST;
-                        if (u == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);
-                        mbar_wait(e_full, ec & 1, 70);
-                        tcgen05_fence_after();
-                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                    if (!progressed && ta < ts) {
+                        const uint32_t yi = y0 + ta, st = yi % NST, eb = ec & 1;
+                        if (mbar_try_wait(&e_full[eb], (ec >> 1) & 1)) {
+                            if (ta == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);
+                            tcgen05_fence_after();
+                            const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                            const uint32_t e1 = smem_u32(sE + eb * 2 * E_BYTES), e2 = e1 + E_BYTES;
 #pragma unroll
-                        for (int k = 0; k < BY / 16; ++k) {
-                            if (MODE == 0)  // dV += P^T dO
-                                umma_f16_ss(tmem_base + TM_A1, make_smem_desc_sw128(smem_u32(sE1) + k * 32, 1024, 0),
-                                            make_smem_desc_sw128(y2 + k * 2048, 1024, YCH), idesc_a, (u != 0 || k != 0) ? 1u : 0u);
-                            // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
-                            umma_f16_ss(tmem_base + TM_A2, make_smem_desc_sw128(smem_u32(sE2) + k * 32, 1024, 0),
-                                        make_smem_desc_sw128(y1 + k * 2048, 1024, YCH), idesc_a, (u != 0 || k != 0) ? 1u : 0u);
+                            for (int k = 0; k < BY / 16; ++k) {
+                                if (MODE == 0)  // dV += P^T dO
+                                    umma_f16_ss(tmem_base + TM_A1, make_smem_desc_sw128(e1 + k * 32, 1024, 0),
+                                                make_smem_desc_sw128(y2 + k * 2048, 1024, YCH), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
+                                // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
+                                umma_f16_ss(tmem_base + TM_A2, make_smem_desc_sw128(e2 + k * 32, 1024, 0),
+                                            make_smem_desc_sw128(y1 + k * 2048, 1024, YCH), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
+                            }
+                            umma_commit(&e_done[eb]);
+                            umma_commit(&y_empty[st]);
+                            ++ec; ++ta;
+                            progressed = true;
                         }
-                        umma_commit(e_done);
-                        umma_commit(&y_empty[st]);
-                        ++ec;
+                    }
+                    if (!progressed) {
+                        if (t_spin == 0) t_spin = clock64();
+                        else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
+                            printf("[vlb200] attn_bwd_tc MMA watchdog: block %d mode %d ts %d ta %d n %d\n", blockIdx.x, MODE, ts, ta, n);
+                            __trap();
+                        }
+                    } else {
+                        t_spin = 0;
                     }
                 }
                 yc += n;
@@ -282,15 +305,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                         const float dl = MODE == 0 ? sDelta[tb * BY + col] : row_delta;
                         const float s = __uint_as_float(t1[col >> 5][col & 31]);
                         const float dp = __uint_as_float(t2[col >> 5][col & 31]);
-                        const float pr = ok ? exp2f(fmaf(s, sl2, -l2)) : 0.f;
+                        const float pr = ok ? ex2_approx(fmaf(s, sl2, -l2)) : 0.f;
                         pv[e] = pr;
                         dv[e] = pr * (dp - dl) * p.scale;
                     }
                     e1[c >> 1] = pack_bf16x2(pv[0], pv[1]);
                     e2[c >> 1] = pack_bf16x2(dv[0], dv[1]);
                 }
-                // E buffers are free once the accumulate MMAs of the previous tile have completed
-                if (ec > 0) mbar_wait(e_done, (ec - 1) & 1, 90);
+                // this E buffer is free once the accumulate MMAs of its previous use (two tiles back) have completed
+                const uint32_t eb = ec & 1;
+                if ((ec >> 1) > 0) mbar_wait(&e_done[eb], ((ec >> 1) - 1) & 1, 90 + eb);
+                uint8_t* sE1 = sE + eb * 2 * E_BYTES;
+                uint8_t* sE2 = sE1 + E_BYTES;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const uint32_t off = r * 128 + ((u ^ (r & 7)) << 4);
@@ -300,12 +326,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane_idx == 0) mbar_arrive(e_full);
+                if (lane_idx == 0) mbar_arrive(&e_full[eb]);
                 ++ec;
             }
             // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work)
-            if (n > 0) {
-                mbar_wait(e_done, (ec - 1) & 1, 95);
+            if (n > 0) {  // the commit of the last tile's accumulate MMAs covers every earlier tcgen05 op of the MMA thread
+                mbar_wait(&e_done[(ec - 1) & 1], ((ec - 1) >> 1) & 1, 95);
                 tcgen05_fence_after();
             }
             const bool valid = xrow < p.S;
@@ -355,7 +381,7 @@ template <int DH, int MODE>
 static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, const Params& p,
                   cudaStream_t s) {
     constexpr int NCH = DH / 64;
-    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + 2 * BX * 128 + 4 * BY * 4 + 256 + 1024;
+    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + 4 * BX * 128 + 4 * BY * 4 + 256 + 1024;
     auto kern = attn_bwd_tc_kernel<DH, MODE>;
     static bool configured = false;
     if (!configured) {

@@ -66,6 +66,14 @@ __device__ __forceinline__ int num_kv_tiles(const Params& p, int b, int qb) {
     return (kmax + BN - 1) / BN;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr int NSTAGE = 3;  // K/V ring depth
+
 template <int DH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -75,37 +83,35 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     constexpr int Q_BYTES = NCH * CHUNK_BYTES;
     constexpr int KV_BYTES = NCH * CHUNK_BYTES;  // one K or V tile
     constexpr int P_BYTES = 2 * CHUNK_BYTES;     // [128 q][128 keys] bf16
+    constexpr int KP_BYTES = KV_BYTES > P_BYTES ? KV_BYTES : P_BYTES;  // K_j slot, reused for P_j once S_j has retired
+    constexpr int STAGE_BYTES = KP_BYTES + KV_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t TM_S = 0, TM_O = 256;     // S buffers at columns 0 / 128, O at 256
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + Q_BYTES;            // 2 stages
-    uint8_t* sV = sK + 2 * KV_BYTES;       // 2 stages
-    uint8_t* sP = sV + 2 * KV_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint8_t* sStage = sQ + Q_BYTES;  // NSTAGE x { KP slot, V slot }
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + NSTAGE * STAGE_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
-    uint64_t* kv_full = bars + 2;   // [2]
-    uint64_t* kv_empty = bars + 4;  // [2]
-    uint64_t* s_full = bars + 6;    // [2]
-    uint64_t* s_empty = bars + 8;   // [2]
-    uint64_t* p_full = bars + 10;
-    uint64_t* pv_done = bars + 11;
-    uint64_t* o_free = bars + 12;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* kv_full = bars + 2;              // [NSTAGE]
+    uint64_t* kv_empty = kv_full + NSTAGE;     // [NSTAGE]
+    uint64_t* p_full = kv_empty + NSTAGE;      // [NSTAGE]
+    uint64_t* s_full = p_full + NSTAGE;        // [2]
+    uint64_t* s_empty = s_full + 2;            // [2]
+    uint64_t* pv_done = s_empty + 2;
+    uint64_t* o_free = pv_done + 1;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
 
     const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
 
     if (warp_idx == 0 && lane_idx == 0) {
         prefetch_tensormap(&tma_q); prefetch_tensormap(&tma_k); prefetch_tensormap(&tma_v);
         mbar_init(q_full, 1); mbar_init(q_empty, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-        }
-        mbar_init(p_full, 4); mbar_init(pv_done, 1); mbar_init(o_free, 4);
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&p_full[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+        mbar_init(pv_done, 1); mbar_init(o_free, 4);
         fence_barrier_init();
     }
     if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -117,7 +123,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     if (warp_idx == 0) {
         // ===================== TMA producer =====================
         if (lane_idx == 0) {
-            uint32_t item = 0, kvc = 0;
+            uint32_t item = 0, g = 0;  // g = global KV-tile counter (ring position)
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
                 int b, h, qb;
                 work_coords(p, w, b, h, qb);
@@ -128,14 +134,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 mbar_arrive_expect_tx(q_full, Q_BYTES);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_q, q_full, sQ + c * CHUNK_BYTES, h * DH + c * 64, row0 + qb * BM);
-                for (int j = 0; j < n_tiles; ++j, ++kvc) {
-                    const int st = kvc & 1;
-                    mbar_wait(&kv_empty[st], ((kvc >> 1) & 1) ^ 1, 20 + st);
+                for (int j = 0; j < n_tiles; ++j, ++g) {
+                    const uint32_t st = g % NSTAGE;
+                    mbar_wait(&kv_empty[st], ((g / NSTAGE) & 1) ^ 1, 20 + st);  // PV of the tile 3 back retired (K/P and V slots free)
                     mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
+                    uint8_t* kp = sStage + st * STAGE_BYTES;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        tma_load_2d(&tma_k, &kv_full[st], sK + st * KV_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
-                        tma_load_2d(&tma_v, &kv_full[st], sV + st * KV_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
+                        tma_load_2d(&tma_k, &kv_full[st], kp + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
+                        tma_load_2d(&tma_v, &kv_full[st], kp + KP_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
                     }
                 }
             }
@@ -145,50 +152,65 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         if (lane_idx == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
-            uint32_t item = 0, kvc = 0, sc = 0, pc = 0;
+            uint32_t item = 0, g0 = 0, sc = 0;
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
                 int b, h, qb;
                 work_coords(p, w, b, h, qb);
                 const int n_tiles = num_kv_tiles(p, b, qb);
                 mbar_wait(q_full, item & 1, 30);
                 tcgen05_fence_after();
-                const uint32_t kv0 = kvc;
-                for (int j = 0; j <= n_tiles; ++j) {
-                    if (j < n_tiles) {
-                        // ---- S_j = Q K_j^T into S buffer (sc & 1)
-                        const uint32_t kvi = kv0 + j, st = kvi & 1, sb = sc & 1;
-                        mbar_wait(&kv_full[st], (kvi >> 1) & 1, 40 + st);
-                        mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1, 50 + sb);
-                        tcgen05_fence_after();
+                // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
+                // published -- neither blocks the other (a blocked in-order loop exposed the full TMA latency per tile)
+                int js = 0, jp = 0;
+                long long t_spin = 0;
+                while (jp < n_tiles) {
+                    bool progressed = false;
+                    if (js < n_tiles) {
+                        const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
+                        if (mbar_try_wait(&kv_full[st], (g / NSTAGE) & 1) && mbar_try_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1)) {
+                            tcgen05_fence_after();
+                            const uint32_t kbase = smem_u32(sStage + st * STAGE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < DH / 16; ++k) {
-                            const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-                            const uint64_t a = make_smem_desc_sw128(smem_u32(sQ) + off, 1024, 0);
-                            const uint64_t bd = make_smem_desc_sw128(smem_u32(sK + st * KV_BYTES) + off, 1024, 0);
-                            umma_f16_ss(tmem_base + TM_S + sb * BN, a, bd, idesc_s, k != 0);
+                            for (int k = 0; k < DH / 16; ++k) {
+                                const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+                                umma_f16_ss(tmem_base + TM_S + sb * BN, make_smem_desc_sw128(smem_u32(sQ) + off, 1024, 0),
+                                            make_smem_desc_sw128(kbase + off, 1024, 0), idesc_s, k != 0);
+                            }
+                            umma_commit(&s_full[sb]);
+                            if (js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
+                            ++sc; ++js;
+                            progressed = true;
                         }
-                        umma_commit(&s_full[sb]);
-                        if (j == n_tiles - 1) umma_commit(q_empty);  // Q tile no longer needed once S of the last tile retires
-                        ++sc;
                     }
-                    if (j >= 1) {
-                        // ---- O (+)= P_{j-1} V_{j-1}
-                        const uint32_t t = j - 1, kvi = kv0 + t, st = kvi & 1;
-                        if (t == 0) mbar_wait(o_free, (item & 1) ^ 1, 60);  // epilogue of the previous item has read O
-                        mbar_wait(p_full, pc & 1, 70);
-                        tcgen05_fence_after();
+                    if (!progressed && jp < js) {
+                        const uint32_t g = g0 + jp, st = g % NSTAGE;
+                        if (mbar_try_wait(&p_full[st], (g / NSTAGE) & 1)) {
+                            if (jp == 0) mbar_wait(o_free, (item & 1) ^ 1, 60);  // epilogue of the previous item has read O
+                            tcgen05_fence_after();
+                            const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
 #pragma unroll
-                        for (int k = 0; k < BN / 16; ++k) {
-                            const uint64_t a = make_smem_desc_sw128(smem_u32(sP) + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 1024, 0);
-                            const uint64_t bd = make_smem_desc_sw128(smem_u32(sV + st * KV_BYTES) + k * (16 * 128), 1024, CHUNK_BYTES);
-                            umma_f16_ss(tmem_base + TM_O, a, bd, idesc_o, (t != 0 || k != 0) ? 1u : 0u);
+                            for (int k = 0; k < BN / 16; ++k) {
+                                umma_f16_ss(tmem_base + TM_O, make_smem_desc_sw128(pbase + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 1024, 0),
+                                            make_smem_desc_sw128(vbase + k * (16 * 128), 1024, CHUNK_BYTES), idesc_o,
+                                            (jp != 0 || k != 0) ? 1u : 0u);
+                            }
+                            umma_commit(pv_done);
+                            umma_commit(&kv_empty[st]);
+                            ++jp;
+                            progressed = true;
                         }
-                        umma_commit(pv_done);
-                        umma_commit(&kv_empty[st]);
-                        ++pc;
+                    }
+                    if (!progressed) {
+                        if (t_spin == 0) t_spin = clock64();
+                        else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
+                            printf("[vlb200] attn_fwd_tc MMA watchdog: block %d js %d jp %d n %d\n", blockIdx.x, js, jp, n_tiles);
+                            __trap();
+                        }
+                    } else {
+                        t_spin = 0;
                     }
                 }
-                kvc += n_tiles;
+                g0 += n_tiles;
             }
         }
     } else {
@@ -197,7 +219,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const int r = quad * 32 + lane_idx;  // row inside the Q tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        uint32_t item = 0, sc = 0, pvc = 0;  // pvc = number of PV MMAs whose completion this thread has accounted for
+        uint32_t item = 0, sc = 0, g = 0;  // g = global tile counter (== number of PVs issued for earlier tiles)
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
             int b, h, qb;
             work_coords(p, w, b, h, qb);
@@ -206,8 +228,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             kv_len = max(kv_len, 1);
             const int qrow = qb * BM + r;
             float m_run = -INFINITY, l_run = 0.f;
-            for (int j = 0; j < n_tiles; ++j, ++sc) {
-                const uint32_t sb = sc & 1;
+            for (int j = 0; j < n_tiles; ++j, ++sc, ++g) {
+                const uint32_t sb = sc & 1, st = g % NSTAGE;
                 mbar_wait(&s_full[sb], (sc >> 1) & 1, 80 + sb);
                 tcgen05_fence_after();
                 uint32_t sr[4][32];
@@ -220,30 +242,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 const int k0 = j * BN;
                 const bool need_mask = (k0 + BN > kv_len) || (p.causal && k0 + BN > qb * BM);
                 float mx = -INFINITY;
+                if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(sr[c][i]) * sl2;
-                        if (need_mask) {
+                        for (int i = 0; i < 32; ++i) {
                             const int key = k0 + c * 32 + i;
-                            if (key >= kv_len || (p.causal && key > qrow)) x = -INFINITY;
+                            if (key >= kv_len || (p.causal && key > qrow)) sr[c][i] = 0xff800000u;  // -inf
+                            mx = fmaxf(mx, __uint_as_float(sr[c][i]));
                         }
-                        sr[c][i] = __float_as_uint(x);
-                        mx = fmaxf(mx, x);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
                     }
                 }
+                mx *= sl2;  // scale > 0: max commutes with the scaling (log2 domain from here on)
                 // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^RESCALE_THRESHOLD
                 float corr = 1.f;
                 bool need = false;
                 if (mx > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
                     const float m_new = mx == -INFINITY ? m_run : mx;
-                    if (m_run != -INFINITY && m_new != m_run) { corr = exp2f(m_run - m_new); need = true; }
+                    if (m_run != -INFINITY && m_new != m_run) { corr = ex2_approx(m_run - m_new); need = true; }
                     m_run = m_new;
                 }
-                const float m_use = m_run == -INFINITY ? 0.f : m_run;
-                // the P buffer and O are free once PV of the previous tile has completed
-                if (j > 0) mbar_wait(pv_done, (pvc - 1) & 1, 90);
+                const float neg_m = m_run == -INFINITY ? 0.f : -m_run;
+                // P = exp2(s*c - m) (bf16) into the K slot of this stage (K_j is dead: S_j has retired), laid out as a
+                // K-major 128B-swizzled A operand: chunk = 64 keys, row pitch 128 B
+                uint8_t* sP = sStage + st * STAGE_BYTES;
+                float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][u * 8 + 2 * e]), sl2, neg_m));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][u * 8 + 2 * e + 1]), sl2, neg_m));
+                            rs0 += p0;
+                            rs1 += p1;
+                            w4[e] = pack_bf16x2(p0, p1);
+                        }
+                        const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 64-key chunk (c >> 1)
+                        *reinterpret_cast<uint4*>(sP + (c >> 1) * CHUNK_BYTES + r * 128 + ((unit ^ (r & 7)) << 4)) =
+                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                l_run = l_run * corr + (rs0 + rs1);
+                // publish P only after PV of the previous tile has retired: keeps the pv_done phase bookkeeping exact
+                // (a waiter never runs two phases ahead) and orders the (rare) O correction before the next PV
+                if (j > 0) mbar_wait(pv_done, (g - 1) & 1, 90);
                 if (j > 0 && __any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
                     tcgen05_fence_after();
 #pragma unroll
@@ -257,34 +308,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     }
                     tmem_st_wait();
                 }
-                // P = exp2(s - m) (bf16) written as a K-major 128B-swizzled A operand: chunk = 64 keys, row pitch 128 B
-                float rs = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint32_t w4[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float p0 = exp2f(__uint_as_float(sr[c][u * 8 + 2 * e]) - m_use);
-                            const float p1 = exp2f(__uint_as_float(sr[c][u * 8 + 2 * e + 1]) - m_use);
-                            rs += p0 + p1;
-                            w4[e] = pack_bf16x2(p0, p1);
-                        }
-                        const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 64-key chunk (c >> 1)
-                        *reinterpret_cast<uint4*>(sP + (c >> 1) * CHUNK_BYTES + r * 128 + ((unit ^ (r & 7)) << 4)) =
-                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    }
-                }
-                l_run = l_run * corr + rs;
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane_idx == 0) mbar_arrive(p_full);
-                ++pvc;  // PV_j will be issued for this tile
+                if (lane_idx == 0) mbar_arrive(&p_full[st]);
             }
             // ---- epilogue: wait for the last PV, normalise, store O and LSE
-            mbar_wait(pv_done, (pvc - 1) & 1, 95);
+            mbar_wait(pv_done, (g - 1) & 1, 95);
             tcgen05_fence_after();
             const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
             const bool valid = qrow < p.S;
@@ -322,7 +352,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 
 template <int DH>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t s) {
-    constexpr int smem_bytes = (DH / 64) * 128 * 128 * 5 + 2 * 128 * 128 + 256 + 1024;
+    constexpr int kv_bytes = (DH / 64) * 128 * 128;
+    constexpr int kp_bytes = kv_bytes > 2 * 128 * 128 ? kv_bytes : 2 * 128 * 128;
+    constexpr int smem_bytes = kv_bytes + NSTAGE * (kp_bytes + kv_bytes) + 256 + 1024;
     auto kern = attn_fwd_tc_kernel<DH>;
     static bool configured = false;
     if (!configured) {
