@@ -448,3 +448,7 @@ def cast_bf16_to_f32(src, dst):
     dst.copy_(src.float())
     _c()
     return dst
+
+
+attn_fwd_tc = attn_fwd  # the tcgen05 kernels have the same contract as the mma.sync ones
+attn_bwd_tc = attn_bwd

@@ -29,7 +29,8 @@ using namespace ptx;
 constexpr int BX = 128;  // stationary rows
 constexpr int BY = 64;   // streamed rows
 constexpr int NST = 3;   // streamed-tile ring depth
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;  // TMA warp, MMA warp, 8 elementwise warps (two per TMEM lane quadrant)
+constexpr int NEW = 8;         // elementwise warps
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 struct Params {
@@ -116,9 +117,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
         prefetch_tensormap(&tma_x1); prefetch_tensormap(&tma_x2); prefetch_tensormap(&tma_y1); prefetch_tensormap(&tma_y2);
         mbar_init(x_full, 1); mbar_init(x_empty, 1);
         for (int i = 0; i < NST; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], 4); mbar_init(&e_done[i], 1); }
-        mbar_init(acc_free, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NEW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], NEW); mbar_init(&e_done[i], 1); }
+        mbar_init(acc_free, NEW);
         fence_barrier_init();
     }
     if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
@@ -245,10 +246,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             }
         }
     } else {
-        // ===================== elementwise + epilogue (4 warps, one stationary row per thread) =====================
+        // ===================== elementwise + epilogue (8 warps: row = TMEM lane, two warps split the columns) ==========
         const int quad = warp_idx & 3;
+        const int half = (warp_idx - 2) >> 2;  // 0: columns [0,32) of a score tile, 1: columns [32,64)
         const int r = quad * 32 + lane_idx;
-        const int tid_e = threadIdx.x - 64;  // 0..127 inside the elementwise group
+        const int tid_e = threadIdx.x - 64;    // 0..255 inside the elementwise group
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
         uint32_t tc = 0, ec = 0;
@@ -259,58 +261,81 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             const int n = (ye - yb) * reps;
             int kv_len = p.seqlens ? p.seqlens[b] : p.S;
             kv_len = max(min(kv_len, p.S), 0);
-            const int xrow = xb * BX + r;  // MODE 0: key index ; MODE 1: query index
+            const int x0 = xb * BX;
+            const int xrow = x0 + r;  // MODE 0: key index ; MODE 1: query index
             float row_lse2 = 0.f, row_delta = 0.f;
             if (MODE == 1 && xrow < p.S) {
                 const long long si = ((long long)b * p.H + hx) * p.S + xrow;
                 row_lse2 = p.lse[si] * LOG2E_F;
                 row_delta = p.delta[si];
             }
+            // MODE 0: per-column (query) statistics are staged through smem one tile ahead
+            float nl = 0.f, nd = 0.f;
+            auto fetch_stats = [&](int t) {
+                if (MODE == 0 && tid_e < BY && t < n) {
+                    const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                    const int q = yt * BY + tid_e;
+                    const long long si = ((long long)b * p.H + (hx * group + rep)) * p.S + q;
+                    nl = q < p.S ? p.lse[si] * LOG2E_F : 0.f;
+                    nd = q < p.S ? p.delta[si] : 0.f;
+                }
+            };
+            if (MODE == 0 && n > 0) {
+                fetch_stats(0);
+                if (tid_e < BY) { sLse[(tc & 1) * BY + tid_e] = nl; sDelta[(tc & 1) * BY + tid_e] = nd; }
+            }
             for (int t = 0; t < n; ++t, ++tc) {
                 const uint32_t tb = tc & 1;
-                const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                const int yt = yb + t % (ye - yb);
                 const int y0 = yt * BY;
-                if (MODE == 0) {  // per-column (query) statistics of this streamed tile -> smem
-                    if (tid_e < BY) {
-                        const int q = y0 + tid_e;
-                        const int hq = hx * group + rep;
-                        const long long si = ((long long)b * p.H + hq) * p.S + q;
-                        sLse[tb * BY + tid_e] = q < p.S ? p.lse[si] * LOG2E_F : 0.f;
-                        sDelta[tb * BY + tid_e] = q < p.S ? p.delta[si] : 0.f;
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (MODE == 0) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");  // statistics of tile t are visible
+                    fetch_stats(t + 1);                              // global loads for tile t+1 fly during this tile
                 }
                 mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
                 tcgen05_fence_after();
-                uint32_t t1[2][32], t2[2][32];
-                tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY, t1[0]);
-                tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + 32, t1[1]);
-                tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY, t2[0]);
-                tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + 32, t2[1]);
+                uint32_t t1[32], t2[32];
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, t1);
+                tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, t2);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&t_empty[tb]);
-                uint32_t e1[32], e2[32];
+                // mask only tiles that touch the causal diagonal or the end of the valid range
+                const int ymax = y0 + BY - 1;
+                bool need_mask;
+                if (MODE == 0) need_mask = ymax >= kv_len || x0 + BX > kv_len || (p.causal && x0 + BX - 1 > y0);
+                else need_mask = ymax >= kv_len || x0 + BX > kv_len || (p.causal && ymax > x0);
+                const float* cl = sLse + tb * BY + half * 32;
+                const float* cd = sDelta + tb * BY + half * 32;
+                uint32_t e1[16], e2[16];
 #pragma unroll
-                for (int c = 0; c < BY; c += 2) {
-                    float pv[2], dv[2];
+                for (int c4 = 0; c4 < 32; c4 += 4) {
+                    float l4[4], d4[4];
+                    if (MODE == 0) {
+                        const float4 a = *reinterpret_cast<const float4*>(cl + c4);
+                        const float4 d = *reinterpret_cast<const float4*>(cd + c4);
+                        l4[0] = a.x; l4[1] = a.y; l4[2] = a.z; l4[3] = a.w;
+                        d4[0] = d.x; d4[1] = d.y; d4[2] = d.z; d4[3] = d.w;
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int col = c + e;
-                        const int key = MODE == 0 ? xrow : y0 + col;
-                        const int qi = MODE == 0 ? y0 + col : xrow;
-                        const bool ok = key < kv_len && qi < kv_len && (!p.causal || key <= qi);
-                        const float l2 = MODE == 0 ? sLse[tb * BY + col] : row_lse2;
-                        const float dl = MODE == 0 ? sDelta[tb * BY + col] : row_delta;
-                        const float s = __uint_as_float(t1[col >> 5][col & 31]);
-                        const float dp = __uint_as_float(t2[col >> 5][col & 31]);
-                        const float pr = ok ? ex2_approx(fmaf(s, sl2, -l2)) : 0.f;
-                        pv[e] = pr;
-                        dv[e] = pr * (dp - dl) * p.scale;
+                        for (int e = 0; e < 4; ++e) { l4[e] = row_lse2; d4[e] = row_delta; }
                     }
-                    e1[c >> 1] = pack_bf16x2(pv[0], pv[1]);
-                    e2[c >> 1] = pack_bf16x2(dv[0], dv[1]);
+                    float pv[4], dv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = half * 32 + c4 + e;
+                        float pr = ex2_approx(fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]));
+                        if (need_mask) {
+                            const int key = MODE == 0 ? xrow : y0 + col;
+                            const int qi = MODE == 0 ? y0 + col : xrow;
+                            if (!(key < kv_len && qi < kv_len && (!p.causal || key <= qi))) pr = 0.f;
+                        }
+                        pv[e] = pr;
+                        dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]) * p.scale;
+                    }
+                    e1[c4 >> 1] = pack_bf16x2(pv[0], pv[1]); e1[(c4 >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+                    e2[c4 >> 1] = pack_bf16x2(dv[0], dv[1]); e2[(c4 >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
                 }
                 // this E buffer is free once the accumulate MMAs of its previous use (two tiles back) have completed
                 const uint32_t eb = ec & 1;
@@ -318,8 +343,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 uint8_t* sE1 = sE + eb * 2 * E_BYTES;
                 uint8_t* sE2 = sE1 + E_BYTES;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t off = r * 128 + ((u ^ (r & 7)) << 4);
+                for (int u = 0; u < 4; ++u) {
+                    const int unit = half * 4 + u;
+                    const uint32_t off = r * 128 + ((unit ^ (r & 7)) << 4);
                     if (MODE == 0) *reinterpret_cast<uint4*>(sE1 + off) = make_uint4(e1[u * 4], e1[u * 4 + 1], e1[u * 4 + 2], e1[u * 4 + 3]);
                     *reinterpret_cast<uint4*>(sE2 + off) = make_uint4(e2[u * 4], e2[u * 4 + 1], e2[u * 4 + 2], e2[u * 4 + 3]);
                 }
@@ -328,8 +354,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&e_full[eb]);
                 ++ec;
+                if (MODE == 0 && tid_e < BY && t + 1 < n) {  // publish tile t+1's statistics (other buffer)
+                    sLse[((tc + 1) & 1) * BY + tid_e] = nl;
+                    sDelta[((tc + 1) & 1) * BY + tid_e] = nd;
+                }
             }
-            // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work)
+            // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work); columns split by `half`
             if (n > 0) {  // the commit of the last tile's accumulate MMAs covers every earlier tcgen05 op of the MMA thread
                 mbar_wait(&e_done[(ec - 1) & 1], ((ec - 1) >> 1) & 1, 95);
                 tcgen05_fence_after();
@@ -340,7 +370,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             for (int a = (MODE == 0 ? 0 : 1); a < 2; ++a) {
                 __nv_bfloat16* dst = (a == 0 ? p.out1 + grow * p.ld1 : p.out2 + grow * p.ld2) + (long long)hx * DH;
 #pragma unroll
-                for (int c = 0; c < DH / 32; ++c) {
+                for (int cc = 0; cc < DH / 64; ++cc) {
+                    const int c = half * (DH / 64) + cc;
                     uint32_t acc[32];
                     if (n > 0) {
                         tmem_ld_32x32b(tmem_base + lane_addr + (a == 0 ? TM_A1 : TM_A2) + c * 32, acc);

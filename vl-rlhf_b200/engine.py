@@ -257,7 +257,7 @@ class LlavaDPOEngine:
         for i in range(cfg.v_used_layers):
             ops.layernorm_fwd(x, v[f"v{i}.ln1.w"], v[f"v{i}.ln1.b"], cfg.v_eps, out=h)
             ops.gemm(h, v[f"v{i}.wqkv"], out=qkv, bias=v[f"v{i}.bqkv"])
-            ops.attn_fwd(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, None, None, Bv, Sv, cfg.v_heads, cfg.v_heads,
+            ops.attn_fwd_tc(qkv[:, :dv], qkv[:, dv:2 * dv], qkv[:, 2 * dv:], att, None, None, Bv, Sv, cfg.v_heads, cfg.v_heads,
                          cfg.v_head_dim, False, scale)
             ops.gemm(att, v[f"v{i}.wo"], out=x, bias=v[f"v{i}.bo"], residual=x)
             ops.layernorm_fwd(x, v[f"v{i}.ln2.w"], v[f"v{i}.ln2.b"], cfg.v_eps, out=h)
@@ -306,7 +306,7 @@ class LlavaDPOEngine:
             ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=rstd1)
             ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
             ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
-            ops.attn_fwd(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, lse, m.seqlens, m.n_seq, m.S, H, KV, dh,
+            ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, lse, m.seqlens, m.n_seq, m.S, H, KV, dh,
                          True, scale)
             ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
             ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=rstd2)
@@ -373,7 +373,7 @@ class LlavaDPOEngine:
             # ---- attention
             ops.gemm(dx2, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wo"])             # dWo = dxmid^T att
             ops.gemm(dx2, w[f"L{i}.wo"], b_kmajor=False, out=datt)                            # datt = dxmid Wo
-            ops.attn_bwd(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
+            ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
                          dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh,
                          True, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
