@@ -56,7 +56,7 @@ int vlb200_perturb_bf16(void* dst, const void* base, const void* other, uint64_t
  *   opA: a_kmajor=1 -> A is row-major [M,K] (lda >= K);  a_kmajor=0 -> A is row-major [K,M] (lda >= M)
  *   opB: b_kmajor=1 -> B is row-major [N,K] (ldb >= K)   (nn.Linear weight layout: y = x W^T)
  *        b_kmajor=0 -> B is row-major [K,N] (ldb >= N)
- *   epilogue: + bias[n] (bf16 or NULL), activation, + residual[m,n] (bf16, ldr, or NULL),
+ *   epilogue: + bias[n] (bf16 or NULL), activation, + residual[m,n] (bf16 or fp32 per residual_dtype, ldr, or NULL),
  *             accumulate=1 adds the previous contents of D (gradient accumulation).
  *   out_dtype: VLB200_BF16 or VLB200_F32.   All leading dimensions in elements; pointers 16-byte
  *   aligned; lda/ldb multiples of 8.                                                         */
@@ -64,8 +64,8 @@ int vlb200_perturb_bf16(void* dst, const void* base, const void* other, uint64_t
 #define VLB200_ACT_QUICK_GELU 1 /* x * sigmoid(1.702 x)   (CLIP MLP) */
 #define VLB200_ACT_GELU_ERF 2   /* projector */
 int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D, int ldd,
-                     int out_dtype, int M, int N, int K, const void* bias, int act, const void* residual, int ldr,
-                     int accumulate, void* stream);
+                     int out_dtype, int M, int N, int K, const void* bias, int act, const void* residual, int residual_dtype,
+                     int ldr, int accumulate, void* stream);
 
 /* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
  * logits: [rows, V] (dtype bf16|f32, row stride ld_logits elements).  Row r predicts target[r];
@@ -101,15 +101,16 @@ int vlb200_dpo_loss(const float* policy_logps, const float* ref_logps, int n_pai
 
 /* ---- norms ----------------------------------------------------------------------------
  * RMSNorm = LlamaRMSNorm (transformers modeling_llama.py:53-67); LayerNorm = CLIP pre/layer norms
- * (modeling_clip.py).  x,y,w,b bf16; statistics fp32.  cols % 8 == 0, cols <= 8192.            */
-int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int rows, int cols,
-                       float eps, void* stream);
+ * (modeling_clip.py).  y,w,b bf16; x is bf16 or fp32 (x_dtype: the residual stream is kept in fp32); statistics fp32.
+ * cols % 8 == 0, cols <= 8192.                                                                 */
+int vlb200_rmsnorm_fwd(const void* x, int x_dtype, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int rows,
+                       int cols, float eps, void* stream);
 /* dx = d(rmsnorm)/dx (+ dres), dw (+)= sum_rows dy * xhat.  x/dy/dx/dres contiguous [rows, cols].
  * workspace: vlb200_norm_bwd_workspace_floats(cols) floats.                                    */
 int vlb200_norm_bwd_workspace_floats(int cols);
-int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+int vlb200_rmsnorm_bwd(const void* dy, const void* x, int x_dtype, const void* w, const float* rstd, const void* dres, void* dx,
                        void* dw, int dw_accumulate, float* workspace, int rows, int cols, void* stream);
-int vlb200_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows,
+int vlb200_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int rows,
                          int cols, float eps, void* stream);
 /* out[c] (bf16) (+)= sum_r a[r, c]  (bias gradients).  workspace as for rmsnorm_bwd.            */
 int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, void* out, int accumulate, float* workspace,
@@ -157,7 +158,7 @@ int vlb200_llava_merge_index(const int64_t* input_ids, const int64_t* attention_
                              int* mask_merged, int* position_ids, int* seqlens, int* img_pos, int* row_of_text,
                              int64_t* target, int* status, void* stream);
 int vlb200_llava_merge_embed(const int* src_map, const void* embed_tokens, const void* image_features, void* out,
-                             int rows, int d, void* stream);
+                             int out_dtype, int rows, int d, void* stream);
 /* dembed_f32[V,d] += text-row grads (fp32 atomics); dimage_features = sum over sequences sharing the image */
 int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
                            void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq, int d,

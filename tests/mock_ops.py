@@ -346,9 +346,9 @@ def llava_merge_embed(m, embed_tokens, image_features, out):
     s = m.src_map.long()
     out.zero_()
     t = s >= 0
-    out[t] = embed_tokens[s[t]]
+    out[t] = embed_tokens[s[t]].to(out.dtype)
     im = (s < 0) & (s != INT_MIN)
-    out[im] = image_features[-1 - s[im]]
+    out[im] = image_features[-1 - s[im]].to(out.dtype)
     _c()
     return out
 

@@ -18,18 +18,18 @@ SIGNATURES = {
     "vlb200_init_uniform": (c_int, [c_void_p, c_int, c_uint64, c_uint32, c_float, c_float, c_void_p]),
     "vlb200_perturb_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_float, c_float, c_void_p]),
     "vlb200_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                 c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+                                 c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vlb200_logps_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlb200_logps_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_int64, c_void_p]),
     "vlb200_dpo_loss": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
-    "vlb200_rmsnorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "vlb200_rmsnorm_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
     "vlb200_norm_bwd_workspace_floats": (c_int, [c_int]),
-    "vlb200_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                   c_int, c_int, c_void_p]),
-    "vlb200_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float,
+    "vlb200_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, c_int, c_int, c_void_p]),
+    "vlb200_layernorm_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float,
                                      c_void_p]),
     "vlb200_colsum": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vlb200_rope": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -47,7 +47,7 @@ SIGNATURES = {
     "vlb200_llava_merge_index": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
-    "vlb200_llava_merge_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vlb200_llava_merge_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vlb200_llava_merge_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_void_p]),
     "vlb200_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

@@ -269,8 +269,9 @@ __global__ void merge_index_kernel(const int64_t* __restrict__ ids, const int64_
 }
 
 // out[r, :] = embed[src] | image_features[-1-src] | 0
+template <typename OT>
 __global__ void merge_embed_kernel(const int* __restrict__ src_map, const __nv_bfloat16* __restrict__ embed,
-                                   const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int rows, int d) {
+                                   const __nv_bfloat16* __restrict__ img, OT* __restrict__ out, int rows, int d) {
     const int chunks = d >> 3;
     const size_t total = (size_t)rows * chunks;
     for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
@@ -280,7 +281,14 @@ __global__ void merge_embed_kernel(const int* __restrict__ src_map, const __nv_b
         uint4 v = make_uint4(0, 0, 0, 0);
         if (s >= 0) v = *reinterpret_cast<const uint4*>(embed + (size_t)s * d + c * 8);
         else if (s != INT_MIN) v = *reinterpret_cast<const uint4*>(img + (size_t)(-1 - s) * d + c * 8);
-        *reinterpret_cast<uint4*>(out + r * d + c * 8) = v;
+        if constexpr (sizeof(OT) == 2) {
+            *reinterpret_cast<uint4*>(out + r * d + c * 8) = v;
+        } else {
+            float f[8];
+            unpack8e(v, f);
+            *reinterpret_cast<float4*>(out + r * d + c * 8) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(out + r * d + c * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
     }
 }
 // text rows: dembed[id] += dx[r] (fp32 atomics: token ids repeat);  image rows handled by merge_img_bwd_kernel
@@ -533,9 +541,13 @@ extern "C" int vlb200_llava_merge_index(const int64_t* input_ids, const int64_t*
     return VLB200_OK;
 }
 extern "C" int vlb200_llava_merge_embed(const int* src_map, const void* embed_tokens, const void* image_features, void* out,
-                                        int rows, int d, void* stream) {
+                                        int out_dtype, int rows, int d, void* stream) {
     VLB_REQUIRE(src_map && embed_tokens && image_features && out && d % 8 == 0, "merge_embed: bad arguments");
-    merge_embed_kernel<<<grid_for((size_t)rows * (d / 8), 256), 256, 0, as_stream(stream)>>>(src_map, CBF(embed_tokens), CBF(image_features), BF(out), rows, d);
+    VLB_REQUIRE(out_dtype == VLB200_BF16 || out_dtype == VLB200_F32, "merge_embed: bad out dtype");
+    if (out_dtype == VLB200_F32)
+        merge_embed_kernel<float><<<grid_for((size_t)rows * (d / 8), 256), 256, 0, as_stream(stream)>>>(src_map, CBF(embed_tokens), CBF(image_features), (float*)out, rows, d);
+    else
+        merge_embed_kernel<__nv_bfloat16><<<grid_for((size_t)rows * (d / 8), 256), 256, 0, as_stream(stream)>>>(src_map, CBF(embed_tokens), CBF(image_features), BF(out), rows, d);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;

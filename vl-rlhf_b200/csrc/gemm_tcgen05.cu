@@ -29,7 +29,8 @@ struct Params {
     int out_f32;
     const __nv_bfloat16* bias;
     int act;
-    const __nv_bfloat16* residual;
+    const void* residual;
+    int residual_f32;
     long long ldr;
     int accumulate;
     int group;         // rasterisation: tiles of `group` M-blocks (or N-blocks) sweep the other dimension together
@@ -218,17 +219,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
                     }
                     if (p.residual != nullptr) {
-                        const __nv_bfloat16* rp = p.residual + (long long)row * p.ldr + col0;
+                        if (p.residual_f32) {
+                            const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + col0;
 #pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            if (col0 + j8 * 8 < p.N) {
-                                const uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
-                                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                if (col0 + j4 * 4 < p.N) {
+                                    const float4 b = *reinterpret_cast<const float4*>(rp + j4 * 4);
+                                    v[j4 * 4] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                                }
+                            }
+                        } else {
+                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)row * p.ldr + col0;
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 f = unpack_bf16x2(bw[q]);
-                                    v[j8 * 8 + 2 * q] += f.x;
-                                    v[j8 * 8 + 2 * q + 1] += f.y;
+                            for (int j8 = 0; j8 < 4; ++j8) {
+                                if (col0 + j8 * 8 < p.N) {
+                                    const uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f = unpack_bf16x2(bw[q]);
+                                        v[j8 * 8 + 2 * q] += f.x;
+                                        v[j8 * 8 + 2 * q + 1] += f.y;
+                                    }
                                 }
                             }
                         }
@@ -390,7 +402,7 @@ static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtenso
 
 extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D,
                                 int ldd, int out_dtype, int M, int N, int K, const void* bias, int act,
-                                const void* residual, int ldr, int accumulate, void* stream) {
+                                const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
     using namespace vlb;
     using namespace vlb::gemm;
     VLB_REQUIRE(A && B && D, "gemm: null pointer");
@@ -399,6 +411,7 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     VLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%d / ldb=%d must be multiples of 8 elements (TMA 16 B strides)",
                 lda, ldb);
     VLB_REQUIRE(ldd % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "gemm: ldd/ldr must be multiples of 8");
+    VLB_REQUIRE(residual == nullptr || residual_dtype == VLB200_BF16 || residual_dtype == VLB200_F32, "gemm: bad residual dtype");
     VLB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 "gemm: pointers must be 16-byte aligned");
@@ -426,7 +439,8 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     p.D = D; p.ldd = ldd; p.out_f32 = out_dtype == VLB200_F32;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.act = act;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+    p.residual = residual;
+    p.residual_f32 = residual_dtype == VLB200_F32;
     p.ldr = ldr;
     p.accumulate = accumulate;
     {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group

@@ -33,25 +33,37 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return o;
 }
 
-// y = w * (x * rsqrt(mean(x^2) + eps))            (fp32 math, one rounding at the end)
+// 8 consecutive elements as floats from a bf16 (16 B) or fp32 (32 B) row
+template <typename XT>
+__device__ __forceinline__ void load8(const XT* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// y = w * (x * rsqrt(mean(x^2) + eps))            (fp32 math, one rounding at the end; x may be bf16 or fp32)
+template <typename XT>
 __global__ void __launch_bounds__(NORM_THREADS)
-rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+rmsnorm_fwd_kernel(const XT* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                    __nv_bfloat16* __restrict__ y, long long ldy, float* __restrict__ rstd_out, int cols, float eps) {
     __shared__ float sm[4];
     const int row = blockIdx.x;
     const int nvec = cols >> 3;
-    const __nv_bfloat16* xr = x + (size_t)row * ldx;
-    uint4 xv[NORM_MAX_VEC];
+    const XT* xr = x + (size_t)row * ldx;
+    float xf[NORM_MAX_VEC][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < NORM_MAX_VEC; ++k) {
         const int i = threadIdx.x + k * NORM_THREADS;
         if (i < nvec) {
-            xv[k] = *reinterpret_cast<const uint4*>(xr + (size_t)i * 8);
-            float f[8];
-            unpack8(xv[k], f);
+            load8<XT>(xr + (size_t)i * 8, xf[k]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+            for (int j = 0; j < 8; ++j) ss += xf[k][j] * xf[k][j];
         }
     }
     ss = block_sum_128(ss, sm);
@@ -63,19 +75,18 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __n
         const int i = threadIdx.x + k * NORM_THREADS;
         if (i < nvec) {
             float f[8], g[8];
-            unpack8(xv[k], f);
             unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), g);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = g[j] * (f[j] * rstd);
+            for (int j = 0; j < 8; ++j) f[j] = g[j] * (xf[k][j] * rstd);
             *reinterpret_cast<uint4*>(yr + (size_t)i * 8) = pack8(f);
         }
     }
 }
 
 // dx = rstd * (w*dy - xhat * mean(w*dy*xhat)) (+ dres);   dw_partial[cta] += dy * xhat
-template <int VPT>
+template <int VPT, typename XT>
 __global__ void __launch_bounds__(NORM_THREADS)
-rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const XT* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
                    const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial,
                    int rows, int cols) {
@@ -93,20 +104,20 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const float rstd = rstd_in[row];
         const size_t off = (size_t)row * cols;
-        uint4 xv[VPT], gv[VPT];
+        float xs[VPT][8];
+        uint4 gv[VPT];
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
             const int i = threadIdx.x + k * NORM_THREADS;
             if (i < nvec) {
-                xv[k] = *reinterpret_cast<const uint4*>(x + off + (size_t)i * 8);
+                load8<XT>(x + off + (size_t)i * 8, xs[k]);
                 gv[k] = *reinterpret_cast<const uint4*>(dy + off + (size_t)i * 8);
-                float xf[8], gf[8];
-                unpack8(xv[k], xf);
+                float gf[8];
                 unpack8(gv[k], gf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float xh = xf[j] * rstd;
+                    const float xh = xs[k][j] * rstd;
                     dot += wv[k][j] * gf[j] * xh;
                     dw[k][j] += gf[j] * xh;
                 }
@@ -117,11 +128,10 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         for (int k = 0; k < VPT; ++k) {
             const int i = threadIdx.x + k * NORM_THREADS;
             if (i < nvec) {
-                float xf[8], gf[8], o[8];
-                unpack8(xv[k], xf);
+                float gf[8], o[8];
                 unpack8(gv[k], gf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rstd * (wv[k][j] * gf[j] - xf[j] * rstd * dot);
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (wv[k][j] * gf[j] - xs[k][j] * rstd * dot);
                 if (dres) {
                     float rf[8];
                     unpack8(*reinterpret_cast<const uint4*>(dres + off + (size_t)i * 8), rf);
@@ -165,25 +175,24 @@ colsum_rows_kernel(const __nv_bfloat16* __restrict__ a, long long lda, int rows,
 }
 
 // LayerNorm forward (CLIP): y = (x - mean) * rsqrt(var + eps) * w + b
+template <typename XT>
 __global__ void __launch_bounds__(NORM_THREADS)
-layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
+layernorm_fwd_kernel(const XT* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                      const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long ldy, int cols,
                      float eps) {
     __shared__ float sm[4];
     const int row = blockIdx.x;
     const int nvec = cols >> 3;
-    const __nv_bfloat16* xr = x + (size_t)row * ldx;
-    uint4 xv[NORM_MAX_VEC];
+    const XT* xr = x + (size_t)row * ldx;
+    float xf[NORM_MAX_VEC][8];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NORM_MAX_VEC; ++k) {
         const int i = threadIdx.x + k * NORM_THREADS;
         if (i < nvec) {
-            xv[k] = *reinterpret_cast<const uint4*>(xr + (size_t)i * 8);
-            float f[8];
-            unpack8(xv[k], f);
+            load8<XT>(xr + (size_t)i * 8, xf[k]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s += f[j];
+            for (int j = 0; j < 8; ++j) s += xf[k][j];
         }
     }
     const float mean = block_sum_128(s, sm) / (float)cols;
@@ -192,10 +201,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
     for (int k = 0; k < NORM_MAX_VEC; ++k) {
         const int i = threadIdx.x + k * NORM_THREADS;
         if (i < nvec) {
-            float f[8];
-            unpack8(xv[k], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; v += d * d; }
+            for (int j = 0; j < 8; ++j) { const float d = xf[k][j] - mean; v += d * d; }
         }
     }
     const float rstd = rsqrtf(block_sum_128(v, sm) / (float)cols + eps);
@@ -205,11 +212,10 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const _
         const int i = threadIdx.x + k * NORM_THREADS;
         if (i < nvec) {
             float f[8], g[8], h[8];
-            unpack8(xv[k], f);
             unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), g);
             unpack8(*reinterpret_cast<const uint4*>(b + (size_t)i * 8), h);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[j] + h[j];
+            for (int j = 0; j < 8; ++j) f[j] = (xf[k][j] - mean) * rstd * g[j] + h[j];
             *reinterpret_cast<uint4*>(yr + (size_t)i * 8) = pack8(f);
         }
     }
@@ -225,14 +231,19 @@ static int check_cols(int cols, const char* who) {
     return VLB200_OK;
 }
 
-extern "C" int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int rows,
-                                  int cols, float eps, void* stream) {
+extern "C" int vlb200_rmsnorm_fwd(const void* x, int x_dtype, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd,
+                                  int rows, int cols, float eps, void* stream) {
     VLB_REQUIRE(x && w && y, "rmsnorm_fwd: null pointer");
     if (int rc = check_cols(cols, "rmsnorm_fwd")) return rc;
     VLB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "rmsnorm_fwd: row strides must be multiples of 8");
     if (rows <= 0) return VLB200_OK;
-    rmsnorm_fwd_kernel<<<rows, NORM_THREADS, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w,
-                                                                    (__nv_bfloat16*)y, ldy, rstd, cols, eps);
+    VLB_REQUIRE(x_dtype == VLB200_BF16 || x_dtype == VLB200_F32, "rmsnorm_fwd: bad x dtype");
+    if (x_dtype == VLB200_F32)
+        rmsnorm_fwd_kernel<float><<<rows, NORM_THREADS, 0, as_stream(stream)>>>((const float*)x, ldx, (const __nv_bfloat16*)w,
+                                                                               (__nv_bfloat16*)y, ldy, rstd, cols, eps);
+    else
+        rmsnorm_fwd_kernel<__nv_bfloat16><<<rows, NORM_THREADS, 0, as_stream(stream)>>>(
+            (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, ldy, rstd, cols, eps);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
@@ -240,7 +251,7 @@ extern "C" int vlb200_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, voi
 
 extern "C" int vlb200_norm_bwd_workspace_floats(int cols) { return 8 * num_sms() * cols; }
 
-extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, int x_dtype, const void* w, const float* rstd, const void* dres,
                                   void* dx, void* dw, int dw_accumulate, float* workspace, int rows, int cols,
                                   void* stream) {
     VLB_REQUIRE(dy && x && w && rstd && dx && dw && workspace, "rmsnorm_bwd: null pointer");
@@ -249,10 +260,18 @@ extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, 
     const int grid = rows < 8 * num_sms() ? rows : 8 * num_sms();
     cudaStream_t s = as_stream(stream);
     const int vpt = ((cols >> 3) + NORM_THREADS - 1) / NORM_THREADS;
-#define VLB_RMS_BWD(V)                                                                                         \
-    rmsnorm_bwd_kernel<V><<<grid, NORM_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,     \
-                                                        (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres, \
-                                                        (__nv_bfloat16*)dx, workspace, rows, cols)
+    VLB_REQUIRE(x_dtype == VLB200_BF16 || x_dtype == VLB200_F32, "rmsnorm_bwd: bad x dtype");
+#define VLB_RMS_BWD(V)                                                                                                     \
+    do {                                                                                                                   \
+        if (x_dtype == VLB200_F32)                                                                                         \
+            rmsnorm_bwd_kernel<V, float><<<grid, NORM_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const float*)x,           \
+                                                                       (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres, \
+                                                                       (__nv_bfloat16*)dx, workspace, rows, cols);        \
+        else                                                                                                               \
+            rmsnorm_bwd_kernel<V, __nv_bfloat16><<<grid, NORM_THREADS, 0, s>>>(                                            \
+                (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres, \
+                (__nv_bfloat16*)dx, workspace, rows, cols);                                                               \
+    } while (0)
     if (vpt <= 1) VLB_RMS_BWD(1);
     else if (vpt <= 2) VLB_RMS_BWD(2);
     else if (vpt <= 4) VLB_RMS_BWD(4);
@@ -281,14 +300,18 @@ extern "C" int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, voi
     return VLB200_OK;
 }
 
-extern "C" int vlb200_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+extern "C" int vlb200_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
                                     int rows, int cols, float eps, void* stream) {
     VLB_REQUIRE(x && w && b && y, "layernorm_fwd: null pointer");
     if (int rc = check_cols(cols, "layernorm_fwd")) return rc;
     if (rows <= 0) return VLB200_OK;
-    layernorm_fwd_kernel<<<rows, NORM_THREADS, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, ldx,
-                                                                      (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,
-                                                                      (__nv_bfloat16*)y, ldy, cols, eps);
+    VLB_REQUIRE(x_dtype == VLB200_BF16 || x_dtype == VLB200_F32, "layernorm_fwd: bad x dtype");
+    if (x_dtype == VLB200_F32)
+        layernorm_fwd_kernel<float><<<rows, NORM_THREADS, 0, as_stream(stream)>>>(
+            (const float*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, cols, eps);
+    else
+        layernorm_fwd_kernel<__nv_bfloat16><<<rows, NORM_THREADS, 0, as_stream(stream)>>>(
+            (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, cols, eps);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;

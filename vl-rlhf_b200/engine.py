@@ -287,7 +287,9 @@ class LlavaDPOEngine:
         ops.gemm(ph, w["proj.w2"], out=img, bias=w["proj.b2"])
         # embed + merge (K7, K8)
         L = cfg.layers
-        x = self.buf("x.0" if save else "s.x0", (T, d))
+        # the residual stream is kept in fp32 (bf16 would add a 2^-9 relative rounding per layer that compounds
+        # through 32 layers); every GEMM operand (normed activations, q/k/v, attention out, SwiGLU out) is bf16
+        x = self.buf("x.0" if save else "s.x0", (T, d), torch.float32)
         ops.llava_merge_embed(m, w["embed"], img, x)
         h = self.buf("s.h", (T, d))
         act = self.buf("s.act", (T, cfg.ff))
@@ -300,9 +302,9 @@ class LlavaDPOEngine:
             qkv = self.buf(f"{pre}.qkv{sfx}", (T, cfg.qkv_dim))
             att = self.buf(f"{pre}.att{sfx}", (T, hd))
             lse = self.buf(f"{pre}.lse{sfx}", (m.n_seq, H, m.S), torch.float32)
-            xmid = self.buf(f"{pre}.xmid{sfx}", (T, d))
+            xmid = self.buf(f"{pre}.xmid{sfx}", (T, d), torch.float32)
             gu = self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff))
-            xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d))
+            xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d), torch.float32)
             ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=rstd1)
             ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
             ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)

@@ -74,6 +74,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     assert out.shape == (M, N)
     check(_L.vlb200_gemm_bf16(_ptr(a), _rowmajor_ld(a), int(a_kmajor), _ptr(b), _rowmajor_ld(b), int(b_kmajor),
                               _ptr(out), _rowmajor_ld(out), _dt(out), M, N, K, _ptr(bias), act, _ptr(residual),
+                              _dt(residual) if residual is not None else BF16,
                               _rowmajor_ld(residual) if residual is not None else 0, int(accumulate), _stream()))
     return out
 
@@ -150,8 +151,8 @@ def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torc
                 rstd: Optional[torch.Tensor] = None):
     rows, cols = x.shape
     if out is None:
-        out = torch.empty_like(x)
-    check(_L.vlb200_rmsnorm_fwd(_ptr(x), _rowmajor_ld(x), _ptr(w), _ptr(out), _rowmajor_ld(out), _ptr(rstd), rows, cols,
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_L.vlb200_rmsnorm_fwd(_ptr(x), _dt(x), _rowmajor_ld(x), _ptr(w), _ptr(out), _rowmajor_ld(out), _ptr(rstd), rows, cols,
                                 eps, _stream()))
     return out
 
@@ -161,8 +162,8 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.
     rows, cols = x.shape
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     if out is None:
-        out = torch.empty_like(x)
-    check(_L.vlb200_rmsnorm_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(rstd), _ptr(dres), _ptr(out), _ptr(dw),
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_L.vlb200_rmsnorm_bwd(_ptr(dy), _ptr(x), _dt(x), _ptr(w), _ptr(rstd), _ptr(dres), _ptr(out), _ptr(dw),
                                 int(dw_accumulate), _ptr(_workspace(cols, x.device)), rows, cols, _stream()))
     return out
 
@@ -170,8 +171,8 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.
 def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None):
     rows, cols = x.shape
     if out is None:
-        out = torch.empty_like(x)
-    check(_L.vlb200_layernorm_fwd(_ptr(x), _rowmajor_ld(x), _ptr(w), _ptr(b), _ptr(out), _rowmajor_ld(out), rows, cols,
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_L.vlb200_layernorm_fwd(_ptr(x), _dt(x), _rowmajor_ld(x), _ptr(w), _ptr(b), _ptr(out), _rowmajor_ld(out), rows, cols,
                                   eps, _stream()))
     return out
 
@@ -299,7 +300,7 @@ def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, lab
 
 
 def llava_merge_embed(m: MergeIndex, embed_tokens: torch.Tensor, image_features: torch.Tensor, out: torch.Tensor):
-    check(_L.vlb200_llava_merge_embed(_ptr(m.src_map), _ptr(embed_tokens), _ptr(image_features), _ptr(out),
+    check(_L.vlb200_llava_merge_embed(_ptr(m.src_map), _ptr(embed_tokens), _ptr(image_features), _ptr(out), _dt(out),
                                       m.n_seq * m.S, embed_tokens.shape[1], _stream()))
     return out
 
