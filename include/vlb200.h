@@ -67,6 +67,10 @@ int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ld
                      int out_dtype, int M, int N, int K, const void* bias, int act, const void* residual, int residual_dtype,
                      int ldr, int accumulate, void* stream);
 
+/* mode 1: 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, B tile split across the pair) where M,N >= 256;
+ * mode 0: single-CTA 128x256 tiles.  Default from the environment variable VLB200_GEMM_2CTA (unset = 0).   */
+int vlb200_set_gemm_mode(int mode);
+
 /* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
  * logits: [rows, V] (dtype bf16|f32, row stride ld_logits elements).  Row r predicts target[r];
  * target[r] < 0 (label_pad) rows are skipped without being read.  rows = n_seq * rows_per_seq

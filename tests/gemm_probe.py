@@ -15,6 +15,10 @@ CASES = [
     ("nt_both_mn", 256, 512, 256, 0, 0, ""),
     ("tn_big", 4096, 4096, 4096, 1, 1, "time"),
     ("tn_epi", 384, 768, 320, 1, 1, "epi"),
+    ("tn_odd", 12792, 4096, 4096, 1, 1, "time"),
+    ("wgrad", 4096, 11008, 12792, 0, 0, "time"),
+    ("dgrad", 12792, 4096, 22016, 1, 0, "time"),
+    ("gate_up", 12792, 22016, 4096, 1, 1, "time"),
 ]
 
 
@@ -65,26 +69,34 @@ def run_case(name, M, N, K, ak, bk, extra):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"   time {ms:.3f} ms  -> {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
-        e0.record()
-        for _ in range(10):
-            torch.matmul(a, b.t(), out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        print(f"   cuBLAS {ms:.3f} ms -> {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+        if ak and bk:
+            wt = b.t()
+            ref = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            for _ in range(3):
+                torch.matmul(a, wt, out=ref)
+            e0.record()
+            for _ in range(10):
+                torch.matmul(a, wt, out=ref)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"   cuBLAS {ms:.3f} ms -> {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
     return 0 if not bad.any() else 1
 
 
 if __name__ == "__main__":
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] not in ("1cta", "2cta"):
         c = [c for c in CASES if c[0] == sys.argv[1]][0]
         sys.exit(run_case(*c))
+    mode = sys.argv[1] if len(sys.argv) > 1 else "1cta"
+    env = dict(os.environ, VLB200_GEMM_2CTA="1" if mode == "2cta" else "0")
+    print("gemm probe mode:", mode)
     fails = 0
     for c in CASES:
         try:
-            r = subprocess.run([sys.executable, __file__, c[0]], timeout=120, capture_output=True, text=True)
+            r = subprocess.run([sys.executable, __file__, c[0]], timeout=120, capture_output=True, text=True, env=env)
             print(r.stdout, end="")
             if r.returncode != 0:
                 fails += 1

@@ -165,7 +165,10 @@ def test_config1_7b_shapes_logps_and_loss_parity(pkg):
     ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
     out = eng.step(ids, am, lb, px, train=False)
     pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
-    print("config1 policy logps", pol, "golden", d["policy_logps"])
+    print("config1 policy logps", pol, "golden", d["policy_logps"], "rel", np.abs(pol / d["policy_logps"] - 1))
+    print("config1 ref    logps", ref, "golden", d["ref_logps"], "rel", np.abs(ref / d["ref_logps"] - 1))
+    if "policy_logps_refdtype_bf16" in d.files:
+        print("reference's own bf16 path vs its fp32 path: rel", np.abs(d["policy_logps_refdtype_bf16"] / d["policy_logps"] - 1))
     np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
     np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
     # per-pair loss / rewards: margins are differences of ~1e3-sized log-probs, each good to 1e-3 relative

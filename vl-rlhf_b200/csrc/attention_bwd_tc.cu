@@ -191,17 +191,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                         if (mbar_try_wait(&y_full[st], (yi / NST) & 1) && mbar_try_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1)) {
                             tcgen05_fence_after();
                             const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                            // descriptors: constant fields built once, only the 16-byte-granular start address advances
+                            const uint64_t dx1 = make_smem_desc_sw128(smem_u32(sX1), 1024, 0), dx2 = make_smem_desc_sw128(smem_u32(sX2), 1024, 0);
+                            const uint64_t dy1 = make_smem_desc_sw128(y1, 1024, 0), dy2 = make_smem_desc_sw128(y2, 1024, 0);
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
-                                umma_f16_ss(tmem_base + TM_T1 + tb * BY, make_smem_desc_sw128(smem_u32(sX1) + xo, 1024, 0),
-                                            make_smem_desc_sw128(y1 + yo, 1024, 0), idesc_t, k != 0);
+                                const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                umma_f16_ss(tmem_base + TM_T1 + tb * BY, dx1 + xo, dy1 + yo, idesc_t, k != 0);
                             }
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t xo = (k >> 2) * XCH + (k & 3) * 32, yo = (k >> 2) * YCH + (k & 3) * 32;
-                                umma_f16_ss(tmem_base + TM_T2 + tb * BY, make_smem_desc_sw128(smem_u32(sX2) + xo, 1024, 0),
-                                            make_smem_desc_sw128(y2 + yo, 1024, 0), idesc_t, k != 0);
+                                const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                umma_f16_ss(tmem_base + TM_T2 + tb * BY, dx2 + xo, dy2 + yo, idesc_t, k != 0);
                             }
                             umma_commit(&t_full[tb]);
                             if (ts == n - 1) umma_commit(x_empty);
@@ -216,14 +217,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                             tcgen05_fence_after();
                             const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
                             const uint32_t e1 = smem_u32(sE + eb * 2 * E_BYTES), e2 = e1 + E_BYTES;
+                            const uint64_t de1 = make_smem_desc_sw128(e1, 1024, 0), de2 = make_smem_desc_sw128(e2, 1024, 0);
+                            const uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
 #pragma unroll
                             for (int k = 0; k < BY / 16; ++k) {
                                 if (MODE == 0)  // dV += P^T dO
-                                    umma_f16_ss(tmem_base + TM_A1, make_smem_desc_sw128(e1 + k * 32, 1024, 0),
-                                                make_smem_desc_sw128(y2 + k * 2048, 1024, YCH), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
+                                    umma_f16_ss(tmem_base + TM_A1, de1 + (uint64_t)(k * 2), by2 + (uint64_t)(k * 128), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
                                 // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
-                                umma_f16_ss(tmem_base + TM_A2, make_smem_desc_sw128(e2 + k * 32, 1024, 0),
-                                            make_smem_desc_sw128(y1 + k * 2048, 1024, YCH), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
+                                umma_f16_ss(tmem_base + TM_A2, de2 + (uint64_t)(k * 2), by1 + (uint64_t)(k * 128), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
                             }
                             umma_commit(&e_done[eb]);
                             umma_commit(&y_empty[st]);

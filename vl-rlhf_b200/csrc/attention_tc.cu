@@ -169,12 +169,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                         const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
                         if (mbar_try_wait(&kv_full[st], (g / NSTAGE) & 1) && mbar_try_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1)) {
                             tcgen05_fence_after();
-                            const uint32_t kbase = smem_u32(sStage + st * STAGE_BYTES);
+                            const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 0);
+                            const uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0);
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-                                umma_f16_ss(tmem_base + TM_S + sb * BN, make_smem_desc_sw128(smem_u32(sQ) + off, 1024, 0),
-                                            make_smem_desc_sw128(kbase + off, 1024, 0), idesc_s, k != 0);
+                                const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
+                                umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
                             }
                             umma_commit(&s_full[sb]);
                             if (js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
@@ -188,11 +188,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                             if (jp == 0) mbar_wait(o_free, (item & 1) ^ 1, 60);  // epilogue of the previous item has read O
                             tcgen05_fence_after();
                             const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
+                            const uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
 #pragma unroll
                             for (int k = 0; k < BN / 16; ++k) {
-                                umma_f16_ss(tmem_base + TM_O, make_smem_desc_sw128(pbase + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 1024, 0),
-                                            make_smem_desc_sw128(vbase + k * (16 * 128), 1024, CHUNK_BYTES), idesc_o,
-                                            (jp != 0 || k != 0) ? 1u : 0u);
+                                umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
+                                            dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
                             }
                             umma_commit(pv_done);
                             umma_commit(&kv_empty[st]);

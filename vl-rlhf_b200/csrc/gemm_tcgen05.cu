@@ -5,6 +5,7 @@
 // warps 2-5 = epilogue (TMEM lane quadrant = warp_idx % 4).  One CTA per SM, grid = #SMs.
 //
 // Replaces every nn.Linear the reference reaches through transformers (see include/vlb200.h).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -64,6 +65,98 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == VLB200_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
     if (act == VLB200_ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     return x;
+}
+
+// epilogue for 32 consecutive fp32 accumulator columns of one row: bias, activation, residual, accumulate, store
+__device__ __forceinline__ void epilogue_store_32(const Params& p, int row, int col0, const uint32_t (&r)[32]) {
+    if (row < p.M && col0 < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j8 * 8);
+                                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f = unpack_bf16x2(bw[q]);
+                                    v[j8 * 8 + 2 * q] += f.x;
+                                    v[j8 * 8 + 2 * q + 1] += f.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.act != VLB200_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+                    }
+                    if (p.residual != nullptr) {
+                        if (p.residual_f32) {
+                            const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + col0;
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                if (col0 + j4 * 4 < p.N) {
+                                    const float4 b = *reinterpret_cast<const float4*>(rp + j4 * 4);
+                                    v[j4 * 4] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+                                }
+                            }
+                        } else {
+                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)row * p.ldr + col0;
+#pragma unroll
+                            for (int j8 = 0; j8 < 4; ++j8) {
+                                if (col0 + j8 * 8 < p.N) {
+                                    const uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
+                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f = unpack_bf16x2(bw[q]);
+                                        v[j8 * 8 + 2 * q] += f.x;
+                                        v[j8 * 8 + 2 * q + 1] += f.y;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            if (col0 + j4 * 4 < p.N) {
+                                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                                if (p.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(dp + j4 * 4);
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(dp + j4 * 4) = o;
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                if (p.accumulate) {
+                                    const uint4 b = *reinterpret_cast<const uint4*>(dp + j8 * 8);
+                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f = unpack_bf16x2(bw[q]);
+                                        v[j8 * 8 + 2 * q] += f.x;
+                                        v[j8 * 8 + 2 * q + 1] += f.y;
+                                    }
+                                }
+                                uint4 o;
+                                o.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+                                o.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                                o.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+                                o.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                                *reinterpret_cast<uint4*>(dp + j8 * 8) = o;
+                            }
+                        }
+                    }
+    }
 }
 
 template <int BLOCK_N, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
@@ -194,95 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 uint32_t r[32];
                 tmem_ld_32x32(taddr0 + c * 32, r);
                 tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                if (row < p.M && col0 < p.N) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias != nullptr) {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            if (col0 + j8 * 8 < p.N) {
-                                const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j8 * 8);
-                                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 f = unpack_bf16x2(bw[q]);
-                                    v[j8 * 8 + 2 * q] += f.x;
-                                    v[j8 * 8 + 2 * q + 1] += f.y;
-                                }
-                            }
-                        }
-                    }
-                    if (p.act != VLB200_ACT_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-                    }
-                    if (p.residual != nullptr) {
-                        if (p.residual_f32) {
-                            const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)row * p.ldr + col0;
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                if (col0 + j4 * 4 < p.N) {
-                                    const float4 b = *reinterpret_cast<const float4*>(rp + j4 * 4);
-                                    v[j4 * 4] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-                                }
-                            }
-                        } else {
-                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (long long)row * p.ldr + col0;
-#pragma unroll
-                            for (int j8 = 0; j8 < 4; ++j8) {
-                                if (col0 + j8 * 8 < p.N) {
-                                    const uint4 b = *reinterpret_cast<const uint4*>(rp + j8 * 8);
-                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const float2 f = unpack_bf16x2(bw[q]);
-                                        v[j8 * 8 + 2 * q] += f.x;
-                                        v[j8 * 8 + 2 * q + 1] += f.y;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (p.out_f32) {
-                        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            if (col0 + j4 * 4 < p.N) {
-                                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                                if (p.accumulate) {
-                                    const float4 old = *reinterpret_cast<const float4*>(dp + j4 * 4);
-                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                }
-                                *reinterpret_cast<float4*>(dp + j4 * 4) = o;
-                            }
-                        }
-                    } else {
-                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            if (col0 + j8 * 8 < p.N) {
-                                if (p.accumulate) {
-                                    const uint4 b = *reinterpret_cast<const uint4*>(dp + j8 * 8);
-                                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const float2 f = unpack_bf16x2(bw[q]);
-                                        v[j8 * 8 + 2 * q] += f.x;
-                                        v[j8 * 8 + 2 * q + 1] += f.y;
-                                    }
-                                }
-                                uint4 o;
-                                o.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-                                o.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-                                o.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-                                o.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-                                *reinterpret_cast<uint4*>(dp + j8 * 8) = o;
-                            }
-                        }
-                    }
-                }
+                epilogue_store_32(p, row, n0 + c * 32, r);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -296,6 +301,204 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (warp_idx == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2.
+// Each CTA loads its own 128 rows of A and HALF of the B tile (128 of the 256 N rows); the pair's MMA reads both
+// halves, so B traffic per FLOP halves (r1 profile: the 1-CTA kernel is L2->SM bandwidth hungry at 85 FLOP/B).
+//   * full[stage]   lives in the leader CTA (rank 0): 2 arrivals (leader arrive.expect_tx of both CTAs' bytes, peer remote
+//                    arrive); both CTAs' TMA loads complete_tx on it (cta_group::2 loads with the peer bit cleared)
+//   * empty[stage], tmem_full[acc]: one per CTA, signalled by a multicast tcgen05.commit from the leader's MMA thread
+//   * tmem_empty[acc]: in the leader, 8 arrivals (4 epilogue warps of each CTA; the peer arrives remotely via mapa)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const void* map, uint64_t* leader_bar_local_alias, void* smem_dst, int c0, int c1) {
+    const uint32_t bar = smem_u32(leader_bar_local_alias) & 0xFEFFFFFFu;  // clear the peer bit: CTA 0's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar_local_alias, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar_local_alias)), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {  // arrives at this smem offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+constexpr int PAIR_M = 256, PAIR_N = 256, HALF_N = 128;
+
+template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+    constexpr int B_TILE_BYTES = HALF_N * BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // per CTA
+    constexpr int TMEM_COLS = 2 * PAIR_N;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_TILE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane_idx = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp_idx == 0 && lane_idx == 0) {
+        prefetch_tensormap(&tma_a);
+        prefetch_tensormap(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);
+        }
+        fence_barrier_init();
+    }
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast
+    if (warp_idx == 1) tmem_alloc_2cta(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane_idx == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+                int m_blk, n_blk;
+                tile_coords(p, tile, m_blk, n_blk);
+                const int m0 = m_blk * PAIR_M + (int)rank * BLOCK_M, n0 = n_blk * PAIR_N + (int)rank * HALF_N;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * A_TILE_BYTES;
+                    uint8_t* sb = smem_b + stage * B_TILE_BYTES;
+                    const int k0 = kb * BLOCK_K;
+                    if constexpr (A_KMAJOR) {
+                        tma_load_2d_2sm(&tma_a, &full_bar[stage], sa, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_2sm(&tma_a, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
+                    }
+                    if constexpr (B_KMAJOR) {
+                        tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < HALF_N / 64; ++i) tma_load_2d_2sm(&tma_b, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
+                    }
+                    if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane_idx == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(PAIR_M, PAIR_N, !A_KMAJOR, !B_KMAJOR);
+            constexpr uint32_t LBO = BLOCK_K * 128;
+            constexpr uint32_t A_KADV = A_KMAJOR ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+            constexpr uint32_t B_KADV = B_KMAJOR ? (UMMA_K * 2) >> 4 : (UMMA_K * 128) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 200 + acc);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * PAIR_N;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 300 + stage);
+                    tcgen05_fence_after();
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_TILE_BYTES), 1024, A_KMAJOR ? 0 : LBO);
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_TILE_BYTES), 1024, B_KMAJOR ? 0 : LBO);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_f16_ss_2cta(tmem_d, a_desc + (uint64_t)(k * A_KADV), b_desc + (uint64_t)(k * B_KADV), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2cta(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2cta(&tmem_full_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps per CTA; this CTA owns rows [m0 + rank*128, +128)) =====================
+        const int quad = warp_idx & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+            int m_blk, n_blk;
+            tile_coords(p, tile, m_blk, n_blk);
+            const int row = m_blk * PAIR_M + (int)rank * BLOCK_M + quad * 32 + lane_idx;
+            const int n0 = n_blk * PAIR_N;
+            mbar_wait(&tmem_full_bar[acc], acc_phase, 400 + acc);
+            tcgen05_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * PAIR_N;
+#pragma unroll 1
+            for (int c = 0; c < PAIR_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr0 + c * 32, r);
+                tmem_ld_wait();
+                epilogue_store_32(p, row, n0 + c * 32, r);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane_idx == 0) {
+                if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+                else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();  // the peer's smem/TMEM must stay alive until the leader's last MMA and commits have retired
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2cta(tmem_base, TMEM_COLS);
     }
 }
 
@@ -388,6 +591,32 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     return VLB200_OK;
 }
 
+template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+    constexpr int smem_bytes = STAGES * (A_TILE_BYTES + HALF_N * BLOCK_K * 2) + 256 + 1024;
+    auto kern = gemm_bf16_2cta_kernel<STAGES, A_KMAJOR, B_KMAJOR>;
+    static bool configured = false;
+    if (!configured) {
+        VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int max_pairs = num_sms() / 2;
+    const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+    kern<<<2 * pairs, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+static int dispatch_2cta(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
+    if (ak && bk) return launch_2cta<6, true, true>(ta, tb, p, s);
+    if (ak && !bk) return launch_2cta<6, true, false>(ta, tb, p, s);
+    if (!ak && bk) return launch_2cta<6, false, true>(ta, tb, p, s);
+    return launch_2cta<6, false, false>(ta, tb, p, s);
+}
+
+static int g_gemm_mode = -1;  // -1: read VLB200_GEMM_2CTA on first use; 0: 1-CTA kernel; 1: 2-CTA pairs where the shape allows
+
 template <int BLOCK_N, int STAGES>
 static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
                           cudaStream_t s) {
@@ -418,8 +647,13 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     VLB_REQUIRE(out_dtype == VLB200_BF16 || out_dtype == VLB200_F32, "gemm: bad out_dtype %d", out_dtype);
     VLB_REQUIRE(a_kmajor ? lda >= K : lda >= M, "gemm: lda too small");
     VLB_REQUIRE(b_kmajor ? ldb >= K : ldb >= N, "gemm: ldb too small");
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("VLB200_GEMM_2CTA");
+        g_gemm_mode = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    const bool use_pair = g_gemm_mode == 1 && M >= 256 && N >= 256;
     const bool big_n = N > 128;
-    const int BN = big_n ? 256 : 128;
+    const int BN = use_pair ? HALF_N : (big_n ? 256 : 128);  // rows of B fetched per TMA box
 
     CUtensorMap ta, tb;
     int rc;
@@ -432,8 +666,9 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
 
     Params p;
     p.M = M; p.N = N; p.K = K;
-    p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
-    p.num_n_blocks = (N + BN - 1) / BN;
+    const int TM = use_pair ? PAIR_M : BLOCK_M, TN = use_pair ? PAIR_N : BN;
+    p.num_m_blocks = (M + TM - 1) / TM;
+    p.num_n_blocks = (N + TN - 1) / TN;
     p.num_tiles = p.num_m_blocks * p.num_n_blocks;
     p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
     p.D = D; p.ldd = ldd; p.out_f32 = out_dtype == VLB200_F32;
@@ -445,7 +680,7 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     p.accumulate = accumulate;
     {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group
         const double budget = 32.0 * 1024 * 1024;
-        const double a_blk = (double)BLOCK_M * K * 2, b_blk = (double)BN * K * 2;
+        const double a_blk = (double)TM * K * 2, b_blk = (double)TN * K * 2;
         const double a_bytes = (double)M * K * 2, b_bytes = (double)N * K * 2;
         int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
         int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
@@ -455,6 +690,12 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
         p.group = p.group_along_n ? gn : gm;
     }
     cudaStream_t s = as_stream(stream);
+    if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
     if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
     return dispatch_major<128, 6>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
+}
+
+extern "C" int vlb200_set_gemm_mode(int mode) {
+    vlb::gemm::g_gemm_mode = mode ? 1 : 0;
+    return VLB200_OK;
 }

@@ -249,7 +249,9 @@ class LlavaDPOEngine:
         ops.clip_cls_rows_(x, v["v.cls"], pos[0], Bv, Sv)
         h = self.buf("v.h", (Bv * Sv, dv))
         ops.layernorm_fwd(x, v["v.pre.w"], v["v.pre.b"], cfg.v_eps, out=h)
-        x, h = h, x
+        xb = x                                                       # bf16 scratch (embeddings no longer needed)
+        x = self.buf("v.x32", (Bv * Sv, dv), torch.float32)          # fp32 residual stream, like the decoder
+        ops.cast_bf16_to_f32(h.view(-1), x.view(-1))
         qkv = self.buf("v.qkv", (Bv * Sv, 3 * dv))
         att = self.buf("v.att", (Bv * Sv, dv))
         f = self.buf("v.f", (Bv * Sv, cfg.v_ff))
@@ -264,7 +266,8 @@ class LlavaDPOEngine:
             ops.gemm(h, v[f"v{i}.w1"], out=f, bias=v[f"v{i}.b1"], act=ops.ACT_QUICK_GELU)
             ops.gemm(f, v[f"v{i}.w2"], out=x, bias=v[f"v{i}.b2"], residual=x)
         feats = self.buf("v.feats", (Bv * P, dv))  # drop CLS (Llava/__init__.py:182-183)
-        ops.copy_rows(x, Sv * dv, dv, 1, feats, P * dv, dv, Bv, P, dv)
+        ops.cast_f32_to_bf16(x.view(-1), xb.view(-1))
+        ops.copy_rows(xb, Sv * dv, dv, 1, feats, P * dv, dv, Bv, P, dv)
         return feats
 
     # ------------------------------------------------------------------ forward of one model copy

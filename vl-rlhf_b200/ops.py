@@ -79,6 +79,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     return out
 
 
+def set_gemm_mode(mode: int):
+    """1: CTA-pair (cta_group::2) 256x256 tiles where the shape allows; 0: single-CTA 128x256 tiles."""
+    check(_L.vlb200_set_gemm_mode(int(mode)))
+
+
 def logps_fwd(logits: torch.Tensor, target: torch.Tensor, n_seq: int, weight: Optional[torch.Tensor] = None,
               average_log_prob: bool = False):
     """logits [rows, V] (bf16|f32); target [rows] int64 (<0 = skip).  -> (logps[n_seq], per_token[rows], lse[rows])"""
