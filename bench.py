@@ -41,6 +41,16 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
+                "source": t["source"]}
+    except Exception:
+        return None
+
+
 def step_flops(cfg, n_pairs, S, rows_lm):
     """Algorithmic FLOPs of one step: policy fwd + 2x bwd + reference fwd; ViT once per pair."""
     d, ff, L = cfg.hidden, cfg.ff, cfg.layers
@@ -271,12 +281,12 @@ def run_b200(args):
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
                        "step_tflop_algorithmic": flops / 1e12,
                        "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
-            "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 9 * 4,
+            "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                     "ms_per_step": ms_e2e, "last_metrics": last},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,4,K-major,K-major> (tcgen05, gate_up fwd shape)",
                          "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                         "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": None},
+                         "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": _traffic()},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

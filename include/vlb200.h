@@ -68,7 +68,7 @@ int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ld
                      int ldr, int accumulate, void* stream);
 
 /* mode 1: 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, B tile split across the pair) where M,N >= 256;
- * mode 0: single-CTA 128x256 tiles.  Default from the environment variable VLB200_GEMM_2CTA (unset = 0).   */
+ * mode 0: single-CTA 128x256 tiles.  Default 1; the environment variable VLB200_GEMM_2CTA=0 selects mode 0.   */
 int vlb200_set_gemm_mode(int mode);
 
 /* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
@@ -119,6 +119,11 @@ int vlb200_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const void* w,
 /* out[c] (bf16) (+)= sum_r a[r, c]  (bias gradients).  workspace as for rmsnorm_bwd.            */
 int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, void* out, int accumulate, float* workspace,
                   void* stream);
+
+/* fp32 column sums and a fp32 dot product: TRL's `logits/chosen|rejected` metric is the mean of the full [B,S,V] logits
+ * tensor, which equals dot(colsum(h_rows), colsum(W_lm)) / (B*S*V) -- no logits needed.          */
+int vlb200_colsum_f32(const void* a, int64_t lda, int rows, int cols, float* out, float* workspace, void* stream);
+int vlb200_dot_f32(const float* a, const float* b, int n, float scale, float* out, void* stream);
 
 /* ---- RoPE / SwiGLU / GELU (modeling_llama.py:146-184, modeling_llava.py:87-107) -----------
  * rope: rotate-half in place on the first n_rot_heads heads (q heads then k heads) of each row of qkv;

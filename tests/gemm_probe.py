@@ -60,11 +60,11 @@ def run_case(name, M, N, K, ak, bk, extra):
     if extra == "time":
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         for _ in range(3):
-            ops.gemm(a, b, out=out)
+            ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            ops.gemm(a, b, out=out)
+            ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out=out)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10

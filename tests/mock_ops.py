@@ -452,3 +452,15 @@ def cast_bf16_to_f32(src, dst):
 
 attn_fwd_tc = attn_fwd  # the tcgen05 kernels have the same contract as the mma.sync ones
 attn_bwd_tc = attn_bwd
+
+
+def colsum_f32(a, out):
+    out.copy_(a.float().sum(0))
+    _c(2)
+    return out
+
+
+def dot_f32(a, b, scale, out):
+    out[0] = (a * b).sum() * scale
+    _c()
+    return out

@@ -151,6 +151,24 @@ def test_optimizer_step_reduces_loss_and_tracks_master(pkg):
     assert torch.equal(ref[k].float().cpu(), wr[k])
 
 
+def test_train_step_metric_keys_and_values(pkg):
+    """The public end-to-end call (host batch in, TRL metric dict out) incl. the logits/* means computed without logits."""
+    config, engine, host, ops = pkg
+    eng, rcfg, d, batch, cb = build(pkg, "g4_small")
+    got = eng.train_step(batch, train=True)
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    with torch.no_grad():
+        loss, metrics, aux = R.get_batch_loss_metrics(rcfg, wp, wr, batch)
+    assert set(got) >= {"loss", "rewards/chosen", "rewards/rejected", "rewards/accuracies", "rewards/margins",
+                        "logps/chosen", "logps/rejected", "logits/chosen", "logits/rejected"}
+    assert abs(got["loss"] - float(loss)) < 5e-2
+    for k in ("logps/chosen", "logps/rejected"):
+        assert abs(got[k] / float(metrics[k]) - 1) < 1e-3, k
+    for k in ("logits/chosen", "logits/rejected"):
+        assert abs(got[k] - float(metrics[k])) < 5e-3, (k, got[k], float(metrics[k]))
+    assert got["grad_norm"] > 0
+
+
 def test_config1_7b_shapes_logps_and_loss_parity(pkg):
     """BASELINE.json configs[0]: LLaVA-1.5-7B shapes, 2 pairs, text 128 (703 merged), loss/logprob parity against the
     reference's LlavaForRL.forward + get_batch_logps + dpo_loss run in fp32 on CPU (tests/golden/g5_config1_7b.npz).

@@ -235,3 +235,19 @@ def test_plugin_concatenated_forward_and_module(cpu_plugin, cpu_pkg):
     gq = names["language_model.model.layers.0.self_attn.q_proj.weight"].grad
     assert gq is not None and float(gq.float().abs().sum()) > 0
     assert gq.data_ptr() == model.engine.hf_state("grad")["language_model.model.layers.0.self_attn.q_proj.weight"].data_ptr()
+
+
+def test_train_step_metrics_match_oracle(cpu_pkg):
+    """engine.train_step returns TRL's metric keys; values (incl. the logits/* means computed without logits) vs the oracle."""
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+    got = eng.train_step(batch, train=True)
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    with torch.no_grad():
+        loss, metrics, aux = R.get_batch_loss_metrics(rcfg, wp, wr, batch)
+    assert abs(got["loss"] - float(loss)) < 2e-3
+    for k in ("rewards/chosen", "rewards/rejected", "rewards/margins", "logps/chosen", "logps/rejected"):
+        assert abs(got[k] - float(metrics[k])) < 2e-3 * max(1.0, abs(float(metrics[k]))), k
+    assert got["rewards/accuracies"] == float(metrics["rewards/accuracies"])
+    for k in ("logits/chosen", "logits/rejected"):
+        assert abs(got[k] - float(metrics[k])) < 2e-3, (k, got[k], float(metrics[k]))

@@ -649,7 +649,7 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     VLB_REQUIRE(b_kmajor ? ldb >= K : ldb >= N, "gemm: ldb too small");
     if (g_gemm_mode < 0) {
         const char* e = getenv("VLB200_GEMM_2CTA");
-        g_gemm_mode = (e != nullptr && e[0] == '1') ? 1 : 0;
+        g_gemm_mode = (e != nullptr && e[0] == '0') ? 0 : 1;  // CTA pairs by default
     }
     const bool use_pair = g_gemm_mode == 1 && M >= 256 && N >= 256;
     const bool big_n = N > 128;

@@ -164,6 +164,30 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int np
     out[c] = __float2bfloat16(s);
 }
 
+// out[c] (f32) = sum_p partial[p, c]
+__global__ void colsum_partials_f32_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * cols + c];
+    out[c] = s;
+}
+// out[0] = scale * sum_i a[i] * b[i]   (single CTA; n is a hidden size)
+__global__ void __launch_bounds__(256) dot_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float scale,
+                                                      float* __restrict__ out) {
+    __shared__ float sm[8];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += a[i] * b[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += sm[k];
+        out[0] = t * scale;
+    }
+}
+
 // column sums of a bf16 matrix (bias gradients): partial[cta, c] = sum over the CTA's rows
 __global__ void __launch_bounds__(256)
 colsum_rows_kernel(const __nv_bfloat16* __restrict__ a, long long lda, int rows, int cols, float* __restrict__ partial) {
@@ -312,6 +336,28 @@ extern "C" int vlb200_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, con
     else
         layernorm_fwd_kernel<__nv_bfloat16><<<rows, NORM_THREADS, 0, as_stream(stream)>>>(
             (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, cols, eps);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_colsum_f32(const void* a, int64_t lda, int rows, int cols, float* out, float* workspace, void* stream) {
+    VLB_REQUIRE(a && out && workspace, "colsum_f32: null pointer");
+    if (rows <= 0 || cols <= 0) return VLB200_OK;
+    const int gx = rows < 2 * num_sms() ? rows : 2 * num_sms();
+    dim3 grid(gx, (cols + 255) / 256);
+    cudaStream_t s = as_stream(stream);
+    colsum_rows_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, lda, rows, cols, workspace);
+    VLB_LAUNCH_CHECK();
+    colsum_partials_f32_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, gx, cols, out);
+    count_launch(2);
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_dot_f32(const float* a, const float* b, int n, float scale, float* out, void* stream) {
+    VLB_REQUIRE(a && b && out && n > 0, "dot_f32: bad arguments");
+    dot_f32_kernel<<<1, 256, 0, as_stream(stream)>>>(a, b, n, scale, out);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;

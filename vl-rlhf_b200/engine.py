@@ -330,6 +330,13 @@ class LlavaDPOEngine:
         logps, per_tok, lse_v = ops.logps_fwd(logits, m.target, m.n_seq, weight=ddpo_weight)
         if save:
             self._saved = dict(m=m, feats=feats, x_last=x, lse_v=lse_v, ddpo_weight=ddpo_weight)
+            # TRL's `logits/chosen|rejected` = mean of the full [B,S,V] logits = dot(colsum(h), colsum(W_lm)) / (B*S*V)  (K19)
+            half = T // 2
+            cs = self.buf("m.colsum", (3, d), torch.float32)
+            ops.colsum_f32(h[:half], cs[0]); ops.colsum_f32(h[half:], cs[1]); ops.colsum_f32(w["lm_head"], cs[2])
+            self.logit_means = self.buf("m.logit_means", (2,), torch.float32)
+            inv = 1.0 / (float(half) * cfg.vocab)
+            ops.dot_f32(cs[0], cs[2], inv, self.logit_means[0:1]); ops.dot_f32(cs[1], cs[2], inv, self.logit_means[1:2])
         return logps
 
     # ------------------------------------------------------------------ backward of the policy copy
@@ -487,11 +494,13 @@ class LlavaDPOEngine:
         out = self.step(*self.prepare_inputs(ids, am, lb, px, wt), train=train)
         n = out.policy_logps.numel() // 2
         packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
-                            (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0)]).cpu()  # the D2H read
+                            (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0),
+                            (self.logit_means if train else out.stats[:2] * 0)]).cpu()  # the D2H read
         world = self.world_size()
         return {"loss": float(packed[0]), "rewards/accuracies": float(packed[1]), "rewards/chosen": float(packed[2]),
                 "rewards/rejected": float(packed[3]), "rewards/margins": float(packed[4]),
                 "logps/chosen": float(packed[6]), "logps/rejected": float(packed[7]),
+                "logits/chosen": float(packed[9]), "logits/rejected": float(packed[10]),
                 "grad_norm": float(packed[8]) ** 0.5 / world}
 
     def check_merge_status(self, m: "ops.MergeIndex"):

@@ -189,6 +189,20 @@ def colsum(a: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
     return out
 
 
+def colsum_f32(a: torch.Tensor, out: torch.Tensor):
+    rows, cols = a.shape
+    assert out.dtype == torch.float32 and out.numel() == cols
+    check(_L.vlb200_colsum_f32(_ptr(a), _rowmajor_ld(a), rows, cols, _ptr(out), _ptr(_workspace(max(cols, 8), a.device)),
+                               _stream()))
+    return out
+
+
+def dot_f32(a: torch.Tensor, b: torch.Tensor, scale: float, out: torch.Tensor):
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.numel() == b.numel()
+    check(_L.vlb200_dot_f32(_ptr(a), _ptr(b), a.numel(), scale, _ptr(out), _stream()))
+    return out
+
+
 def rope_(qkv: torch.Tensor, pos: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, n_rot_heads: int, head_dim: int,
           inverse: bool = False):
     assert pos.dtype == torch.int32 and cos_t.dtype == torch.float32 and sin_t.dtype == torch.float32
