@@ -284,7 +284,7 @@ def run_b200(args):
             "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                     "ms_per_step": ms_e2e, "last_metrics": last},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,4,K-major,K-major> (tcgen05, gate_up fwd shape)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,K-major> (tcgen05 cta_group::2, 256x256 pair tiles, gate_up fwd shape)",
                          "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
                          "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": _traffic()},
             "clocks": clocks,
