@@ -115,19 +115,33 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference's PyTorch-CPU path (oracle port), bounded sample of the same workload
 # ----------------------------------------------------------------------------------------------
-def cpu_sample_seconds_per_pair(threads: int):
-    """One pair (2 sequences x 1599 merged tokens) of the config-2 workload through the oracle port, with the
-    32 identical decoder layers sampled once: time(ViT+projector, 1 image) x 4 (the reference runs the tower for
-    chosen/rejected x policy/reference) + 32 x [layer fwd+bwd (policy) + layer fwd (reference)] + final
-    norm/lm_head/get_batch_logps fwd+bwd (policy) + fwd (reference) on the full [2,1599,32064] logits."""
+_CPU_W = {}
+
+
+def cpu_sample_setup(threads: int):
+    """7B-shape weights for the bounded CPU sample (ViT, projector, ONE decoder layer, final norm, lm_head); built once."""
     import torch
     from oracle import restate as R
     torch.set_num_threads(threads)
+    if "w" not in _CPU_W:
+        cfg = R.LLAVA15_7B
+        one = R.LlavaCfg(**{**cfg.__dict__, "layers": 1})
+        _CPU_W["one"] = one
+        _CPU_W["w"] = R.make_weights(one, 0, [n for n, *_ in R.weight_specs(one)])
+    return _CPU_W["one"], _CPU_W["w"]
+
+
+def cpu_sample_seconds_per_pair(threads: int):
+    """Bounded sample of the config-2 workload through the oracle port (the reference's PyTorch-CPU path): ONE sequence of
+    1599 merged tokens (half a pair; times are doubled), with the 32 identical decoder layers sampled once:
+    per pair = 4 x time(ViT+projector, 1 image)   [the reference runs the tower for chosen/rejected x policy/reference]
+             + 2 x { 32 x [layer fwd+bwd (policy) + layer fwd (reference)]
+                     + final norm/lm_head/get_batch_logps on the full [1,1599,32064] logits: fwd+bwd (policy) + fwd (reference) }"""
+    import torch
+    from oracle import restate as R
+    one, w = cpu_sample_setup(threads)
     cfg = R.LLAVA15_7B
     S, d = TEXT_LEN - 1 + cfg.n_patches, cfg.hidden
-    one = R.LlavaCfg(**{**cfg.__dict__, "layers": 1})
-    names = [n for n, *_ in R.weight_specs(one)]
-    w = R.make_weights(one, 0, names)
     g = torch.Generator().manual_seed(0)
     t = {}
     with torch.no_grad():
@@ -136,9 +150,9 @@ def cpu_sample_seconds_per_pair(threads: int):
         feats = R.clip_vision_features(cfg, w, px)[:, 1:]
         R.projector(cfg, w, feats)
         t["vit_proj_1img"] = time.perf_counter() - t0
-    x = torch.randn(2, S, d, generator=g) * 0.02
-    mask = torch.ones(2, S, dtype=torch.long)
-    pos = torch.arange(S)[None].expand(2, S)
+    x = torch.randn(1, S, d, generator=g) * 0.02
+    mask = torch.ones(1, S, dtype=torch.long)
+    pos = torch.arange(S)[None]
     lw = {k: v.clone().requires_grad_(True) for k, v in w.items() if k.startswith("language_model.model.layers.0.")}
     wl = dict(w)
     wl.update(lw)
@@ -146,30 +160,31 @@ def cpu_sample_seconds_per_pair(threads: int):
     t0 = time.perf_counter()
     h = R.llama_decoder(one, wl, xin, mask, pos, return_hidden=True)  # 1 layer + final norm
     h.sum().backward()
-    t["layer_fwd_bwd"] = time.perf_counter() - t0
+    t["layer_fwd_bwd_1seq"] = time.perf_counter() - t0
     with torch.no_grad():
         t0 = time.perf_counter()
         R.llama_decoder(one, w, x, mask, pos, return_hidden=True)
-        t["layer_fwd"] = time.perf_counter() - t0
-    labels = torch.randint(3, 32000, (2, S), generator=g)
+        t["layer_fwd_1seq"] = time.perf_counter() - t0
+    labels = torch.randint(3, 32000, (1, S), generator=g)
     labels[:, :PROMPT_LEN + cfg.n_patches - 1] = -100
     hw = w["language_model.lm_head.weight"].clone().requires_grad_(True)
     hh = h.detach().clone().requires_grad_(True)
     t0 = time.perf_counter()
     logits = torch.nn.functional.linear(hh, hw).float()
     R.get_batch_logps(logits, labels).sum().backward()
-    t["head_fwd_bwd"] = time.perf_counter() - t0
+    t["head_fwd_bwd_1seq"] = time.perf_counter() - t0
     with torch.no_grad():
         t0 = time.perf_counter()
         R.get_batch_logps(torch.nn.functional.linear(hh, hw).float(), labels)
-        t["head_fwd"] = time.perf_counter() - t0
-    per_pair = 4 * t["vit_proj_1img"] + cfg.layers * (t["layer_fwd_bwd"] + t["layer_fwd"]) + t["head_fwd_bwd"] + t["head_fwd"]
+        t["head_fwd_1seq"] = time.perf_counter() - t0
+    per_pair = 4 * t["vit_proj_1img"] + 2 * (cfg.layers * (t["layer_fwd_bwd_1seq"] + t["layer_fwd_1seq"]) + t["head_fwd_bwd_1seq"]
+                                             + t["head_fwd_1seq"])
     return per_pair, t
 
 
-CPU_SAMPLE_DESC = ("oracle port (torch fp32 CPU): 1 pair = 2 seq x 1599 tokens at 7B shapes; ViT+projector on 1 image x4, "
-                   "one decoder layer fwd+bwd and fwd timed and scaled x32, full-vocab lm_head+get_batch_logps fwd+bwd and fwd; "
-                   "optimizer and all-reduce not included")
+CPU_SAMPLE_DESC = ("oracle port (torch fp32 CPU), 7B shapes, ONE sequence of 1599 merged tokens (half a pair, doubled): ViT+projector "
+                   "on 1 image x4; one decoder layer fwd+bwd and fwd timed, scaled x32; full-vocab lm_head+get_batch_logps fwd+bwd and "
+                   "fwd; optimizer and all-reduce not included")
 
 
 def run_reference(args):
@@ -177,6 +192,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    cpu_sample_setup(cores)
     for _ in range(min(args.warmup, 1)):
         cpu_sample_seconds_per_pair(cores)
     ts = []

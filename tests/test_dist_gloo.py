@@ -39,6 +39,7 @@ def _worker(rank, world, port, out_dir):
     a = eng.prepare_inputs(cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"],
                            cb["concatenated_img_input_dict"]["pixel_values"])
     # local gradient (before the all-reduce) for the cross-check
+    eng.overlap_allreduce = False
     pol, m, feats = eng.forward_logps(*a[:4], which="policy", save=True)
     ref, _, _ = eng.forward_logps(*a[:4], which="ref", save=False, feats=feats, m=m)
     _, _, _, _, grad = mock_ops.dpo_loss(pol, ref, 0.1)
@@ -47,8 +48,14 @@ def _worker(rank, world, port, out_dir):
     eng.allreduce_grads()
     summed = eng.grads.clone()
     eng.optimizer_step()
+    # same step again from the same state with the per-layer buckets overlapped with backward: identical sums
+    eng2 = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3), device="cpu")
+    eng2.init_synthetic(0)
+    assert eng2.overlap_allreduce
+    eng2.step(*a[:4], train=True)
     torch.save({"local": local, "summed": summed, "params": eng.params.clone(), "world": eng.world_size(),
-                "sumsq": eng.grad_sumsq.clone()}, os.path.join(out_dir, f"rank{rank}.pt"))
+                "sumsq": eng.grad_sumsq.clone(), "params_overlap": eng2.params.clone(), "grads_overlap": eng2.grads.clone()},
+               os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,3 +77,6 @@ def test_two_rank_data_parallel_step(tmp_path):
     # identical replicas after the step
     assert torch.equal(r0["params"], r1["params"])
     assert torch.equal(r0["sumsq"], r1["sumsq"])
+    # bucketed + overlapped all-reduce gives the same reduced gradients and the same parameters
+    assert torch.equal(r0["grads_overlap"], r0["summed"]) and torch.equal(r1["grads_overlap"], r0["summed"])
+    assert torch.equal(r0["params_overlap"], r0["params"]) and torch.equal(r1["params_overlap"], r1["params"])

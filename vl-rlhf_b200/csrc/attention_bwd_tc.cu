@@ -14,6 +14,7 @@
 //
 // Replaces the autograd backward of LlamaAttention (modeling_llama.py:199-290).
 #include <algorithm>
+#include <type_traits>
 
 #include "ptx.cuh"
 
@@ -310,34 +311,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 const float* cl = sLse + tb * BY + half * 32;
                 const float* cd = sDelta + tb * BY + half * 32;
                 uint32_t e1[16], e2[16];
+                // two straight-line copies of the tile body (masked / unmasked): a per-element `if (need_mask)` costs a
+                // divergence region per element (seen in the r1 SASS: 33 BSSY/BSYNC pairs, 134 ISETP per 32 elements)
+                auto tile_body = [&](auto masked_tag) {
+                    constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-                for (int c4 = 0; c4 < 32; c4 += 4) {
-                    float l4[4], d4[4];
-                    if (MODE == 0) {
-                        const float4 a = *reinterpret_cast<const float4*>(cl + c4);
-                        const float4 d = *reinterpret_cast<const float4*>(cd + c4);
-                        l4[0] = a.x; l4[1] = a.y; l4[2] = a.z; l4[3] = a.w;
-                        d4[0] = d.x; d4[1] = d.y; d4[2] = d.z; d4[3] = d.w;
-                    } else {
+                    for (int c4 = 0; c4 < 32; c4 += 4) {
+                        float l4[4], d4[4];
+                        if (MODE == 0) {
+                            const float4 a = *reinterpret_cast<const float4*>(cl + c4);
+                            const float4 d = *reinterpret_cast<const float4*>(cd + c4);
+                            l4[0] = a.x; l4[1] = a.y; l4[2] = a.z; l4[3] = a.w;
+                            d4[0] = d.x; d4[1] = d.y; d4[2] = d.z; d4[3] = d.w;
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { l4[e] = row_lse2; d4[e] = row_delta; }
-                    }
-                    float pv[4], dv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int col = half * 32 + c4 + e;
-                        float pr = ex2_approx(fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]));
-                        if (need_mask) {
-                            const int key = MODE == 0 ? xrow : y0 + col;
-                            const int qi = MODE == 0 ? y0 + col : xrow;
-                            if (!(key < kv_len && qi < kv_len && (!p.causal || key <= qi))) pr = 0.f;
+                            for (int e = 0; e < 4; ++e) { l4[e] = row_lse2; d4[e] = row_delta; }
                         }
-                        pv[e] = pr;
-                        dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]) * p.scale;
+                        float pv[4], dv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = half * 32 + c4 + e;
+                            float pr = ex2_approx(fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]));
+                            if (MASKED) {
+                                const int key = MODE == 0 ? xrow : y0 + col;
+                                const int qi = MODE == 0 ? y0 + col : xrow;
+                                if (!(key < kv_len && qi < kv_len && (!p.causal || key <= qi))) pr = 0.f;
+                            }
+                            pv[e] = pr;
+                            dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]) * p.scale;
+                        }
+                        e1[c4 >> 1] = pack_bf16x2(pv[0], pv[1]); e1[(c4 >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+                        e2[c4 >> 1] = pack_bf16x2(dv[0], dv[1]); e2[(c4 >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
                     }
-                    e1[c4 >> 1] = pack_bf16x2(pv[0], pv[1]); e1[(c4 >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-                    e2[c4 >> 1] = pack_bf16x2(dv[0], dv[1]); e2[(c4 >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
-                }
+                };
+                if (need_mask) tile_body(std::true_type{});
+                else tile_body(std::false_type{});
                 // this E buffer is free once the accumulate MMAs of its previous use (two tiles back) have completed
                 const uint32_t eb = ec & 1;
                 if ((ec >> 1) > 0) mbar_wait(&e_done[eb], ((ec >> 1) - 1) & 1, 90 + eb);

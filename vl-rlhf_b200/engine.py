@@ -166,6 +166,10 @@ class LlavaDPOEngine:
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
+        import os as _os
+        # launch per-layer gradient buckets on the NCCL stream while backward continues (VLB200_OVERLAP_ALLREDUCE=0: one all-reduce)
+        self.overlap_allreduce = _os.environ.get("VLB200_OVERLAP_ALLREDUCE", "1") != "0"
+        self._pending = []
         self._bufs: Dict[str, torch.Tensor] = {}
         self._build_rope_tables()
 
@@ -361,6 +365,7 @@ class LlavaDPOEngine:
         dx = self.buf("b.dx0", (T, d))
         dx2 = self.buf("b.dx1", (T, d))
         ops.rmsnorm_bwd(dxf, sv["x_last"], w["norm"], self._bufs["a.rstd_f"], g["norm"], out=dx)
+        self._reduce_bucket(self.layout.offsets["norm"], self.layout.size)          # norm + lm_head gradients are final
         h = self.buf("s.h", (T, d))
         act = self.buf("s.act", (T, cfg.ff))
         dact = self.buf("b.dact", (T, cfg.ff))
@@ -393,6 +398,8 @@ class LlavaDPOEngine:
             ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"])            # dWqkv = dqkv^T h1
             ops.gemm(dqkv, w[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)                        # dh1 = dqkv Wqkv
             ops.rmsnorm_bwd(dnorm, x_in, w[f"L{i}.ln1"], rstd1, g[f"L{i}.ln1"], dres=dx2, out=dx)
+            self._reduce_bucket(self.layout.offsets[f"L{i}.ln1"],
+                                self.layout.offsets[f"L{i + 1}.ln1"] if i + 1 < cfg.layers else self.layout.offsets["norm"])
         # ---- embedding / merge / projector
         feats = sv["feats"]
         nimg = feats.shape[0]
@@ -408,12 +415,29 @@ class LlavaDPOEngine:
         ops.gelu_bwd(z, dph, out=dph)
         ops.gemm(dph, feats, a_kmajor=False, b_kmajor=False, out=g["proj.w1"])
         ops.colsum(dph, g["proj.b1"])
+        self._reduce_bucket(0, self.layout.offsets["L0.ln1"])                         # projector + embedding
 
     # ------------------------------------------------------------------ optimizer + data parallel
+    def _dist_on(self) -> bool:
+        return torch.distributed.is_available() and torch.distributed.is_initialized() and self.world_size() > 1
+
+    def _reduce_bucket(self, lo: int, hi: int):
+        """Bucketed all-reduce overlapped with backward: the gradients in [lo, hi) of the flat buffer are final, so
+        their sum-reduction starts now on the NCCL stream (ordered after the kernels already enqueued)."""
+        if self.overlap_allreduce and self._dist_on() and hi > lo:
+            self._pending.append(torch.distributed.all_reduce(self.grads[lo:hi], op=torch.distributed.ReduceOp.SUM,
+                                                              group=self.pg, async_op=True))
+
     def allreduce_grads(self):
-        """ONE NCCL all-reduce over the flat bf16 gradient buffer (sum; the 1/world scale is folded into AdamW)."""
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                   and torch.distributed.get_world_size() > 1):
+        """Gradient all-reduce over the flat bf16 buffer (sum; the 1/world scale is folded into AdamW): either the
+        per-layer buckets launched during backward are awaited, or one all-reduce covers the whole buffer."""
+        if not self._dist_on():
+            return
+        if self._pending:
+            for h in self._pending:
+                h.wait()
+            self._pending = []
+        else:
             torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
     def world_size(self) -> int:
