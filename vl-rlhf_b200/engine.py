@@ -167,8 +167,11 @@ class LlavaDPOEngine:
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
         import os as _os
-        # launch per-layer gradient buckets on the NCCL stream while backward continues (VLB200_OVERLAP_ALLREDUCE=0: one all-reduce)
-        self.overlap_allreduce = _os.environ.get("VLB200_OVERLAP_ALLREDUCE", "1") != "0"
+        # VLB200_OVERLAP_ALLREDUCE=1 launches per-layer gradient buckets on the NCCL stream while backward continues.
+        # Measured on 2xB200 (profiles/r1_bench_7b_2gpu_overlap.md): 697.4 ms/step overlapped vs 689.9 ms with ONE
+        # all-reduce after backward -- the NCCL kernels take SMs from the persistent GEMMs' static tile schedule and
+        # cost more than the ~28 ms they hide, so the single all-reduce is the default.
+        self.overlap_allreduce = _os.environ.get("VLB200_OVERLAP_ALLREDUCE", "0") == "1"
         self._pending = []
         self._bufs: Dict[str, torch.Tensor] = {}
         self._build_rope_tables()
