@@ -173,6 +173,24 @@ int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* d
                            void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq, int d,
                            void* stream);
 
+/* ---- LLaVA-Next text/image merge -- models/LlavaNext/__init__.py:38-171 (_merge_input_ids_with_image_features)
+ * Differences from the LLaVA-1.5 merge above: image k contributes feat_off[k+1]-feat_off[k] PACKED feature rows
+ * (anyres "spatial_unpad" + image_newline, modeling_llava_next.py pack_image_features; the row gather that builds
+ * them is vlb200_gather_rows over the index vl-rlhf_b200/host.py:anyres_pack_index computes), tokens whose
+ * attention_mask is 0 are never written, merged_len is the longest valid merged sequence (host-computed:
+ * (mask==1).sum() - n_image_tokens + sum(feature_lens), :83-87) and pad-token embeddings are kept.  Right padding
+ * only (status 3 otherwise).  img_rows[rep*total_feats + k] = flat merged row of packed feature row k in the rep-th
+ * sequence sharing the image (rep = seq / n_img_batch: chosen, rejected).  status: 0 ok, 1 overflow of merged_len,
+ * 2 wrong number of <image> tokens (:75-79), 3 not right-padded, 4 masked <image> token. */
+int vlb200_llavanext_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels,
+                                 const int* feat_off, int n_seq, int text_len, int merged_len, int n_img_batch,
+                                 int imgs_per_seq, int total_feats, int image_token, int ignore_index, int* src_map,
+                                 int64_t* labels_merged, int* mask_merged, int* position_ids, int* seqlens, int* img_rows,
+                                 int* row_of_text, int64_t* target, int* status, void* stream);
+/* backward of the merge: dembed_f32[id] += dx[row] for text rows; dimage_features[k] = sum_rep dx[img_rows[rep, k]] */
+int vlb200_llavanext_merge_bwd(const int* src_map, const int* img_rows, const void* dx, float* dembed_f32,
+                               void* dimage_features, int n_rows, int total_feats, int reps, int d, void* stream);
+
 /* ---- attention (K4, K12) -- CLIPAttention (modeling_clip.py:261-334), LlamaAttention
  * (modeling_llama.py:199-290).  q/k/v/out rows are tokens (row = b*S + t), head h at column h*head_dim.
  * causal + key-padding via seqlens[B] (attended prefix length; NULL = S).  lse/delta: [B,H,S] f32.

@@ -43,6 +43,26 @@ def hf_config(cfg: R.LlavaCfg):
     return c
 
 
+def hf_config_next(cfg: R.LlavaCfg):
+    """llava-v1.6-mistral-7b-hf style config: CLIP tower + MistralConfig decoder (no sliding window) + anyres pinpoints."""
+    from transformers import CLIPVisionConfig, LlavaNextConfig, MistralConfig
+    v = CLIPVisionConfig(hidden_size=cfg.v_hidden, intermediate_size=cfg.v_ff, num_hidden_layers=cfg.v_layers,
+                         num_attention_heads=cfg.v_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                         hidden_act="quick_gelu", layer_norm_eps=cfg.v_eps, projection_dim=cfg.v_hidden)
+    t = MistralConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.ff,
+                      num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads, num_key_value_heads=cfg.kv_heads,
+                      rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
+                      sliding_window=None, tie_word_embeddings=False, head_dim=cfg.head_dim)
+    c = LlavaNextConfig(vision_config=v, text_config=t, image_token_index=cfg.image_token_index,
+                        projector_hidden_act="gelu", vision_feature_select_strategy="default",
+                        vision_feature_layer=cfg.vision_feature_layer, tie_word_embeddings=False,
+                        image_grid_pinpoints=[list(p) for p in cfg.image_grid_pinpoints])
+    c.pad_token_id = cfg.pad_token_id
+    c.ignore_index = cfg.ignore_index
+    c._attn_implementation = "eager"
+    return c
+
+
 def hf_name(name: str) -> str:
     """transformers-4.41 parameter name -> transformers-5.5 LlavaForConditionalGeneration name."""
     if name == "language_model.lm_head.weight":
@@ -67,7 +87,11 @@ def streamed_weights(cfg: R.LlavaCfg, seed: int, which: str):
 def build_reference_model(cfg: R.LlavaCfg, weights):
     """weights: dict name->tensor, or an iterator of (name, tensor)."""
     _, _, LlavaShim = ref_shim.reference_symbols()
-    hc = hf_config(cfg)
+    if cfg.family == "llava_next":
+        from oracle._llavanext_shim import LlavaNextShim as LlavaShim  # noqa: F811
+        hc = hf_config_next(cfg)
+    else:
+        hc = hf_config(cfg)
     with torch.device("meta"):
         m = LlavaShim(hc)
     m = m.to_empty(device="cpu")
@@ -208,9 +232,12 @@ def g3_ddpo():
     np.savez_compressed(os.path.join(GOLDEN, "g3_ddpo.npz"), **out)
 
 
-def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed: int, ddpo: bool):
-    batch = R.make_batch(cfg, n_pairs, text_len, prompt_len, seed, ddpo_like=ddpo)
+def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed: int, ddpo: bool,
+              image_sizes=None):
+    batch = R.make_batch(cfg, n_pairs, text_len, prompt_len, seed, ddpo_like=ddpo, image_sizes=image_sizes)
     out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
+    if image_sizes is not None:
+        out["image_sizes"] = np.asarray(image_sizes, dtype=np.int64)
     res = {}
     for who in ("policy", "ref"):
         t0 = time.time()
@@ -246,6 +273,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config1", action="store_true")
     ap.add_argument("--config1-bf16", dest="config1_bf16", action="store_true")
+    ap.add_argument("--next", action="store_true", help="only the LLaVA-Next fixtures (g6_*)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -256,11 +284,22 @@ def main():
         # BASELINE.json configs[0]: LLaVA-1.5-7B shapes, 2 pairs, text 128 (+575 -> 703), fp32 CPU
         g45_llava("g5_config1_7b", R.LLAVA15_7B, 2, 128, 32, 0, ddpo=False)
         return
+    if args.next:
+        g6_next()
+        return
     g1_logps()
     g2_loss()
     g3_ddpo()
     g45_llava("g4_tiny", R.TINY, 2, 24, 8, 0, ddpo=True)
     g45_llava("g4_small", R.SMALL, 2, 96, 24, 0, ddpo=True)
+    g6_next()
+
+
+def g6_next():
+    """LLaVA-Next (models/LlavaNext LlavaNextForRL through oracle/_llavanext_shim.py): anyres crops of mixed aspect
+    ratios (square -> 2x2 grid, wide -> 1x2 / 1x3 with unpadding, tall -> 2x1), image_newline, GQA decoder, DDPO."""
+    g45_llava("g6_next_tiny", R.TINY_NEXT, 3, 24, 8, 0, ddpo=True, image_sizes=[(28, 28), (20, 50), (60, 25)])
+    g45_llava("g6_next_small", R.SMALL_NEXT, 2, 96, 24, 0, ddpo=True, image_sizes=[(112, 112), (90, 300)])
 
 
 

@@ -49,6 +49,9 @@ class LlavaCfg:
     image_token_index: int = 32000
     pad_token_id: int = 32001
     ignore_index: int = -100
+    # "llava" (models/Llava) | "llava_next" (models/LlavaNext: anyres crops, image_newline, Mistral/Vicuna decoder)
+    family: str = "llava"
+    image_grid_pinpoints: Tuple[Tuple[int, int], ...] = ()
 
     @property
     def n_patches(self) -> int:
@@ -80,6 +83,23 @@ TINY = LlavaCfg(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_heads=
 SMALL = LlavaCfg(image_size=112, patch_size=14, v_hidden=256, v_layers=3, v_heads=4, v_ff=512,
                  hidden=512, layers=2, heads=4, kv_heads=4, ff=1024, vocab=2048,
                  image_token_index=2000, pad_token_id=2001)
+
+
+# LLaVA-Next (llava-v1.6-mistral-7b-hf config.json): CLIP-L/336 tower, Mistral-7B decoder (GQA 32/8, ff 14336,
+# rope theta 1e6, no sliding window in -Instruct-v0.2), anyres pinpoints
+LLAVA_NEXT_PINPOINTS = ((336, 672), (672, 336), (672, 672), (1008, 336), (336, 1008))
+LLAVANEXT_MISTRAL_7B = LlavaCfg(hidden=4096, layers=32, heads=32, kv_heads=8, ff=14336, vocab=32064, rope_theta=1e6,
+                                image_token_index=32000, pad_token_id=32001, family="llava_next",
+                                image_grid_pinpoints=LLAVA_NEXT_PINPOINTS)
+_TINY_PINS = ((28, 56), (56, 28), (56, 56), (84, 28), (28, 84))
+TINY_NEXT = LlavaCfg(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_heads=2, v_ff=256,
+                     hidden=256, layers=2, heads=4, kv_heads=2, ff=256, vocab=320, rope_theta=1e6,
+                     image_token_index=300, pad_token_id=301, family="llava_next", image_grid_pinpoints=_TINY_PINS)
+_SMALL_PINS = ((112, 224), (224, 112), (224, 224), (336, 112), (112, 336))
+SMALL_NEXT = LlavaCfg(image_size=112, patch_size=14, v_hidden=256, v_layers=3, v_heads=4, v_ff=512,
+                      hidden=512, layers=2, heads=4, kv_heads=2, ff=1024, vocab=2048, rope_theta=1e6,
+                      image_token_index=2000, pad_token_id=2001, family="llava_next",
+                      image_grid_pinpoints=_SMALL_PINS)
 
 
 # --------------------------------------------------------------------------------------
@@ -148,15 +168,17 @@ def weight_specs(cfg: LlavaCfg) -> List[Tuple[str, Tuple[int, ...], float, float
         ("multi_modal_projector.linear_2.bias", (cfg.hidden,), 0.02, 0.0),
         ("language_model.model.embed_tokens.weight", (cfg.vocab, cfg.hidden), a, 0.0),
     ]
+    if cfg.family == "llava_next":  # nn.Parameter of LlavaNextForConditionalGeneration (modeling_llava_next.py)
+        specs.append(("image_newline", (cfg.hidden,), a, 0.0))
     kv = cfg.kv_heads * cfg.head_dim
     for i in range(cfg.layers):
         p = f"language_model.model.layers.{i}."
         specs += [
             (p + "input_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
-            (p + "self_attn.q_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+            (p + "self_attn.q_proj.weight", (cfg.heads * cfg.head_dim, cfg.hidden), a, 0.0),
             (p + "self_attn.k_proj.weight", (kv, cfg.hidden), a, 0.0),
             (p + "self_attn.v_proj.weight", (kv, cfg.hidden), a, 0.0),
-            (p + "self_attn.o_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+            (p + "self_attn.o_proj.weight", (cfg.hidden, cfg.heads * cfg.head_dim), a, 0.0),
             (p + "post_attention_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
             (p + "mlp.gate_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),
             (p + "mlp.up_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),
@@ -184,7 +206,7 @@ def make_weights(cfg: LlavaCfg, seed: int, names: Optional[List[str]] = None) ->
 # --------------------------------------------------------------------------------------
 
 def make_batch(cfg: LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed: int,
-               ddpo_like: bool = False) -> Dict[str, torch.Tensor]:
+               ddpo_like: bool = False, image_sizes: Optional[List[Tuple[int, int]]] = None) -> Dict[str, torch.Tensor]:
     """Collated batch exactly as VLDPODataCollatorWithPadding emits it (base/collator.py:26-68):
     right-padded chosen_/rejected_ input_ids / attention_mask / labels + img_input_dict.pixel_values.
     One <image> placeholder at position 1 (after BOS); labels = -100 on prompt and padding."""
@@ -220,6 +242,20 @@ def make_batch(cfg: LlavaCfg, n_pairs: int, text_len: int, prompt_len: int, seed
         out[f"{key}_input_ids"] = torch.from_numpy(ids)
         out[f"{key}_attention_mask"] = torch.from_numpy(mask)
         out[f"{key}_labels"] = torch.from_numpy(labels)
+    if cfg.family == "llava_next":
+        # LlavaNextProcessor output (models/LlavaNext/__init__.py:348-380 collate): pixel_values [B, max_crops, 3, H, W]
+        # (base crop first, zero-padded to the largest crop count) + image_sizes [B, 2] = (height, width)
+        sizes = image_sizes if image_sizes is not None else [(cfg.image_size, cfg.image_size)] * B
+        assert len(sizes) == B
+        crops = [image_size_to_num_patches(sz, cfg.image_grid_pinpoints, cfg.image_size) for sz in sizes]
+        mc = max(crops)
+        n_pix = B * mc * 3 * cfg.image_size * cfg.image_size
+        pix = bf16_round(hash_uniform(n_pix, tensor_seed("pixel_values", seed), 1.7320508)).reshape(
+            B, mc, 3, cfg.image_size, cfg.image_size).clone()
+        for b in range(B):
+            pix[b, crops[b]:] = 0
+        out["img_input_dict"] = {"pixel_values": pix, "image_sizes": torch.tensor(sizes, dtype=torch.int64)}
+        return out
     n_pix = B * 3 * cfg.image_size * cfg.image_size
     pix = bf16_round(hash_uniform(n_pix, tensor_seed("pixel_values", seed), 1.7320508)).reshape(
         B, 3, cfg.image_size, cfg.image_size)
@@ -516,6 +552,156 @@ def llava_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, attentio
 
 
 # --------------------------------------------------------------------------------------
+# LLaVA-Next: transformers-4.41 modeling_llava_next.py helpers (select_best_resolution from
+# image_processing_utils.py, get_anyres_image_grid_shape, image_size_to_num_patches, unpad_image,
+# pack_image_features) + models/LlavaNext/__init__.py:38-171 merge and :173-345 forward
+# --------------------------------------------------------------------------------------
+
+def select_best_resolution(original_size, possible_resolutions):
+    """(height, width) of the pinpoint with the largest effective and then smallest wasted resolution."""
+    oh, ow = original_size
+    best, max_eff, min_waste = None, 0, float("inf")
+    for h, w in possible_resolutions:
+        scale = min(w / ow, h / oh)
+        dw, dh = int(ow * scale), int(oh * scale)
+        eff = min(dw * dh, ow * oh)
+        waste = w * h - eff
+        if eff > max_eff or (eff == max_eff and waste < min_waste):
+            max_eff, min_waste, best = eff, waste, (h, w)
+    return best
+
+
+def _as_pair(x):
+    return tuple(int(v) for v in (x.tolist() if hasattr(x, "tolist") else x))
+
+
+def get_anyres_image_grid_shape(image_size, grid_pinpoints, patch_size):
+    h, w = select_best_resolution(_as_pair(image_size), [tuple(p) for p in grid_pinpoints])
+    return h // patch_size, w // patch_size
+
+
+def image_size_to_num_patches(image_size, grid_pinpoints, patch_size) -> int:
+    """number of crops the processor emitted for this image: the grid cells + the base crop."""
+    h, w = select_best_resolution(_as_pair(image_size), [tuple(p) for p in grid_pinpoints])
+    return len(range(0, h, patch_size)) * len(range(0, w, patch_size)) + 1
+
+
+def unpad_image(t: torch.Tensor, original_size) -> torch.Tensor:
+    """[C, H, W] feature map of the padded+resized image -> the rows/cols that hold the original aspect."""
+    oh, ow = _as_pair(original_size)
+    ch, cw = t.shape[1:]
+    if ow / oh > cw / ch:
+        new_h = int(round(oh * (cw / ow), 7))
+        pad = (ch - new_h) // 2
+        return t[:, pad:ch - pad, :]
+    new_w = int(round(ow * (ch / oh), 7))
+    pad = (cw - new_w) // 2
+    return t[:, :, pad:cw - pad]
+
+
+def pack_image_features(cfg: LlavaCfg, image_features: List[torch.Tensor], image_sizes, image_newline: torch.Tensor):
+    """"spatial_unpad": base crop features, then the grid crops stitched into one [gh*g, gw*g] map, unpadded,
+    one image_newline appended per map row.  -> (concatenated [sum F, d], feature_lens [n_images])."""
+    new, lens = [], []
+    g = cfg.image_size // cfg.patch_size
+    for i, feat in enumerate(image_features):
+        if feat.shape[0] > 1:
+            base, rest = feat[0], feat[1:]
+            gh, gw = get_anyres_image_grid_shape(image_sizes[i], cfg.image_grid_pinpoints, cfg.image_size)
+            rest = rest.view(gh, gw, g, g, -1).permute(4, 0, 2, 1, 3).contiguous().flatten(1, 2).flatten(2, 3)
+            rest = unpad_image(rest, image_sizes[i])
+            rest = torch.cat((rest, image_newline[:, None, None].expand(*rest.shape[:-1], 1).to(rest.dtype)), dim=-1)
+            feat = torch.cat((base, rest.flatten(1, 2).transpose(0, 1)), dim=0)
+        else:
+            feat = torch.cat((feat[0], image_newline[None].to(feat.dtype)), dim=0)
+        new.append(feat)
+        lens.append(feat.shape[0])
+    return torch.cat(new, dim=0), torch.tensor(lens, dtype=torch.long)
+
+
+def next_merge_input_ids_with_image_features(cfg: LlavaCfg, image_features, feature_lens, inputs_embeds, input_ids,
+                                             attention_mask, labels, padding_side: str = "right"):
+    """models/LlavaNext/__init__.py:38-171.  Unlike the LLaVA-1.5 merge, tokens with attention_mask == 0 are not
+    written at all and the merged length is the longest VALID merged sequence."""
+    num_image_features, embed_dim = image_features.shape
+    if int(feature_lens.sum()) != num_image_features:
+        raise ValueError(f"{feature_lens=} / {feature_lens.sum()} != {image_features.shape=}")
+    batch_size = input_ids.shape[0]
+    _left = bool(torch.any(attention_mask[:, 0] == 0))
+    _right = bool(torch.any(attention_mask[:, -1] == 0))
+    left_padding = True
+    if batch_size > 1:
+        if _left and not _right:
+            left_padding = True
+        elif not _left and _right:
+            left_padding = False
+        elif not _left and not _right:
+            left_padding = padding_side == "left"
+        else:
+            raise ValueError(f"both side of attention_mask has zero, invalid. {attention_mask}")
+    special = input_ids == cfg.image_token_index
+    num_special = torch.sum(special, dim=-1)
+    if int(special.sum()) != feature_lens.shape[0]:
+        raise ValueError(f"Number of image tokens in input_ids ({int(special.sum())}) different from num_images "
+                         f"({feature_lens.shape[0]}).")
+    per_seq = torch.tensor([int(x.sum()) for x in feature_lens.split(num_special.tolist(), dim=0)])
+    embed_sequence_lengths = (attention_mask == 1).long().sum(-1) - num_special + per_seq
+    max_embed_dim = int(embed_sequence_lengths.max())
+    batch_indices, non_image_indices = torch.where((input_ids != cfg.image_token_index) & (attention_mask == 1))
+    step = special.long()
+    step[step == 1] = feature_lens - 1
+    new_token_positions = torch.cumsum(step + 1, -1) - 1
+    if left_padding:
+        new_token_positions = new_token_positions + (max_embed_dim - 1 - new_token_positions[:, -1:])
+    text_to_overwrite = new_token_positions[batch_indices, non_image_indices]
+    final_embedding = torch.zeros(batch_size, max_embed_dim, embed_dim, dtype=inputs_embeds.dtype)
+    final_attention_mask = torch.zeros(batch_size, max_embed_dim, dtype=attention_mask.dtype)
+    final_labels = torch.full((batch_size, max_embed_dim), cfg.ignore_index, dtype=torch.long)
+    final_embedding[batch_indices, text_to_overwrite] = inputs_embeds[batch_indices, non_image_indices]
+    final_attention_mask[batch_indices, text_to_overwrite] = attention_mask[batch_indices, non_image_indices]
+    final_labels[batch_indices, text_to_overwrite] = labels[batch_indices, non_image_indices]
+    image_to_overwrite = torch.full((batch_size, max_embed_dim), True)
+    image_to_overwrite[batch_indices, text_to_overwrite] = False
+    idx = torch.arange(max_embed_dim)[None].expand(batch_size, max_embed_dim)
+    lens = embed_sequence_lengths[:, None]
+    image_to_overwrite &= ((max_embed_dim - idx) <= lens) if left_padding else (idx < lens)
+    if int(image_to_overwrite.sum()) != num_image_features:
+        raise ValueError(f"{image_to_overwrite.sum()=} != {num_image_features=} The input provided to the model are "
+                         "wrong.")
+    final_embedding[image_to_overwrite] = image_features.contiguous().reshape(-1, embed_dim)
+    final_attention_mask |= image_to_overwrite
+    position_ids = (final_attention_mask.cumsum(-1) - 1).masked_fill_((final_attention_mask == 0), 1)
+    return final_embedding, final_attention_mask, final_labels, position_ids, image_to_overwrite
+
+
+def llava_next_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, attention_mask, labels, pixel_values,
+                       image_sizes):
+    """models/LlavaNext/__init__.py:173-345, training branch -> (logits, labels, image_position_map)."""
+    ids0 = input_ids.clone()
+    ids0[input_ids == cfg.image_token_index] = 0  # :203-205
+    inputs_embeds = F.embedding(ids0, w["language_model.model.embed_tokens.weight"])
+    crops = [image_size_to_num_patches(sz, cfg.image_grid_pinpoints, cfg.image_size) for sz in image_sizes]  # :211-218
+    if pixel_values.dim() == 5:
+        pixel_values = torch.cat([pv[:n] for pv, n in zip(pixel_values, crops)], dim=0)  # :220-225
+    elif pixel_values.dim() != 4:
+        raise ValueError(f"pixel_values of shape {pixel_values.shape}, expect to be of 4 or 5 dimensions")
+    feats = clip_vision_features(cfg, w, pixel_values)[:, 1:]  # :230-236
+    image_features = projector(cfg, w, feats)  # :238
+    image_features = torch.split(image_features, crops, dim=0)
+    image_features, feature_lens = pack_image_features(cfg, list(image_features), image_sizes, w["image_newline"])
+    emb, mask, new_labels, pos, img_map = next_merge_input_ids_with_image_features(
+        cfg, image_features, feature_lens, inputs_embeds, input_ids, attention_mask, labels)  # :251-262
+    logits = llama_decoder(cfg, w, emb, mask, pos)
+    return logits, new_labels, img_map
+
+
+def model_forward(cfg: LlavaCfg, w, input_ids, attention_mask, labels, **img):
+    if cfg.family == "llava_next":
+        return llava_next_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"], img["image_sizes"])
+    return llava_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"])
+
+
+# --------------------------------------------------------------------------------------
 # base/trainer.py:190-242 concatenated_forward  +  trl 0.8.1 get_batch_loss_metrics (restated)
 # --------------------------------------------------------------------------------------
 
@@ -523,7 +709,7 @@ def concatenated_forward(cfg: LlavaCfg, w, batch, loss_type: str = "sigmoid", la
                          padding_value: int = 0):
     cb = concatenated_inputs(batch, label_pad_token_id, padding_value)
     n = batch["chosen_labels"].shape[0]
-    logits, final_labels, _ = llava_forward(cfg, w, cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+    logits, final_labels, _ = model_forward(cfg, w, cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
                                             cb["concatenated_labels"], **cb["concatenated_img_input_dict"])
     all_logps = get_batch_logps(logits, final_labels, mask_shared_tokens=(loss_type == "ddpo"),
                                 label_pad_token_id=label_pad_token_id)

@@ -365,6 +365,90 @@ def llava_merge_bwd(m, dx, dembed_f32, dimage_features):
     _c(2)
 
 
+
+def llavanext_merge_index(input_ids, attention_mask, labels, feat_off, total_feats, merged_len, n_img_batch,
+                          imgs_per_seq, image_token, ignore_index=-100):
+    INT_MIN = -(2 ** 31)
+    n_seq, L = input_ids.shape
+    S = int(merged_len)
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, S, -1, n_img_batch, imgs_per_seq
+    m.total_feats, m.reps = int(total_feats), n_seq // n_img_batch
+    m.src_map = torch.full((n_seq * S,), INT_MIN, dtype=torch.int32)
+    m.labels = torch.full((n_seq, S), ignore_index, dtype=torch.int64)
+    m.mask = torch.zeros(n_seq, S, dtype=torch.int32)
+    m.pos = torch.ones(n_seq * S, dtype=torch.int32)
+    m.seqlens = torch.zeros(n_seq, dtype=torch.int32)
+    m.img_pos = torch.zeros(m.reps * m.total_feats, dtype=torch.int32)
+    m.row_of_text = torch.zeros(n_seq * (L - 1), dtype=torch.int32)
+    m.target = torch.full((n_seq * (L - 1),), -100, dtype=torch.int64)
+    m.status = torch.zeros(1, dtype=torch.int32)
+    off = feat_off.tolist()
+    for b in range(n_seq):
+        p = slot = 0
+        seen_masked = False
+        base = (b % n_img_batch) * imgs_per_seq
+        rep = b // n_img_batch
+        for j in range(L):
+            t = int(input_ids[b, j])
+            rj = b * (L - 1) + j - 1
+            if int(attention_mask[b, j]) == 0:
+                seen_masked = True
+                if t == image_token:
+                    m.status[0] = 4
+                if j >= 1:
+                    m.row_of_text[rj] = b * S
+                continue
+            if seen_masked:
+                m.status[0] = 3
+            if t == image_token:
+                if slot < imgs_per_seq and p + off[base + slot + 1] - off[base + slot] <= S:
+                    k0, F = off[base + slot], off[base + slot + 1] - off[base + slot]
+                    for f in range(F):
+                        m.src_map[b * S + p + f] = -1 - (k0 + f)
+                        m.mask[b, p + f] = 1
+                        m.img_pos[rep * m.total_feats + k0 + f] = b * S + p + f
+                else:
+                    F = 0
+                    m.status[0] = 1
+                if j >= 1:
+                    m.row_of_text[rj] = b * S + max(p - 1, 0)
+                p += F
+                slot += 1
+            else:
+                if p < S:
+                    m.src_map[b * S + p] = t
+                    m.mask[b, p] = 1
+                    m.labels[b, p] = int(labels[b, j])
+                else:
+                    m.status[0] = 1
+                if j >= 1:
+                    m.row_of_text[rj] = b * S + max(p - 1, 0)
+                    lv = int(labels[b, j])
+                    m.target[rj] = -100 if (lv == ignore_index or p == 0) else lv
+                p += 1
+        if slot != imgs_per_seq:
+            m.status[0] = 2
+        if p > S:
+            m.status[0] = 1
+        n = min(p, S)
+        m.pos[b * S:b * S + n] = torch.arange(n, dtype=torch.int32)
+        m.seqlens[b] = n
+    _c()
+    return m
+
+
+def llavanext_merge_bwd(m, dx, dembed_f32, dimage_features):
+    s = m.src_map.long()
+    t = s >= 0
+    dembed_f32.index_add_(0, s[t], dx[t].float())
+    rows = m.img_pos.long().view(m.reps, m.total_feats)
+    acc = torch.zeros(dimage_features.shape, dtype=torch.float32)
+    for r in range(m.reps):
+        acc += dx[rows[r]].float()
+    dimage_features.copy_(acc.to(dimage_features.dtype))
+    _c(2)
+
 def _attn_ref(q, k, v, seqlens, B, S, H, KVH, dh, causal, scale):
     qf = q.float().reshape(B, S, H, dh)
     kf = k.float().reshape(B, S, KVH, dh).repeat_interleave(H // KVH, 2)

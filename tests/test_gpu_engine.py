@@ -22,7 +22,10 @@ def pkg():
     return config, engine, host, ops
 
 
-CASES = {"g4_tiny": ("TINY", R.TINY, 2, 24, 8), "g4_small": ("SMALL", R.SMALL, 2, 96, 24)}
+CASES = {"g4_tiny": ("TINY", R.TINY, 2, 24, 8), "g4_small": ("SMALL", R.SMALL, 2, 96, 24),
+         # LLaVA-Next (models/LlavaNext): anyres crops with unpadding, image_newline, GQA 4/2, rope theta 1e6
+         "g6_next_tiny": ("TINY_NEXT", R.TINY_NEXT, 3, 24, 8), "g6_next_small": ("SMALL_NEXT", R.SMALL_NEXT, 2, 96, 24)}
+ALL_TAGS = list(CASES)
 
 
 def build(pkg, tag, loss_type="sigmoid", with_optimizer=True):
@@ -33,18 +36,21 @@ def build(pkg, tag, loss_type="sigmoid", with_optimizer=True):
     eng = engine.LlavaDPOEngine(getattr(config, name), config.TrainConfig(loss_type=loss_type, learning_rate=1e-3),
                                 with_optimizer=with_optimizer)
     eng.init_synthetic(seed)
-    batch = R.make_batch(rcfg, npairs, tl, pl, seed, ddpo_like=True)
+    sizes = [tuple(x) for x in d["image_sizes"].tolist()] if "image_sizes" in d.files else None
+    batch = R.make_batch(rcfg, npairs, tl, pl, seed, ddpo_like=True, image_sizes=sizes)
     cb = host.concatenated_inputs(batch)
     return eng, rcfg, d, batch, cb
 
 
 def stage(eng, host, cb, rcfg, ddpo=False):
+    """-> the argument tuple of eng.step (5 entries, 6 with the anyres plan for LLaVA-Next)."""
     ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
-    wt = host.ddpo_row_weights(ids, lb, rcfg.image_token_index, rcfg.n_patches) if ddpo else None
-    return eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"], wt)
+    img = cb["concatenated_img_input_dict"]
+    wt = eng.ddpo_weights(ids, am, lb, img.get("image_sizes")) if ddpo else None
+    return eng.prepare_inputs(ids, am, lb, img["pixel_values"], wt, img.get("image_sizes"))
 
 
-@pytest.mark.parametrize("tag", ["g4_tiny", "g4_small"])
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_synthetic_weights_bit_exact(pkg, tag):
     eng, rcfg, d, batch, cb = build(pkg, tag, with_optimizer=False)
     wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
@@ -61,12 +67,19 @@ def test_synthetic_weights_bit_exact(pkg, tag):
     assert n_checked > 20
 
 
-@pytest.mark.parametrize("tag", ["g4_tiny", "g4_small"])
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_forward_logps_and_loss_parity(pkg, tag):
     config, engine, host, ops = pkg
     eng, rcfg, d, batch, cb = build(pkg, tag, with_optimizer=False)
-    ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
-    out = eng.step(ids, am, lb, px, train=False)
+    a = stage(eng, host, cb, rcfg)
+    out = eng.step(*a, train=False)
+    if len(a) == 6:  # LLaVA-Next: the merged labels are bit-exact with the reference's (integer work)
+        m = ops.llavanext_merge_index(a[0], a[1], a[2], a[5].feat_off, a[5].total_feats, a[5].merged_len, len(a[5].crops),
+                                      1, rcfg.image_token_index)
+        assert int(m.status) == 0
+        assert np.array_equal(m.labels.cpu().numpy(), d["labels"])
+        src = m.src_map.view(m.n_seq, m.S)
+        assert np.array_equal(((src < 0) & (src != -(2 ** 31))).cpu().numpy(), d["image_position_map"])
     pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
     # golden = reference LlavaForRL.forward + get_batch_logps (fp32 CPU)
     np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
@@ -91,24 +104,23 @@ def test_forward_logps_and_loss_parity(pkg, tag):
                                    rtol=2e-2 if lt == "ipo" else 0)
 
 
-@pytest.mark.parametrize("tag", ["g4_tiny", "g4_small"])
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_ddpo_parity(pkg, tag):
     config, engine, host, ops = pkg
     eng, rcfg, d, batch, cb = build(pkg, tag, loss_type="ddpo", with_optimizer=False)
-    ids, am, lb, px, wt = stage(eng, host, cb, rcfg, ddpo=True)
-    assert int(wt.sum()) > 0
-    out = eng.step(ids, am, lb, px, ddpo_weight=wt, train=False)
+    a = stage(eng, host, cb, rcfg, ddpo=True)
+    assert int(a[4].sum()) > 0
+    out = eng.step(*a, train=False)
     np.testing.assert_allclose(out.policy_logps.cpu().numpy(), d["policy_logps_ddpo"], rtol=1e-3, atol=1e-2)
     np.testing.assert_allclose(out.ref_logps.cpu().numpy(), d["ref_logps_ddpo"], rtol=1e-3, atol=1e-2)
     np.testing.assert_allclose(out.losses.cpu().numpy(), d["ddpo_losses"], atol=5e-3)
 
 
-@pytest.mark.parametrize("tag", ["g4_tiny", "g4_small"])
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_backward_matches_oracle_autograd(pkg, tag):
     config, engine, host, ops = pkg
     eng, rcfg, d, batch, cb = build(pkg, tag, with_optimizer=False)
-    ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
-    eng.step(ids, am, lb, px, train=True)
+    eng.step(*stage(eng, host, cb, rcfg), train=True)
     torch.cuda.synchronize()
     got = {k: v.float().cpu() for k, v in eng.hf_state("grad").items()}
     wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
@@ -151,10 +163,11 @@ def test_optimizer_step_reduces_loss_and_tracks_master(pkg):
     assert torch.equal(ref[k].float().cpu(), wr[k])
 
 
-def test_train_step_metric_keys_and_values(pkg):
+@pytest.mark.parametrize("tag", ["g4_small", "g6_next_small"])
+def test_train_step_metric_keys_and_values(pkg, tag):
     """The public end-to-end call (host batch in, TRL metric dict out) incl. the logits/* means computed without logits."""
     config, engine, host, ops = pkg
-    eng, rcfg, d, batch, cb = build(pkg, "g4_small")
+    eng, rcfg, d, batch, cb = build(pkg, tag)
     got = eng.train_step(batch, train=True)
     wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
     with torch.no_grad():
@@ -208,3 +221,43 @@ def test_merge_validity_errors(pkg):
     m = ops.llava_merge_index(a, b, c, rcfg.n_patches, px.shape[0], 1, rcfg.image_token_index, rcfg.pad_token_id)
     with pytest.raises(ValueError):
         eng.check_merge_status(m)
+
+
+def test_next_merge_kernels_match_host_mock(pkg):
+    """Integer kernels of the LLaVA-Next merge == the plain-Python mirror (tests/mock_ops.py), bit-exact; the backward
+    gather-sum over the two sequences that share an image == index_add."""
+    config, engine, host, ops = pkg
+    from tests import mock_ops
+    cfg = R.SMALL_NEXT
+    sizes = [(112, 112), (90, 300), (200, 100), (50, 50)]
+    batch = R.make_batch(cfg, 4, 50, 8, seed=9, image_sizes=sizes)
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    plan = host.anyres_pack_index(sizes, cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+    S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
+    want = mock_ops.llavanext_merge_index(ids, am, lb, plan.feat_off, plan.total_feats, S, 4, 1, cfg.image_token_index)
+    got = ops.llavanext_merge_index(ids.cuda(), am.cuda(), lb.cuda(), plan.feat_off.cuda(), plan.total_feats, S, 4, 1,
+                                    cfg.image_token_index)
+    assert int(got.status) == 0
+    for k in ("src_map", "labels", "mask", "pos", "seqlens", "img_pos", "target"):
+        assert torch.equal(getattr(got, k).cpu(), getattr(want, k)), k
+    live = want.target >= 0
+    assert torch.equal(got.row_of_text.cpu()[live], want.row_of_text[live])
+    d = 64
+    g = torch.Generator().manual_seed(0)
+    dx = torch.randn(8 * S, d, generator=g).to(torch.bfloat16)
+    de_w = torch.zeros(cfg.vocab, d)
+    di_w = torch.zeros(plan.total_feats, d, dtype=torch.bfloat16)
+    mock_ops.llavanext_merge_bwd(want, dx, de_w, di_w)
+    de_g = torch.zeros(cfg.vocab, d, device="cuda")
+    di_g = torch.zeros(plan.total_feats, d, dtype=torch.bfloat16, device="cuda")
+    ops.llavanext_merge_bwd(got, dx.cuda(), de_g, di_g)
+    assert torch.equal(di_g.cpu(), di_w)
+    torch.testing.assert_close(de_g.cpu(), de_w, rtol=1e-5, atol=1e-5)
+    # the reference's ValueErrors (LlavaNext/__init__.py:75-79, 60-71) surface through the status word
+    bad = ids.clone(); bad[0, 3] = cfg.image_token_index
+    st = ops.llavanext_merge_index(bad.cuda(), am.cuda(), lb.cuda(), plan.feat_off.cuda(), plan.total_feats, S + 400, 4, 1,
+                                   cfg.image_token_index)
+    eng = engine.LlavaDPOEngine(config.TINY_NEXT, config.TrainConfig(), with_optimizer=False)
+    with pytest.raises(ValueError):
+        eng.check_merge_status(st)

@@ -34,19 +34,24 @@ def cpu_pkg():
 
 def _setup(cpu_pkg, tag="g4_tiny", loss_type="sigmoid", with_optimizer=False):
     config, engine, host, ops = cpu_pkg
-    name, rcfg, npairs, tl, pl = {"g4_tiny": ("TINY", R.TINY, 2, 24, 8), "g4_small": ("SMALL", R.SMALL, 2, 96, 24)}[tag]
+    name, rcfg, npairs, tl, pl = {"g4_tiny": ("TINY", R.TINY, 2, 24, 8), "g4_small": ("SMALL", R.SMALL, 2, 96, 24),
+                                  "g6_next_tiny": ("TINY_NEXT", R.TINY_NEXT, 3, 24, 8),
+                                  "g6_next_small": ("SMALL_NEXT", R.SMALL_NEXT, 2, 96, 24)}[tag]
     d = np.load(os.path.join(G, tag + ".npz"))
+    sizes = [tuple(x) for x in d["image_sizes"].tolist()] if "image_sizes" in d.files else None
     eng = engine.LlavaDPOEngine(getattr(config, name), config.TrainConfig(loss_type=loss_type, learning_rate=1e-3),
                                 device="cpu", with_optimizer=with_optimizer)
     eng.init_synthetic(int(d["seed"]))
-    batch = R.make_batch(rcfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True)
+    batch = R.make_batch(rcfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True, image_sizes=sizes)
     cb = host.concatenated_inputs(batch)
     return eng, rcfg, d, batch, cb
 
 
 def test_config_mirrors_oracle_specs(cpu_pkg):
     config, engine, host, ops = cpu_pkg
-    for a, b in ((config.TINY, R.TINY), (config.SMALL, R.SMALL), (config.LLAVA15_7B, R.LLAVA15_7B)):
+    for a, b in ((config.TINY, R.TINY), (config.SMALL, R.SMALL), (config.LLAVA15_7B, R.LLAVA15_7B),
+                 (config.TINY_NEXT, R.TINY_NEXT), (config.SMALL_NEXT, R.SMALL_NEXT),
+                 (config.LLAVANEXT_MISTRAL_7B, R.LLAVANEXT_MISTRAL_7B)):
         assert config.weight_specs(a) == R.weight_specs(b)
         assert a.n_patches == b.n_patches and a.v_used_layers == b.v_used_layers
     assert config.tensor_seed("x.y", 3) == R.tensor_seed("x.y", 3)
@@ -133,6 +138,164 @@ def test_engine_backward_parity_cpu_mock(cpu_pkg):
         g, want = got[k].reshape(leaf.shape), leaf.grad
         rel = (g - want).norm().item() / max(want.norm().item(), 1e-12)
         assert rel < 5e-2, f"{k}: rel {rel}"
+
+
+# ------------------------------------------------------------------------------------------
+# LLaVA-Next: anyres packing index, merge, DDPO mask and the engine over the mock ops
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rcfg", [R.TINY_NEXT, R.SMALL_NEXT, R.LLAVANEXT_MISTRAL_7B])
+def test_anyres_pack_index_equals_reference_packing(cpu_pkg, rcfg):
+    """pack_image_features restated with tensors (oracle) on features that carry their own row number == the
+    integer index the product builds (bit-exact), over square / wide / tall / extreme aspect ratios."""
+    config, engine, host, ops = cpu_pkg
+    P = rcfg.n_patches
+    s = rcfg.image_size
+    sizes = [(s, s), (20, 50), (60, 25), (100, 100), (37, 211), (500, 90), (333, 334), (640, 480), (480, 640), (1000, 300),
+             (17, 17), (2 * s, 2 * s), (s, 3 * s), (3 * s, s)]
+    plan = host.anyres_pack_index(sizes, rcfg.image_grid_pinpoints, rcfg.image_size, rcfg.patch_size)
+    crops = [R.image_size_to_num_patches(x, rcfg.image_grid_pinpoints, rcfg.image_size) for x in sizes]
+    assert crops == plan.crops
+    feats = torch.arange(sum(crops) * P, dtype=torch.float32).reshape(sum(crops), P, 1)
+    packed, lens = R.pack_image_features(rcfg, list(torch.split(feats, crops, 0)), sizes,
+                                         torch.tensor([float(plan.n_crop_rows)]))
+    assert lens.tolist() == plan.feature_lens and plan.total_feats == int(lens.sum())
+    assert torch.equal(packed.flatten().to(torch.int32), plan.pack_index)
+    nl = plan.pack_index == plan.n_crop_rows
+    assert torch.equal(plan.scatter_index[~nl], plan.pack_index[~nl]) and bool((plan.scatter_index[nl] == -1).all())
+    assert torch.equal(plan.newline_rows.long(), torch.nonzero(nl).flatten())
+    assert plan.scatter_index[~nl].unique().numel() == int((~nl).sum())  # every crop row is used at most once
+
+
+def test_next_merge_index_equals_reference_merge(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    cfg = R.TINY_NEXT
+    sizes = [(28, 28), (20, 50), (60, 25)]
+    batch = R.make_batch(cfg, 3, 30, 8, seed=5, image_sizes=sizes)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    plan = host.anyres_pack_index(sizes, cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+    S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
+    m = ops.llavanext_merge_index(ids, am, lb, plan.feat_off, plan.total_feats, S, 3, 1, cfg.image_token_index)
+    assert int(m.status) == 0
+    lens2 = torch.tensor(plan.feature_lens * 2)
+    d = 4
+    feats = torch.arange(1, 2 * plan.total_feats + 1, dtype=torch.float32)[:, None].expand(-1, d) * -1.0
+    # the reference sees the duplicated image batch [v, v]: feature rows of the second copy differ only by offset
+    emb_w = torch.arange(cfg.vocab, dtype=torch.float32)[:, None].expand(-1, d) + 1.0
+    ids0 = ids.clone(); ids0[ids == cfg.image_token_index] = 0
+    fe, fm, fl, pos, imap = R.next_merge_input_ids_with_image_features(
+        cfg, feats, lens2, torch.nn.functional.embedding(ids0, emb_w), ids, am, lb)
+    assert fe.shape[1] == S == m.S
+    assert torch.equal(m.labels, fl) and torch.equal(m.mask.long(), fm)
+    assert torch.equal(m.pos.view(6, S).long(), pos)
+    src = m.src_map.view(6, S).long()
+    INT_MIN = -(2 ** 31)
+    assert torch.equal(src < 0, imap | (src == INT_MIN)) and torch.equal((src < 0) & (src != INT_MIN), imap)
+    # text rows hold the token's embedding row; image rows hold packed feature row k (second copy: k + total)
+    want = fe[..., 0]
+    got = torch.where(src >= 0, src.float() + 1.0, torch.zeros_like(want))
+    k = (-1 - src).clamp(min=0)
+    rep = (torch.arange(6) // 3)[:, None]
+    got = torch.where(imap, -(k + rep * plan.total_feats + 1).float(), got)
+    assert torch.equal(got, want)
+    assert torch.equal(m.seqlens.long(), fm.sum(-1))
+    # img_rows inverse map
+    rows = m.img_pos.view(2, plan.total_feats).long()
+    assert torch.equal(m.src_map.long()[rows], (-1 - torch.arange(plan.total_feats))[None].expand(2, -1))
+    # wrong image count / left padding are flagged like the reference's ValueErrors
+    bad = ids.clone(); bad[0, 3] = cfg.image_token_index
+    assert int(ops.llavanext_merge_index(bad, am, lb, plan.feat_off, plan.total_feats, S + 20, 3, 1,
+                                         cfg.image_token_index).status) == 2
+    am2 = am.clone(); am2[1, 0] = 0; am2[:, -1] = 0
+    assert int(ops.llavanext_merge_index(ids, am2, lb, plan.feat_off, plan.total_feats, S, 3, 1,
+                                         cfg.image_token_index).status) == 3
+
+
+def test_next_ddpo_row_weights_equal_reference_mask(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    cfg = R.SMALL_NEXT
+    sizes = [(112, 112), (90, 300), (200, 100)]
+    batch = R.make_batch(cfg, 3, 60, 8, seed=2, ddpo_like=True, image_sizes=sizes)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    plan = host.anyres_pack_index(sizes, cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+    S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
+    w = host.ddpo_row_weights(ids, lb, cfg.image_token_index, plan.feature_lens * 2, attention_mask=am, merged_len=S)
+    feats = torch.ones(2 * plan.total_feats, 2)
+    ids0 = ids.clone(); ids0[ids == cfg.image_token_index] = 0
+    _, _, fl, _, _ = R.next_merge_input_ids_with_image_features(cfg, feats, torch.tensor(plan.feature_lens * 2),
+                                                                torch.ones(*ids.shape, 2), ids, am, lb)
+    shift = fl[:, 1:].clone()
+    shift[shift == -100] = 0
+    mask = R.ddpo_shared_mask(shift)
+    m = ops.llavanext_merge_index(ids, am, lb, plan.feat_off, plan.total_feats, S, 3, 1, cfg.image_token_index)
+    rows = m.row_of_text.view(6, -1).long() - (torch.arange(6) * m.S)[:, None]
+    want = torch.gather(mask, 1, rows.clamp(min=0)).to(torch.uint8)
+    tgt = m.target.view(6, -1)
+    assert torch.equal(w[tgt >= 0], want[tgt >= 0])
+    assert int(w.sum()) > 0
+
+
+@pytest.mark.parametrize("tag", ["g6_next_tiny", "g6_next_small"])
+def test_next_engine_forward_parity_cpu_mock(cpu_pkg, tag):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, tag)
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    pol = eng.hf_state("policy")
+    assert "image_newline" in pol
+    for k, v in wp.items():
+        if k in pol:
+            assert torch.equal(pol[k].float().reshape(v.shape), v), k
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    img = cb["concatenated_img_input_dict"]
+    a = eng.prepare_inputs(ids, am, lb, img["pixel_values"], None, img["image_sizes"])
+    assert len(a) == 6
+    out = eng.step(*a, train=False)
+    assert np.array_equal(eng_labels(eng, a), d["labels"])
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps"], rtol=1e-3)
+    np.testing.assert_allclose(out.ref_logps.numpy(), d["ref_logps"], rtol=1e-3)
+    wt = eng.ddpo_weights(ids, am, lb, img["image_sizes"])
+    a = eng.prepare_inputs(ids, am, lb, img["pixel_values"], wt, img["image_sizes"])
+    out = eng.step(*a, train=False)
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps_ddpo"], rtol=1e-3, atol=1e-2)
+    # the flat-crop form of pixel_values (4-D) is accepted too
+    crops = a[5].crops
+    flat = torch.cat([pv[:c] for pv, c in zip(batch["img_input_dict"]["pixel_values"], crops)], 0)
+    b = eng.prepare_inputs(ids, am, lb, flat, wt, batch["img_input_dict"]["image_sizes"])
+    assert torch.equal(b[3], a[3])
+    with pytest.raises(ValueError):
+        eng.prepare_inputs(ids, am, lb, flat[:-1], wt, batch["img_input_dict"]["image_sizes"])
+    with pytest.raises(ValueError):
+        eng.prepare_inputs(ids, am, lb, flat, wt)
+
+
+def eng_labels(eng, a):
+    from tests import mock_ops
+    plan = a[5]
+    m = mock_ops.llavanext_merge_index(a[0], a[1], a[2], plan.feat_off, plan.total_feats, plan.merged_len, len(plan.crops), 1,
+                                       eng.cfg.image_token_index)
+    return m.labels.numpy()
+
+
+def test_next_engine_backward_parity_cpu_mock(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g6_next_tiny")
+    metrics = eng.train_step(batch, train=True)
+    got = {k: v.float() for k, v in eng.hf_state("grad").items()}
+    wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in wp.items() if not k.startswith("vision_tower.")}
+    w = dict(wp)
+    w.update(leaves)
+    loss, want_metrics, _ = R.get_batch_loss_metrics(rcfg, w, wr, batch)
+    loss.backward()
+    assert "image_newline" in leaves and leaves["image_newline"].grad.abs().max() > 0
+    for k, leaf in leaves.items():
+        g, want = got[k].reshape(leaf.shape), leaf.grad
+        rel = (g - want).norm().item() / max(want.norm().item(), 1e-12)
+        assert rel < 5e-2, f"{k}: rel {rel}"
+    assert abs(metrics["loss"] - float(loss.detach())) < 2e-3
+    for k in ("rewards/chosen", "rewards/rejected", "logps/chosen", "logps/rejected", "logits/chosen", "logits/rejected"):
+        assert abs(metrics[k] - float(want_metrics[k])) <= 2e-3 * max(1.0, abs(float(want_metrics[k]))), k
 
 
 def test_engine_optimizer_cpu_mock(cpu_pkg):
@@ -245,7 +408,7 @@ def test_train_step_metrics_match_oracle(cpu_pkg):
     wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
     with torch.no_grad():
         loss, metrics, aux = R.get_batch_loss_metrics(rcfg, wp, wr, batch)
-    assert abs(got["loss"] - float(loss)) < 2e-3
+    assert abs(got["loss"] - float(loss.detach())) < 2e-3
     for k in ("rewards/chosen", "rewards/rejected", "rewards/margins", "logps/chosen", "logps/rejected"):
         assert abs(got[k] - float(metrics[k])) < 2e-3 * max(1.0, abs(float(metrics[k]))), k
     assert got["rewards/accuracies"] == float(metrics["rewards/accuracies"])

@@ -57,14 +57,18 @@ def test_g3_ddpo_diff_ids_matches_reference():
     assert d["identical_ia"].size == 0 and d["insertion_ia"].size == 0
 
 
-@pytest.mark.parametrize("tag,cfg,npairs,tl,pl", [("g4_tiny", R.TINY, 2, 24, 8), ("g4_small", R.SMALL, 2, 96, 24)])
+@pytest.mark.parametrize("tag,cfg,npairs,tl,pl", [
+    ("g4_tiny", R.TINY, 2, 24, 8), ("g4_small", R.SMALL, 2, 96, 24),
+    # LLaVA-Next (LlavaNextForRL run through oracle/_llavanext_shim.py): anyres grids 1x2 / 2x1 with unpadding, GQA
+    ("g6_next_tiny", R.TINY_NEXT, 3, 24, 8), ("g6_next_small", R.SMALL_NEXT, 2, 96, 24)])
 def test_g4_llava_forward_matches_reference(tag, cfg, npairs, tl, pl):
     d = load(tag + ".npz")
     wp, wr = R.make_policy_and_ref(cfg, int(d["seed"]))
-    batch = R.make_batch(cfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True)
+    sizes = [tuple(x) for x in d["image_sizes"].tolist()] if "image_sizes" in d.files else None
+    batch = R.make_batch(cfg, npairs, tl, pl, int(d["seed"]), ddpo_like=True, image_sizes=sizes)
     cb = R.concatenated_inputs(batch)
     with torch.no_grad():
-        logits, labels, img_map = R.llava_forward(cfg, wp, cb["concatenated_input_ids"],
+        logits, labels, img_map = R.model_forward(cfg, wp, cb["concatenated_input_ids"],
                                                   cb["concatenated_attention_mask"], cb["concatenated_labels"],
                                                   **cb["concatenated_img_input_dict"])
     assert np.array_equal(labels.numpy(), d["labels"])

@@ -35,6 +35,9 @@ class ModelConfig:
     pad_token_id: int = 32001
     ignore_index: int = -100
     max_positions: int = 4096
+    # "llava" (models/Llava/__init__.py) | "llava_next" (models/LlavaNext/__init__.py: anyres crops + image_newline)
+    family: str = "llava"
+    image_grid_pinpoints: Tuple[Tuple[int, int], ...] = ()
 
     @property
     def n_patches(self) -> int:
@@ -72,6 +75,21 @@ TINY = ModelConfig(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_hea
 # exercises the production tile shapes (head dims 64 / 128, several tiles per GEMM)
 SMALL = ModelConfig(image_size=112, patch_size=14, v_hidden=256, v_layers=3, v_heads=4, v_ff=512, hidden=512, layers=2,
                     heads=4, kv_heads=4, ff=1024, vocab=2048, image_token_index=2000, pad_token_id=2001)
+
+
+# llava-v1.6-mistral-7b-hf: CLIP-L/336 tower, Mistral-7B-Instruct-v0.2 decoder (GQA 32/8, ff 14336, theta 1e6, no
+# sliding window), anyres pinpoints (BASELINE.json configs[3])
+LLAVA_NEXT_PINPOINTS = ((336, 672), (672, 336), (672, 672), (1008, 336), (336, 1008))
+LLAVANEXT_MISTRAL_7B = ModelConfig(hidden=4096, layers=32, heads=32, kv_heads=8, ff=14336, vocab=32064, rope_theta=1e6,
+                                   family="llava_next", image_grid_pinpoints=LLAVA_NEXT_PINPOINTS, max_positions=8192)
+TINY_NEXT = ModelConfig(image_size=28, patch_size=14, v_hidden=128, v_layers=3, v_heads=2, v_ff=256, hidden=256, layers=2,
+                        heads=4, kv_heads=2, ff=256, vocab=320, rope_theta=1e6, image_token_index=300, pad_token_id=301,
+                        family="llava_next",
+                        image_grid_pinpoints=((28, 56), (56, 28), (56, 56), (84, 28), (28, 84)))
+SMALL_NEXT = ModelConfig(image_size=112, patch_size=14, v_hidden=256, v_layers=3, v_heads=4, v_ff=512, hidden=512,
+                         layers=2, heads=4, kv_heads=2, ff=1024, vocab=2048, rope_theta=1e6, image_token_index=2000,
+                         pad_token_id=2001, family="llava_next",
+                         image_grid_pinpoints=((112, 224), (224, 112), (224, 224), (336, 112), (112, 336)))
 
 
 @dataclass
@@ -121,14 +139,16 @@ def weight_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], float, fl
           ("multi_modal_projector.linear_2.weight", (cfg.hidden, cfg.hidden), a, 0.0),
           ("multi_modal_projector.linear_2.bias", (cfg.hidden,), 0.02, 0.0),
           ("language_model.model.embed_tokens.weight", (cfg.vocab, cfg.hidden), a, 0.0)]
+    if cfg.family == "llava_next":
+        s.append(("image_newline", (cfg.hidden,), a, 0.0))
     kv = cfg.kv_heads * cfg.head_dim
     for i in range(cfg.layers):
         p = f"language_model.model.layers.{i}."
         s += [(p + "input_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
-              (p + "self_attn.q_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+              (p + "self_attn.q_proj.weight", (cfg.heads * cfg.head_dim, cfg.hidden), a, 0.0),
               (p + "self_attn.k_proj.weight", (kv, cfg.hidden), a, 0.0),
               (p + "self_attn.v_proj.weight", (kv, cfg.hidden), a, 0.0),
-              (p + "self_attn.o_proj.weight", (cfg.hidden, cfg.hidden), a, 0.0),
+              (p + "self_attn.o_proj.weight", (cfg.hidden, cfg.heads * cfg.head_dim), a, 0.0),
               (p + "post_attention_layernorm.weight", (cfg.hidden,), 0.1, 1.0),
               (p + "mlp.gate_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),
               (p + "mlp.up_proj.weight", (cfg.ff, cfg.hidden), a, 0.0),

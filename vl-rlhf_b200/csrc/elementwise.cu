@@ -330,6 +330,98 @@ __global__ void merge_img_bwd_kernel(const int* __restrict__ img_pos, const __nv
     }
 }
 
+// ---------------------------------------------------------------- LLaVA-Next merge index (LlavaNext/__init__.py:38-171)
+// Same outputs as merge_index_kernel, but (i) image k contributes feat_off[k+1]-feat_off[k] packed feature rows
+// (anyres: variable per image), (ii) tokens with attention_mask == 0 are never written (:96-99,124-127) and S is the
+// longest VALID merged sequence (host-computed), (iii) pad-token embeddings are not zeroed.  Right padding only.
+//   img_rows[rep*total_feats + k] = flat merged row holding packed feature row k in the rep-th sequence that
+//   uses it (rep = b / n_img_batch: chosen, rejected).
+__global__ void next_merge_index_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ amask,
+                                        const int64_t* __restrict__ labels, const int* __restrict__ feat_off, int n_seq,
+                                        int L, int S, int n_img_batch, int imgs_per_seq, int total_feats, int image_token,
+                                        int ignore_index, int* __restrict__ src_map, int64_t* __restrict__ labels_m,
+                                        int* __restrict__ mask_m, int* __restrict__ pos_ids, int* __restrict__ seqlen,
+                                        int* __restrict__ img_rows, int* __restrict__ row_of_text,
+                                        int64_t* __restrict__ target, int* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq) return;
+    const int64_t* id = ids + (size_t)b * L;
+    const int64_t* am = amask + (size_t)b * L;
+    const int64_t* lb = labels + (size_t)b * L;
+    int* sm = src_map + (size_t)b * S;
+    int64_t* lm = labels_m + (size_t)b * S;
+    int* mm = mask_m + (size_t)b * S;
+    for (int p = 0; p < S; ++p) { sm[p] = INT_MIN; lm[p] = ignore_index; mm[p] = 0; pos_ids[(size_t)b * S + p] = 1; }
+    int p = 0, slot = 0;
+    bool seen_masked = false;
+    const int img_base = (b % n_img_batch) * imgs_per_seq;
+    const int rep = b / n_img_batch;
+    for (int j = 0; j < L; ++j) {
+        const int64_t t = id[j];
+        const size_t rj = (size_t)b * (L - 1) + j - 1;
+        if (am[j] == 0) {
+            seen_masked = true;
+            if (t == image_token) atomicExch(status, 4);  // an <image> placeholder outside the attended prefix
+            if (j >= 1) { row_of_text[rj] = b * S; target[rj] = -100; }
+            continue;
+        }
+        if (seen_masked) atomicExch(status, 3);  // attended token after a masked one: not right padding
+        if (t == image_token) {
+            const int k0 = slot < imgs_per_seq ? feat_off[img_base + slot] : 0;
+            const int F = slot < imgs_per_seq ? feat_off[img_base + slot + 1] - k0 : 0;
+            if (slot < imgs_per_seq && p + F <= S) {
+                for (int f = 0; f < F; ++f) {
+                    sm[p + f] = -1 - (k0 + f);
+                    mm[p + f] = 1;
+                    img_rows[(size_t)rep * total_feats + k0 + f] = b * S + p + f;
+                }
+            } else {
+                atomicExch(status, 1);
+            }
+            if (j >= 1) { row_of_text[rj] = b * S + (p > 0 ? p - 1 : 0); target[rj] = -100; }
+            p += F;
+            ++slot;
+        } else {
+            if (p < S) {
+                sm[p] = (int)t;
+                mm[p] = 1;
+                lm[p] = lb[j];
+            } else {
+                atomicExch(status, 1);
+            }
+            if (j >= 1) {
+                row_of_text[rj] = b * S + (p > 0 ? p - 1 : 0);
+                target[rj] = (lb[j] == ignore_index || p == 0) ? -100 : lb[j];
+            }
+            ++p;
+        }
+    }
+    if (slot != imgs_per_seq) atomicExch(status, 2);
+    if (p > S) atomicExch(status, 1);
+    const int len = p < S ? p : S;
+    for (int q = 0; q < len; ++q) pos_ids[(size_t)b * S + q] = q;  // mask is a prefix: cumsum(mask) - 1
+    seqlen[b] = len;
+}
+// dimg[k, :] = sum over reps of dx[img_rows[rep*total + k], :]
+__global__ void next_merge_img_bwd_kernel(const int* __restrict__ img_rows, const __nv_bfloat16* __restrict__ dx,
+                                          __nv_bfloat16* __restrict__ dimg, int total_feats, int reps, int d) {
+    const int chunks = d >> 3;
+    const size_t total = (size_t)total_feats * chunks;
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(w % chunks);
+        const size_t k = w / chunks;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < reps; ++r) {
+            const int row = img_rows[(size_t)r * total_feats + k];
+            float v[8];
+            unpack8e(*reinterpret_cast<const uint4*>(dx + (size_t)row * d + c * 8), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+        *reinterpret_cast<uint4*>(dimg + k * d + c * 8) = pack8e(acc);
+    }
+}
+
 // ---------------------------------------------------------------- optimizer
 __global__ void sumsq_partial_kernel(const __nv_bfloat16* __restrict__ x, size_t n8, float* __restrict__ partial) {
     __shared__ float sm[8];
@@ -560,6 +652,35 @@ extern "C" int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, co
     merge_embed_bwd_kernel<<<grid_for((size_t)n_seq * merged_len * (d / 8), 256), 256, 0, s>>>(src_map, CBF(dx), dembed_f32, n_seq * merged_len, d);
     VLB_LAUNCH_CHECK();
     merge_img_bwd_kernel<<<grid_for((size_t)n_img_batch * feats_per_seq * (d / 8), 256), 256, 0, s>>>(img_pos, CBF(dx), BF(dimage_features), n_seq, n_img_batch, merged_len, feats_per_seq, d);
+    count_launch(2);
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+extern "C" int vlb200_llavanext_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels,
+                                            const int* feat_off, int n_seq, int text_len, int merged_len, int n_img_batch,
+                                            int imgs_per_seq, int total_feats, int image_token, int ignore_index,
+                                            int* src_map, int64_t* labels_merged, int* mask_merged, int* position_ids,
+                                            int* seqlens, int* img_rows, int* row_of_text, int64_t* target, int* status,
+                                            void* stream) {
+    VLB_REQUIRE(input_ids && attention_mask && labels && feat_off && src_map && labels_merged && mask_merged &&
+                    position_ids && seqlens && img_rows && row_of_text && target && status, "next_merge_index: null pointer");
+    VLB_REQUIRE(n_img_batch > 0 && n_seq % n_img_batch == 0, "next_merge_index: n_seq must be a multiple of the image batch");
+    VLB_REQUIRE(merged_len > 0 && text_len > 1 && total_feats > 0 && imgs_per_seq > 0, "next_merge_index: bad sizes");
+    VLB_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), as_stream(stream)));
+    VLB_CHECK_CUDA(cudaMemsetAsync(img_rows, 0, sizeof(int) * (size_t)(n_seq / n_img_batch) * total_feats, as_stream(stream)));
+    next_merge_index_kernel<<<(n_seq + 31) / 32, 32, 0, as_stream(stream)>>>(input_ids, attention_mask, labels, feat_off, n_seq, text_len, merged_len, n_img_batch, imgs_per_seq, total_feats, image_token, ignore_index, src_map, labels_merged, mask_merged, position_ids, seqlens, img_rows, row_of_text, target, status);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+extern "C" int vlb200_llavanext_merge_bwd(const int* src_map, const int* img_rows, const void* dx, float* dembed_f32,
+                                          void* dimage_features, int n_rows, int total_feats, int reps, int d,
+                                          void* stream) {
+    VLB_REQUIRE(src_map && img_rows && dx && dembed_f32 && dimage_features && d % 8 == 0 && reps > 0, "next_merge_bwd: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    merge_embed_bwd_kernel<<<grid_for((size_t)n_rows * (d / 8), 256), 256, 0, s>>>(src_map, CBF(dx), dembed_f32, n_rows, d);
+    VLB_LAUNCH_CHECK();
+    next_merge_img_bwd_kernel<<<grid_for((size_t)total_feats * (d / 8), 256), 256, 0, s>>>(img_rows, CBF(dx), BF(dimage_features), total_feats, reps, d);
     count_launch(2);
     VLB_LAUNCH_CHECK();
     return VLB200_OK;

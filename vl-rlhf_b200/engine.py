@@ -1,7 +1,8 @@
-"""The B200-native DPO step for the LLaVA-1.5 family.
+"""The B200-native DPO step for the LLaVA-1.5 family and LLaVA-Next (anyres crops + image_newline, GQA decoder).
 
 Replaces, behind the reference's own interfaces (see plugin.py):
   * `LlavaForRL.forward` incl. `_merge_input_ids_with_image_features`   (models/Llava/__init__.py:36-271)
+  * `LlavaNextForRL.forward` incl. its merge and `pack_image_features`   (models/LlavaNext/__init__.py:38-345)
   * `VLDPOTrainer.concatenated_forward / get_batch_logps / dpo_loss`      (base/trainer.py:148-301)
   * trl `DPOTrainer.get_batch_loss_metrics` (policy pass, no-grad reference pass, loss, reward stats)
   * autograd backward + AdamW + the data-parallel gradient all-reduce (accelerate/DeepSpeed in the reference)
@@ -73,6 +74,8 @@ def _trainable_layout(cfg: ModelConfig) -> Arena:
     a = Arena()
     d = cfg.hidden
     a.add("proj.w1", (d, cfg.v_hidden)); a.add("proj.b1", (d,)); a.add("proj.w2", (d, d)); a.add("proj.b2", (d,))
+    if cfg.family == "llava_next":
+        a.add("image_newline", (d,))
     a.add("embed", (cfg.vocab, d))
     for i in range(cfg.layers):
         a.add(f"L{i}.ln1", (d,)); a.add(f"L{i}.wqkv", (cfg.qkv_dim, d)); a.add(f"L{i}.wo", (d, cfg.heads * cfg.head_dim))
@@ -101,6 +104,8 @@ def hf_views(cfg: ModelConfig, w: Dict[str, torch.Tensor], vision: Optional[Dict
     out["multi_modal_projector.linear_1.weight"] = w["proj.w1"]; out["multi_modal_projector.linear_1.bias"] = w["proj.b1"]
     out["multi_modal_projector.linear_2.weight"] = w["proj.w2"]; out["multi_modal_projector.linear_2.bias"] = w["proj.b2"]
     out["language_model.model.embed_tokens.weight"] = w["embed"]
+    if cfg.family == "llava_next":
+        out["image_newline"] = w["image_newline"]
     for i in range(cfg.layers):
         p = f"language_model.model.layers.{i}."
         qkv, gu = w[f"L{i}.wqkv"], w[f"L{i}.wgu"]
@@ -173,6 +178,7 @@ class LlavaDPOEngine:
         # cost more than the ~28 ms they hide, so the single all-reduce is the default.
         self.overlap_allreduce = _os.environ.get("VLB200_OVERLAP_ALLREDUCE", "0") == "1"
         self._pending = []
+        self._anyres = None  # host.AnyresPlan of the batch in flight (LLaVA-Next only)
         self._bufs: Dict[str, torch.Tensor] = {}
         self._build_rope_tables()
 
@@ -293,8 +299,16 @@ class LlavaDPOEngine:
         else:
             ph = self.buf("p.h_ref", (nimg, d))
             ops.gemm(feats, w["proj.w1"], out=ph, bias=w["proj.b1"], act=ops.ACT_GELU_ERF)
-        img = self.buf("p.img", (nimg, d))
-        ops.gemm(ph, w["proj.w2"], out=img, bias=w["proj.b2"])
+        plan = self._anyres
+        img = self.buf("p.img", (nimg + (1 if plan is not None else 0), d))
+        ops.gemm(ph, w["proj.w2"], out=img[:nimg], bias=w["proj.b2"])
+        if plan is not None:
+            # LLaVA-Next "spatial_unpad" packing (LlavaNext/__init__.py:240-249): one row gather over the crop
+            # features; image_newline sits in the extra last row of `img` and is read once per stitched map row
+            ops.copy_rows(w["image_newline"], d, d, 0, img[nimg:], d, d, 1, 1, d)
+            packed = self.buf("p.packed", (plan.total_feats, d))
+            ops.gather_rows(img, plan.pack_index, packed)
+            img = packed
         # embed + merge (K7, K8)
         L = cfg.layers
         # the residual stream is kept in fp32 (bf16 would add a 2^-9 relative rounding per layer that compounds
@@ -408,7 +422,17 @@ class LlavaDPOEngine:
         nimg = feats.shape[0]
         dimg = self.buf("b.dimg", (nimg, d))
         ops.zero_(self.dembed_f32)
-        ops.llava_merge_bwd(m, dx, self.dembed_f32, dimg)
+        plan = self._anyres
+        if plan is None:
+            ops.llava_merge_bwd(m, dx, self.dembed_f32, dimg)
+        else:
+            dpacked = self.buf("b.dpacked", (plan.total_feats, d))
+            ops.llavanext_merge_bwd(m, dx, self.dembed_f32, dpacked)
+            ops.zero_(dimg)                                    # crop rows cut away by the unpadding get no gradient
+            ops.scatter_rows(dpacked, plan.scatter_index, dimg)
+            dnl = self.buf("b.dnewline", (plan.newline_rows.numel(), d))
+            ops.gather_rows(dpacked, plan.newline_rows, dnl)
+            ops.colsum(dnl, g["image_newline"])
         ops.cast_f32_to_bf16(self.dembed_f32.view(-1), g["embed"].view(-1))
         ph, z = self._bufs["p.h"], self._bufs["p.z"]
         ops.gemm(dimg, ph, a_kmajor=False, b_kmajor=False, out=g["proj.w2"])
@@ -458,40 +482,74 @@ class LlavaDPOEngine:
 
     # ------------------------------------------------------------------ the step
     def prepare_inputs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
-                       pixel_values: torch.Tensor, ddpo_weight: Optional[torch.Tensor] = None):
+                       pixel_values: torch.Tensor, ddpo_weight: Optional[torch.Tensor] = None,
+                       image_sizes: Optional[torch.Tensor] = None):
         """Host -> device staging of one concatenated batch (the H2D copies of the step).  Inputs may be CPU
-        (pinned or not) or CUDA tensors.  pixel_values may be [B,...] or the reference's duplicated [2B,...]."""
+        (pinned or not) or CUDA tensors.  pixel_values may be [B,...] or the reference's duplicated [2B,...].
+        LLaVA-Next: pixel_values is the processor's [B, max_crops, 3, H, W] (or the flat [sum crops, 3, H, W]) and
+        `image_sizes` [B, 2] is required; the returned tuple then carries a 6th element, the anyres plan."""
         dev = self.device
+        cfg = self.cfg
         n_seq = input_ids.shape[0]
+        plan = None
+        if cfg.family == "llava_next":
+            from . import host
+            if image_sizes is None:
+                raise ValueError("LLaVA-Next needs image_sizes (LlavaNext/__init__.py:211-218)")
+            if image_sizes.shape[0] == n_seq:
+                image_sizes = image_sizes[: n_seq // 2]
+            plan = host.anyres_pack_index(image_sizes.cpu(), cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+            plan.merged_len = host.next_merged_len(input_ids, attention_mask, plan.feature_lens, cfg.image_token_index)
+            if pixel_values.dim() == 5:  # stacked crops: keep each image's real crops (:220-225)
+                if pixel_values.shape[0] == n_seq:
+                    pixel_values = pixel_values[: n_seq // 2]
+                if all(c == pixel_values.shape[1] for c in plan.crops):
+                    pixel_values = pixel_values.reshape(-1, *pixel_values.shape[2:])
+                else:
+                    pixel_values = torch.cat([pv[:c] for pv, c in zip(pixel_values, plan.crops)], dim=0)
+            elif pixel_values.dim() != 4:
+                raise ValueError(f"pixel_values of shape {pixel_values.shape}, expect to be of 4 or 5 dimensions")
+            elif pixel_values.shape[0] == 2 * sum(plan.crops):
+                pixel_values = pixel_values[: sum(plan.crops)]
+            if pixel_values.shape[0] != sum(plan.crops):
+                raise ValueError(f"{pixel_values.shape[0]} crops given, image_sizes imply {sum(plan.crops)}")
+            plan.to(dev)
+        elif pixel_values.shape[0] == n_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
+            pixel_values = pixel_values[: n_seq // 2]
         ids = input_ids.to(dev, non_blocking=True).contiguous()
         am = attention_mask.to(dev, non_blocking=True).contiguous()
         lb = labels.to(dev, non_blocking=True).contiguous()
-        if pixel_values.shape[0] == n_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
-            pixel_values = pixel_values[: n_seq // 2]
         px = pixel_values.to(dev, non_blocking=True).contiguous()
         if px.dtype not in (torch.float32, torch.bfloat16):
             px = px.float()
         wt = ddpo_weight.to(dev, non_blocking=True).reshape(-1).contiguous() if ddpo_weight is not None else None
-        return ids, am, lb, px, wt
+        return (ids, am, lb, px, wt) if plan is None else (ids, am, lb, px, wt, plan)
 
-    def forward_logps(self, ids, am, lb, px, ddpo_weight=None, which: str = "policy", save: bool = False,
+    def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
                       feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None):
         cfg = self.cfg
+        if (cfg.family == "llava_next") != (anyres is not None):
+            raise ValueError("the anyres plan from prepare_inputs is required for (and only for) LLaVA-Next")
+        self._anyres = anyres
         if m is None:
             imgs_per_seq = 1
-            m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0], imgs_per_seq, cfg.image_token_index,
-                                      cfg.pad_token_id, cfg.ignore_index)
+            if anyres is not None:
+                m = ops.llavanext_merge_index(ids, am, lb, anyres.feat_off, anyres.total_feats, anyres.merged_len,
+                                              len(anyres.crops), imgs_per_seq, cfg.image_token_index, cfg.ignore_index)
+            else:
+                m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0], imgs_per_seq, cfg.image_token_index,
+                                          cfg.pad_token_id, cfg.ignore_index)
         if feats is None:
             feats = self.vision_features(px)
         w = self.policy if which == "policy" else self.ref
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
-    def step(self, ids, am, lb, px, ddpo_weight=None, train: bool = True) -> StepOutput:
+    def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
         backward + gradient all-reduce + AdamW."""
         tc = self.tc
-        pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, "policy", save=train)
-        ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, "ref", save=False, feats=feats, m=m)
+        pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train)
+        ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    1.0, want_grad=train)
         out = StepOutput()
@@ -515,10 +573,11 @@ class LlavaDPOEngine:
         cb = host.concatenated_inputs(batch, False, tc.label_pad_token_id, tc.padding_value)
         ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
         px = batch["img_input_dict"]["pixel_values"]  # one copy per pair: the [v, v] duplicate is never shipped
+        sizes = batch["img_input_dict"].get("image_sizes")
         wt = None
         if tc.loss_type == "ddpo":
-            wt = host.ddpo_row_weights(ids, lb, self.cfg.image_token_index, self.cfg.n_patches, tc.label_pad_token_id)
-        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt), train=train)
+            wt = self.ddpo_weights(ids, am, lb, sizes)
+        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train)
         n = out.policy_logps.numel() // 2
         packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
                             (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0),
@@ -530,6 +589,21 @@ class LlavaDPOEngine:
                 "logits/chosen": float(packed[9]), "logits/rejected": float(packed[10]),
                 "grad_norm": float(packed[8]) ** 0.5 / world}
 
+    def ddpo_weights(self, ids, am, lb, image_sizes=None) -> torch.Tensor:
+        """Host-side DDPO row weights of one concatenated batch (trainer.py:169-184 over the merged label layout)."""
+        from . import host
+        cfg, tc = self.cfg, self.tc
+        if cfg.family != "llava_next":
+            return host.ddpo_row_weights(ids, lb, cfg.image_token_index, cfg.n_patches, tc.label_pad_token_id)
+        n_seq = ids.shape[0]
+        if image_sizes.shape[0] == n_seq:
+            image_sizes = image_sizes[: n_seq // 2]
+        plan = host.anyres_pack_index(image_sizes.cpu(), cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+        per_seq = [plan.feature_lens[b % len(plan.feature_lens)] for b in range(n_seq)]
+        S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
+        return host.ddpo_row_weights(ids, lb, cfg.image_token_index, per_seq, tc.label_pad_token_id, attention_mask=am,
+                                     merged_len=S)
+
     def check_merge_status(self, m: "ops.MergeIndex"):
         """Synchronising validity check mirroring the reference's ValueError (Llava/__init__.py:90-94)."""
         st = int(m.status.item())
@@ -539,3 +613,5 @@ class LlavaDPOEngine:
                              "tokens in this build).")
         if st == 3:
             raise ValueError("attention_mask must be a right-padded prefix mask (left padding is not supported yet)")
+        if st == 4:
+            raise ValueError("an <image> placeholder lies outside the attended prefix of its sequence")

@@ -2,6 +2,9 @@
 
   * `concatenated_inputs`  <- VLDPOTrainer.concatenated_inputs (base/trainer.py:124-146) + the trl-0.8.1
     parent it calls (pad chosen/rejected to a common length, concatenate chosen-then-rejected).
+  * `anyres_*`             <- the integer side of LLaVA-Next's "spatial_unpad" packing (transformers-4.41
+    modeling_llava_next.py get_anyres_image_grid_shape / image_size_to_num_patches / unpad_image / pack_image_features,
+    called from models/LlavaNext/__init__.py:211-249): which projector-output row lands on which packed row.
   * `ddpo_row_weights`     <- the mask_shared_tokens branch of get_batch_logps (base/trainer.py:169-184) over
     utils/diff_lib.get_diff_ids (difflib.SequenceMatcher, autojunk ON).  The reference runs this inside the
     step with a device sync (`.tolist()`); here it runs on the host batch before the step (collator side).
@@ -9,7 +12,7 @@
 from __future__ import annotations
 
 import difflib
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -63,32 +66,145 @@ def get_diff_ids(a_seq: List[int], b_seq: List[int], min_match_size: int = 3) ->
     return a_ids, b_ids
 
 
-def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches: int,
-                     label_pad_token_id: int = -100, min_match_size: int = 3) -> torch.Tensor:
+def best_resolution(original_size: Sequence[int], pinpoints) -> Tuple[int, int]:
+    """(height, width) pinpoint that keeps the most of the image and then wastes the least canvas."""
+    oh, ow = int(original_size[0]), int(original_size[1])
+    key = None
+    best = None
+    for h, w in pinpoints:
+        sc = min(w / ow, h / oh)
+        eff = min(int(ow * sc) * int(oh * sc), ow * oh)
+        k = (eff, -(w * h - eff))
+        if key is None or k > key:  # strict: the first pinpoint wins ties, as in the reference loop
+            key, best = k, (int(h), int(w))
+    return best
+
+
+def anyres_grid(original_size, pinpoints, crop: int) -> Tuple[int, int]:
+    h, w = best_resolution(original_size, pinpoints)
+    return h // crop, w // crop
+
+
+def anyres_num_crops(original_size, pinpoints, crop: int) -> int:
+    """crops the processor emits for one image: ceil-grid cells of the chosen pinpoint + the base crop."""
+    h, w = best_resolution(original_size, pinpoints)
+    return -(-h // crop) * -(-w // crop) + 1
+
+
+class AnyresPlan:
+    """Row bookkeeping of one batch of anyres images (all host integers; `to(device)` stages the index vectors)."""
+    __slots__ = ("crops", "feature_lens", "feat_off", "pack_index", "scatter_index", "newline_rows", "n_crop_rows",
+                 "total_feats", "merged_len")
+
+    def to(self, device):
+        for k in ("feat_off", "pack_index", "scatter_index", "newline_rows"):
+            setattr(self, k, getattr(self, k).to(device, non_blocking=True))
+        return self
+
+
+def anyres_pack_index(image_sizes, pinpoints, image_size: int, patch_size: int) -> AnyresPlan:
+    """pack_image_features as an index: packed row r of image i reads projector-output row pack_index[r]
+    (crop-major, `g*g` rows per crop, images concatenated) or the image_newline row (index n_crop_rows).
+
+    Per image: the base crop's g*g rows; then the grid crops seen as one (gh*g) x (gw*g) map, cropped to the
+    original aspect ratio (unpad_image) and read row by row with one newline after every map row."""
+    g = image_size // patch_size
+    P = g * g
+    sizes = [(int(s[0]), int(s[1])) for s in (image_sizes.tolist() if hasattr(image_sizes, "tolist") else image_sizes)]
+    plan = AnyresPlan()
+    plan.crops = [anyres_num_crops(sz, pinpoints, image_size) for sz in sizes]
+    plan.n_crop_rows = sum(plan.crops) * P
+    NL = plan.n_crop_rows
+    idx: List[int] = []
+    lens: List[int] = []
+    row0 = 0
+    for (oh, ow), n in zip(sizes, plan.crops):
+        start = len(idx)
+        idx.extend(range(row0, row0 + P))  # base crop
+        if n > 1:
+            gh, gw = anyres_grid((oh, ow), pinpoints, image_size)
+            H, W = gh * g, gw * g
+            y0, y1, x0, x1 = 0, H, 0, W
+            if ow / oh > W / H:  # wider than the canvas: rows were padded
+                new_h = int(round(oh * (W / ow), 7))
+                pad = (H - new_h) // 2
+                y0, y1 = pad, H - pad
+            else:
+                new_w = int(round(ow * (H / oh), 7))
+                pad = (W - new_w) // 2
+                x0, x1 = pad, W - pad
+            for y in range(y0, y1):
+                cy, ry = divmod(y, g)
+                for x in range(x0, x1):
+                    cx, rx = divmod(x, g)
+                    idx.append(row0 + (1 + cy * gw + cx) * P + ry * g + rx)
+                idx.append(NL)
+        else:
+            idx.append(NL)
+        lens.append(len(idx) - start)
+        row0 += n * P
+    pk = torch.tensor(idx, dtype=torch.int32)
+    plan.pack_index = pk
+    plan.scatter_index = torch.where(pk == NL, torch.full_like(pk, -1), pk)
+    plan.newline_rows = torch.nonzero(pk == NL).flatten().to(torch.int32)
+    plan.feature_lens = lens
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    plan.feat_off = torch.tensor(off, dtype=torch.int32)
+    plan.total_feats = off[-1]
+    return plan
+
+
+def next_merged_len(input_ids: torch.Tensor, attention_mask: torch.Tensor, feature_lens: Sequence[int],
+                    image_token_index: int, imgs_per_seq: int = 1) -> int:
+    """max_embed_dim of LlavaNext/__init__.py:81-87: the longest valid merged sequence.  `feature_lens` holds one
+    entry per image of the image batch; sequence b uses images (b % n_img_batch) * imgs_per_seq + slot."""
+    n_img_batch = len(feature_lens) // imgs_per_seq
+    per_img_seq = torch.tensor([sum(feature_lens[i * imgs_per_seq:(i + 1) * imgs_per_seq]) for i in range(n_img_batch)])
+    n_seq = input_ids.shape[0]
+    feat = per_img_seq[torch.arange(n_seq) % n_img_batch].to(input_ids.device)
+    n_special = (input_ids == image_token_index).sum(-1)
+    return int(((attention_mask == 1).sum(-1) - n_special + feat).max())
+
+
+def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches,
+                     label_pad_token_id: int = -100, min_match_size: int = 3,
+                     attention_mask: Optional[torch.Tensor] = None, merged_len: Optional[int] = None) -> torch.Tensor:
     """uint8 weights [2B, L-1] for the text-level logits rows (row j-1 predicts text token j).
 
     The reference diffs the *merged* shifted label sequences (length S-1: image positions are -100 -> 0,
-    trainer.py:161-166), so the merged sequences are rebuilt here exactly (autojunk depends on the length)."""
+    trainer.py:161-166), so the merged sequences are rebuilt here exactly (autojunk depends on the length).
+    `n_patches` is an int (LLaVA-1.5) or one packed feature length per sequence (LLaVA-Next).  With
+    `attention_mask`/`merged_len` given the LLaVA-Next merge is mirrored: masked tokens are dropped and every
+    sequence is padded with ignore labels to `merged_len` (LlavaNext/__init__.py:96-127)."""
     ids = input_ids.cpu()
     lab = labels.cpu()
+    am = attention_mask.cpu() if attention_mask is not None else None
     n2, L = ids.shape
     assert n2 % 2 == 0
     n = n2 // 2
     out = torch.zeros(n2, L - 1, dtype=torch.uint8)
+    per_seq = [int(n_patches)] * n2 if isinstance(n_patches, int) else [int(x) for x in n_patches]
+    assert len(per_seq) == n2
 
     def merged_shift(b):
         seq: List[int] = []
         row_pos: List[int] = []  # merged shifted index for text token j (>=1), -1 if none
         for j in range(L):
             t = int(ids[b, j])
-            if t == image_token_index:
+            if am is not None and int(am[b, j]) == 0:
+                row_pos.append(-1)
+            elif t == image_token_index:
                 start = len(seq)
-                seq.extend([0] * n_patches)
+                seq.extend([0] * per_seq[b])
                 row_pos.append(start - 1)
             else:
                 v = int(lab[b, j])
                 row_pos.append(len(seq) - 1)
                 seq.append(0 if v == label_pad_token_id else v)
+        if merged_len is not None:
+            seq.extend([0] * (merged_len - len(seq)))
         return seq[1:], row_pos
 
     for i in range(n):

@@ -290,7 +290,7 @@ def zero_(t: torch.Tensor):
 class MergeIndex:
     """Device-side result of the integer merge pass (Llava/__init__.py:36-109)."""
     __slots__ = ("src_map", "labels", "mask", "pos", "seqlens", "img_pos", "row_of_text", "target", "status",
-                 "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq")
+                 "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq", "total_feats", "reps")
 
 
 def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_patches: int,
@@ -328,6 +328,42 @@ def llava_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, d
     assert dembed_f32.dtype == torch.float32
     check(_L.vlb200_llava_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32), _ptr(dimage_features),
                                     m.n_seq, m.n_img_batch, m.S, m.imgs_per_seq * m.P, dx.shape[1], _stream()))
+
+
+def llavanext_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
+                          feat_off: torch.Tensor, total_feats: int, merged_len: int, n_img_batch: int, imgs_per_seq: int,
+                          image_token: int, ignore_index: int = -100):
+    """Integer merge pass of LlavaNextForRL (LlavaNext/__init__.py:38-171): variable packed feature lengths
+    (`feat_off` int32 prefix offsets, one entry per image + 1), masked tokens dropped, S = `merged_len`."""
+    n_seq, L = input_ids.shape
+    S = int(merged_len)
+    dev = input_ids.device
+    for t in (input_ids, attention_mask, labels):
+        assert t.dtype == torch.int64 and t.is_contiguous() and t.shape == (n_seq, L)
+    assert feat_off.dtype == torch.int32 and feat_off.numel() == n_img_batch * imgs_per_seq + 1
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, S, -1, n_img_batch, imgs_per_seq
+    m.total_feats, m.reps = int(total_feats), n_seq // n_img_batch
+    m.src_map = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
+    m.labels = torch.empty(n_seq, S, dtype=torch.int64, device=dev)
+    m.mask = torch.empty(n_seq, S, dtype=torch.int32, device=dev)
+    m.pos = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
+    m.seqlens = torch.empty(n_seq, dtype=torch.int32, device=dev)
+    m.img_pos = torch.empty(m.reps * m.total_feats, dtype=torch.int32, device=dev)  # img_rows
+    m.row_of_text = torch.empty(n_seq * (L - 1), dtype=torch.int32, device=dev)
+    m.target = torch.empty(n_seq * (L - 1), dtype=torch.int64, device=dev)
+    m.status = torch.empty(1, dtype=torch.int32, device=dev)
+    check(_L.vlb200_llavanext_merge_index(_ptr(input_ids), _ptr(attention_mask), _ptr(labels), _ptr(feat_off), n_seq, L, S,
+                                          n_img_batch, imgs_per_seq, m.total_feats, image_token, ignore_index,
+                                          _ptr(m.src_map), _ptr(m.labels), _ptr(m.mask), _ptr(m.pos), _ptr(m.seqlens),
+                                          _ptr(m.img_pos), _ptr(m.row_of_text), _ptr(m.target), _ptr(m.status), _stream()))
+    return m
+
+
+def llavanext_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, dimage_features: torch.Tensor):
+    assert dembed_f32.dtype == torch.float32 and dimage_features.shape[0] == m.total_feats
+    check(_L.vlb200_llavanext_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32),
+                                        _ptr(dimage_features), m.n_seq * m.S, m.total_feats, m.reps, dx.shape[1], _stream()))
 
 
 # ------------------------------------------------------------------------------------------

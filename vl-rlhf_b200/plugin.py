@@ -138,7 +138,7 @@ class B200LlavaForRL(nn.Module):
         return self._hf.items()
 
     @property
-    def default_lora_target(self) -> List[str]:  # Llava/__init__.py:273-286
+    def default_lora_target(self) -> List[str]:  # Llava/__init__.py:273-286, LlavaNext/__init__.py:347-360
         return ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
 
     def get_vision_tower(self):
@@ -165,8 +165,7 @@ class _EngineLogps(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, engine, inputs):
-        ids, am, lb, px, wt = inputs
-        logps, m, feats = engine.forward_logps(ids, am, lb, px, wt, "policy", save=True)
+        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True)
         ctx.engine = engine
         return logps
 
@@ -187,10 +186,11 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
                                   getattr(self, "label_pad_token_id", -100), getattr(self, "padding_value", 0) or 0)
     ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
     px = batch["img_input_dict"]["pixel_values"]
+    sizes = batch["img_input_dict"].get("image_sizes")  # LLaVA-Next (LlavaNext/__init__.py:348-380 collators)
     wt = None
     if self.loss_type == "ddpo":
-        wt = host.ddpo_row_weights(ids, lb, eng.cfg.image_token_index, eng.cfg.n_patches)
-    inputs = eng.prepare_inputs(ids, am, lb, px, wt)
+        wt = eng.ddpo_weights(ids, am, lb, sizes)
+    inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes)
     n = batch["chosen_labels"].shape[0]
     if which == "policy" and torch.is_grad_enabled():
         anchor = torch.zeros(1, device=eng.device, requires_grad=True)
@@ -227,10 +227,18 @@ def install():
         def training_step(self, model, inputs):  # trainer.py:303-308 without the per-step empty_cache()/gc
             return super(VLDPOTrainer, self).training_step(model, inputs)
 
-    ref = llava.core_mapper
-    llava.core_mapper = ModelCoreMapper(
-        model=B200LlavaForRL, processor=ref.processor, dpo_collator=ref.dpo_collator, dpo_trainer=LlavaB200DPOTrainer,
-        reward_model=ref.reward_model, value_model=ref.value_model, reward_collator=ref.reward_collator,
-        reward_trainer=ref.reward_trainer, sft_collator=ref.sft_collator, sft_trainer=ref.sft_trainer,
-        ppo_collator=ref.ppo_collator, ppo_trainer=ref.ppo_trainer)
-    return llava.core_mapper
+    def swap(mod):
+        ref = mod.core_mapper
+        mod.core_mapper = ModelCoreMapper(
+            model=B200LlavaForRL, processor=ref.processor, dpo_collator=ref.dpo_collator, dpo_trainer=LlavaB200DPOTrainer,
+            reward_model=ref.reward_model, value_model=ref.value_model, reward_collator=ref.reward_collator,
+            reward_trainer=ref.reward_trainer, sft_collator=ref.sft_collator, sft_trainer=ref.sft_trainer,
+            ppo_collator=ref.ppo_collator, ppo_trainer=ref.ppo_trainer)
+        return mod.core_mapper
+
+    mapper = swap(llava)
+    try:  # LLaVA-Next shares the trainer; its processor / collators (image_sizes) stay the reference's
+        swap(importlib.import_module("vlrlhf.models.LlavaNext"))
+    except Exception:  # the reference's LlavaNext module needs a transformers that still has the 4.41 symbols
+        pass
+    return mapper
