@@ -18,6 +18,7 @@
 #ifndef VLB200_H
 #define VLB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -225,6 +226,24 @@ int vlb200_adamw(void* param_bf16, const void* grad_bf16, float* master, float* 
                  const float* grad_sumsq, float max_grad_norm, void* stream);
 int vlb200_cast_f32_to_bf16(const float* src, void* dst, uint64_t n, float scale, void* stream);
 int vlb200_cast_bf16_to_f32(const void* src, float* dst, uint64_t n, void* stream);
+
+/* ---- input pipeline: CLIP image preprocessing of the DPO collator on the GPU -----------------
+ * Replaces `self.processor.image_processor(images=imgs, return_tensors="pt")` in
+ * LlavaDPODataCollatorWithPadding.__call__ (models/Llava/__init__.py:435-443) = transformers-4.41
+ * CLIPImageProcessor.preprocess: Pillow Image.resize(BICUBIC) to shortest edge -> center crop -> x*(1/255) in float64
+ * stored float32 -> (x-mean)/std in float32 -> CHW.  image: device uint8 [in_h, in_w, 3] RGB (the decoded file).
+ * coef_h/bounds_h ([new_w, ksize_h] int32, [new_w, 2] int32 = first tap, tap count) and coef_v/bounds_v
+ * ([new_h, ksize_v], [new_h, 2]) are Pillow's 22-bit fixed-point resampling tables (Resample.c precompute_coeffs +
+ * normalize_coeffs_8bpc), device-resident, built by vl-rlhf_b200/preprocess.py.  (top,left,crop_h,crop_w) is the
+ * center crop inside the resized [new_h, new_w] image; only input rows [row0, row0+rows) feed it.  workspace holds the
+ * uint8 result of the horizontal pass (rows*crop_w*3 bytes).  mean_std_host: 6 floats on the HOST (mean RGB, std RGB).
+ * out: [3, crop_h, crop_w] VLB200_F32 (what the reference's collator emits) or VLB200_BF16 (its rounding).
+ * Bit-exact with Pillow + numpy for uint8 input. */
+size_t vlb200_clip_preprocess_workspace_bytes(int in_h, int crop_w);
+int vlb200_clip_preprocess_u8(const uint8_t* image, int in_h, int in_w, const int* coef_h, const int* bounds_h, int ksize_h,
+                              const int* coef_v, const int* bounds_v, int ksize_v, int new_h, int new_w, int top, int left,
+                              int crop_h, int crop_w, int row0, int rows, uint8_t* workspace, size_t workspace_bytes,
+                              double rescale, const float* mean_std_host, void* out, int out_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--config1", action="store_true")
     ap.add_argument("--config1-bf16", dest="config1_bf16", action="store_true")
     ap.add_argument("--next", action="store_true", help="only the LLaVA-Next fixtures (g6_*)")
+    ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -287,12 +288,44 @@ def main():
     if args.next:
         g6_next()
         return
+    if args.preprocess:
+        g7_clip_preprocess()
+        return
     g1_logps()
     g2_loss()
     g3_ddpo()
     g45_llava("g4_tiny", R.TINY, 2, 24, 8, 0, ddpo=True)
     g45_llava("g4_small", R.SMALL, 2, 96, 24, 0, ddpo=True)
     g6_next()
+    g7_clip_preprocess()
+
+
+from oracle.image_restate import G7_SIZES, synthetic_image  # noqa: E402
+
+
+def g7_clip_preprocess():
+    """What LlavaDPODataCollatorWithPadding (models/Llava/__init__.py:435-443) gets from
+    `processor.image_processor(images=imgs, return_tensors="pt")`: transformers' PIL-backend CLIP processor (the
+    4.41 slow processor's code path: Pillow bicubic resize, numpy crop / rescale / normalize) at the llava-1.5
+    settings (shortest_edge 336, crop 336, OpenAI CLIP mean/std), run here on seeded synthetic RGB images.
+    Stored: a per-image digest of the float32 output plus the full tensor for two images (keeps the file small)."""
+    import hashlib
+    from PIL import Image
+    from transformers.models.clip.image_processing_pil_clip import CLIPImageProcessorPil
+    proc = CLIPImageProcessorPil(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336})
+    out = {"sizes": np.array(G7_SIZES, dtype=np.int64)}
+    for i, (h, w) in enumerate(G7_SIZES):
+        img = synthetic_image(h, w, i)
+        pv = proc(images=[Image.fromarray(img)], return_tensors="np")["pixel_values"][0]
+        assert pv.dtype == np.float32 and pv.shape == (3, 336, 336)
+        out[f"sha256_{i}"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pv).tobytes()).digest(), dtype=np.uint8)
+        out[f"sum_{i}"] = np.float64(pv.astype(np.float64).sum())
+        if i in (0, 4):
+            out[f"pixel_values_{i}"] = pv
+            nw, nh = (int(336 * w / h), 336) if h <= w else (336, int(336 * h / w))
+            out[f"resized_u8_{i}"] = np.array(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
+    np.savez_compressed(os.path.join(GOLDEN, "g7_clip_preprocess.npz"), **out)
+    print("g7_clip_preprocess", {k: v.shape for k, v in out.items() if k.startswith("pixel")})
 
 
 def g6_next():

@@ -298,6 +298,28 @@ def test_next_engine_backward_parity_cpu_mock(cpu_pkg):
         assert abs(metrics[k] - float(want_metrics[k])) <= 2e-3 * max(1.0, abs(float(want_metrics[k]))), k
 
 
+def test_precomputed_reference_logps_skip_the_ref_pass(cpu_pkg):
+    """TRL precompute_ref_log_probs: `reference_*_logps` in the batch replace the no-grad reference forward."""
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+    base = eng.train_step(batch, train=False)
+    n0 = ops.launch_count()
+    eng.train_step(batch, train=False)
+    full = ops.launch_count() - n0
+    b2 = dict(batch)
+    b2["reference_chosen_logps"] = torch.from_numpy(d["ref_logps"][:2])
+    b2["reference_rejected_logps"] = torch.from_numpy(d["ref_logps"][2:])
+    n0 = ops.launch_count()
+    got = eng.train_step(b2, train=False)
+    assert ops.launch_count() - n0 < 0.75 * full  # the reference decoder pass is gone
+    for k in ("loss", "rewards/chosen", "rewards/rejected", "rewards/margins"):
+        assert abs(got[k] - base[k]) < 2e-3, k
+    with pytest.raises(ValueError):
+        a = eng.prepare_inputs(*(cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels")),
+                               cb["concatenated_img_input_dict"]["pixel_values"])
+        eng.step(*a, train=False, ref_logps=torch.zeros(3))
+
+
 def test_engine_optimizer_cpu_mock(cpu_pkg):
     config, engine, host, ops = cpu_pkg
     eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny", with_optimizer=True)
@@ -414,3 +436,43 @@ def test_train_step_metrics_match_oracle(cpu_pkg):
     assert got["rewards/accuracies"] == float(metrics["rewards/accuracies"])
     for k in ("logits/chosen", "logits/rejected"):
         assert abs(got[k] - float(metrics[k])) < 2e-3, (k, got[k], float(metrics[k]))
+
+
+# ------------------------------------------------------------------------------------------
+# collator (base/collator.py:26-68 + Llava/__init__.py:435-443) against the reference's own class
+# ------------------------------------------------------------------------------------------
+def test_collator_matches_reference_collator(tmp_path):
+    from oracle import ref_shim, image_restate as IR
+    ref_shim.install()
+    from vlrlhf.base.collator import VLDPODataCollatorWithPadding
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200.collator import B200DPODataCollatorWithPadding, load_rgb
+    Image = pytest.importorskip("PIL.Image")
+    rs = np.random.RandomState(0)
+    feats = []
+    for i, (pl, cl, rl) in enumerate([(5, 12, 9), (8, 7, 14), (3, 20, 20)]):
+        path = str(tmp_path / f"im{i}.png")
+        Image.fromarray(IR.synthetic_image(60 + 10 * i, 90 - 7 * i, i)).save(path)
+        f = {"prompt": f"p{i}", "img_path": path, "reference_chosen_logps": -1.5 * i, "reference_rejected_logps": -2.0 - i}
+        for name, n in (("prompt", pl), ("chosen", cl), ("rejected", rl)):
+            f[f"{name}_input_ids"] = rs.randint(3, 300, n).tolist()
+            f[f"{name}_attention_mask"] = [1] * n
+            if name != "prompt":
+                f[f"{name}_labels"] = [-100] * pl + f[f"{name}_input_ids"][pl:]
+        feats.append(f)
+    want = VLDPODataCollatorWithPadding(pad_token_id=301, label_pad_token_id=-100)(feats)
+    fake_pre = lambda imgs: torch.from_numpy(np.stack([IR.clip_preprocess(im, 48, 48) for im in imgs]))  # noqa: E731
+    got = B200DPODataCollatorWithPadding(pad_token_id=301, label_pad_token_id=-100, preprocessor=fake_pre)(feats)
+    assert set(want) | {"img_input_dict"} == set(got)
+    for k, v in want.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.equal(got[k], v) and got[k].dtype == v.dtype, k
+        else:
+            assert got[k] == v, k
+    # prompt is left padded, responses right padded
+    assert got["prompt_input_ids"][2, 0] == 301 and got["chosen_input_ids"][1, -1] == 301
+    # image step: decoded RGB of the same files through the (here CPU stand-in) preprocessor
+    assert got["img_input_dict"]["pixel_values"].shape == (3, 3, 48, 48)
+    assert np.array_equal(load_rgb(feats[1]["img_path"]), IR.synthetic_image(70, 83, 1))
+    with pytest.raises(ValueError):
+        B200DPODataCollatorWithPadding(is_encoder_decoder=True)

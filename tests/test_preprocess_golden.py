@@ -1,0 +1,59 @@
+"""Image side of the DPO collator -- CPU tests.
+
+* the oracle (oracle/image_restate.py: Pillow's 8-bit bicubic resampler + transformers' crop/rescale/normalize
+  restated in numpy) against the committed fixture minted from Pillow + transformers' PIL-backend CLIP processor
+  (tests/golden/g7_clip_preprocess.npz) and, when Pillow is importable, against Pillow itself on fresh sizes;
+* the product's host tables (vl-rlhf_b200/preprocess.py, vectorised) == the oracle's loop restatement, bit-exact.
+The CUDA kernels themselves are checked in tests/test_gpu_preprocess.py.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import image_restate as IR
+
+G = os.path.join(os.path.dirname(__file__), "golden", "g7_clip_preprocess.npz")
+
+
+def test_oracle_matches_golden_fixture():
+    d = np.load(G)
+    sizes = [tuple(x) for x in d["sizes"].tolist()]
+    assert sizes == IR.G7_SIZES
+    for i, (h, w) in enumerate(sizes):
+        img = IR.synthetic_image(h, w, i)
+        pv = IR.clip_preprocess(img)
+        assert pv.dtype == np.float32 and pv.shape == (3, 336, 336)
+        digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pv).tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(digest, d[f"sha256_{i}"]), (i, h, w)  # bit-exact float32 output
+        if f"pixel_values_{i}" in d.files:
+            assert np.array_equal(pv, d[f"pixel_values_{i}"])
+            nh, nw = IR.shortest_edge_size(h, w, 336)
+            assert np.array_equal(IR.pil_bicubic_resize_u8(img, (nh, nw)), d[f"resized_u8_{i}"])
+
+
+def test_oracle_matches_pillow_on_fresh_sizes():
+    Image = pytest.importorskip("PIL.Image")
+    rs = np.random.RandomState(7)
+    for (h, w), (oh, ow) in [((123, 457), (336, 1248)), ((900, 350), (864, 336)), ((64, 64), (336, 336)),
+                             ((336, 500), (336, 500)), ((1200, 1600), (336, 448)), ((10, 3000), (5, 7))]:
+        img = rs.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(IR.pil_bicubic_resize_u8(img, (oh, ow)), want), ((h, w), (oh, ow))
+
+
+def test_product_host_tables_equal_oracle():
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import preprocess as P
+    for i, o in [(640, 448), (480, 336), (336, 336), (300, 336), (1000, 1120), (2048, 504), (70, 470), (337, 337), (50, 336),
+                 (3, 7), (4000, 336), (97, 336), (211, 730)]:
+        ks, b, kk = IR.precompute_coeffs(i, 0.0, float(i), o)
+        k2, b2, c2 = P.resample_tables(i, o)
+        assert ks == k2 and np.array_equal(b, b2) and np.array_equal(IR.normalize_coeffs_8bpc(kk), c2), (i, o)
+    for hw in [(480, 640), (640, 480), (336, 336), (1000, 300), (200, 333), (1365, 2048), (337, 336), (97, 211)]:
+        nh, nw = IR.shortest_edge_size(*hw, 336)
+        g = P.resize_geometry(*hw, 336, 336)
+        assert (nh, nw) == g[:2] and g[2] == (nh - 336) // 2 and g[3] == (nw - 336) // 2
+    with pytest.raises(ValueError):
+        P.resize_geometry(100, 100, 224, 336)

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvlb200.so")
@@ -74,6 +74,10 @@ SIGNATURES = {
                              c_float, c_float, c_int, c_float, c_void_p, c_float, c_void_p]),
     "vlb200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_uint64, c_float, c_void_p]),
     "vlb200_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "vlb200_clip_preprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vlb200_clip_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_double,
+                                          c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 

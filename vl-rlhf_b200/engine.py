@@ -544,12 +544,20 @@ class LlavaDPOEngine:
         w = self.policy if which == "policy" else self.ref
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
-    def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True) -> StepOutput:
+    def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True,
+             ref_logps: Optional[torch.Tensor] = None) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
-        backward + gradient all-reduce + AdamW."""
+        backward + gradient all-reduce + AdamW.  `ref_logps` ([2B] fp32, chosen then rejected) replaces the reference
+        pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
+        the collator's `_logps` keys, base/collator.py:62-64)."""
         tc = self.tc
         pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train)
-        ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, feats=feats, m=m)
+        if ref_logps is not None:
+            ref = ref_logps.to(self.device, torch.float32).reshape(-1).contiguous()
+            if ref.numel() != pol.numel():
+                raise ValueError(f"ref_logps holds {ref.numel()} values, the batch has {pol.numel()} sequences")
+        else:
+            ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    1.0, want_grad=train)
         out = StepOutput()
@@ -577,7 +585,11 @@ class LlavaDPOEngine:
         wt = None
         if tc.loss_type == "ddpo":
             wt = self.ddpo_weights(ids, am, lb, sizes)
-        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train)
+        ref_logps = None
+        if "reference_chosen_logps" in batch and "reference_rejected_logps" in batch:  # precompute_ref_log_probs
+            ref_logps = torch.cat([torch.as_tensor(batch["reference_chosen_logps"], dtype=torch.float32).reshape(-1),
+                                   torch.as_tensor(batch["reference_rejected_logps"], dtype=torch.float32).reshape(-1)])
+        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train, ref_logps=ref_logps)
         n = out.policy_logps.numel() // 2
         packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
                             (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0),

@@ -428,3 +428,24 @@ def cast_f32_to_bf16(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
 def cast_bf16_to_f32(src: torch.Tensor, dst: torch.Tensor):
     check(_L.vlb200_cast_bf16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()))
     return dst
+
+
+# ------------------------------------------------------------------------------------------
+# input pipeline: CLIP image preprocessing (Llava/__init__.py:435-443 -> CLIPImageProcessor)
+# ------------------------------------------------------------------------------------------
+def clip_preprocess_u8(image: torch.Tensor, coef_h: torch.Tensor, bounds_h: torch.Tensor, ksize_h: int, coef_v: torch.Tensor,
+                       bounds_v: torch.Tensor, ksize_v: int, new_h: int, new_w: int, top: int, left: int, crop_h: int,
+                       crop_w: int, row0: int, rows: int, workspace: torch.Tensor, rescale: float, mean_std_host,
+                       out: torch.Tensor):
+    """image uint8 [H, W, 3] (CUDA) -> out [3, crop_h, crop_w]; `mean_std_host` is a contiguous float32 numpy array
+    of 6 values (mean RGB, std RGB) on the host."""
+    assert image.dtype == torch.uint8 and image.is_contiguous() and image.dim() == 3 and image.shape[2] == 3
+    assert workspace.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (3, crop_h, crop_w)
+    for t in (coef_h, bounds_h, coef_v, bounds_v):
+        assert t.dtype == torch.int32 and t.is_contiguous()
+    assert mean_std_host.dtype.name == "float32" and mean_std_host.size == 6 and mean_std_host.flags["C_CONTIGUOUS"]
+    check(_L.vlb200_clip_preprocess_u8(_ptr(image), int(image.shape[0]), int(image.shape[1]), _ptr(coef_h), _ptr(bounds_h),
+                                       ksize_h, _ptr(coef_v), _ptr(bounds_v), ksize_v, new_h, new_w, top, left, crop_h, crop_w,
+                                       row0, rows, _ptr(workspace), workspace.numel(), float(rescale),
+                                       mean_std_host.ctypes.data, _ptr(out), _dt(out), _stream()))
+    return out
