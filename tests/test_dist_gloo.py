@@ -32,7 +32,9 @@ def _worker(rank, world, port, out_dir):
     from vlrlhf_b200 import config, host
     from oracle import restate as R
     torch.set_num_threads(2)
+    os.environ["VLB200_SHARD_OPTIMIZER"] = "0"   # replicated AdamW first: the plain all-reduce path
     eng = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3), device="cpu")
+    assert not eng.shard_optimizer
     eng.init_synthetic(0)  # same weights on every rank
     batch = R.make_batch(R.TINY, 2, 24, 8, seed=100 + rank)  # rank-local pairs
     cb = host.concatenated_inputs(batch)
@@ -53,8 +55,19 @@ def _worker(rank, world, port, out_dir):
     eng2.init_synthetic(0)
     eng2.overlap_allreduce = True
     eng2.step(*a[:4], train=True)
+    # optimizer sharded over the ranks (the default when world > 1): reduce-scatter, AdamW on the own slice, all-gather
+    os.environ["VLB200_SHARD_OPTIMIZER"] = "1"
+    eng3 = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3), device="cpu")
+    assert eng3.shard_optimizer and eng3.n_flat % (2 * engine.ALIGN) == 0
+    assert eng3.master.numel() == eng3.n_flat // 2 and eng3.shard_lo == rank * eng3.n_flat // 2
+    eng3.init_synthetic(0)
+    eng3.step(*a[:4], train=True)
+    n = eng.params.numel()
     torch.save({"local": local, "summed": summed, "params": eng.params.clone(), "world": eng.world_size(),
-                "sumsq": eng.grad_sumsq.clone(), "params_overlap": eng2.params.clone(), "grads_overlap": eng2.grads.clone()},
+                "sumsq": eng.grad_sumsq.clone(), "params_overlap": eng2.params.clone(), "grads_overlap": eng2.grads.clone(),
+                "params_sharded": eng3.params[:n].clone(), "sumsq_sharded": eng3.grad_sumsq.clone(),
+                "grads_sharded_own": eng3.grads[eng3.shard_lo:eng3.shard_hi].clone(), "shard": (eng3.shard_lo, eng3.shard_hi),
+                "master_sharded": eng3.master.clone(), "master": eng.master.clone()},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -80,3 +93,16 @@ def test_two_rank_data_parallel_step(tmp_path):
     # bucketed + overlapped all-reduce gives the same reduced gradients and the same parameters
     assert torch.equal(r0["grads_overlap"], r0["summed"]) and torch.equal(r1["grads_overlap"], r0["summed"])
     assert torch.equal(r0["params_overlap"], r0["params"]) and torch.equal(r1["params_overlap"], r1["params"])
+    # sharded optimizer: replicas identical after the all-gather, each rank's reduced slice == the all-reduced buffer,
+    # and the update equals the replicated one (the gradient-norm scalar is summed in a different order: 1-ulp slack)
+    assert torch.equal(r0["params_sharded"], r1["params_sharded"])
+    n = r0["summed"].numel()
+    for r in (r0, r1):
+        lo, hi = r["shard"]
+        hi_c = min(hi, n)
+        assert torch.equal(r["grads_sharded_own"][:hi_c - lo], r0["summed"][lo:hi_c])
+        torch.testing.assert_close(r["master_sharded"][:hi_c - lo], r["master"][lo:hi_c], rtol=1e-6, atol=1e-9)
+    assert torch.equal(r0["sumsq_sharded"], r1["sumsq_sharded"])
+    torch.testing.assert_close(r0["sumsq_sharded"], r0["sumsq"], rtol=1e-5, atol=0)
+    same = (r0["params_sharded"] == r0["params"]).float().mean().item()
+    assert same > 0.9999, same

@@ -35,7 +35,7 @@ def load_rgb(path: str) -> np.ndarray:
     """`Image.open(path).convert("RGB")` as an [H, W, 3] uint8 array (host decode, Llava/__init__.py:439)."""
     from PIL import Image
     with Image.open(path) as im:
-        return np.asarray(im.convert("RGB"))
+        return np.array(im.convert("RGB"))  # writable copy
 
 
 class B200DPODataCollatorWithPadding:

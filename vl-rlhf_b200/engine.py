@@ -154,9 +154,23 @@ class LlavaDPOEngine:
         self.layout = _trainable_layout(cfg)
         self.vlayout = _vision_layout(cfg)
         n = self.layout.size
-        self.params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)      # policy (projector + LLM)
-        self.ref_params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)  # frozen reference copy
-        self.grads = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        import os as _os
+        # Optimizer sharding across the data-parallel ranks (ZeRO-1 style; the reference's default DeepSpeed config
+        # shards optimizer state too, accelerate_config/zero2.yaml): gradients are reduce-SCATTERED, each rank runs
+        # AdamW on its 1/world slice of the flat buffers (fp32 master + moments exist for that slice only) and the
+        # updated bf16 parameters are all-gathered.  Same wire traffic as one all-reduce, AdamW time and optimizer
+        # memory divided by world.  Results equal the replicated update (AdamW is elementwise).
+        world = self.world_size()
+        self.shard_optimizer = world > 1 and with_optimizer and _os.environ.get("VLB200_SHARD_OPTIMIZER", "1") != "0"
+        gran = ALIGN * world
+        n_flat = (n + gran - 1) // gran * gran if self.shard_optimizer else n
+        self.n_flat = n_flat
+        rank = torch.distributed.get_rank(self.pg) if world > 1 else 0
+        self.shard_lo, self.shard_hi = (rank * (n_flat // world), (rank + 1) * (n_flat // world)) if self.shard_optimizer \
+            else (0, n_flat)
+        self.params = torch.zeros(n_flat, dtype=torch.bfloat16, device=self.device)  # policy (projector + LLM)
+        self.ref_params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)   # frozen reference copy
+        self.grads = torch.zeros(n_flat, dtype=torch.bfloat16, device=self.device)
         self.vparams = torch.zeros(self.vlayout.size, dtype=torch.bfloat16, device=self.device)  # frozen vision tower
         self.policy = Weights(self.layout, self.params)
         self.ref = Weights(self.layout, self.ref_params)
@@ -164,14 +178,14 @@ class LlavaDPOEngine:
         self.vis = Weights(self.vlayout, self.vparams)
         self.with_optimizer = with_optimizer
         if with_optimizer:
-            self.master = torch.zeros(n, dtype=torch.float32, device=self.device)
-            self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
-            self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+            ns = self.shard_hi - self.shard_lo
+            self.master = torch.zeros(ns, dtype=torch.float32, device=self.device)
+            self.exp_avg = torch.zeros(ns, dtype=torch.float32, device=self.device)
+            self.exp_avg_sq = torch.zeros(ns, dtype=torch.float32, device=self.device)
         self.dembed_f32 = torch.zeros(cfg.vocab, cfg.hidden, dtype=torch.float32, device=self.device)
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
-        import os as _os
         # VLB200_OVERLAP_ALLREDUCE=1 launches per-layer gradient buckets on the NCCL stream while backward continues.
         # Measured on 2xB200 (profiles/r1_bench_7b_2gpu_overlap.md): 697.4 ms/step overlapped vs 689.9 ms with ONE
         # all-reduce after backward -- the NCCL kernels take SMs from the persistent GEMMs' static tile schedule and
@@ -225,7 +239,7 @@ class LlavaDPOEngine:
             ops.init_uniform_(other, tensor_seed(name, seed + 1), scale, shift)
             ops.perturb_(ref[name].view(-1), dst.view(-1), other, ref_alpha, 1.0 if name.endswith("norm.weight") else 0.0)
         if self.with_optimizer:
-            ops.cast_bf16_to_f32(self.params, self.master)
+            ops.cast_bf16_to_f32(self.params[self.shard_lo:self.shard_hi], self.master)
         if self.device.type == "cuda":
             torch.cuda.synchronize()
 
@@ -235,7 +249,7 @@ class LlavaDPOEngine:
             if k in dst:
                 dst[k].copy_(v.to(device=self.device, dtype=torch.bfloat16).view(dst[k].shape))
         if which == "policy" and self.with_optimizer:
-            ops.cast_bf16_to_f32(self.params, self.master)
+            ops.cast_bf16_to_f32(self.params[self.shard_lo:self.shard_hi], self.master)
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
@@ -464,6 +478,10 @@ class LlavaDPOEngine:
             for h in self._pending:
                 h.wait()
             self._pending = []
+        elif self.shard_optimizer:
+            # in place: rank r keeps the sum of slice r (only that slice is read by the sharded AdamW)
+            torch.distributed.reduce_scatter_tensor(self.grads[self.shard_lo:self.shard_hi], self.grads,
+                                                    op=torch.distributed.ReduceOp.SUM, group=self.pg)
         else:
             torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
@@ -475,10 +493,16 @@ class LlavaDPOEngine:
     def optimizer_step(self):
         tc = self.tc
         self.opt_step += 1
-        ops.sumsq(self.grads, self.grad_sumsq, self.sumsq_ws)
-        ops.adamw_(self.params, self.grads, self.master, self.exp_avg, self.exp_avg_sq, tc.learning_rate, tc.adam_beta1,
+        lo, hi = self.shard_lo, self.shard_hi
+        g, p = self.grads[lo:hi], self.params[lo:hi]
+        ops.sumsq(g, self.grad_sumsq, self.sumsq_ws)
+        if self.shard_optimizer:  # global gradient norm = sum of the slices' squared norms (one fp32 scalar)
+            torch.distributed.all_reduce(self.grad_sumsq, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        ops.adamw_(p, g, self.master, self.exp_avg, self.exp_avg_sq, tc.learning_rate, tc.adam_beta1,
                    tc.adam_beta2, tc.adam_eps, tc.weight_decay, self.opt_step, grad_scale=1.0 / self.world_size(),
                    grad_sumsq=self.grad_sumsq, max_grad_norm=tc.max_grad_norm)
+        if self.shard_optimizer:
+            torch.distributed.all_gather_into_tensor(self.params, p, group=self.pg)
 
     # ------------------------------------------------------------------ the step
     def prepare_inputs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
