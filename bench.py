@@ -32,6 +32,8 @@ PAIRS_PER_GPU = 4
 TEXT_LEN = 1024
 PROMPT_LEN = 128
 WORKLOAD = "LLaVA-1.5-7B DPO bf16 full-FT, 4 pairs/GPU, text 1024 (1599 merged), 1x336px image/pair"
+WORKLOAD_NEXT = ("LLaVA-Next-Mistral-7B DDPO bf16 full-FT (configs[3], side measurement), 4 pairs/GPU, text 1024, 1x336px image "
+                 "-> 3 anyres crops -> 1176 packed image tokens (2199 merged), activation checkpointing")
 
 
 def peaks():
@@ -60,7 +62,8 @@ def step_flops(cfg, n_pairs, S, rows_lm):
     dv, Sv = cfg.v_hidden, cfg.n_patches + 1
     vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + cfg.n_patches * 2 * cfg.patch_k * dv
     proj = cfg.n_patches * 2 * (dv * d + d * d)
-    return n_pairs * (2 * per_seq * 4 + vit + proj * 4) + lm * 4
+    crops = getattr(cfg, "_bench_crops_per_image", 1)  # LLaVA-Next: the tower and projector run once per anyres crop
+    return n_pairs * (2 * per_seq * 4 + crops * (vit + proj * 4)) + lm * 4
 
 
 class ClockSampler:
@@ -225,15 +228,23 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import config, engine, host, ops, synthetic
-    cfg = {"7b": config.LLAVA15_7B, "small": config.SMALL, "tiny": config.TINY}[args.model]
-    text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model == "7b" else (96, 24)
-    eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=args.loss_type))
+    cfg = {"7b": config.LLAVA15_7B, "small": config.SMALL, "tiny": config.TINY, "next7b": config.LLAVANEXT_MISTRAL_7B,
+           "next_small": config.SMALL_NEXT}[args.model]
+    text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
+    is_next = cfg.family == "llava_next"
+    loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
+    # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
+    eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b")))
     eng.init_synthetic(0)  # same weights on every rank
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)  # rank-local pairs
     cb = host.concatenated_inputs(batch)
-    dev_inputs = eng.prepare_inputs(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
-                                    cb["concatenated_labels"], batch["img_input_dict"]["pixel_values"])
-    S = text_len - 1 + cfg.n_patches
+    ids_h, am_h, lb_h = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+    sizes_h = batch["img_input_dict"].get("image_sizes")
+    wt_h = eng.ddpo_weights(ids_h, am_h, lb_h, sizes_h) if loss_type == "ddpo" else None
+    dev_inputs = eng.prepare_inputs(ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"], wt_h, sizes_h)
+    S = dev_inputs[5].merged_len if is_next else text_len - 1 + cfg.n_patches
+    if is_next:
+        cfg._bench_crops_per_image = dev_inputs[5].crops[0]
     rows_lm = 2 * PAIRS_PER_GPU * (text_len - 1)
 
     def barrier():
@@ -254,7 +265,7 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    step_dev = lambda: eng.step(*dev_inputs[:4], train=True)  # noqa: E731
+    step_dev = lambda: eng.step(*dev_inputs, train=True)  # noqa: E731
     last = {}
 
     def step_e2e():
@@ -278,7 +289,7 @@ def run_b200(args):
     T = 2 * PAIRS_PER_GPU * S
     a = eng.buf("s.h", (T, cfg.hidden))
     wgu = eng.policy["L0.wgu"]
-    out = eng.buf("a.gu.0", (T, 2 * cfg.ff))
+    out = eng.buf("s.gu" if eng.tc.activation_checkpointing else "a.gu.0", (T, 2 * cfg.ff))
     gemm_ms = timed(lambda: ops.gemm(a, wgu, out=out), 10)
     pk, pk_src = peaks()
     gemm_tf = 2.0 * T * 2 * cfg.ff * cfg.hidden / gemm_ms / 1e9
@@ -291,8 +302,10 @@ def run_b200(args):
             "metric": METRIC, "value": pairs / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.model == "7b" else f"{args.model} (dev config, NOT the benchmark)",
-                       "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": args.loss_type,
+            "config": {"workload": WORKLOAD if args.model == "7b" else (
+                           WORKLOAD_NEXT if args.model == "next7b" else f"{args.model} (dev config, NOT the benchmark)"),
+                       "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
+                       "activation_checkpointing": eng.tc.activation_checkpointing,
                        "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master+moments, max_grad_norm 1.0",
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
                        "step_tflop_algorithmic": flops / 1e12,
@@ -321,7 +334,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny"])
+    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small"],
+                    help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO (side measurement)")
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")

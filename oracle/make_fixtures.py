@@ -246,8 +246,10 @@ def g45_llava(tag: str, cfg: R.LlavaCfg, n_pairs: int, text_len: int, prompt_len
         logps, o = reference_concatenated_forward(m, cfg, batch, "sigmoid")
         res[who] = logps
         out[f"{who}_logps"] = logps.numpy()
-        if ddpo:
-            dl, _ = reference_concatenated_forward(m, cfg, batch, "ddpo")
+        if ddpo:  # same forward, the reference's get_batch_logps with mask_shared_tokens=True (trainer.py:169-184)
+            VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+            dl = VLDPOTrainer.get_batch_logps(o.logits, o.labels, average_log_prob=False, is_encoder_decoder=False,
+                                              label_pad_token_id=-100, mask_shared_tokens=True)
             out[f"{who}_logps_ddpo"] = dl.numpy()
             res[who + "_ddpo"] = dl
         if who == "policy":
@@ -274,6 +276,7 @@ def main():
     ap.add_argument("--config1", action="store_true")
     ap.add_argument("--config1-bf16", dest="config1_bf16", action="store_true")
     ap.add_argument("--next", action="store_true", help="only the LLaVA-Next fixtures (g6_*)")
+    ap.add_argument("--config4", action="store_true", help="LLaVA-Next-Mistral-7B shapes, DDPO (BASELINE.json configs[3])")
     ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -287,6 +290,11 @@ def main():
         return
     if args.next:
         g6_next()
+        return
+    if args.config4:
+        # BASELINE.json configs[3] at parity size: Mistral-7B decoder + CLIP-L/336 anyres, 1 pair, text 96, one wide
+        # image (1x2 grid -> 3 crops, unpadded), DDPO token weights, fp32 CPU
+        g45_llava("g8_config4_next7b", R.LLAVANEXT_MISTRAL_7B, 1, 96, 24, 0, ddpo=True, image_sizes=[(400, 640)])
         return
     if args.preprocess:
         g7_clip_preprocess()

@@ -261,3 +261,50 @@ def test_next_merge_kernels_match_host_mock(pkg):
     eng = engine.LlavaDPOEngine(config.TINY_NEXT, config.TrainConfig(), with_optimizer=False)
     with pytest.raises(ValueError):
         eng.check_merge_status(st)
+
+
+@pytest.mark.parametrize("tag", ["g4_small", "g6_next_small"])
+def test_activation_checkpointing_bit_identical(pkg, tag):
+    """TrainConfig.activation_checkpointing keeps only the fp32 layer inputs and recomputes each layer in backward:
+    every kernel is deterministic, so gradients and log-probs are bit-identical to the keep-everything schedule."""
+    config, engine, host, ops = pkg
+    res = []
+    for ckpt in (False, True):
+        eng, rcfg, d, batch, cb = build(pkg, tag, with_optimizer=False)
+        eng.tc.activation_checkpointing = ckpt
+        out = eng.step(*stage(eng, host, cb, rcfg), train=True)
+        torch.cuda.synchronize()
+        res.append((eng.grads.clone(), out.policy_logps.clone()))
+        assert (not any(k.startswith("a.qkv") for k in eng._bufs)) == ckpt
+    assert torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][0], res[1][0])
+
+
+def test_config4_next7b_shapes_ddpo_parity(pkg):
+    """BASELINE.json configs[3] at parity size: LLaVA-Next-Mistral-7B shapes (CLIP-L/336 anyres crops, Mistral decoder
+    GQA 32/8, ff 14336, theta 1e6), 1 pair, text 96, DDPO token weights -- against the reference's LlavaNextForRL.forward
+    + get_batch_logps(mask_shared_tokens) + dpo_loss run in fp32 on CPU (tests/golden/g8_config4_next7b.npz)."""
+    config, engine, host, ops = pkg
+    path = os.path.join(G, "g8_config4_next7b.npz")
+    if not os.path.exists(path):
+        pytest.skip("g8 fixture not generated yet (oracle/make_fixtures.py --config4)")
+    d = np.load(path)
+    rcfg = R.LLAVANEXT_MISTRAL_7B
+    sizes = [tuple(x) for x in d["image_sizes"].tolist()]
+    eng = engine.LlavaDPOEngine(config.LLAVANEXT_MISTRAL_7B, config.TrainConfig(loss_type="ddpo"), with_optimizer=False)
+    eng.init_synthetic(int(d["seed"]))
+    batch = R.make_batch(rcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True,
+                         image_sizes=sizes)
+    cb = host.concatenated_inputs(batch)
+    for ddpo, key in ((False, "policy_logps"), (True, "policy_logps_ddpo")):
+        a = stage(eng, host, cb, rcfg, ddpo=ddpo)
+        out = eng.step(*a, train=False)
+        pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
+        rkey = key.replace("policy", "ref")
+        print("config4", key, pol, "golden", d[key], "rel", np.abs(pol / d[key] - 1), "ref rel", np.abs(ref / d[rkey] - 1))
+        np.testing.assert_allclose(pol, d[key], rtol=1e-3)
+        np.testing.assert_allclose(ref, d[rkey], rtol=1e-3)
+    slack = 0.1 * 1e-3 * np.abs(d["policy_logps_ddpo"]).max() * 4
+    np.testing.assert_allclose(out.losses.cpu().numpy(), d["ddpo_losses"], atol=slack)
+    del eng
+    torch.cuda.empty_cache()

@@ -320,6 +320,20 @@ def test_precomputed_reference_logps_skip_the_ref_pass(cpu_pkg):
         eng.step(*a, train=False, ref_logps=torch.zeros(3))
 
 
+def test_activation_checkpointing_gives_identical_gradients(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    grads = []
+    for ckpt in (False, True):
+        eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+        eng.tc.activation_checkpointing = ckpt
+        ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+        out = eng.step(*eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"]), train=True)
+        grads.append((eng.grads.clone(), out.policy_logps.clone()))
+        saved = [k for k in eng._bufs if k.startswith("a.qkv")]
+        assert (len(saved) == 0) == ckpt  # per-layer activations are not kept when checkpointing
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
 def test_engine_optimizer_cpu_mock(cpu_pkg):
     config, engine, host, ops = cpu_pkg
     eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny", with_optimizer=True)

@@ -108,6 +108,9 @@ class TrainConfig:
     adam_eps: float = 1e-6
     weight_decay: float = 0.0
     max_grad_norm: float = 1.0
+    # HF TrainingArguments.gradient_checkpointing (dpo.py:21 / scripts/*.sh --gradient_checkpointing True): keep only
+    # each decoder layer's fp32 input, recompute the layer (minus down_proj) in backward
+    activation_checkpointing: bool = False
 
 
 def tensor_seed(name: str, base_seed: int) -> int:

@@ -297,6 +297,41 @@ class LlavaDPOEngine:
         ops.copy_rows(xb, Sv * dv, dv, 1, feats, P * dv, dv, Bv, P, dv)
         return feats
 
+    # ------------------------------------------------------------------ one decoder layer
+    def _layer_bufs(self, pre: str, sfx: str, m: "ops.MergeIndex") -> Dict[str, torch.Tensor]:
+        cfg = self.cfg
+        T = m.n_seq * m.S
+        H, dh = cfg.heads, cfg.head_dim
+        return dict(rstd1=self.buf(f"{pre}.rstd1{sfx}", (T,), torch.float32),
+                    rstd2=self.buf(f"{pre}.rstd2{sfx}", (T,), torch.float32),
+                    qkv=self.buf(f"{pre}.qkv{sfx}", (T, cfg.qkv_dim)), att=self.buf(f"{pre}.att{sfx}", (T, H * dh)),
+                    lse=self.buf(f"{pre}.lse{sfx}", (m.n_seq, H, m.S), torch.float32),
+                    xmid=self.buf(f"{pre}.xmid{sfx}", (T, cfg.hidden), torch.float32),
+                    gu=self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff)))
+
+    def _layer_fwd(self, w: Weights, i: int, x: torch.Tensor, b: Dict[str, torch.Tensor], m: "ops.MergeIndex",
+                   xn: Optional[torch.Tensor]):
+        """Decoder layer i on the fp32 residual stream x -> xn (K9-K14).  xn=None stops after the gate|up GEMM: the
+        recompute of a checkpointed layer needs the saved-for-backward tensors, not the layer output."""
+        cfg = self.cfg
+        d, T = cfg.hidden, m.n_seq * m.S
+        H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
+        hd, kvd = H * dh, KV * dh
+        h = self.buf("s.h", (T, d))
+        qkv, att, xmid, gu = b["qkv"], b["att"], b["xmid"], b["gu"]
+        ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=b["rstd1"])
+        ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
+        ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
+        ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
+                        True, 1.0 / math.sqrt(dh))
+        ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
+        ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
+        ops.gemm(h, w[f"L{i}.wgu"], out=gu)
+        if xn is not None:
+            act = self.buf("s.act", (T, cfg.ff))
+            ops.swiglu_fwd(gu, act)
+            ops.gemm(act, w[f"L{i}.wd"], out=xn, residual=xmid)
+
     # ------------------------------------------------------------------ forward of one model copy
     def _forward(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, tag: str, save: bool,
                  ddpo_weight: Optional[torch.Tensor]):
@@ -329,31 +364,16 @@ class LlavaDPOEngine:
         # through 32 layers); every GEMM operand (normed activations, q/k/v, attention out, SwiGLU out) is bf16
         x = self.buf("x.0" if save else "s.x0", (T, d), torch.float32)
         ops.llava_merge_embed(m, w["embed"], img, x)
-        h = self.buf("s.h", (T, d))
-        act = self.buf("s.act", (T, cfg.ff))
-        scale = 1.0 / math.sqrt(dh)
+        ckpt = save and self.tc.activation_checkpointing
         for i in range(L):
-            sfx = f".{i}" if save else ""
-            pre = "a" if save else "s"
-            rstd1 = self.buf(f"{pre}.rstd1{sfx}", (T,), torch.float32)
-            rstd2 = self.buf(f"{pre}.rstd2{sfx}", (T,), torch.float32)
-            qkv = self.buf(f"{pre}.qkv{sfx}", (T, cfg.qkv_dim))
-            att = self.buf(f"{pre}.att{sfx}", (T, hd))
-            lse = self.buf(f"{pre}.lse{sfx}", (m.n_seq, H, m.S), torch.float32)
-            xmid = self.buf(f"{pre}.xmid{sfx}", (T, d), torch.float32)
-            gu = self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff))
+            # saved for backward: everything (pre "a", one set per layer) or, with activation checkpointing, only the
+            # fp32 layer input x.{i} (the rest is recomputed by _backward into the shared scratch set "s")
+            keep = save and not ckpt
+            b = self._layer_bufs("a" if keep else "s", f".{i}" if keep else "", m)
             xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d), torch.float32)
-            ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=rstd1)
-            ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
-            ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
-            ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, lse, m.seqlens, m.n_seq, m.S, H, KV, dh,
-                         True, scale)
-            ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
-            ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=rstd2)
-            ops.gemm(h, w[f"L{i}.wgu"], out=gu)
-            ops.swiglu_fwd(gu, act)
-            ops.gemm(act, w[f"L{i}.wd"], out=xn, residual=xmid)
+            self._layer_fwd(w, i, x, b, m, xn)
             x = xn
+        h = self.buf("s.h", (T, d))
         rstd_f = self.buf("a.rstd_f" if save else "s.rstd_f", (T,), torch.float32)
         ops.rmsnorm_fwd(x, w["norm"], cfg.rms_eps, out=h, rstd=rstd_f)
         # lm_head only on rows that can carry a label (K15) + fused log-prob gather (K16)
@@ -407,8 +427,13 @@ class LlavaDPOEngine:
         scale = 1.0 / math.sqrt(dh)
         for i in reversed(range(cfg.layers)):
             x_in = self._bufs[f"x.{i}"]
-            xmid, gu, qkv, att = (self._bufs[f"a.{k}.{i}"] for k in ("xmid", "gu", "qkv", "att"))
-            rstd1, rstd2, lse = (self._bufs[f"a.{k}.{i}"] for k in ("rstd1", "rstd2", "lse"))
+            if self.tc.activation_checkpointing:  # recompute the layer's saved tensors from its fp32 input
+                sb = self._layer_bufs("s", "", m)
+                self._layer_fwd(w, i, x_in, sb, m, None)
+            else:
+                sb = self._layer_bufs("a", f".{i}", m)
+            xmid, gu, qkv, att = (sb[k] for k in ("xmid", "gu", "qkv", "att"))
+            rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- MLP
             ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h)                         # recompute h2
             ops.swiglu_fwd(gu, act)                                                           # recompute act

@@ -12,7 +12,10 @@ import torch
 from .config import ModelConfig
 
 
-def make_batch(cfg: ModelConfig, n_pairs: int, text_len: int, prompt_len: int, seed: int, pin: bool = False) -> Dict:
+def make_batch(cfg: ModelConfig, n_pairs: int, text_len: int, prompt_len: int, seed: int, pin: bool = False,
+               image_sizes=None) -> Dict:
+    """LLaVA-Next (`cfg.family == "llava_next"`): pixel_values is the processor's [B, max_crops, 3, H, W] stack and
+    `image_sizes` [B, 2] (height, width; default: square crop-sized images) rides along (LlavaNext/__init__.py:211-225)."""
     g = np.random.RandomState(seed)
     lo, hi = 3, min(cfg.image_token_index, cfg.vocab) - 1
     B, L = n_pairs, text_len
@@ -38,7 +41,16 @@ def make_batch(cfg: ModelConfig, n_pairs: int, text_len: int, prompt_len: int, s
         out[f"{key}_attention_mask"] = torch.from_numpy(mask)
         out[f"{key}_labels"] = torch.from_numpy(labels)
     gen = torch.Generator().manual_seed(seed)
-    out["img_input_dict"] = {"pixel_values": torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=gen)}
+    if cfg.family == "llava_next":
+        from .host import anyres_num_crops
+        sizes = list(image_sizes) if image_sizes is not None else [(cfg.image_size, cfg.image_size)] * B
+        crops = [anyres_num_crops(sz, cfg.image_grid_pinpoints, cfg.image_size) for sz in sizes]
+        px = torch.randn(B, max(crops), 3, cfg.image_size, cfg.image_size, generator=gen)
+        for b, c in enumerate(crops):
+            px[b, c:] = 0
+        out["img_input_dict"] = {"pixel_values": px, "image_sizes": torch.tensor(sizes, dtype=torch.int64)}
+    else:
+        out["img_input_dict"] = {"pixel_values": torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=gen)}
     if pin:
         for k, v in list(out.items()):
             if isinstance(v, torch.Tensor):
