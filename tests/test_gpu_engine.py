@@ -153,6 +153,7 @@ def test_optimizer_step_reduces_loss_and_tracks_master(pkg):
         out = eng.step(ids, am, lb, px, train=True)
         losses.append(float(out.stats[0]))
     assert losses[-1] < losses[0], losses
+    eng.wait_optimizer()  # the optimizer runs on a side stream; order this stream after it before peeking at its state
     assert torch.equal(eng.params, eng.master.to(torch.bfloat16))
     assert torch.isfinite(eng.master).all()
     assert eng.opt_step == 4 and float(eng.grad_sumsq) > 0

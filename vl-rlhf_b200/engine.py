@@ -192,6 +192,16 @@ class LlavaDPOEngine:
         # cost more than the ~28 ms they hide, so the single all-reduce is the default.
         self.overlap_allreduce = _os.environ.get("VLB200_OVERLAP_ALLREDUCE", "0") == "1"
         self._pending = []
+        # Deferred optimizer: the gradient reduction + grad-norm + AdamW (+ parameter all-gather) of step t run on a
+        # side stream and overlap the frozen-reference forward of step t+1, which does not read the policy weights.
+        # AdamW/sumsq are HBM-bound kernels without shared memory, so their CTAs co-reside with the persistent GEMM
+        # CTAs instead of displacing them.  The policy forward waits on `opt_done` (device-side event wait).
+        self.async_optimizer = self.device.type == "cuda" and _os.environ.get("VLB200_ASYNC_OPTIMIZER", "1") != "0"
+        self._opt_pending = False
+        if self.device.type == "cuda":
+            self.opt_stream = torch.cuda.Stream(device=self.device)
+            self.opt_done = torch.cuda.Event()
+            self.norm_done = torch.cuda.Event()
         self._anyres = None  # host.AnyresPlan of the batch in flight (LLaVA-Next only)
         self._bufs: Dict[str, torch.Tensor] = {}
         self._build_rope_tables()
@@ -207,12 +217,22 @@ class LlavaDPOEngine:
         self.rope_cos = freqs.cos().contiguous().to(self.device)
         self.rope_sin = freqs.sin().contiguous().to(self.device)
 
+    def wait_optimizer(self):
+        """Order the current stream after the deferred optimizer step (no host block).  Called before anything that
+        reads the policy weights or writes the gradient buffer; call it yourself before touching `params`,
+        `master`, `grads` … directly."""
+        if self._opt_pending:
+            torch.cuda.current_stream(self.device).wait_event(self.opt_done)
+            self._opt_pending = False
+
     def hf_state(self, which: str = "policy") -> Dict[str, torch.Tensor]:
+        self.wait_optimizer()
         w = {"policy": self.policy, "ref": self.ref, "grad": self.g}[which]
         return hf_views(self.cfg, w.t, self.vis.t if which != "grad" else None)
 
     def init_synthetic(self, seed: int, ref_alpha: float = 0.05):
         """Seeded random-init weights of the architecture (bit-identical to oracle.restate.make_policy_and_ref)."""
+        self.wait_optimizer()
         cfg = self.cfg
         pol, ref = self.hf_state("policy"), self.hf_state("ref")
         tmp_cache: Dict[int, torch.Tensor] = {}
@@ -244,7 +264,7 @@ class LlavaDPOEngine:
             torch.cuda.synchronize()
 
     def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], which: str = "policy"):
-        dst = self.hf_state(which)
+        dst = self.hf_state(which)  # (waits for a deferred optimizer step)
         for k, v in sd.items():
             if k in dst:
                 dst[k].copy_(v.to(device=self.device, dtype=torch.bfloat16).view(dst[k].shape))
@@ -396,6 +416,7 @@ class LlavaDPOEngine:
 
     # ------------------------------------------------------------------ backward of the policy copy
     def _backward(self, grad_logps: torch.Tensor):
+        self.wait_optimizer()  # the gradient buffer is about to be overwritten
         cfg, w, g = self.cfg, self.policy, self.g
         sv = self._saved
         m: ops.MergeIndex = sv["m"]
@@ -523,6 +544,8 @@ class LlavaDPOEngine:
         ops.sumsq(g, self.grad_sumsq, self.sumsq_ws)
         if self.shard_optimizer:  # global gradient norm = sum of the slices' squared norms (one fp32 scalar)
             torch.distributed.all_reduce(self.grad_sumsq, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        if self.device.type == "cuda":
+            self.norm_done.record()  # the logged grad_norm is final here; AdamW only reads it
         ops.adamw_(p, g, self.master, self.exp_avg, self.exp_avg_sq, tc.learning_rate, tc.adam_beta1,
                    tc.adam_beta2, tc.adam_eps, tc.weight_decay, self.opt_step, grad_scale=1.0 / self.world_size(),
                    grad_sumsq=self.grad_sumsq, max_grad_norm=tc.max_grad_norm)
@@ -590,6 +613,8 @@ class LlavaDPOEngine:
                                           cfg.pad_token_id, cfg.ignore_index)
         if feats is None:
             feats = self.vision_features(px)
+        if which == "policy":
+            self.wait_optimizer()
         w = self.policy if which == "policy" else self.ref
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
@@ -600,13 +625,16 @@ class LlavaDPOEngine:
         pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
         the collator's `_logps` keys, base/collator.py:62-64)."""
         tc = self.tc
-        pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train)
         if ref_logps is not None:
+            pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train)
             ref = ref_logps.to(self.device, torch.float32).reshape(-1).contiguous()
             if ref.numel() != pol.numel():
                 raise ValueError(f"ref_logps holds {ref.numel()} values, the batch has {pol.numel()} sequences")
         else:
-            ref, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, feats=feats, m=m)
+            # reference pass first: it reads none of the policy weights, so the previous step's deferred optimizer
+            # (side stream) overlaps it; the policy pass below waits for `opt_done`
+            ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False)
+            pol, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    1.0, want_grad=train)
         out = StepOutput()
@@ -616,10 +644,20 @@ class LlavaDPOEngine:
         out.grad_norm = None
         if train:
             self._backward(grad)
-            self.allreduce_grads()
-            if self.with_optimizer:
-                self.optimizer_step()
+            if self.async_optimizer and self.with_optimizer:
+                main = torch.cuda.current_stream(self.device)
+                self.opt_stream.wait_stream(main)            # gradients are final
+                with torch.cuda.stream(self.opt_stream):
+                    self.allreduce_grads()
+                    self.optimizer_step()
+                    self.opt_done.record()
+                self._opt_pending = True
                 out.grad_norm = self.grad_sumsq
+            else:
+                self.allreduce_grads()
+                if self.with_optimizer:
+                    self.optimizer_step()
+                    out.grad_norm = self.grad_sumsq
         return out
 
     def train_step(self, batch: Dict, train: bool = True) -> Dict[str, float]:
@@ -640,6 +678,8 @@ class LlavaDPOEngine:
                                    torch.as_tensor(batch["reference_rejected_logps"], dtype=torch.float32).reshape(-1)])
         out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train, ref_logps=ref_logps)
         n = out.policy_logps.numel() // 2
+        if self._opt_pending:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
+            torch.cuda.current_stream(self.device).wait_event(self.norm_done)
         packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
                             (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0),
                             (self.logit_means if train else out.stats[:2] * 0)]).cpu()  # the D2H read

@@ -26,6 +26,7 @@ def run() -> None:
     got = out.policy_logps.cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-3)
     assert abs(float(out.stats[0]) - float(loss)) < 5e-2, (float(out.stats[0]), float(loss))
+    eng.wait_optimizer()
     assert torch.isfinite(eng.master).all()
     print(f"smoke ok: logps {got.round(3).tolist()} loss {float(out.stats[0]):.5f} (oracle {float(loss):.5f}); "
           f"{ops.launch_count() - n0} vlb200 kernel launches")
