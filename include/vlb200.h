@@ -245,6 +245,22 @@ int vlb200_clip_preprocess_u8(const uint8_t* image, int in_h, int in_w, const in
                               int crop_h, int crop_w, int row0, int rows, uint8_t* workspace, size_t workspace_bytes,
                               double rescale, const float* mean_std_host, void* out, int out_dtype, void* stream);
 
+/* ---- DDPO token mask on the HOST (CPU integer work; no GPU, no launch) -------------------------------------------
+ * The mask_shared_tokens branch of VLDPOTrainer.get_batch_logps (base/trainer.py:169-184) over
+ * utils/diff_lib.get_diff_ids (utils/diff_lib.py:116-180), which calls Python difflib.SequenceMatcher
+ * (autojunk on).  All pointers are HOST pointers.
+ * host_matching_blocks: SequenceMatcher(None, a, b).get_matching_blocks() -> triples[3*t] = (i, j, size), the
+ *   (len(a), len(b), 0) sentinel included; returns the block count, or -1 (see vlb200_last_error).
+ * host_ddpo_row_weights: input_ids / attention_mask (NULL = LLaVA-1.5 merge: padded tokens stay in the sequence) /
+ *   labels are the concatenated batch [n_seq, text_len] (chosen rows, then rejected rows); feat_len_per_seq[b] = image
+ *   feature rows merged into sequence b; merged_len >= 0 pads every merged label sequence with ignore labels to that
+ *   length (LLaVA-Next: LlavaNext/__init__.py:96-127), -1 = no padding.  weights[b, j-1] = 1 iff text token j of
+ *   sequence b lies in a span modified on both sides (the tokens DDPO keeps). */
+int vlb200_host_matching_blocks(const int64_t* a, int na, const int64_t* b, int nb, int* triples, int max_blocks);
+int vlb200_host_ddpo_row_weights(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels, int n_seq,
+                                 int text_len, int image_token, const int* feat_len_per_seq, int merged_len,
+                                 int64_t label_pad_token_id, int min_match_size, uint8_t* weights);
+
 #ifdef __cplusplus
 }
 #endif

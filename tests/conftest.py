@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """The host logic calls native host routines of libvlb200 (DDPO diff): make sure the in-tree library exists
+    (nvcc cross-compiles here; on the GPU box the prebuilt .so travelled with the snapshot)."""
+    if not os.path.exists(os.path.join(ROOT, "vl-rlhf_b200", "libvlb200.so")):
+        import __graft_entry__ as g
+        g.build()
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

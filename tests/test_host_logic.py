@@ -79,6 +79,54 @@ def test_get_diff_ids_golden(cpu_pkg):
         assert ia == d[c + "_ia"].tolist() and ib == d[c + "_ib"].tolist(), c
 
 
+def test_native_matching_blocks_equal_difflib(cpu_pkg):
+    """vlb200_host_matching_blocks (C++ restatement of difflib.SequenceMatcher incl. autojunk) == CPython difflib,
+    bit-exact, on random edits, popular elements (image/prompt zeros) and the n >= 200 autojunk threshold."""
+    import difflib
+    import random
+    config, engine, host, ops = cpu_pkg
+    rnd = random.Random(0)
+    for trial in range(200):
+        n = rnd.choice([0, 1, 5, 30, 199, 200, 201, 400, 1600])
+        vocab = rnd.choice([2, 5, 50, 1000])
+        a = [rnd.randint(0, vocab) for _ in range(n)]
+        b = list(a)
+        for _ in range(rnd.randint(0, 10)):
+            if b:
+                s0 = rnd.randrange(len(b))
+                b[s0:s0 + rnd.randint(1, 8)] = [rnd.randint(0, vocab) for _ in range(rnd.randint(0, 8))]
+        if rnd.random() < 0.3:
+            b = [rnd.randint(0, vocab) for _ in range(max(0, n + rnd.randint(-20, 20)))]
+        if rnd.random() < 0.5:
+            a, b = [0] * rnd.randint(0, 300) + a, [0] * rnd.randint(0, 300) + b
+        want = [tuple(x) for x in difflib.SequenceMatcher(None, a, b).get_matching_blocks()]
+        assert host.matching_blocks_native(a, b) == want, (trial, len(a), len(b))
+    d = np.load(os.path.join(G, "g3_ddpo.npz"))  # the reference's get_diff_ids cases, through the native matcher
+    for c in sorted({k[:-2] for k in d.files if k.endswith("_a")}):
+        a, b = d[c + "_a"].tolist(), d[c + "_b"].tolist()
+        assert host.matching_blocks_native(a, b) == [tuple(x) for x in difflib.SequenceMatcher(None, a, b).get_matching_blocks()]
+
+
+def test_native_ddpo_row_weights_equal_python_mirror(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    for seed in range(3):
+        cfg = R.SMALL
+        cb = R.concatenated_inputs(R.make_batch(cfg, 3, 120, 10, seed=seed, ddpo_like=True))
+        ids, lb = cb["concatenated_input_ids"], cb["concatenated_labels"]
+        assert torch.equal(host.ddpo_row_weights(ids, lb, cfg.image_token_index, cfg.n_patches),
+                           host.ddpo_row_weights_native(ids, lb, cfg.image_token_index, cfg.n_patches))
+        cfg, sizes = R.SMALL_NEXT, [(112, 112), (90, 300), (200, 100)]
+        cb = R.concatenated_inputs(R.make_batch(cfg, 3, 80, 8, seed=seed, ddpo_like=True, image_sizes=sizes))
+        ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+        plan = host.anyres_pack_index(sizes, cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+        S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
+        w1 = host.ddpo_row_weights(ids, lb, cfg.image_token_index, plan.feature_lens * 2, attention_mask=am, merged_len=S)
+        w2 = host.ddpo_row_weights_native(ids, lb, cfg.image_token_index, plan.feature_lens * 2, attention_mask=am, merged_len=S)
+        assert torch.equal(w1, w2) and int(w1.sum()) > 0
+    with pytest.raises(ValueError):
+        host.ddpo_row_weights_native(ids[:3], lb[:3], cfg.image_token_index, [1, 1, 1])
+
+
 def test_ddpo_row_weights_equal_reference_mask(cpu_pkg):
     config, engine, host, ops = cpu_pkg
     cfg = R.TINY

@@ -74,6 +74,9 @@ SIGNATURES = {
                              c_float, c_float, c_int, c_float, c_void_p, c_float, c_void_p]),
     "vlb200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_uint64, c_float, c_void_p]),
     "vlb200_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "vlb200_host_matching_blocks": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]),
+    "vlb200_host_ddpo_row_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int64,
+                                             c_int, c_void_p]),
     "vlb200_clip_preprocess_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vlb200_clip_preprocess_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_double,

@@ -695,15 +695,15 @@ class LlavaDPOEngine:
         from . import host
         cfg, tc = self.cfg, self.tc
         if cfg.family != "llava_next":
-            return host.ddpo_row_weights(ids, lb, cfg.image_token_index, cfg.n_patches, tc.label_pad_token_id)
+            return host.ddpo_row_weights_native(ids, lb, cfg.image_token_index, cfg.n_patches, tc.label_pad_token_id)
         n_seq = ids.shape[0]
         if image_sizes.shape[0] == n_seq:
             image_sizes = image_sizes[: n_seq // 2]
         plan = host.anyres_pack_index(image_sizes.cpu(), cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
         per_seq = [plan.feature_lens[b % len(plan.feature_lens)] for b in range(n_seq)]
         S = host.next_merged_len(ids, am, plan.feature_lens, cfg.image_token_index)
-        return host.ddpo_row_weights(ids, lb, cfg.image_token_index, per_seq, tc.label_pad_token_id, attention_mask=am,
-                                     merged_len=S)
+        return host.ddpo_row_weights_native(ids, lb, cfg.image_token_index, per_seq, tc.label_pad_token_id,
+                                            attention_mask=am, merged_len=S)
 
     def check_merge_status(self, m: "ops.MergeIndex"):
         """Synchronising validity check mirroring the reference's ValueError (Llava/__init__.py:90-94)."""

@@ -218,3 +218,40 @@ def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_
             if pb[j] in sb:
                 out[n + i, j - 1] = 1
     return out
+
+
+def ddpo_row_weights_native(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches,
+                            label_pad_token_id: int = -100, min_match_size: int = 3,
+                            attention_mask: Optional[torch.Tensor] = None, merged_len: Optional[int] = None) -> torch.Tensor:
+    """`ddpo_row_weights` through the native host routine `vlb200_host_ddpo_row_weights` (a C++ restatement of
+    difflib's matcher, ~50x faster than the pure-Python mirror above; same result bit for bit)."""
+    from . import _lib
+    L_ = _lib.load()
+    ids = input_ids.cpu().contiguous()
+    lab = labels.cpu().contiguous()
+    am = attention_mask.cpu().contiguous() if attention_mask is not None else None
+    assert ids.dtype == torch.int64 and lab.dtype == torch.int64 and (am is None or am.dtype == torch.int64)
+    n2, L = ids.shape
+    per_seq = torch.tensor([int(n_patches)] * n2 if isinstance(n_patches, int) else [int(x) for x in n_patches],
+                           dtype=torch.int32)
+    assert per_seq.numel() == n2
+    out = torch.zeros(n2, L - 1, dtype=torch.uint8)
+    _lib.check(L_.vlb200_host_ddpo_row_weights(ids.data_ptr(), am.data_ptr() if am is not None else None, lab.data_ptr(), n2,
+                                               L, image_token_index, per_seq.data_ptr(),
+                                               -1 if merged_len is None else int(merged_len), label_pad_token_id,
+                                               min_match_size, out.data_ptr()))
+    return out
+
+
+def matching_blocks_native(a_seq: List[int], b_seq: List[int]) -> List[Tuple[int, int, int]]:
+    """difflib.SequenceMatcher(None, a, b).get_matching_blocks() through `vlb200_host_matching_blocks`."""
+    from . import _lib
+    L_ = _lib.load()
+    a = torch.tensor(a_seq, dtype=torch.int64)
+    b = torch.tensor(b_seq, dtype=torch.int64)
+    cap = min(len(a_seq), len(b_seq)) + 2
+    out = torch.zeros(cap, 3, dtype=torch.int32)
+    n = L_.vlb200_host_matching_blocks(a.data_ptr(), len(a_seq), b.data_ptr(), len(b_seq), out.data_ptr(), cap)
+    if n < 0:
+        raise RuntimeError(L_.vlb200_last_error().decode())
+    return [tuple(r) for r in out[:n].tolist()]
