@@ -316,3 +316,26 @@ def test_config4_next7b_shapes_ddpo_parity(pkg):
     np.testing.assert_allclose(out.losses.cpu().numpy(), d["ddpo_losses"], atol=slack)
     del eng
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name", ["SMALL", "SMALL_NEXT"])
+def test_hf_checkpoint_roundtrip_on_gpu(pkg, tmp_path, name):
+    """save_pretrained -> from_pretrained through the plugin model: same parameters, same log-probs (f-4)."""
+    config, engine, host, ops = pkg
+    from vlrlhf_b200 import checkpoint, plugin
+    cfg = getattr(config, name)
+    rcfg = getattr(R, name)
+    a = plugin.B200LlavaForRL(cfg, config.TrainConfig(), with_optimizer=False)
+    a.engine.init_synthetic(3)
+    a.hf_config_dict = checkpoint.hf_config_dict(cfg)
+    assert checkpoint.config_from_hf(a.hf_config_dict) == cfg
+    a.save_pretrained(str(tmp_path), max_shard_size=4 << 20)
+    b = plugin.B200LlavaForRL.from_pretrained(str(tmp_path), torch_dtype=torch.bfloat16, with_optimizer=False)
+    assert b.cfg == cfg
+    assert torch.equal(a.engine.params, b.engine.params) and torch.equal(a.engine.vparams, b.engine.vparams)
+    assert torch.equal(b.engine.ref_params, b.engine.params[: b.engine.ref_params.numel()])  # reference copy = initial policy
+    sizes = [(112, 112), (90, 300)] if cfg.family == "llava_next" else None
+    batch = R.make_batch(rcfg, 2, 48, 12, seed=5, image_sizes=sizes)
+    cb = host.concatenated_inputs(batch)
+    outs = [m.engine.step(*stage(m.engine, host, cb, rcfg), train=False).policy_logps for m in (a, b)]
+    assert torch.equal(outs[0], outs[1])

@@ -538,3 +538,65 @@ def test_collator_matches_reference_collator(tmp_path):
     assert np.array_equal(load_rgb(feats[1]["img_path"]), IR.synthetic_image(70, 83, 1))
     with pytest.raises(ValueError):
         B200DPODataCollatorWithPadding(is_encoder_decoder=True)
+
+
+# ------------------------------------------------------------------------------------------
+# HF checkpoint interchange (f-4): from_pretrained / save_pretrained of the plugin model
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", ["llava", "llava_next"])
+def test_hf_checkpoint_roundtrip(cpu_pkg, cpu_plugin, tmp_path, family):
+    transformers = pytest.importorskip("transformers")
+    pytest.importorskip("safetensors")
+    from oracle import make_fixtures as MF
+    config, engine, host, ops = cpu_pkg
+    rcfg = R.TINY if family == "llava" else R.TINY_NEXT
+    if family == "llava":
+        hf = transformers.LlavaForConditionalGeneration(MF.hf_config(rcfg))
+    else:
+        hf = transformers.LlavaNextForConditionalGeneration(MF.hf_config_next(rcfg))
+    hf = hf.to(torch.bfloat16)
+    src = str(tmp_path / "src")
+    hf.save_pretrained(src, safe_serialization=True)
+    model = cpu_plugin.B200LlavaForRL.from_pretrained(src, torch_dtype=torch.bfloat16, device="cpu", with_optimizer=True)
+    want_cfg = getattr(config, "TINY" if family == "llava" else "TINY_NEXT")
+    for f in ("hidden", "layers", "heads", "kv_heads", "ff", "vocab", "v_hidden", "v_layers", "image_size", "patch_size",
+              "image_token_index", "family", "image_grid_pinpoints", "rope_theta", "rms_eps", "vision_feature_layer"):
+        assert getattr(model.cfg, f) == getattr(want_cfg, f), f
+    from vlrlhf_b200 import checkpoint
+    sd = {checkpoint.legacy_name(k): v for k, v in hf.state_dict().items()}
+    pol, ref = model.engine.hf_state("policy"), model.engine.hf_state("ref")
+    assert len(pol) > 30
+    for k, t in pol.items():
+        assert torch.equal(t.reshape(sd[k].shape), sd[k]), k
+        if not k.startswith("vision_tower."):
+            assert torch.equal(ref[k].reshape(sd[k].shape), sd[k]), k
+    assert torch.equal(model.engine.master, model.engine.params.float())
+    unused = set(sd) - set(pol)
+    assert unused and all(("encoder.layers" in k) or ("post_layernorm" in k) for k in unused)
+    # one optimizer step, then export: the saved policy is complete and carries the update
+    eng = model.engine
+    eng.tc.learning_rate = 1e-3
+    sizes = [(28, 28), (20, 50)] if family == "llava_next" else None
+    eng.train_step(R.make_batch(rcfg, 2, 24, 8, 0, image_sizes=sizes), train=True)
+    out = str(tmp_path / "out")
+    files = model.save_pretrained(out, max_shard_size=200_000)  # force several shards + an index
+    assert len(files) > 1 and os.path.exists(os.path.join(out, "model.safetensors.index.json"))
+    saved = dict(checkpoint.iter_checkpoint(out))
+    assert set(saved) == set(sd)  # 4.41 names, nothing missing
+    changed = 0
+    for k, t in saved.items():
+        assert t.dtype == torch.bfloat16 and tuple(t.shape) == tuple(sd[k].shape), k
+        if k in pol and not k.startswith("vision_tower."):
+            assert torch.equal(t, eng.hf_state("policy")[k].reshape(t.shape))
+            changed += int(not torch.equal(t, sd[k]))
+        else:
+            assert torch.equal(t, sd[k]), k  # frozen tower + unused tensors written back unchanged
+    assert changed > 10
+    # the reference's loader (HF from_pretrained) accepts the directory
+    cls = transformers.LlavaForConditionalGeneration if family == "llava" else transformers.LlavaNextForConditionalGeneration
+    back, info = cls.from_pretrained(out, torch_dtype=torch.bfloat16, output_loading_info=True)
+    assert not info["missing_keys"] and not info["unexpected_keys"], info
+    k = "language_model.model.layers.1.mlp.down_proj.weight"
+    assert torch.equal({checkpoint.legacy_name(n): v for n, v in back.state_dict().items()}[k], saved[k])
+    with pytest.raises(ValueError):
+        checkpoint.config_from_hf({"model_type": "qwen"})

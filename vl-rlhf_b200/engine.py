@@ -263,6 +263,12 @@ class LlavaDPOEngine:
         if self.device.type == "cuda":
             torch.cuda.synchronize()
 
+    def sync_master_from_params(self):
+        """fp32 master copy of this rank's optimizer slice <- the bf16 policy parameters (after loading weights)."""
+        self.wait_optimizer()
+        if self.with_optimizer:
+            ops.cast_bf16_to_f32(self.params[self.shard_lo:self.shard_hi], self.master)
+
     def load_hf_state_dict(self, sd: Dict[str, torch.Tensor], which: str = "policy"):
         dst = self.hf_state(which)  # (waits for a deferred optimizer step)
         for k, v in sd.items():

@@ -137,6 +137,37 @@ class B200LlavaForRL(nn.Module):
     def hf_named_parameters(self):
         return self._hf.items()
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, *args, config=None, torch_dtype=None,
+                        train: Optional[TrainConfig] = None, device: str = "cuda", with_optimizer: bool = True, **kwargs):
+        """`MyAutoModel.from_pretrained(path, config=config, torch_dtype=…)` of utils/auto_load.py:522-535: a local HF
+        checkpoint directory (config.json + safetensors) streamed into the flat arenas; the reference copy starts equal
+        to the policy (TRL deep-copies the model when no ref_model is given).  HF-only kwargs (device_map,
+        quantization_config, use_flash_attention_2, …) are accepted and ignored; bf16 is the only compute dtype."""
+        import json
+        import os
+        from . import checkpoint
+        if torch_dtype not in (None, torch.bfloat16, "bfloat16", "auto"):
+            raise ValueError(f"torch_dtype {torch_dtype}: the B200 path computes in bf16 only")
+        path = pretrained_model_name_or_path
+        if not os.path.isdir(path):
+            raise FileNotFoundError(f"{path}: a local checkpoint directory is required (there is no hub access)")
+        with open(os.path.join(path, "config.json")) as f:
+            cfg_dict = json.load(f)
+        model = cls(checkpoint.config_from_hf(config if config is not None else cfg_dict), train, device=device,
+                    with_optimizer=with_optimizer)
+        model.hf_config_dict = cfg_dict
+        model.config = config
+        checkpoint.load_hf_checkpoint(model.engine, path)
+        return model
+
+    def save_pretrained(self, save_directory: str, max_shard_size: int = 5 << 30, **kwargs):
+        """HF-layout export of the trained policy (safetensors shards + index + config.json, transformers-4.41 names)
+        so the reference's eval harness / merge scripts reload it (dpo.py:89-95,147-149; utils/common.py:21-55)."""
+        from . import checkpoint
+        return checkpoint.save_hf_checkpoint(self.engine, save_directory, getattr(self, "hf_config_dict", None),
+                                             max_shard_bytes=int(max_shard_size))
+
     @property
     def default_lora_target(self) -> List[str]:  # Llava/__init__.py:273-286, LlavaNext/__init__.py:347-360
         return ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
