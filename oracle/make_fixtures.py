@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--next", action="store_true", help="only the LLaVA-Next fixtures (g6_*)")
     ap.add_argument("--config4", action="store_true", help="LLaVA-Next-Mistral-7B shapes, DDPO (BASELINE.json configs[3])")
     ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
+    ap.add_argument("--qwen", action="store_true", help="only the Qwen-VL + LoRA fixtures (g9_*)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -298,6 +299,9 @@ def main():
         return
     if args.preprocess:
         g7_clip_preprocess()
+        return
+    if args.qwen:
+        g9_qwen()
         return
     g1_logps()
     g2_loss()
@@ -334,6 +338,97 @@ def g7_clip_preprocess():
             out[f"resized_u8_{i}"] = np.array(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
     np.savez_compressed(os.path.join(GOLDEN, "g7_clip_preprocess.npz"), **out)
     print("g7_clip_preprocess", {k: v.shape for k, v in out.items() if k.startswith("pixel")})
+
+
+class _LoraLinear(torch.nn.Module):
+    """peft.tuners.lora.Linear.forward restated (peft is not installed): result = base(x) + lora_B(lora_A(x)) * scaling
+    (dropout is disabled by DPOTrainer's disable_dropout=True)."""
+
+    def __init__(self, base: torch.nn.Linear, A: torch.Tensor, B: torch.Tensor, scaling: float):
+        super().__init__()
+        self.base, self.scaling = base, scaling
+        self.A, self.B = torch.nn.Parameter(A.clone()), torch.nn.Parameter(B.clone())
+
+    def forward(self, x):
+        return self.base(x) + torch.nn.functional.linear(torch.nn.functional.linear(x, self.A), self.B) * self.scaling
+
+
+def build_reference_qwen(qcfg, base_w):
+    """The reference's vendored QWenLMHeadModel (models/QwenVL/modeling_qwen.py) on a small config, fp32."""
+    ref_shim.install()
+    from vlrlhf.models.QwenVL.configuration_qwen import QWenConfig
+    from vlrlhf.models.QwenVL import QwenVLForRL
+    hc = QWenConfig(vocab_size=qcfg.vocab, hidden_size=qcfg.hidden, num_hidden_layers=qcfg.layers,
+                    num_attention_heads=qcfg.heads, kv_channels=qcfg.head_dim, intermediate_size=2 * qcfg.ff,
+                    seq_length=2048, max_position_embeddings=2048, bf16=False, fp16=False, fp32=True, use_flash_attn=False,
+                    use_dynamic_ntk=True, use_logn_attn=True, rotary_emb_base=qcfg.rope_theta,
+                    layer_norm_epsilon=qcfg.rms_eps, no_bias=True,
+                    visual=dict(heads=qcfg.v_heads, image_size=qcfg.image_size, image_start_id=qcfg.image_start_id,
+                                layers=qcfg.v_layers, mlp_ratio=qcfg.v_mlp / qcfg.v_width, output_dim=qcfg.hidden,
+                                patch_size=qcfg.patch_size, width=qcfg.v_width, n_queries=qcfg.n_queries))
+    m = QwenVLForRL(hc)
+    sd = m.state_dict()
+    assert set(sd) == set(base_w), (sorted(set(sd) ^ set(base_w))[:8])
+    with torch.no_grad():
+        for k, v in base_w.items():
+            assert sd[k].shape == v.shape, k
+            sd[k].copy_(v)
+        # Resampler.pos_embed is a non-trainable sincos table built in __init__ (visual.py:112-114); keep it
+    # transformers 5.x dropped ModuleUtilsMixin.get_head_mask; 4.41 returns [None] * n for head_mask=None
+    m.transformer.get_head_mask = lambda head_mask, n, *a, **k: [None] * n
+    m.eval()
+    return m
+
+
+def g9_qwen():
+    """Qwen-VL + LoRA (BASELINE.json configs[2] at parity size): reference QwenVLForRL.forward with the adapters on
+    (policy) and off (reference), VLDPOTrainer.get_batch_logps / dpo_loss on top."""
+    from oracle import qwen_restate as Q
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    for tag, qcfg, n_pairs, text_len, prompt_len in (("g9_qwen_tiny", Q.TINY_QWEN, 2, 48, 24),
+                                                     ("g9_qwen_small", Q.SMALL_QWEN, 2, 128, 72)):
+        seed = 0
+        base_w, lora_w = Q.make_weights(qcfg, seed)
+        m = build_reference_qwen(qcfg, {k: v for k, v in base_w.items()} | {
+            "transformer.visual.attn_pool.pos_embed": Q.sincos_2d(qcfg.hidden, int(qcfg.n_queries ** 0.5))})
+        batch = Q.make_batch(qcfg, n_pairs, text_len, prompt_len, seed, ddpo_like=True)
+        cb = R.concatenated_inputs(batch, -100, 0)
+        pixels = cb["concatenated_img_input_dict"]["pixel_values"]
+        m.transformer.visual.encode = lambda paths, _m=m, _p=pixels: _m.transformer.visual(_p)  # no disk reads here
+        out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
+        res = {}
+        for who in ("ref", "policy"):
+            if who == "policy":  # adapters on
+                for i, blk in enumerate(m.transformer.h):
+                    for t in Q.LORA_TARGETS:
+                        parent = blk.attn if t.startswith("attn.") else blk.mlp
+                        name = t.split(".")[1]
+                        setattr(parent, name, _LoraLinear(getattr(parent, name), lora_w[f"transformer.h.{i}.{t}.lora_A"],
+                                                          lora_w[f"transformer.h.{i}.{t}.lora_B"], qcfg.lora_scale))
+            with torch.no_grad():
+                o = m(input_ids=cb["concatenated_input_ids"], attention_mask=cb["concatenated_attention_mask"],
+                      use_cache=False, return_dict=True)
+            logits = o.logits.float()
+            for lt in ("sigmoid", "ddpo"):
+                lp = VLDPOTrainer.get_batch_logps(logits, cb["concatenated_labels"], average_log_prob=False,
+                                                  is_encoder_decoder=False, label_pad_token_id=-100,
+                                                  mask_shared_tokens=(lt == "ddpo"))
+                res[who + ("_ddpo" if lt == "ddpo" else "")] = lp
+                out[f"{who}_logps" + ("_ddpo" if lt == "ddpo" else "")] = lp.numpy()
+            if who == "policy":
+                out["image_position_map"] = o.image_position_map.numpy()
+                out["policy_logits_mean_chosen"] = logits[:n_pairs].mean().numpy()
+                out["policy_logits_mean_rejected"] = logits[n_pairs:].mean().numpy()
+                if logits.numel() < 2_000_000:
+                    out["policy_logits"] = logits.numpy()
+        n = n_pairs
+        for lt in ("sigmoid", "ipo", "hinge", "kto_pair", "ddpo"):
+            sfx = "_ddpo" if lt == "ddpo" else ""
+            pl, rl = res["policy" + sfx], res["ref" + sfx]
+            l, c, r = ref_dpo_loss(pl[:n], pl[n:], rl[:n], rl[n:], 0.1, 0.0, lt)
+            out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
+        np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
+        print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "sigmoid_losses"}, flush=True)
 
 
 def g6_next():
