@@ -192,6 +192,16 @@ int vlb200_llavanext_merge_index(const int64_t* input_ids, const int64_t* attent
 int vlb200_llavanext_merge_bwd(const int* src_map, const int* img_rows, const void* dx, float* dembed_f32,
                                void* dimage_features, int n_rows, int total_feats, int reps, int d, void* stream);
 
+/* ---- Qwen-VL image placement -- models/QwenVL/modeling_qwen.py:524-528 (span scan) and :614-621 (overwrite)
+ * The text already holds n_queries placeholder tokens between <img> (image_start_id) and </img> (image_start_id+1);
+ * those positions read image feature rows (src_map = -1 - (image*n_queries + q)), every other position its own
+ * embedding row.  merged length == text_len, labels pass through (the model returns none, base/trainer.py:225-229),
+ * position ids = arange (:573-580).  status: 0 ok, 2 malformed / wrong number of <img> spans, 3 not right-padded. */
+int vlb200_qwen_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels, int n_seq,
+                            int text_len, int n_queries, int n_img_batch, int imgs_per_seq, int image_start_id,
+                            int ignore_index, int* src_map, int64_t* labels_out, int* mask_out, int* position_ids,
+                            int* seqlens, int* row_of_text, int64_t* target, int* status, void* stream);
+
 /* ---- attention (K4, K12) -- CLIPAttention (modeling_clip.py:261-334), LlamaAttention
  * (modeling_llama.py:199-290).  q/k/v/out rows are tokens (row = b*S + t), head h at column h*head_dim.
  * causal + key-padding via seqlens[B] (attended prefix length; NULL = S).  lse/delta: [B,H,S] f32.

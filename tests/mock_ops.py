@@ -449,6 +449,51 @@ def llavanext_merge_bwd(m, dx, dembed_f32, dimage_features):
     dimage_features.copy_(acc.to(dimage_features.dtype))
     _c(2)
 
+
+def qwen_merge_index(input_ids, attention_mask, labels, n_queries, n_img_batch, imgs_per_seq, image_start_id, ignore_index=-100):
+    n_seq, L = input_ids.shape
+    Q = n_queries
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, L, Q, n_img_batch, imgs_per_seq
+    m.total_feats, m.reps = n_img_batch * imgs_per_seq * Q, n_seq // n_img_batch
+    m.src_map = input_ids.to(torch.int32).reshape(-1).clone()
+    m.labels = labels.clone()
+    m.mask = attention_mask.to(torch.int32).clone()
+    m.pos = torch.arange(L, dtype=torch.int32).repeat(n_seq)
+    m.seqlens = torch.zeros(n_seq, dtype=torch.int32)
+    m.img_pos = None
+    m.row_of_text = (torch.arange(n_seq)[:, None] * L + torch.arange(L - 1)[None]).to(torch.int32).reshape(-1)
+    tgt = labels[:, 1:].clone()
+    tgt[tgt == ignore_index] = -100
+    m.target = tgt.reshape(-1).contiguous()
+    m.status = torch.zeros(1, dtype=torch.int32)
+    for b in range(n_seq):
+        slot, open_, prefix = 0, -1, True
+        base = (b % n_img_batch) * imgs_per_seq
+        for j in range(L):
+            t = int(input_ids[b, j])
+            if int(attention_mask[b, j]):
+                if not prefix:
+                    m.status[0] = 3
+                m.seqlens[b] = j + 1
+            else:
+                prefix = False
+            if t == image_start_id:
+                if open_ >= 0:
+                    m.status[0] = 2
+                open_ = j
+            elif t == image_start_id + 1:
+                if open_ < 0 or j - open_ - 1 != Q or slot >= imgs_per_seq:
+                    m.status[0] = 2
+                else:
+                    m.src_map[b * L + open_ + 1:b * L + j] = -1 - ((base + slot) * Q + torch.arange(Q, dtype=torch.int32))
+                open_ = -1
+                slot += 1
+        if open_ >= 0 or slot != imgs_per_seq:
+            m.status[0] = 2
+    _c()
+    return m
+
 def _attn_ref(q, k, v, seqlens, B, S, H, KVH, dh, causal, scale):
     qf = q.float().reshape(B, S, H, dh)
     kf = k.float().reshape(B, S, KVH, dh).repeat_interleave(H // KVH, 2)

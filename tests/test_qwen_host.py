@@ -1,0 +1,173 @@
+"""Qwen-VL + LoRA variant (BASELINE.json configs[2]) -- CPU tests.
+
+* oracle/qwen_restate.py against the fixtures minted from the reference's vendored QWenLMHeadModel + VisionTransformer
+  (tests/golden/g9_qwen_*.npz: policy = base + adapters, reference = adapters off);
+* the engine's orchestration (vl-rlhf_b200/engine_qwen.py over tests/mock_ops.py) against the fixtures and the oracle's
+  autograd: log-probs, DDPO, adapter gradients, activation checkpointing, optimizer, metrics.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qwen_restate as Q
+from oracle import restate as R
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {"g9_qwen_tiny": ("TINY_QWEN", Q.TINY_QWEN), "g9_qwen_small": ("SMALL_QWEN", Q.SMALL_QWEN)}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_qwen_oracle_matches_reference_fixture(tag):
+    qcfg = CASES[tag][1]
+    d = np.load(os.path.join(G, tag + ".npz"))
+    w, lora = Q.make_weights(qcfg, int(d["seed"]))
+    batch = Q.make_batch(qcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+    with torch.no_grad():
+        pc, pr, pcl, prl, imap = Q.concatenated_forward(qcfg, w, lora, batch)
+        rc, rr, _, _, _ = Q.concatenated_forward(qcfg, w, None, batch)
+    assert np.array_equal(imap.numpy(), d["image_position_map"])
+    np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), d["policy_logps"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(torch.cat([rc, rr]).numpy(), d["ref_logps"], rtol=1e-5, atol=1e-3)
+    if "policy_logits" in d.files:
+        np.testing.assert_allclose(torch.cat([pcl, prl]).numpy(), d["policy_logits"], rtol=2e-4, atol=2e-4)
+    assert np.abs(d["policy_logps"] - d["ref_logps"]).max() > 0.05  # the adapters carry signal
+    with torch.no_grad():
+        for lt in ("sigmoid", "ddpo", "kto_pair", "ipo", "hinge"):
+            _, _, aux = Q.get_batch_loss_metrics(qcfg, w, lora, batch, loss_type=lt)
+            np.testing.assert_allclose(aux["losses"].numpy(), d[f"{lt}_losses"], rtol=1e-3, atol=1e-4)
+            if lt == "ddpo":
+                pol = torch.cat([aux["policy_chosen_logps"], aux["policy_rejected_logps"]]).numpy()
+                np.testing.assert_allclose(pol, d["policy_logps_ddpo"], rtol=1e-5, atol=1e-3)
+
+
+@pytest.fixture(scope="module")
+def qpkg():
+    import vlrlhf_b200  # noqa: F401
+    from tests import mock_ops
+    names = ("vlrlhf_b200.ops", "vlrlhf_b200.engine", "vlrlhf_b200.engine_qwen")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules["vlrlhf_b200.ops"] = mock_ops
+    sys.modules.pop("vlrlhf_b200.engine", None)
+    sys.modules.pop("vlrlhf_b200.engine_qwen", None)
+    importlib.import_module("vlrlhf_b200.engine")
+    engine_qwen = importlib.import_module("vlrlhf_b200.engine_qwen")
+    from vlrlhf_b200 import config, host
+    yield config, engine_qwen, host, mock_ops
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+def _setup(qpkg, tag, loss_type="sigmoid", with_optimizer=False, **tc):
+    config, EQ, host, ops = qpkg
+    name, qcfg = CASES[tag]
+    d = np.load(os.path.join(G, tag + ".npz"))
+    eng = EQ.QwenVLDPOEngine(getattr(config, name), config.TrainConfig(loss_type=loss_type, learning_rate=1e-3, **tc),
+                             device="cpu", with_optimizer=with_optimizer)
+    eng.init_synthetic(int(d["seed"]))
+    batch = Q.make_batch(qcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+    return eng, qcfg, d, batch
+
+
+def test_qwen_config_and_weights_mirror_oracle(qpkg):
+    config, EQ, host, ops = qpkg
+    eng, qcfg, d, batch = _setup(qpkg, "g9_qwen_tiny")
+    w, lora = Q.make_weights(qcfg, 0)
+    st = eng.hf_state("policy")
+    for k, v in lora.items():
+        assert torch.equal(st[k].float(), v), k
+    for k, v in w.items():
+        if not k.startswith("transformer.visual."):
+            assert torch.equal(st[k].float().reshape(v.shape), v), k
+    assert set(eng.hf_state("ref")) == {k for k in w if not k.startswith("transformer.visual.")}
+    assert set(eng.hf_state("grad")) == set(lora)
+    # position tables: the host transforms equal the oracle's
+    assert torch.equal(host.sincos_2d(qcfg.hidden, 4), Q.sincos_2d(qcfg.hidden, 4))
+    t = torch.randn(256, 8)
+    assert torch.equal(host.interpolate_pos_table(t, 64), Q.get_abs_pos(t, 64))
+
+
+def test_qwen_merge_index_matches_reference_placement(qpkg):
+    config, EQ, host, ops = qpkg
+    qcfg = Q.TINY_QWEN
+    batch = Q.make_batch(qcfg, 3, 60, 24, seed=3)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    m = ops.qwen_merge_index(ids, am, lb, qcfg.n_queries, 3, 1, qcfg.image_start_id)
+    assert int(m.status) == 0 and m.S == 60
+    src = m.src_map.view(6, 60).long()
+    spans = Q.image_spans(qcfg, ids).tolist()
+    for (i, a, b) in spans:
+        assert b - a - 1 == qcfg.n_queries
+        assert torch.equal(src[i, a + 1:b], -1 - ((i % 3) * qcfg.n_queries + torch.arange(qcfg.n_queries)))
+        other = torch.ones(60, dtype=torch.bool); other[a + 1:b] = False
+        assert torch.equal(src[i][other], ids[i][other])
+    assert torch.equal(m.seqlens.long(), am.sum(-1)) and torch.equal(m.pos.view(6, 60)[0].long(), torch.arange(60))
+    assert torch.equal(m.target.view(6, 59), torch.where(lb[:, 1:] == -100, torch.full_like(lb[:, 1:], -100), lb[:, 1:]))
+    bad = ids.clone(); bad[0, 5] = qcfg.pad_token_id  # one placeholder missing inside the span -> malformed? no: still Q tokens
+    bad[0, 2 + qcfg.n_queries] = 7                      # the </img> marker is gone
+    assert int(ops.qwen_merge_index(bad, am, lb, qcfg.n_queries, 3, 1, qcfg.image_start_id).status) == 2
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_qwen_engine_forward_parity_cpu_mock(qpkg, tag):
+    config, EQ, host, ops = qpkg
+    eng, qcfg, d, batch = _setup(qpkg, tag)
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    a = eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"])
+    # the resampler output against the oracle's visual tower
+    w, lora = Q.make_weights(qcfg, int(d["seed"]))
+    with torch.no_grad():
+        want = Q.visual_forward(qcfg, w, batch["img_input_dict"]["pixel_values"])
+    got = eng.vision_features(a[3]).float().view(want.shape)
+    assert (got - want).abs().max() <= 3e-2 * want.abs().max()
+    out = eng.step(*a, train=False)
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps"], rtol=1e-3)
+    np.testing.assert_allclose(out.ref_logps.numpy(), d["ref_logps"], rtol=1e-3)
+    wt = eng.ddpo_weights(ids, am, lb)
+    assert int(wt.sum()) > 0
+    out = eng.step(*eng.prepare_inputs(ids, am, lb, cb["concatenated_img_input_dict"]["pixel_values"], wt), train=False)
+    np.testing.assert_allclose(out.policy_logps.numpy(), d["policy_logps_ddpo"], rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(out.ref_logps.numpy(), d["ref_logps_ddpo"], rtol=1e-3, atol=1e-2)
+
+
+def test_qwen_engine_adapter_gradients_match_oracle_autograd(qpkg):
+    config, EQ, host, ops = qpkg
+    grads = {}
+    for ckpt in (False, True):
+        eng, qcfg, d, batch = _setup(qpkg, "g9_qwen_tiny", activation_checkpointing=ckpt)
+        metrics = eng.train_step(batch, train=True)
+        grads[ckpt] = eng.grads.clone()
+    assert torch.equal(grads[False], grads[True])  # recompute == keep
+    got = {k: v.float() for k, v in eng.hf_state("grad").items()}
+    w, lora = Q.make_weights(qcfg, int(d["seed"]))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in lora.items()}
+    loss, want_metrics, _ = Q.get_batch_loss_metrics(qcfg, w, leaves, batch)
+    loss.backward()
+    for k, leaf in leaves.items():
+        rel = (got[k] - leaf.grad).norm().item() / max(leaf.grad.norm().item(), 1e-12)
+        assert rel < 5e-2, f"{k}: rel {rel}"
+    assert abs(metrics["loss"] - float(loss.detach())) < 2e-3
+    for k in ("rewards/chosen", "rewards/rejected", "logps/chosen", "logps/rejected", "logits/chosen", "logits/rejected"):
+        assert abs(metrics[k] - float(want_metrics[k])) <= 2e-3 * max(1.0, abs(float(want_metrics[k]))), k
+
+
+def test_qwen_engine_optimizer_updates_only_adapters(qpkg):
+    config, EQ, host, ops = qpkg
+    eng, qcfg, d, batch = _setup(qpkg, "g9_qwen_tiny", with_optimizer=True, weight_decay=0.05)
+    base0 = eng.bparams.clone()
+    vis0 = eng.vparams.clone()
+    l0 = eng.train_step(batch, train=True)["loss"]
+    for _ in range(4):
+        l1 = eng.train_step(batch, train=True)["loss"]
+    assert l1 < l0
+    assert torch.equal(eng.bparams, base0) and torch.equal(eng.vparams, vis0)
+    assert torch.equal(eng.params, eng.master.to(torch.bfloat16))
+    assert eng.master.numel() == eng.layout.size  # optimizer state covers the adapters only

@@ -58,6 +58,9 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlb200_llavanext_merge_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                            c_void_p]),
+    "vlb200_qwen_merge_index": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     "vlb200_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vlb200_attn_fwd_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

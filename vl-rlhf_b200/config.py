@@ -159,3 +159,141 @@ def weight_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], float, fl
     s += [("language_model.model.norm.weight", (cfg.hidden,), 0.1, 1.0),
           ("language_model.lm_head.weight", (cfg.vocab, cfg.hidden), 3.0 * a, 0.0)]
     return s
+
+
+# ------------------------------------------------------------------------------------------------
+# Qwen-VL (BASELINE.json configs[2]): open_clip ViT-bigG/14 + resampler, Qwen-7B decoder, LoRA on the
+# LM (scripts/dpo_qwenvl.sh: r 64, alpha 16, c_attn / attn.c_proj / w1 / w2), vision tower frozen.
+# Parameter names follow the reference's vendored model (models/QwenVL/modeling_qwen.py, visual.py).
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class QwenModelConfig:
+    image_size: int = 448
+    patch_size: int = 14
+    v_width: int = 1664
+    v_layers: int = 48
+    v_heads: int = 16
+    v_mlp: int = 8192
+    n_queries: int = 256
+    v_eps: float = 1e-6
+    pos_table: int = 256
+    hidden: int = 4096
+    layers: int = 32
+    heads: int = 32
+    ff: int = 11008
+    vocab: int = 151936
+    rms_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    image_start_id: int = 151857
+    pad_token_id: int = 151643
+    ignore_index: int = -100
+    lora_r: int = 64
+    lora_alpha: float = 16.0
+    max_positions: int = 4096
+    family: str = "qwen_vl"
+
+    @property
+    def n_patches(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+    @property
+    def kv_heads(self) -> int:
+        return self.heads
+
+    @property
+    def qkv_dim(self) -> int:
+        return 3 * self.hidden
+
+    @property
+    def v_head_dim(self) -> int:
+        return self.v_width // self.v_heads
+
+    @property
+    def v_head_pad(self) -> int:
+        """ViT heads are laid out at the next supported attention head size (104 -> 128): zero-padded q/k/v dims leave
+        q.k and the context unchanged."""
+        return 64 if self.v_head_dim <= 64 else 128
+
+    @property
+    def r_heads(self) -> int:
+        return self.hidden // 128
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_r
+
+    @property
+    def patch_k(self) -> int:
+        return 3 * self.patch_size * self.patch_size
+
+    @property
+    def patch_k_padded(self) -> int:
+        return (self.patch_k + 7) // 8 * 8
+
+    @property
+    def image_token_index(self) -> int:  # the token DDPO's merged-label layout treats as "image start" (no expansion here)
+        return -1
+
+
+QWEN_VL_CHAT = QwenModelConfig()
+TINY_QWEN = QwenModelConfig(image_size=112, patch_size=14, v_width=208, v_layers=2, v_heads=2, v_mlp=416, n_queries=16,
+                            hidden=256, layers=2, heads=2, ff=256, vocab=512, image_start_id=500, pad_token_id=499,
+                            lora_r=16, lora_alpha=8.0)
+SMALL_QWEN = QwenModelConfig(image_size=224, patch_size=14, v_width=416, v_layers=2, v_heads=4, v_mlp=1024, n_queries=64,
+                             hidden=512, layers=2, heads=4, ff=1024, vocab=2048, image_start_id=2000, pad_token_id=1999,
+                             lora_r=16, lora_alpha=8.0)
+QWEN_LORA_TARGETS = ("attn.c_attn", "attn.c_proj", "mlp.w1", "mlp.w2")
+
+
+def qwen_weight_specs(cfg: QwenModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    """(reference state-dict name, shape, uniform half-width, shift) of the frozen base model (synthetic-init recipe)."""
+    a = 0.02 * math.sqrt(3.0)
+    d, w = cfg.hidden, cfg.v_width
+    s: List[Tuple[str, Tuple[int, ...], float, float]] = []
+    v = "transformer.visual."
+    s += [(v + "positional_embedding", (cfg.pos_table, w), a, 0.0), (v + "proj", (d, d), a, 0.0),
+          (v + "conv1.weight", (w, 3, cfg.patch_size, cfg.patch_size), a, 0.0),
+          (v + "ln_pre.weight", (w,), 0.1, 1.0), (v + "ln_pre.bias", (w,), 0.02, 0.0)]
+    for i in range(cfg.v_layers):
+        p = f"{v}transformer.resblocks.{i}."
+        s += [(p + "ln_1.weight", (w,), 0.1, 1.0), (p + "ln_1.bias", (w,), 0.02, 0.0),
+              (p + "ln_2.weight", (w,), 0.1, 1.0), (p + "ln_2.bias", (w,), 0.02, 0.0),
+              (p + "attn.in_proj.weight", (3 * w, w), a, 0.0), (p + "attn.in_proj.bias", (3 * w,), 0.02, 0.0),
+              (p + "attn.out_proj.weight", (w, w), a, 0.0), (p + "attn.out_proj.bias", (w,), 0.02, 0.0),
+              (p + "mlp.c_fc.weight", (cfg.v_mlp, w), a, 0.0), (p + "mlp.c_fc.bias", (cfg.v_mlp,), 0.02, 0.0),
+              (p + "mlp.c_proj.weight", (w, cfg.v_mlp), a, 0.0), (p + "mlp.c_proj.bias", (w,), 0.02, 0.0)]
+    p = v + "attn_pool."
+    s += [(p + "query", (cfg.n_queries, d), a, 0.0), (p + "kv_proj.weight", (d, w), a, 0.0),
+          (p + "attn.in_proj_weight", (3 * d, d), a, 0.0), (p + "attn.in_proj_bias", (3 * d,), 0.02, 0.0),
+          (p + "attn.out_proj.weight", (d, d), a, 0.0), (p + "attn.out_proj.bias", (d,), 0.02, 0.0),
+          (p + "ln_q.weight", (d,), 0.1, 1.0), (p + "ln_q.bias", (d,), 0.02, 0.0),
+          (p + "ln_kv.weight", (d,), 0.1, 1.0), (p + "ln_kv.bias", (d,), 0.02, 0.0)]
+    s += [(v + "ln_post.weight", (d,), 0.1, 1.0), (v + "ln_post.bias", (d,), 0.02, 0.0)]
+    s += [("transformer.wte.weight", (cfg.vocab, d), a, 0.0)]
+    for i in range(cfg.layers):
+        p = f"transformer.h.{i}."
+        s += [(p + "ln_1.weight", (d,), 0.1, 1.0),
+              (p + "attn.c_attn.weight", (3 * d, d), a, 0.0), (p + "attn.c_attn.bias", (3 * d,), 0.02, 0.0),
+              (p + "attn.c_proj.weight", (d, d), a, 0.0),
+              (p + "ln_2.weight", (d,), 0.1, 1.0),
+              (p + "mlp.w1.weight", (cfg.ff, d), a, 0.0), (p + "mlp.w2.weight", (cfg.ff, d), a, 0.0),
+              (p + "mlp.c_proj.weight", (d, cfg.ff), a, 0.0)]
+    s += [("transformer.ln_f.weight", (d,), 0.1, 1.0), ("lm_head.weight", (cfg.vocab, d), 3.0 * a, 0.0)]
+    return s
+
+
+def qwen_lora_specs(cfg: QwenModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    """`<module>.lora_A` [r, in] / `.lora_B` [out, r] per target module (peft layout).  peft starts B at 0; the
+    synthetic recipe draws B too so the adapter path carries signal in parity tests."""
+    a = 0.02 * math.sqrt(3.0)
+    d, r = cfg.hidden, cfg.lora_r
+    outs = {"attn.c_attn": 3 * d, "attn.c_proj": d, "mlp.w1": cfg.ff, "mlp.w2": cfg.ff}
+    s = []
+    for i in range(cfg.layers):
+        for t in QWEN_LORA_TARGETS:
+            s += [(f"transformer.h.{i}.{t}.lora_A", (r, d), a, 0.0), (f"transformer.h.{i}.{t}.lora_B", (outs[t], r), a, 0.0)]
+    return s

@@ -422,6 +422,53 @@ __global__ void next_merge_img_bwd_kernel(const int* __restrict__ img_rows, cons
     }
 }
 
+// ---------------------------------------------------------------- Qwen-VL image placement (modeling_qwen.py:524-528,614-621)
+// The sequence already holds n_queries placeholder tokens between <img> (image_start_id) and </img> (+1): those
+// positions read image feature rows, everything else (the two markers and padding included) reads its own embedding.
+// S == L, labels pass through, position ids are arange(L) for every row (:573-580), seqlen = attended prefix.
+__global__ void qwen_merge_index_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ amask,
+                                        const int64_t* __restrict__ labels, int n_seq, int L, int Q, int n_img_batch,
+                                        int imgs_per_seq, int image_start, int ignore_index, int* __restrict__ src_map,
+                                        int64_t* __restrict__ labels_m, int* __restrict__ mask_m, int* __restrict__ pos_ids,
+                                        int* __restrict__ seqlen, int* __restrict__ row_of_text,
+                                        int64_t* __restrict__ target, int* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_seq) return;
+    const int64_t* id = ids + (size_t)b * L;
+    const int64_t* am = amask + (size_t)b * L;
+    const int64_t* lb = labels + (size_t)b * L;
+    int* sm = src_map + (size_t)b * L;
+    const int img_base = (b % n_img_batch) * imgs_per_seq;
+    int slot = 0, open = -1, len = 0;
+    bool prefix = true;
+    for (int j = 0; j < L; ++j) {
+        const int64_t t = id[j];
+        sm[j] = (int)t;
+        labels_m[(size_t)b * L + j] = lb[j];
+        mask_m[(size_t)b * L + j] = (int)am[j];
+        pos_ids[(size_t)b * L + j] = j;
+        if (am[j]) { if (!prefix) atomicExch(status, 3); len = j + 1; } else prefix = false;
+        if (j >= 1) {
+            row_of_text[(size_t)b * (L - 1) + j - 1] = b * L + j - 1;
+            target[(size_t)b * (L - 1) + j - 1] = lb[j] == ignore_index ? -100 : lb[j];
+        }
+        if (t == image_start) {
+            if (open >= 0) atomicExch(status, 2);  // nested <img>
+            open = j;
+        } else if (t == image_start + 1) {
+            if (open < 0 || j - open - 1 != Q || slot >= imgs_per_seq) {
+                atomicExch(status, 2);
+            } else {
+                for (int q = 0; q < Q; ++q) sm[open + 1 + q] = -1 - ((img_base + slot) * Q + q);
+            }
+            open = -1;
+            ++slot;
+        }
+    }
+    if (open >= 0 || slot != imgs_per_seq) atomicExch(status, 2);
+    seqlen[b] = len;
+}
+
 // ---------------------------------------------------------------- optimizer
 __global__ void sumsq_partial_kernel(const __nv_bfloat16* __restrict__ x, size_t n8, float* __restrict__ partial) {
     __shared__ float sm[8];
@@ -682,6 +729,20 @@ extern "C" int vlb200_llavanext_merge_bwd(const int* src_map, const int* img_row
     VLB_LAUNCH_CHECK();
     next_merge_img_bwd_kernel<<<grid_for((size_t)total_feats * (d / 8), 256), 256, 0, s>>>(img_rows, CBF(dx), BF(dimage_features), total_feats, reps, d);
     count_launch(2);
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+extern "C" int vlb200_qwen_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels, int n_seq,
+                                       int text_len, int n_queries, int n_img_batch, int imgs_per_seq, int image_start_id,
+                                       int ignore_index, int* src_map, int64_t* labels_out, int* mask_out, int* position_ids,
+                                       int* seqlens, int* row_of_text, int64_t* target, int* status, void* stream) {
+    VLB_REQUIRE(input_ids && attention_mask && labels && src_map && labels_out && mask_out && position_ids && seqlens &&
+                    row_of_text && target && status, "qwen_merge_index: null pointer");
+    VLB_REQUIRE(n_img_batch > 0 && n_seq % n_img_batch == 0 && text_len > 1 && n_queries > 0 && imgs_per_seq > 0,
+                "qwen_merge_index: bad sizes");
+    VLB_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), as_stream(stream)));
+    qwen_merge_index_kernel<<<(n_seq + 31) / 32, 32, 0, as_stream(stream)>>>(input_ids, attention_mask, labels, n_seq, text_len, n_queries, n_img_batch, imgs_per_seq, image_start_id, ignore_index, src_map, labels_out, mask_out, position_ids, seqlens, row_of_text, target, status);
+    count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
 }

@@ -146,13 +146,22 @@ class StepOutput:
 
 
 class LlavaDPOEngine:
+    has_ref_copy = True       # a frozen reference copy of the trainable arena (full fine-tuning)
+    needs_embed_grad = True   # fp32 scatter target for the embedding gradient
+
+    def _make_layouts(self) -> Tuple[Arena, Arena]:
+        """-> (trainable arena, frozen vision arena); subclasses add their own frozen arenas in _alloc_family()."""
+        return _trainable_layout(self.cfg), _vision_layout(self.cfg)
+
+    def _alloc_family(self):
+        pass
+
     def __init__(self, cfg: ModelConfig, train: Optional[TrainConfig] = None, device: str = "cuda",
                  with_optimizer: bool = True, process_group=None):
         self.cfg, self.tc = cfg, train or TrainConfig()
         self.device = torch.device(device)
         self.pg = process_group
-        self.layout = _trainable_layout(cfg)
-        self.vlayout = _vision_layout(cfg)
+        self.layout, self.vlayout = self._make_layouts()
         n = self.layout.size
         import os as _os
         # Optimizer sharding across the data-parallel ranks (ZeRO-1 style; the reference's default DeepSpeed config
@@ -169,11 +178,11 @@ class LlavaDPOEngine:
         self.shard_lo, self.shard_hi = (rank * (n_flat // world), (rank + 1) * (n_flat // world)) if self.shard_optimizer \
             else (0, n_flat)
         self.params = torch.zeros(n_flat, dtype=torch.bfloat16, device=self.device)  # policy (projector + LLM)
-        self.ref_params = torch.zeros(n, dtype=torch.bfloat16, device=self.device)   # frozen reference copy
+        self.ref_params = torch.zeros(n if self.has_ref_copy else 0, dtype=torch.bfloat16, device=self.device)  # frozen reference copy
         self.grads = torch.zeros(n_flat, dtype=torch.bfloat16, device=self.device)
         self.vparams = torch.zeros(self.vlayout.size, dtype=torch.bfloat16, device=self.device)  # frozen vision tower
         self.policy = Weights(self.layout, self.params)
-        self.ref = Weights(self.layout, self.ref_params)
+        self.ref = Weights(self.layout, self.ref_params) if self.has_ref_copy else None
         self.g = Weights(self.layout, self.grads)
         self.vis = Weights(self.vlayout, self.vparams)
         self.with_optimizer = with_optimizer
@@ -182,7 +191,9 @@ class LlavaDPOEngine:
             self.master = torch.zeros(ns, dtype=torch.float32, device=self.device)
             self.exp_avg = torch.zeros(ns, dtype=torch.float32, device=self.device)
             self.exp_avg_sq = torch.zeros(ns, dtype=torch.float32, device=self.device)
-        self.dembed_f32 = torch.zeros(cfg.vocab, cfg.hidden, dtype=torch.float32, device=self.device)
+        self.dembed_f32 = torch.zeros(cfg.vocab, cfg.hidden, dtype=torch.float32, device=self.device) \
+            if self.needs_embed_grad else None
+        self._alloc_family()
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
@@ -399,26 +410,53 @@ class LlavaDPOEngine:
             xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d), torch.float32)
             self._layer_fwd(w, i, x, b, m, xn)
             x = xn
+        return self._head_forward(x, w["norm"], w["lm_head"], m, feats, save, ddpo_weight)
+
+    def _head_forward(self, x: torch.Tensor, norm_w: torch.Tensor, lm_w: torch.Tensor, m: "ops.MergeIndex", feats, save: bool,
+                      ddpo_weight: Optional[torch.Tensor]):
+        """Final RMSNorm -> lm_head on the rows that can carry a label (K15) -> fused log-prob gather (K16)."""
+        cfg = self.cfg
+        d, T = cfg.hidden, m.n_seq * m.S
         h = self.buf("s.h", (T, d))
         rstd_f = self.buf("a.rstd_f" if save else "s.rstd_f", (T,), torch.float32)
-        ops.rmsnorm_fwd(x, w["norm"], cfg.rms_eps, out=h, rstd=rstd_f)
-        # lm_head only on rows that can carry a label (K15) + fused log-prob gather (K16)
+        ops.rmsnorm_fwd(x, norm_w, cfg.rms_eps, out=h, rstd=rstd_f)
         R = m.n_seq * (m.L - 1)
         hsel = self.buf("a.hsel" if save else "s.hsel", (R, d))
         ops.gather_rows(h, m.row_of_text, hsel)
         logits = self.buf("a.logits" if save else "s.logits", (R, cfg.vocab), torch.float32)
-        ops.gemm(hsel, w["lm_head"], out=logits)
+        ops.gemm(hsel, lm_w, out=logits)
         logps, per_tok, lse_v = ops.logps_fwd(logits, m.target, m.n_seq, weight=ddpo_weight)
         if save:
             self._saved = dict(m=m, feats=feats, x_last=x, lse_v=lse_v, ddpo_weight=ddpo_weight)
             # TRL's `logits/chosen|rejected` = mean of the full [B,S,V] logits = dot(colsum(h), colsum(W_lm)) / (B*S*V)  (K19)
             half = T // 2
             cs = self.buf("m.colsum", (3, d), torch.float32)
-            ops.colsum_f32(h[:half], cs[0]); ops.colsum_f32(h[half:], cs[1]); ops.colsum_f32(w["lm_head"], cs[2])
+            ops.colsum_f32(h[:half], cs[0]); ops.colsum_f32(h[half:], cs[1]); ops.colsum_f32(lm_w, cs[2])
             self.logit_means = self.buf("m.logit_means", (2,), torch.float32)
             inv = 1.0 / (float(half) * cfg.vocab)
             ops.dot_f32(cs[0], cs[2], inv, self.logit_means[0:1]); ops.dot_f32(cs[1], cs[2], inv, self.logit_means[1:2])
         return logps
+
+    def _head_backward(self, grad_logps: torch.Tensor, norm_w: torch.Tensor, lm_w: torch.Tensor, g_norm: torch.Tensor,
+                       g_lm: Optional[torch.Tensor]) -> torch.Tensor:
+        """d(log-probs) -> gradient of the last decoder layer's output (bf16 [T, d]); g_lm=None: lm_head is frozen."""
+        cfg, sv = self.cfg, self._saved
+        m = sv["m"]
+        d, T = cfg.hidden, m.n_seq * m.S
+        R = m.n_seq * (m.L - 1)
+        logits, hsel = self._bufs["a.logits"], self._bufs["a.hsel"]
+        dlogits = self.buf("b.dlogits", (R, cfg.vocab))
+        ops.logps_bwd(logits, m.target, m.n_seq, sv["lse_v"], grad_logps, weight=sv["ddpo_weight"], out=dlogits)
+        if g_lm is not None:
+            ops.gemm(dlogits, hsel, a_kmajor=False, b_kmajor=False, out=g_lm)              # dW = dlogits^T hsel
+        dhsel = self.buf("b.dhsel", (R, d))
+        ops.gemm(dlogits, lm_w, b_kmajor=False, out=dhsel)                                 # dh = dlogits W
+        dxf = self.buf("b.dxf", (T, d))
+        ops.zero_(dxf)
+        ops.scatter_rows(dhsel, m.row_of_text, dxf)
+        dx = self.buf("b.dx0", (T, d))
+        ops.rmsnorm_bwd(dxf, sv["x_last"], norm_w, self._bufs["a.rstd_f"], g_norm, out=dx)
+        return dx
 
     # ------------------------------------------------------------------ backward of the policy copy
     def _backward(self, grad_logps: torch.Tensor):
@@ -429,20 +467,9 @@ class LlavaDPOEngine:
         d, T = cfg.hidden, m.n_seq * m.S
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
-        R = m.n_seq * (m.L - 1)
-        logits = self._bufs["a.logits"]
-        hsel = self._bufs["a.hsel"]
-        dlogits = self.buf("b.dlogits", (R, cfg.vocab))
-        ops.logps_bwd(logits, m.target, m.n_seq, sv["lse_v"], grad_logps, weight=sv["ddpo_weight"], out=dlogits)
-        ops.gemm(dlogits, hsel, a_kmajor=False, b_kmajor=False, out=g["lm_head"])            # dW = dlogits^T hsel
-        dhsel = self.buf("b.dhsel", (R, d))
-        ops.gemm(dlogits, w["lm_head"], b_kmajor=False, out=dhsel)                           # dh = dlogits W
-        dxf = self.buf("b.dxf", (T, d))
-        ops.zero_(dxf)
-        ops.scatter_rows(dhsel, m.row_of_text, dxf)
-        dx = self.buf("b.dx0", (T, d))
+        dx = self._head_backward(grad_logps, w["norm"], w["lm_head"], g["norm"], g["lm_head"])
+        dxf = self._bufs["b.dxf"]
         dx2 = self.buf("b.dx1", (T, d))
-        ops.rmsnorm_bwd(dxf, sv["x_last"], w["norm"], self._bufs["a.rstd_f"], g["norm"], out=dx)
         self._reduce_bucket(self.layout.offsets["norm"], self.layout.size)          # norm + lm_head gradients are final
         h = self.buf("s.h", (T, d))
         act = self.buf("s.act", (T, cfg.ff))

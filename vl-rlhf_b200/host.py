@@ -255,3 +255,33 @@ def matching_blocks_native(a_seq: List[int], b_seq: List[int]) -> List[Tuple[int
     if n < 0:
         raise RuntimeError(L_.vlb200_last_error().decode())
     return [tuple(r) for r in out[:n].tolist()]
+
+
+# ------------------------------------------------------------------------------------------
+# Qwen-VL position tables (models/QwenVL/visual.py:24-96): weight transforms done once at load time
+# ------------------------------------------------------------------------------------------
+def sincos_2d(embed_dim: int, grid: int) -> torch.Tensor:
+    """get_2d_sincos_pos_embed: float32 [grid*grid, embed_dim] (w-coordinate first, as the reference's meshgrid)."""
+    import numpy as np
+    gh = np.arange(grid, dtype=np.float32)
+    gw = np.arange(grid, dtype=np.float32)
+    g = np.stack(np.meshgrid(gw, gh), axis=0).reshape([2, 1, grid, grid])
+
+    def one(dim, pos):
+        omega = np.arange(dim // 2, dtype=np.float32)
+        omega /= dim / 2.0
+        omega = 1.0 / 10000 ** omega
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+    return torch.from_numpy(np.concatenate([one(embed_dim // 2, g[0]), one(embed_dim // 2, g[1])], axis=1)).float()
+
+
+def interpolate_pos_table(table: torch.Tensor, n_target: int) -> torch.Tensor:
+    """get_abs_pos: bicubic interpolation (align_corners=False) of a square [g*g, C] table to n_target positions."""
+    import math
+    src, tgt = int(math.sqrt(table.shape[0])), int(math.sqrt(n_target))
+    if src == tgt:
+        return table
+    return torch.nn.functional.interpolate(table.float().reshape(1, src, src, -1).permute(0, 3, 1, 2), size=(tgt, tgt),
+                                           mode="bicubic", align_corners=False).permute(0, 2, 3, 1).flatten(0, 2)

@@ -366,6 +366,32 @@ def llavanext_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tenso
                                         _ptr(dimage_features), m.n_seq * m.S, m.total_feats, m.reps, dx.shape[1], _stream()))
 
 
+def qwen_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_queries: int,
+                     n_img_batch: int, imgs_per_seq: int, image_start_id: int, ignore_index: int = -100):
+    """Integer pass of QWenModel.forward's image placement (modeling_qwen.py:524-528,614-621); S == L."""
+    n_seq, L = input_ids.shape
+    dev = input_ids.device
+    for t in (input_ids, attention_mask, labels):
+        assert t.dtype == torch.int64 and t.is_contiguous() and t.shape == (n_seq, L)
+    m = MergeIndex()
+    m.n_seq, m.L, m.S, m.P, m.n_img_batch, m.imgs_per_seq = n_seq, L, L, n_queries, n_img_batch, imgs_per_seq
+    m.total_feats, m.reps = n_img_batch * imgs_per_seq * n_queries, n_seq // n_img_batch
+    m.src_map = torch.empty(n_seq * L, dtype=torch.int32, device=dev)
+    m.labels = torch.empty(n_seq, L, dtype=torch.int64, device=dev)
+    m.mask = torch.empty(n_seq, L, dtype=torch.int32, device=dev)
+    m.pos = torch.empty(n_seq * L, dtype=torch.int32, device=dev)
+    m.seqlens = torch.empty(n_seq, dtype=torch.int32, device=dev)
+    m.img_pos = None
+    m.row_of_text = torch.empty(n_seq * (L - 1), dtype=torch.int32, device=dev)
+    m.target = torch.empty(n_seq * (L - 1), dtype=torch.int64, device=dev)
+    m.status = torch.empty(1, dtype=torch.int32, device=dev)
+    check(_L.vlb200_qwen_merge_index(_ptr(input_ids), _ptr(attention_mask), _ptr(labels), n_seq, L, n_queries, n_img_batch,
+                                     imgs_per_seq, image_start_id, ignore_index, _ptr(m.src_map), _ptr(m.labels), _ptr(m.mask),
+                                     _ptr(m.pos), _ptr(m.seqlens), _ptr(m.row_of_text), _ptr(m.target), _ptr(m.status),
+                                     _stream()))
+    return m
+
+
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
