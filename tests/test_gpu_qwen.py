@@ -123,8 +123,11 @@ def test_qwen_forward_logps_loss_and_ddpo_parity(pkg, tag):
     np.testing.assert_allclose(out.chosen_rewards.cpu().numpy(), d["sigmoid_cr"], atol=slack)
     wt = eng.ddpo_weights(ids, am, lb)
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px, wt), train=False)
-    np.testing.assert_allclose(out.policy_logps.cpu().numpy(), d["policy_logps_ddpo"], rtol=0, atol=1e-3 * np.abs(d["policy_logps"]))
-    np.testing.assert_allclose(out.ref_logps.cpu().numpy(), d["ref_logps_ddpo"], rtol=0, atol=1e-3 * np.abs(d["ref_logps"]))
+    # DDPO sums a subset of the same per-token terms: absolute error bounded by the full sum's 1e-3 budget
+    for got, key, full in ((out.policy_logps, "policy_logps_ddpo", "policy_logps"), (out.ref_logps, "ref_logps_ddpo", "ref_logps")):
+        err = np.abs(got.cpu().numpy() - d[key])
+        print(f"[{tag}] {key} abs err", err, "budget", 1e-3 * np.abs(d[full]), "values", d[key])
+        assert (err <= 1e-3 * np.abs(d[full])).all(), (key, err)
 
 
 @pytest.mark.parametrize("tag", list(CASES))

@@ -50,18 +50,28 @@ def qpkg():
     from tests import mock_ops
     names = ("vlrlhf_b200.ops", "vlrlhf_b200.engine", "vlrlhf_b200.engine_qwen")
     saved = {k: sys.modules.get(k) for k in names}
+    saved_attr = {k: getattr(vlrlhf_b200, k.split(".")[1], None) for k in names}
     sys.modules["vlrlhf_b200.ops"] = mock_ops
-    sys.modules.pop("vlrlhf_b200.engine", None)
-    sys.modules.pop("vlrlhf_b200.engine_qwen", None)
+    vlrlhf_b200.ops = mock_ops  # `from . import ops` resolves through the package attribute when it exists
+    for k in names[1:]:
+        sys.modules.pop(k, None)
+        if hasattr(vlrlhf_b200, k.split(".")[1]):
+            delattr(vlrlhf_b200, k.split(".")[1])
     importlib.import_module("vlrlhf_b200.engine")
     engine_qwen = importlib.import_module("vlrlhf_b200.engine_qwen")
     from vlrlhf_b200 import config, host
     yield config, engine_qwen, host, mock_ops
     for k, v in saved.items():
+        attr = k.split(".")[1]
         if v is None:
             sys.modules.pop(k, None)
         else:
             sys.modules[k] = v
+        if saved_attr[k] is None:
+            if hasattr(vlrlhf_b200, attr):
+                delattr(vlrlhf_b200, attr)
+        else:
+            setattr(vlrlhf_b200, attr, saved_attr[k])
 
 
 def _setup(qpkg, tag, loss_type="sigmoid", with_optimizer=False, **tc):
