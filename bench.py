@@ -229,9 +229,11 @@ def run_b200(args):
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import config, engine, host, ops, synthetic
     cfg = {"7b": config.LLAVA15_7B, "small": config.SMALL, "tiny": config.TINY, "next7b": config.LLAVANEXT_MISTRAL_7B,
-           "next_small": config.SMALL_NEXT}[args.model]
+           "next_small": config.SMALL_NEXT, "qwen7b": config.QWEN_VL_CHAT, "qwen_small": config.SMALL_QWEN}[args.model]
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
     is_next = cfg.family == "llava_next"
+    if cfg.family == "qwen_vl":
+        return run_b200_qwen(args, cfg, world, rank, local)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
     eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b")))
@@ -328,14 +330,93 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_qwen(args, cfg, world, rank, local):
+    """Side measurement for BASELINE.json configs[2]: Qwen-VL-Chat DPO, LoRA r=64 on the LM, frozen tower, 4 pairs/GPU,
+    text 1024 (the 256 image tokens sit inside the text), one 448-px image per pair.  Same timing rules as run_b200."""
+    import torch
+    import torch.distributed as dist
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import config, engine_qwen, host, ops, synthetic
+    full = args.model == "qwen7b"
+    text_len, prompt_len = (1024, 320) if full else (128, 72)
+    eng = engine_qwen.QwenVLDPOEngine(cfg, config.TrainConfig(loss_type=args.loss_type, learning_rate=1e-5, weight_decay=0.05))
+    eng.init_synthetic(0)
+    batch = synthetic.make_qwen_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
+    cb = host.concatenated_inputs(batch)
+    ids_h, am_h, lb_h = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+    wt_h = eng.ddpo_weights(ids_h, am_h, lb_h) if args.loss_type == "ddpo" else None
+    dev_inputs = eng.prepare_inputs(ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"], wt_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    last = {}
+    step_dev = lambda: eng.step(*dev_inputs, train=True)  # noqa: E731
+    step_e2e = lambda: last.update(eng.train_step(batch, train=True))  # noqa: E731
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = ops.launch_count()
+    ms_dev = timed(step_dev, args.steps)
+    launches = ops.launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
+    clocks = sampler.stop() if sampler else None
+    # algorithmic FLOPs: LM forward x3 (policy fwd, reference fwd, dgrad-only backward) per sequence, adapters, tower once/pair
+    d, ff, L, S, r = cfg.hidden, cfg.ff, cfg.layers, text_len, cfg.lora_r
+    p_layer = 3 * d * d + d * d + 3 * d * ff
+    lin_seq, attn_seq = S * 2 * p_layer * L, L * 2 * S * S * d
+    per_seq = 3 * lin_seq + 4 * attn_seq  # linear: policy fwd + reference fwd + dgrad; attention: 2 fwd + a 2x backward
+    lora_seq = S * 2 * L * r * (d + 3 * d + d + d + 2 * (d + ff))
+    rows_lm = 2 * PAIRS_PER_GPU * (text_len - 1)
+    w, P = cfg.v_width, cfg.n_patches
+    vit = cfg.v_layers * (P * 2 * (4 * w * w + 2 * w * cfg.v_mlp) + 4 * P * P * w) + P * 2 * cfg.patch_k * w
+    resampler = P * 2 * (w * d + 2 * d * d) + 4 * cfg.n_queries * P * d + cfg.n_queries * 2 * 2 * d * d
+    flops = PAIRS_PER_GPU * (2 * (per_seq + lora_seq * 3) + vit + resampler) + rows_lm * 2 * d * cfg.vocab * 3
+    pk, pk_src = peaks()
+    if rank == 0:
+        pairs = PAIRS_PER_GPU * world
+        h2d = sum(int(t.numel() * t.element_size()) for t in (ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"]))
+        line = {"metric": METRIC, "value": pairs / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": ("Qwen-VL-Chat DPO bf16 (configs[2], side measurement), LoRA r=64 alpha=16 on c_attn/attn.c_proj/"
+                                        "w1/w2, frozen ViT-bigG+resampler, 4 pairs/GPU, text 1024 incl. 256 image tokens, 1x448px "
+                                        "image/pair") if full else f"{args.model} (dev config, NOT the benchmark)",
+                           "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": text_len, "loss_type": args.loss_type,
+                           "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
+                           "step_tflop_algorithmic": flops / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                        "ms_per_step": ms_e2e, "last_metrics": last},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small"],
-                    help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO (side measurement)")
+    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small"],
+                    help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO, qwen7b = configs[2] Qwen-VL-Chat LoRA (side measurements)")
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
