@@ -106,3 +106,45 @@ def test_two_rank_data_parallel_step(tmp_path):
     torch.testing.assert_close(r0["sumsq_sharded"], r0["sumsq"], rtol=1e-5, atol=0)
     same = (r0["params_sharded"] == r0["params"]).float().mean().item()
     assert same > 0.9999, same
+
+
+def _qwen_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib
+    import vlrlhf_b200  # noqa: F401
+    from tests import mock_ops
+    sys.modules["vlrlhf_b200.ops"] = mock_ops
+    vlrlhf_b200.ops = mock_ops
+    EQ = importlib.import_module("vlrlhf_b200.engine_qwen")
+    from vlrlhf_b200 import config
+    from oracle import qwen_restate as Q
+    torch.set_num_threads(2)
+    out = {}
+    for shard in ("0", "1"):
+        os.environ["VLB200_SHARD_OPTIMIZER"] = shard
+        eng = EQ.QwenVLDPOEngine(config.TINY_QWEN, config.TrainConfig(learning_rate=1e-3), device="cpu")
+        assert eng.shard_optimizer == (shard == "1")
+        eng.init_synthetic(0)
+        batch = Q.make_batch(Q.TINY_QWEN, 2, 48, 24, seed=100 + rank)  # rank-local pairs
+        eng.train_step(batch, train=True)
+        out[f"params{shard}"] = eng.params[: eng.layout.size].clone()
+        out[f"base{shard}"] = eng.bparams.clone()
+    torch.save(out, os.path.join(out_dir, f"qrank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_qwen_lora_step(tmp_path):
+    """Qwen-VL + LoRA under data parallelism: only the adapter arena is reduced / sharded; replicas stay identical and the
+    sharded update equals the replicated one."""
+    port = _free_port()
+    mp.spawn(_qwen_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "qrank0.pt"), torch.load(tmp_path / "qrank1.pt")
+    for s in ("0", "1"):
+        assert torch.equal(r0[f"params{s}"], r1[f"params{s}"])
+        assert torch.equal(r0[f"base{s}"], r1[f"base{s}"])
+    assert (r0["params0"] == r0["params1"]).float().mean().item() > 0.9999
