@@ -309,8 +309,8 @@ def test_config4_next7b_shapes_ddpo_parity(pkg):
         else:
             # DDPO log-probs are a 0/1-weighted SUBSET of the same per-token terms (a few dozen of the ~70 labelled
             # tokens here): their absolute error is bounded by the budget the 1e-3 relative bound gives the full sum
-            np.testing.assert_allclose(pol, d[key], rtol=0, atol=1e-3 * np.abs(d["policy_logps"]))
-            np.testing.assert_allclose(ref, d[rkey], rtol=0, atol=1e-3 * np.abs(d["ref_logps"]))
+            assert (np.abs(pol - d[key]) <= 1e-3 * np.abs(d["policy_logps"])).all()
+            assert (np.abs(ref - d[rkey]) <= 1e-3 * np.abs(d["ref_logps"])).all()
             assert np.abs(pol / d[key] - 1).max() < 5e-3
     slack = 0.1 * 1e-3 * np.abs(d["policy_logps_ddpo"]).max() * 4
     np.testing.assert_allclose(out.losses.cpu().numpy(), d["ddpo_losses"], atol=slack)
