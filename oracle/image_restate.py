@@ -127,6 +127,17 @@ def clip_preprocess(img: np.ndarray, size: int = 336, crop: int = 336, mean: Seq
     return np.ascontiguousarray(x.transpose(2, 0, 1))
 
 
+def square_preprocess(img: np.ndarray, size: int = 448, mean: Sequence[float] = OPENAI_CLIP_MEAN,
+                      std: Sequence[float] = OPENAI_CLIP_STD) -> np.ndarray:
+    """Qwen-VL / InternLM-XC2 image transform (models/QwenVL/visual.py:354-362, InternLMXC2/modeling_internlm_xcomposer2.py
+    :67-73): torchvision Resize((size, size), BICUBIC) on the PIL image (= Pillow resize, aspect ratio NOT kept) ->
+    ToTensor (uint8 / 255 in float32) -> Normalize ((x - mean) / std in float32).  [H, W, 3] uint8 -> [3, size, size]."""
+    r = pil_bicubic_resize_u8(img, (size, size))
+    x = r.astype(np.float32) / np.float32(255)
+    x = (x - np.array(mean, dtype=np.float32)) / np.array(std, dtype=np.float32)
+    return np.ascontiguousarray(x.transpose(2, 0, 1))
+
+
 # ---- seeded synthetic RGB images shared by the fixture generator (make_fixtures.py --preprocess) and the tests
 def synthetic_image(h: int, w: int, seed: int) -> np.ndarray:
     """[h, w, 3] uint8: smooth colour waves + noise + hard edges (exercises the negative bicubic lobes / clipping)."""

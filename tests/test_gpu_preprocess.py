@@ -93,3 +93,12 @@ def test_collator_end_to_end_on_gpu(P, tmp_path):
     for i, (h, w) in enumerate([(400, 600), (700, 500)]):
         assert np.array_equal(pv[i].cpu().numpy(), IR.clip_preprocess(IR.synthetic_image(h, w, i)))
     assert batch["chosen_input_ids"].shape == (2, 3) and batch["rejected_labels"][0].tolist() == [-100, 2]
+
+
+def test_square_transform_on_gpu(P):
+    """Qwen-VL (448) / InternLM-XC2 (490) transform: Resize((s, s)) + ToTensor + Normalize, bit-exact."""
+    for size, (h, w), seed in ((448, (300, 500), 1), (448, (700, 333), 2), (490, (490, 490), 3), (112, (60, 45), 4)):
+        img = IR.synthetic_image(h, w, seed)
+        got = P.ClipPreprocessor(size=size, square=True)([img])[0].cpu().numpy()
+        assert got.shape == (3, size, size)
+        assert np.array_equal(got, IR.square_preprocess(img, size)), (size, h, w)

@@ -57,3 +57,16 @@ def test_product_host_tables_equal_oracle():
         assert (nh, nw) == g[:2] and g[2] == (nh - 336) // 2 and g[3] == (nw - 336) // 2
     with pytest.raises(ValueError):
         P.resize_geometry(100, 100, 224, 336)
+
+
+def test_square_transform_matches_torchvision():
+    """Qwen-VL / XC2 transform: the oracle == torchvision Resize((s, s), BICUBIC) + ToTensor + Normalize, bit for bit."""
+    tv = pytest.importorskip("torchvision.transforms")
+    Image = pytest.importorskip("PIL.Image")
+    from torchvision.transforms import InterpolationMode
+    for size, (h, w), seed in ((448, (300, 500), 1), (448, (700, 333), 2), (490, (490, 490), 3), (112, (60, 45), 4)):
+        img = IR.synthetic_image(h, w, seed)
+        t = tv.Compose([tv.Resize((size, size), interpolation=InterpolationMode.BICUBIC), tv.ToTensor(),
+                        tv.Normalize(IR.OPENAI_CLIP_MEAN, IR.OPENAI_CLIP_STD)])
+        want = t(Image.fromarray(img)).numpy()
+        assert np.array_equal(IR.square_preprocess(img, size), want), (size, h, w)

@@ -181,3 +181,141 @@ def test_qwen_engine_optimizer_updates_only_adapters(qpkg):
     assert torch.equal(eng.bparams, base0) and torch.equal(eng.vparams, vis0)
     assert torch.equal(eng.params, eng.master.to(torch.bfloat16))
     assert eng.master.numel() == eng.layout.size  # optimizer state covers the adapters only
+
+
+# ------------------------------------------------------------------------------------------
+# plugin side: checkpoints, adapters, images named in the token stream
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def qplugin(qpkg):
+    for k in ("vlrlhf_b200.plugin", "vlrlhf_b200.plugin_qwen"):
+        sys.modules.pop(k, None)
+    import vlrlhf_b200
+    for a in ("plugin", "plugin_qwen"):
+        if hasattr(vlrlhf_b200, a):
+            delattr(vlrlhf_b200, a)
+    plugin = importlib.import_module("vlrlhf_b200.plugin")
+    pq = importlib.import_module("vlrlhf_b200.plugin_qwen")
+    yield plugin, pq
+    for k in ("vlrlhf_b200.plugin", "vlrlhf_b200.plugin_qwen"):
+        sys.modules.pop(k, None)
+    for a in ("plugin", "plugin_qwen"):
+        if hasattr(vlrlhf_b200, a):
+            delattr(vlrlhf_b200, a)
+
+
+def _spell(path: str, qcfg, total: int):
+    b = list(path.encode("utf-8"))
+    return [qcfg.image_start_id] + b + [qcfg.image_start_id + 2] * (total - len(b)) + [qcfg.image_start_id + 1]
+
+
+def test_image_paths_from_ids_like_reference(qplugin):
+    plugin, pq = qplugin
+    qcfg = Q.TINY_QWEN
+    ids = torch.full((3, 40), 7, dtype=torch.int64)
+    paths = ["/tmp/a.png", "d/i_01.jpg", "x"]
+    for i, p in enumerate(paths):
+        blk = _spell(p, qcfg, qcfg.n_queries)
+        ids[i, 2 + i:2 + i + len(blk)] = torch.tensor(blk)
+    got = pq.image_paths_from_ids(ids, qcfg.image_start_id)
+    # the reference's loop (modeling_qwen.py:524-534)
+    bos, eos = torch.where(ids == qcfg.image_start_id), torch.where(ids == qcfg.image_start_id + 1)
+    want = []
+    for i, a, b in torch.stack((bos[0], bos[1], eos[1]), dim=1):
+        image = ids[i][a + 1:b - 1].tolist()
+        image = image[: image.index(qcfg.image_start_id + 2)]
+        want.append(bytes(image).decode("utf-8"))
+    assert got == want == paths
+
+
+def test_qwen_from_pretrained_adapters_and_plugin_forward(qpkg, qplugin, tmp_path, monkeypatch):
+    pytest.importorskip("safetensors")
+    from safetensors.torch import save_file
+    import json
+    config, EQ, host, ops = qpkg
+    plugin, pq = qplugin
+    qcfg = Q.TINY_QWEN
+    w, lora = Q.make_weights(qcfg, 0)
+    src = tmp_path / "ckpt"
+    src.mkdir()
+    save_file({k: v.to(torch.bfloat16).contiguous() for k, v in w.items()}, str(src / "model.safetensors"))
+    hf_cfg = dict(model_type="qwen", vocab_size=qcfg.vocab, hidden_size=qcfg.hidden, num_hidden_layers=qcfg.layers,
+                  num_attention_heads=qcfg.heads, kv_channels=qcfg.head_dim, intermediate_size=2 * qcfg.ff, seq_length=2048,
+                  layer_norm_epsilon=qcfg.rms_eps, rotary_emb_base=qcfg.rope_theta,
+                  visual=dict(heads=qcfg.v_heads, image_size=qcfg.image_size, image_start_id=qcfg.image_start_id,
+                              layers=qcfg.v_layers, mlp_ratio=qcfg.v_mlp / qcfg.v_width, output_dim=qcfg.hidden,
+                              patch_size=qcfg.patch_size, width=qcfg.v_width, n_queries=qcfg.n_queries))
+    (src / "config.json").write_text(json.dumps(hf_cfg))
+    model = pq.B200QwenVLForRL.from_pretrained(str(src), torch_dtype=torch.bfloat16, device="cpu", lora_r=qcfg.lora_r,
+                                               lora_alpha=qcfg.lora_alpha)
+    mc = model.cfg
+    for f in ("hidden", "layers", "heads", "ff", "vocab", "v_width", "v_layers", "v_heads", "v_mlp", "n_queries", "image_size",
+              "image_start_id", "lora_r", "lora_alpha"):
+        assert getattr(mc, f) == getattr(config.TINY_QWEN, f), f
+    st = model.engine.hf_state("ref")
+    for k, v in w.items():
+        if not k.startswith("transformer.visual."):
+            assert torch.equal(st[k].float().reshape(v.shape), v), k
+    # frozen base, trainable adapters with gradient views
+    trainable = {n for n, p in model._hf.items() if p.requires_grad}
+    assert trainable == set(lora)
+    # peft init (B = 0): the policy equals the reference
+    batch = Q.make_batch(qcfg, 2, 48, 24, seed=1)
+    cb = host.concatenated_inputs(batch)
+    a = model.engine.prepare_inputs(cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"],
+                                    cb["concatenated_img_input_dict"]["pixel_values"])
+    out = model.engine.step(*a, train=False)
+    assert torch.allclose(out.policy_logps, out.ref_logps, rtol=0, atol=1e-3)
+    with torch.no_grad():
+        want = torch.cat(Q.concatenated_forward(qcfg, w, None, batch)[:2])
+    np.testing.assert_allclose(out.ref_logps.numpy(), want.numpy(), rtol=1e-3)
+    # adapters: write the synthetic ones in PEFT naming, load, save, reload
+    views = model.engine.lora_views(model.engine.policy)
+    for k, v in lora.items():
+        views[k].copy_(v.to(torch.bfloat16))
+    files = model.save_pretrained(str(tmp_path / "adapter"))
+    assert files == ["adapter_model.safetensors", "adapter_config.json"]
+    acfg = json.loads((tmp_path / "adapter" / "adapter_config.json").read_text())
+    assert acfg["r"] == qcfg.lora_r and acfg["peft_type"] == "LORA" and sorted(acfg["target_modules"]) == sorted(model.default_lora_target)
+    from safetensors import safe_open
+    with safe_open(str(tmp_path / "adapter" / "adapter_model.safetensors"), "pt") as f:
+        keys = set(f.keys())
+        assert keys == {f"base_model.model.{k}.weight" for k in lora}
+        k0 = "base_model.model.transformer.h.1.mlp.w1.lora_B.weight"
+        assert torch.equal(f.get_tensor(k0).float(), lora["transformer.h.1.mlp.w1.lora_B"])
+    model.reset_adapters()
+    assert float(views["transformer.h.0.attn.c_attn.lora_B"].abs().max()) == 0.0
+    model.load_adapter(str(tmp_path / "adapter"))
+    for k, v in lora.items():
+        assert torch.equal(views[k].float(), v), k
+    # LoraConfig validation of the trainer hook
+    from types import SimpleNamespace
+    pq.check_peft_config(model, SimpleNamespace(r=qcfg.lora_r, lora_alpha=qcfg.lora_alpha, target_modules=["c_attn", "attn.c_proj", "w1", "w2"]))
+    for bad in (None, SimpleNamespace(r=4, lora_alpha=qcfg.lora_alpha, target_modules=["c_attn", "attn.c_proj", "w1", "w2"]),
+                SimpleNamespace(r=qcfg.lora_r, lora_alpha=qcfg.lora_alpha, target_modules=["c_attn"])):
+        with pytest.raises(ValueError):
+            pq.check_peft_config(model, bad)
+    # the trainer-level call on a reference-format batch (no img_input_dict: images are named in the token stream)
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import image_restate as IR
+    imgs = [IR.synthetic_image(90, 120, 1), IR.synthetic_image(130, 80, 2)]
+    b2 = {k: v.clone() for k, v in batch.items() if k != "img_input_dict"}
+    monkeypatch.chdir(tmp_path)  # short relative names: the tiny config has only 16 placeholder tokens to spell a path
+    for i, im in enumerate(imgs):
+        path = f"q{i}.png"
+        Image.fromarray(im).save(path)
+        blk = torch.tensor(_spell(path, qcfg, qcfg.n_queries))
+        for side in ("chosen", "rejected"):
+            b2[f"{side}_input_ids"][i, 1:1 + len(blk)] = blk
+    model._preprocessor = lambda arrs: torch.from_numpy(np.stack([IR.square_preprocess(x, qcfg.image_size) for x in arrs]))
+    trainer = SimpleNamespace(loss_type="sigmoid", is_encoder_decoder=False, label_pad_token_id=-100, padding_value=0)
+    with torch.no_grad():
+        pc, pr, _, _ = plugin.concatenated_forward(trainer, model, b2)
+        rc, rr, _, _ = plugin.concatenated_forward(trainer, plugin.RefView(model), b2)
+    b3 = dict(b2)
+    b3["img_input_dict"] = {"pixel_values": model._preprocessor(imgs)}
+    with torch.no_grad():
+        w_pc, w_pr, _, _, _ = Q.concatenated_forward(qcfg, w, lora, b3)
+        w_rc, w_rr, _, _, _ = Q.concatenated_forward(qcfg, w, None, b3)
+    np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), torch.cat([w_pc, w_pr]).numpy(), rtol=1e-3)
+    np.testing.assert_allclose(torch.cat([rc, rr]).numpy(), torch.cat([w_rc, w_rr]).numpy(), rtol=1e-3)

@@ -216,8 +216,11 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     cb = host.concatenated_inputs(batch, getattr(self, "is_encoder_decoder", False),
                                   getattr(self, "label_pad_token_id", -100), getattr(self, "padding_value", 0) or 0)
     ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
-    px = batch["img_input_dict"]["pixel_values"]
-    sizes = batch["img_input_dict"].get("image_sizes")  # LLaVA-Next (LlavaNext/__init__.py:348-380 collators)
+    if "img_input_dict" in batch:
+        px = batch["img_input_dict"]["pixel_values"]
+        sizes = batch["img_input_dict"].get("image_sizes")  # LLaVA-Next (LlavaNext/__init__.py:348-380 collators)
+    else:  # Qwen-VL: the images are named inside the token stream (modeling_qwen.py:524-537)
+        px, sizes = model_pixels(model, batch["chosen_input_ids"]), None
     wt = None
     if self.loss_type == "ddpo":
         wt = eng.ddpo_weights(ids, am, lb, sizes)
@@ -232,11 +235,19 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     return logps[:n], logps[n:], None, None
 
 
+def model_pixels(model, input_ids: torch.Tensor) -> torch.Tensor:
+    owner = getattr(model, "_owner", model)
+    if not hasattr(owner, "pixel_values_for"):
+        raise ValueError("the batch carries no img_input_dict and the model cannot resolve images from its token stream")
+    return owner.pixel_values_for(input_ids)
+
+
 class RefView:
     """`ref_model` handle for TRL's `self.ref_model(...)`/concatenated_forward(self.ref_model, batch) call."""
 
-    def __init__(self, model: B200LlavaForRL):
+    def __init__(self, model):
         self.engine = model.engine
+        self._owner = model
         self._which = "ref"
 
 

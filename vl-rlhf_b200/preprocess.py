@@ -69,12 +69,17 @@ def resize_geometry(h: int, w: int, size: int, crop: int) -> Tuple[int, int, int
 
 
 class ClipPreprocessor:
-    """`CLIPImageProcessor(size={"shortest_edge": s}, crop_size=c)` for decoded RGB uint8 images, on the GPU."""
+    """`CLIPImageProcessor(size={"shortest_edge": s}, crop_size=c)` for decoded RGB uint8 images, on the GPU.
+
+    `square=True` is the Qwen-VL / InternLM-XC2 transform instead (visual.py:354-362): torchvision
+    `Resize((s, s), BICUBIC)` without keeping the aspect ratio, `ToTensor`, `Normalize` -- the same two kernels with the
+    crop covering the whole resized image (uint8 / 255 in float32 equals the float64-multiply rescale for all 256 values)."""
 
     def __init__(self, size: int = 336, crop: int = 336, image_mean: Sequence[float] = OPENAI_CLIP_MEAN,
                  image_std: Sequence[float] = OPENAI_CLIP_STD, rescale_factor: float = 1 / 255, device: str = "cuda",
-                 out_dtype: torch.dtype = torch.float32):
-        self.size, self.crop = int(size), int(crop)
+                 out_dtype: torch.dtype = torch.float32, square: bool = False):
+        self.size, self.crop = int(size), int(size if square else crop)
+        self.square = bool(square)
         self.rescale = float(rescale_factor)
         self.device = torch.device(device)
         self.out_dtype = out_dtype
@@ -100,7 +105,7 @@ class ClipPreprocessor:
         if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3:
             raise ValueError(f"expected an [H, W, 3] uint8 RGB image, got {tuple(image.shape)} {image.dtype}")
         h, w = int(image.shape[0]), int(image.shape[1])
-        new_h, new_w, top, left = resize_geometry(h, w, self.size, self.crop)
+        new_h, new_w, top, left = (self.size, self.size, 0, 0) if self.square else resize_geometry(h, w, self.size, self.crop)
         kh, bh, ch, _ = self._tables(w, new_w)
         kv, bv, cv, bv_host = self._tables(h, new_h)
         row0 = int(bv_host[top, 0])
