@@ -279,6 +279,7 @@ def main():
     ap.add_argument("--config4", action="store_true", help="LLaVA-Next-Mistral-7B shapes, DDPO (BASELINE.json configs[3])")
     ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
     ap.add_argument("--qwen", action="store_true", help="only the Qwen-VL + LoRA fixtures (g9_*)")
+    ap.add_argument("--xc2", action="store_true", help="only the InternLM-XComposer2 + PLoRA/LoRA fixtures (g10_*)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -302,6 +303,9 @@ def main():
         return
     if args.qwen:
         g9_qwen()
+        return
+    if args.xc2:
+        g10_xc2()
         return
     g1_logps()
     g2_loss()
@@ -429,6 +433,131 @@ def g9_qwen():
             out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
         np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
         print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "sigmoid_losses"}, flush=True)
+
+
+class _LoraOverPLoRA(torch.nn.Module):
+    """peft lora.Linear over the reference's PLoRA module: result = base_layer(x, im_mask) + lora_B(lora_A(x)) * scaling."""
+
+    def __init__(self, base, A, B, scaling):
+        super().__init__()
+        self.base, self.scaling = base, scaling
+        self.A, self.B = torch.nn.Parameter(A.clone()), torch.nn.Parameter(B.clone())
+
+    def forward(self, x, im_mask=None):
+        return self.base(x, im_mask) + torch.nn.functional.linear(torch.nn.functional.linear(x, self.A), self.B) * self.scaling
+
+
+def build_reference_xc2(xcfg, base_w):
+    """The reference's InternLMXC2ForRL (models/InternLMXC2) on a small config.  Its constructor hard-codes the CLIP-L/336
+    tower (downloaded) and the 1024->4096 projector; same-structure small builders are patched in (build_mlp.py:6-28,37-91),
+    everything that runs in forward is the reference's code."""
+    ref_shim.install()
+    import torch.nn as nn
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from vlrlhf.models.InternLMXC2.configuration_internlm_xcomposer2 import InternLMXcomposer2Config
+    import vlrlhf.models.InternLMXC2.modeling_internlm_xcomposer2 as M
+    import vlrlhf.models.InternLMXC2.modeling_internlm2 as M2
+    import vlrlhf.models.InternLMXC2.build_mlp as BM
+    # the reference hard-codes PLoRA(r=256, alpha=256) in the attention / MLP constructors: scale the rank with the config
+    orig_plora_init = BM.PLoRA.__init__
+
+    def plora_init(self, *a, lora_r=8, lora_alpha=16, **k):
+        orig_plora_init(self, *a, lora_r=xcfg.plora_r, lora_alpha=xcfg.plora_alpha, **{**k, "lora_dropout": 0.0})
+    BM.PLoRA.__init__ = plora_init
+
+    class Tower(nn.Module):
+        def __init__(self):
+            super().__init__()
+            vc = CLIPVisionConfig(hidden_size=xcfg.v_hidden, intermediate_size=xcfg.v_ff, num_hidden_layers=xcfg.v_layers,
+                                  num_attention_heads=xcfg.v_heads, image_size=xcfg.image_size, patch_size=xcfg.patch_size,
+                                  hidden_act="quick_gelu", layer_norm_eps=xcfg.v_eps, projection_dim=xcfg.v_hidden)
+            vc._attn_implementation = "eager"
+            self.vision_tower = CLIPVisionModel(vc)
+            self.select_layer, self.select_feature, self.is_loaded = -1, "patch", True
+        feature_select = BM.CLIPVisionTower.feature_select
+        forward = BM.CLIPVisionTower.forward
+        dtype = property(lambda self: self.vision_tower.dtype)
+        device = property(lambda self: self.vision_tower.device)
+
+    M.build_vision_tower = lambda: Tower()
+    M.build_vision_projector = lambda: nn.Sequential(nn.Linear(xcfg.v_hidden, xcfg.hidden), nn.GELU(),
+                                                     nn.Linear(xcfg.hidden, xcfg.hidden))
+    c = InternLMXcomposer2Config(vocab_size=xcfg.vocab, hidden_size=xcfg.hidden, intermediate_size=xcfg.ff,
+                                 num_hidden_layers=xcfg.layers, num_attention_heads=xcfg.heads,
+                                 num_key_value_heads=xcfg.kv_heads, rms_norm_eps=xcfg.rms_eps, rope_theta=xcfg.rope_theta,
+                                 max_position_embeddings=4096, bias=False, pad_token_id=xcfg.pad_token_id)
+    c._attn_implementation = "eager"
+    c.rope_scaling = None       # transformers 5.x rewrites rope_scaling into {"rope_type": ...}; 4.x default is None
+    c.max_length = 4096
+    c.img_size = xcfg.image_size
+    c.image_token_index, c.ignore_index = xcfg.image_token_index, xcfg.ignore_index
+    from vlrlhf.models.InternLMXC2 import InternLMXC2ForRL
+    m = InternLMXC2ForRL(c)
+    BM.PLoRA.__init__ = orig_plora_init
+    sd = m.state_dict()
+    missing = [k for k in base_w if k not in sd]
+    assert not missing, missing[:5]
+    with torch.no_grad():
+        for k, v in base_w.items():
+            assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+            sd[k].copy_(v)
+        for k in sd:
+            if k not in base_w:
+                assert "post_layernorm" in k or "position_ids" in k, k
+                if "post_layernorm" in k:
+                    sd[k].fill_(1.0 if k.endswith("weight") else 0.0)
+    emb = m.vit.vision_tower.vision_model.embeddings
+    emb.position_ids = torch.arange(emb.num_positions).expand((1, -1))
+    m.eval()
+    return m
+
+
+def g10_xc2():
+    """InternLM-XComposer2-VL + PLoRA + LoRA (BASELINE.json configs[4] at parity size): policy = adapters on, reference =
+    adapters off (the frozen PLoRA image-token adapters stay on in both), DPO / DDPO / KTO-pair losses on top."""
+    from oracle import xc2_restate as X
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    for tag, xcfg, n_pairs, text_len, prompt_len in (("g10_xc2_tiny", X.TINY_XC2, 2, 24, 8), ("g10_xc2_small", X.SMALL_XC2, 2, 96, 24)):
+        seed = 0
+        base_w, lora_w = X.make_weights(xcfg, seed)
+        m = build_reference_xc2(xcfg, base_w)
+        batch = R.make_batch(xcfg, n_pairs, text_len, prompt_len, seed, ddpo_like=True)
+        cb = R.concatenated_inputs(batch, -100, 0)
+        out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
+        res = {}
+        for who in ("ref", "policy"):
+            if who == "policy":
+                for i, layer in enumerate(m.model.layers):
+                    for lin in X.LINEARS:
+                        parent = layer.attention if lin.startswith("attention.") else layer.feed_forward
+                        name = lin.split(".")[1]
+                        setattr(parent, name, _LoraOverPLoRA(getattr(parent, name), lora_w[f"model.layers.{i}.{lin}.lora_A"],
+                                                             lora_w[f"model.layers.{i}.{lin}.lora_B"], xcfg.lora_scale))
+            with torch.no_grad():
+                o = m(input_ids=cb["concatenated_input_ids"], attention_mask=cb["concatenated_attention_mask"],
+                      labels=cb["concatenated_labels"], use_cache=False, return_dict=True,
+                      **cb["concatenated_img_input_dict"])
+            logits = o.logits.float()
+            for lt in ("sigmoid", "ddpo"):
+                lp = VLDPOTrainer.get_batch_logps(logits, o.labels, average_log_prob=False, is_encoder_decoder=False,
+                                                  label_pad_token_id=-100, mask_shared_tokens=(lt == "ddpo"))
+                res[who + ("_ddpo" if lt == "ddpo" else "")] = lp
+                out[f"{who}_logps" + ("_ddpo" if lt == "ddpo" else "")] = lp.numpy()
+            if who == "policy":
+                out["labels"] = o.labels.numpy()
+                out["image_position_map"] = o.image_position_map.numpy()
+                out["policy_logits_mean_chosen"] = logits[:n_pairs].mean().numpy()
+                out["policy_logits_mean_rejected"] = logits[n_pairs:].mean().numpy()
+                if logits.numel() < 2_000_000:
+                    out["policy_logits"] = logits.numpy()
+        n = n_pairs
+        for lt in ("sigmoid", "ipo", "hinge", "kto_pair", "ddpo"):
+            sfx = "_ddpo" if lt == "ddpo" else ""
+            pl, rl = res["policy" + sfx], res["ref" + sfx]
+            l, c, r = ref_dpo_loss(pl[:n], pl[n:], rl[:n], rl[n:], 0.1, 0.0, lt)
+            out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
+        np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
+        print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "kto_pair_losses"}, flush=True)
 
 
 def g6_next():
