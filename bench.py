@@ -229,10 +229,11 @@ def run_b200(args):
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import config, engine, host, ops, synthetic
     cfg = {"7b": config.LLAVA15_7B, "small": config.SMALL, "tiny": config.TINY, "next7b": config.LLAVANEXT_MISTRAL_7B,
-           "next_small": config.SMALL_NEXT, "qwen7b": config.QWEN_VL_CHAT, "qwen_small": config.SMALL_QWEN}[args.model]
+           "next_small": config.SMALL_NEXT, "qwen7b": config.QWEN_VL_CHAT, "qwen_small": config.SMALL_QWEN, "xc2_7b": config.XC2_VL_7B,
+           "xc2_small": config.SMALL_XC2}[args.model]
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
     is_next = cfg.family == "llava_next"
-    if cfg.family == "qwen_vl":
+    if cfg.family in ("qwen_vl", "xc2"):
         return run_b200_qwen(args, cfg, world, rank, local)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
@@ -336,12 +337,21 @@ def run_b200_qwen(args, cfg, world, rank, local):
     import torch
     import torch.distributed as dist
     import vlrlhf_b200  # noqa: F401
-    from vlrlhf_b200 import config, engine_qwen, host, ops, synthetic
-    full = args.model == "qwen7b"
-    text_len, prompt_len = (1024, 320) if full else (128, 72)
-    eng = engine_qwen.QwenVLDPOEngine(cfg, config.TrainConfig(loss_type=args.loss_type, learning_rate=1e-5, weight_decay=0.05))
-    eng.init_synthetic(0)
-    batch = synthetic.make_qwen_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
+    from vlrlhf_b200 import config, engine_qwen, engine_xc2, host, ops, synthetic
+    full = args.model in ("qwen7b", "xc2_7b")
+    is_xc2 = cfg.family == "xc2"
+    if is_xc2:  # configs[4]: KTO-pair, text 1024 + 1225 image tokens (490 px) = 2248 merged
+        text_len, prompt_len = (1024, 32) if full else (96, 24)
+        loss_type = "kto_pair" if args.loss_type == "sigmoid" else args.loss_type
+        eng = engine_xc2.XC2DPOEngine(cfg, config.TrainConfig(loss_type=loss_type, learning_rate=1e-5, weight_decay=0.1))
+        eng.init_synthetic(0)
+        batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
+        args.loss_type = loss_type
+    else:
+        text_len, prompt_len = (1024, 320) if full else (128, 72)
+        eng = engine_qwen.QwenVLDPOEngine(cfg, config.TrainConfig(loss_type=args.loss_type, learning_rate=1e-5, weight_decay=0.05))
+        eng.init_synthetic(0)
+        batch = synthetic.make_qwen_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
     cb = host.concatenated_inputs(batch)
     ids_h, am_h, lb_h = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
     wt_h = eng.ddpo_weights(ids_h, am_h, lb_h) if args.loss_type == "ddpo" else None
@@ -376,6 +386,8 @@ def run_b200_qwen(args, cfg, world, rank, local):
     launches = ops.launch_count() - n0
     ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
     clocks = sampler.stop() if sampler else None
+    if is_xc2:
+        return _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, last, text_len, batch, ids_h, am_h, lb_h)
     # algorithmic FLOPs: LM forward x3 (policy fwd, reference fwd, dgrad-only backward) per sequence, adapters, tower once/pair
     d, ff, L, S, r = cfg.hidden, cfg.ff, cfg.layers, text_len, cfg.lora_r
     p_layer = 3 * d * d + d * d + 3 * d * ff
@@ -409,13 +421,51 @@ def run_b200_qwen(args, cfg, world, rank, local):
         dist.destroy_process_group()
 
 
+def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, last, text_len, batch, ids_h, am_h, lb_h):
+    import torch.distributed as dist
+    d, ff, L, r, pr, P = cfg.hidden, cfg.ff, cfg.layers, cfg.lora_r, cfg.plora_r, cfg.n_patches
+    S = text_len - 1 + P
+    hd, kvd = cfg.heads * cfg.head_dim, cfg.kv_heads * cfg.head_dim
+    p_layer = cfg.qkv_dim * d + d * hd + 3 * d * ff
+    lin_seq, attn_seq = S * 2 * p_layer * L, L * 2 * S * S * d
+    lora_seq = S * 2 * L * r * ((d + cfg.qkv_dim) + (hd + d) + 2 * (d + ff) + (ff + d))
+    plora_seq = P * 2 * L * pr * ((d + cfg.qkv_dim) + (hd + d) + 2 * (d + ff) + (ff + d))   # image rows only, frozen
+    per_seq = 3 * (lin_seq + plora_seq) + 4 * attn_seq + 3 * lora_seq
+    rows_lm = 2 * PAIRS_PER_GPU * (text_len - 1)
+    dv, Sv = cfg.v_hidden, P + 1
+    vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + P * 2 * cfg.patch_k * dv
+    proj = P * 2 * (dv * d + d * d) * 2
+    flops = PAIRS_PER_GPU * (2 * per_seq + vit + proj) + rows_lm * 2 * d * cfg.vocab * 3
+    pk, pk_src = peaks()
+    if rank == 0:
+        pairs = PAIRS_PER_GPU * world
+        h2d = sum(int(t.numel() * t.element_size()) for t in (ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"]))
+        line = {"metric": METRIC, "value": pairs / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": ("InternLM-XComposer2-VL-7B KTO-pair bf16 (configs[4], side measurement), LoRA r=64 on wqkv/wo/"
+                                        "w1/w2/w3 + frozen partial-LoRA r=256 on the image rows, frozen CLIP-L/490 + projector, "
+                                        "4 pairs/GPU, text 1024 (2248 merged), 1x490px image/pair") if args.model == "xc2_7b"
+                           else f"{args.model} (dev config, NOT the benchmark)",
+                           "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": args.loss_type,
+                           "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
+                           "step_tflop_algorithmic": flops / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                        "ms_per_step": ms_e2e, "last_metrics": last},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small"],
+    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small", "xc2_7b", "xc2_small"],
                     help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO, qwen7b = configs[2] Qwen-VL-Chat LoRA (side measurements)")
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")

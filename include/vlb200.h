@@ -153,6 +153,10 @@ int vlb200_gather_rows(const void* src, int64_t ld_src, const int* index, void* 
                        void* stream);
 int vlb200_scatter_rows(const void* src, int64_t ld_src, const int* index, void* dst, int64_t ld_dst, int n, int cols,
                         void* stream);
+/* dst[index[i], :] += scale * src[i, :] (index unique, < 0 skipped; dst bf16 or fp32): InternLM-XComposer2's partial LoRA
+ * `res[im_mask] += Plora_B(Plora_A(x[im_mask])) * scaling` (models/InternLMXC2/build_mlp.py:194-203) on gathered image rows */
+int vlb200_scatter_add_rows(const void* src, int64_t ld_src, const int* index, void* dst, int dst_dtype, int64_t ld_dst, int n,
+                            int cols, float scale, void* stream);
 int vlb200_memset_zero(void* dst, uint64_t bytes, void* stream);
 
 /* ---- LLaVA text/image merge (K7+K8) -- models/Llava/__init__.py:36-109 ---------------------

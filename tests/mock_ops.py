@@ -269,6 +269,14 @@ def scatter_rows(src, index, out):
     return out
 
 
+def scatter_add_rows(src, index, out, scale=1.0):
+    idx = index.long()
+    ok = idx >= 0
+    out[idx[ok]] = (out[idx[ok]].float() + scale * src[ok].float()).to(out.dtype)
+    _c()
+    return out
+
+
 def zero_(t):
     t.zero_()
     return t

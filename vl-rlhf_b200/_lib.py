@@ -46,6 +46,7 @@ SIGNATURES = {
                                  c_void_p]),
     "vlb200_gather_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "vlb200_scatter_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vlb200_scatter_add_rows": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
     "vlb200_memset_zero": (c_int, [c_void_p, c_uint64, c_void_p]),
     "vlb200_llava_merge_index": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

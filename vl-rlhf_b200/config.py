@@ -297,3 +297,76 @@ def qwen_lora_specs(cfg: QwenModelConfig) -> List[Tuple[str, Tuple[int, ...], fl
         for t in QWEN_LORA_TARGETS:
             s += [(f"transformer.h.{i}.{t}.lora_A", (r, d), a, 0.0), (f"transformer.h.{i}.{t}.lora_B", (outs[t], r), a, 0.0)]
     return s
+
+
+# ------------------------------------------------------------------------------------------------
+# InternLM-XComposer2-VL (BASELINE.json configs[4]): CLIP-L/14 at 490 px (35x35 patches, last layer),
+# Linear-GELU-Linear projector, InternLM2-7B (GQA 32/8) whose every linear carries a frozen partial-LoRA (r 256) on the
+# image rows; training adapts peft LoRA r 64 on attention.wqkv/wo and feed_forward.w1/w2/w3 (scripts/dpo_internlmxc2vl7b.sh).
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class XC2ModelConfig(ModelConfig):
+    plora_r: int = 256
+    plora_alpha: float = 256.0
+    lora_r: int = 64
+    lora_alpha: float = 64.0
+
+    @property
+    def plora_scale(self) -> float:
+        return self.plora_alpha / self.plora_r
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_r
+
+
+XC2_VL_7B = XC2ModelConfig(image_size=490, vision_feature_layer=-1, hidden=4096, layers=32, heads=32, kv_heads=8, ff=14336,
+                           vocab=92544, rms_eps=1e-5, rope_theta=1e6, image_token_index=92543, pad_token_id=2, family="xc2")
+TINY_XC2 = XC2ModelConfig(image_size=70, patch_size=14, v_hidden=128, v_layers=2, v_heads=2, v_ff=256, vision_feature_layer=-1,
+                          hidden=256, layers=2, heads=4, kv_heads=2, ff=512, vocab=512, rms_eps=1e-5, rope_theta=1e6,
+                          image_token_index=500, pad_token_id=2, family="xc2", plora_r=32, plora_alpha=32.0, lora_r=16,
+                          lora_alpha=16.0)
+SMALL_XC2 = XC2ModelConfig(image_size=112, patch_size=14, v_hidden=256, v_layers=2, v_heads=4, v_ff=512,
+                           vision_feature_layer=-1, hidden=512, layers=2, heads=4, kv_heads=2, ff=1024, vocab=2048,
+                           rms_eps=1e-5, rope_theta=1e6, image_token_index=2000, pad_token_id=2, family="xc2", plora_r=64,
+                           plora_alpha=64.0, lora_r=16, lora_alpha=16.0)
+XC2_LINEARS = ("attention.wqkv", "attention.wo", "feed_forward.w1", "feed_forward.w3", "feed_forward.w2")
+
+
+def xc2_linear_dims(cfg: XC2ModelConfig):
+    d, dh = cfg.hidden, cfg.head_dim
+    return {"attention.wqkv": ((cfg.heads + 2 * cfg.kv_heads) * dh, d), "attention.wo": (d, cfg.heads * dh),
+            "feed_forward.w1": (cfg.ff, d), "feed_forward.w3": (cfg.ff, d), "feed_forward.w2": (d, cfg.ff)}
+
+
+def xc2_weight_specs(cfg: XC2ModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    a = 0.02 * math.sqrt(3.0)
+    s: List[Tuple[str, Tuple[int, ...], float, float]] = []
+    for name, shape, scale, shift in weight_specs(cfg):
+        if name.startswith("vision_tower.vision_model."):
+            s.append(("vit." + name, shape, scale, shift))
+    s += [("vision_proj.0.weight", (cfg.hidden, cfg.v_hidden), a, 0.0), ("vision_proj.0.bias", (cfg.hidden,), 0.02, 0.0),
+          ("vision_proj.2.weight", (cfg.hidden, cfg.hidden), a, 0.0), ("vision_proj.2.bias", (cfg.hidden,), 0.02, 0.0),
+          ("model.tok_embeddings.weight", (cfg.vocab, cfg.hidden), a, 0.0)]
+    dims = xc2_linear_dims(cfg)
+    for i in range(cfg.layers):
+        p = f"model.layers.{i}."
+        s += [(p + "attention_norm.weight", (cfg.hidden,), 0.1, 1.0), (p + "ffn_norm.weight", (cfg.hidden,), 0.1, 1.0)]
+        for lin in XC2_LINEARS:
+            out, inn = dims[lin]
+            s += [(p + lin + ".weight", (out, inn), a, 0.0), (p + lin + ".Plora_A.weight", (cfg.plora_r, inn), a, 0.0),
+                  (p + lin + ".Plora_B.weight", (out, cfg.plora_r), a, 0.0)]
+    s += [("model.norm.weight", (cfg.hidden,), 0.1, 1.0), ("output.weight", (cfg.vocab, cfg.hidden), 3.0 * a, 0.0)]
+    return s
+
+
+def xc2_lora_specs(cfg: XC2ModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    a = 0.02 * math.sqrt(3.0)
+    dims = xc2_linear_dims(cfg)
+    s = []
+    for i in range(cfg.layers):
+        for lin in XC2_LINEARS:
+            out, inn = dims[lin]
+            s += [(f"model.layers.{i}.{lin}.lora_A", (cfg.lora_r, inn), a, 0.0),
+                  (f"model.layers.{i}.{lin}.lora_B", (out, cfg.lora_r), a, 0.0)]
+    return s

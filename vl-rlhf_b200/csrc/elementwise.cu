@@ -195,6 +195,36 @@ __global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, long 
         if (s >= 0) *reinterpret_cast<uint4*>(dst + (size_t)s * ldd + c * 8) = *reinterpret_cast<const uint4*>(src + i * lds + c * 8);
     }
 }
+// dst[idx[i], :] += scale * src[i, :]   (idx unique -> no atomics; idx < 0 skipped): the partial-LoRA update of
+// InternLM-XComposer2 (build_mlp.py:194-203: res[im_mask] += Plora_B(Plora_A(x[im_mask])) * scaling)
+template <typename DT>
+__global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, const int* __restrict__ idx,
+                                        DT* __restrict__ dst, long long ldd, int n, int cols, float scale) {
+    const int chunks = cols >> 3;
+    const size_t total = (size_t)n * chunks;
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(w % chunks);
+        const size_t i = w / chunks;
+        const int s = idx[i];
+        if (s < 0) continue;
+        float a[8];
+        unpack8e(*reinterpret_cast<const uint4*>(src + i * lds + c * 8), a);
+        DT* d = dst + (size_t)s * ldd + c * 8;
+        if constexpr (sizeof(DT) == 2) {
+            float b[8];
+            unpack8e(*reinterpret_cast<const uint4*>(d), b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] += scale * a[j];
+            *reinterpret_cast<uint4*>(d) = pack8e(b);
+        } else {
+            float4 lo = *reinterpret_cast<const float4*>(d), hi = *reinterpret_cast<const float4*>(d + 4);
+            lo.x += scale * a[0]; lo.y += scale * a[1]; lo.z += scale * a[2]; lo.w += scale * a[3];
+            hi.x += scale * a[4]; hi.y += scale * a[5]; hi.z += scale * a[6]; hi.w += scale * a[7];
+            *reinterpret_cast<float4*>(d) = lo;
+            *reinterpret_cast<float4*>(d + 4) = hi;
+        }
+    }
+}
 
 // ---------------------------------------------------------------- LLaVA merge index (Llava/__init__.py:36-109)
 // One thread per sequence scans its L text tokens (integer work, ~L iterations).  Requires every sequence
@@ -653,6 +683,19 @@ extern "C" int vlb200_scatter_rows(const void* src, int64_t ld_src, const int* i
     VLB_REQUIRE(src && index && dst && cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0, "scatter_rows: alignment");
     if (n <= 0) return VLB200_OK;
     scatter_rows_kernel<<<grid_for((size_t)n * (cols / 8), 256), 256, 0, as_stream(stream)>>>(CBF(src), ld_src, index, BF(dst), ld_dst, n, cols);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+extern "C" int vlb200_scatter_add_rows(const void* src, int64_t ld_src, const int* index, void* dst, int dst_dtype, int64_t ld_dst,
+                                       int n, int cols, float scale, void* stream) {
+    VLB_REQUIRE(src && index && dst && cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0, "scatter_add_rows: alignment");
+    VLB_REQUIRE(dst_dtype == VLB200_BF16 || dst_dtype == VLB200_F32, "scatter_add_rows: bad dst dtype");
+    if (n <= 0) return VLB200_OK;
+    if (dst_dtype == VLB200_F32)
+        scatter_add_rows_kernel<float><<<grid_for((size_t)n * (cols / 8), 256), 256, 0, as_stream(stream)>>>(CBF(src), ld_src, index, (float*)dst, ld_dst, n, cols, scale);
+    else
+        scatter_add_rows_kernel<__nv_bfloat16><<<grid_for((size_t)n * (cols / 8), 256), 256, 0, as_stream(stream)>>>(CBF(src), ld_src, index, BF(dst), ld_dst, n, cols, scale);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;

@@ -278,6 +278,14 @@ def scatter_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor):
     return out
 
 
+def scatter_add_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    """out[index[i], :] += scale * src[i, :]  (unique rows; out bf16 or fp32, may be a column slice)"""
+    assert index.dtype == torch.int32 and src.dtype == torch.bfloat16 and src.shape[0] == index.numel()
+    check(_L.vlb200_scatter_add_rows(_ptr(src), _rowmajor_ld(src), _ptr(index), _ptr(out), _dt(out), _rowmajor_ld(out),
+                                     index.numel(), src.shape[1], float(scale), _stream()))
+    return out
+
+
 def zero_(t: torch.Tensor):
     assert t.is_contiguous()
     check(_L.vlb200_memset_zero(_ptr(t), t.numel() * t.element_size(), _stream()))
