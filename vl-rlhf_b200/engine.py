@@ -16,7 +16,7 @@ full-vocab logits are computed only for rows that can carry a label, the discard
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 

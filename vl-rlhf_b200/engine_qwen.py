@@ -24,15 +24,13 @@ What is different from the LLaVA engine:
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 
 from . import ops
-from .config import QWEN_LORA_TARGETS, QwenModelConfig, TrainConfig, qwen_lora_specs, qwen_weight_specs, tensor_seed
+from .config import QwenModelConfig, qwen_lora_specs, qwen_weight_specs, tensor_seed
 from .engine import Arena, LlavaDPOEngine, Weights
-
-_T2K = {"attn.c_attn": "qkv", "attn.c_proj": "o", "mlp.w1": "w1", "mlp.w2": "w2"}
 
 
 def _lora_layout(cfg: QwenModelConfig) -> Arena:
