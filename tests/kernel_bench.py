@@ -104,6 +104,11 @@ def main():
     bw_case("rmsnorm fwd", lambda: ops.rmsnorm_fwd(x, w, 1e-5, out=y, rstd=rstd), 2 * T * d * 2)
     dw = torch.zeros(d, dtype=bf, device=dev)
     bw_case("rmsnorm bwd (+dres)", lambda: ops.rmsnorm_bwd(y, x, w, rstd, dw, dres=x, out=y), 4 * T * d * 2)
+    x32 = x.float()
+    y2 = torch.empty_like(x)
+    bw_case("rmsnorm fwd (fp32 x)", lambda: ops.rmsnorm_fwd(x32, w, 1e-5, out=y, rstd=rstd), T * d * 6)
+    bw_case("rmsnorm bwd (fp32 x,+dres)", lambda: ops.rmsnorm_bwd(y, x32, w, rstd, dw, dres=x, out=y2), T * d * 10)
+    del x32, y2
     gu = torch.randn(T, 2 * ff, device=dev).to(bf)
     a2 = torch.empty(T, ff, dtype=bf, device=dev)
     bw_case("swiglu fwd", lambda: ops.swiglu_fwd(gu, a2), 3 * T * ff * 2)

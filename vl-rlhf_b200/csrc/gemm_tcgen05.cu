@@ -678,8 +678,9 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     p.residual_f32 = residual_dtype == VLB200_F32;
     p.ldr = ldr;
     p.accumulate = accumulate;
-    {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group
-        const double budget = 32.0 * 1024 * 1024;
+    {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group (VLB200_RASTER_MB overrides)
+        static const double budget_mb = [] { const char* e = getenv("VLB200_RASTER_MB"); return e ? atof(e) : 32.0; }();
+        const double budget = budget_mb * 1024 * 1024;
         const double a_blk = (double)TM * K * 2, b_blk = (double)TN * K * 2;
         const double a_bytes = (double)M * K * 2, b_bytes = (double)N * K * 2;
         int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;

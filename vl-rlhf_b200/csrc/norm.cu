@@ -93,32 +93,39 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const XT* __restrict__ 
     __shared__ float sm[4];
     const int nvec = cols >> 3;
     float dw[VPT][8];
-    float wv[VPT][8];
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
-        const int i = threadIdx.x + k * NORM_THREADS;
 #pragma unroll
         for (int j = 0; j < 8; ++j) dw[k][j] = 0.f;
-        if (i < nvec) unpack8(*reinterpret_cast<const uint4*>(w + (size_t)i * 8), wv[k]);
     }
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const float rstd = rstd_in[row];
         const size_t off = (size_t)row * cols;
+        // every global load of the row is issued before the block reduction: x, dy and the residual gradient are all in
+        // flight together (the weight vector is re-read through L1 instead of living in 32 registers per thread)
         float xs[VPT][8];
-        uint4 gv[VPT];
-        float dot = 0.f;
+        uint4 gv[VPT], rv[VPT];
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
             const int i = threadIdx.x + k * NORM_THREADS;
             if (i < nvec) {
                 load8<XT>(x + off + (size_t)i * 8, xs[k]);
-                gv[k] = *reinterpret_cast<const uint4*>(dy + off + (size_t)i * 8);
-                float gf[8];
+                gv[k] = ld_nc_v4(dy + off + (size_t)i * 8);
+                if (dres) rv[k] = ld_nc_v4(dres + off + (size_t)i * 8);
+            }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int i = threadIdx.x + k * NORM_THREADS;
+            if (i < nvec) {
+                float gf[8], wv[8];
                 unpack8(gv[k], gf);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(w + (size_t)i * 8)), wv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float xh = xs[k][j] * rstd;
-                    dot += wv[k][j] * gf[j] * xh;
+                    dot += wv[j] * gf[j] * xh;
                     dw[k][j] += gf[j] * xh;
                 }
             }
@@ -128,13 +135,14 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const XT* __restrict__ 
         for (int k = 0; k < VPT; ++k) {
             const int i = threadIdx.x + k * NORM_THREADS;
             if (i < nvec) {
-                float gf[8], o[8];
+                float gf[8], wv[8], o[8];
                 unpack8(gv[k], gf);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(w + (size_t)i * 8)), wv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rstd * (wv[k][j] * gf[j] - xs[k][j] * rstd * dot);
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (wv[j] * gf[j] - xs[k][j] * rstd * dot);
                 if (dres) {
                     float rf[8];
-                    unpack8(*reinterpret_cast<const uint4*>(dres + off + (size_t)i * 8), rf);
+                    unpack8(rv[k], rf);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] += rf[j];
                 }
@@ -153,24 +161,49 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const XT* __restrict__ 
     }
 }
 
-// out[c] (bf16) (+)= sum_p partial[p, c]
-__global__ void colsum_partials_kernel(const float* __restrict__ partial, int nparts, int cols,
-                                       __nv_bfloat16* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum_p partial[p, c]: 32 columns per CTA, the partials split over 8 warps (coalesced 128-byte rows, several
+// loads in flight per lane), then a shared-memory reduction over the warps.  Deterministic: fixed summation order.
+__device__ __forceinline__ float colsum_partials_body(const float* __restrict__ partial, int nparts, int cols, int& c) {
+    __shared__ float sm[8][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    c = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < cols) {
+        int p = wid;
+        for (; p + 24 < nparts; p += 32) {
+            s0 += partial[(size_t)p * cols + c];
+            s1 += partial[(size_t)(p + 8) * cols + c];
+            s2 += partial[(size_t)(p + 16) * cols + c];
+            s3 += partial[(size_t)(p + 24) * cols + c];
+        }
+        for (; p < nparts; p += 8) s0 += partial[(size_t)p * cols + c];
+    }
+    sm[wid][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * cols + c];
-    if (accumulate) s += __bfloat162float(out[c]);
-    out[c] = __float2bfloat16(s);
+    if (wid == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sm[w][lane];
+    }
+    return s;
+}
+// out[c] (bf16) (+)= sum_p partial[p, c]
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial, int nparts, int cols,
+                                                              __nv_bfloat16* __restrict__ out, int accumulate) {
+    int c;
+    float s = colsum_partials_body(partial, nparts, cols, c);
+    if (threadIdx.x < 32 && c < cols) {
+        if (accumulate) s += __bfloat162float(out[c]);
+        out[c] = __float2bfloat16(s);
+    }
 }
 
 // out[c] (f32) = sum_p partial[p, c]
-__global__ void colsum_partials_f32_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * cols + c];
-    out[c] = s;
+__global__ void __launch_bounds__(256) colsum_partials_f32_kernel(const float* __restrict__ partial, int nparts, int cols,
+                                                                  float* __restrict__ out) {
+    int c;
+    const float s = colsum_partials_body(partial, nparts, cols, c);
+    if (threadIdx.x < 32 && c < cols) out[c] = s;
 }
 // out[0] = scale * sum_i a[i] * b[i]   (single CTA; n is a hidden size)
 __global__ void __launch_bounds__(256) dot_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float scale,
@@ -302,7 +335,7 @@ extern "C" int vlb200_rmsnorm_bwd(const void* dy, const void* x, int x_dtype, co
     else VLB_RMS_BWD(8);
 #undef VLB_RMS_BWD
     VLB_LAUNCH_CHECK();
-    colsum_partials_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, grid, cols, (__nv_bfloat16*)dw, dw_accumulate);
+    colsum_partials_kernel<<<(cols + 31) / 32, 256, 0, s>>>(workspace, grid, cols, (__nv_bfloat16*)dw, dw_accumulate);
     count_launch(2);
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
@@ -318,7 +351,7 @@ extern "C" int vlb200_colsum(const void* a, int64_t lda, int rows, int cols, voi
     cudaStream_t s = as_stream(stream);
     colsum_rows_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, lda, rows, cols, workspace);
     VLB_LAUNCH_CHECK();
-    colsum_partials_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, gx, cols, (__nv_bfloat16*)out, accumulate);
+    colsum_partials_kernel<<<(cols + 31) / 32, 256, 0, s>>>(workspace, gx, cols, (__nv_bfloat16*)out, accumulate);
     count_launch(2);
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
@@ -349,7 +382,7 @@ extern "C" int vlb200_colsum_f32(const void* a, int64_t lda, int rows, int cols,
     cudaStream_t s = as_stream(stream);
     colsum_rows_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, lda, rows, cols, workspace);
     VLB_LAUNCH_CHECK();
-    colsum_partials_f32_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, gx, cols, out);
+    colsum_partials_f32_kernel<<<(cols + 31) / 32, 256, 0, s>>>(workspace, gx, cols, out);
     count_launch(2);
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
