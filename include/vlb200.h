@@ -248,8 +248,10 @@ int vlb200_cast_bf16_to_f32(const void* src, float* dst, uint64_t n, void* strea
  * stored float32 -> (x-mean)/std in float32 -> CHW.  image: device uint8 [in_h, in_w, 3] RGB (the decoded file).
  * coef_h/bounds_h ([new_w, ksize_h] int32, [new_w, 2] int32 = first tap, tap count) and coef_v/bounds_v
  * ([new_h, ksize_v], [new_h, 2]) are Pillow's 22-bit fixed-point resampling tables (Resample.c precompute_coeffs +
- * normalize_coeffs_8bpc), device-resident, built by vl-rlhf_b200/preprocess.py.  (top,left,crop_h,crop_w) is the
- * center crop inside the resized [new_h, new_w] image; only input rows [row0, row0+rows) feed it.  workspace holds the
+ * normalize_coeffs_8bpc), device-resident, built by vl-rlhf_b200/preprocess.py.  (top,left,crop_h,crop_w) is the output
+ * window in resized-image coordinates: the center crop for CLIP, one 336x336 cell of the zero-padded anyres canvas for
+ * LLaVA-Next (LlavaNextImageProcessor get_image_patches: top/left may be negative or reach past the resized image; pixels
+ * outside it are the canvas' uint8 zeros).  Only input rows [row0, row0+rows) feed the window (rows may be 0).  workspace holds the
  * uint8 result of the horizontal pass (rows*crop_w*3 bytes).  mean_std_host: 6 floats on the HOST (mean RGB, std RGB).
  * out: [3, crop_h, crop_w] VLB200_F32 (what the reference's collator emits) or VLB200_BF16 (its rounding).
  * Bit-exact with Pillow + numpy for uint8 input. */

@@ -138,6 +138,37 @@ def square_preprocess(img: np.ndarray, size: int = 448, mean: Sequence[float] = 
     return np.ascontiguousarray(x.transpose(2, 0, 1))
 
 
+def anyres_preprocess(img: np.ndarray, pinpoints, crop: int = 336, mean: Sequence[float] = OPENAI_CLIP_MEAN,
+                      std: Sequence[float] = OPENAI_CLIP_STD) -> np.ndarray:
+    """transformers-4.41 LlavaNextImageProcessor.preprocess for one image (what LlavaNextProcessor hands the reference's
+    collator, models/LlavaNext/__init__.py): select_best_resolution -> resize keeping the aspect ratio
+    (get_patch_output_size) -> zero-pad the uint8 canvas to the chosen pinpoint (centered) -> cut crop x crop cells
+    row-major; the base view is the whole image resized to crop x crop; every view is then rescaled and normalised.
+    [H, W, 3] uint8 -> [1 + cells, 3, crop, crop] float32."""
+    from .restate import select_best_resolution
+    h, w = img.shape[:2]
+    th, tw = select_best_resolution((h, w), [tuple(p) for p in pinpoints])
+    sw, sh = tw / w, th / h
+    if sw < sh:
+        nw, nh = tw, min(math.ceil(h * sw), th)
+    else:
+        nh, nw = th, min(math.ceil(w * sh), tw)
+    resized = pil_bicubic_resize_u8(img, (nh, nw))
+    px, rx = divmod(tw - nw, 2)
+    py, ry = divmod(th - nh, 2)
+    canvas = np.pad(resized, ((py, py + ry), (px, px + rx), (0, 0)), mode="constant", constant_values=0)
+    views = [pil_bicubic_resize_u8(img, (crop, crop))]
+    for r in range(0, th, crop):
+        for c in range(0, tw, crop):
+            views.append(canvas[r:r + crop, c:c + crop])
+    out = []
+    for v in views:
+        x = (v.astype(np.float64) * (1 / 255)).astype(np.float32)
+        x = (x - np.array(mean, dtype=np.float32)) / np.array(std, dtype=np.float32)
+        out.append(x.transpose(2, 0, 1))
+    return np.ascontiguousarray(np.stack(out))
+
+
 # ---- seeded synthetic RGB images shared by the fixture generator (make_fixtures.py --preprocess) and the tests
 def synthetic_image(h: int, w: int, seed: int) -> np.ndarray:
     """[h, w, 3] uint8: smooth colour waves + noise + hard edges (exercises the negative bicubic lobes / clipping)."""

@@ -102,3 +102,22 @@ def test_square_transform_on_gpu(P):
         got = P.ClipPreprocessor(size=size, square=True)([img])[0].cpu().numpy()
         assert got.shape == (3, size, size)
         assert np.array_equal(got, IR.square_preprocess(img, size)), (size, h, w)
+
+
+def test_anyres_preprocessor_on_gpu(P):
+    """LLaVA-Next image processor on the GPU: base view + zero-padded canvas cells, bit-exact; ragged view counts are
+    zero-padded like _pad_for_batching; the crops drive the anyres engine path unchanged."""
+    pins = [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]
+    pre = P.AnyresPreprocessor(pins)
+    shapes = [(336, 336), (400, 640), (900, 300), (150, 1000), (50, 60), (1200, 1300)]
+    imgs = [IR.synthetic_image(h, w, s) for s, (h, w) in enumerate(shapes)]
+    out, sizes = pre(imgs)
+    assert sizes.tolist() == [list(s) for s in shapes]
+    for i, img in enumerate(imgs):
+        want = IR.anyres_preprocess(img, pins)
+        got = out[i, :want.shape[0]].cpu().numpy()
+        assert np.array_equal(got, want), (shapes[i], np.abs(got - want).max())
+        assert float(out[i, want.shape[0]:].abs().max()) == 0.0 if want.shape[0] < out.shape[1] else True
+    from vlrlhf_b200 import host
+    crops = [host.anyres_num_crops(s, pins, 336) for s in shapes]
+    assert crops == [IR.anyres_preprocess(im, pins).shape[0] for im in imgs]

@@ -70,3 +70,21 @@ def test_square_transform_matches_torchvision():
                         tv.Normalize(IR.OPENAI_CLIP_MEAN, IR.OPENAI_CLIP_STD)])
         want = t(Image.fromarray(img)).numpy()
         assert np.array_equal(IR.square_preprocess(img, size), want), (size, h, w)
+
+
+def test_anyres_oracle_matches_hf_llava_next_processor():
+    """oracle.anyres_preprocess == transformers' PIL-backend LlavaNextImageProcessor (the 4.41 slow processor's code path)
+    on square / wide / tall / tiny / huge images, bit for bit; image_sizes pass through."""
+    Image = pytest.importorskip("PIL.Image")
+    mod = pytest.importorskip("transformers.models.llava_next.image_processing_pil_llava_next")
+    pins = [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]
+    proc = mod.LlavaNextImageProcessorPil(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336},
+                                          image_grid_pinpoints=pins)
+    for seed, (h, w) in enumerate([(336, 336), (400, 640), (900, 300), (150, 1000), (50, 60), (1200, 1300), (672, 671)]):
+        img = IR.synthetic_image(h, w, seed)
+        o = proc(images=[Image.fromarray(img)], return_tensors="np")
+        want = o["pixel_values"][0]
+        got = IR.anyres_preprocess(img, pins)
+        assert got.shape == want.shape, (h, w, got.shape, want.shape)
+        assert np.array_equal(got, want), (h, w, np.abs(got - want).max())
+        assert tuple(o["image_sizes"][0]) == (h, w)

@@ -73,5 +73,9 @@ class B200DPODataCollatorWithPadding:
             if self.preprocessor is None:
                 raise RuntimeError("a preprocessor (vlrlhf_b200.preprocess.ClipPreprocessor) is required for images")
             images = [self.image_loader(p) for p in batch["img_path"]]
-            batch["img_input_dict"] = dict(pixel_values=self.preprocessor(images))
+            pv = self.preprocessor(images)
+            if isinstance(pv, tuple):  # LLaVA-Next: (pixel_values [B, views, 3, c, c], image_sizes [B, 2])
+                batch["img_input_dict"] = dict(pixel_values=pv[0], image_sizes=pv[1])
+            else:
+                batch["img_input_dict"] = dict(pixel_values=pv)
         return batch

@@ -124,3 +124,69 @@ class ClipPreprocessor:
         for i, im in enumerate(images):
             self.one(im, out[i])
         return out
+
+
+class AnyresPreprocessor:
+    """`LlavaNextImageProcessor` (transformers 4.41) for decoded RGB uint8 images on the GPU: the base view (whole image
+    resized to crop x crop) plus the crop x crop cells of the aspect-preserving resize pasted on the zero canvas of the best
+    pinpoint.  Each view is one `vlb200_clip_preprocess_u8` call with the view's window in resized-image coordinates
+    (negative / overshooting offsets read the canvas' zero padding).  -> (pixel_values [B, max_views, 3, c, c] zero padded
+    like `_pad_for_batching`, image_sizes [B, 2])."""
+
+    def __init__(self, pinpoints, crop: int = 336, image_mean: Sequence[float] = OPENAI_CLIP_MEAN,
+                 image_std: Sequence[float] = OPENAI_CLIP_STD, rescale_factor: float = 1 / 255, device: str = "cuda",
+                 out_dtype: torch.dtype = torch.float32):
+        self.pinpoints = [tuple(int(x) for x in p) for p in pinpoints]
+        self.inner = ClipPreprocessor(size=crop, crop=crop, image_mean=image_mean, image_std=image_std,
+                                      rescale_factor=rescale_factor, device=device, out_dtype=out_dtype, square=True)
+        self.crop = int(crop)
+
+    def geometry(self, h: int, w: int):
+        """-> (th, tw, nh, nw, py, px): pinpoint, aspect-preserving size inside it, paste offset."""
+        from .host import best_resolution
+        th, tw = best_resolution((h, w), self.pinpoints)
+        sw, sh = tw / w, th / h
+        if sw < sh:
+            nw, nh = tw, min(math.ceil(h * sw), th)
+        else:
+            nh, nw = th, min(math.ceil(w * sh), tw)
+        return th, tw, nh, nw, (th - nh) // 2, (tw - nw) // 2
+
+    def _window(self, img: torch.Tensor, nh: int, nw: int, top: int, left: int, out: torch.Tensor):
+        p, c = self.inner, self.crop
+        h, w = int(img.shape[0]), int(img.shape[1])
+        kh, bh, ch, _ = p._tables(w, nw)
+        kv, bv, cv, bv_host = p._tables(h, nh)
+        y0, y1 = max(top, 0), min(top + c, nh)  # resized rows the window touches
+        if y1 > y0:
+            row0 = int(bv_host[y0, 0])
+            rows = int(bv_host[y1 - 1, 0] + bv_host[y1 - 1, 1]) - row0
+        else:
+            row0, rows = 0, 0
+        need = max(rows * c * 3, 16)
+        if p._ws is None or p._ws.numel() < need:
+            p._ws = torch.empty(need, dtype=torch.uint8, device=p.device)
+        ops.clip_preprocess_u8(img, ch, bh, kh, cv, bv, kv, nh, nw, top, left, c, c, row0, rows, p._ws, p.rescale, p._mean_std, out)
+
+    def __call__(self, images: List[Union[np.ndarray, torch.Tensor]]):
+        c, dev = self.crop, self.inner.device
+        geo, views = [], []
+        for im in images:
+            h, w = int(im.shape[0]), int(im.shape[1])
+            g = self.geometry(h, w)
+            geo.append(g)
+            views.append(1 + (g[0] // c) * (g[1] // c))
+        out = torch.zeros(len(images), max(views), 3, c, c, dtype=self.inner.out_dtype, device=dev)
+        for i, im in enumerate(images):
+            if isinstance(im, np.ndarray):
+                im = torch.from_numpy(np.ascontiguousarray(im))
+            img = im.to(dev, non_blocking=True).contiguous()
+            th, tw, nh, nw, py, px = geo[i]
+            self._window(img, c, c, 0, 0, out[i, 0])  # base view: the whole image resized to c x c
+            k = 1
+            for r in range(0, th, c):
+                for col in range(0, tw, c):
+                    self._window(img, nh, nw, r - py, col - px, out[i, k])
+                    k += 1
+        sizes = torch.tensor([[int(im.shape[0]), int(im.shape[1])] for im in images], dtype=torch.int64)
+        return out, sizes
