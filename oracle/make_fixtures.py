@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
     ap.add_argument("--qwen", action="store_true", help="only the Qwen-VL + LoRA fixtures (g9_*)")
     ap.add_argument("--xc2", action="store_true", help="only the InternLM-XComposer2 + PLoRA/LoRA fixtures (g10_*)")
+    ap.add_argument("--lora", action="store_true", help="only the LLaVA / LLaVA-Next + LoRA fixtures (g11_*)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -306,6 +307,9 @@ def main():
         return
     if args.xc2:
         g10_xc2()
+        return
+    if args.lora:
+        g11_lora()
         return
     g1_logps()
     g2_loss()
@@ -558,6 +562,58 @@ def g10_xc2():
             out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
         np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
         print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "kto_pair_losses"}, flush=True)
+
+
+def g11_lora():
+    """LLaVA-1.5 / LLaVA-Next with peft-style LoRA on the decoder linears (what scripts/dpo_llava.sh, dpo_llavanext.sh,
+    kto_*.sh, ddpo_*.sh train): the reference's LlavaForRL / LlavaNextForRL with the adapters applied by hand (peft is not
+    installed; `_LoraLinear` = peft lora.Linear.forward) = policy, adapters off = reference (TRL's null_ref_context)."""
+    from oracle import lora_restate as LR
+    VLDPOTrainer, _, _ = ref_shim.reference_symbols()
+    cases = (("g11_lora_tiny", LR.TINY_LORA, 2, 24, 8, None), ("g11_lora_small", LR.SMALL_LORA, 2, 96, 24, None),
+             ("g11_next_lora_tiny", LR.TINY_NEXT_LORA, 3, 24, 8, [(28, 28), (20, 50), (60, 25)]),
+             ("g11_next_lora_small", LR.SMALL_NEXT_LORA, 2, 96, 24, [(112, 112), (90, 300)]))
+    for tag, cfg, n_pairs, text_len, prompt_len, image_sizes in cases:
+        seed = 0
+        base_w, lora_w = LR.make_weights(cfg, seed)
+        m = build_reference_model(cfg, base_w)
+        batch = R.make_batch(cfg, n_pairs, text_len, prompt_len, seed, ddpo_like=True, image_sizes=image_sizes)
+        cb = R.concatenated_inputs(batch, -100, 0)
+        out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}
+        if image_sizes is not None:
+            out["image_sizes"] = np.asarray(image_sizes, dtype=np.int64)
+        res = {}
+        for who in ("ref", "policy"):
+            if who == "policy":  # adapters on
+                for i, layer in enumerate(m.model.language_model.layers):
+                    for lin in LR.LINEARS:
+                        parent_name, name = lin.split(".")
+                        parent = getattr(layer, parent_name)
+                        key = f"language_model.model.layers.{i}.{lin}"
+                        setattr(parent, name, _LoraLinear(getattr(parent, name), lora_w[key + ".lora_A"],
+                                                          lora_w[key + ".lora_B"], cfg.lora_scale))
+            with torch.no_grad():
+                o = m(input_ids=cb["concatenated_input_ids"], attention_mask=cb["concatenated_attention_mask"],
+                      labels=cb["concatenated_labels"], use_cache=False, **cb["concatenated_img_input_dict"])
+            logits = o.logits.float()
+            for lt in ("sigmoid", "ddpo"):
+                lp = VLDPOTrainer.get_batch_logps(logits, o.labels, average_log_prob=False, is_encoder_decoder=False,
+                                                  label_pad_token_id=-100, mask_shared_tokens=(lt == "ddpo"))
+                res[who + ("_ddpo" if lt == "ddpo" else "")] = lp
+                out[f"{who}_logps" + ("_ddpo" if lt == "ddpo" else "")] = lp.numpy()
+            if who == "policy":
+                out["labels"] = o.labels.numpy()
+                out["image_position_map"] = o.image_position_map.numpy()
+                out["policy_logits_mean_chosen"] = logits[:n_pairs].mean().numpy()
+                out["policy_logits_mean_rejected"] = logits[n_pairs:].mean().numpy()
+        n = n_pairs
+        for lt in ("sigmoid", "ipo", "hinge", "kto_pair", "ddpo"):
+            sfx = "_ddpo" if lt == "ddpo" else ""
+            pl, rl = res["policy" + sfx], res["ref" + sfx]
+            l, c, r = ref_dpo_loss(pl[:n], pl[n:], rl[:n], rl[n:], 0.1, 0.0, lt)
+            out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
+        np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
+        print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "sigmoid_losses"}, flush=True)
 
 
 def g6_next():

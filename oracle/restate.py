@@ -501,9 +501,20 @@ def rotate_half(x):
     return torch.cat((-x2, x1), dim=-1)
 
 
+def lora_linear(x, w: Dict[str, torch.Tensor], module: str, lora: Optional[Dict[str, torch.Tensor]], scale: float):
+    """nn.Linear, or peft.tuners.lora.Linear.forward over it when `lora` holds `<module>.lora_A|lora_B` (peft is not on
+    disk; published algorithm): result = base(x) + lora_B(lora_A(dropout(x))) * scaling, dropout off (TRL's
+    disable_dropout, base/trainer.py:58)."""
+    y = F.linear(x, w[module + ".weight"])
+    if lora is not None and module + ".lora_A" in lora:
+        y = y + F.linear(F.linear(x, lora[module + ".lora_A"]), lora[module + ".lora_B"]) * scale
+    return y
+
+
 def llama_decoder(cfg: LlavaCfg, w: Dict[str, torch.Tensor], inputs_embeds, attention_mask, position_ids,
-                  return_hidden: bool = False):
+                  return_hidden: bool = False, lora: Optional[Dict[str, torch.Tensor]] = None, lora_scale: float = 1.0):
     B, S, _ = inputs_embeds.shape
+    lin = lambda x, module: lora_linear(x, w, module, lora, lora_scale)  # noqa: E731
     H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
     cos, sin = rope_cos_sin(cfg, position_ids)
     cos, sin = cos[:, None], sin[:, None]
@@ -516,9 +527,9 @@ def llama_decoder(cfg: LlavaCfg, w: Dict[str, torch.Tensor], inputs_embeds, atte
     for i in range(cfg.layers):
         p = f"language_model.model.layers.{i}."
         h = rms_norm(x, w[p + "input_layernorm.weight"], cfg.rms_eps)
-        q = F.linear(h, w[p + "self_attn.q_proj.weight"]).view(B, S, H, dh).transpose(1, 2)
-        k = F.linear(h, w[p + "self_attn.k_proj.weight"]).view(B, S, KV, dh).transpose(1, 2)
-        v = F.linear(h, w[p + "self_attn.v_proj.weight"]).view(B, S, KV, dh).transpose(1, 2)
+        q = lin(h, p + "self_attn.q_proj").view(B, S, H, dh).transpose(1, 2)
+        k = lin(h, p + "self_attn.k_proj").view(B, S, KV, dh).transpose(1, 2)
+        v = lin(h, p + "self_attn.v_proj").view(B, S, KV, dh).transpose(1, 2)
         q = q * cos + rotate_half(q) * sin
         k = k * cos + rotate_half(k) * sin
         if KV != H:
@@ -526,10 +537,10 @@ def llama_decoder(cfg: LlavaCfg, w: Dict[str, torch.Tensor], inputs_embeds, atte
             v = v.repeat_interleave(H // KV, dim=1)
         att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + bias, dim=-1)
         o = (att @ v).transpose(1, 2).reshape(B, S, H * dh)
-        x = x + F.linear(o, w[p + "self_attn.o_proj.weight"])
+        x = x + lin(o, p + "self_attn.o_proj")
         h = rms_norm(x, w[p + "post_attention_layernorm.weight"], cfg.rms_eps)
-        h = F.silu(F.linear(h, w[p + "mlp.gate_proj.weight"])) * F.linear(h, w[p + "mlp.up_proj.weight"])
-        x = x + F.linear(h, w[p + "mlp.down_proj.weight"])
+        h = F.silu(lin(h, p + "mlp.gate_proj")) * lin(h, p + "mlp.up_proj")
+        x = x + lin(h, p + "mlp.down_proj")
     x = rms_norm(x, w["language_model.model.norm.weight"], cfg.rms_eps)
     if return_hidden:
         return x
@@ -540,14 +551,15 @@ def llama_decoder(cfg: LlavaCfg, w: Dict[str, torch.Tensor], inputs_embeds, atte
 # models/Llava/__init__.py:111-271  LlavaForRL.forward (training branch: pixel_values given)
 # --------------------------------------------------------------------------------------
 
-def llava_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, attention_mask, labels, pixel_values):
+def llava_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, attention_mask, labels, pixel_values,
+                  lora: Optional[Dict[str, torch.Tensor]] = None, lora_scale: float = 1.0):
     """-> (logits fp32 [2B,S,V], labels [2B,S], image_position_map [2B,S])."""
     inputs_embeds = F.embedding(input_ids, w["language_model.model.embed_tokens.weight"])  # :174
     feats = clip_vision_features(cfg, w, pixel_values)[:, 1:]  # :178-183
     image_features = projector(cfg, w, feats)  # :191
     emb, mask, new_labels, pos, img_map = merge_input_ids_with_image_features(
         cfg, image_features, inputs_embeds, input_ids, attention_mask, labels)  # :192-196
-    logits = llama_decoder(cfg, w, emb, mask, pos)  # :232-243
+    logits = llama_decoder(cfg, w, emb, mask, pos, lora=lora, lora_scale=lora_scale)  # :232-243
     return logits, new_labels, img_map
 
 
@@ -675,7 +687,7 @@ def next_merge_input_ids_with_image_features(cfg: LlavaCfg, image_features, feat
 
 
 def llava_next_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, attention_mask, labels, pixel_values,
-                       image_sizes):
+                       image_sizes, lora: Optional[Dict[str, torch.Tensor]] = None, lora_scale: float = 1.0):
     """models/LlavaNext/__init__.py:173-345, training branch -> (logits, labels, image_position_map)."""
     ids0 = input_ids.clone()
     ids0[input_ids == cfg.image_token_index] = 0  # :203-205
@@ -691,14 +703,15 @@ def llava_next_forward(cfg: LlavaCfg, w: Dict[str, torch.Tensor], input_ids, att
     image_features, feature_lens = pack_image_features(cfg, list(image_features), image_sizes, w["image_newline"])
     emb, mask, new_labels, pos, img_map = next_merge_input_ids_with_image_features(
         cfg, image_features, feature_lens, inputs_embeds, input_ids, attention_mask, labels)  # :251-262
-    logits = llama_decoder(cfg, w, emb, mask, pos)
+    logits = llama_decoder(cfg, w, emb, mask, pos, lora=lora, lora_scale=lora_scale)
     return logits, new_labels, img_map
 
 
-def model_forward(cfg: LlavaCfg, w, input_ids, attention_mask, labels, **img):
+def model_forward(cfg: LlavaCfg, w, input_ids, attention_mask, labels, lora=None, lora_scale: float = 1.0, **img):
     if cfg.family == "llava_next":
-        return llava_next_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"], img["image_sizes"])
-    return llava_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"])
+        return llava_next_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"], img["image_sizes"],
+                                  lora=lora, lora_scale=lora_scale)
+    return llava_forward(cfg, w, input_ids, attention_mask, labels, img["pixel_values"], lora=lora, lora_scale=lora_scale)
 
 
 # --------------------------------------------------------------------------------------

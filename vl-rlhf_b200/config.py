@@ -370,3 +370,61 @@ def xc2_lora_specs(cfg: XC2ModelConfig) -> List[Tuple[str, Tuple[int, ...], floa
             s += [(f"model.layers.{i}.{lin}.lora_A", (cfg.lora_r, inn), a, 0.0),
                   (f"model.layers.{i}.{lin}.lora_B", (out, cfg.lora_r), a, 0.0)]
     return s
+
+
+# ------------------------------------------------------------------------------------------------
+# LLaVA-1.5 / LLaVA-Next with peft LoRA on the decoder linears -- what every reference launch script actually trains
+# (scripts/dpo_llava.sh:24-30, scripts/dpo_llavanext.sh:24-30, scripts/kto_llava.sh, scripts/ddpo_llava.sh:
+# `--use_lora True --lora_r 128 --lora_alpha 256 --lora_target_modules auto`).  "auto" resolves to the short names of
+# the language model's nn.Linear modules minus lm_head (models/Llava/__init__.py:273-286): q_proj, k_proj, v_proj,
+# o_proj, gate_proj, up_proj, down_proj.  (peft matches those suffixes wherever they occur, i.e. it would also wrap the
+# CLIP tower's q/k/v_proj; this build adapts the decoder only -- equivalent to spelling `--lora_target_modules` with
+# the language_model prefix -- and keeps the tower frozen like `--freeze_vision_tower True` intends.)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class LlavaLoRAModelConfig(ModelConfig):
+    lora_r: int = 128
+    lora_alpha: float = 256.0
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_r
+
+
+LLAVA_LORA_LINEARS = ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj",
+                      "mlp.up_proj", "mlp.down_proj")
+
+
+def with_lora(cfg: ModelConfig, r: int = 128, alpha: float = 256.0) -> LlavaLoRAModelConfig:
+    """The same architecture with decoder LoRA adapters of rank r (a LLaVA-1.5 or LLaVA-Next ModelConfig in)."""
+    import dataclasses
+    return LlavaLoRAModelConfig(**{f.name: getattr(cfg, f.name) for f in dataclasses.fields(ModelConfig)}, lora_r=r,
+                                lora_alpha=alpha)
+
+
+LLAVA15_7B_LORA = with_lora(LLAVA15_7B)
+LLAVANEXT_MISTRAL_7B_LORA = with_lora(LLAVANEXT_MISTRAL_7B)
+TINY_LORA = with_lora(TINY, 16, 32.0)
+SMALL_LORA = with_lora(SMALL, 16, 32.0)
+TINY_NEXT_LORA = with_lora(TINY_NEXT, 16, 32.0)
+SMALL_NEXT_LORA = with_lora(SMALL_NEXT, 16, 32.0)
+
+
+def llava_linear_dims(cfg: ModelConfig):
+    d, hd, kvd = cfg.hidden, cfg.heads * cfg.head_dim, cfg.kv_heads * cfg.head_dim
+    return {"self_attn.q_proj": (hd, d), "self_attn.k_proj": (kvd, d), "self_attn.v_proj": (kvd, d),
+            "self_attn.o_proj": (d, hd), "mlp.gate_proj": (cfg.ff, d), "mlp.up_proj": (cfg.ff, d), "mlp.down_proj": (d, cfg.ff)}
+
+
+def llava_lora_specs(cfg: LlavaLoRAModelConfig) -> List[Tuple[str, Tuple[int, ...], float, float]]:
+    """`language_model.model.layers.{i}.<linear>.lora_A` [r, in] / `.lora_B` [out, r].  peft starts B at 0; the synthetic
+    recipe draws B too so the adapter path carries signal in the parity tests."""
+    a = 0.02 * math.sqrt(3.0)
+    dims = llava_linear_dims(cfg)
+    s = []
+    for i in range(cfg.layers):
+        for lin in LLAVA_LORA_LINEARS:
+            out, inn = dims[lin]
+            s += [(f"language_model.model.layers.{i}.{lin}.lora_A", (cfg.lora_r, inn), a, 0.0),
+                  (f"language_model.model.layers.{i}.{lin}.lora_B", (out, cfg.lora_r), a, 0.0)]
+    return s

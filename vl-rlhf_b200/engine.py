@@ -370,15 +370,15 @@ class LlavaDPOEngine:
             ops.gemm(act, w[f"L{i}.wd"], out=xn, residual=xmid)
 
     # ------------------------------------------------------------------ forward of one model copy
-    def _forward(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, tag: str, save: bool,
-                 ddpo_weight: Optional[torch.Tensor]):
+    def _merged_embeddings(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, save_projector: bool,
+                           x_name: str) -> torch.Tensor:
+        """Projector (K6) -> [LLaVA-Next: pack_image_features] -> token embedding + merge (K7, K8): the fp32 input of
+        decoder layer 0, [T, d].  save_projector keeps the pre-GELU activations for the projector's backward."""
         cfg = self.cfg
         d, T = cfg.hidden, m.n_seq * m.S
-        H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
-        hd, kvd = H * dh, KV * dh
         nimg = feats.shape[0]
         # projector (K6)
-        if save:
+        if save_projector:
             z = self.buf("p.z", (nimg, d)); ph = self.buf("p.h", (nimg, d))
             ops.gemm(feats, w["proj.w1"], out=z, bias=w["proj.b1"])
             ops.gelu_fwd(z, ph)
@@ -396,11 +396,18 @@ class LlavaDPOEngine:
             ops.gather_rows(img, plan.pack_index, packed)
             img = packed
         # embed + merge (K7, K8)
-        L = cfg.layers
         # the residual stream is kept in fp32 (bf16 would add a 2^-9 relative rounding per layer that compounds
         # through 32 layers); every GEMM operand (normed activations, q/k/v, attention out, SwiGLU out) is bf16
-        x = self.buf("x.0" if save else "s.x0", (T, d), torch.float32)
+        x = self.buf(x_name, (T, d), torch.float32)
         ops.llava_merge_embed(m, w["embed"], img, x)
+        return x
+
+    def _forward(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, tag: str, save: bool,
+                 ddpo_weight: Optional[torch.Tensor]):
+        cfg = self.cfg
+        d, T = cfg.hidden, m.n_seq * m.S
+        L = cfg.layers
+        x = self._merged_embeddings(w, m, feats, save, "x.0" if save else "s.x0")
         ckpt = save and self.tc.activation_checkpointing
         for i in range(L):
             # saved for backward: everything (pre "a", one set per layer) or, with activation checkpointing, only the
