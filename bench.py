@@ -230,11 +230,14 @@ def run_b200(args):
     from vlrlhf_b200 import config, engine, host, ops, synthetic
     cfg = {"7b": config.LLAVA15_7B, "small": config.SMALL, "tiny": config.TINY, "next7b": config.LLAVANEXT_MISTRAL_7B,
            "next_small": config.SMALL_NEXT, "qwen7b": config.QWEN_VL_CHAT, "qwen_small": config.SMALL_QWEN, "xc2_7b": config.XC2_VL_7B,
-           "xc2_small": config.SMALL_XC2}[args.model]
+           "xc2_small": config.SMALL_XC2, "7b_lora": config.LLAVA15_7B_LORA, "next7b_lora": config.LLAVANEXT_MISTRAL_7B_LORA,
+           "small_lora": config.SMALL_LORA, "next_small_lora": config.SMALL_NEXT_LORA}[args.model]
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
     is_next = cfg.family == "llava_next"
     if cfg.family in ("qwen_vl", "xc2"):
         return run_b200_qwen(args, cfg, world, rank, local)
+    if getattr(cfg, "lora_r", 0):
+        return run_b200_lora(args, cfg, world, rank, local)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
     eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b")))
@@ -421,6 +424,96 @@ def run_b200_qwen(args, cfg, world, rank, local):
         dist.destroy_process_group()
 
 
+def run_b200_lora(args, cfg, world, rank, local):
+    """Side measurement: LLaVA-1.5-7B / LLaVA-Next-Mistral-7B trained the way the reference's launch scripts do it
+    (scripts/dpo_llava.sh, dpo_llavanext.sh: LoRA r=128 alpha=256 on the seven decoder linears, frozen tower/projector,
+    reference pass = adapters off), 4 pairs/GPU, text 1024, one 336-px image per pair.  Same timing rules as run_b200."""
+    import torch
+    import torch.distributed as dist
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import config, engine_lora, host, ops, synthetic
+    full = args.model in ("7b_lora", "next7b_lora")
+    is_next = cfg.family == "llava_next"
+    text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if full else (96, 24)
+    loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
+    eng = engine_lora.LlavaLoRADPOEngine(cfg, config.TrainConfig(loss_type=loss_type, learning_rate=1e-5,
+                                                                 activation_checkpointing=args.checkpointing))
+    eng.init_synthetic(0)
+    batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
+    cb = host.concatenated_inputs(batch)
+    ids_h, am_h, lb_h = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+    sizes_h = batch["img_input_dict"].get("image_sizes")
+    wt_h = eng.ddpo_weights(ids_h, am_h, lb_h, sizes_h) if loss_type == "ddpo" else None
+    dev_inputs = eng.prepare_inputs(ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"], wt_h, sizes_h)
+    S = dev_inputs[5].merged_len if is_next else text_len - 1 + cfg.n_patches
+    crops = dev_inputs[5].crops[0] if is_next else 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    last = {}
+    step_dev = lambda: eng.step(*dev_inputs, train=True)  # noqa: E731
+    step_e2e = lambda: last.update(eng.train_step(batch, train=True))  # noqa: E731
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = ops.launch_count()
+    ms_dev = timed(step_dev, args.steps)
+    launches = ops.launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
+    clocks = sampler.stop() if sampler else None
+    # algorithmic FLOPs: base linears x3 (policy fwd, reference fwd, dgrad-only backward), attention 2 fwd + a 2x backward,
+    # adapters x3 (fwd, dA/dB, dt/dx), tower once per crop, frozen projector once per pass
+    d, ff, L, r = cfg.hidden, cfg.ff, cfg.layers, cfg.lora_r
+    hd, kvd = cfg.heads * cfg.head_dim, cfg.kv_heads * cfg.head_dim
+    p_layer = cfg.qkv_dim * d + d * hd + 3 * d * ff
+    lin_seq, attn_seq = S * 2 * p_layer * L, L * 2 * S * S * d
+    lora_seq = S * 2 * L * r * ((3 * d + cfg.qkv_dim) + (hd + d) + 2 * (d + ff) + (ff + d))
+    per_seq = 3 * lin_seq + 4 * attn_seq + 3 * lora_seq
+    rows_lm = 2 * PAIRS_PER_GPU * (text_len - 1)
+    dv, Sv, P = cfg.v_hidden, cfg.n_patches + 1, cfg.n_patches
+    vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + P * 2 * cfg.patch_k * dv
+    proj = P * 2 * (dv * d + d * d) * 2
+    flops = PAIRS_PER_GPU * (2 * per_seq + crops * (vit + proj)) + rows_lm * 2 * d * cfg.vocab * 3
+    pk, pk_src = peaks()
+    if rank == 0:
+        pairs = PAIRS_PER_GPU * world
+        h2d = sum(int(t.numel() * t.element_size()) for t in (ids_h, am_h, lb_h, batch["img_input_dict"]["pixel_values"]))
+        name = "LLaVA-Next-Mistral-7B DDPO" if is_next else "LLaVA-1.5-7B DPO"
+        line = {"metric": METRIC, "value": pairs / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": (f"{name} bf16 with LoRA r={r} alpha={cfg.lora_alpha:g} on q/k/v/o/gate/up/down_proj (the reference "
+                                        f"scripts' setting; side measurement), frozen CLIP-L/336 + projector, 4 pairs/GPU, text 1024 "
+                                        f"({S} merged), 1x336px image/pair") if full else f"{args.model} (dev config, NOT the benchmark)",
+                           "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
+                           "activation_checkpointing": eng.tc.activation_checkpointing,
+                           "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
+                           "step_tflop_algorithmic": flops / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                        "ms_per_step": ms_e2e, "last_metrics": last},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, last, text_len, batch, ids_h, am_h, lb_h):
     import torch.distributed as dist
     d, ff, L, r, pr, P = cfg.hidden, cfg.ff, cfg.layers, cfg.lora_r, cfg.plora_r, cfg.n_patches
@@ -465,10 +558,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small", "xc2_7b", "xc2_small"],
+    ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small", "xc2_7b", "xc2_small",
+                                                   "7b_lora", "next7b_lora", "small_lora", "next_small_lora"],
                     help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO, qwen7b = configs[2] Qwen-VL-Chat LoRA (side measurements)")
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--checkpointing", action="store_true", help="activation checkpointing (the *_lora side measurements)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -139,7 +139,8 @@ def load_hf_checkpoint(engine, path: str, strict: bool = True) -> Dict[str, torc
             seen.add(k)
         else:
             extra[k] = t
-    missing = [k for k in pol if k not in seen]
+    # adapter tensors of a LoRA engine are not part of a base checkpoint (peft keeps them in adapter_model.safetensors)
+    missing = [k for k in pol if k not in seen and not k.endswith((".lora_A", ".lora_B"))]
     if strict and missing:
         raise KeyError(f"checkpoint lacks {len(missing)} tensors, e.g. {missing[:4]}")
     engine.extra_state = extra

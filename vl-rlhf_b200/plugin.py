@@ -242,13 +242,19 @@ def model_pixels(model, input_ids: torch.Tensor) -> torch.Tensor:
     return owner.pixel_values_for(input_ids)
 
 
-class RefView:
-    """`ref_model` handle for TRL's `self.ref_model(...)`/concatenated_forward(self.ref_model, batch) call."""
+class RefView(nn.Module):
+    """`ref_model` handle for TRL's concatenated_forward(self.ref_model, batch) call: the same engine, reference weights
+    (full fine-tuning: the frozen copy; LoRA: the shared base with the adapters off).  A parameter-less nn.Module so the
+    trainer's `.eval()` / dropout / accelerate bookkeeping accepts it without copying the engine."""
 
     def __init__(self, model):
-        self.engine = model.engine
-        self._owner = model
+        super().__init__()
+        object.__setattr__(self, "engine", model.engine)
+        object.__setattr__(self, "_owner", model)     # not registered as a sub-module: no parameters are exposed twice
         self._which = "ref"
+
+    def forward(self, *a, **k):
+        raise RuntimeError("RefView is consumed by concatenated_forward; it has no logits-producing forward")
 
 
 def install():
