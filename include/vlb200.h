@@ -68,6 +68,16 @@ int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ld
                      int out_dtype, int M, int N, int K, const void* bias, int act, const void* residual, int residual_dtype,
                      int ldr, int accumulate, void* stream);
 
+/* Same GEMM with (a) a second operand pair contracted into the same accumulator,
+ *   D = epilogue( alpha * ( opA(A) opB(B)^T + opA(A2) opB(B2)^T ) ),   A2: [M,K2] / [K2,M], B2: [N,K2] / [K2,N]
+ * in the majorness of A / B (A2 = B2 = NULL, K2 = 0: none), and (b) a scale on the accumulator.  This is the LoRA linear
+ * of peft (`base(x) + lora_B(lora_A(x)) * scaling`; the reference trains with it, utils/auto_load.py:559-578) in ONE
+ * launch: y = x W^T + ts B^T with ts = bf16(scaling * x A^T), and its input gradient dx = dy W + dt A.            */
+int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, const void* A2, int lda2,
+                        const void* B2, int ldb2, int K2, void* D, int ldd, int out_dtype, int M, int N, int K, float alpha,
+                        const void* bias, int act, const void* residual, int residual_dtype, int ldr, int accumulate,
+                        void* stream);
+
 /* mode 1: 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, B tile split across the pair) where M,N >= 256;
  * mode 0: single-CTA 128x256 tiles.  Default 1; the environment variable VLB200_GEMM_2CTA=0 selects mode 0.   */
 int vlb200_set_gemm_mode(int mode);

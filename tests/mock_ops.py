@@ -49,12 +49,22 @@ def perturb_(dst, base, other, alpha, shift):
 
 
 def gemm(a, b, *, a_kmajor=True, b_kmajor=True, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
-         residual=None, accumulate=False):
+         residual=None, accumulate=False, a2=None, b2=None, alpha=1.0):
     A = a.float() if a_kmajor else a.float().t()
     B = b.float() if b_kmajor else b.float().t()
     if A.shape[1] != B.shape[1]:
         raise ValueError("gemm: contraction mismatch")
     y = A @ B.t()
+    if (a2 is None) != (b2 is None):
+        raise ValueError("gemm: a2 and b2 come together")
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and b2.dtype == torch.bfloat16
+        A2 = a2.float() if a_kmajor else a2.float().t()
+        B2 = b2.float() if b_kmajor else b2.float().t()
+        if A2.shape[0] != A.shape[0] or B2.shape[0] != B.shape[0] or A2.shape[1] != B2.shape[1]:
+            raise ValueError("gemm: second operand pair does not match")
+        y = y + A2 @ B2.t()
+    y = y * alpha
     if bias is not None:
         y = y + bias.float()
     if act == ACT_QUICK_GELU:

@@ -72,6 +72,67 @@ def test_gemm_epilogues(ops):
         ops.gemm(a, bf(torch.randn(N, K + 8, device="cuda")))
 
 
+@pytest.mark.parametrize("M,N,K,K2,ak,bk", [(300, 320, 200, 48, 1, 1), (128, 128, 64, 16, 1, 1), (1000, 1024, 512, 128, 1, 1),
+                                            (520, 768, 392, 96, 1, 0), (264, 512, 256, 64, 0, 1), (200, 264, 136, 40, 0, 0),
+                                            (700, 96, 300, 16, 1, 0)])
+def test_gemm_second_operand_pair_and_alpha(ops, M, N, K, K2, ak, bk):
+    """D = alpha * (A B^T + A2 B2^T): the LoRA linear / its input gradient in one launch.  Ragged K and K2 (neither a
+    multiple of the 64-wide k-block), column-slice operands, 1-CTA and CTA-pair tile shapes, every majorness."""
+    torch.manual_seed(M + N + K + K2)
+    dev = "cuda"
+
+    def operand(rows_major, inner, outer, pad):   # a view with a padded leading dimension (a multiple of 8 elements)
+        cols = inner if rows_major else outer
+        full = bf(torch.randn(outer if rows_major else inner, (cols + 7) // 8 * 8 + pad, device=dev) * 0.5)
+        return full[:, :cols]
+
+    a, b = operand(ak, K, M, 8), operand(bk, K, N, 16)
+    a2, b2 = operand(ak, K2, M, 24), operand(bk, K2, N, 8)
+    f = lambda t, kmaj: t.float() if kmaj else t.float().t()  # noqa: E731
+    want = f(a, ak) @ f(b, bk).t() + f(a2, ak) @ f(b2, bk).t()
+    got = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), a2=a2, b2=b2, out_dtype=torch.float32)
+    close(got, want, rtol=1e-3, atol=1e-3)
+    res = torch.randn(M, N, device=dev)
+    got = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), a2=a2, b2=b2, alpha=0.25, residual=res, out_dtype=torch.float32)
+    close(got, 0.25 * want + res, rtol=1e-3, atol=1e-3)
+    got16 = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), a2=a2, b2=b2, alpha=2.0)
+    close(got16, 2.0 * want, rtol=1e-2, atol=2e-2)
+    close(ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), alpha=0.5, out_dtype=torch.float32), 0.5 * (f(a, ak) @ f(b, bk).t()),
+          rtol=1e-3, atol=1e-3)
+    with pytest.raises(ValueError):
+        ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), a2=a2)
+
+
+@pytest.mark.parametrize("M,N,K,K2,ak,bk", [(512, 128, 4096, 0, 0, 0), (128, 1024, 5000, 0, 0, 0), (384, 256, 2048, 64, 1, 1),
+                                            (200, 96, 3000, 0, 1, 0), (256, 136, 2104, 0, 0, 1)])
+def test_gemm_split_k_skinny_outputs(ops, M, N, K, K2, ak, bk):
+    """Few output tiles, long contraction (the LoRA weight-gradient shapes): the 1-CTA kernel splits K over the SMs and a
+    second kernel sums the fp32 partials in a fixed order -- same results as the unsplit path, bit-reproducible."""
+    torch.manual_seed(M + N + K)
+    dev = "cuda"
+    f = lambda t, kmaj: t.float() if kmaj else t.float().t()  # noqa: E731
+    a = bf(torch.randn((M, K) if ak else (K, M), device=dev) * 0.25)
+    b = bf(torch.randn((N, K) if bk else (K, N), device=dev) * 0.25)
+    want = f(a, ak) @ f(b, bk).t()
+    kw = {}
+    if K2:
+        a2 = bf(torch.randn((M, K2) if ak else (K2, M), device=dev) * 0.25)
+        b2 = bf(torch.randn((N, K2) if bk else (K2, N), device=dev) * 0.25)
+        want = want + f(a2, ak) @ f(b2, bk).t()
+        kw = dict(a2=a2, b2=b2)
+    got = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out_dtype=torch.float32, **kw)
+    close(got, want, rtol=1e-3, atol=2e-3)
+    again = ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out_dtype=torch.float32, **kw)
+    assert torch.equal(got, again)                       # deterministic reduction order
+    res = torch.randn(M, N, device=dev)
+    acc = torch.full((M, N), 2.0, device=dev)
+    ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out=acc, alpha=0.5, residual=res, accumulate=True, **kw)
+    close(acc, 0.5 * want + res + 2.0, rtol=1e-3, atol=2e-3)
+    out16 = bf(torch.ones(M, N + 8, device=dev))[:, :N]   # bf16, strided destination, accumulate
+    ops.gemm(a, b, a_kmajor=bool(ak), b_kmajor=bool(bk), out=out16, accumulate=True, **kw)
+    close(out16, want + 1.0, rtol=1e-2, atol=3e-2)
+
+
 # ------------------------------------------------------------------ norms
 @pytest.mark.parametrize("rows,cols", [(37, 128), (1000, 4096), (5, 1024)])
 def test_rmsnorm_fwd_bwd(ops, rows, cols):

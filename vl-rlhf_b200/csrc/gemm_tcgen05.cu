@@ -25,6 +25,12 @@ constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 struct Params {
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_tiles, num_k_blocks;
+    int kb1;           // k-blocks [0, kb1) come from the first operand pair, [kb1, num_k_blocks) from the second (A2, B2)
+    float alpha;       // the accumulator is scaled by alpha before bias / activation / residual
+    // split-K (1-CTA kernel only): work item t = split * num_tiles + tile covers k-blocks [split * kb_per_split, ...) and
+    // stores its raw fp32 partial tile to ws[split][M][N]; splitk_reduce_kernel sums the partials in a fixed order
+    int splits, kb_per_split;
+    float* ws;
     void* D;
     long long ldd;
     int out_f32;
@@ -72,7 +78,7 @@ __device__ __forceinline__ void epilogue_store_32(const Params& p, int row, int 
     if (row < p.M && col0 < p.N) {
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
                     if (p.bias != nullptr) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
@@ -161,7 +167,8 @@ __device__ __forceinline__ void epilogue_store_32(const Params& p, int row, int 
 
 template <int BLOCK_N, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, const Params p) {
     constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_TX_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages
@@ -184,6 +191,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (warp_idx == 0 && lane_idx == 0) {
         prefetch_tensormap(&tma_a);
         prefetch_tensormap(&tma_b);
+        if (p.kb1 < p.num_k_blocks) {
+            prefetch_tensormap(&tma_a2);
+            prefetch_tensormap(&tma_b2);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -205,29 +216,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane_idx == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int t = blockIdx.x; t < p.num_tiles * p.splits; t += gridDim.x) {
                 int m_blk, n_blk;
+                const int tile = t % p.num_tiles, split = t / p.num_tiles;
                 tile_coords(p, tile, m_blk, n_blk);
                 const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int kb_begin = split * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                     mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX_BYTES);
                     uint8_t* sa = smem_a + stage * A_TILE_BYTES;
                     uint8_t* sb = smem_b + stage * B_TILE_BYTES;
-                    const int k0 = kb * BLOCK_K;
+                    // second K segment (A2, B2): same tile format, its own tensor maps; a ragged segment end is
+                    // zero-filled by TMA, so the segments need not be multiples of BLOCK_K
+                    const bool seg2 = kb >= p.kb1;
+                    const CUtensorMap* ma = seg2 ? &tma_a2 : &tma_a;
+                    const CUtensorMap* mb = seg2 ? &tma_b2 : &tma_b;
+                    const int k0 = (seg2 ? kb - p.kb1 : kb) * BLOCK_K;
                     if constexpr (A_KMAJOR) {
-                        tma_load_2d(&tma_a, &full_bar[stage], sa, k0, m0);  // box {64 k, 128 m}
+                        tma_load_2d(ma, &full_bar[stage], sa, k0, m0);  // box {64 k, 128 m}
                     } else {
 #pragma unroll
                         for (int i = 0; i < BLOCK_M / 64; ++i)  // box {64 m, 64 k}
-                            tma_load_2d(&tma_a, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
+                            tma_load_2d(ma, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
                     }
                     if constexpr (B_KMAJOR) {
-                        tma_load_2d(&tma_b, &full_bar[stage], sb, k0, n0);  // box {64 k, BLOCK_N n}
+                        tma_load_2d(mb, &full_bar[stage], sb, k0, n0);  // box {64 k, BLOCK_N n}
                     } else {
 #pragma unroll
                         for (int i = 0; i < BLOCK_N / 64; ++i)  // box {64 n, 64 k}
-                            tma_load_2d(&tma_b, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
+                            tma_load_2d(mb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -246,11 +264,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int t = blockIdx.x; t < p.num_tiles * p.splits; t += gridDim.x) {
+                const int split = t / p.num_tiles;
+                const int kb_begin = split * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 200 + acc);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 300 + stage);
                     tcgen05_fence_after();
                     const uint64_t a_desc =
@@ -260,7 +280,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * A_KADV), b_desc + (uint64_t)(k * B_KADV), idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                                    ((kb - kb_begin) | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -274,8 +294,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may touch
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int t = blockIdx.x; t < p.num_tiles * p.splits; t += gridDim.x) {
             int m_blk, n_blk;
+            const int tile = t % p.num_tiles, split = t / p.num_tiles;
             tile_coords(p, tile, m_blk, n_blk);
             const int row = m_blk * BLOCK_M + quad * 32 + lane_idx;
             const int n0 = n_blk * BLOCK_N;
@@ -287,7 +308,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 uint32_t r[32];
                 tmem_ld_32x32(taddr0 + c * 32, r);
                 tmem_ld_wait();
-                epilogue_store_32(p, row, n0 + c * 32, r);
+                if (p.splits == 1) {
+                    epilogue_store_32(p, row, n0 + c * 32, r);
+                } else if (row < p.M) {   // raw partial sums; N % 8 == 0 keeps every float4 inside the row
+                    float* wp = p.ws + ((long long)split * p.M + row) * p.N + n0 + c * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        if (n0 + c * 32 + j4 * 4 < p.N)
+                            *reinterpret_cast<float4*>(wp + j4 * 4) =
+                                make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]),
+                                            __uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3]));
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -301,6 +332,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (warp_idx == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// D = epilogue(alpha * sum_s ws[s]) for a split-K launch: partials summed in split order (deterministic), then the same
+// residual / accumulate / output-dtype handling as the fused epilogue (bias and activation are not combined with split-K)
+__global__ void splitk_reduce_kernel(const Params p) {
+    const long long n4 = (long long)p.N / 4, total = (long long)p.M * n4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / n4;
+        const int col = (int)(i - row * n4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < p.splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(p.ws + ((long long)s * p.M + row) * p.N + col);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float v[4] = {acc.x * p.alpha, acc.y * p.alpha, acc.z * p.alpha, acc.w * p.alpha};
+        if (p.residual != nullptr) {
+            if (p.residual_f32) {
+                const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + row * p.ldr + col);
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            } else {
+                const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + row * p.ldr + col);
+                const float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y);
+                v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+            }
+        }
+        if (p.out_f32) {
+            float* dp = reinterpret_cast<float*>(p.D) + row * p.ldd + col;
+            float4 o = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(dp);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(dp) = o;
+        } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + row * p.ldd + col;
+            if (p.accumulate) {
+                const uint2 b = *reinterpret_cast<const uint2*>(dp);
+                const float2 f0 = unpack_bf16x2(b.x), f1 = unpack_bf16x2(b.y);
+                v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+            }
+            uint2 o;
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(dp) = o;
+        }
     }
 }
 
@@ -361,7 +438,8 @@ constexpr int PAIR_M = 256, PAIR_N = 256, HALF_N = 128;
 
 template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                      const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, const Params p) {
     constexpr int B_TILE_BYTES = HALF_N * BLOCK_K * 2;
     constexpr uint32_t STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // per CTA
     constexpr int TMEM_COLS = 2 * PAIR_N;
@@ -385,6 +463,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     if (warp_idx == 0 && lane_idx == 0) {
         prefetch_tensormap(&tma_a);
         prefetch_tensormap(&tma_b);
+        if (p.kb1 < p.num_k_blocks) {
+            prefetch_tensormap(&tma_a2);
+            prefetch_tensormap(&tma_b2);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 2);
             mbar_init(&empty_bar[s], 1);
@@ -416,18 +498,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * A_TILE_BYTES;
                     uint8_t* sb = smem_b + stage * B_TILE_BYTES;
-                    const int k0 = kb * BLOCK_K;
+                    const bool seg2 = kb >= p.kb1;   // second K segment (A2, B2), see the 1-CTA kernel
+                    const CUtensorMap* ma = seg2 ? &tma_a2 : &tma_a;
+                    const CUtensorMap* mb = seg2 ? &tma_b2 : &tma_b;
+                    const int k0 = (seg2 ? kb - p.kb1 : kb) * BLOCK_K;
                     if constexpr (A_KMAJOR) {
-                        tma_load_2d_2sm(&tma_a, &full_bar[stage], sa, k0, m0);
+                        tma_load_2d_2sm(ma, &full_bar[stage], sa, k0, m0);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_2sm(&tma_a, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
+                        for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_2sm(ma, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k0);
                     }
                     if constexpr (B_KMAJOR) {
-                        tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, k0, n0);
+                        tma_load_2d_2sm(mb, &full_bar[stage], sb, k0, n0);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < HALF_N / 64; ++i) tma_load_2d_2sm(&tma_b, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
+                        for (int i = 0; i < HALF_N / 64; ++i) tma_load_2d_2sm(mb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k0);
                     }
                     if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -576,7 +661,8 @@ int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
 }
 
 template <int BLOCK_N, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                  const Params& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_TILE_BYTES + BLOCK_N * BLOCK_K * 2) + 256 + 1024;
     auto kern = gemm_bf16_kernel<BLOCK_N, STAGES, A_KMAJOR, B_KMAJOR>;
     static bool configured = false;
@@ -584,15 +670,24 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
         VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
-    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+    const int work = p.num_tiles * p.splits;
+    const int grid = work < num_sms() ? work : num_sms();
+    kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, ta2, tb2, p);
     count_launch();
     VLB_LAUNCH_CHECK();
+    if (p.splits > 1) {
+        const long long total = (long long)p.M * (p.N / 4);
+        const int blocks = (int)((total + 255) / 256 < 4LL * num_sms() ? (total + 255) / 256 : 4LL * num_sms());
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p);
+        count_launch();
+        VLB_LAUNCH_CHECK();
+    }
     return VLB200_OK;
 }
 
 template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
-static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                       const Params& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_TILE_BYTES + HALF_N * BLOCK_K * 2) + 256 + 1024;
     auto kern = gemm_bf16_2cta_kernel<STAGES, A_KMAJOR, B_KMAJOR>;
     static bool configured = false;
@@ -602,36 +697,57 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const Param
     }
     const int max_pairs = num_sms() / 2;
     const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-    kern<<<2 * pairs, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+    kern<<<2 * pairs, NUM_THREADS, smem_bytes, stream>>>(ta, tb, ta2, tb2, p);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
 }
 
-static int dispatch_2cta(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t s) {
-    if (ak && bk) return launch_2cta<6, true, true>(ta, tb, p, s);
-    if (ak && !bk) return launch_2cta<6, true, false>(ta, tb, p, s);
-    if (!ak && bk) return launch_2cta<6, false, true>(ta, tb, p, s);
-    return launch_2cta<6, false, false>(ta, tb, p, s);
+static int dispatch_2cta(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
+                         const CUtensorMap& tb2, const Params& p, cudaStream_t s) {
+    if (ak && bk) return launch_2cta<6, true, true>(ta, tb, ta2, tb2, p, s);
+    if (ak && !bk) return launch_2cta<6, true, false>(ta, tb, ta2, tb2, p, s);
+    if (!ak && bk) return launch_2cta<6, false, true>(ta, tb, ta2, tb2, p, s);
+    return launch_2cta<6, false, false>(ta, tb, ta2, tb2, p, s);
+}
+
+// split-K partials: one device buffer, grown on demand (warm-up only; a grow synchronises the device first because
+// launches already queued may still be writing the old buffer)
+static float* g_splitk_ws = nullptr;
+static size_t g_splitk_ws_bytes = 0;
+static int splitk_workspace(size_t bytes, float** out) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (bytes > g_splitk_ws_bytes) {
+        VLB_CHECK_CUDA(cudaDeviceSynchronize());
+        if (g_splitk_ws) VLB_CHECK_CUDA(cudaFree(g_splitk_ws));
+        g_splitk_ws = nullptr; g_splitk_ws_bytes = 0;
+        const size_t want = bytes < (size_t(64) << 20) ? (size_t(64) << 20) : bytes;
+        VLB_CHECK_CUDA(cudaMalloc(&g_splitk_ws, want));
+        g_splitk_ws_bytes = want;
+    }
+    *out = g_splitk_ws;
+    return VLB200_OK;
 }
 
 static int g_gemm_mode = -1;  // -1: read VLB200_GEMM_2CTA on first use; 0: 1-CTA kernel; 1: 2-CTA pairs where the shape allows
 
 template <int BLOCK_N, int STAGES>
-static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
-                          cudaStream_t s) {
-    if (ak && bk) return launch<BLOCK_N, STAGES, true, true>(ta, tb, p, s);
-    if (ak && !bk) return launch<BLOCK_N, STAGES, true, false>(ta, tb, p, s);
-    if (!ak && bk) return launch<BLOCK_N, STAGES, false, true>(ta, tb, p, s);
-    return launch<BLOCK_N, STAGES, false, false>(ta, tb, p, s);
+static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
+                          const CUtensorMap& tb2, const Params& p, cudaStream_t s) {
+    if (ak && bk) return launch<BLOCK_N, STAGES, true, true>(ta, tb, ta2, tb2, p, s);
+    if (ak && !bk) return launch<BLOCK_N, STAGES, true, false>(ta, tb, ta2, tb2, p, s);
+    if (!ak && bk) return launch<BLOCK_N, STAGES, false, true>(ta, tb, ta2, tb2, p, s);
+    return launch<BLOCK_N, STAGES, false, false>(ta, tb, ta2, tb2, p, s);
 }
 
 }  // namespace gemm
 }  // namespace vlb
 
-extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D,
-                                int ldd, int out_dtype, int M, int N, int K, const void* bias, int act,
-                                const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
+extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
+                                   const void* A2, int lda2, const void* B2, int ldb2, int K2, void* D, int ldd,
+                                   int out_dtype, int M, int N, int K, float alpha, const void* bias, int act,
+                                   const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
     using namespace vlb;
     using namespace vlb::gemm;
     VLB_REQUIRE(A && B && D, "gemm: null pointer");
@@ -647,15 +763,41 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     VLB_REQUIRE(out_dtype == VLB200_BF16 || out_dtype == VLB200_F32, "gemm: bad out_dtype %d", out_dtype);
     VLB_REQUIRE(a_kmajor ? lda >= K : lda >= M, "gemm: lda too small");
     VLB_REQUIRE(b_kmajor ? ldb >= K : ldb >= N, "gemm: ldb too small");
+    const bool dual = A2 != nullptr || B2 != nullptr || K2 > 0;
+    if (dual) {
+        VLB_REQUIRE(A2 && B2 && K2 > 0, "gemm: the second operand pair needs A2, B2 and K2 > 0");
+        VLB_REQUIRE(lda2 % 8 == 0 && ldb2 % 8 == 0, "gemm: lda2=%d / ldb2=%d must be multiples of 8 elements", lda2, ldb2);
+        VLB_REQUIRE((reinterpret_cast<uintptr_t>(A2) & 15) == 0 && (reinterpret_cast<uintptr_t>(B2) & 15) == 0,
+                    "gemm: A2/B2 must be 16-byte aligned");
+        VLB_REQUIRE(a_kmajor ? lda2 >= K2 : lda2 >= M, "gemm: lda2 too small");
+        VLB_REQUIRE(b_kmajor ? ldb2 >= K2 : ldb2 >= N, "gemm: ldb2 too small");
+    }
     if (g_gemm_mode < 0) {
         const char* e = getenv("VLB200_GEMM_2CTA");
         g_gemm_mode = (e != nullptr && e[0] == '0') ? 0 : 1;  // CTA pairs by default
     }
-    const bool use_pair = g_gemm_mode == 1 && M >= 256 && N >= 256;
-    const bool big_n = N > 128;
+    // skinny outputs with a long contraction (LoRA weight gradients dB = dy^T ts, dA = dt^T x: a handful of tiles, K = all
+    // tokens of the batch) would occupy a few SMs only: 128x128 tiles on the 1-CTA kernel, split along K so that every SM
+    // streams a slice (r2 probe: 95 us at 1.1 TB/s for M 4096, N 128, K 12792 without it)
+    const int kblocks_total = (K + BLOCK_K - 1) / BLOCK_K + (dual ? (K2 + BLOCK_K - 1) / BLOCK_K : 0);
+    const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128);
+    static const bool splitk_on = [] { const char* e = getenv("VLB200_SPLITK"); return !(e && e[0] == '0'); }();
+    const bool skinny = splitk_on && tiles128 <= num_sms() && kblocks_total >= 32 && bias == nullptr && act == VLB200_ACT_NONE &&
+                        N % 4 == 0;
+    int splits = 1, kb_per_split = kblocks_total;
+    if (skinny) {
+        splits = num_sms() / (int)tiles128;
+        if (splits > kblocks_total / 8) splits = kblocks_total / 8;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+        kb_per_split = (kblocks_total + splits - 1) / splits;
+        splits = (kblocks_total + kb_per_split - 1) / kb_per_split;   // no empty split
+    }
+    const bool use_pair = !skinny && g_gemm_mode == 1 && M >= 256 && N >= 256;
+    const bool big_n = !skinny && N > 128;
     const int BN = use_pair ? HALF_N : (big_n ? 256 : 128);  // rows of B fetched per TMA box
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, ta2, tb2;
     int rc;
     if (a_kmajor) rc = get_tensor_map(A, K, M, lda, BLOCK_K, BLOCK_M, &ta);
     else rc = get_tensor_map(A, M, K, lda, 64, BLOCK_K, &ta);
@@ -663,6 +805,16 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     if (b_kmajor) rc = get_tensor_map(B, K, N, ldb, BLOCK_K, BN, &tb);
     else rc = get_tensor_map(B, N, K, ldb, 64, BLOCK_K, &tb);
     if (rc) return rc;
+    if (dual) {
+        if (a_kmajor) rc = get_tensor_map(A2, K2, M, lda2, BLOCK_K, BLOCK_M, &ta2);
+        else rc = get_tensor_map(A2, M, K2, lda2, 64, BLOCK_K, &ta2);
+        if (rc) return rc;
+        if (b_kmajor) rc = get_tensor_map(B2, K2, N, ldb2, BLOCK_K, BN, &tb2);
+        else rc = get_tensor_map(B2, N, K2, ldb2, 64, BLOCK_K, &tb2);
+        if (rc) return rc;
+    } else {
+        ta2 = ta; tb2 = tb;  // never dereferenced (kb1 == num_k_blocks)
+    }
 
     Params p;
     p.M = M; p.N = N; p.K = K;
@@ -670,7 +822,14 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     p.num_m_blocks = (M + TM - 1) / TM;
     p.num_n_blocks = (N + TN - 1) / TN;
     p.num_tiles = p.num_m_blocks * p.num_n_blocks;
-    p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb1 = (K + BLOCK_K - 1) / BLOCK_K;
+    p.num_k_blocks = p.kb1 + (dual ? (K2 + BLOCK_K - 1) / BLOCK_K : 0);
+    p.alpha = alpha;
+    p.splits = splits; p.kb_per_split = kb_per_split; p.ws = nullptr;
+    if (splits > 1) {
+        rc = splitk_workspace((size_t)splits * M * N * sizeof(float), &p.ws);
+        if (rc) return rc;
+    }
     p.D = D; p.ldd = ldd; p.out_f32 = out_dtype == VLB200_F32;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.act = act;
@@ -681,8 +840,9 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
     {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group (VLB200_RASTER_MB overrides)
         static const double budget_mb = [] { const char* e = getenv("VLB200_RASTER_MB"); return e ? atof(e) : 32.0; }();
         const double budget = budget_mb * 1024 * 1024;
-        const double a_blk = (double)TM * K * 2, b_blk = (double)TN * K * 2;
-        const double a_bytes = (double)M * K * 2, b_bytes = (double)N * K * 2;
+        const double Kt = (double)K + (dual ? K2 : 0);
+        const double a_blk = (double)TM * Kt * 2, b_blk = (double)TN * Kt * 2;
+        const double a_bytes = (double)M * Kt * 2, b_bytes = (double)N * Kt * 2;
         int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
         int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
         const double cost_m = a_bytes + b_bytes * ((p.num_m_blocks + gm - 1) / gm);
@@ -691,9 +851,16 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
         p.group = p.group_along_n ? gn : gm;
     }
     cudaStream_t s = as_stream(stream);
-    if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
-    if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
-    return dispatch_major<128, 6>(a_kmajor != 0, b_kmajor != 0, ta, tb, p, s);
+    if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
+    if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
+    return dispatch_major<128, 6>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
+}
+
+extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D,
+                                int ldd, int out_dtype, int M, int N, int K, const void* bias, int act,
+                                const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
+    return vlb200_gemm_bf16_ex(A, lda, a_kmajor, B, ldb, b_kmajor, nullptr, 0, nullptr, 0, 0, D, ldd, out_dtype, M, N, K, 1.0f,
+                               bias, act, residual, residual_dtype, ldr, accumulate, stream);
 }
 
 extern "C" int vlb200_set_gemm_mode(int mode) {

@@ -11,11 +11,11 @@ anyres packing, merge, head and loss kernels.  What changes with LoRA:
     adapters (320 M parameters at r = 128 on the 7B decoder) and so does the data-parallel gradient reduction.
   * backward runs no base weight-gradient GEMM (a third of the full fine-tuning step's FLOPs) and stops at decoder layer
     0: embeddings, projector, image_newline and the tower are frozen by peft.
-  * LoRA linear (peft lora.Linear.forward, dropout off under TRL's disable_dropout): t = x A^T (fp32 out) ->
-    ts = bf16(s t) -> u = ts B^T -> y = x W^T + u in ONE epilogue (the adapter term enters through the base GEMM's
-    residual slot, so the sum is rounded once); q/k/v_proj and gate/up_proj share their input, so their A matrices are
-    stacked ([3r, d], [2r, d]: one GEMM each) and their B products land in column slices of one u.  Backward:
-    dB = dy^T ts, dt = s (dy B), dA = dt^T x, dx = dy W + dt A (accumulated by a second GEMM).
+  * LoRA linear (peft lora.Linear.forward, dropout off under TRL's disable_dropout): t = x A^T (fp32 accumulator) ->
+    ts = bf16(s t) -> y = x W^T + ts B^T in ONE launch (the adapter term is a second operand pair contracted into the
+    base GEMM's accumulator, `vlb200_gemm_bf16_ex`: no [T, out]-sized intermediate in HBM, one rounding); q/k/v_proj and
+    gate/up_proj share their input, so their A matrices are stacked ([3r, d], [2r, d]: one GEMM each).  Backward:
+    dB = dy^T ts, dt = bf16(s dy B), dA = dt^T x, dx = dy W + dt A (again one launch with two operand pairs).
 """
 from __future__ import annotations
 
@@ -150,46 +150,44 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         def lora_t(xin, A, key, cols):
             """ts = bf16(s * xin A^T): kept in the saved set when the backward will need it, else in scratch"""
             ts = b[key] if key in b else self.buf(f"l.ts.{cols}", (T, cols))
-            t32 = self.buf(f"l.t32.{cols}", (T, cols), torch.float32)
-            ops.gemm(xin, A, out=t32)
-            ops.cast_f32_to_bf16(t32.view(-1), ts.view(-1), cfg.lora_scale)
+            ops.gemm(xin, A, out=ts, alpha=cfg.lora_scale)
             return ts
 
+        # every adapted linear is ONE launch: y = x W^T + ts B^T (second operand pair of the GEMM, no u in HBM)
         ops.rmsnorm_fwd(x, base[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=b["rstd1"])
+        wqkv = base[f"L{i}.wqkv"]
         if lora is None:
-            ops.gemm(h, base[f"L{i}.wqkv"], out=qkv)
+            ops.gemm(h, wqkv, out=qkv)
         else:
             ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", 3 * r)
-            u = self.buf("l.u", (T, cfg.qkv_dim))
-            ops.gemm(ts[:, :r], lora[f"L{i}.q.B"], out=u[:, :hd])
-            ops.gemm(ts[:, r:2 * r], lora[f"L{i}.k.B"], out=u[:, hd:hd + kvd])
-            ops.gemm(ts[:, 2 * r:], lora[f"L{i}.v.B"], out=u[:, hd + kvd:])
-            ops.gemm(h, base[f"L{i}.wqkv"], out=qkv, residual=u)
+            for j, (lo, hi, n) in enumerate(((0, hd, "q"), (hd, hd + kvd, "k"), (hd + kvd, hd + 2 * kvd, "v"))):
+                ops.gemm(h, wqkv[lo:hi], a2=ts[:, j * r:(j + 1) * r], b2=lora[f"L{i}.{n}.B"], out=qkv[:, lo:hi])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
         ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
                         True, 1.0 / math.sqrt(dh))
-        ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
-        if lora is not None:
-            ts = lora_t(att, lora[f"L{i}.o.A"], "ts_o", r)
-            ops.gemm(ts, lora[f"L{i}.o.B"], out=xmid, accumulate=True)   # fp32 accumulate into the residual stream
-        ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         if lora is None:
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu)
+            ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
+        else:
+            ts = lora_t(att, lora[f"L{i}.o.A"], "ts_o", r)
+            ops.gemm(att, base[f"L{i}.wo"], a2=ts, b2=lora[f"L{i}.o.B"], out=xmid, residual=x)
+        ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
+        wgu = base[f"L{i}.wgu"]
+        if lora is None:
+            ops.gemm(h, wgu, out=gu)
         else:
             ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r)
-            u = self.buf("l.ugu", (T, 2 * ff))
-            ops.gemm(ts[:, :r], lora[f"L{i}.g.B"], out=u[:, :ff])
-            ops.gemm(ts[:, r:], lora[f"L{i}.u.B"], out=u[:, ff:])
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu, residual=u)
+            ops.gemm(h, wgu[:ff], a2=ts[:, :r], b2=lora[f"L{i}.g.B"], out=gu[:, :ff])
+            ops.gemm(h, wgu[ff:], a2=ts[:, r:], b2=lora[f"L{i}.u.B"], out=gu[:, ff:])
         if xn is not None or (lora is not None and "ts_d" in b):
             act = self.buf("s.act", (T, ff))
             ops.swiglu_fwd(gu, act)
             if lora is not None:
                 ts = lora_t(act, lora[f"L{i}.d.A"], "ts_d", r)
             if xn is not None:
-                ops.gemm(act, base[f"L{i}.wd"], out=xn, residual=xmid)
-                if lora is not None:
-                    ops.gemm(ts, lora[f"L{i}.d.B"], out=xn, accumulate=True)
+                if lora is None:
+                    ops.gemm(act, base[f"L{i}.wd"], out=xn, residual=xmid)
+                else:
+                    ops.gemm(act, base[f"L{i}.wd"], a2=ts, b2=lora[f"L{i}.d.B"], out=xn, residual=xmid)
 
     # ------------------------------------------------------------------ forward of one pass
     def _forward(self, w, m, feats, tag: str, save: bool, ddpo_weight):
@@ -226,10 +224,8 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
         delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
-        # dt = s * dy B of the adapters that share an input, side by side (3r: q|k|v, 2r: gate|up, r: o, down)
-        d3_32 = self.buf("b.d3_32", (T, 3 * r), torch.float32); d3 = self.buf("b.d3", (T, 3 * r))
-        d2_32 = self.buf("b.d2_32", (T, 2 * r), torch.float32); d2 = self.buf("b.d2", (T, 2 * r))
-        d1_32 = self.buf("b.d1_32", (T, r), torch.float32); d1 = self.buf("b.d1", (T, r))
+        # dt = bf16(s * dy B) of the adapters that share an input, side by side (3r: q|k|v, 2r: gate|up, r: o, down)
+        d3 = self.buf("b.d3", (T, 3 * r)); d2 = self.buf("b.d2", (T, 2 * r)); d1 = self.buf("b.d1", (T, r))
         scale = 1.0 / math.sqrt(dh)
         for i in reversed(range(cfg.layers)):
             x_in = self._bufs[f"x.{i}"]
@@ -243,31 +239,25 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- down_proj
             ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"])      # dBd = dx^T ts_d
-            ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=d1_32)                        # dt = dx Bd
-            ops.cast_f32_to_bf16(d1_32.view(-1), d1.view(-1), s)
+            ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=d1, alpha=s)                  # dt = s dx Bd
             ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"])             # dAd = dt^T act
-            ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, out=dact)                          # dact = dx Wd
-            ops.gemm(d1, lora[f"L{i}.d.A"], b_kmajor=False, out=dact, accumulate=True)        #      + dt Ad
+            ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
             # ---- gate | up
             ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h)                      # recompute h2
             ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
             tsg = sb["ts_gu"]
             ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.g.B"])
             ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.u.B"])
-            ops.gemm(gu[:, :ff], lora[f"L{i}.g.B"], b_kmajor=False, out=d2_32[:, :r])
-            ops.gemm(gu[:, ff:], lora[f"L{i}.u.B"], b_kmajor=False, out=d2_32[:, r:])
-            ops.cast_f32_to_bf16(d2_32.view(-1), d2.view(-1), s)
+            ops.gemm(gu[:, :ff], lora[f"L{i}.g.B"], b_kmajor=False, out=d2[:, :r], alpha=s)
+            ops.gemm(gu[:, ff:], lora[f"L{i}.u.B"], b_kmajor=False, out=d2[:, r:], alpha=s)
             ops.gemm(d2, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])              # dA = dt^T h2  [2r, d]
-            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                        # dh2 = dgu Wgu
-            ops.gemm(d2, lora[f"L{i}.gu.A"], b_kmajor=False, out=dnorm, accumulate=True)      #      + dt A
+            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=d2, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- o_proj
             ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])
-            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=d1_32)
-            ops.cast_f32_to_bf16(d1_32.view(-1), d1.view(-1), s)
+            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=d1, alpha=s)
             ops.gemm(d1, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])
-            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, out=datt)                         # datt = dxmid Wo
-            ops.gemm(d1, lora[f"L{i}.o.A"], b_kmajor=False, out=datt, accumulate=True)
+            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
                             dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
@@ -277,12 +267,10 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             cols = ((0, hd, "q"), (hd, hd + kvd, "k"), (hd + kvd, hd + 2 * kvd, "v"))
             for j, (lo, hi, n) in enumerate(cols):
                 ops.gemm(dqkv[:, lo:hi], tsq[:, j * r:(j + 1) * r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.{n}.B"])
-                ops.gemm(dqkv[:, lo:hi], lora[f"L{i}.{n}.B"], b_kmajor=False, out=d3_32[:, j * r:(j + 1) * r])
-            ops.cast_f32_to_bf16(d3_32.view(-1), d3.view(-1), s)
+                ops.gemm(dqkv[:, lo:hi], lora[f"L{i}.{n}.B"], b_kmajor=False, out=d3[:, j * r:(j + 1) * r], alpha=s)
             ops.gemm(d3, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])             # [3r, d]
             if i > 0:  # nothing below decoder layer 0 is trainable: its input gradient is never read
-                ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)                 # dh1 = dqkv Wqkv
-                ops.gemm(d3, lora[f"L{i}.qkv.A"], b_kmajor=False, out=dnorm, accumulate=True)
+                ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=d3, b2=lora[f"L{i}.qkv.A"], out=dnorm)
                 ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)
             self._reduce_bucket(self.layout.offsets[f"L{i}.qkv.A"],
                                 self.layout.offsets[f"L{i + 1}.qkv.A"] if i + 1 < cfg.layers else self.layout.size)

@@ -11,9 +11,9 @@ What is different from the LLaVA engine:
     adapters are trainable, so the flat trainable/gradient/optimizer arenas hold 112 M parameters instead of 7 B, the
     backward runs no base weight-gradient GEMM (2/3 of the full-FT backward FLOPs) and nothing flows into embeddings or
     the vision tower (frozen: `--freeze_vision_tower True`; peft freezes the resampler too).
-  * LoRA linear: t = x A^T (fp32 out) -> ts = bf16(s * t) -> u = ts B^T -> y = x W^T + b + u in ONE epilogue (the adapter
-    term enters through the GEMM's residual slot, so the sum is rounded once); backward: dB = dy^T ts, dt = s * (dy B),
-    dA = dt^T x, dx = dy W + dt A (accumulated by the second GEMM).
+  * LoRA linear: ts = bf16(s * x A^T) -> y = x W^T + b + ts B^T in ONE launch (the adapter term is a second operand pair
+    contracted into the base GEMM's accumulator, `vlb200_gemm_bf16_ex`: no [T, out] intermediate in HBM, one rounding);
+    backward: dB = dy^T ts, dt = bf16(s * dy B), dA = dt^T x, dx = dy W + dt A (again one launch, two operand pairs).
   * ViT-bigG: per-head interleaved q|k|v projection re-laid out at load time as [q heads | k heads | v heads] with each
     104-wide head zero-padded to 128 (q.k and the context are unchanged), so the tcgen05 attention kernel runs as is;
     positional tables are interpolated once on the host (visual.py:24-45 is a weight transform for a fixed image size).
@@ -310,34 +310,31 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         def lora_t(xin, A, key, cols, scratch):
             """ts = bf16(s * xin A^T): kept in the saved set when the backward will need it, else in scratch"""
             ts = b[key] if key in b else self.buf(scratch, (T, cols))
-            t32 = self.buf(f"l.t32.{cols}", (T, cols), torch.float32)
-            ops.gemm(xin, A, out=t32)
-            ops.cast_f32_to_bf16(t32.view(-1), ts.view(-1), cfg.lora_scale)
+            ops.gemm(xin, A, out=ts, alpha=cfg.lora_scale)
             return ts
 
+        # every adapted linear is ONE launch: y = x W^T + b + ts B^T (second operand pair of the GEMM)
         if lora is None:
             ops.gemm(h, base[f"L{i}.wqkv"], out=qkv, bias=base[f"L{i}.bqkv"])
         else:
             ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", r, "l.ts")
-            u = self.buf("l.u", (T, 3 * d))
-            ops.gemm(ts, lora[f"L{i}.qkv.B"], out=u)
-            ops.gemm(h, base[f"L{i}.wqkv"], out=qkv, bias=base[f"L{i}.bqkv"], residual=u)
+            ops.gemm(h, base[f"L{i}.wqkv"], a2=ts, b2=lora[f"L{i}.qkv.B"], out=qkv, bias=base[f"L{i}.bqkv"])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh)
         ops.attn_fwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, H, dh, True,
                         1.0 / math.sqrt(dh))
-        ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
-        if lora is not None:
-            ts = lora_t(att, lora[f"L{i}.o.A"], "ts_o", r, "l.ts")
-            ops.gemm(ts, lora[f"L{i}.o.B"], out=xmid, accumulate=True)   # fp32 accumulate into the residual stream
-        ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         if lora is None:
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu)
+            ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
+        else:
+            ts = lora_t(att, lora[f"L{i}.o.A"], "ts_o", r, "l.ts")
+            ops.gemm(att, base[f"L{i}.wo"], a2=ts, b2=lora[f"L{i}.o.B"], out=xmid, residual=x)
+        ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
+        wgu = base[f"L{i}.wgu"]
+        if lora is None:
+            ops.gemm(h, wgu, out=gu)
         else:
             ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r, "l.ts2")
-            u = self.buf("l.ugu", (T, 2 * ff))
-            ops.gemm(ts[:, :r], lora[f"L{i}.w2.B"], out=u[:, :ff])
-            ops.gemm(ts[:, r:], lora[f"L{i}.w1.B"], out=u[:, ff:])
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu, residual=u)
+            ops.gemm(h, wgu[:ff], a2=ts[:, :r], b2=lora[f"L{i}.w2.B"], out=gu[:, :ff])
+            ops.gemm(h, wgu[ff:], a2=ts[:, r:], b2=lora[f"L{i}.w1.B"], out=gu[:, ff:])
         if xn is not None:
             act = self.buf("s.act", (T, ff))
             ops.swiglu_fwd(gu, act)
@@ -378,10 +375,8 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         dqkv = self.buf("b.dqkv", (T, 3 * d))
         datt = self.buf("b.datt", (T, d))
         delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
-        dt32 = self.buf("b.dt32", (T, 2 * r), torch.float32)   # dt = s * dy B of the two MLP adapters, side by side
-        dt = self.buf("b.dt", (T, 2 * r))
-        dr32 = self.buf("b.dr32", (T, r), torch.float32)       # same for the r-wide adapters (c_attn, attn.c_proj)
-        dr = self.buf("b.dr", (T, r))
+        dt = self.buf("b.dt", (T, 2 * r))   # dt = bf16(s * dy B) of the two MLP adapters, side by side
+        dr = self.buf("b.dr", (T, r))       # same for the r-wide adapters (c_attn, attn.c_proj)
         scale = 1.0 / math.sqrt(dh)
 
         for i in reversed(range(cfg.layers)):
@@ -400,31 +395,25 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             tsg = sb["ts_gu"]
             ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w2.B"])   # dB2 = dgate^T ts2
             ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"])   # dB1 = dup^T ts1
-            ops.gemm(gu[:, :ff], lora[f"L{i}.w2.B"], b_kmajor=False, out=dt32[:, :r])          # dt2 = dgate B2
-            ops.gemm(gu[:, ff:], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt32[:, r:])          # dt1 = dup B1
-            ops.cast_f32_to_bf16(dt32.view(-1), dt.view(-1), s)
+            ops.gemm(gu[:, :ff], lora[f"L{i}.w2.B"], b_kmajor=False, out=dt[:, :r], alpha=s)   # dt2 = s dgate B2
+            ops.gemm(gu[:, ff:], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt[:, r:], alpha=s)   # dt1 = s dup B1
             ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])              # dA = dt^T h2  [2r, d]
-            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                        # dh2 = dgu Wgu
-            ops.gemm(dt, lora[f"L{i}.gu.A"], b_kmajor=False, out=dnorm, accumulate=True)      #      + dt A
+            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=dt, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- attention output projection (LoRA on attn.c_proj)
             ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])     # dBo = dxmid^T ts_o
-            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr32)                        # dt = dxmid Bo
-            ops.cast_f32_to_bf16(dr32.view(-1), dr.view(-1), s)
+            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr, alpha=s)                 # dt = s dxmid Bo
             ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])            # dAo = dt^T att
-            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, out=datt)                         # datt = dxmid Wo
-            ops.gemm(dr, lora[f"L{i}.o.A"], b_kmajor=False, out=datt, accumulate=True)       #       + dt Ao
+            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
                             dqkv[:, 2 * d:], m.seqlens, m.n_seq, m.S, H, H, dh, True, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh, inverse=True)
             # ---- fused qkv projection (LoRA on attn.c_attn; the bias is frozen)
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
             ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"])
-            ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr32, out_dtype=torch.float32)
-            ops.cast_f32_to_bf16(dr32.view(-1), dr.view(-1), s)
+            ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr, alpha=s)
             ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])
-            ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)                     # dh1 = dqkv Wqkv
-            ops.gemm(dr, lora[f"L{i}.qkv.A"], b_kmajor=False, out=dnorm, accumulate=True)
+            ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.qkv.A"], out=dnorm)   # dh1 = dqkv Wqkv + dt A
             ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)
             self._reduce_bucket(self.layout.offsets[f"L{i}.qkv.A"],
                                 self.layout.offsets[f"L{i + 1}.qkv.A"] if i + 1 < cfg.layers else self.layout.size)

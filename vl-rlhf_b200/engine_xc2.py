@@ -243,9 +243,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
 
         def lora_t(xin, A, key, cols, scratch):
             ts = b[key] if key in b else self.buf(scratch, (T, cols))
-            t32 = self.buf(f"l.t32.{cols}", (T, cols), torch.float32)
-            ops.gemm(xin, A, out=t32)
-            ops.cast_f32_to_bf16(t32.view(-1), ts.view(-1), cfg.lora_scale)
+            ops.gemm(xin, A, out=ts, alpha=cfg.lora_scale)
             return ts
 
         ops.rmsnorm_fwd(x, base[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=b["rstd1"])
@@ -253,27 +251,25 @@ class XC2DPOEngine(QwenVLDPOEngine):
             ops.gemm(h, base[f"L{i}.wqkv"], out=qkv)
         else:
             ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", r, "l.ts")
-            u = self.buf("l.u", (T, cfg.qkv_dim))
-            ops.gemm(ts, lora[f"L{i}.qkv.B"], out=u)
-            ops.gemm(h, base[f"L{i}.wqkv"], out=qkv, residual=u)
+            ops.gemm(h, base[f"L{i}.wqkv"], a2=ts, b2=lora[f"L{i}.qkv.B"], out=qkv)   # y = x W^T + ts B^T in one launch
         self._plora_fwd(h, base[f"L{i}.p.qkv.A"], [(base[f"L{i}.p.qkv.B"], qkv, slice(0, pr))], m, "qkv")
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
         ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
                         True, 1.0 / math.sqrt(dh))
-        ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
-        if lora is not None:
+        if lora is None:
+            ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
+        else:
             ts = lora_t(att, lora[f"L{i}.o.A"], "ts_o", r, "l.ts")
-            ops.gemm(ts, lora[f"L{i}.o.B"], out=xmid, accumulate=True)
+            ops.gemm(att, base[f"L{i}.wo"], a2=ts, b2=lora[f"L{i}.o.B"], out=xmid, residual=x)
         self._plora_fwd(att, base[f"L{i}.p.o.A"], [(base[f"L{i}.p.o.B"], xmid, slice(0, pr))], m, "o")
         ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         if lora is None:
             ops.gemm(h, base[f"L{i}.wgu"], out=gu)
         else:
             ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r, "l.ts2")
-            u = self.buf("l.ugu", (T, 2 * ff))
-            ops.gemm(ts[:, :r], lora[f"L{i}.w1.B"], out=u[:, :ff])
-            ops.gemm(ts[:, r:], lora[f"L{i}.w3.B"], out=u[:, ff:])
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu, residual=u)
+            wgu = base[f"L{i}.wgu"]
+            ops.gemm(h, wgu[:ff], a2=ts[:, :r], b2=lora[f"L{i}.w1.B"], out=gu[:, :ff])
+            ops.gemm(h, wgu[ff:], a2=ts[:, r:], b2=lora[f"L{i}.w3.B"], out=gu[:, ff:])
         self._plora_fwd(h, base[f"L{i}.p.gu.A"], [(base[f"L{i}.p.w1.B"], gu[:, :ff], slice(0, pr)),
                                                    (base[f"L{i}.p.w3.B"], gu[:, ff:], slice(pr, 2 * pr))], m, "gu")
         if xn is not None or (lora is not None and "ts_d" in b):
@@ -282,9 +278,10 @@ class XC2DPOEngine(QwenVLDPOEngine):
             if lora is not None:
                 ts = lora_t(act, lora[f"L{i}.d.A"], "ts_d", r, "l.ts")
             if xn is not None:
-                ops.gemm(act, base[f"L{i}.wd"], out=xn, residual=xmid)
-                if lora is not None:
-                    ops.gemm(ts, lora[f"L{i}.d.B"], out=xn, accumulate=True)
+                if lora is None:
+                    ops.gemm(act, base[f"L{i}.wd"], out=xn, residual=xmid)
+                else:
+                    ops.gemm(act, base[f"L{i}.wd"], a2=ts, b2=lora[f"L{i}.d.B"], out=xn, residual=xmid)
                 self._plora_fwd(act, base[f"L{i}.p.d.A"], [(base[f"L{i}.p.d.B"], xn, slice(0, pr))], m, "d")
 
     # ------------------------------------------------------------------ forward of one pass
@@ -328,9 +325,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
         delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
-        dt32 = self.buf("b.dt32", (T, 2 * r), torch.float32)
-        dt = self.buf("b.dt", (T, 2 * r))
-        dr32 = self.buf("b.dr32", (T, r), torch.float32)
+        dt = self.buf("b.dt", (T, 2 * r))   # dt = bf16(s * dy B): gate | up side by side; dr: the r-wide adapters
         dr = self.buf("b.dr", (T, r))
         scale = 1.0 / math.sqrt(dh)
         for i in reversed(range(cfg.layers)):
@@ -345,11 +340,9 @@ class XC2DPOEngine(QwenVLDPOEngine):
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- down projection (LoRA + PLoRA on feed_forward.w2)
             ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"])      # dBd = dx^T ts_d
-            ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=dr32)
-            ops.cast_f32_to_bf16(dr32.view(-1), dr.view(-1), s)
+            ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=dr, alpha=s)
             ops.gemm(dr, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"])             # dAd = dt^T act
-            ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, out=dact)                          # dact = dx Wd
-            ops.gemm(dr, lora[f"L{i}.d.A"], b_kmajor=False, out=dact, accumulate=True)        #      + dt Ad
+            ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
             self._plora_bwd([(dx, base[f"L{i}.p.d.B"], slice(0, pr))], base[f"L{i}.p.d.A"], dact)
             # ---- gate | up
             ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h)                      # recompute h2
@@ -357,22 +350,18 @@ class XC2DPOEngine(QwenVLDPOEngine):
             tsg = sb["ts_gu"]
             ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"])
             ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w3.B"])
-            ops.gemm(gu[:, :ff], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt32[:, :r])
-            ops.gemm(gu[:, ff:], lora[f"L{i}.w3.B"], b_kmajor=False, out=dt32[:, r:])
-            ops.cast_f32_to_bf16(dt32.view(-1), dt.view(-1), s)
+            ops.gemm(gu[:, :ff], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt[:, :r], alpha=s)
+            ops.gemm(gu[:, ff:], lora[f"L{i}.w3.B"], b_kmajor=False, out=dt[:, r:], alpha=s)
             ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])
-            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                        # dh2 = dgu Wgu
-            ops.gemm(dt, lora[f"L{i}.gu.A"], b_kmajor=False, out=dnorm, accumulate=True)
+            ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=dt, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             self._plora_bwd([(gu[:, :ff], base[f"L{i}.p.w1.B"], slice(0, pr)), (gu[:, ff:], base[f"L{i}.p.w3.B"], slice(pr, 2 * pr))],
                             base[f"L{i}.p.gu.A"], dnorm)
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- attention output projection
             ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])
-            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr32)
-            ops.cast_f32_to_bf16(dr32.view(-1), dr.view(-1), s)
+            ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr, alpha=s)
             ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])
-            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, out=datt)
-            ops.gemm(dr, lora[f"L{i}.o.A"], b_kmajor=False, out=datt, accumulate=True)
+            ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)
             self._plora_bwd([(dx2, base[f"L{i}.p.o.B"], slice(0, pr))], base[f"L{i}.p.o.A"], datt)
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
                             dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale)
@@ -380,11 +369,9 @@ class XC2DPOEngine(QwenVLDPOEngine):
             # ---- fused qkv projection
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
             ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"])
-            ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr32)
-            ops.cast_f32_to_bf16(dr32.view(-1), dr.view(-1), s)
+            ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr, alpha=s)
             ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])
-            ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)
-            ops.gemm(dr, lora[f"L{i}.qkv.A"], b_kmajor=False, out=dnorm, accumulate=True)
+            ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.qkv.A"], out=dnorm)
             self._plora_bwd([(dqkv, base[f"L{i}.p.qkv.B"], slice(0, pr))], base[f"L{i}.p.qkv.A"], dnorm)
             ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)
             self._reduce_bucket(self.layout.offsets[f"L{i}.qkv.A"],

@@ -60,22 +60,36 @@ def perturb_(dst: torch.Tensor, base: torch.Tensor, other: torch.Tensor, alpha: 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
-         accumulate: bool = False) -> torch.Tensor:
-    """D[M,N] = epilogue(opA(a) @ opB(b)^T).
+         accumulate: bool = False, a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
+         alpha: float = 1.0) -> torch.Tensor:
+    """D[M,N] = epilogue(alpha * (opA(a) @ opB(b)^T + opA(a2) @ opB(b2)^T)).
 
-    a: [M,K] if a_kmajor else [K,M];  b: [N,K] if b_kmajor (nn.Linear weight) else [K,N]."""
+    a: [M,K] if a_kmajor else [K,M];  b: [N,K] if b_kmajor (nn.Linear weight) else [K,N];  the optional second pair
+    (a2: [M,K2] / [K2,M], b2: [N,K2] / [K2,N], same majorness) is contracted into the same accumulator -- the LoRA term
+    of a peft linear, or of its input gradient, without a round trip through HBM."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
     N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
     if K != Kb:
         raise ValueError(f"gemm: contraction mismatch {K} vs {Kb}")
+    K2 = 0
+    if (a2 is None) != (b2 is None):
+        raise ValueError("gemm: a2 and b2 come together")
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and b2.dtype == torch.bfloat16
+        M2, K2 = (a2.shape[0], a2.shape[1]) if a_kmajor else (a2.shape[1], a2.shape[0])
+        N2, K2b = (b2.shape[0], b2.shape[1]) if b_kmajor else (b2.shape[1], b2.shape[0])
+        if (M2, N2) != (M, N) or K2 != K2b:
+            raise ValueError(f"gemm: second operand pair [{M2},{K2}] x [{N2},{K2b}] does not match M={M}, N={N}")
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.shape == (M, N)
-    check(_L.vlb200_gemm_bf16(_ptr(a), _rowmajor_ld(a), int(a_kmajor), _ptr(b), _rowmajor_ld(b), int(b_kmajor),
-                              _ptr(out), _rowmajor_ld(out), _dt(out), M, N, K, _ptr(bias), act, _ptr(residual),
-                              _dt(residual) if residual is not None else BF16,
-                              _rowmajor_ld(residual) if residual is not None else 0, int(accumulate), _stream()))
+    check(_L.vlb200_gemm_bf16_ex(_ptr(a), _rowmajor_ld(a), int(a_kmajor), _ptr(b), _rowmajor_ld(b), int(b_kmajor),
+                                 _ptr(a2), _rowmajor_ld(a2) if a2 is not None else 0, _ptr(b2),
+                                 _rowmajor_ld(b2) if b2 is not None else 0, K2,
+                                 _ptr(out), _rowmajor_ld(out), _dt(out), M, N, K, float(alpha), _ptr(bias), act, _ptr(residual),
+                                 _dt(residual) if residual is not None else BF16,
+                                 _rowmajor_ld(residual) if residual is not None else 0, int(accumulate), _stream()))
     return out
 
 
