@@ -78,6 +78,15 @@ int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const void* B, int
                         const void* bias, int act, const void* residual, int residual_dtype, int ldr, int accumulate,
                         void* stream);
 
+/* Llama/Mistral MLP front half in one launch (modeling_llama.py:182-184): act[M,ff] = silu(A Wg^T) * (A Wu^T) with
+ * Wgu = [Wg; Wu] row-major [2*ff, K] (nn.Linear layout).  The CTA-pair kernel puts 128 gate columns and the matching 128 up
+ * columns into one accumulator (CTA 0 loads the gate rows of a tile, CTA 1 the up rows) and applies SwiGLU in the epilogue
+ * on the bf16-rounded projections -- bit-identical to vlb200_gemm_bf16 into gu followed by vlb200_swiglu_fwd.  gu [M, 2*ff]
+ * receives the bf16 gate|up projections when write_gu != 0 (needed by vlb200_swiglu_bwd) and is otherwise scratch that is
+ * only touched for shapes the pair kernel does not take (M < 256 or ff % 128 != 0: GEMM + elementwise kernel).          */
+int vlb200_gemm_swiglu_bf16(const void* A, int lda, const void* Wgu, int ldb, void* gu, int ld_gu, int write_gu, void* act,
+                            int ld_act, int M, int ff, int K, void* stream);
+
 /* mode 1: 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, B tile split across the pair) where M,N >= 256;
  * mode 0: single-CTA 128x256 tiles.  Default 1; the environment variable VLB200_GEMM_2CTA=0 selects mode 0.   */
 int vlb200_set_gemm_mode(int mode);

@@ -82,6 +82,18 @@ def gemm(a, b, *, a_kmajor=True, b_kmajor=True, out=None, out_dtype=torch.bfloat
     return out
 
 
+def gemm_swiglu(a, wgu, gu, act, write_gu=True):
+    ff = wgu.shape[0] // 2
+    if wgu.shape[1] != a.shape[1] or tuple(gu.shape) != (a.shape[0], 2 * ff) or tuple(act.shape) != (a.shape[0], ff):
+        raise ValueError("gemm_swiglu: shape mismatch")
+    y = (a.float() @ wgu.float().t()).to(torch.bfloat16)
+    act.copy_((F.silu(y[:, :ff].float()) * y[:, ff:].float()).to(torch.bfloat16))
+    if write_gu:
+        gu.copy_(y)
+    _c()
+    return act
+
+
 def logps_fwd(logits, target, n_seq, weight=None, average_log_prob=False):
     rows, V = logits.shape
     if target.numel() != rows or rows % n_seq != 0:

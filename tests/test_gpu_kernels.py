@@ -133,6 +133,32 @@ def test_gemm_split_k_skinny_outputs(ops, M, N, K, K2, ak, bk):
     close(out16, want + 1.0, rtol=1e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize("M,ff,K", [(600, 384, 320), (1000, 1408, 512), (256, 128, 64), (130, 256, 192), (512, 200, 128)])
+def test_gemm_swiglu_epilogue_bit_equal_to_two_kernels(ops, M, ff, K):
+    """act = silu(a Wg^T) * (a Wu^T) from the CTA-pair kernel's epilogue == GEMM into gate|up followed by the elementwise
+    SwiGLU kernel, bit for bit (the last two shapes take the documented fallback: M < 256 / ff % 128 != 0)."""
+    torch.manual_seed(M + ff + K)
+    a = bf(torch.randn(M, K, device="cuda") * 0.5)
+    wgu = bf(torch.randn(2 * ff, K, device="cuda") * 0.2)
+    gu_ref = ops.gemm(a, wgu)
+    act_ref = ops.swiglu_fwd(gu_ref)
+    gu = torch.full((M, 2 * ff), 7.0, device="cuda", dtype=torch.bfloat16)
+    act = torch.empty(M, ff, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_swiglu(a, wgu, gu, act, write_gu=True)
+    assert torch.equal(act, act_ref) and torch.equal(gu, gu_ref)
+    fused = M >= 256 and ff % 128 == 0
+    gu.fill_(7.0)
+    act.zero_()
+    ops.gemm_swiglu(a, wgu, gu, act, write_gu=False)
+    assert torch.equal(act, act_ref)
+    if fused:
+        assert bool((gu == 7.0).all())     # the projections never reached HBM
+    want = F.silu(a.float() @ wgu[:ff].float().t()) * (a.float() @ wgu[ff:].float().t())
+    close(act, want, rtol=2e-2, atol=2e-2)
+    with pytest.raises(ValueError):
+        ops.gemm_swiglu(a, wgu, gu, act[:, :-8])
+
+
 # ------------------------------------------------------------------ norms
 @pytest.mark.parametrize("rows,cols", [(37, 128), (1000, 4096), (5, 1024)])
 def test_rmsnorm_fwd_bwd(ops, rows, cols):

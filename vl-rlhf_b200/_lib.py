@@ -22,6 +22,8 @@ SIGNATURES = {
     "vlb200_gemm_bf16_ex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int,
                                     c_int, c_int, c_void_p]),
+    "vlb200_gemm_swiglu_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_void_p]),
     "vlb200_set_gemm_mode": (c_int, [c_int]),
     "vlb200_logps_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),

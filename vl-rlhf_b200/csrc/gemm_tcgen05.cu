@@ -31,6 +31,10 @@ struct Params {
     // stores its raw fp32 partial tile to ws[split][M][N]; splitk_reduce_kernel sums the partials in a fixed order
     int splits, kb_per_split;
     float* ws;
+    // SwiGLU pair kernel: B = [gate rows | up rows] ([2*ff, K]); D = act [M, ff]; G (optional) receives the bf16 gate|up
+    int ff;
+    __nv_bfloat16* G;
+    long long ldg;
     void* D;
     long long ldd;
     int out_f32;
@@ -436,7 +440,38 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
 
 constexpr int PAIR_M = 256, PAIR_N = 256, HALF_N = 128;
 
-template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+// SwiGLU epilogue for 32 consecutive columns of one row: g, u are rounded to bf16 first and act is computed from the rounded
+// values with the arithmetic of swiglu_fwd_kernel (elementwise.cu), so the fused result equals GEMM -> swiglu_fwd bit for
+// bit and the backward's recompute from the saved gate|up stays consistent (modeling_llama.py:182-184).
+__device__ __forceinline__ void epilogue_swiglu_32(const Params& p, int row, int col0, const uint32_t (&rg)[32],
+                                                   const uint32_t (&ru)[32]) {
+    if (row >= p.M || col0 >= p.ff) return;
+    __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
+    __nv_bfloat16* gp = p.G != nullptr ? p.G + (long long)row * p.ldg + col0 : nullptr;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        if (col0 + j8 * 8 < p.ff) {
+            uint4 gb, ub, ob;
+            uint32_t* gw = reinterpret_cast<uint32_t*>(&gb);
+            uint32_t* uw = reinterpret_cast<uint32_t*>(&ub);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&ob);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                gw[q] = pack_bf16x2(__uint_as_float(rg[j8 * 8 + 2 * q]), __uint_as_float(rg[j8 * 8 + 2 * q + 1]));
+                uw[q] = pack_bf16x2(__uint_as_float(ru[j8 * 8 + 2 * q]), __uint_as_float(ru[j8 * 8 + 2 * q + 1]));
+                const float2 g = unpack_bf16x2(gw[q]), u = unpack_bf16x2(uw[q]);
+                ow[q] = pack_bf16x2(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
+            }
+            *reinterpret_cast<uint4*>(ap + j8 * 8) = ob;
+            if (gp != nullptr) {
+                *reinterpret_cast<uint4*>(gp + j8 * 8) = gb;
+                *reinterpret_cast<uint4*>(gp + p.ff + j8 * 8) = ub;
+            }
+        }
+    }
+}
+
+template <int STAGES, bool A_KMAJOR, bool B_KMAJOR, bool SWIGLU = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                       const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_b2, const Params p) {
@@ -492,7 +527,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
                 int m_blk, n_blk;
                 tile_coords(p, tile, m_blk, n_blk);
-                const int m0 = m_blk * PAIR_M + (int)rank * BLOCK_M, n0 = n_blk * PAIR_N + (int)rank * HALF_N;
+                // SWIGLU: the pair's 256 accumulator columns are 128 gate columns (CTA 0's half of B) next to the SAME 128 up
+                // columns (CTA 1's half, p.ff rows further down the fused gate|up weight)
+                const int m0 = m_blk * PAIR_M + (int)rank * BLOCK_M;
+                const int n0 = SWIGLU ? n_blk * HALF_N + (int)rank * p.ff : n_blk * PAIR_N + (int)rank * HALF_N;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
@@ -562,12 +600,23 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             mbar_wait(&tmem_full_bar[acc], acc_phase, 400 + acc);
             tcgen05_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * PAIR_N;
+            if constexpr (SWIGLU) {
 #pragma unroll 1
-            for (int c = 0; c < PAIR_N / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr0 + c * 32, r);
-                tmem_ld_wait();
-                epilogue_store_32(p, row, n0 + c * 32, r);
+                for (int c = 0; c < HALF_N / 32; ++c) {
+                    uint32_t rg[32], ru[32];
+                    tmem_ld_32x32(taddr0 + c * 32, rg);
+                    tmem_ld_32x32(taddr0 + HALF_N + c * 32, ru);
+                    tmem_ld_wait();
+                    epilogue_swiglu_32(p, row, n_blk * HALF_N + c * 32, rg, ru);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < PAIR_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr0 + c * 32, r);
+                    tmem_ld_wait();
+                    epilogue_store_32(p, row, n0 + c * 32, r);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -685,11 +734,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     return VLB200_OK;
 }
 
-template <int STAGES, bool A_KMAJOR, bool B_KMAJOR>
+template <int STAGES, bool A_KMAJOR, bool B_KMAJOR, bool SWIGLU = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                        const Params& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_TILE_BYTES + HALF_N * BLOCK_K * 2) + 256 + 1024;
-    auto kern = gemm_bf16_2cta_kernel<STAGES, A_KMAJOR, B_KMAJOR>;
+    auto kern = gemm_bf16_2cta_kernel<STAGES, A_KMAJOR, B_KMAJOR, SWIGLU>;
     static bool configured = false;
     if (!configured) {
         VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -826,6 +875,7 @@ extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const v
     p.num_k_blocks = p.kb1 + (dual ? (K2 + BLOCK_K - 1) / BLOCK_K : 0);
     p.alpha = alpha;
     p.splits = splits; p.kb_per_split = kb_per_split; p.ws = nullptr;
+    p.ff = 0; p.G = nullptr; p.ldg = 0;
     if (splits > 1) {
         rc = splitk_workspace((size_t)splits * M * N * sizeof(float), &p.ws);
         if (rc) return rc;
@@ -861,6 +911,62 @@ extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void
                                 const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
     return vlb200_gemm_bf16_ex(A, lda, a_kmajor, B, ldb, b_kmajor, nullptr, 0, nullptr, 0, 0, D, ldd, out_dtype, M, N, K, 1.0f,
                                bias, act, residual, residual_dtype, ldr, accumulate, stream);
+}
+
+extern "C" int vlb200_swiglu_fwd(const void* gate_up, int64_t ld_gu, void* act, int64_t ld_act, int rows, int ff, void* stream);
+
+extern "C" int vlb200_gemm_swiglu_bf16(const void* A, int lda, const void* Wgu, int ldb, void* gu, int ld_gu, int write_gu,
+                                       void* act, int ld_act, int M, int ff, int K, void* stream) {
+    using namespace vlb;
+    using namespace vlb::gemm;
+    VLB_REQUIRE(A && Wgu && gu && act, "gemm_swiglu: null pointer");
+    VLB_REQUIRE(M > 0 && ff > 0 && K > 0 && ff % 8 == 0, "gemm_swiglu: bad shape M=%d ff=%d K=%d", M, ff, K);
+    VLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ld_gu % 8 == 0 && ld_act % 8 == 0 && lda >= K && ldb >= K && ld_gu >= 2 * ff &&
+                    ld_act >= ff, "gemm_swiglu: bad leading dimensions");
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("VLB200_GEMM_2CTA");
+        g_gemm_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    static const bool fuse_on = [] { const char* e = getenv("VLB200_FUSE_SWIGLU"); return !(e && e[0] == '0'); }();
+    if (!(fuse_on && g_gemm_mode == 1 && M >= 256 && ff % HALF_N == 0)) {
+        // shapes the CTA-pair kernel does not take: plain GEMM into the gate|up buffer, then the elementwise kernel
+        int rc = vlb200_gemm_bf16(A, lda, 1, Wgu, ldb, 1, gu, ld_gu, VLB200_BF16, M, 2 * ff, K, nullptr, VLB200_ACT_NONE, nullptr,
+                                  VLB200_BF16, 0, 0, stream);
+        if (rc) return rc;
+        return vlb200_swiglu_fwd(gu, ld_gu, act, ld_act, M, ff, stream);
+    }
+    VLB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wgu) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0,
+                "gemm_swiglu: pointers must be 16-byte aligned");
+    CUtensorMap ta, tb;
+    int rc = get_tensor_map(A, K, M, lda, BLOCK_K, BLOCK_M, &ta);
+    if (rc) return rc;
+    rc = get_tensor_map(Wgu, K, 2 * ff, ldb, BLOCK_K, HALF_N, &tb);
+    if (rc) return rc;
+    Params p;
+    p.M = M; p.N = ff; p.K = K;
+    p.num_m_blocks = (M + PAIR_M - 1) / PAIR_M;
+    p.num_n_blocks = ff / HALF_N;
+    p.num_tiles = p.num_m_blocks * p.num_n_blocks;
+    p.kb1 = p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p.alpha = 1.0f;
+    p.splits = 1; p.kb_per_split = p.num_k_blocks; p.ws = nullptr;
+    p.D = act; p.ldd = ld_act; p.out_f32 = 0;
+    p.bias = nullptr; p.act = VLB200_ACT_NONE; p.residual = nullptr; p.residual_f32 = 0; p.ldr = 0; p.accumulate = 0;
+    p.ff = ff; p.G = write_gu ? reinterpret_cast<__nv_bfloat16*>(gu) : nullptr; p.ldg = ld_gu;
+    {   // same raster choice as the plain GEMM: a pair tile holds 256 rows of A and 128 gate + 128 up rows of B
+        static const double budget_mb = [] { const char* e = getenv("VLB200_RASTER_MB"); return e ? atof(e) : 32.0; }();
+        const double budget = budget_mb * 1024 * 1024;
+        const double a_blk = (double)PAIR_M * K * 2, b_blk = (double)PAIR_N * K * 2;
+        const double a_bytes = (double)M * K * 2, b_bytes = 2.0 * ff * K * 2;
+        int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
+        int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
+        const double cost_m = a_bytes + b_bytes * ((p.num_m_blocks + gm - 1) / gm);
+        const double cost_n = b_bytes + a_bytes * ((p.num_n_blocks + gn - 1) / gn);
+        p.group_along_n = cost_n < cost_m;
+        p.group = p.group_along_n ? gn : gm;
+    }
+    return launch_2cta<6, true, true, true>(ta, tb, ta, tb, p, as_stream(stream));
 }
 
 extern "C" int vlb200_set_gemm_mode(int mode) {

@@ -347,9 +347,11 @@ class LlavaDPOEngine:
                     gu=self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff)))
 
     def _layer_fwd(self, w: Weights, i: int, x: torch.Tensor, b: Dict[str, torch.Tensor], m: "ops.MergeIndex",
-                   xn: Optional[torch.Tensor]):
+                   xn: Optional[torch.Tensor], keep_gu: bool = True):
         """Decoder layer i on the fp32 residual stream x -> xn (K9-K14).  xn=None stops after the gate|up GEMM: the
-        recompute of a checkpointed layer needs the saved-for-backward tensors, not the layer output."""
+        recompute of a checkpointed layer needs the saved-for-backward tensors, not the layer output.  keep_gu=False
+        (reference pass, checkpointed forward): the gate|up projections are consumed inside the GEMM epilogue and never
+        reach HBM."""
         cfg = self.cfg
         d, T = cfg.hidden, m.n_seq * m.S
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
@@ -363,10 +365,11 @@ class LlavaDPOEngine:
                         True, 1.0 / math.sqrt(dh))
         ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
         ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
-        ops.gemm(h, w[f"L{i}.wgu"], out=gu)
-        if xn is not None:
+        if xn is None:
+            ops.gemm(h, w[f"L{i}.wgu"], out=gu)
+        else:
             act = self.buf("s.act", (T, cfg.ff))
-            ops.swiglu_fwd(gu, act)
+            ops.gemm_swiglu(h, w[f"L{i}.wgu"], gu, act, write_gu=keep_gu)   # SwiGLU in the gate|up GEMM's epilogue
             ops.gemm(act, w[f"L{i}.wd"], out=xn, residual=xmid)
 
     # ------------------------------------------------------------------ forward of one model copy
@@ -415,7 +418,7 @@ class LlavaDPOEngine:
             keep = save and not ckpt
             b = self._layer_bufs("a" if keep else "s", f".{i}" if keep else "", m)
             xn = self.buf(f"x.{i + 1}" if save else ("s.x1" if i % 2 == 0 else "s.x0"), (T, d), torch.float32)
-            self._layer_fwd(w, i, x, b, m, xn)
+            self._layer_fwd(w, i, x, b, m, xn, keep_gu=keep)
             x = xn
         return self._head_forward(x, w["norm"], w["lm_head"], m, feats, save, ddpo_weight)
 

@@ -329,15 +329,16 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.gemm(att, base[f"L{i}.wo"], a2=ts, b2=lora[f"L{i}.o.B"], out=xmid, residual=x)
         ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         wgu = base[f"L{i}.wgu"]
-        if lora is None:
-            ops.gemm(h, wgu, out=gu)
+        act = self.buf("s.act", (T, ff))
+        if lora is None:   # reference pass: SwiGLU in the GEMM epilogue, gate|up never reaches HBM
+            ops.gemm_swiglu(h, wgu, gu, act, write_gu=False)
         else:
             ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r, "l.ts2")
             ops.gemm(h, wgu[:ff], a2=ts[:, :r], b2=lora[f"L{i}.w2.B"], out=gu[:, :ff])
             ops.gemm(h, wgu[ff:], a2=ts[:, r:], b2=lora[f"L{i}.w1.B"], out=gu[:, ff:])
         if xn is not None:
-            act = self.buf("s.act", (T, ff))
-            ops.swiglu_fwd(gu, act)
+            if lora is not None:
+                ops.swiglu_fwd(gu, act)
             ops.gemm(act, base[f"L{i}.wd"], out=xn, residual=xmid)
 
     # ------------------------------------------------------------------ forward of one pass

@@ -93,6 +93,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     return out
 
 
+def gemm_swiglu(a: torch.Tensor, wgu: torch.Tensor, gu: torch.Tensor, act: torch.Tensor, write_gu: bool = True) -> torch.Tensor:
+    """act[M,ff] = silu(a Wg^T) * (a Wu^T), wgu = [Wg; Wu] ([2*ff, K]); gu [M, 2*ff] receives the bf16 gate|up projections
+    when write_gu (the backward needs them) and is scratch otherwise.  Bit-identical to gemm(a, wgu, out=gu); swiglu_fwd(gu)."""
+    assert a.dtype == wgu.dtype == gu.dtype == act.dtype == torch.bfloat16
+    M, K = a.shape
+    ff = wgu.shape[0] // 2
+    if wgu.shape[1] != K or tuple(gu.shape) != (M, 2 * ff) or tuple(act.shape) != (M, ff):
+        raise ValueError("gemm_swiglu: shape mismatch")
+    check(_L.vlb200_gemm_swiglu_bf16(_ptr(a), _rowmajor_ld(a), _ptr(wgu), _rowmajor_ld(wgu), _ptr(gu), _rowmajor_ld(gu),
+                                     int(write_gu), _ptr(act), _rowmajor_ld(act), M, ff, K, _stream()))
+    return act
+
+
 def set_gemm_mode(mode: int):
     """1: CTA-pair (cta_group::2) 256x256 tiles where the shape allows; 0: single-CTA 128x256 tiles."""
     check(_L.vlb200_set_gemm_mode(int(mode)))
