@@ -18,6 +18,25 @@ if which == "gemm":
     out = torch.empty(T, 2 * ff, dtype=bf, device=dev)
     for _ in range(4):
         ops.gemm(x, w, out=out)
+elif which == "gemm_swiglu":   # gate|up GEMM with SwiGLU in the epilogue (reference pass: gate|up never written)
+    x = torch.randn(T, d, device=dev).to(bf)
+    w = torch.randn(2 * ff, d, device=dev).to(bf) * 0.02
+    gu = torch.empty(T, 2 * ff, dtype=bf, device=dev)
+    act = torch.empty(T, ff, dtype=bf, device=dev)
+    for _ in range(4):
+        ops.gemm_swiglu(x, w, gu, act, write_gu=False)
+elif which == "lora":          # LoRA linear in one launch (second operand pair) and a split-K weight gradient
+    r = 128
+    x = torch.randn(T, d, device=dev).to(bf)
+    w = torch.randn(ff, d, device=dev).to(bf) * 0.02
+    ts = torch.randn(T, 2 * r, device=dev).to(bf)
+    Bm = torch.randn(ff, r, device=dev).to(bf) * 0.02
+    out = torch.empty(T, 2 * ff, dtype=bf, device=dev)
+    dy = torch.randn(T, d, device=dev).to(bf)
+    dB = torch.empty(d, r, dtype=bf, device=dev)
+    for _ in range(4):
+        ops.gemm(x, w, a2=ts[:, :r], b2=Bm, out=out[:, :ff])
+        ops.gemm(dy, ts[:, :r], a_kmajor=False, b_kmajor=False, out=dB)
 elif which == "attn":
     qkv = torch.randn(T, 3 * d, device=dev).to(bf)
     out = torch.empty(T, d, dtype=bf, device=dev)
