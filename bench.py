@@ -44,13 +44,12 @@ def peaks():
 
 
 def _traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    """(DRAM bytes per launch of the dominant kernel, provenance) from the committed `ncu --set full` capture (profiles/)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
-                "source": t["source"]}
+        return t["dram_bytes_read"] + t["dram_bytes_write"], {"algorithmic_bytes": t["algorithmic_bytes"], "source": t["source"]}
     except Exception:
-        return None
+        return None, None
 
 
 def step_flops(cfg, n_pairs, S, rows_lm):
@@ -119,6 +118,40 @@ class ClockSampler:
 # CPU arm: the reference's PyTorch-CPU path (oracle port), bounded sample of the same workload
 # ----------------------------------------------------------------------------------------------
 _CPU_W = {}
+_CPU_THREADS = []
+
+
+def host_threads() -> int:
+    """Threads for the CPU arm: the CPUs this process may run on (affinity mask, capped by the cgroup CPU quota), then the
+    fastest of {n, n/2, n/4, ...} on a 4096^3 fp32 matmul -- a box that shows 128 logical CPUs ran the sample 3x SLOWER
+    with 128 torch threads than this 8-core container (r1: 35.8 s vs 1.2 s for the ViT part)."""
+    if _CPU_THREADS:
+        return _CPU_THREADS[0]
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    cands, c = [], n
+    while c >= 4:
+        cands.append(c)
+        c //= 2
+    best, best_t = n, float("inf")
+    if len(cands) > 1:
+        a = torch.randn(4096, 4096)
+        for c in cands:
+            torch.set_num_threads(c)
+            a @ a
+            t0 = time.perf_counter()
+            a @ a
+            dt = time.perf_counter() - t0
+            if dt < best_t * 0.95:   # prefer more threads unless fewer are clearly faster
+                best, best_t = c, dt
+    _CPU_THREADS.append(best)
+    return best
 
 
 def cpu_sample_setup(threads: int):
@@ -194,7 +227,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     cpu_sample_setup(cores)
     for _ in range(min(args.warmup, 1)):
         cpu_sample_seconds_per_pair(cores)
@@ -208,8 +241,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": sec_per_pair * PAIRS_PER_GPU * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU host cores only; extrapolated from a bounded sample"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE_DESC,
-                             "parts_s": {k: round(x, 3) for k, x in parts.items()}},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
+                             "sample": CPU_SAMPLE_DESC, "parts_s": {k: round(x, 3) for k, x in parts.items()}},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -299,7 +332,23 @@ def run_b200(args):
     gemm_ms = timed(lambda: ops.gemm(a, wgu, out=out), 10)
     pk, pk_src = peaks()
     gemm_tf = 2.0 * T * 2 * cfg.ff * cfg.hidden / gemm_ms / 1e9
+    traffic, traffic_detail = _traffic()
     flops = step_flops(cfg, PAIRS_PER_GPU, S, rows_lm)
+    # second kernel family of the north_star ("fraction of the attention/GEMM roofline"): the fused causal attention of one
+    # decoder layer, forward and backward, on random q|k|v at the step's shape; algorithmic FLOPs = causal half of QK^T + PV
+    nseq, H, KV, dh = 2 * PAIRS_PER_GPU, cfg.heads, cfg.kv_heads, cfg.head_dim
+    hd, kvd = H * dh, KV * dh
+    qkv = (torch.randn(T, cfg.qkv_dim, device="cuda") * 0.5).to(torch.bfloat16)
+    att, datt, dqkv = torch.empty(T, hd, dtype=torch.bfloat16, device="cuda"), (torch.randn(T, hd, device="cuda") * 0.1).to(torch.bfloat16), torch.empty_like(qkv)
+    lse, delta = (torch.empty(nseq, H, S, dtype=torch.float32, device="cuda") for _ in range(2))
+    full = torch.full((nseq,), S, dtype=torch.int32, device="cuda")
+    sc = 1.0 / dh ** 0.5
+    q_, k_, v_ = qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:]
+    af_ms = timed(lambda: ops.attn_fwd_tc(q_, k_, v_, att, lse, full, nseq, S, H, KV, dh, True, sc), 10)
+    ab_ms = timed(lambda: ops.attn_bwd_tc(q_, k_, v_, att, datt, lse, delta, dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:],
+                                          full, nseq, S, H, KV, dh, True, sc), 10)
+    attn_fl = 4.0 * S * S * dh * H * nseq / 2
+    del qkv, att, datt, dqkv
     if rank == 0:
         pairs = PAIRS_PER_GPU * world
         h2d = sum(int(t.numel() * t.element_size()) for t in (cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
@@ -321,13 +370,21 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,K-major> (tcgen05 cta_group::2, 256x256 pair tiles, gate_up fwd shape)",
                          "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                         "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": _traffic()},
+                         "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": traffic, "traffic_detail": traffic_detail},
+            "roofline_attention": [
+                {"bound": "tensor", "kernel": f"attn_fwd_tc_kernel<{dh}> (tcgen05 causal FlashAttention forward, one decoder layer)",
+                 "achieved": attn_fl / af_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": attn_fl / af_ms / 1e9 / pk["bf16_tflops"],
+                 "ms": af_ms},
+                {"bound": "tensor", "kernel": f"attn_delta_kernel + attn_bwd_tc_kernel<{dh},dKdV> + <{dh},dQ> (backward of the same layer)",
+                 "achieved": 2.5 * attn_fl / ab_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                 "frac": 2.5 * attn_fl / ab_ms / 1e9 / pk["bf16_tflops"], "ms": ab_ms}],
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = host_threads()
             sec, parts = cpu_sample_seconds_per_pair(cores)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE_DESC,
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
+                                    "sample": CPU_SAMPLE_DESC,
                                     "parts_s": {k: round(x, 3) for k, x in parts.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
