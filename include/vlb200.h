@@ -91,6 +91,11 @@ int vlb200_gemm_swiglu_bf16(const void* A, int lda, const void* Wgu, int ldb, vo
  * mode 0: single-CTA 128x256 tiles.  Default 1; the environment variable VLB200_GEMM_2CTA=0 selects mode 0.   */
 int vlb200_set_gemm_mode(int mode);
 
+/* Tile rasterisation budget in MB: the group of operand panels the concurrently running tiles keep L2-resident while the
+ * other operand streams past (default 32, or the environment variable VLB200_RASTER_MB; mb <= 0 restores that).  A tuning
+ * knob: results do not depend on it.                                                                                 */
+int vlb200_set_gemm_raster_mb(double mb);
+
 /* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
  * logits: [rows, V] (dtype bf16|f32, row stride ld_logits elements).  Row r predicts target[r];
  * target[r] < 0 (label_pad) rows are skipped without being read.  rows = n_seq * rows_per_seq

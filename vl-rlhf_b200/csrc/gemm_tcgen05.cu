@@ -779,6 +779,26 @@ static int splitk_workspace(size_t bytes, float** out) {
     return VLB200_OK;
 }
 
+// Rasterisation: tiles of `group` blocks of one operand sweep the other dimension together, so that group (budget MB of
+// operand panels) stays L2-resident while the other operand streams past once per group.  The orientation/size with the
+// fewest modelled DRAM re-reads wins.  Budget: vlb200_set_gemm_raster_mb() > VLB200_RASTER_MB > 32 (r1d probe: 32 MB is the
+// best single setting at the config-2 shapes).
+static double g_raster_mb = -1.0;
+static void choose_raster(Params& p, double M, double N, double Kt, int TM, int TN) {
+    if (g_raster_mb <= 0.0) {
+        const char* e = getenv("VLB200_RASTER_MB");
+        g_raster_mb = e && atof(e) > 0.0 ? atof(e) : 32.0;
+    }
+    const double budget = g_raster_mb * 1024 * 1024;
+    const double a_blk = TM * Kt * 2, b_blk = TN * Kt * 2;
+    const double a_bytes = M * Kt * 2, b_bytes = N * Kt * 2;
+    int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
+    int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
+    const double cost_m = a_bytes + b_bytes * ((p.num_m_blocks + gm - 1) / gm);
+    const double cost_n = b_bytes + a_bytes * ((p.num_n_blocks + gn - 1) / gn);
+    p.group_along_n = cost_n < cost_m;
+    p.group = p.group_along_n ? gn : gm;
+}
 static int g_gemm_mode = -1;  // -1: read VLB200_GEMM_2CTA on first use; 0: 1-CTA kernel; 1: 2-CTA pairs where the shape allows
 
 template <int BLOCK_N, int STAGES>
@@ -887,19 +907,7 @@ extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const v
     p.residual_f32 = residual_dtype == VLB200_F32;
     p.ldr = ldr;
     p.accumulate = accumulate;
-    {   // pick the raster that minimises DRAM re-reads with a ~32 MB resident operand group (VLB200_RASTER_MB overrides)
-        static const double budget_mb = [] { const char* e = getenv("VLB200_RASTER_MB"); return e ? atof(e) : 32.0; }();
-        const double budget = budget_mb * 1024 * 1024;
-        const double Kt = (double)K + (dual ? K2 : 0);
-        const double a_blk = (double)TM * Kt * 2, b_blk = (double)TN * Kt * 2;
-        const double a_bytes = (double)M * Kt * 2, b_bytes = (double)N * Kt * 2;
-        int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
-        int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
-        const double cost_m = a_bytes + b_bytes * ((p.num_m_blocks + gm - 1) / gm);
-        const double cost_n = b_bytes + a_bytes * ((p.num_n_blocks + gn - 1) / gn);
-        p.group_along_n = cost_n < cost_m;
-        p.group = p.group_along_n ? gn : gm;
-    }
+    vlb::gemm::choose_raster(p, (double)M, (double)N, (double)K + (dual ? K2 : 0), TM, TN);
     cudaStream_t s = as_stream(stream);
     if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
     if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
@@ -954,19 +962,14 @@ extern "C" int vlb200_gemm_swiglu_bf16(const void* A, int lda, const void* Wgu, 
     p.D = act; p.ldd = ld_act; p.out_f32 = 0;
     p.bias = nullptr; p.act = VLB200_ACT_NONE; p.residual = nullptr; p.residual_f32 = 0; p.ldr = 0; p.accumulate = 0;
     p.ff = ff; p.G = write_gu ? reinterpret_cast<__nv_bfloat16*>(gu) : nullptr; p.ldg = ld_gu;
-    {   // same raster choice as the plain GEMM: a pair tile holds 256 rows of A and 128 gate + 128 up rows of B
-        static const double budget_mb = [] { const char* e = getenv("VLB200_RASTER_MB"); return e ? atof(e) : 32.0; }();
-        const double budget = budget_mb * 1024 * 1024;
-        const double a_blk = (double)PAIR_M * K * 2, b_blk = (double)PAIR_N * K * 2;
-        const double a_bytes = (double)M * K * 2, b_bytes = 2.0 * ff * K * 2;
-        int gm = (int)(budget / a_blk); gm = gm < 4 ? 4 : gm; gm = gm > p.num_m_blocks ? p.num_m_blocks : gm;
-        int gn = (int)(budget / b_blk); gn = gn < 2 ? 2 : gn; gn = gn > p.num_n_blocks ? p.num_n_blocks : gn;
-        const double cost_m = a_bytes + b_bytes * ((p.num_m_blocks + gm - 1) / gm);
-        const double cost_n = b_bytes + a_bytes * ((p.num_n_blocks + gn - 1) / gn);
-        p.group_along_n = cost_n < cost_m;
-        p.group = p.group_along_n ? gn : gm;
-    }
+    // a pair tile holds 256 rows of A and 128 gate + 128 up rows of B
+    vlb::gemm::choose_raster(p, (double)M, 2.0 * ff, (double)K, PAIR_M, PAIR_N);
     return launch_2cta<6, true, true, true>(ta, tb, ta, tb, p, as_stream(stream));
+}
+
+extern "C" int vlb200_set_gemm_raster_mb(double mb) {
+    vlb::gemm::g_raster_mb = mb;  // <= 0: back to VLB200_RASTER_MB / the default on the next launch
+    return VLB200_OK;
 }
 
 extern "C" int vlb200_set_gemm_mode(int mode) {

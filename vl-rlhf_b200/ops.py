@@ -106,6 +106,11 @@ def gemm_swiglu(a: torch.Tensor, wgu: torch.Tensor, gu: torch.Tensor, act: torch
     return act
 
 
+def set_gemm_raster_mb(mb: float):
+    """L2 budget (MB) of the tile rasterisation; <= 0 restores VLB200_RASTER_MB / the default.  Tuning only."""
+    check(_L.vlb200_set_gemm_raster_mb(float(mb)))
+
+
 def set_gemm_mode(mode: int):
     """1: CTA-pair (cta_group::2) 256x256 tiles where the shape allows; 0: single-CTA 128x256 tiles."""
     check(_L.vlb200_set_gemm_mode(int(mode)))
