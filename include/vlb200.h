@@ -202,6 +202,17 @@ int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* d
                            void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq, int d,
                            void* stream);
 
+/* Packed rows for the merge indices above: keep the first len[b] = row_starts[b+1] - row_starts[b] rows of
+ * every sequence and stack the sequences back to back.  src_map_packed / position_ids_packed [row_starts[n_seq]] receive
+ * the surviving rows; the row lists row_of_text [n_text_rows] and img_rows [n_img_rows] (flat padded rows b*merged_len + p)
+ * are rewritten IN PLACE to packed rows, -1 where p >= len[b] (vlb200_gather_rows then yields a zero row and
+ * vlb200_scatter_rows skips it); img_pos [n_img_pos] (position inside sequence i / feats_per_seq) becomes an absolute packed
+ * row, to be consumed with merged_len = 0.  NULL lists are skipped.  Right padding only (the merge kernels enforce it).  */
+int vlb200_pack_merge_rows(const int* src_map, const int* position_ids, const int* row_starts, int n_seq, int merged_len,
+                           int* src_map_packed, int* position_ids_packed, int* row_of_text, int64_t n_text_rows,
+                           int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,
+                           void* stream);
+
 /* ---- LLaVA-Next text/image merge -- models/LlavaNext/__init__.py:38-171 (_merge_input_ids_with_image_features)
  * Differences from the LLaVA-1.5 merge above: image k contributes feat_off[k+1]-feat_off[k] PACKED feature rows
  * (anyres "spatial_unpad" + image_newline, modeling_llava_next.py pack_image_features; the row gather that builds
@@ -253,6 +264,22 @@ int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
                     void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,
                     int head_dim, int causal, float scale, void* stream);
+
+/* Ragged ("packed") rows -- SURVEY.md f-2, the var-len FlashAttention form: sequence b occupies rows
+ * [row_starts[b], row_starts[b] + seqlens[b]) of q/k/v/out (total_rows rows in all) instead of [b*S, (b+1)*S), so the
+ * padding the DPO collator adds (base/collator.py:44-60) costs no GEMM, norm or attention-store work.  S stays the upper
+ * bound of seqlens and the per-sequence stride of lse/delta [B, H, S]; rows at or beyond seqlens[b] are neither read as
+ * statistics nor written.  row_starts == NULL: identical to the functions above.                                     */
+int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                              int64_t ldo, float* lse, const int* seqlens, const int* row_starts, int64_t total_rows, int B,
+                              int S, int H, int KVH, int head_dim, int causal, float scale, void* stream);
+int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, const int* row_starts,
+                             int64_t total_rows, int B, int S, int H, int head_dim, void* stream);
+int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta,
+                              void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens,
+                              const int* row_starts, int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal,
+                              float scale, void* stream);
 
 /* ---- optimizer (K24: torch.optim.AdamW semantics, HF Trainer max_grad_norm clipping) ---------
  * sumsq: out[0] (+)= sum x^2 (deterministic two-stage; workspace 1024 floats).

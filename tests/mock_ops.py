@@ -305,7 +305,67 @@ def zero_(t):
 
 
 class MergeIndex:
-    pass
+    row_starts = None
+    total_feats = None
+    reps = None
+
+    @property
+    def packed(self):
+        return self.row_starts is not None
+
+    @property
+    def starts(self):
+        return self.row_starts
+
+    @property
+    def T(self):
+        return self.rows if self.packed else self.n_seq * self.S
+
+    @property
+    def T_chosen(self):
+        return self.rows_chosen if self.packed else (self.n_seq // 2) * self.S
+
+    @property
+    def row_stride(self):
+        return 0 if self.packed else self.S
+
+
+def pack_merge_rows(m, seq_lens):
+    """CPU mirror of vlb200_pack_merge_rows (csrc/elementwise.cu): keep the first seq_lens[b] rows of every sequence."""
+    lens = [int(x) for x in seq_lens]
+    if len(lens) != m.n_seq or any(n < 0 or n > m.S for n in lens):
+        raise ValueError(f"pack_merge_rows: {len(lens)} lengths for {m.n_seq} sequences of at most {m.S} rows")
+    if m.packed:
+        raise ValueError("pack_merge_rows: already packed")
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    S = m.S
+    keep = torch.cat([torch.arange(b * S, b * S + n) for b, n in enumerate(lens)]) if starts[-1] else torch.zeros(0, dtype=torch.long)
+    st = torch.tensor(starts, dtype=torch.long)
+    ln = torch.tensor(lens, dtype=torch.long)
+
+    def remap(rows):
+        r = rows.long()
+        b, p_ = r.clamp(min=0) // S, r.clamp(min=0) % S
+        ok = (r >= 0) & (b < m.n_seq)
+        bb = b.clamp(max=m.n_seq - 1)
+        new = torch.where(ok & (p_ < ln[bb]), st[bb] + p_, torch.full_like(r, -1))
+        return torch.where(r < 0, r, new).to(torch.int32)
+
+    m.src_map = m.src_map.reshape(-1)[keep].contiguous()
+    m.pos = m.pos.reshape(-1)[keep].contiguous()
+    m.row_of_text = remap(m.row_of_text.reshape(-1))
+    if m.total_feats is not None and m.reps is not None:   # LLaVA-Next: flat merged rows
+        m.img_pos = remap(m.img_pos.reshape(-1))
+    else:                                                   # LLaVA-1.5: positions inside the sequence -> absolute rows
+        feats = m.imgs_per_seq * m.P
+        b = torch.arange(m.img_pos.numel()) // feats
+        m.img_pos = (m.img_pos.reshape(-1).long() + st[b]).to(torch.int32)
+    m.row_starts = torch.tensor(starts, dtype=torch.int32)
+    m.rows, m.rows_chosen = max(starts[-1], 1), starts[m.n_seq // 2]
+    _c(3)
+    return m
 
 
 def llava_merge_index(input_ids, attention_mask, labels, n_patches, n_img_batch, imgs_per_seq, image_token, pad_token,
@@ -609,8 +669,46 @@ def cast_bf16_to_f32(src, dst):
     return dst
 
 
-attn_fwd_tc = attn_fwd  # the tcgen05 kernels have the same contract as the mma.sync ones
-attn_bwd_tc = attn_bwd
+def _unpack_rows(t, row_starts, seqlens, B, S):
+    """packed rows [sum(len), C] -> padded [B*S, C] (zeros in the padding rows)"""
+    out = torch.zeros(B * S, t.shape[1], dtype=t.dtype)
+    for b in range(B):
+        n, r0 = int(seqlens[b]), int(row_starts[b])
+        out[b * S:b * S + n] = t[r0:r0 + n]
+    return out
+
+
+def _pack_rows_into(dst, padded, row_starts, seqlens, B, S):
+    for b in range(B):
+        n, r0 = int(seqlens[b]), int(row_starts[b])
+        dst[r0:r0 + n] = padded[b * S:b * S + n].to(dst.dtype)
+
+
+def attn_fwd_tc(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale, row_starts=None, total_rows=0):
+    """Same contract as the mma.sync kernels; row_starts: packed rows (only the attended prefix of every sequence is written,
+    lse rows beyond it are left untouched -- as the CUDA kernel does)."""
+    if row_starts is None:
+        return attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    qp, kp, vp = (_unpack_rows(t, row_starts, seqlens, B, S) for t in (q, k, v))
+    op = torch.zeros(B * S, H * head_dim, dtype=out.dtype)
+    lp = torch.zeros(B, H, S) if lse is not None else None
+    attn_fwd(qp, kp, vp, op, lp, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    _pack_rows_into(out, op, row_starts, seqlens, B, S)
+    if lse is not None:
+        for b in range(B):
+            lse[b, :, :int(seqlens[b])] = lp[b, :, :int(seqlens[b])]
+    return out
+
+
+def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale, row_starts=None,
+                total_rows=0):
+    if row_starts is None:
+        return attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    qp, kp, vp, dop = (_unpack_rows(t, row_starts, seqlens, B, S) for t in (q, k, v, dout))
+    dqp, dkp, dvp = (torch.zeros(B * S, t.shape[1], dtype=t.dtype) for t in (dq, dk, dv))
+    attn_bwd(qp, kp, vp, None, dop, lse, delta, dqp, dkp, dvp, seqlens, B, S, H, KVH, head_dim, causal, scale)
+    for dst, src in ((dq, dqp), (dk, dkp), (dv, dvp)):
+        _pack_rows_into(dst, src, row_starts, seqlens, B, S)
 
 
 def colsum_f32(a, out):

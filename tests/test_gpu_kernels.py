@@ -397,3 +397,116 @@ def test_adamw_matches_torch(ops):
         ops.adamw_(param, g, master, m, v, 1e-3, 0.9, 0.98, 1e-6, 0.01, step, grad_scale=1.0, grad_sumsq=ss, max_grad_norm=1.0)
         torch.testing.assert_close(master, ref_p.detach(), rtol=2e-5, atol=1e-7)
         assert torch.equal(param, bf(master))
+
+
+# ------------------------------------------------------------------ packed (ragged) rows, SURVEY.md f-2
+@pytest.mark.parametrize("B,S,H,KV,dh,lens", [
+    (3, 200, 2, 2, 128, [200, 131, 77]),      # tiles straddle sequence boundaries
+    (4, 130, 4, 2, 128, [130, 64, 1, 129]),   # GQA, a one-token sequence
+    (3, 300, 4, 4, 64, [256, 300, 128]),      # lengths on tile boundaries
+    (2, 96, 2, 2, 64, [0, 96]),               # an empty sequence
+])
+def test_attention_varlen_equals_padded(ops, B, S, H, KV, dh, lens):
+    """The var-len entry points (packed rows: sequence b at row_starts[b]) give, on every attended row, bit for bit what the
+    padded entry points give, and write nothing else."""
+    torch.manual_seed(S + H + dh)
+    dev = "cuda"
+    ld = (H + 2 * KV) * dh
+    hq, hk = H * dh, KV * dh
+    qkv = bf(torch.randn(B * S, ld, device=dev))
+    seqlens = torch.tensor(lens, device=dev, dtype=torch.int32)
+    scale = 1.0 / math.sqrt(dh)
+    valid = (torch.arange(S, device=dev)[None] < seqlens[:, None].long()).view(-1)
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    T = starts[-1]
+    row_starts = torch.tensor(starts, device=dev, dtype=torch.int32)
+    # padded run
+    out = torch.empty(B * S, hq, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+    ops.attn_fwd_tc(qkv[:, :hq], qkv[:, hq:hq + hk], qkv[:, hq + hk:], out, lse, seqlens, B, S, H, KV, dh, True, scale)
+    dout = bf(torch.randn(B * S, hq, device=dev)) * valid.view(-1, 1)
+    dqkv = torch.zeros_like(qkv)
+    delta = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+    ops.attn_bwd_tc(qkv[:, :hq], qkv[:, hq:hq + hk], qkv[:, hq + hk:], out, dout, lse, delta, dqkv[:, :hq], dqkv[:, hq:hq + hk],
+                    dqkv[:, hq + hk:], seqlens, B, S, H, KV, dh, True, scale)
+    # packed run: NaN-poisoned outputs and statistics show any row that is written or read without belonging to a sequence
+    qkv_p = qkv[valid].contiguous()
+    dout_p = dout[valid].contiguous()
+    out_p = torch.full((T, hq), float("nan"), dtype=torch.bfloat16, device=dev)
+    lse_p = torch.full((B, H, S), float("nan"), dtype=torch.float32, device=dev)
+    ops.attn_fwd_tc(qkv_p[:, :hq], qkv_p[:, hq:hq + hk], qkv_p[:, hq + hk:], out_p, lse_p, seqlens, B, S, H, KV, dh, True, scale,
+                    row_starts=row_starts, total_rows=T)
+    assert torch.equal(out_p, out[valid])
+    vmask = (torch.arange(S, device=dev)[None] < seqlens[:, None].long())[:, None, :].expand(B, H, S)
+    assert torch.equal(lse_p[vmask], lse[vmask])
+    assert torch.isnan(lse_p[~vmask]).all()          # statistics of rows beyond a sequence are never written
+    dqkv_p = torch.full_like(qkv_p, float("nan"))
+    delta_p = torch.full((B, H, S), float("nan"), dtype=torch.float32, device=dev)
+    ops.attn_bwd_tc(qkv_p[:, :hq], qkv_p[:, hq:hq + hk], qkv_p[:, hq + hk:], out_p, dout_p, lse_p, delta_p, dqkv_p[:, :hq],
+                    dqkv_p[:, hq:hq + hk], dqkv_p[:, hq + hk:], seqlens, B, S, H, KV, dh, True, scale, row_starts=row_starts,
+                    total_rows=T)
+    assert torch.isfinite(dqkv_p).all()               # ... nor read
+    assert torch.equal(delta_p[vmask], delta[vmask])
+    assert torch.equal(dqkv_p, dqkv[valid])
+
+
+def test_pack_merge_rows_equals_mirror(ops):
+    """vlb200_pack_merge_rows == the plain-Python mirror (tests/mock_ops.py) for the LLaVA-1.5 and LLaVA-Next merge indices,
+    and the packed merge (embedding rows, image-gradient rows) equals the padded one on the surviving rows."""
+    from oracle import restate as R
+    from tests import mock_ops
+    from vlrlhf_b200 import host
+    cfg = R.TINY
+    batch = R.make_batch(cfg, 3, 20, 6, seed=5, ddpo_like=True)
+    cb = R.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    am[4, 15:] = 0   # ragged right padding
+    lb[4, 15:] = -100
+    am[1, 18:] = 0
+    lb[1, 18:] = -100
+    P, d = cfg.n_patches, cfg.hidden
+    lens = host.merged_seq_lens(ids, am, cfg.image_token_index, P)
+    m_pad = ops.llava_merge_index(ids.cuda(), am.cuda(), lb.cuda(), P, 3, 1, cfg.image_token_index, cfg.pad_token_id)
+    assert m_pad.seqlens.cpu().tolist() == lens
+    m = ops.pack_merge_rows(ops.llava_merge_index(ids.cuda(), am.cuda(), lb.cuda(), P, 3, 1, cfg.image_token_index, cfg.pad_token_id), lens)
+    want = mock_ops.pack_merge_rows(mock_ops.llava_merge_index(ids, am, lb, P, 3, 1, cfg.image_token_index, cfg.pad_token_id), lens)
+    assert m.T == want.T == sum(lens) and m.T_chosen == want.T_chosen == sum(lens[:3]) and m.row_stride == 0
+    for k in ("src_map", "pos", "row_of_text", "img_pos", "row_starts"):
+        assert torch.equal(getattr(m, k).cpu().reshape(-1), getattr(want, k).reshape(-1)), k
+    torch.manual_seed(0)
+    emb, img = bf(torch.randn(cfg.vocab, d)).cuda(), bf(torch.randn(3 * P, d)).cuda()
+    S = m_pad.S
+    keep = torch.cat([torch.arange(b * S, b * S + n) for b, n in enumerate(lens)]).cuda()
+    x_pad = torch.empty(6 * S, d, dtype=torch.float32, device="cuda")
+    x = torch.empty(m.T, d, dtype=torch.float32, device="cuda")
+    ops.llava_merge_embed(m_pad, emb, img, x_pad)
+    ops.llava_merge_embed(m, emb, img, x)
+    assert torch.equal(x, x_pad[keep])
+    dx_pad = bf(torch.randn(6 * S, d)).cuda()
+    dx_pad[torch.ones(6 * S, dtype=torch.bool, device="cuda").index_fill_(0, keep, False)] = 0  # padding rows carry no gradient
+    de_pad, de = (torch.zeros(cfg.vocab, d, dtype=torch.float32, device="cuda") for _ in range(2))
+    di_pad, di = (torch.empty(3 * P, d, dtype=torch.bfloat16, device="cuda") for _ in range(2))
+    ops.llava_merge_bwd(m_pad, dx_pad, de_pad, di_pad)
+    ops.llava_merge_bwd(m, dx_pad[keep].contiguous(), de, di)
+    assert torch.equal(di, di_pad)
+    close(de, de_pad, 1e-5, 1e-5)   # fp32 atomics: order differs
+    with pytest.raises(ValueError):
+        ops.pack_merge_rows(m, lens)  # already packed
+    # LLaVA-Next layout: img_pos holds flat merged rows
+    ncfg = R.TINY_NEXT
+    sizes = [(28, 28), (20, 50), (60, 25)]
+    nb = R.make_batch(ncfg, 3, 20, 6, seed=7, ddpo_like=True, image_sizes=sizes)
+    ncb = R.concatenated_inputs(nb)
+    nids, nam, nlb = (ncb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    plan = host.anyres_pack_index(torch.tensor(sizes), ncfg.image_grid_pinpoints, ncfg.image_size, ncfg.patch_size)
+    SN = host.next_merged_len(nids, nam, plan.feature_lens, ncfg.image_token_index)
+    nlens = host.merged_seq_lens(nids, nam, ncfg.image_token_index, [plan.feature_lens[b % 3] for b in range(6)])
+    args = (plan.feat_off, plan.total_feats, SN, 3, 1, ncfg.image_token_index)
+    mn = ops.llavanext_merge_index(nids.cuda(), nam.cuda(), nlb.cuda(), plan.feat_off.cuda(), *args[1:])
+    assert mn.seqlens.cpu().tolist() == nlens
+    mn = ops.pack_merge_rows(mn, nlens)
+    wn = mock_ops.pack_merge_rows(mock_ops.llavanext_merge_index(nids, nam, nlb, *args), nlens)
+    for k in ("src_map", "pos", "row_of_text", "img_pos", "row_starts"):
+        assert torch.equal(getattr(mn, k).cpu().reshape(-1), getattr(wn, k).reshape(-1)), k

@@ -600,3 +600,71 @@ def test_hf_checkpoint_roundtrip(cpu_pkg, cpu_plugin, tmp_path, family):
     assert torch.equal({checkpoint.legacy_name(n): v for n, v in back.state_dict().items()}[k], saved[k])
     with pytest.raises(ValueError):
         checkpoint.config_from_hf({"model_type": "qwen"})
+
+
+# ------------------------------------------------------------------------------------------
+# packed rows (TrainConfig.pack_sequences) over the mock ops
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,ckpt", [("g4_tiny", False), ("g4_tiny", True), ("g6_next_tiny", False)])
+def test_packed_step_equals_padded_step(cpu_pkg, tag, ckpt):
+    """Dropping the padding rows changes nothing a DPO step returns except the `logits/*` means: log-probs, loss, rewards and
+    every gradient are those of the padded batch (and so within 1e-3 of the reference fixtures)."""
+    config, engine, host, ops = cpu_pkg
+    res = []
+    for pack in (False, True):
+        eng, rcfg, d, batch, cb = _setup(cpu_pkg, tag)
+        eng.tc.pack_sequences, eng.tc.activation_checkpointing = pack, ckpt
+        n_pad = int((batch["chosen_attention_mask"] == 0).sum() + (batch["rejected_attention_mask"] == 0).sum())
+        assert n_pad > 0  # the fixture batch is ragged
+        metrics = eng.train_step(batch, train=True)
+        m = eng._saved["m"]
+        assert m.packed == pack
+        if pack:
+            assert m.T < m.n_seq * m.S and m.T == sum(eng.host_seq_lens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                                                          batch["img_input_dict"].get("image_sizes")))
+            assert eng._bufs["x.0"].shape[0] == m.T and eng._stores["x.0"].numel() == m.n_seq * m.S * eng.cfg.hidden
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in m0:
+        if not k.startswith("logits/"):
+            assert m0[k] == m1[k], k
+    assert torch.equal(g0, g1)
+    np.testing.assert_allclose([m1["logps/chosen"], m1["logps/rejected"]],
+                               [d["policy_logps"][:len(d["policy_logps"]) // 2].mean(), d["policy_logps"][len(d["policy_logps"]) // 2:].mean()],
+                               rtol=1e-3)
+
+
+def test_packed_rows_shrink_and_grow_between_batches(cpu_pkg):
+    """Workspaces are views of storage reserved at the padded size: a longer batch after a shorter one reuses it."""
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+    eng.tc.pack_sequences = True
+    want = eng.train_step(batch, train=False)
+    store = eng._stores["s.h"]
+    short = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    for side in ("chosen", "rejected"):
+        short[f"{side}_attention_mask"][:, -6:] = 0
+        short[f"{side}_labels"][:, -6:] = -100
+    eng.train_step(short, train=False)
+    assert eng._stores["s.h"] is store and eng._bufs["s.h"].shape[0] < want_rows(eng, cb)
+    again = eng.train_step(batch, train=False)
+    assert eng._stores["s.h"] is store
+    assert again == want
+
+
+def want_rows(eng, cb):
+    return sum(eng.host_seq_lens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"]))
+
+
+def test_merged_seq_lens_equal_merge_index_and_reject_left_padding(cpu_pkg):
+    config, engine, host, ops = cpu_pkg
+    eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    m = ops.llava_merge_index(ids, am, lb, rcfg.n_patches, ids.shape[0] // 2, 1, rcfg.image_token_index, rcfg.pad_token_id)
+    assert host.merged_seq_lens(ids, am, rcfg.image_token_index, rcfg.n_patches) == m.seqlens.tolist()
+    left = am.clone()
+    left[0, 0] = 0
+    with pytest.raises(ValueError):
+        host.merged_seq_lens(ids, left, rcfg.image_token_index, rcfg.n_patches)
+    with pytest.raises(ValueError):
+        ops.pack_merge_rows(m, [1] * (m.n_seq + 1))

@@ -163,3 +163,19 @@ def test_lora_peft_init_makes_policy_equal_reference(lpkg):
     eng.reset_adapters(0)
     m = eng.train_step(batch, train=False)
     assert abs(m["loss"] - float(np.log(2.0))) < 1e-6 and m["rewards/margins"] == 0.0
+
+
+@pytest.mark.parametrize("tag", ["g11_lora_tiny", "g11_next_lora_tiny"])
+def test_lora_packed_step_equals_padded_step(lpkg, tag):
+    """TrainConfig.pack_sequences on the LoRA engine: same log-probs, loss, rewards and adapter gradients as the padded step."""
+    res = []
+    for pack in (False, True):
+        eng, cfg, d, batch = _setup(lpkg, tag, pack_sequences=pack)
+        metrics = eng.train_step(batch, train=True)
+        assert eng._saved["m"].packed == pack
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in m0:
+        if not k.startswith("logits/"):
+            assert m0[k] == m1[k], k
+    assert torch.equal(g0, g1) and float(g0.float().abs().sum()) > 0

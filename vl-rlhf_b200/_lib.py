@@ -76,6 +76,17 @@ SIGNATURES = {
     "vlb200_attn_bwd_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vlb200_attn_fwd_tc_varlen": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                          c_void_p]),
+    "vlb200_attn_delta_varlen": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                         c_int, c_void_p]),
+    "vlb200_attn_bwd_tc_varlen": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                          c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                          c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                          c_void_p]),
+    "vlb200_pack_merge_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "vlb200_attn_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

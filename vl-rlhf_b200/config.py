@@ -111,6 +111,11 @@ class TrainConfig:
     # HF TrainingArguments.gradient_checkpointing (dpo.py:21 / scripts/*.sh --gradient_checkpointing True): keep only
     # each decoder layer's fp32 input, recompute the layer (minus down_proj) in backward
     activation_checkpointing: bool = False
+    # drop the collator's padding rows (base/collator.py:44-60) from the merged batch -- sequences are stacked
+    # back to back, attention runs var-len -- so padded positions cost nothing.  Log-probs, losses, rewards and gradients
+    # are those of the padded batch; only TRL's `logits/chosen|rejected` metric changes meaning (it averages over the
+    # attended positions instead of all positions).  LLaVA-1.5 / LLaVA-Next engines (full fine-tune and LoRA).
+    pack_sequences: bool = False
 
 
 def tensor_seed(name: str, base_seed: int) -> int:

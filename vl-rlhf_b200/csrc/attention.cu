@@ -234,14 +234,16 @@ attn_fwd_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------ backward: delta = rowsum(dO * O)
+// row_starts (or null): first row of each sequence when the rows are ragged / packed; delta stays [B, H, S]
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
-                                  long long lddo, float* __restrict__ delta, int B, int S, int H, int DH) {
+                                  long long lddo, float* __restrict__ delta, const int* __restrict__ row_starts, size_t rows,
+                                  int B, int S, int H, int DH) {
     const int warps_per_block = blockDim.x >> 5;
-    const size_t total = (size_t)B * S * H;
+    const size_t total = rows * H;
     const int lane = threadIdx.x & 31;
     for (size_t w = blockIdx.x * (size_t)warps_per_block + (threadIdx.x >> 5); w < total; w += (size_t)gridDim.x * warps_per_block) {
         const int h = (int)(w % H);
-        const size_t row = w / H;  // b*S + t
+        const size_t row = w / H;  // b*S + t, or row_starts[b] + t
         const __nv_bfloat16* op = o + row * ldo + (size_t)h * DH;
         const __nv_bfloat16* dp = dout + row * lddo + (size_t)h * DH;
         float acc = 0.f;
@@ -251,7 +253,15 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
             acc += a.x * d.x + a.y * d.y;
         }
         acc = warp_sum(acc);
-        if (lane == 0) delta[((size_t)(row / S) * H + h) * S + (row % S)] = acc;
+        if (lane == 0) {
+            size_t b = row / S, t = row % S;
+            if (row_starts != nullptr) {
+                b = 0;
+                while (b + 1 < (size_t)B && (size_t)row_starts[b + 1] <= row) ++b;
+                t = row - (size_t)row_starts[b];
+            }
+            if (t < (size_t)S) delta[(b * H + h) * S + t] = acc;
+        }
     }
 }
 
@@ -571,16 +581,23 @@ extern "C" int vlb200_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
     return attn::launch_fwd<128>(p, causal, as_stream(stream));
 }
 
-extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
-                                 int head_dim, void* stream) {
+extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
+                                        const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream) {
     VLB_REQUIRE(out && dout && delta, "attn_delta: null pointer");
-    const size_t nw = (size_t)B * S * H;
+    VLB_REQUIRE(row_starts == nullptr || total_rows > 0, "attn_delta: row_starts needs total_rows");
+    const size_t rows = row_starts ? (size_t)total_rows : (size_t)B * S;
+    const size_t nw = rows * H;
     const int blocks = (int)std::min<size_t>((nw + 7) / 8, (size_t)num_sms() * 16);
     attn::attn_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo,
-                                                                  delta, B, S, H, head_dim);
+                                                                  delta, row_starts, rows, B, S, H, head_dim);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
+}
+
+extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
+                                 int head_dim, void* stream) {
+    return vlb200_attn_delta_varlen(out, ldo, dout, lddo, delta, nullptr, 0, B, S, H, head_dim, stream);
 }
 
 extern "C" int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
@@ -592,7 +609,8 @@ extern "C" int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_
     cudaStream_t s = as_stream(stream);
     const size_t nw = (size_t)B * S * H;
     const int blocks = (int)std::min<size_t>((nw + 7) / 8, (size_t)num_sms() * 16);
-    attn::attn_delta_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo, delta, B, S, H, head_dim);
+    attn::attn_delta_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo, delta, nullptr,
+                                                   (size_t)B * S, B, S, H, head_dim);
     count_launch();
     VLB_LAUNCH_CHECK();
     attn::Params p{};

@@ -38,6 +38,7 @@ struct Params {
     const float* lse;    // [B, H, S] natural log
     const float* delta;  // [B, H, S]
     const int* seqlens;
+    const int* row_starts;  // [B] or null: first row of each sequence (ragged / packed rows); null: b*S
     __nv_bfloat16* out1; long long ld1;  // MODE 0: dV ; MODE 1: unused
     __nv_bfloat16* out2; long long ld2;  // MODE 0: dK ; MODE 1: dQ
     int B, S, H, KVH, causal;
@@ -140,7 +141,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 item_range<MODE>(p, b, xb, yb, ye, reps);
                 const int n = (ye - yb) * reps;
                 if (n == 0) continue;
-                const int row0 = b * p.S;
+                const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
                 const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
                 mbar_wait(x_empty, (item & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(x_full, 2 * X_BYTES);
@@ -266,7 +267,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             const int x0 = xb * BX;
             const int xrow = x0 + r;  // MODE 0: key index ; MODE 1: query index
             float row_lse2 = 0.f, row_delta = 0.f;
-            if (MODE == 1 && xrow < p.S) {
+            // rows at or beyond kv_len are masked below (their tiles always take the masked path): their statistics are never
+            // read -- with packed rows they were never written
+            if (MODE == 1 && xrow < kv_len) {
                 const long long si = ((long long)b * p.H + hx) * p.S + xrow;
                 row_lse2 = p.lse[si] * LOG2E_F;
                 row_delta = p.delta[si];
@@ -278,8 +281,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
                     const int q = yt * BY + tid_e;
                     const long long si = ((long long)b * p.H + (hx * group + rep)) * p.S + q;
-                    nl = q < p.S ? p.lse[si] * LOG2E_F : 0.f;
-                    nd = q < p.S ? p.delta[si] : 0.f;
+                    nl = q < kv_len ? p.lse[si] * LOG2E_F : 0.f;
+                    nd = q < kv_len ? p.delta[si] : 0.f;
                 }
             };
             if (MODE == 0 && n > 0) {
@@ -373,8 +376,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 mbar_wait(&e_done[(ec - 1) & 1], ((ec - 1) >> 1) & 1, 95);
                 tcgen05_fence_after();
             }
-            const bool valid = xrow < p.S;
-            const long long grow = (long long)b * p.S + xrow;
+            const bool valid = xrow < (p.row_starts ? kv_len : p.S);  // packed rows: the tile may run into the next sequence
+            const long long grow = (p.row_starts ? (long long)p.row_starts[b] : (long long)b * p.S) + xrow;
 #pragma unroll
             for (int a = (MODE == 0 ? 0 : 1); a < 2; ++a) {
                 __nv_bfloat16* dst = (a == 0 ? p.out1 + grow * p.ld1 : p.out2 + grow * p.ld2) + (long long)hx * DH;
@@ -438,22 +441,24 @@ static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMa
 }  // namespace attn_bwd_tc
 }  // namespace vlb
 
-extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
-                                 int head_dim, void* stream);
+extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
+                                        const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream);
 
-extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                  const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta,
-                                  void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens,
-                                  int B, int S, int H, int KVH, int head_dim, int causal, float scale, void* stream) {
+extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                         const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                         float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                         const int* seqlens, const int* row_starts, int64_t total_rows, int B, int S, int H,
+                                         int KVH, int head_dim, int causal, float scale, void* stream) {
     using namespace vlb;
     using namespace vlb::attn_bwd_tc;
     VLB_REQUIRE(q && k && v && out && dout && lse && delta && dq && dk && dv, "attn_bwd_tc: null pointer");
+    VLB_REQUIRE(row_starts == nullptr || (seqlens != nullptr && total_rows > 0), "attn_bwd_tc: row_starts needs seqlens and total_rows");
     VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_bwd_tc: bad B/S/H/KVH");
     VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_bwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
     VLB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
                 "attn_bwd_tc: row strides must be multiples of 8");
-    if (int rc = vlb200_attn_delta(out, ldo, dout, lddo, delta, B, S, H, head_dim, stream)) return rc;
-    const uint64_t rows = (uint64_t)B * S;
+    if (int rc = vlb200_attn_delta_varlen(out, ldo, dout, lddo, delta, row_starts, total_rows, B, S, H, head_dim, stream)) return rc;
+    const uint64_t rows = row_starts ? (uint64_t)total_rows : (uint64_t)B * S;  // TMA zero-fills past the last row
     const uint64_t qcols = (uint64_t)H * head_dim, kcols = (uint64_t)KVH * head_dim;
     CUtensorMap xk, xv, yq, ydo, xq, xdo, yk, yv;
     int rc;
@@ -466,7 +471,7 @@ extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int
     if ((rc = gemm::get_tensor_map(k, kcols, rows, ldk, 64, BY, &yk))) return rc;
     if ((rc = gemm::get_tensor_map(v, kcols, rows, ldv, 64, BY, &yv))) return rc;
     Params p{};
-    p.lse = lse; p.delta = delta; p.seqlens = seqlens;
+    p.lse = lse; p.delta = delta; p.seqlens = seqlens; p.row_starts = row_starts;
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_xb = (S + BX - 1) / BX;
     cudaStream_t s = as_stream(stream);
@@ -479,4 +484,12 @@ extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int
     p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq;
     p.n_work = p.n_xb * H * B;
     return head_dim == 64 ? launch<64, 1>(xq, xdo, yk, yv, p, s) : launch<128, 1>(xq, xdo, yk, yv, p, s);
+}
+
+extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta,
+                                  void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens,
+                                  int B, int S, int H, int KVH, int head_dim, int causal, float scale, void* stream) {
+    return vlb200_attn_bwd_tc_varlen(q, ldq, k, ldk, v, ldv, out, ldo, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, seqlens,
+                                     nullptr, 0, B, S, H, KVH, head_dim, causal, scale, stream);
 }

@@ -34,6 +34,7 @@ struct Params {
     __nv_bfloat16* o; long long ldo;
     float* lse;          // [B, H, S] or null
     const int* seqlens;  // [B] or null
+    const int* row_starts;  // [B] or null: first row of each sequence (ragged / packed rows); null: sequence b starts at b*S
     int B, S, H, KVH, causal;
     float scale;
     int n_qb, n_work;
@@ -129,7 +130,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 work_coords(p, w, b, h, qb);
                 const int kvh = h / (p.H / p.KVH);
                 const int n_tiles = num_kv_tiles(p, b, qb);
-                const int row0 = b * p.S;
+                const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
                 mbar_wait(q_empty, (item & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(q_full, Q_BYTES);
 #pragma unroll
@@ -317,8 +318,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             mbar_wait(pv_done, (g - 1) & 1, 95);
             tcgen05_fence_after();
             const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-            const bool valid = qrow < p.S;
-            __nv_bfloat16* op = p.o + ((long long)b * p.S + qrow) * p.ldo + (long long)h * DH;
+            // packed rows: the tile may run into the next sequence's rows, so only the attended prefix is stored
+            const bool valid = qrow < (p.row_starts && p.seqlens ? min(p.seqlens[b], p.S) : p.S);
+            const long long row0 = p.row_starts ? p.row_starts[b] : (long long)b * p.S;
+            __nv_bfloat16* op = p.o + (row0 + qrow) * p.ldo + (long long)h * DH;
 #pragma unroll
             for (int c = 0; c < DH / 32; ++c) {
                 uint32_t orow[32];
@@ -371,25 +374,35 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 }  // namespace attn_tc
 }  // namespace vlb
 
-extern "C" int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                  void* out, int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH,
-                                  int head_dim, int causal, float scale, void* stream) {
+extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                         void* out, int64_t ldo, float* lse, const int* seqlens, const int* row_starts,
+                                         int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal, float scale,
+                                         void* stream) {
     using namespace vlb;
     VLB_REQUIRE(q && k && v && out, "attn_fwd_tc: null pointer");
+    VLB_REQUIRE(row_starts == nullptr || (seqlens != nullptr && total_rows > 0), "attn_fwd_tc: row_starts needs seqlens and total_rows");
     VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_fwd_tc: bad B/S/H/KVH");
     VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_fwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
     VLB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attn_fwd_tc: row strides must be multiples of 8");
-    const uint64_t rows = (uint64_t)B * S;
+    // ragged rows: the maps end at total_rows, so a tile that runs past the last sequence is zero-filled by TMA
+    const uint64_t rows = row_starts ? (uint64_t)total_rows : (uint64_t)B * S;
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = gemm::get_tensor_map(q, (uint64_t)H * head_dim, rows, ldq, 64, 128, &tq))) return rc;
     if ((rc = gemm::get_tensor_map(k, (uint64_t)KVH * head_dim, rows, ldk, 64, 128, &tk))) return rc;
     if ((rc = gemm::get_tensor_map(v, (uint64_t)KVH * head_dim, rows, ldv, 64, 128, &tv))) return rc;
     attn_tc::Params p{};
-    p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.seqlens = seqlens;
+    p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.seqlens = seqlens; p.row_starts = row_starts;
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
     if (head_dim == 64) return attn_tc::launch<64>(tq, tk, tv, p, as_stream(stream));
     return attn_tc::launch<128>(tq, tk, tv, p, as_stream(stream));
+}
+
+extern "C" int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  void* out, int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH,
+                                  int head_dim, int causal, float scale, void* stream) {
+    return vlb200_attn_fwd_tc_varlen(q, ldq, k, ldk, v, ldv, out, ldo, lse, seqlens, nullptr, 0, B, S, H, KVH, head_dim, causal,
+                                     scale, stream);
 }

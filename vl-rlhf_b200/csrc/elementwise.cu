@@ -360,6 +360,39 @@ __global__ void merge_img_bwd_kernel(const int* __restrict__ img_pos, const __nv
     }
 }
 
+// ---------------------------------------------------------------- packed (ragged) rows: drop the padding rows of a merge index
+// The merge kernels above lay sequence b out at rows [b*S, (b+1)*S).  With right padding only the first len[b] rows of a
+// sequence are attended; packing keeps those and stacks the sequences back to back (sequence b at row_starts[b],
+// row_starts = exclusive prefix sum of len), so every row-wise kernel and GEMM runs over sum(len) rows instead of n_seq*S.
+//   src_map_p / pos_p [row_starts[n_seq]]: the surviving rows of src_map / pos
+//   row lists (row_of_text, img_rows: flat padded rows b*S + p) are rewritten in place to packed rows, -1 where p >= len[b]
+//   (vlb200_gather_rows yields a zero row, vlb200_scatter_rows skips it);  img_pos (position p inside sequence b) becomes
+//   the absolute packed row row_starts[b] + p (consumers then pass merged_len = 0).
+__global__ void pack_rows_kernel(const int* __restrict__ src_map, const int* __restrict__ pos, const int* __restrict__ row_starts,
+                                 int n_seq, int S, int* __restrict__ src_map_p, int* __restrict__ pos_p) {
+    const size_t total = (size_t)n_seq * S;
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < total; r += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(r / S), p = (int)(r % S);
+        const int start = row_starts[b];
+        if (p < row_starts[b + 1] - start) {
+            src_map_p[start + p] = src_map[r];
+            pos_p[start + p] = pos[r];
+        }
+    }
+}
+__global__ void remap_rows_kernel(int* __restrict__ rows, size_t n, const int* __restrict__ row_starts, int n_seq, int S) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = rows[i];
+        if (r < 0) continue;
+        const int b = r / S, p = r % S;
+        rows[i] = (b < n_seq && p < row_starts[b + 1] - row_starts[b]) ? row_starts[b] + p : -1;
+    }
+}
+__global__ void abs_img_pos_kernel(int* __restrict__ img_pos, size_t n, int feats_per_seq, const int* __restrict__ row_starts) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        img_pos[i] += row_starts[i / feats_per_seq];
+}
+
 // ---------------------------------------------------------------- LLaVA-Next merge index (LlavaNext/__init__.py:38-171)
 // Same outputs as merge_index_kernel, but (i) image k contributes feat_off[k+1]-feat_off[k] packed feature rows
 // (anyres: variable per image), (ii) tokens with attention_mask == 0 are never written (:96-99,124-127) and S is the
@@ -707,6 +740,32 @@ extern "C" int vlb200_memset_zero(void* dst, uint64_t bytes, void* stream) {
     return VLB200_OK;
 }
 
+extern "C" int vlb200_pack_merge_rows(const int* src_map, const int* position_ids, const int* row_starts, int n_seq, int merged_len,
+                                      int* src_map_packed, int* position_ids_packed, int* row_of_text, int64_t n_text_rows,
+                                      int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,
+                                      void* stream) {
+    VLB_REQUIRE(src_map && position_ids && row_starts && src_map_packed && position_ids_packed && n_seq > 0 && merged_len > 0,
+                "pack_merge_rows: bad arguments");
+    VLB_REQUIRE(img_pos == nullptr || feats_per_seq > 0, "pack_merge_rows: img_pos needs feats_per_seq");
+    cudaStream_t s = as_stream(stream);
+    pack_rows_kernel<<<grid_for((size_t)n_seq * merged_len, 256), 256, 0, s>>>(src_map, position_ids, row_starts, n_seq, merged_len,
+                                                                             src_map_packed, position_ids_packed);
+    count_launch();
+    if (row_of_text != nullptr && n_text_rows > 0) {
+        remap_rows_kernel<<<grid_for((size_t)n_text_rows, 256), 256, 0, s>>>(row_of_text, (size_t)n_text_rows, row_starts, n_seq, merged_len);
+        count_launch();
+    }
+    if (img_rows != nullptr && n_img_rows > 0) {
+        remap_rows_kernel<<<grid_for((size_t)n_img_rows, 256), 256, 0, s>>>(img_rows, (size_t)n_img_rows, row_starts, n_seq, merged_len);
+        count_launch();
+    }
+    if (img_pos != nullptr && n_img_pos > 0) {
+        abs_img_pos_kernel<<<grid_for((size_t)n_img_pos, 256), 256, 0, s>>>(img_pos, (size_t)n_img_pos, feats_per_seq, row_starts);
+        count_launch();
+    }
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
 extern "C" int vlb200_llava_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels,
                                         int n_seq, int text_len, int merged_len, int n_patches, int n_img_batch,
                                         int imgs_per_seq, int image_token, int pad_token, int ignore_index, int* src_map,

@@ -16,7 +16,7 @@ full-vocab logits are computed only for rows that can carry a label, the discard
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -215,6 +215,9 @@ class LlavaDPOEngine:
             self.norm_done = torch.cuda.Event()
         self._anyres = None  # host.AnyresPlan of the batch in flight (LLaVA-Next only)
         self._bufs: Dict[str, torch.Tensor] = {}
+        self._stores: Dict[str, torch.Tensor] = {}   # flat storage behind the (possibly smaller) views in _bufs
+        self._pad_rows = 0                            # packed rows: padded row count (capacity) and row count of the batch
+        self._cur_rows = 0
         self._build_rope_tables()
 
     # ------------------------------------------------------------------ weights
@@ -290,11 +293,27 @@ class LlavaDPOEngine:
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        """Named workspace: allocated once, reused every step.  Packed rows (TrainConfig.pack_sequences): the row count changes
+        with every batch, so a workspace whose leading dimension is the batch's row count reserves the padded row count and
+        later requests are served as views of that storage (it only ever grows)."""
         t = self._bufs.get(name)
         shape = tuple(int(s) for s in shape)
-        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+        if t is not None and t.dtype == dtype and tuple(t.shape) == shape:
+            return t
+        if not self._pad_rows:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[name] = t
+            return t
+        n = 1
+        for dim in shape:
+            n *= dim
+        cap = n // shape[0] * self._pad_rows if shape and shape[0] == self._cur_rows and self._cur_rows < self._pad_rows else n
+        store = self._stores.get(name)
+        if store is None or store.dtype != dtype or store.numel() < n:
+            store = torch.empty(max(n, cap), dtype=dtype, device=self.device)
+            self._stores[name] = store
+        t = store[:n].view(shape)
+        self._bufs[name] = t
         return t
 
     # ------------------------------------------------------------------ vision tower (frozen, once per pair)
@@ -337,7 +356,7 @@ class LlavaDPOEngine:
     # ------------------------------------------------------------------ one decoder layer
     def _layer_bufs(self, pre: str, sfx: str, m: "ops.MergeIndex") -> Dict[str, torch.Tensor]:
         cfg = self.cfg
-        T = m.n_seq * m.S
+        T = m.T
         H, dh = cfg.heads, cfg.head_dim
         return dict(rstd1=self.buf(f"{pre}.rstd1{sfx}", (T,), torch.float32),
                     rstd2=self.buf(f"{pre}.rstd2{sfx}", (T,), torch.float32),
@@ -353,7 +372,7 @@ class LlavaDPOEngine:
         (reference pass, checkpointed forward): the gate|up projections are consumed inside the GEMM epilogue and never
         reach HBM."""
         cfg = self.cfg
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         h = self.buf("s.h", (T, d))
@@ -362,7 +381,7 @@ class LlavaDPOEngine:
         ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
         ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh))
+                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
         ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
         ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         if xn is None:
@@ -378,7 +397,7 @@ class LlavaDPOEngine:
         """Projector (K6) -> [LLaVA-Next: pack_image_features] -> token embedding + merge (K7, K8): the fp32 input of
         decoder layer 0, [T, d].  save_projector keeps the pre-GELU activations for the projector's backward."""
         cfg = self.cfg
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         nimg = feats.shape[0]
         # projector (K6)
         if save_projector:
@@ -408,7 +427,7 @@ class LlavaDPOEngine:
     def _forward(self, w: Weights, m: "ops.MergeIndex", feats: torch.Tensor, tag: str, save: bool,
                  ddpo_weight: Optional[torch.Tensor]):
         cfg = self.cfg
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         L = cfg.layers
         x = self._merged_embeddings(w, m, feats, save, "x.0" if save else "s.x0")
         ckpt = save and self.tc.activation_checkpointing
@@ -426,7 +445,7 @@ class LlavaDPOEngine:
                       ddpo_weight: Optional[torch.Tensor]):
         """Final RMSNorm -> lm_head on the rows that can carry a label (K15) -> fused log-prob gather (K16)."""
         cfg = self.cfg
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         h = self.buf("s.h", (T, d))
         rstd_f = self.buf("a.rstd_f" if save else "s.rstd_f", (T,), torch.float32)
         ops.rmsnorm_fwd(x, norm_w, cfg.rms_eps, out=h, rstd=rstd_f)
@@ -439,12 +458,14 @@ class LlavaDPOEngine:
         if save:
             self._saved = dict(m=m, feats=feats, x_last=x, lse_v=lse_v, ddpo_weight=ddpo_weight)
             # TRL's `logits/chosen|rejected` = mean of the full [B,S,V] logits = dot(colsum(h), colsum(W_lm)) / (B*S*V)  (K19)
-            half = T // 2
+            # (packed rows: the mean runs over the attended positions only -- the reference also averages the logits of its
+            # padding positions, which a packed batch never computes; the one metric that differs)
+            half = m.T_chosen
             cs = self.buf("m.colsum", (3, d), torch.float32)
             ops.colsum_f32(h[:half], cs[0]); ops.colsum_f32(h[half:], cs[1]); ops.colsum_f32(lm_w, cs[2])
             self.logit_means = self.buf("m.logit_means", (2,), torch.float32)
-            inv = 1.0 / (float(half) * cfg.vocab)
-            ops.dot_f32(cs[0], cs[2], inv, self.logit_means[0:1]); ops.dot_f32(cs[1], cs[2], inv, self.logit_means[1:2])
+            inv_c, inv_r = 1.0 / (float(max(half, 1)) * cfg.vocab), 1.0 / (float(max(T - half, 1)) * cfg.vocab)
+            ops.dot_f32(cs[0], cs[2], inv_c, self.logit_means[0:1]); ops.dot_f32(cs[1], cs[2], inv_r, self.logit_means[1:2])
         return logps
 
     def _head_backward(self, grad_logps: torch.Tensor, norm_w: torch.Tensor, lm_w: torch.Tensor, g_norm: torch.Tensor,
@@ -452,7 +473,7 @@ class LlavaDPOEngine:
         """d(log-probs) -> gradient of the last decoder layer's output (bf16 [T, d]); g_lm=None: lm_head is frozen."""
         cfg, sv = self.cfg, self._saved
         m = sv["m"]
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         R = m.n_seq * (m.L - 1)
         logits, hsel = self._bufs["a.logits"], self._bufs["a.hsel"]
         dlogits = self.buf("b.dlogits", (R, cfg.vocab))
@@ -474,7 +495,7 @@ class LlavaDPOEngine:
         cfg, w, g = self.cfg, self.policy, self.g
         sv = self._saved
         m: ops.MergeIndex = sv["m"]
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         dx = self._head_backward(grad_logps, w["norm"], w["lm_head"], g["norm"], g["lm_head"])
@@ -512,7 +533,7 @@ class LlavaDPOEngine:
             ops.gemm(dx2, w[f"L{i}.wo"], b_kmajor=False, out=datt)                            # datt = dxmid Wo
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
                          dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                         True, scale)
+                         True, scale, row_starts=m.starts, total_rows=m.T)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             ops.rmsnorm_fwd(x_in, w[f"L{i}.ln1"], cfg.rms_eps, out=h)                         # recompute h1
             ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"])            # dWqkv = dqkv^T h1
@@ -641,7 +662,9 @@ class LlavaDPOEngine:
         return (ids, am, lb, px, wt) if plan is None else (ids, am, lb, px, wt, plan)
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
-                      feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None):
+                      feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None, seq_lens=None):
+        """`seq_lens` (host ints, merged length of every sequence; host.merged_seq_lens) is only read with
+        TrainConfig.pack_sequences; without it the lengths are read back from the device (one synchronisation)."""
         cfg = self.cfg
         if (cfg.family == "llava_next") != (anyres is not None):
             raise ValueError("the anyres plan from prepare_inputs is required for (and only for) LLaVA-Next")
@@ -654,6 +677,9 @@ class LlavaDPOEngine:
             else:
                 m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0], imgs_per_seq, cfg.image_token_index,
                                           cfg.pad_token_id, cfg.ignore_index)
+            if self.tc.pack_sequences:   # drop the padding rows: every kernel below runs over sum(len) rows
+                ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":
@@ -662,21 +688,21 @@ class LlavaDPOEngine:
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
     def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True,
-             ref_logps: Optional[torch.Tensor] = None) -> StepOutput:
+             ref_logps: Optional[torch.Tensor] = None, seq_lens=None) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
         backward + gradient all-reduce + AdamW.  `ref_logps` ([2B] fp32, chosen then rejected) replaces the reference
         pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
         the collator's `_logps` keys, base/collator.py:62-64)."""
         tc = self.tc
         if ref_logps is not None:
-            pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train)
+            pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, seq_lens=seq_lens)
             ref = ref_logps.to(self.device, torch.float32).reshape(-1).contiguous()
             if ref.numel() != pol.numel():
                 raise ValueError(f"ref_logps holds {ref.numel()} values, the batch has {pol.numel()} sequences")
         else:
             # reference pass first: it reads none of the policy weights, so the previous step's deferred optimizer
             # (side stream) overlaps it; the policy pass below waits for `opt_done`
-            ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False)
+            ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, seq_lens=seq_lens)
             pol, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    1.0, want_grad=train)
@@ -719,7 +745,8 @@ class LlavaDPOEngine:
         if "reference_chosen_logps" in batch and "reference_rejected_logps" in batch:  # precompute_ref_log_probs
             ref_logps = torch.cat([torch.as_tensor(batch["reference_chosen_logps"], dtype=torch.float32).reshape(-1),
                                    torch.as_tensor(batch["reference_rejected_logps"], dtype=torch.float32).reshape(-1)])
-        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train, ref_logps=ref_logps)
+        seq_lens = self.host_seq_lens(ids, am, sizes) if tc.pack_sequences else None
+        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train, ref_logps=ref_logps, seq_lens=seq_lens)
         n = out.policy_logps.numel() // 2
         if self._opt_pending:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
             torch.cuda.current_stream(self.device).wait_event(self.norm_done)
@@ -732,6 +759,19 @@ class LlavaDPOEngine:
                 "logps/chosen": float(packed[6]), "logps/rejected": float(packed[7]),
                 "logits/chosen": float(packed[9]), "logits/rejected": float(packed[10]),
                 "grad_norm": float(packed[8]) ** 0.5 / world}
+
+    def host_seq_lens(self, ids, am, image_sizes=None) -> List[int]:
+        """Merged length of every sequence of one concatenated host batch (packed steps: the rows that survive)."""
+        from . import host
+        cfg = self.cfg
+        if cfg.family != "llava_next":
+            return host.merged_seq_lens(ids, am, cfg.image_token_index, cfg.n_patches)
+        n_seq = ids.shape[0]
+        if image_sizes.shape[0] == n_seq:
+            image_sizes = image_sizes[: n_seq // 2]
+        plan = host.anyres_pack_index(image_sizes.cpu(), cfg.image_grid_pinpoints, cfg.image_size, cfg.patch_size)
+        return host.merged_seq_lens(ids, am, cfg.image_token_index,
+                                    [plan.feature_lens[b % len(plan.feature_lens)] for b in range(n_seq)])
 
     def ddpo_weights(self, ids, am, lb, image_sizes=None) -> torch.Tensor:
         """Host-side DDPO row weights of one concatenated batch (trainer.py:169-184 over the merged label layout)."""

@@ -133,7 +133,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
     # ------------------------------------------------------------------ decoder layer (base weights, adapters `lora` or None)
     def _layer_bufs(self, pre: str, sfx: str, m):
         b = super()._layer_bufs(pre, sfx, m)
-        T, r = m.n_seq * m.S, self.cfg.lora_r
+        T, r = m.T, self.cfg.lora_r
         if pre == "a":
             b.update(ts_qkv=self.buf(f"a.ts_qkv{sfx}", (T, 3 * r)), ts_o=self.buf(f"a.ts_o{sfx}", (T, r)),
                      ts_gu=self.buf(f"a.ts_gu{sfx}", (T, 2 * r)), ts_d=self.buf(f"a.ts_d{sfx}", (T, r)))
@@ -141,7 +141,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
 
     def _layer_fwd(self, w, i: int, x, b, m, xn, lora: Optional[Weights] = None):
         cfg, base = self.cfg, self.base
-        d, T, ff, r = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r
+        d, T, ff, r = cfg.hidden, m.T, cfg.ff, cfg.lora_r
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         h = self.buf("s.h", (T, d))
@@ -164,7 +164,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
                 ops.gemm(h, wqkv[lo:hi], a2=ts[:, j * r:(j + 1) * r], b2=lora[f"L{i}.{n}.B"], out=qkv[:, lo:hi])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
         ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh))
+                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -193,7 +193,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
     # ------------------------------------------------------------------ forward of one pass
     def _forward(self, w, m, feats, tag: str, save: bool, ddpo_weight):
         cfg, base = self.cfg, self.base
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         lora = self.policy if tag == "policy" else None
         x = self._merged_embeddings(base, m, feats, False, "x.0" if save else "s.x0")   # frozen projector / embeddings
         ckpt = save and self.tc.activation_checkpointing
@@ -211,7 +211,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
         m = sv["m"]
-        d, T, ff, r = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r
+        d, T, ff, r = cfg.hidden, m.T, cfg.ff, cfg.lora_r
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         s = cfg.lora_scale
@@ -260,7 +260,8 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             ops.gemm(d1, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
-                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale)
+                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale,
+                            row_starts=m.starts, total_rows=m.T)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             # ---- q | k | v
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1

@@ -435,7 +435,9 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         return ids, am, lb, px, wt
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
-                      feats=None, m=None):
+                      feats=None, m=None, seq_lens=None):
+        if self.tc.pack_sequences:
+            raise ValueError("pack_sequences is implemented for the LLaVA-1.5 / LLaVA-Next engines only")
         cfg = self.cfg
         self._anyres = None
         if m is None:

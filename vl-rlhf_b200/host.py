@@ -168,6 +168,25 @@ def next_merged_len(input_ids: torch.Tensor, attention_mask: torch.Tensor, featu
     return int(((attention_mask == 1).sum(-1) - n_special + feat).max())
 
 
+def merged_seq_lens(input_ids: torch.Tensor, attention_mask: torch.Tensor, image_token_index: int, feat_rows) -> List[int]:
+    """Merged length of every sequence's attended prefix -- what the merge kernels report as `seqlens` -- computed on the
+    host so that a packed step (TrainConfig.pack_sequences) needs no device read-back: attended text tokens minus the
+    <image> placeholders plus the image feature rows (Llava/__init__.py:44-47, LlavaNext/__init__.py:81-87).  `feat_rows`:
+    feature rows per sequence (an int, or one entry per sequence).  Right padding only (the DPO collator's,
+    base/collator.py:44-60); anything else raises the engine's left-padding ValueError."""
+    ids, am = input_ids.cpu(), attention_mask.cpu()
+    n_seq = ids.shape[0]
+    att = am == 1
+    if bool((att[:, 1:] & ~att[:, :-1]).any()):
+        raise ValueError("attention_mask must be a right-padded prefix mask (left padding is not supported yet)")
+    rows = torch.as_tensor(feat_rows, dtype=torch.int64).reshape(-1)
+    rows = rows.expand(n_seq) if rows.numel() == 1 else rows
+    if rows.numel() != n_seq:
+        raise ValueError(f"feat_rows holds {rows.numel()} entries for {n_seq} sequences")
+    n_img = ((ids == image_token_index) & att).sum(-1)
+    return [int(v) for v in (att.sum(-1) - n_img + rows)]
+
+
 def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches,
                      label_pad_token_id: int = -100, min_match_size: int = 3,
                      attention_mask: Optional[torch.Tensor] = None, merged_len: Optional[int] = None) -> torch.Tensor:

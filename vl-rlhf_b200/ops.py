@@ -330,7 +330,34 @@ def zero_(t: torch.Tensor):
 class MergeIndex:
     """Device-side result of the integer merge pass (Llava/__init__.py:36-109)."""
     __slots__ = ("src_map", "labels", "mask", "pos", "seqlens", "img_pos", "row_of_text", "target", "status",
-                 "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq", "total_feats", "reps")
+                 "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq", "total_feats", "reps",
+                 "row_starts", "rows", "rows_chosen")
+
+    # Row layout of the merged activations.  Padded (default): sequence b at rows [b*S, (b+1)*S).  Packed (pack_merge_rows):
+    # sequence b at rows [row_starts[b], row_starts[b] + len[b]), `rows` = sum(len) in all, `rows_chosen` of them chosen.
+    @property
+    def packed(self) -> bool:
+        return getattr(self, "row_starts", None) is not None
+
+    @property
+    def starts(self) -> Optional[torch.Tensor]:
+        """[n_seq + 1] int32 first rows of the sequences when packed, else None."""
+        return getattr(self, "row_starts", None)
+
+    @property
+    def T(self) -> int:
+        """Rows of every merged activation matrix."""
+        return self.rows if self.packed else self.n_seq * self.S
+
+    @property
+    def T_chosen(self) -> int:
+        """Rows of the chosen half (the first n_seq/2 sequences)."""
+        return self.rows_chosen if self.packed else (self.n_seq // 2) * self.S
+
+    @property
+    def row_stride(self) -> int:
+        """merged_len argument of the kernels that address rows as b*merged_len + p (0: positions are absolute rows)."""
+        return 0 if self.packed else self.S
 
 
 def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_patches: int,
@@ -360,14 +387,14 @@ def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, lab
 
 def llava_merge_embed(m: MergeIndex, embed_tokens: torch.Tensor, image_features: torch.Tensor, out: torch.Tensor):
     check(_L.vlb200_llava_merge_embed(_ptr(m.src_map), _ptr(embed_tokens), _ptr(image_features), _ptr(out), _dt(out),
-                                      m.n_seq * m.S, embed_tokens.shape[1], _stream()))
+                                      m.T, embed_tokens.shape[1], _stream()))
     return out
 
 
 def llava_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, dimage_features: torch.Tensor):
     assert dembed_f32.dtype == torch.float32
     check(_L.vlb200_llava_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32), _ptr(dimage_features),
-                                    m.n_seq, m.n_img_batch, m.S, m.imgs_per_seq * m.P, dx.shape[1], _stream()))
+                                    m.n_seq, m.n_img_batch, m.row_stride, m.imgs_per_seq * m.P, dx.shape[1], _stream()))
 
 
 def llavanext_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
@@ -403,7 +430,39 @@ def llavanext_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor,
 def llavanext_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, dimage_features: torch.Tensor):
     assert dembed_f32.dtype == torch.float32 and dimage_features.shape[0] == m.total_feats
     check(_L.vlb200_llavanext_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32),
-                                        _ptr(dimage_features), m.n_seq * m.S, m.total_feats, m.reps, dx.shape[1], _stream()))
+                                        _ptr(dimage_features), m.T, m.total_feats, m.reps, dx.shape[1], _stream()))
+
+
+def pack_merge_rows(m: MergeIndex, seq_lens) -> MergeIndex:
+    """Drop the padding rows of a LLaVA-1.5 / LLaVA-Next merge index: `seq_lens` (host ints, one per sequence,
+    == m.seqlens) gives the attended prefix of every sequence; afterwards sequence b lives at rows
+    [row_starts[b], row_starts[b] + seq_lens[b]) and m.T = sum(seq_lens).  m.labels / m.mask keep the padded [n_seq, S] layout
+    (they feed no kernel)."""
+    lens = [int(x) for x in seq_lens]
+    if len(lens) != m.n_seq or any(n < 0 or n > m.S for n in lens):
+        raise ValueError(f"pack_merge_rows: {len(lens)} lengths for {m.n_seq} sequences of at most {m.S} rows")
+    if m.packed:
+        raise ValueError("pack_merge_rows: already packed")
+    starts = [0]
+    for n in lens:
+        starts.append(starts[-1] + n)
+    dev = m.src_map.device
+    row_starts = torch.tensor(starts, dtype=torch.int32).to(dev, non_blocking=True)
+    rows = max(starts[-1], 1)
+    src_p = torch.empty(rows, dtype=torch.int32, device=dev)
+    pos_p = torch.empty(rows, dtype=torch.int32, device=dev)
+    next_layout = getattr(m, "total_feats", None) is not None and getattr(m, "reps", None) is not None
+    img_pos, n_img_pos, feats, img_rows, n_img_rows = None, 0, 0, None, 0
+    if next_layout:      # LLaVA-Next: img_pos holds flat merged rows
+        img_rows, n_img_rows = m.img_pos, m.img_pos.numel()
+    else:                # LLaVA-1.5: img_pos holds positions inside the sequence
+        img_pos, n_img_pos, feats = m.img_pos, m.img_pos.numel(), m.imgs_per_seq * m.P
+    check(_L.vlb200_pack_merge_rows(_ptr(m.src_map), _ptr(m.pos), _ptr(row_starts), m.n_seq, m.S, _ptr(src_p), _ptr(pos_p),
+                                    _ptr(m.row_of_text), m.row_of_text.numel(), _ptr(img_pos), n_img_pos, feats,
+                                    _ptr(img_rows), n_img_rows, _stream()))
+    m.src_map, m.pos = src_p, pos_p
+    m.row_starts, m.rows, m.rows_chosen = row_starts, rows, starts[m.n_seq // 2]
+    return m
 
 
 def qwen_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_queries: int,
@@ -445,11 +504,17 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
 
 def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
                 seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool,
-                scale: float):
-    """tcgen05/TMEM/TMA forward; same contract as attn_fwd."""
-    check(_L.vlb200_attn_fwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
-                                out.stride(0), _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale,
-                                _stream()))
+                scale: float, row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
+    """tcgen05/TMEM/TMA forward; same contract as attn_fwd.  row_starts ([B+1] int32) + total_rows: packed rows, sequence b
+    at rows [row_starts[b], row_starts[b] + seqlens[b]) (include/vlb200.h: vlb200_attn_fwd_tc_varlen)."""
+    if row_starts is None:
+        check(_L.vlb200_attn_fwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                    out.stride(0), _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale,
+                                    _stream()))
+    else:
+        check(_L.vlb200_attn_fwd_tc_varlen(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                           out.stride(0), _ptr(lse), _ptr(seqlens), _ptr(row_starts), int(total_rows), B, S, H,
+                                           KVH, head_dim, int(causal), scale, _stream()))
     return out
 
 
@@ -460,12 +525,20 @@ def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, 
                              scale, _stream()))
 
 
-def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
-    """tcgen05/TMEM/TMA backward; same contract as attn_bwd."""
-    check(_L.vlb200_attn_bwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
-                                out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
-                                _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim,
-                                int(causal), scale, _stream()))
+def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale,
+                row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
+    """tcgen05/TMEM/TMA backward; same contract as attn_bwd.  row_starts/total_rows: packed rows (see attn_fwd_tc)."""
+    if row_starts is None:
+        check(_L.vlb200_attn_bwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                    out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
+                                    _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim,
+                                    int(causal), scale, _stream()))
+    else:
+        check(_L.vlb200_attn_bwd_tc_varlen(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                           out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq),
+                                           dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens),
+                                           _ptr(row_starts), int(total_rows), B, S, H, KVH, head_dim, int(causal), scale,
+                                           _stream()))
 
 
 # ------------------------------------------------------------------------------------------
