@@ -273,7 +273,8 @@ def run_b200(args):
         return run_b200_lora(args, cfg, world, rank, local)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
-    eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b")))
+    eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b"),
+                                                        pack_sequences=args.pack))
     eng.init_synthetic(0)  # same weights on every rank
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)  # rank-local pairs
     cb = host.concatenated_inputs(batch)
@@ -304,7 +305,9 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    step_dev = lambda: eng.step(*dev_inputs, train=True)  # noqa: E731
+    # --pack (side measurement, SURVEY f-2): the padding rows of the ragged synthetic batch are dropped from every kernel
+    seq_lens = eng.host_seq_lens(ids_h, am_h, sizes_h) if args.pack else None
+    step_dev = lambda: eng.step(*dev_inputs, train=True, seq_lens=seq_lens)  # noqa: E731
     last = {}
 
     def step_e2e():
@@ -360,7 +363,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD if args.model == "7b" else (
                            WORKLOAD_NEXT if args.model == "next7b" else f"{args.model} (dev config, NOT the benchmark)"),
                        "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
-                       "activation_checkpointing": eng.tc.activation_checkpointing,
+                       "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
+                       "rows_per_step": (sum(seq_lens) if seq_lens else 2 * PAIRS_PER_GPU * S),
                        "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master+moments, max_grad_norm 1.0",
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
                        "step_tflop_algorithmic": flops / 1e12,
@@ -494,7 +498,8 @@ def run_b200_lora(args, cfg, world, rank, local):
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if full else (96, 24)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     eng = engine_lora.LlavaLoRADPOEngine(cfg, config.TrainConfig(loss_type=loss_type, learning_rate=1e-5,
-                                                                 activation_checkpointing=args.checkpointing))
+                                                                 activation_checkpointing=args.checkpointing,
+                                                                 pack_sequences=args.pack))
     eng.init_synthetic(0)
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
     cb = host.concatenated_inputs(batch)
@@ -524,7 +529,8 @@ def run_b200_lora(args, cfg, world, rank, local):
         return float(ms) / steps
 
     last = {}
-    step_dev = lambda: eng.step(*dev_inputs, train=True)  # noqa: E731
+    seq_lens = eng.host_seq_lens(ids_h, am_h, sizes_h) if args.pack else None
+    step_dev = lambda: eng.step(*dev_inputs, train=True, seq_lens=seq_lens)  # noqa: E731
     step_e2e = lambda: last.update(eng.train_step(batch, train=True))  # noqa: E731
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -559,7 +565,7 @@ def run_b200_lora(args, cfg, world, rank, local):
                                         f"scripts' setting; side measurement), frozen CLIP-L/336 + projector, 4 pairs/GPU, text 1024 "
                                         f"({S} merged), 1x336px image/pair") if full else f"{args.model} (dev config, NOT the benchmark)",
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
-                           "activation_checkpointing": eng.tc.activation_checkpointing,
+                           "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
                            "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
@@ -622,6 +628,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--checkpointing", action="store_true", help="activation checkpointing (the *_lora side measurements)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--pack", action="store_true",
+                    help="TrainConfig.pack_sequences (side measurement: padding rows dropped; the headline run keeps them, as the reference does)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -339,3 +339,48 @@ def test_hf_checkpoint_roundtrip_on_gpu(pkg, tmp_path, name):
     cb = host.concatenated_inputs(batch)
     outs = [m.engine.step(*stage(m.engine, host, cb, rcfg), train=False).policy_logps for m in (a, b)]
     assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------ packed rows
+@pytest.mark.parametrize("tag,ddpo", [("g4_small", False), ("g4_small", True), ("g6_next_small", False)])
+def test_packed_step_equals_padded_step(pkg, tag, ddpo):
+    """TrainConfig.pack_sequences drops the padding rows of the ragged fixture batch: the log-probs are bit-identical (every
+    surviving row goes through the same arithmetic), the fixtures still hold to 1e-3, the gradients agree to accumulation
+    order (the weight gradients contract over the rows), and nothing non-finite leaks in from unwritten rows."""
+    config, engine, host, ops = pkg
+    res = []
+    for pack in (False, True):
+        eng, rcfg, d, batch, cb = build(pkg, tag, loss_type="ddpo" if ddpo else "sigmoid", with_optimizer=False)
+        eng.tc.pack_sequences = pack
+        args = stage(eng, host, cb, rcfg, ddpo=ddpo)
+        lens = eng.host_seq_lens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                 cb["concatenated_img_input_dict"].get("image_sizes")) if pack else None
+        eng.step(*args, train=True, seq_lens=lens)   # allocates the workspaces
+        if pack:   # poison them, storage beyond the packed rows included: what a packed step does not write it must not read
+            for t in eng._stores.values():
+                if t.is_floating_point():
+                    t.fill_(float("nan"))
+        out = eng.step(*args, train=True, seq_lens=lens)
+        m = eng._saved["m"]
+        assert m.packed == pack
+        if pack:
+            assert m.T == sum(lens) < m.n_seq * m.S
+        torch.cuda.synchronize()
+        res.append((out.policy_logps.clone(), out.ref_logps.clone(), out.losses.clone(), eng.grads.clone().float()))
+    (p0, r0, l0, g0), (p1, r1, l1, g1) = res
+    assert torch.equal(p0, p1) and torch.equal(r0, r1) and torch.equal(l0, l1)
+    key = "policy_logps_ddpo" if ddpo else "policy_logps"
+    np.testing.assert_allclose(p1.cpu().numpy(), d[key], rtol=1e-3, atol=1e-2 if ddpo else 0)
+    assert torch.isfinite(g1).all()
+    rel = ((g0 - g1).norm() / g0.norm()).item()
+    assert rel < 2e-3, f"gradient rel l2 {rel}"
+
+
+def test_packed_step_without_host_lengths_reads_them_back(pkg):
+    """step() without seq_lens falls back to reading the merge kernel's seqlens from the device (one synchronisation)."""
+    config, engine, host, ops = pkg
+    eng, rcfg, d, batch, cb = build(pkg, "g4_tiny", with_optimizer=False)
+    want = eng.step(*stage(eng, host, cb, rcfg), train=False).policy_logps.clone()
+    eng.tc.pack_sequences = True
+    got = eng.step(*stage(eng, host, cb, rcfg), train=False).policy_logps
+    assert eng._stores and torch.equal(got, want)
