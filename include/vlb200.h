@@ -201,13 +201,18 @@ int vlb200_llava_merge_embed(const int* src_map, const void* embed_tokens, const
 int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
                            void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq, int d,
                            void* stream);
+/* The same over n_rows rows of dx with sequence b's image position p at row b*row_stride + p; row_stride = 0: img_pos holds
+ * absolute rows (packed rows, after vlb200_pack_merge_rows). */
+int vlb200_llava_merge_bwd_rows(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
+                                void* dimage_features, int64_t n_rows, int n_seq, int n_img_batch, int row_stride,
+                                int feats_per_seq, int d, void* stream);
 
 /* Packed rows for the merge indices above: keep the first len[b] = row_starts[b+1] - row_starts[b] rows of
  * every sequence and stack the sequences back to back.  src_map_packed / position_ids_packed [row_starts[n_seq]] receive
  * the surviving rows; the row lists row_of_text [n_text_rows] and img_rows [n_img_rows] (flat padded rows b*merged_len + p)
  * are rewritten IN PLACE to packed rows, -1 where p >= len[b] (vlb200_gather_rows then yields a zero row and
  * vlb200_scatter_rows skips it); img_pos [n_img_pos] (position inside sequence i / feats_per_seq) becomes an absolute packed
- * row, to be consumed with merged_len = 0.  NULL lists are skipped.  Right padding only (the merge kernels enforce it).  */
+ * row, to be consumed through vlb200_llava_merge_bwd_rows with row_stride = 0.  NULL lists are skipped.  Right padding only (the merge kernels enforce it).  */
 int vlb200_pack_merge_rows(const int* src_map, const int* position_ids, const int* row_starts, int n_seq, int merged_len,
                            int* src_map_packed, int* position_ids_packed, int* row_of_text, int64_t n_text_rows,
                            int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,

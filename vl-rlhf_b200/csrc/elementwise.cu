@@ -367,7 +367,7 @@ __global__ void merge_img_bwd_kernel(const int* __restrict__ img_pos, const __nv
 //   src_map_p / pos_p [row_starts[n_seq]]: the surviving rows of src_map / pos
 //   row lists (row_of_text, img_rows: flat padded rows b*S + p) are rewritten in place to packed rows, -1 where p >= len[b]
 //   (vlb200_gather_rows yields a zero row, vlb200_scatter_rows skips it);  img_pos (position p inside sequence b) becomes
-//   the absolute packed row row_starts[b] + p (consumers then pass merged_len = 0).
+//   the absolute packed row row_starts[b] + p (vlb200_llava_merge_bwd_rows with row_stride = 0).
 __global__ void pack_rows_kernel(const int* __restrict__ src_map, const int* __restrict__ pos, const int* __restrict__ row_starts,
                                  int n_seq, int S, int* __restrict__ src_map_p, int* __restrict__ pos_p) {
     const size_t total = (size_t)n_seq * S;
@@ -793,17 +793,23 @@ extern "C" int vlb200_llava_merge_embed(const int* src_map, const void* embed_to
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
 }
-extern "C" int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
-                                      void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq,
-                                      int d, void* stream) {
-    VLB_REQUIRE(src_map && img_pos && dx && dembed_f32 && dimage_features && d % 8 == 0, "merge_bwd: bad arguments");
+extern "C" int vlb200_llava_merge_bwd_rows(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
+                                           void* dimage_features, int64_t n_rows, int n_seq, int n_img_batch, int row_stride,
+                                           int feats_per_seq, int d, void* stream) {
+    VLB_REQUIRE(src_map && img_pos && dx && dembed_f32 && dimage_features && d % 8 == 0 && n_rows > 0, "merge_bwd: bad arguments");
     cudaStream_t s = as_stream(stream);
-    merge_embed_bwd_kernel<<<grid_for((size_t)n_seq * merged_len * (d / 8), 256), 256, 0, s>>>(src_map, CBF(dx), dembed_f32, n_seq * merged_len, d);
+    merge_embed_bwd_kernel<<<grid_for((size_t)n_rows * (d / 8), 256), 256, 0, s>>>(src_map, CBF(dx), dembed_f32, (int)n_rows, d);
     VLB_LAUNCH_CHECK();
-    merge_img_bwd_kernel<<<grid_for((size_t)n_img_batch * feats_per_seq * (d / 8), 256), 256, 0, s>>>(img_pos, CBF(dx), BF(dimage_features), n_seq, n_img_batch, merged_len, feats_per_seq, d);
+    merge_img_bwd_kernel<<<grid_for((size_t)n_img_batch * feats_per_seq * (d / 8), 256), 256, 0, s>>>(img_pos, CBF(dx), BF(dimage_features), n_seq, n_img_batch, row_stride, feats_per_seq, d);
     count_launch(2);
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
+}
+extern "C" int vlb200_llava_merge_bwd(const int* src_map, const int* img_pos, const void* dx, float* dembed_f32,
+                                      void* dimage_features, int n_seq, int n_img_batch, int merged_len, int feats_per_seq,
+                                      int d, void* stream) {
+    return vlb200_llava_merge_bwd_rows(src_map, img_pos, dx, dembed_f32, dimage_features, (int64_t)n_seq * merged_len, n_seq,
+                                       n_img_batch, merged_len, feats_per_seq, d, stream);
 }
 extern "C" int vlb200_llavanext_merge_index(const int64_t* input_ids, const int64_t* attention_mask, const int64_t* labels,
                                             const int* feat_off, int n_seq, int text_len, int merged_len, int n_img_batch,

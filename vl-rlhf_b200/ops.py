@@ -393,8 +393,9 @@ def llava_merge_embed(m: MergeIndex, embed_tokens: torch.Tensor, image_features:
 
 def llava_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tensor, dimage_features: torch.Tensor):
     assert dembed_f32.dtype == torch.float32
-    check(_L.vlb200_llava_merge_bwd(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32), _ptr(dimage_features),
-                                    m.n_seq, m.n_img_batch, m.row_stride, m.imgs_per_seq * m.P, dx.shape[1], _stream()))
+    check(_L.vlb200_llava_merge_bwd_rows(_ptr(m.src_map), _ptr(m.img_pos), _ptr(dx), _ptr(dembed_f32), _ptr(dimage_features),
+                                         m.T, m.n_seq, m.n_img_batch, m.row_stride, m.imgs_per_seq * m.P, dx.shape[1],
+                                         _stream()))
 
 
 def llavanext_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
