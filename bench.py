@@ -324,7 +324,7 @@ def run_b200(args):
     if nvtx:
         torch.cuda.nvtx.range_pop()
     launches = (ops.launch_count() - n0)
-    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else None
     clocks = sampler.stop() if sampler else None
 
     # dominant kernel live: the tcgen05 GEMM at its largest forward shape (gate_up: [T,d] x [2ff,d]^T)
@@ -369,7 +369,7 @@ def run_b200(args):
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
                        "step_tflop_algorithmic": flops / 1e12,
                        "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
-            "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+            "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                     "ms_per_step": ms_e2e, "last_metrics": last},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,K-major> (tcgen05 cta_group::2, 256x256 pair tiles, gate_up fwd shape)",
@@ -448,7 +448,7 @@ def run_b200_qwen(args, cfg, world, rank, local):
     n0 = ops.launch_count()
     ms_dev = timed(step_dev, args.steps)
     launches = ops.launch_count() - n0
-    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else None
     clocks = sampler.stop() if sampler else None
     if is_xc2:
         return _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, last, text_len, batch, ids_h, am_h, lb_h)
@@ -477,7 +477,7 @@ def run_b200_qwen(args, cfg, world, rank, local):
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
                            "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
-                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
@@ -538,7 +538,7 @@ def run_b200_lora(args, cfg, world, rank, local):
     n0 = ops.launch_count()
     ms_dev = timed(step_dev, args.steps)
     launches = ops.launch_count() - n0
-    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else float("nan")
+    ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else None
     clocks = sampler.stop() if sampler else None
     # algorithmic FLOPs: base linears x3 (policy fwd, reference fwd, dgrad-only backward), attention 2 fwd + a 2x backward,
     # adapters x3 (fwd, dA/dB, dt/dx), tower once per crop, frozen projector once per pass
@@ -569,7 +569,7 @@ def run_b200_lora(args, cfg, world, rank, local):
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
                            "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
-                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
@@ -607,7 +607,7 @@ def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, l
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
                            "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
-                "e2e": {"value": pairs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
+                "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
