@@ -258,6 +258,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # with NCCL_DEBUG=VERSION|WARN (set on the GPU boxes) NCCL prints "NCCL version ..." on STDOUT, next to the one JSON
+        # line this script owes its caller: send NCCL's own log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import config, engine, host, ops, synthetic
