@@ -459,11 +459,12 @@ def test_plugin_dpo_loss_like_reference(cpu_plugin):
         cpu_plugin.dpo_loss(SimpleNamespace(beta=0.1, label_smoothing=0, loss_type="x", reference_free=False), pc, pr, rc, rr)
 
 
-def test_plugin_concatenated_forward_and_module(cpu_plugin, cpu_pkg):
+@pytest.mark.parametrize("pack", [False, True])
+def test_plugin_concatenated_forward_and_module(cpu_plugin, cpu_pkg, pack):
     from types import SimpleNamespace
     config, engine, host, ops = cpu_pkg
     d = np.load(os.path.join(G, "g4_tiny.npz"))
-    model = cpu_plugin.B200LlavaForRL(config.TINY, config.TrainConfig(), device="cpu", with_optimizer=False)
+    model = cpu_plugin.B200LlavaForRL(config.TINY, config.TrainConfig(pack_sequences=pack), device="cpu", with_optimizer=False)
     model.engine.init_synthetic(int(d["seed"]))
     names = dict(model.hf_named_parameters())
     assert "language_model.model.layers.0.self_attn.q_proj.weight" in names
@@ -481,6 +482,7 @@ def test_plugin_concatenated_forward_and_module(cpu_plugin, cpu_pkg):
     losses.mean().backward()  # autograd -> engine backward -> .grad views of the flat gradient buffer
     gq = names["language_model.model.layers.0.self_attn.q_proj.weight"].grad
     assert gq is not None and float(gq.float().abs().sum()) > 0
+    assert model.engine._saved["m"].packed == pack
     assert gq.data_ptr() == model.engine.hf_state("grad")["language_model.model.layers.0.self_attn.q_proj.weight"].data_ptr()
 
 

@@ -164,6 +164,8 @@ class LlavaDPOEngine:
         self.layout, self.vlayout = self._make_layouts()
         n = self.layout.size
         import os as _os
+        if train is None and _os.environ.get("VLB200_PACK_SEQUENCES", "0") == "1":
+            self.tc.pack_sequences = True   # launcher-level switch: the reference's dpo.py builds the model without a TrainConfig
         # Optimizer sharding across the data-parallel ranks (ZeRO-1 style; the reference's default DeepSpeed config
         # shards optimizer state too, accelerate_config/zero2.yaml): gradients are reduce-SCATTERED, each rank runs
         # AdamW on its 1/world slice of the flat buffers (fp32 master + moments exist for that slice only) and the

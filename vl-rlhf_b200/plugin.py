@@ -195,15 +195,15 @@ class _EngineLogps(torch.autograd.Function):
     backward pass and leaves the gradients in the parameters' .grad views."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, inputs):
-        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True)
+    def forward(ctx, anchor, engine, inputs, seq_lens):
+        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens)
         ctx.engine = engine
         return logps
 
     @staticmethod
     def backward(ctx, g):
         ctx.engine._backward(g.float().contiguous())
-        return torch.zeros(1, device=g.device), None, None
+        return torch.zeros(1, device=g.device), None, None, None
 
 
 def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, torch.LongTensor]]
@@ -225,13 +225,15 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     if self.loss_type == "ddpo":
         wt = eng.ddpo_weights(ids, am, lb, sizes)
     inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes)
+    # TrainConfig.pack_sequences: the merged lengths come from the host batch, so the step stays free of device read-backs
+    seq_lens = eng.host_seq_lens(ids, am, sizes) if eng.tc.pack_sequences else None
     n = batch["chosen_labels"].shape[0]
     if which == "policy" and torch.is_grad_enabled():
         anchor = torch.zeros(1, device=eng.device, requires_grad=True)
-        logps = _EngineLogps.apply(anchor, eng, inputs)
+        logps = _EngineLogps.apply(anchor, eng, inputs, seq_lens)
     else:
         with torch.no_grad():
-            logps, _, _ = eng.forward_logps(*inputs, which=which, save=False)
+            logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens)
     return logps[:n], logps[n:], None, None
 
 
