@@ -670,3 +670,7 @@ def test_merged_seq_lens_equal_merge_index_and_reject_left_padding(cpu_pkg):
         host.merged_seq_lens(ids, left, rcfg.image_token_index, rcfg.n_patches)
     with pytest.raises(ValueError):
         ops.pack_merge_rows(m, [1] * (m.n_seq + 1))
+    cut = am.clone()
+    cut[1, 1:] = 0   # the <image> placeholder (position 1) falls outside the attended prefix
+    with pytest.raises(ValueError):
+        host.merged_seq_lens(ids, cut, rcfg.image_token_index, rcfg.n_patches)

@@ -1,0 +1,125 @@
+"""The oracle restatement against the LIVE reference (build container only: skipped where /root/reference is absent, e.g. on
+the GPU box -- there the committed vectors in tests/golden/, minted from these same reference functions by
+oracle/make_fixtures.py, are the pin).
+
+The reference's own code runs here through oracle/ref_shim.py (stub trl / peft / accelerate / deepspeed modules, nothing of
+the reference is copied): VLDPOTrainer.get_batch_logps, VLDPOTrainer.dpo_loss, diff_lib.get_diff_ids and LlavaForRL /
+LlavaNextForRL forward incl. _merge_input_ids_with_image_features.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, restate as R
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    T, get_diff_ids, _ = ref_shim.reference_symbols()
+    return T, get_diff_ids
+
+
+def _labels(g, n_seq, S, V):
+    lb = torch.randint(3, V, (n_seq, S), generator=g)
+    for b in range(n_seq):
+        lb[b, : int(torch.randint(1, S // 2, (1,), generator=g))] = -100          # prompt
+        lb[b, S - int(torch.randint(0, S // 4, (1,), generator=g)):] = -100        # right padding
+    return lb
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("average", [False, True])
+def test_get_batch_logps_equals_reference(ref, dtype, average):
+    T, _ = ref
+    g = torch.Generator().manual_seed(11)
+    logits = (torch.randn(4, 37, 211, generator=g) * 3).to(dtype)
+    lb = _labels(g, 4, 37, 211)
+    want = T.get_batch_logps(logits, lb, average_log_prob=average, label_pad_token_id=-100, is_encoder_decoder=False)
+    got = R.get_batch_logps(logits, lb, average_log_prob=average)
+    assert got.dtype == want.dtype and torch.equal(got, want)
+    with pytest.raises(ValueError):
+        T.get_batch_logps(logits[:, :-1], lb)
+    with pytest.raises(ValueError):
+        R.get_batch_logps(logits[:, :-1], lb)
+
+
+def test_get_batch_logps_ddpo_mask_equals_reference(ref):
+    """mask_shared_tokens (base/trainer.py:169-184): chosen/rejected differ by a few substituted spans."""
+    T, _ = ref
+    g = torch.Generator().manual_seed(5)
+    S, V = 120, 97
+    chosen = _labels(g, 2, S, V)
+    rejected = chosen.clone()
+    for b in range(2):
+        for _ in range(3):
+            a = int(torch.randint(S // 2, S - 12, (1,), generator=g))
+            n = int(torch.randint(1, 8, (1,), generator=g))
+            rejected[b, a:a + n] = torch.where(rejected[b, a:a + n] == -100, rejected[b, a:a + n],
+                                               torch.randint(3, V, (n,), generator=g))
+    lb = torch.cat([chosen, rejected])
+    logits = torch.randn(4, S, V, generator=g)
+    want = T.get_batch_logps(logits, lb, mask_shared_tokens=True)
+    got = R.get_batch_logps(logits, lb, mask_shared_tokens=True)
+    assert torch.equal(got, want)
+    assert not torch.equal(want, T.get_batch_logps(logits, lb))     # the mask removes shared tokens
+
+
+@pytest.mark.parametrize("loss_type", ["sigmoid", "ddpo", "hinge", "ipo", "kto_pair"])
+@pytest.mark.parametrize("ls,reference_free", [(0.0, False), (0.1, False), (0.0, True)])
+def test_dpo_loss_equals_reference(ref, loss_type, ls, reference_free):
+    T, _ = ref
+    g = torch.Generator().manual_seed(3)
+    pc, pr, rc, rr = (torch.randn(5, generator=g) * 4 - 60 for _ in range(4))
+    me = SimpleNamespace(beta=0.1, label_smoothing=ls, loss_type=loss_type, reference_free=reference_free,
+                         accelerator=SimpleNamespace(device="cpu"))
+    want = T.dpo_loss(me, pc, pr, rc, rr)
+    got = R.dpo_loss(pc, pr, rc, rr, 0.1, ls, loss_type, reference_free)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        T.dpo_loss(SimpleNamespace(**{**me.__dict__, "loss_type": "nope"}), pc, pr, rc, rr)
+    with pytest.raises(ValueError):
+        R.dpo_loss(pc, pr, rc, rr, 0.1, ls, "nope", reference_free)
+
+
+def test_get_diff_ids_equals_reference(ref):
+    _, get_diff_ids = ref
+    rng = np.random.RandomState(0)
+    for case in range(60):
+        n = int(rng.randint(5, 400))
+        a = rng.randint(0, 12 if case % 3 == 0 else 400, size=n).tolist()   # small alphabets trigger autojunk (n >= 200)
+        b = list(a)
+        for _ in range(int(rng.randint(0, 6))):
+            i = int(rng.randint(0, len(b)))
+            k = int(rng.randint(0, 9))
+            b[i:i + k] = rng.randint(0, 400, size=int(rng.randint(0, 9))).tolist()
+        want = get_diff_ids(a, b, min_match_size=3)
+        got = R.get_diff_ids(a, b, 3)
+        assert (list(got[0]), list(got[1])) == (list(want[0]), list(want[1])), case
+
+
+@pytest.mark.parametrize("name,sizes", [("TINY", None), ("TINY_NEXT", [(28, 28), (20, 50), (60, 25)])])
+def test_llava_forward_and_merge_equal_reference(name, sizes):
+    """LlavaForRL / LlavaNextForRL.forward (merge included) on seeded weights and a ragged collated batch: merged labels and
+    image-position map bit-equal, per-sequence log-probs of the reference's logits == the oracle's concatenated_forward."""
+    from oracle import make_fixtures as MF
+    cfg = getattr(R, name)
+    seed = 4
+    batch = R.make_batch(cfg, 3, 24, 8, seed, ddpo_like=True, image_sizes=sizes)
+    model = MF.build_reference_model(cfg, MF.streamed_weights(cfg, seed, "policy"))
+    want_logps, out = MF.reference_concatenated_forward(model, cfg, batch, "sigmoid")
+    w, _ = R.make_policy_and_ref(cfg, seed)
+    cb = R.concatenated_inputs(batch, -100, 0)
+    with torch.no_grad():
+        pc, pr, pcl, prl = R.concatenated_forward(cfg, w, batch)
+        _, labels, imap = R.model_forward(cfg, w, cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                          cb["concatenated_labels"], **cb["concatenated_img_input_dict"])
+    assert torch.equal(labels, out.labels)
+    assert torch.equal(imap, out.image_position_map)
+    np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), want_logps.numpy(), rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(torch.cat([pcl, prl]).numpy(), out.logits.float().numpy(), rtol=1e-3, atol=2e-4)

@@ -183,8 +183,10 @@ def merged_seq_lens(input_ids: torch.Tensor, attention_mask: torch.Tensor, image
     rows = rows.expand(n_seq) if rows.numel() == 1 else rows
     if rows.numel() != n_seq:
         raise ValueError(f"feat_rows holds {rows.numel()} entries for {n_seq} sequences")
-    n_img = ((ids == image_token_index) & att).sum(-1)
-    return [int(v) for v in (att.sum(-1) - n_img + rows)]
+    is_img = ids == image_token_index
+    if bool((is_img & ~att).any()):
+        raise ValueError("an <image> placeholder lies outside the attended prefix of its sequence")
+    return [int(v) for v in (att.sum(-1) - is_img.sum(-1) + rows)]
 
 
 def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches,
