@@ -37,3 +37,19 @@ def test_missing_extension_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvlb200.so")
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "vl-rlhf_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):   # (the reference tree is cited in comments; no Python file may open it either)
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "/root/reference" in src:
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), root))
+    assert not offenders, offenders
