@@ -674,3 +674,49 @@ def test_merged_seq_lens_equal_merge_index_and_reject_left_padding(cpu_pkg):
     cut[1, 1:] = 0   # the <image> placeholder (position 1) falls outside the attended prefix
     with pytest.raises(ValueError):
         host.merged_seq_lens(ids, cut, rcfg.image_token_index, rcfg.n_patches)
+
+
+def _left_pad(batch, pad_id):
+    """the same collated batch with every sequence's padding moved to the LEFT"""
+    out = dict(batch)
+    for side in ("chosen", "rejected"):
+        ids, am, lb = (batch[f"{side}_{k}"].clone() for k in ("input_ids", "attention_mask", "labels"))
+        for b in range(ids.shape[0]):
+            n = int(am[b].sum())
+            k = ids.shape[1] - n
+            ids[b] = torch.cat([torch.full((k,), pad_id, dtype=ids.dtype), ids[b, :n]])
+            lb[b] = torch.cat([torch.full((k,), -100, dtype=lb.dtype), lb[b, :n]])
+            am[b] = torch.cat([torch.zeros(k, dtype=am.dtype), am[b, :n]])
+        out[f"{side}_input_ids"], out[f"{side}_attention_mask"], out[f"{side}_labels"] = ids, am, lb
+    return out
+
+
+@pytest.mark.parametrize("pack", [False, True])
+def test_left_padded_batch_gives_the_right_padded_results(cpu_pkg, pack):
+    """f-2: train_step moves the attended tokens to the front (host.right_pad_valid_tokens); nothing it returns depends on
+    where the padding sat (the `logits/*` means aside, which cover the padding positions' own logits)."""
+    config, engine, host, ops = cpu_pkg
+    res = []
+    for left in (False, True):
+        eng, rcfg, d, batch, cb = _setup(cpu_pkg, "g4_tiny")
+        eng.tc.pack_sequences = pack
+        b = _left_pad(batch, eng.tc.padding_value) if left else batch
+        if left:
+            assert int(b["rejected_attention_mask"][:, 0].min()) == 0   # really left-padded
+        res.append((eng.train_step(b, train=True), eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in m0:
+        if not k.startswith("logits/"):
+            assert m0[k] == m1[k], k
+    assert torch.equal(g0, g1)
+    ids = torch.tensor([[7, 8, 0, 9], [1, 2, 3, 4]])
+    am = torch.tensor([[1, 1, 0, 1], [1, 1, 1, 1]])
+    lb = torch.tensor([[-100, 8, -100, 9], [-100, 2, 3, 4]])
+    i2, a2, l2 = host.right_pad_valid_tokens(ids, am, lb, 0, -100)    # interleaved padding: order of the valid tokens kept
+    assert i2.tolist() == [[7, 8, 9, 0], [1, 2, 3, 4]] and a2.tolist() == [[1, 1, 1, 0], [1, 1, 1, 1]]
+    assert l2.tolist() == [[-100, 8, 9, -100], [-100, 2, 3, 4]]
+    same = host.right_pad_valid_tokens(i2, a2, l2)
+    assert same[0] is i2 and same[1] is a2 and same[2] is l2          # prefix masks pass through untouched
+    with pytest.raises(ValueError):                                   # the reference's DDPO diff depends on the padding side
+        host.right_pad_valid_tokens(ids, am, lb, 0, -100, loss_type="ddpo")
+    assert host.right_pad_valid_tokens(i2, a2, l2, loss_type="ddpo")[0] is i2

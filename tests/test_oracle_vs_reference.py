@@ -123,3 +123,63 @@ def test_llava_forward_and_merge_equal_reference(name, sizes):
     assert torch.equal(imap, out.image_position_map)
     np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), want_logps.numpy(), rtol=2e-5, atol=2e-4)
     np.testing.assert_allclose(torch.cat([pcl, prl]).numpy(), out.logits.float().numpy(), rtol=1e-3, atol=2e-4)
+
+
+def test_left_padded_reference_equals_right_padded_path():
+    """f-2 (left padding): the reference's LlavaForRL on a LEFT-padded batch gives, per sequence, the log-probs of the
+    right-padded form -- which is what host.right_pad_valid_tokens hands to the engine."""
+    from oracle import make_fixtures as MF
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import host
+    cfg, seed = R.TINY, 9
+    batch = R.make_batch(cfg, 3, 24, 8, seed, ddpo_like=True)
+    left = dict(batch)
+    for side in ("chosen", "rejected"):
+        ids, am, lb = (batch[f"{side}_{k}"].clone() for k in ("input_ids", "attention_mask", "labels"))
+        for b in range(ids.shape[0]):
+            n = int(am[b].sum())
+            k = ids.shape[1] - n
+            ids[b] = torch.cat([torch.zeros(k, dtype=ids.dtype), ids[b, :n]])
+            lb[b] = torch.cat([torch.full((k,), -100, dtype=lb.dtype), lb[b, :n]])
+            am[b] = torch.cat([torch.zeros(k, dtype=am.dtype), am[b, :n]])
+        left[f"{side}_input_ids"], left[f"{side}_attention_mask"], left[f"{side}_labels"] = ids, am, lb
+    assert int(left["rejected_attention_mask"][:, 0].min()) == 0
+    model = MF.build_reference_model(cfg, MF.streamed_weights(cfg, seed, "policy"))
+    want_left, _ = MF.reference_concatenated_forward(model, cfg, left, "sigmoid")
+    want_right, _ = MF.reference_concatenated_forward(model, cfg, batch, "sigmoid")
+    np.testing.assert_allclose(want_left.numpy(), want_right.numpy(), rtol=2e-5, atol=2e-4)   # the reference itself agrees
+    cb = R.concatenated_inputs(left, -100, 0)
+    ids, am, lb = host.right_pad_valid_tokens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                              cb["concatenated_labels"], 0, -100)
+    cr = R.concatenated_inputs(batch, -100, 0)
+    assert torch.equal(am, cr["concatenated_attention_mask"]) and torch.equal(lb, cr["concatenated_labels"])
+    att = am == 1
+    assert torch.equal(ids[att], cr["concatenated_input_ids"][att])
+    w, _ = R.make_policy_and_ref(cfg, seed)
+    with torch.no_grad():
+        logits, labels, _ = R.model_forward(cfg, w, ids, am, lb, **cb["concatenated_img_input_dict"])
+        got = R.get_batch_logps(logits, labels)
+    np.testing.assert_allclose(got.numpy(), want_left.numpy(), rtol=2e-5, atol=2e-4)
+
+
+def test_reference_ddpo_depends_on_the_padding_side(ref):
+    """Why host.right_pad_valid_tokens refuses loss_type='ddpo' on left-padded batches: the reference's own get_batch_logps
+    with mask_shared_tokens gives different results for the same pairs padded on the other side (its diff runs over the
+    padded label sequences, masked positions rewritten to token 0, base/trainer.py:166,177-180)."""
+    T, _ = ref
+    batch = R.make_batch(R.TINY, 3, 24, 8, 0, ddpo_like=True)
+    cb = R.concatenated_inputs(batch, -100, 0)
+    right, am = cb["concatenated_labels"].clone(), cb["concatenated_attention_mask"]
+    V = 50
+    right[right >= V] = right[right >= V] % (V - 3) + 3
+    n_seq, L = right.shape
+    logits_r = torch.randn(n_seq, L, V, generator=torch.Generator().manual_seed(0))
+    left, logits_l = torch.full_like(right, -100), torch.zeros_like(logits_r)
+    for b in range(n_seq):
+        n = int(am[b].sum())
+        left[b, L - n:], logits_l[b, L - n:] = right[b, :n], logits_r[b, :n]
+    torch.testing.assert_close(T.get_batch_logps(logits_r, right), T.get_batch_logps(logits_l, left))   # plain sum: no
+    ddpo_r = T.get_batch_logps(logits_r, right, mask_shared_tokens=True)
+    ddpo_l = T.get_batch_logps(logits_l, left, mask_shared_tokens=True)
+    assert float((ddpo_r - ddpo_l).abs().max()) > 1.0                                                   # DDPO: yes
+    torch.testing.assert_close(R.get_batch_logps(logits_l, left, mask_shared_tokens=True), ddpo_l)      # (the oracle follows)

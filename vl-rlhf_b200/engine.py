@@ -737,7 +737,9 @@ class LlavaDPOEngine:
         from . import host
         tc = self.tc
         cb = host.concatenated_inputs(batch, False, tc.label_pad_token_id, tc.padding_value)
-        ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+        ids, am, lb = host.right_pad_valid_tokens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                                  cb["concatenated_labels"], tc.padding_value, tc.label_pad_token_id,
+                                                  tc.loss_type)
         px = batch["img_input_dict"]["pixel_values"]  # one copy per pair: the [v, v] duplicate is never shipped
         sizes = batch["img_input_dict"].get("image_sizes")
         wt = None

@@ -168,6 +168,34 @@ def next_merged_len(input_ids: torch.Tensor, attention_mask: torch.Tensor, featu
     return int(((attention_mask == 1).sum(-1) - n_special + feat).max())
 
 
+def right_pad_valid_tokens(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
+                           padding_value: int = 0, label_pad_token_id: int = -100, loss_type: str = "sigmoid"):
+    """Left-padded (or otherwise interleaved) batches, SURVEY.md f-2: move every sequence's attended tokens to the front,
+    order kept, and pad on the right.  Nothing the hot path returns depends on WHERE the padding sits: the reference derives
+    the rotary positions from the mask (`position_ids = cumsum(mask) - 1`, Llava/__init__.py:98), masked keys are invisible
+    to every attended query, and get_batch_logps sums over the labelled tokens only (base/trainer.py:185-188) -- so the
+    per-sequence log-probs of the right-padded form are those of the original (checked against the reference's own
+    LlavaForRL on a left-padded batch, tests/test_oracle_vs_reference.py).  Only the padding positions' own (unused) logits
+    move.  Inputs whose masks are already prefixes are returned as they are.
+
+    DDPO is the exception and is refused: the reference diffs the chosen and rejected LABEL sequences padding included
+    (masked positions become token 0, base/trainer.py:166,177-180), so its shared-token mask -- and with it the log-probs --
+    depends on the padding side (measured on the reference itself: up to 130 nats apart on a tiny batch)."""
+    att = attention_mask == 1
+    if not bool((att[:, 1:] & ~att[:, :-1]).any()):
+        return input_ids, attention_mask, labels
+    if loss_type == "ddpo":
+        raise ValueError("loss_type='ddpo' needs right-padded batches (what VLDPODataCollatorWithPadding emits): the reference's "
+                         "token diff runs over the padded label sequences and changes with the padding side")
+    L = input_ids.shape[1]
+    order = torch.argsort((~att).to(torch.int8), dim=1, stable=True)   # attended tokens first, original order kept
+    tail = torch.arange(L, device=input_ids.device)[None, :] >= att.sum(1, keepdim=True)
+    ids = torch.gather(input_ids, 1, order).masked_fill(tail, padding_value)
+    lab = torch.gather(labels, 1, order).masked_fill(tail, label_pad_token_id)
+    am = torch.gather(attention_mask, 1, order).masked_fill(tail, 0)
+    return ids, am, lab
+
+
 def merged_seq_lens(input_ids: torch.Tensor, attention_mask: torch.Tensor, image_token_index: int, feat_rows) -> List[int]:
     """Merged length of every sequence's attended prefix -- what the merge kernels report as `seqlens` -- computed on the
     host so that a packed step (TrainConfig.pack_sequences) needs no device read-back: attended text tokens minus the

@@ -215,7 +215,9 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     which = getattr(model, "_which", "policy")
     cb = host.concatenated_inputs(batch, getattr(self, "is_encoder_decoder", False),
                                   getattr(self, "label_pad_token_id", -100), getattr(self, "padding_value", 0) or 0)
-    ids, am, lb = cb["concatenated_input_ids"], cb["concatenated_attention_mask"], cb["concatenated_labels"]
+    ids, am, lb = host.right_pad_valid_tokens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                              cb["concatenated_labels"], getattr(self, "padding_value", 0) or 0,
+                                              getattr(self, "label_pad_token_id", -100), self.loss_type)
     if "img_input_dict" in batch:
         px = batch["img_input_dict"]["pixel_values"]
         sizes = batch["img_input_dict"].get("image_sizes")  # LLaVA-Next (LlavaNext/__init__.py:348-380 collators)
