@@ -125,14 +125,15 @@ def test_llava_forward_and_merge_equal_reference(name, sizes):
     np.testing.assert_allclose(torch.cat([pcl, prl]).numpy(), out.logits.float().numpy(), rtol=1e-3, atol=2e-4)
 
 
-def test_left_padded_reference_equals_right_padded_path():
-    """f-2 (left padding): the reference's LlavaForRL on a LEFT-padded batch gives, per sequence, the log-probs of the
-    right-padded form -- which is what host.right_pad_valid_tokens hands to the engine."""
+@pytest.mark.parametrize("name,sizes", [("TINY", None), ("TINY_NEXT", [(28, 28), (20, 50), (60, 25)])])
+def test_left_padded_reference_equals_right_padded_path(name, sizes):
+    """f-2 (left padding): the reference's LlavaForRL / LlavaNextForRL on a LEFT-padded batch gives, per sequence, the
+    log-probs of the right-padded form -- which is what host.right_pad_valid_tokens hands to the engine."""
     from oracle import make_fixtures as MF
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import host
-    cfg, seed = R.TINY, 9
-    batch = R.make_batch(cfg, 3, 24, 8, seed, ddpo_like=True)
+    cfg, seed = getattr(R, name), 9
+    batch = R.make_batch(cfg, 3, 24, 8, seed, ddpo_like=True, image_sizes=sizes)
     left = dict(batch)
     for side in ("chosen", "rejected"):
         ids, am, lb = (batch[f"{side}_{k}"].clone() for k in ("input_ids", "attention_mask", "labels"))
