@@ -184,3 +184,32 @@ def test_reference_ddpo_depends_on_the_padding_side(ref):
     ddpo_l = T.get_batch_logps(logits_l, left, mask_shared_tokens=True)
     assert float((ddpo_r - ddpo_l).abs().max()) > 1.0                                                   # DDPO: yes
     torch.testing.assert_close(R.get_batch_logps(logits_l, left, mask_shared_tokens=True), ddpo_l)      # (the oracle follows)
+
+
+@pytest.mark.parametrize("minter", ["g1_logps", "g2_loss", "g3_ddpo", "g4", "g6_next", "g7_clip_preprocess", "g9_qwen",
+                                    "g10_xc2", "g11_lora"])
+def test_committed_fixtures_regenerate_from_the_reference(minter, tmp_path, monkeypatch):
+    """Every committed vector in tests/golden/ (the 7B-shape ones aside: minutes and ~30 GB) comes out of the reference's own
+    functions again, value for value: LlavaForRL, LlavaNextForRL, the vendored QWenLMHeadModel and InternLMXC2ForRL with
+    hand-applied peft-style adapters, get_batch_logps, dpo_loss, get_diff_ids, Pillow + CLIPImageProcessor."""
+    import os
+    from oracle import make_fixtures as MF
+    golden = MF.GOLDEN
+    monkeypatch.setattr(MF, "GOLDEN", str(tmp_path))
+    if minter == "g4":
+        MF.g45_llava("g4_tiny", R.TINY, 2, 24, 8, 0, ddpo=True)
+        MF.g45_llava("g4_small", R.SMALL, 2, 96, 24, 0, ddpo=True)
+    else:
+        getattr(MF, minter)()
+    made = sorted(os.listdir(tmp_path))
+    assert made
+    for f in made:
+        new, old = np.load(os.path.join(tmp_path, f), allow_pickle=True), np.load(os.path.join(golden, f), allow_pickle=True)
+        assert set(new.files) == set(old.files), f
+        for k in old.files:
+            a, b = new[k], old[k]
+            assert a.shape == b.shape and a.dtype == b.dtype, (f, k)
+            if a.dtype.kind in "fc":
+                np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6, err_msg=f"{f}:{k}")
+            else:
+                assert np.array_equal(a, b), (f, k)
