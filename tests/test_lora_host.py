@@ -165,12 +165,12 @@ def test_lora_peft_init_makes_policy_equal_reference(lpkg):
     assert abs(m["loss"] - float(np.log(2.0))) < 1e-6 and m["rewards/margins"] == 0.0
 
 
-@pytest.mark.parametrize("tag", ["g11_lora_tiny", "g11_next_lora_tiny"])
-def test_lora_packed_step_equals_padded_step(lpkg, tag):
+@pytest.mark.parametrize("tag,ckpt,loss_type", [("g11_lora_tiny", False, "sigmoid"), ("g11_next_lora_tiny", True, "ddpo")])
+def test_lora_packed_step_equals_padded_step(lpkg, tag, ckpt, loss_type):
     """TrainConfig.pack_sequences on the LoRA engine: same log-probs, loss, rewards and adapter gradients as the padded step."""
     res = []
     for pack in (False, True):
-        eng, cfg, d, batch = _setup(lpkg, tag, pack_sequences=pack)
+        eng, cfg, d, batch = _setup(lpkg, tag, loss_type=loss_type, pack_sequences=pack, activation_checkpointing=ckpt)
         metrics = eng.train_step(batch, train=True)
         assert eng._saved["m"].packed == pack
         res.append((metrics, eng.grads.clone()))
