@@ -356,9 +356,11 @@ def pack_merge_rows(m, seq_lens):
     m.src_map = m.src_map.reshape(-1)[keep].contiguous()
     m.pos = m.pos.reshape(-1)[keep].contiguous()
     m.row_of_text = remap(m.row_of_text.reshape(-1))
-    if m.total_feats is not None and m.reps is not None:   # LLaVA-Next: flat merged rows
+    if getattr(m, "img_pos", None) is None:                 # Qwen-VL: no image row list
+        pass
+    elif m.total_feats is not None and m.reps is not None:  # LLaVA-Next: flat merged rows
         m.img_pos = remap(m.img_pos.reshape(-1))
-    else:                                                   # LLaVA-1.5: positions inside the sequence -> absolute rows
+    else:                                                   # LLaVA-1.5 / XC2: positions inside the sequence -> absolute rows
         feats = m.imgs_per_seq * m.P
         b = torch.arange(m.img_pos.numel()) // feats
         m.img_pos = (m.img_pos.reshape(-1).long() + st[b]).to(torch.int32)

@@ -319,3 +319,22 @@ def test_qwen_from_pretrained_adapters_and_plugin_forward(qpkg, qplugin, tmp_pat
         w_rc, w_rr, _, _, _ = Q.concatenated_forward(qcfg, w, None, b3)
     np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), torch.cat([w_pc, w_pr]).numpy(), rtol=1e-3)
     np.testing.assert_allclose(torch.cat([rc, rr]).numpy(), torch.cat([w_rc, w_rr]).numpy(), rtol=1e-3)
+
+
+@pytest.mark.parametrize("loss_type,ckpt", [("sigmoid", False), ("ddpo", True)])
+def test_qwen_packed_step_equals_padded_step(qpkg, loss_type, ckpt):
+    """TrainConfig.pack_sequences on the Qwen-VL engine (S == L: the attended tokens survive): same log-probs, loss, rewards
+    and adapter gradients as the padded step."""
+    res = []
+    for pack in (False, True):
+        eng, qcfg, d, batch = _setup(qpkg, "g9_qwen_tiny", loss_type=loss_type, pack_sequences=pack, activation_checkpointing=ckpt)
+        assert int((batch["chosen_attention_mask"] == 0).sum() + (batch["rejected_attention_mask"] == 0).sum()) > 0
+        metrics = eng.train_step(batch, train=True)
+        m = eng._saved["m"]
+        assert m.packed == pack and (not pack or m.T < m.n_seq * m.S)
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in m0:
+        if not k.startswith("logits/"):
+            assert m0[k] == m1[k], k
+    assert torch.equal(g0, g1) and float(g0.float().abs().sum()) > 0

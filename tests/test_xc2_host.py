@@ -155,3 +155,22 @@ def test_xc2_engine_optimizer_updates_only_adapters(xpkg):
     assert l1 < l0
     assert torch.equal(eng.bparams, base0) and torch.equal(eng.vparams, vis0)
     assert torch.equal(eng.params, eng.master.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("loss_type,ckpt", [("kto_pair", False), ("ddpo", True)])
+def test_xc2_packed_step_equals_padded_step(xpkg, loss_type, ckpt):
+    """TrainConfig.pack_sequences on the XC2 engine (the partial-LoRA image rows become absolute packed rows, the arange
+    rotary positions are packed along): same log-probs, loss, rewards and adapter gradients as the padded step."""
+    res = []
+    for pack in (False, True):
+        eng, xcfg, d, batch = _setup(xpkg, "g10_xc2_tiny", loss_type=loss_type, pack_sequences=pack, activation_checkpointing=ckpt)
+        assert int((batch["chosen_attention_mask"] == 0).sum() + (batch["rejected_attention_mask"] == 0).sum()) > 0
+        metrics = eng.train_step(batch, train=True)
+        m = eng._saved["m"]
+        assert m.packed == pack and (not pack or m.T < m.n_seq * m.S)
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in m0:
+        if not k.startswith("logits/"):
+            assert m0[k] == m1[k], k
+    assert torch.equal(g0, g1) and float(g0.float().abs().sum()) > 0

@@ -114,7 +114,7 @@ class TrainConfig:
     # drop the collator's padding rows (base/collator.py:44-60) from the merged batch -- sequences are stacked
     # back to back, attention runs var-len -- so padded positions cost nothing.  Log-probs, losses, rewards and gradients
     # are those of the padded batch; only TRL's `logits/chosen|rejected` metric changes meaning (it averages over the
-    # attended positions instead of all positions).  LLaVA-1.5 / LLaVA-Next engines (full fine-tune and LoRA).
+    # attended positions instead of all positions).  All engines (LLaVA-1.5 / LLaVA-Next full fine-tune and LoRA, Qwen-VL, XC2).
     pack_sequences: bool = False
 
 

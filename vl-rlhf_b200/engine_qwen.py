@@ -294,7 +294,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
     # ------------------------------------------------------------------ decoder layer (base weights b, adapters l or None)
     def _layer_bufs(self, pre: str, sfx: str, m):
         b = super()._layer_bufs(pre, sfx, m)
-        T, r = m.n_seq * m.S, self.cfg.lora_r
+        T, r = m.T, self.cfg.lora_r
         if pre == "a":
             b.update(ts_qkv=self.buf(f"a.ts_qkv{sfx}", (T, r)), ts_o=self.buf(f"a.ts_o{sfx}", (T, r)),
                      ts_gu=self.buf(f"a.ts_gu{sfx}", (T, 2 * r)))
@@ -302,7 +302,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
 
     def _layer_fwd(self, w, i: int, x, b, m, xn, lora: Optional[Weights] = None):
         cfg, base = self.cfg, self.base
-        d, T, ff, r = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r
+        d, T, ff, r = cfg.hidden, m.T, cfg.ff, cfg.lora_r
         H, dh = cfg.heads, cfg.head_dim
         h = self.buf("s.h", (T, d))
         qkv, att, xmid, gu = b["qkv"], b["att"], b["xmid"], b["gu"]
@@ -321,7 +321,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.gemm(h, base[f"L{i}.wqkv"], a2=ts, b2=lora[f"L{i}.qkv.B"], out=qkv, bias=base[f"L{i}.bqkv"])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh)
         ops.attn_fwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, H, dh, True,
-                        1.0 / math.sqrt(dh))
+                        1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -344,7 +344,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
     # ------------------------------------------------------------------ forward of one pass
     def _forward(self, w, m, feats, tag: str, save: bool, ddpo_weight):
         cfg, base = self.cfg, self.base
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         lora = self.policy if tag == "policy" else None
         x = self.buf("x.0" if save else "s.x0", (T, d), torch.float32)
         ops.llava_merge_embed(m, base["embed"], feats, x)   # text rows: wte; placeholder rows: image features (:614-621)
@@ -363,7 +363,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
         m = sv["m"]
-        d, T, ff, r = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r
+        d, T, ff, r = cfg.hidden, m.T, cfg.ff, cfg.lora_r
         H, dh = cfg.heads, cfg.head_dim
         s = cfg.lora_scale
         dx = self._head_backward(grad_logps, base["norm"], base["lm_head"], self._dw_scratch, None)
@@ -407,7 +407,8 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])            # dAo = dt^T att
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
-                            dqkv[:, 2 * d:], m.seqlens, m.n_seq, m.S, H, H, dh, True, scale)
+                            dqkv[:, 2 * d:], m.seqlens, m.n_seq, m.S, H, H, dh, True, scale, row_starts=m.starts,
+                            total_rows=m.T)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh, inverse=True)
             # ---- fused qkv projection (LoRA on attn.c_attn; the bias is frozen)
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
@@ -436,17 +437,23 @@ class QwenVLDPOEngine(LlavaDPOEngine):
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
                       feats=None, m=None, seq_lens=None):
-        if self.tc.pack_sequences:
-            raise ValueError("pack_sequences is implemented for the LLaVA-1.5 / LLaVA-Next engines only")
         cfg = self.cfg
         self._anyres = None
         if m is None:
             m = ops.qwen_merge_index(ids, am, lb, cfg.n_queries, px.shape[0], 1, cfg.image_start_id, cfg.ignore_index)
+            if self.tc.pack_sequences:   # S == L here: the surviving rows are the attended tokens
+                ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":
             self.wait_optimizer()
         return self._forward(None, m, feats, which, save, ddpo_weight), m, feats
+
+    def host_seq_lens(self, ids, am, image_sizes=None):
+        """Packed steps: no token is expanded (S == L), a sequence keeps its attended tokens."""
+        from . import host
+        return host.merged_seq_lens(ids, am, -1, 0)
 
     def ddpo_weights(self, ids, am, lb, image_sizes=None) -> torch.Tensor:
         """DDPO row weights: no token is expanded (S == L), padding stays in the label sequence (as ignore labels)."""

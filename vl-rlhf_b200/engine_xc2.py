@@ -227,7 +227,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
 
     def _layer_bufs(self, pre: str, sfx: str, m):
         b = LlavaDPOEngine._layer_bufs(self, pre, sfx, m)
-        T, r = m.n_seq * m.S, self.cfg.lora_r
+        T, r = m.T, self.cfg.lora_r
         if pre == "a":
             b.update(ts_qkv=self.buf(f"a.ts_qkv{sfx}", (T, r)), ts_o=self.buf(f"a.ts_o{sfx}", (T, r)),
                      ts_gu=self.buf(f"a.ts_gu{sfx}", (T, 2 * r)), ts_d=self.buf(f"a.ts_d{sfx}", (T, r)))
@@ -235,7 +235,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
 
     def _layer_fwd(self, w, i: int, x, b, m, xn, lora: Optional[Weights] = None):
         cfg, base = self.cfg, self.base
-        d, T, ff, r, pr = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r, cfg.plora_r
+        d, T, ff, r, pr = cfg.hidden, m.T, cfg.ff, cfg.lora_r, cfg.plora_r
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         h = self.buf("s.h", (T, d))
@@ -255,7 +255,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         self._plora_fwd(h, base[f"L{i}.p.qkv.A"], [(base[f"L{i}.p.qkv.B"], qkv, slice(0, pr))], m, "qkv")
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
         ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh))
+                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -287,7 +287,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
     # ------------------------------------------------------------------ forward of one pass
     def _forward(self, w, m, feats, tag: str, save: bool, ddpo_weight):
         cfg, base = self.cfg, self.base
-        d, T = cfg.hidden, m.n_seq * m.S
+        d, T = cfg.hidden, m.T
         lora = self.policy if tag == "policy" else None
         nimg = feats.shape[0]
         ph = self.buf("p.h_ref", (nimg, d))                               # frozen projector (build_mlp.py:14-28)
@@ -311,7 +311,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
         m = sv["m"]
-        d, T, ff, r, pr = cfg.hidden, m.n_seq * m.S, cfg.ff, cfg.lora_r, cfg.plora_r
+        d, T, ff, r, pr = cfg.hidden, m.T, cfg.ff, cfg.lora_r, cfg.plora_r
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
         s = cfg.lora_scale
@@ -364,7 +364,8 @@ class XC2DPOEngine(QwenVLDPOEngine):
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)
             self._plora_bwd([(dx2, base[f"L{i}.p.o.B"], slice(0, pr))], base[f"L{i}.p.o.A"], datt)
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
-                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale)
+                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale,
+                            row_starts=m.starts, total_rows=m.T)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             # ---- fused qkv projection
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
@@ -383,8 +384,6 @@ class XC2DPOEngine(QwenVLDPOEngine):
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
                       feats=None, m=None, seq_lens=None):
-        if self.tc.pack_sequences:
-            raise ValueError("pack_sequences is implemented for the LLaVA-1.5 / LLaVA-Next engines only")
         cfg = self.cfg
         self._anyres = None
         if m is None:
@@ -392,14 +391,21 @@ class XC2DPOEngine(QwenVLDPOEngine):
                                       cfg.ignore_index)
             # rotary positions are arange(S) for every row, padded or not (modeling_internlm2.py:186-203)
             m.pos = torch.arange(m.S, dtype=torch.int32, device=ids.device).repeat(m.n_seq)
-        # flat merged rows of every image position (the PLoRA row mask im_mask, __init__.py:87-104)
-        self._img_rows = (m.img_pos.view(m.n_seq, -1) +
-                          (torch.arange(m.n_seq, dtype=torch.int32, device=m.img_pos.device) * m.S)[:, None]).reshape(-1).contiguous()
+            if self.tc.pack_sequences:   # drop the padding rows (the rotary positions above are packed along)
+                ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+        # flat merged rows of every image position (the PLoRA row mask im_mask, __init__.py:87-104); packed: already absolute
+        self._img_rows = m.img_pos if m.packed else (
+            m.img_pos.view(m.n_seq, -1) +
+            (torch.arange(m.n_seq, dtype=torch.int32, device=m.img_pos.device) * m.S)[:, None]).reshape(-1).contiguous()
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":
             self.wait_optimizer()
         return self._forward(None, m, feats, which, save, ddpo_weight), m, feats
+
+    def host_seq_lens(self, ids, am, image_sizes=None):
+        return LlavaDPOEngine.host_seq_lens(self, ids, am, image_sizes)   # one <image> token -> n_patches rows, as LLaVA-1.5
 
     def ddpo_weights(self, ids, am, lb, image_sizes=None) -> torch.Tensor:
         from . import host

@@ -435,7 +435,7 @@ def llavanext_merge_bwd(m: MergeIndex, dx: torch.Tensor, dembed_f32: torch.Tenso
 
 
 def pack_merge_rows(m: MergeIndex, seq_lens) -> MergeIndex:
-    """Drop the padding rows of a LLaVA-1.5 / LLaVA-Next merge index: `seq_lens` (host ints, one per sequence,
+    """Drop the padding rows of a LLaVA-1.5 / LLaVA-Next / Qwen-VL merge index: `seq_lens` (host ints, one per sequence,
     == m.seqlens) gives the attended prefix of every sequence; afterwards sequence b lives at rows
     [row_starts[b], row_starts[b] + seq_lens[b]) and m.T = sum(seq_lens).  m.labels / m.mask keep the padded [n_seq, S] layout
     (they feed no kernel)."""
@@ -454,9 +454,11 @@ def pack_merge_rows(m: MergeIndex, seq_lens) -> MergeIndex:
     pos_p = torch.empty(rows, dtype=torch.int32, device=dev)
     next_layout = getattr(m, "total_feats", None) is not None and getattr(m, "reps", None) is not None
     img_pos, n_img_pos, feats, img_rows, n_img_rows = None, 0, 0, None, 0
-    if next_layout:      # LLaVA-Next: img_pos holds flat merged rows
+    if getattr(m, "img_pos", None) is None:
+        pass                 # Qwen-VL: the image rows are placeholder tokens of the text sequence (frozen tower): no row list
+    elif next_layout:        # LLaVA-Next: img_pos holds flat merged rows
         img_rows, n_img_rows = m.img_pos, m.img_pos.numel()
-    else:                # LLaVA-1.5: img_pos holds positions inside the sequence
+    else:                    # LLaVA-1.5 / XC2: img_pos holds positions inside the sequence
         img_pos, n_img_pos, feats = m.img_pos, m.img_pos.numel(), m.imgs_per_seq * m.P
     check(_L.vlb200_pack_merge_rows(_ptr(m.src_map), _ptr(m.pos), _ptr(row_starts), m.n_seq, m.S, _ptr(src_p), _ptr(pos_p),
                                     _ptr(m.row_of_text), m.row_of_text.numel(), _ptr(img_pos), n_img_pos, feats,
