@@ -62,8 +62,15 @@ def _worker(rank, world, port, out_dir):
     assert eng3.master.numel() == eng3.n_flat // 2 and eng3.shard_lo == rank * eng3.n_flat // 2
     eng3.init_synthetic(0)
     eng3.step(*a[:4], train=True)
+    # packed rows (TrainConfig.pack_sequences): every rank drops its own padding rows -- a different row count per rank, no
+    # collective depends on it -- and lands on the same parameters as the padded sharded step
+    eng4 = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3, pack_sequences=True), device="cpu")
+    eng4.init_synthetic(0)
+    eng4.step(*a[:4], train=True)
+    packed_rows = eng4._saved["m"].T
     n = eng.params.numel()
-    torch.save({"local": local, "summed": summed, "params": eng.params.clone(), "world": eng.world_size(),
+    torch.save({"params_packed": eng4.params[:n].clone(), "packed_rows": packed_rows,
+                "padded_rows": eng4._saved["m"].n_seq * eng4._saved["m"].S, "local": local, "summed": summed, "params": eng.params.clone(), "world": eng.world_size(),
                 "sumsq": eng.grad_sumsq.clone(), "params_overlap": eng2.params.clone(), "grads_overlap": eng2.grads.clone(),
                 "params_sharded": eng3.params[:n].clone(), "sumsq_sharded": eng3.grad_sumsq.clone(),
                 "grads_sharded_own": eng3.grads[eng3.shard_lo:eng3.shard_hi].clone(), "shard": (eng3.shard_lo, eng3.shard_hi),
@@ -106,6 +113,9 @@ def test_two_rank_data_parallel_step(tmp_path):
     torch.testing.assert_close(r0["sumsq_sharded"], r0["sumsq"], rtol=1e-5, atol=0)
     same = (r0["params_sharded"] == r0["params"]).float().mean().item()
     assert same > 0.9999, same
+    # packed rows: identical replicas, identical to the padded sharded step
+    assert torch.equal(r0["params_packed"], r1["params_packed"]) and torch.equal(r0["params_packed"], r0["params_sharded"])
+    assert r0["packed_rows"] < r0["padded_rows"] or r1["packed_rows"] < r1["padded_rows"]
 
 
 def _qwen_worker(rank, world, port, out_dir):
