@@ -722,3 +722,14 @@ def test_left_padded_batch_gives_the_right_padded_results(cpu_pkg, pack):
     with pytest.raises(ValueError):                                   # the reference's DDPO diff depends on the padding side
         host.right_pad_valid_tokens(ids, am, lb, 0, -100, loss_type="ddpo")
     assert host.right_pad_valid_tokens(i2, a2, l2, loss_type="ddpo")[0] is i2
+
+
+def test_pack_sequences_launcher_switch(cpu_pkg, monkeypatch):
+    """VLB200_PACK_SEQUENCES=1 reaches engines built without a TrainConfig (the way the reference's dpo.py builds the model);
+    an explicit TrainConfig keeps its own setting."""
+    config, engine, host, ops = cpu_pkg
+    monkeypatch.setenv("VLB200_PACK_SEQUENCES", "1")
+    assert engine.LlavaDPOEngine(config.TINY, None, device="cpu", with_optimizer=False).tc.pack_sequences
+    assert not engine.LlavaDPOEngine(config.TINY, config.TrainConfig(), device="cpu", with_optimizer=False).tc.pack_sequences
+    monkeypatch.delenv("VLB200_PACK_SEQUENCES")
+    assert not engine.LlavaDPOEngine(config.TINY, None, device="cpu", with_optimizer=False).tc.pack_sequences
