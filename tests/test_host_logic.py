@@ -366,6 +366,14 @@ def test_precomputed_reference_logps_skip_the_ref_pass(cpu_pkg):
         a = eng.prepare_inputs(*(cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels")),
                                cb["concatenated_img_input_dict"]["pixel_values"])
         eng.step(*a, train=False, ref_logps=torch.zeros(3))
+    # the producer half (trl compute_reference_log_probs): one no-grad reference pass, values == the step's own reference pass
+    rc, rr = eng.compute_reference_log_probs(batch)
+    assert rc.device.type == "cpu" and rc.shape == rr.shape == (2,)
+    np.testing.assert_allclose(torch.cat([rc, rr]).numpy(), d["ref_logps"], rtol=1e-3)
+    b3 = dict(batch, reference_chosen_logps=rc, reference_rejected_logps=rr)
+    again = eng.train_step(b3, train=False)
+    for k in ("loss", "rewards/chosen", "rewards/rejected", "rewards/margins", "rewards/accuracies"):
+        assert again[k] == base[k], k
 
 
 def test_activation_checkpointing_gives_identical_gradients(cpu_pkg):

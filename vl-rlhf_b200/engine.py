@@ -764,6 +764,26 @@ class LlavaDPOEngine:
                 "logits/chosen": float(packed[9]), "logits/rejected": float(packed[10]),
                 "grad_norm": float(packed[8]) ** 0.5 / world}
 
+    def compute_reference_log_probs(self, batch: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
+        """trl 0.8.1 DPOTrainer.compute_reference_log_probs (the producer half of precompute_ref_log_probs, base/trainer.py:61,96):
+        one no-grad reference pass over a collated batch -> (reference_chosen_logps, reference_rejected_logps) on the host,
+        ready to be stored with the dataset and fed back through the batch keys of the same names (base/collator.py:62-64),
+        which makes `train_step` skip its reference pass."""
+        from . import host
+        tc = self.tc
+        cb = host.concatenated_inputs(batch, False, tc.label_pad_token_id, tc.padding_value)
+        ids, am, lb = host.right_pad_valid_tokens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                                  cb["concatenated_labels"], tc.padding_value, tc.label_pad_token_id,
+                                                  tc.loss_type)
+        sizes = batch["img_input_dict"].get("image_sizes")
+        wt = self.ddpo_weights(ids, am, lb, sizes) if tc.loss_type == "ddpo" else None
+        seq_lens = self.host_seq_lens(ids, am, sizes) if tc.pack_sequences else None
+        inputs = self.prepare_inputs(ids, am, lb, batch["img_input_dict"]["pixel_values"], wt, sizes)
+        logps, _, _ = self.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens)
+        logps = logps.float().cpu()
+        n = logps.numel() // 2
+        return logps[:n], logps[n:]
+
     def host_seq_lens(self, ids, am, image_sizes=None) -> List[int]:
         """Merged length of every sequence of one concatenated host batch (packed steps: the rows that survive)."""
         from . import host
