@@ -96,6 +96,19 @@ int vlb200_set_gemm_mode(int mode);
  * knob: results do not depend on it.                                                                                 */
 int vlb200_set_gemm_raster_mb(double mb);
 
+/* Rasterisation policy of the CTA-pair kernel.  0 (default): the L2-budget rule above.  1 (or the environment variable
+ * VLB200_RASTER_POLICY=model): per distinct launch shape, the (orientation, group) that reads the least DRAM under an LRU
+ * model of L2 replaying the 74-pair tile schedule (effective capacity VLB200_L2_MODEL_MB, default 60; fitted to the ncu
+ * DRAM reads of profiles/r1d_gemm_dram_traffic.json -- tests/raster_model.py, profiles/r1d_raster_model.md); cached per
+ * shape.  < 0 restores the environment / default.  A tuning knob: results do not depend on it.
+ * vlb200_gemm_plan_raster: host-only query (no GPU needed) of what a policy picks for an [M,K] x [N,K] launch writing
+ * out_bytes (2|4) per element, and the DRAM read bytes the model predicts for that choice.                              */
+int vlb200_set_gemm_raster_policy(int policy);
+int vlb200_gemm_plan_raster(int M, int N, int K, int out_bytes, int policy, int* group, int* along_n, double* model_read_bytes);
+/* Host-side evaluation of the kernels' tile rasterisation (tile index -> block coordinates) for a given group / orientation:
+ * lets a CPU test check that every (group, orientation) the policies can pick visits each output tile exactly once.        */
+int vlb200_gemm_tile_coords(int num_m_blocks, int num_n_blocks, int group, int along_n, int tile, int* m_blk, int* n_blk);
+
 /* ---- log-prob gather (K16) -- base/trainer.py:148-188 VLDPOTrainer.get_batch_logps -------
  * logits: [rows, V] (dtype bf16|f32, row stride ld_logits elements).  Row r predicts target[r];
  * target[r] < 0 (label_pad) rows are skipped without being read.  rows = n_seq * rows_per_seq

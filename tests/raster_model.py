@@ -1,0 +1,146 @@
+"""Development tool (not a pytest file, runs on the CPU): an LRU model of the B200 L2 under the pair GEMM's tile schedule, to
+choose rasterisations offline.
+
+The persistent pair GEMM (csrc/gemm_tcgen05.cu) runs n_pairs = 74 CTA pairs; pair p computes tiles p, p + 74, p + 148, ... of
+the rasterised tile list, and all pairs walk their tile's k-blocks (64 wide) roughly in lockstep.  Per k-block a pair reads
+one 256-row x 64-k slab of A and one 256-row x 64-k slab of B (32 KB each); a finished 256 x 256 tile writes 128 KB (bf16)
+or 256 KB (fp32) of D through the (write-allocating) L2.  The model replays that access stream against an LRU of `cap_mb`
+and counts the slabs that miss = DRAM reads.  It knows nothing about the two L2 partitions, sectors or the hash, so `cap_mb`
+is a fitted "effective capacity": see `fit` below for the value that reproduces the ncu numbers of
+profiles/r1d_gemm_dram_traffic.json.
+
+    python tests/raster_model.py fit            # effective capacity that matches the measured DRAM reads
+    python tests/raster_model.py search [cap]   # best (orientation, group) per GEMM shape of the config-2 step
+"""
+import sys
+from collections import OrderedDict
+
+PAIR, BK, N_PAIRS = 256, 64, 74
+SLAB = PAIR * BK * 2  # bytes of one operand slab (bf16)
+
+
+def tile_order(num_m, num_n, group, along_n):
+    """the kernel's tile_coords(): tile index -> (m_blk, n_blk)"""
+    out = []
+    if not along_n:
+        for g0 in range(0, num_m, group):
+            gm = min(group, num_m - g0)
+            for i in range(gm * num_n):
+                out.append((g0 + i % gm, i // gm))
+    else:
+        for g0 in range(0, num_n, group):
+            gn = min(group, num_n - g0)
+            for i in range(gn * num_m):
+                out.append((i // gn, g0 + i % gn))
+    return out
+
+
+def current_policy(M, N, K, budget_mb=32.0):
+    """choose_raster() of csrc/gemm_tcgen05.cu"""
+    num_m, num_n = -(-M // PAIR), -(-N // PAIR)
+    budget = budget_mb * 1024 * 1024
+    a_blk = b_blk = PAIR * K * 2
+    a_bytes, b_bytes = M * K * 2, N * K * 2
+    gm = min(max(int(budget / a_blk), 4), num_m)
+    gn = min(max(int(budget / b_blk), 2), num_n)
+    cost_m = a_bytes + b_bytes * (-(-num_m // gm))
+    cost_n = b_bytes + a_bytes * (-(-num_n // gn))
+    along_n = cost_n < cost_m
+    return (gn if along_n else gm), along_n
+
+
+def dram_reads(M, N, K, group, along_n, cap_mb, out_bytes=2):
+    """-> DRAM read bytes of one launch under the model"""
+    num_m, num_n, num_k = -(-M // PAIR), -(-N // PAIR), -(-K // BK)
+    tiles = tile_order(num_m, num_n, group, along_n)
+    cap = int(cap_mb * 1024 * 1024)
+    lru, used, miss = OrderedDict(), 0, 0
+    d_tile = PAIR * PAIR * out_bytes
+
+    def touch(key, size, count):
+        nonlocal used, miss
+        if key in lru:
+            lru.move_to_end(key)
+            return
+        if count:
+            miss += 1
+        lru[key] = size
+        used += size
+        while used > cap:
+            _, s = lru.popitem(last=False)
+            used -= s
+
+    for w0 in range(0, len(tiles), N_PAIRS):            # one wave = the tiles the 74 pairs hold at the same time
+        wave = tiles[w0:w0 + N_PAIRS]
+        for kb in range(num_k):
+            for (m, n) in wave:
+                touch(("A", m, kb), SLAB, True)
+                touch(("B", n, kb), SLAB, True)
+        for (m, n) in wave:                              # epilogue: D streams out through L2
+            touch(("D", m, n), d_tile, False)
+    return miss * SLAB
+
+
+T, d, ff = 12792, 4096, 11008
+SHAPES = {  # name: (M, N, K, out_bytes, launches per step)
+    "fwd qkv": (T, 3 * d, d, 2, 64), "fwd o": (T, d, d, 4, 64), "fwd gate_up": (T, 2 * ff, d, 2, 64),
+    "fwd down": (T, d, ff, 4, 64), "dgrad qkv": (T, d, 3 * d, 2, 32), "dgrad o": (T, d, d, 2, 32),
+    "dgrad gate_up": (T, d, 2 * ff, 2, 32), "dgrad down": (T, ff, d, 2, 32), "wgrad qkv": (3 * d, d, T, 2, 32),
+    "wgrad o": (d, d, T, 2, 32), "wgrad gate_up": (2 * ff, d, T, 2, 32), "wgrad down": (d, ff, T, 2, 32),
+}
+# ncu dram__bytes_read.sum per launch at the 32 MB budget (profiles/r1d_gemm_dram_traffic.json h0_mb32 and the first pass of the
+# same probe, profiles/r1d_gemm_l2_probe.md), GB
+MEASURED = {"fwd gate_up": (0.98, 1.32), "fwd qkv": (0.49, 0.53), "fwd down": (1.61, 1.66), "dgrad gate_up": (3.00, 4.44),
+            "wgrad gate_up": (3.01, 3.88)}
+
+
+def fit():
+    print("cap_mb  " + "  ".join(f"{k:>14s}" for k in MEASURED) + "   log-error")
+    best = None
+    for cap in (24, 32, 40, 48, 56, 64, 80, 96, 112):
+        row, err = [], 0.0
+        for name, (lo, hi) in MEASURED.items():
+            M, N, K, ob, _ = SHAPES[name]
+            g, an = current_policy(M, N, K)
+            gb = dram_reads(M, N, K, g, an, cap, ob) / 1e9
+            row.append(gb)
+            import math
+            err += abs(math.log(gb / ((lo * hi) ** 0.5)))
+        print(f"{cap:6d}  " + "  ".join(f"{v:14.2f}" for v in row) + f"   {err:6.2f}")
+        if best is None or err < best[0]:
+            best = (err, cap)
+    print("measured " + "  ".join(f"{lo:6.2f}-{hi:<7.2f}" for lo, hi in MEASURED.values()))
+    print("best effective capacity:", best[1], "MB")
+    return best[1]
+
+
+def search(cap):
+    total_cur = total_best = 0.0
+    print(f"effective L2 capacity {cap} MB;  GB of DRAM reads per launch (operands = the algorithmic minimum)")
+    print(f"{'shape':16s} {'operands':>9s} {'current':>22s} {'best':>22s}")
+    for name, (M, N, K, ob, per_step) in SHAPES.items():
+        num_m, num_n = -(-M // PAIR), -(-N // PAIR)
+        g0, an0 = current_policy(M, N, K)
+        cur = dram_reads(M, N, K, g0, an0, cap, ob) / 1e9
+        best = (cur, g0, an0)
+        for an in (False, True):
+            lim = num_n if an else num_m
+            for g in sorted({1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16, 20, 24, 32, 43, 50, 86, lim}):
+                if g > lim:
+                    continue
+                v = dram_reads(M, N, K, g, an, cap, ob) / 1e9
+                if v < best[0] * 0.999:
+                    best = (v, g, an)
+        alg = (M + N) * K * 2 / 1e9
+        total_cur += cur * per_step
+        total_best += best[0] * per_step
+        print(f"{name:16s} {alg:9.2f} {cur:8.2f} (g={g0:3d} {'N' if an0 else 'M'})      {best[0]:8.2f} (g={best[1]:3d} {'N' if best[2] else 'M'})")
+    print(f"per step: current {total_cur:.0f} GB, best {total_best:.0f} GB of GEMM operand reads")
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "fit"
+    if mode == "fit":
+        fit()
+    else:
+        search(float(sys.argv[2]) if len(sys.argv) > 2 else 64.0)

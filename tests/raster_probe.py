@@ -42,11 +42,15 @@ cases = [  # name, launches per step, flops, fn
     ("wgrad down", 32, 2.0 * T * d * ff, lambda: ops.gemm(x, t_ff, a_kmajor=False, b_kmajor=False, out=g_d)),
     ("wgrad lm_head", 1, 2.0 * R * V * d, lambda: ops.gemm(t_v, t_r, a_kmajor=False, b_kmajor=False, out=g_lm)),
 ]
-budgets = [float(b) for b in (sys.argv[1].split(",") if len(sys.argv) > 1 else "32,16,24,48,64,96,128,32".split(","))]
+# settings: raster budgets in MB (policy 0), or "model" = the LRU-model policy (vlb200_set_gemm_raster_policy(1))
+budgets = [b if b == "model" else float(b) for b in (sys.argv[1].split(",") if len(sys.argv) > 1 else
+                                                     "32,model,16,24,48,64,96,128,model,32".split(","))]
 iters = 16
 res = {}
 for bi, mb in enumerate(budgets):
-    ops.set_gemm_raster_mb(mb)
+    ops.set_gemm_raster_policy(1 if mb == "model" else 0)
+    if mb != "model":
+        ops.set_gemm_raster_mb(mb)
     for name, per_step, fl, fn in cases:
         for _ in range(2):
             fn()
@@ -62,7 +66,7 @@ print("budgets_mb", budgets)
 step = [0.0] * len(budgets)
 for name, per_step, fl, fn in cases:
     ms = res[name]
-    print(f"{name:20s} x{per_step:3d} " + " ".join(f"{m:7.3f}" for m in ms) + f"   best {budgets[ms.index(min(ms))]:.0f} MB", flush=True)
+    print(f"{name:20s} x{per_step:3d} " + " ".join(f"{m:7.3f}" for m in ms) + f"   best {budgets[ms.index(min(ms))]}", flush=True)
     for i, m in enumerate(ms):
         step[i] += per_step * m
 print(f"{'GEMM ms per step':24s} " + " ".join(f"{m:7.1f}" for m in step))

@@ -1,0 +1,56 @@
+"""Host-side checks of the pair GEMM's tile rasterisation (no GPU): the kernels' tile_coords() is a bijection for every
+(group, orientation) a policy can pick, the C++ planner agrees with the Python twin of the L2 model (tests/raster_model.py),
+and the model-driven policy never predicts more DRAM reads than the budget rule."""
+import ctypes
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import raster_model as RM  # noqa: E402
+
+
+def _lib():
+    import vlrlhf_b200  # noqa: F401
+    from vlrlhf_b200 import _lib
+    return _lib.load()
+
+
+def _plan(L, M, N, K, ob, policy):
+    g, an, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    assert L.vlb200_gemm_plan_raster(M, N, K, ob, policy, ctypes.byref(g), ctypes.byref(an), ctypes.byref(b)) == 0
+    return g.value, bool(an.value), b.value
+
+
+def test_tile_coords_is_a_bijection_and_matches_the_python_twin():
+    L = _lib()
+    rng = random.Random(0)
+    cases = [(50, 86, 16, 1), (50, 86, 20, 0), (50, 16, 8, 1), (86, 16, 8, 1), (16, 43, 8, 0), (1, 1, 1, 0), (3, 7, 5, 1)]
+    cases += [(rng.randint(1, 40), rng.randint(1, 40), rng.randint(1, 45), rng.randint(0, 1)) for _ in range(40)]
+    m, n = ctypes.c_int(), ctypes.c_int()
+    for num_m, num_n, group, along_n in cases:
+        got = []
+        for t in range(num_m * num_n):
+            assert L.vlb200_gemm_tile_coords(num_m, num_n, group, along_n, t, ctypes.byref(m), ctypes.byref(n)) == 0
+            got.append((m.value, n.value))
+        assert sorted(got) == [(i, j) for i in range(num_m) for j in range(num_n)], (num_m, num_n, group, along_n)
+        lim = num_n if along_n else num_m
+        assert got == RM.tile_order(num_m, num_n, min(group, lim) if group > lim else group, bool(along_n))
+    assert L.vlb200_gemm_tile_coords(2, 2, 0, 0, 0, ctypes.byref(m), ctypes.byref(n)) != 0      # group 0 is refused
+
+
+def test_planner_matches_the_python_model_on_the_step_shapes():
+    L = _lib()
+    for name, (M, N, K, ob, _) in RM.SHAPES.items():
+        g0, an0, b0 = _plan(L, M, N, K, ob, 0)
+        assert (g0, an0) == RM.current_policy(M, N, K), name                     # policy 0 == choose_raster's budget rule
+        g1, an1, b1 = _plan(L, M, N, K, ob, 1)
+        assert b1 <= b0 * 1.0001, (name, b0, b1)                                 # the model policy never predicts more traffic
+        fine = RM.dram_reads(M, N, K, g1, an1, 60, ob)                           # 64-wide k-blocks vs the planner's 8 chunks
+        assert abs(fine - b1) <= 0.08 * fine, (name, fine, b1)
+        assert b1 >= 0.99 * (M + N) * K * 2                                       # never below the operands themselves
+    # long-K launches: square waves (8-9 blocks of the short dimension) instead of panel residency
+    g, an, _ = _plan(L, *RM.SHAPES["dgrad gate_up"][:4], 1)
+    assert (g, an) == (8, True)
+    g, an, _ = _plan(L, *RM.SHAPES["wgrad gate_up"][:4], 1)
+    assert (g, an) == (8, True)

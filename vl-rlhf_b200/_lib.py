@@ -26,6 +26,9 @@ SIGNATURES = {
                                         c_int, c_void_p]),
     "vlb200_set_gemm_mode": (c_int, [c_int]),
     "vlb200_set_gemm_raster_mb": (c_int, [c_double]),
+    "vlb200_set_gemm_raster_policy": (c_int, [c_int]),
+    "vlb200_gemm_plan_raster": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vlb200_gemm_tile_coords": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vlb200_logps_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlb200_logps_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

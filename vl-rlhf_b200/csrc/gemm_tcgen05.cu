@@ -6,8 +6,12 @@
 //
 // Replaces every nn.Linear the reference reaches through transformers (see include/vlb200.h).
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <unordered_map>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -48,7 +52,7 @@ struct Params {
     int group_along_n;
 };
 
-__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
+__host__ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
     // grouped rasterisation: the CTAs running concurrently share a group of `p.group` blocks of one operand (kept hot
     // in L2) while the other operand streams past once per group; the host picks the orientation/size that minimises
     // the DRAM re-reads (r1 ncu: GROUP_M=8 re-streamed B 12.5x).
@@ -56,7 +60,7 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_bl
         const int tiles_per_group = p.group * p.num_n_blocks;
         const int g = tile / tiles_per_group;
         const int first_m = g * p.group;
-        const int group_m = min(p.num_m_blocks - first_m, p.group);
+        const int group_m = p.num_m_blocks - first_m < p.group ? p.num_m_blocks - first_m : p.group;
         const int in_group = tile - g * tiles_per_group;
         m_blk = first_m + in_group % group_m;
         n_blk = in_group / group_m;
@@ -64,7 +68,7 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_bl
         const int tiles_per_group = p.group * p.num_m_blocks;
         const int g = tile / tiles_per_group;
         const int first_n = g * p.group;
-        const int group_n = min(p.num_n_blocks - first_n, p.group);
+        const int group_n = p.num_n_blocks - first_n < p.group ? p.num_n_blocks - first_n : p.group;
         const int in_group = tile - g * tiles_per_group;
         n_blk = first_n + in_group % group_n;
         m_blk = in_group / group_n;
@@ -799,6 +803,88 @@ static void choose_raster(Params& p, double M, double N, double Kt, int TM, int 
     p.group_along_n = cost_n < cost_m;
     p.group = p.group_along_n ? gn : gm;
 }
+// ---- policy 1 (off by default; VLB200_RASTER_POLICY=model or vlb200_set_gemm_raster_policy(1)): pick (orientation, group) by
+// replaying the tile schedule against an LRU model of L2 -- tests/raster_model.py is the Python twin and
+// profiles/r1d_raster_model.md the fit.  `conc` tiles run at a time and walk K in lockstep (8 chunks here: the result does not
+// depend on the k granularity); per chunk a tile touches one slab of A and one of B, a finished tile streams its D through the
+// (write-allocating) cache.  An effective capacity of ~60 MB -- half of the 126 MB, as if each L2 partition kept its own copy --
+// reproduces the ncu DRAM reads of all five probed shapes at the default raster.  Returns the modelled DRAM read bytes.
+static double lru_model_read_bytes(int num_m, int num_n, double Kt, int TM, int TN, double d_tile_bytes, int group, int along_n,
+                                   double cap_bytes, int conc) {
+    constexpr int NCH = 8;
+    const double a_slab = TM * (Kt / NCH) * 2, b_slab = TN * (Kt / NCH) * 2;
+    const int nA = num_m * NCH, nB = num_n * NCH, nD = num_m * num_n, n = nA + nB + nD;
+    std::vector<int> prev(n + 1, -1), next(n + 1, -1);   // intrusive LRU list over dense keys; n = sentinel (head.next = oldest)
+    std::vector<char> in(n, 0);
+    const int H = n;
+    prev[H] = next[H] = H;
+    double used = 0.0, miss_bytes = 0.0;
+    auto size_of = [&](int k) { return k < nA ? a_slab : (k < nA + nB ? b_slab : d_tile_bytes); };
+    auto unlink = [&](int k) { next[prev[k]] = next[k]; prev[next[k]] = prev[k]; };
+    auto push_new = [&](int k) { prev[k] = prev[H]; next[k] = H; next[prev[H]] = k; prev[H] = k; };
+    auto touch = [&](int k, bool count) {
+        if (in[k]) { unlink(k); push_new(k); return; }
+        if (count) miss_bytes += size_of(k);
+        in[k] = 1; used += size_of(k); push_new(k);
+        while (used > cap_bytes && next[H] != H) {
+            const int old = next[H];
+            unlink(old); in[old] = 0; used -= size_of(old);
+        }
+    };
+    Params q{};
+    q.num_m_blocks = num_m; q.num_n_blocks = num_n; q.group = group; q.group_along_n = along_n;
+    const int tiles = num_m * num_n;
+    std::vector<int> wm(conc), wn(conc);
+    for (int w0 = 0; w0 < tiles; w0 += conc) {
+        const int cnt = tiles - w0 < conc ? tiles - w0 : conc;
+        for (int i = 0; i < cnt; ++i) tile_coords(q, w0 + i, wm[i], wn[i]);
+        for (int c = 0; c < NCH; ++c)
+            for (int i = 0; i < cnt; ++i) { touch(wm[i] * NCH + c, true); touch(nA + wn[i] * NCH + c, true); }
+        for (int i = 0; i < cnt; ++i) touch(nA + nB + wm[i] * num_n + wn[i], false);
+    }
+    return miss_bytes;
+}
+
+static int g_raster_policy = -1;   // -1: read VLB200_RASTER_POLICY on first use; 0: L2 budget (choose_raster); 1: LRU model
+struct RasterPlan { int group, along_n; double model_bytes; };
+static RasterPlan plan_raster_model(int num_m, int num_n, double Kt, int TM, int TN, double d_tile_bytes, int conc) {
+    static const double cap_mb = [] { const char* e = getenv("VLB200_L2_MODEL_MB"); return e && atof(e) > 0.0 ? atof(e) : 60.0; }();
+    static std::map<std::tuple<int, int, long long, int, int, long long, int>, RasterPlan> cache;   // host threads: one (Python GIL)
+    const auto key = std::make_tuple(num_m, num_n, (long long)Kt, TM, TN, (long long)d_tile_bytes, conc);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    static const int cands[] = {1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 16, 20, 24, 32, 43, 50, 64, 86, 1 << 30};
+    RasterPlan best{1, 0, -1.0};
+    for (int along_n = 0; along_n < 2; ++along_n) {
+        const int lim = along_n ? num_n : num_m;
+        int last = -1;
+        for (int c : cands) {
+            const int g = c < lim ? c : lim;
+            if (g == last) break;
+            last = g;
+            const double b = lru_model_read_bytes(num_m, num_n, Kt, TM, TN, d_tile_bytes, g, along_n, cap_mb * 1024 * 1024, conc);
+            if (best.model_bytes < 0.0 || b < best.model_bytes * 0.999) best = RasterPlan{g, along_n, b};
+        }
+    }
+    cache[key] = best;
+    return best;
+}
+static int raster_policy() {
+    if (g_raster_policy < 0) {
+        const char* e = getenv("VLB200_RASTER_POLICY");
+        g_raster_policy = e && (strcmp(e, "model") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
+    }
+    return g_raster_policy;
+}
+// the raster of one pair-kernel launch under the active policy (d_tile_bytes: what a finished tile writes)
+static void choose_raster_pair(Params& p, double M, double N, double Kt, double d_tile_bytes) {
+    if (raster_policy() == 1) {
+        const RasterPlan r = plan_raster_model(p.num_m_blocks, p.num_n_blocks, Kt, PAIR_M, PAIR_N, d_tile_bytes, num_sms() / 2);
+        p.group = r.group; p.group_along_n = r.along_n;
+        return;
+    }
+    choose_raster(p, M, N, Kt, PAIR_M, PAIR_N);
+}
 static int g_gemm_mode = -1;  // -1: read VLB200_GEMM_2CTA on first use; 0: 1-CTA kernel; 1: 2-CTA pairs where the shape allows
 
 template <int BLOCK_N, int STAGES>
@@ -907,7 +993,11 @@ extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const v
     p.residual_f32 = residual_dtype == VLB200_F32;
     p.ldr = ldr;
     p.accumulate = accumulate;
-    vlb::gemm::choose_raster(p, (double)M, (double)N, (double)K + (dual ? K2 : 0), TM, TN);
+    if (use_pair)
+        vlb::gemm::choose_raster_pair(p, (double)M, (double)N, (double)K + (dual ? K2 : 0),
+                                      (double)PAIR_M * PAIR_N * (out_dtype == VLB200_F32 ? 4 : 2));
+    else
+        vlb::gemm::choose_raster(p, (double)M, (double)N, (double)K + (dual ? K2 : 0), TM, TN);
     cudaStream_t s = as_stream(stream);
     if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
     if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
@@ -963,12 +1053,49 @@ extern "C" int vlb200_gemm_swiglu_bf16(const void* A, int lda, const void* Wgu, 
     p.bias = nullptr; p.act = VLB200_ACT_NONE; p.residual = nullptr; p.residual_f32 = 0; p.ldr = 0; p.accumulate = 0;
     p.ff = ff; p.G = write_gu ? reinterpret_cast<__nv_bfloat16*>(gu) : nullptr; p.ldg = ld_gu;
     // a pair tile holds 256 rows of A and 128 gate + 128 up rows of B
-    vlb::gemm::choose_raster(p, (double)M, 2.0 * ff, (double)K, PAIR_M, PAIR_N);
+    vlb::gemm::choose_raster_pair(p, (double)M, 2.0 * ff, (double)K, (double)PAIR_M * PAIR_N * (write_gu ? 3 : 1));
     return launch_2cta<6, true, true, true>(ta, tb, ta, tb, p, as_stream(stream));
 }
 
 extern "C" int vlb200_set_gemm_raster_mb(double mb) {
     vlb::gemm::g_raster_mb = mb;  // <= 0: back to VLB200_RASTER_MB / the default on the next launch
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_set_gemm_raster_policy(int policy) {
+    vlb::gemm::g_raster_policy = policy == 1 ? 1 : (policy < 0 ? -1 : 0);   // < 0: back to VLB200_RASTER_POLICY / the default
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_gemm_plan_raster(int M, int N, int K, int out_bytes, int policy, int* group, int* along_n,
+                                       double* model_read_bytes) {
+    using namespace vlb::gemm;
+    VLB_REQUIRE(M > 0 && N > 0 && K > 0 && (out_bytes == 2 || out_bytes == 4) && group && along_n, "gemm_plan_raster: bad arguments");
+    Params p{};
+    p.num_m_blocks = (M + PAIR_M - 1) / PAIR_M;
+    p.num_n_blocks = (N + PAIR_N - 1) / PAIR_N;
+    const double d_tile = (double)PAIR_M * PAIR_N * out_bytes;
+    if (policy == 1) {
+        const RasterPlan r = plan_raster_model(p.num_m_blocks, p.num_n_blocks, (double)K, PAIR_M, PAIR_N, d_tile, 74);
+        p.group = r.group; p.group_along_n = r.along_n;
+    } else {
+        choose_raster(p, (double)M, (double)N, (double)K, PAIR_M, PAIR_N);
+    }
+    *group = p.group; *along_n = p.group_along_n;
+    if (model_read_bytes) {
+        static const double cap_mb = [] { const char* e = getenv("VLB200_L2_MODEL_MB"); return e && atof(e) > 0.0 ? atof(e) : 60.0; }();
+        *model_read_bytes = lru_model_read_bytes(p.num_m_blocks, p.num_n_blocks, (double)K, PAIR_M, PAIR_N, d_tile, p.group,
+                                                 p.group_along_n, cap_mb * 1024 * 1024, 74);
+    }
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_gemm_tile_coords(int num_m_blocks, int num_n_blocks, int group, int along_n, int tile, int* m_blk, int* n_blk) {
+    VLB_REQUIRE(num_m_blocks > 0 && num_n_blocks > 0 && group > 0 && tile >= 0 && tile < num_m_blocks * num_n_blocks && m_blk && n_blk,
+                "gemm_tile_coords: bad arguments");
+    vlb::gemm::Params p{};
+    p.num_m_blocks = num_m_blocks; p.num_n_blocks = num_n_blocks; p.group = group; p.group_along_n = along_n;
+    vlb::gemm::tile_coords(p, tile, *m_blk, *n_blk);   // the function the kernels call
     return VLB200_OK;
 }
 

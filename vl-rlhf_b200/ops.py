@@ -111,6 +111,12 @@ def set_gemm_raster_mb(mb: float):
     check(_L.vlb200_set_gemm_raster_mb(float(mb)))
 
 
+def set_gemm_raster_policy(policy: int):
+    """0: L2-budget raster (default); 1: the (orientation, group) an LRU model of L2 predicts to read least (tuning only,
+    include/vlb200.h: vlb200_set_gemm_raster_policy); < 0 restores VLB200_RASTER_POLICY / the default."""
+    check(_L.vlb200_set_gemm_raster_policy(int(policy)))
+
+
 def set_gemm_mode(mode: int):
     """1: CTA-pair (cta_group::2) 256x256 tiles where the shape allows; 0: single-CTA 128x256 tiles."""
     check(_L.vlb200_set_gemm_mode(int(mode)))
