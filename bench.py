@@ -259,11 +259,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         # with NCCL_DEBUG=VERSION|WARN (set on the GPU boxes) NCCL prints "NCCL version ..." on STDOUT, next to the one JSON
-        # line this script owes its caller: send NCCL's own log to stderr instead
-        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so a bare VERSION becomes WARN: same one line, on stderr)
+        # line this script owes its caller: send NCCL's own log to a per-process file instead (NCCL honours NCCL_DEBUG_FILE
+        # only above the VERSION level, so a bare VERSION becomes WARN)
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "vlb200_nccl.%h.%p.log"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import vlrlhf_b200  # noqa: F401
     from vlrlhf_b200 import config, engine, host, ops, synthetic
