@@ -46,10 +46,14 @@ def test_planner_matches_the_python_model_on_the_step_shapes():
         assert (g0, an0) == RM.current_policy(M, N, K), name                     # policy 0 == choose_raster's budget rule
         g1, an1, b1 = _plan(L, M, N, K, ob, 1)
         assert b1 <= b0 * 1.0001, (name, b0, b1)                                 # the model policy never predicts more traffic
-        fine = RM.dram_reads(M, N, K, g1, an1, 60, ob)                           # 64-wide k-blocks vs the planner's 8 chunks
-        assert abs(fine - b1) <= 0.08 * fine, (name, fine, b1)
+        fine = RM.dram_reads(M, N, K, g1, an1, 60, ob)                           # 64-wide k-blocks vs the planner's 32 chunks
+        assert abs(fine - b1) <= 0.05 * fine, (name, fine, b1)
         assert b1 >= 0.99 * (M + N) * K * 2                                       # never below the operands themselves
-    # long-K launches: square waves (8-9 blocks of the short dimension) instead of panel residency
+    # short-K launches keep the measured budget rule (its plans only lose on paper by capacity-dependent margins) ...
+    for name in ("fwd qkv", "fwd gate_up", "dgrad down", "dgrad o"):
+        M, N, K, ob, _ = RM.SHAPES[name]
+        assert _plan(L, M, N, K, ob, 1)[:2] == _plan(L, M, N, K, ob, 0)[:2], name
+    # ... long-K launches get square waves (8-9 blocks of the short dimension) instead of panel residency
     g, an, _ = _plan(L, *RM.SHAPES["dgrad gate_up"][:4], 1)
     assert (g, an) == (8, True)
     g, an, _ = _plan(L, *RM.SHAPES["wgrad gate_up"][:4], 1)
