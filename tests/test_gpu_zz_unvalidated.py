@@ -4,7 +4,8 @@ the validated parity tests.
 
 * BASELINE.json configs[1] at its full size (7B shapes, 4 pairs, text 1024) through size-independent properties;
 * packed rows (TrainConfig.pack_sequences) on the Qwen-VL and XC2 engines -- the kernels involved (vlb200_pack_merge_rows,
-  the var-len attention entry points, gather / scatter-add rows) are the ones the LLaVA packed tests already exercise on a GPU.
+  the var-len attention entry points, gather / scatter-add rows) are the ones the LLaVA packed tests already exercise on a GPU;
+* two <image> placeholders per sequence (the multi-slot path of vlb200_llava_merge_index / _merge_bwd).
 """
 import os
 
@@ -125,3 +126,36 @@ def test_xc2_packed_step_equals_padded_step(loss_type):
         return eng
 
     _packed_vs_padded(build, batch, loss_type)
+
+
+def test_two_images_per_sequence_on_the_gpu(pkg):
+    """f-2 (multi-image, uniform count): the merge-index kernel's multi-slot path against its plain-Python mirror, and the
+    engine's step on a two-image batch against the oracle."""
+    from oracle import restate as R
+    from tests import mock_ops
+    config, engine, host, ops = pkg
+    rcfg = R.TINY
+    batch = R.make_batch(rcfg, 2, 24, 8, 3, ddpo_like=True)
+    for side in ("chosen", "rejected"):
+        batch[f"{side}_input_ids"][:, 4] = rcfg.image_token_index
+    batch["img_input_dict"] = {"pixel_values": torch.randn(4, 3, rcfg.image_size, rcfg.image_size,
+                                                          generator=torch.Generator().manual_seed(3))}
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    args = (rcfg.n_patches, 2, 2, rcfg.image_token_index, rcfg.pad_token_id)
+    m = ops.llava_merge_index(ids.cuda(), am.cuda(), lb.cuda(), *args)
+    want = mock_ops.llava_merge_index(ids, am, lb, *args)
+    assert int(m.status.item()) == 0 and m.S == want.S == 24 + 2 * (rcfg.n_patches - 1)
+    for k in ("src_map", "pos", "seqlens", "img_pos", "row_of_text", "target", "labels", "mask"):
+        assert torch.equal(getattr(m, k).cpu().reshape(-1).long(), getattr(want, k).reshape(-1).long()), k
+    for pack in (False, True):
+        eng = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3, pack_sequences=pack), with_optimizer=False)
+        eng.init_synthetic(0)
+        got = eng.train_step(batch, train=True)
+        wp, wr = R.make_policy_and_ref(rcfg, 0)
+        with torch.no_grad():
+            loss, metrics, _ = R.get_batch_loss_metrics(rcfg, wp, wr, batch)
+        assert abs(got["loss"] - float(loss)) < 2e-3
+        for k in ("rewards/chosen", "rewards/rejected", "logps/chosen", "logps/rejected"):
+            assert abs(got[k] - float(metrics[k])) < 2e-3 * max(1.0, abs(float(metrics[k]))), k
+        assert torch.isfinite(eng.grads.float()).all()

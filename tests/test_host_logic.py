@@ -741,3 +741,46 @@ def test_pack_sequences_launcher_switch(cpu_pkg, monkeypatch):
     assert not engine.LlavaDPOEngine(config.TINY, config.TrainConfig(), device="cpu", with_optimizer=False).tc.pack_sequences
     monkeypatch.delenv("VLB200_PACK_SEQUENCES")
     assert not engine.LlavaDPOEngine(config.TINY, None, device="cpu", with_optimizer=False).tc.pack_sequences
+
+
+def _two_image_batch(rcfg, seed=3, n_pairs=2, L=24, pl=8):
+    """every sequence holds TWO <image> placeholders (the second one inside the shared prompt); pixel_values pair-major"""
+    b = R.make_batch(rcfg, n_pairs, L, pl, seed, ddpo_like=True)
+    for side in ("chosen", "rejected"):
+        b[f"{side}_input_ids"][:, 4] = rcfg.image_token_index
+    g = torch.Generator().manual_seed(seed)
+    b["img_input_dict"] = {"pixel_values": torch.randn(n_pairs * 2, 3, rcfg.image_size, rcfg.image_size, generator=g)}
+    return b
+
+
+@pytest.mark.parametrize("pack,loss_type", [(False, "sigmoid"), (True, "ddpo")])
+def test_two_images_per_sequence_match_the_oracle(cpu_pkg, pack, loss_type):
+    """f-2 (multi-image, uniform count): k <image> placeholders per sequence, pixel_values [B*k, ...] -- the merge places the k
+    feature blocks (Llava/__init__.py:44-47,60-94), chosen and rejected share the pair's images; against the oracle's
+    restatement of the reference merge (itself checked on the live reference, tests/test_oracle_vs_reference.py)."""
+    config, engine, host, ops = cpu_pkg
+    batch = _two_image_batch(R.TINY)
+    eng = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(loss_type=loss_type, learning_rate=1e-3, pack_sequences=pack),
+                                device="cpu", with_optimizer=False)
+    eng.init_synthetic(0)
+    assert eng.images_per_sequence(batch) == 2
+    got = eng.train_step(batch, train=True)
+    assert eng._saved["m"].S == 24 + 2 * (R.TINY.n_patches - 1) and eng._saved["m"].imgs_per_seq == 2
+    wp, wr = R.make_policy_and_ref(R.TINY, 0)
+    with torch.no_grad():
+        loss, metrics, _ = R.get_batch_loss_metrics(R.TINY, wp, wr, batch, loss_type=loss_type)
+    assert abs(got["loss"] - float(loss)) < 2e-3
+    for k in ("rewards/chosen", "rewards/rejected", "logps/chosen", "logps/rejected"):
+        assert abs(got[k] - float(metrics[k])) < 2e-3 * max(1.0, abs(float(metrics[k]))), k
+    grads = {k: v.float() for k, v in eng.hf_state("grad").items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in wp.items() if not k.startswith("vision_tower.")}
+    w = dict(wp)
+    w.update(leaves)
+    loss, _, _ = R.get_batch_loss_metrics(R.TINY, w, wr, batch, loss_type=loss_type)
+    loss.backward()
+    for k, leaf in leaves.items():
+        rel = (grads[k].reshape(leaf.shape) - leaf.grad).norm().item() / max(leaf.grad.norm().item(), 1e-12)
+        assert rel < 5e-2, f"{k}: rel {rel}"
+    bad = dict(batch, img_input_dict={"pixel_values": batch["img_input_dict"]["pixel_values"][:3]})
+    with pytest.raises(ValueError):
+        eng.train_step(bad, train=False)            # 3 images do not split over 2 pairs

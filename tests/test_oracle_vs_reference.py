@@ -213,3 +213,27 @@ def test_committed_fixtures_regenerate_from_the_reference(minter, tmp_path, monk
                 np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6, err_msg=f"{f}:{k}")
             else:
                 assert np.array_equal(a, b), (f, k)
+
+
+def test_two_images_per_sequence_reference_equals_oracle():
+    """f-2 (multi-image): the reference's LlavaForRL with two <image> placeholders per sequence (pixel_values [2*B*2, ...] after
+    concatenated_inputs' [v, v] duplication) against the oracle's restated merge: merged labels / image map bit-equal,
+    log-probs equal."""
+    from oracle import make_fixtures as MF
+    cfg, seed = R.TINY, 3
+    batch = R.make_batch(cfg, 2, 24, 8, seed, ddpo_like=True)
+    for side in ("chosen", "rejected"):
+        batch[f"{side}_input_ids"][:, 4] = cfg.image_token_index
+    batch["img_input_dict"] = {"pixel_values": torch.randn(4, 3, cfg.image_size, cfg.image_size,
+                                                          generator=torch.Generator().manual_seed(seed))}
+    model = MF.build_reference_model(cfg, MF.streamed_weights(cfg, seed, "policy"))
+    want, out = MF.reference_concatenated_forward(model, cfg, batch, "sigmoid")
+    assert out.labels.shape[1] == 24 + 2 * (cfg.n_patches - 1)
+    w, _ = R.make_policy_and_ref(cfg, seed)
+    cb = R.concatenated_inputs(batch, -100, 0)
+    with torch.no_grad():
+        pc, pr, _, _ = R.concatenated_forward(cfg, w, batch)
+        _, labels, imap = R.model_forward(cfg, w, cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
+                                          cb["concatenated_labels"], **cb["concatenated_img_input_dict"])
+    assert torch.equal(labels, out.labels) and torch.equal(imap, out.image_position_map)
+    np.testing.assert_allclose(torch.cat([pc, pr]).numpy(), want.numpy(), rtol=2e-5, atol=2e-4)

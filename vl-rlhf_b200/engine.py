@@ -621,9 +621,11 @@ class LlavaDPOEngine:
     # ------------------------------------------------------------------ the step
     def prepare_inputs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
                        pixel_values: torch.Tensor, ddpo_weight: Optional[torch.Tensor] = None,
-                       image_sizes: Optional[torch.Tensor] = None):
+                       image_sizes: Optional[torch.Tensor] = None, imgs_per_seq: int = 1):
         """Host -> device staging of one concatenated batch (the H2D copies of the step).  Inputs may be CPU
-        (pinned or not) or CUDA tensors.  pixel_values may be [B,...] or the reference's duplicated [2B,...].
+        (pinned or not) or CUDA tensors.  pixel_values may be [B,...] or the reference's duplicated [2B,...]; with
+        `imgs_per_seq` = k > 1 (LLaVA-1.5: every sequence holds k <image> placeholders, Llava/__init__.py:44-47) it is
+        [B*k,...] pair-major (or the duplicated [2*B*k,...]).
         LLaVA-Next: pixel_values is the processor's [B, max_crops, 3, H, W] (or the flat [sum crops, 3, H, W]) and
         `image_sizes` [B, 2] is required; the returned tuple then carries a 6th element, the anyres plan."""
         dev = self.device
@@ -652,8 +654,11 @@ class LlavaDPOEngine:
             if pixel_values.shape[0] != sum(plan.crops):
                 raise ValueError(f"{pixel_values.shape[0]} crops given, image_sizes imply {sum(plan.crops)}")
             plan.to(dev)
-        elif pixel_values.shape[0] == n_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
-            pixel_values = pixel_values[: n_seq // 2]
+        else:
+            if pixel_values.shape[0] == n_seq * imgs_per_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
+                pixel_values = pixel_values[: (n_seq // 2) * imgs_per_seq]
+            if imgs_per_seq != 1 and pixel_values.shape[0] != (n_seq // 2) * imgs_per_seq:
+                raise ValueError(f"{pixel_values.shape[0]} images for {n_seq // 2} pairs of {imgs_per_seq} images each")
         ids = input_ids.to(dev, non_blocking=True).contiguous()
         am = attention_mask.to(dev, non_blocking=True).contiguous()
         lb = labels.to(dev, non_blocking=True).contiguous()
@@ -664,7 +669,8 @@ class LlavaDPOEngine:
         return (ids, am, lb, px, wt) if plan is None else (ids, am, lb, px, wt, plan)
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
-                      feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None, seq_lens=None):
+                      feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None, seq_lens=None,
+                      imgs_per_seq: int = 1):
         """`seq_lens` (host ints, merged length of every sequence; host.merged_seq_lens) is only read with
         TrainConfig.pack_sequences; without it the lengths are read back from the device (one synchronisation)."""
         cfg = self.cfg
@@ -672,13 +678,16 @@ class LlavaDPOEngine:
             raise ValueError("the anyres plan from prepare_inputs is required for (and only for) LLaVA-Next")
         self._anyres = anyres
         if m is None:
-            imgs_per_seq = 1
             if anyres is not None:
+                if imgs_per_seq != 1:
+                    raise ValueError("LLaVA-Next: one image per sequence (several anyres images per sequence are not implemented)")
                 m = ops.llavanext_merge_index(ids, am, lb, anyres.feat_off, anyres.total_feats, anyres.merged_len,
                                               len(anyres.crops), imgs_per_seq, cfg.image_token_index, cfg.ignore_index)
             else:
-                m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0], imgs_per_seq, cfg.image_token_index,
-                                          cfg.pad_token_id, cfg.ignore_index)
+                if px.shape[0] % imgs_per_seq:
+                    raise ValueError(f"{px.shape[0]} images do not split into groups of {imgs_per_seq}")
+                m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0] // imgs_per_seq, imgs_per_seq,
+                                          cfg.image_token_index, cfg.pad_token_id, cfg.ignore_index)
             if self.tc.pack_sequences:   # drop the padding rows: every kernel below runs over sum(len) rows
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
@@ -690,21 +699,23 @@ class LlavaDPOEngine:
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
     def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True,
-             ref_logps: Optional[torch.Tensor] = None, seq_lens=None) -> StepOutput:
+             ref_logps: Optional[torch.Tensor] = None, seq_lens=None, imgs_per_seq: int = 1) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
         backward + gradient all-reduce + AdamW.  `ref_logps` ([2B] fp32, chosen then rejected) replaces the reference
         pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
         the collator's `_logps` keys, base/collator.py:62-64)."""
         tc = self.tc
         if ref_logps is not None:
-            pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, seq_lens=seq_lens)
+            pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, seq_lens=seq_lens,
+                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
             ref = ref_logps.to(self.device, torch.float32).reshape(-1).contiguous()
             if ref.numel() != pol.numel():
                 raise ValueError(f"ref_logps holds {ref.numel()} values, the batch has {pol.numel()} sequences")
         else:
             # reference pass first: it reads none of the policy weights, so the previous step's deferred optimizer
             # (side stream) overlaps it; the policy pass below waits for `opt_done`
-            ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, seq_lens=seq_lens)
+            ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, seq_lens=seq_lens,
+                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
             pol, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    1.0, want_grad=train)
@@ -749,8 +760,11 @@ class LlavaDPOEngine:
         if "reference_chosen_logps" in batch and "reference_rejected_logps" in batch:  # precompute_ref_log_probs
             ref_logps = torch.cat([torch.as_tensor(batch["reference_chosen_logps"], dtype=torch.float32).reshape(-1),
                                    torch.as_tensor(batch["reference_rejected_logps"], dtype=torch.float32).reshape(-1)])
-        seq_lens = self.host_seq_lens(ids, am, sizes) if tc.pack_sequences else None
-        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes), train=train, ref_logps=ref_logps, seq_lens=seq_lens)
+        k = self.images_per_sequence(batch)
+        kw = {"imgs_per_seq": k} if k != 1 else {}
+        seq_lens = self.host_seq_lens(ids, am, sizes, **kw) if tc.pack_sequences else None
+        out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes, **kw), train=train, ref_logps=ref_logps,
+                        seq_lens=seq_lens, **kw)
         n = out.policy_logps.numel() // 2
         if self._opt_pending:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
             torch.cuda.current_stream(self.device).wait_event(self.norm_done)
@@ -763,6 +777,18 @@ class LlavaDPOEngine:
                 "logps/chosen": float(packed[6]), "logps/rejected": float(packed[7]),
                 "logits/chosen": float(packed[9]), "logits/rejected": float(packed[10]),
                 "grad_norm": float(packed[8]) ** 0.5 / world}
+
+    def images_per_sequence(self, batch: Dict) -> int:
+        """k for a collated batch whose img_input_dict.pixel_values holds k images per pair, pair-major ([B*k, 3, H, W]; the DPO
+        collator emits k = 1, models/Llava/__init__.py:435-443).  LLaVA-1.5 family only: the other families' pixel layouts carry
+        their own structure (anyres crops, file names in the token stream)."""
+        px = batch["img_input_dict"]["pixel_values"]
+        n_pairs = batch["chosen_input_ids"].shape[0]
+        if self.cfg.family != "llava" or px.dim() != 4 or px.shape[0] == n_pairs:
+            return 1
+        if px.shape[0] % n_pairs:
+            raise ValueError(f"{px.shape[0]} images do not split over {n_pairs} pairs")
+        return px.shape[0] // n_pairs
 
     def compute_reference_log_probs(self, batch: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
         """trl 0.8.1 DPOTrainer.compute_reference_log_probs (the producer half of precompute_ref_log_probs, base/trainer.py:61,96):
@@ -777,19 +803,21 @@ class LlavaDPOEngine:
                                                   tc.loss_type)
         sizes = batch["img_input_dict"].get("image_sizes")
         wt = self.ddpo_weights(ids, am, lb, sizes) if tc.loss_type == "ddpo" else None
-        seq_lens = self.host_seq_lens(ids, am, sizes) if tc.pack_sequences else None
-        inputs = self.prepare_inputs(ids, am, lb, batch["img_input_dict"]["pixel_values"], wt, sizes)
-        logps, _, _ = self.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens)
+        k = self.images_per_sequence(batch)
+        kw = {"imgs_per_seq": k} if k != 1 else {}
+        seq_lens = self.host_seq_lens(ids, am, sizes, **kw) if tc.pack_sequences else None
+        inputs = self.prepare_inputs(ids, am, lb, batch["img_input_dict"]["pixel_values"], wt, sizes, **kw)
+        logps, _, _ = self.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens, **kw)
         logps = logps.float().cpu()
         n = logps.numel() // 2
         return logps[:n], logps[n:]
 
-    def host_seq_lens(self, ids, am, image_sizes=None) -> List[int]:
+    def host_seq_lens(self, ids, am, image_sizes=None, imgs_per_seq: int = 1) -> List[int]:
         """Merged length of every sequence of one concatenated host batch (packed steps: the rows that survive)."""
         from . import host
         cfg = self.cfg
         if cfg.family != "llava_next":
-            return host.merged_seq_lens(ids, am, cfg.image_token_index, cfg.n_patches)
+            return host.merged_seq_lens(ids, am, cfg.image_token_index, cfg.n_patches * imgs_per_seq)
         n_seq = ids.shape[0]
         if image_sizes.shape[0] == n_seq:
             image_sizes = image_sizes[: n_seq // 2]

@@ -195,15 +195,16 @@ class _EngineLogps(torch.autograd.Function):
     backward pass and leaves the gradients in the parameters' .grad views."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, inputs, seq_lens):
-        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens)
+    def forward(ctx, anchor, engine, inputs, seq_lens, imgs_per_seq=1):
+        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens,
+                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
         ctx.engine = engine
         return logps
 
     @staticmethod
     def backward(ctx, g):
         ctx.engine._backward(g.float().contiguous())
-        return torch.zeros(1, device=g.device), None, None, None
+        return torch.zeros(1, device=g.device), None, None, None, None
 
 
 def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, torch.LongTensor]]
@@ -226,16 +227,18 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     wt = None
     if self.loss_type == "ddpo":
         wt = eng.ddpo_weights(ids, am, lb, sizes)
-    inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes)
+    k = eng.images_per_sequence(batch) if "img_input_dict" in batch else 1   # several <image> placeholders per sequence
+    kw = {"imgs_per_seq": k} if k != 1 else {}
+    inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes, **kw)
     # TrainConfig.pack_sequences: the merged lengths come from the host batch, so the step stays free of device read-backs
-    seq_lens = eng.host_seq_lens(ids, am, sizes) if eng.tc.pack_sequences else None
+    seq_lens = eng.host_seq_lens(ids, am, sizes, **kw) if eng.tc.pack_sequences else None
     n = batch["chosen_labels"].shape[0]
     if which == "policy" and torch.is_grad_enabled():
         anchor = torch.zeros(1, device=eng.device, requires_grad=True)
-        logps = _EngineLogps.apply(anchor, eng, inputs, seq_lens)
+        logps = _EngineLogps.apply(anchor, eng, inputs, seq_lens, k)
     else:
         with torch.no_grad():
-            logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens)
+            logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens, **kw)
     return logps[:n], logps[n:], None, None
 
 
