@@ -234,7 +234,7 @@ int vlb200_pack_merge_rows(const int* src_map, const int* position_ids, const in
 /* ---- LLaVA-Next text/image merge -- models/LlavaNext/__init__.py:38-171 (_merge_input_ids_with_image_features)
  * Differences from the LLaVA-1.5 merge above: image k contributes feat_off[k+1]-feat_off[k] PACKED feature rows
  * (anyres "spatial_unpad" + image_newline, modeling_llava_next.py pack_image_features; the row gather that builds
- * them is vlb200_gather_rows over the index vl-rlhf_b200/host.py:anyres_pack_index computes), tokens whose
+ * them is vlb200_gather_rows over the index vlrlhf_b200/host.py:anyres_pack_index computes), tokens whose
  * attention_mask is 0 are never written, merged_len is the longest valid merged sequence (host-computed:
  * (mask==1).sum() - n_image_tokens + sum(feature_lens), :83-87) and pad-token embeddings are kept.  Right padding
  * only (status 3 otherwise).  img_rows[rep*total_feats + k] = flat merged row of packed feature row k in the rep-th
@@ -263,25 +263,18 @@ int vlb200_qwen_merge_index(const int64_t* input_ids, const int64_t* attention_m
  * (modeling_llama.py:199-290).  q/k/v/out rows are tokens (row = b*S + t), head h at column h*head_dim.
  * causal + key-padding via seqlens[B] (attended prefix length; NULL = S).  lse/delta: [B,H,S] f32.
  * head_dim 64 or 128; H % KVH == 0 (GQA).                                                          */
-int vlb200_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
-                    int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH, int head_dim, int causal,
-                    float scale, void* stream);
-/* tcgen05/TMEM/TMA forward (same contract as vlb200_attn_fwd; S and O accumulate in TMEM, K/V tiles arrive by TMA) */
+/* tcgen05/TMEM/TMA forward (S and O accumulate in TMEM, K/V tiles arrive by TMA) */
 int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                        int64_t ldo, float* lse, const int* seqlens, int B, int S, int H, int KVH, int head_dim, int causal,
                        float scale, void* stream);
 /* delta[b,h,t] = sum_d dout[t,h,d] * out[t,h,d]  (softmax-backward row statistic) */
 int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
                       int head_dim, void* stream);
-/* tcgen05/TMEM/TMA backward (same contract as vlb200_attn_bwd): pass 1 dK,dV (key tile stationary), pass 2 dQ */
+/* tcgen05/TMEM/TMA backward: pass 1 dK,dV (key tile stationary), pass 2 dQ */
 int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
                        int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
                        void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,
                        int head_dim, int causal, float scale, void* stream);
-int vlb200_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
-                    int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
-                    void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, int B, int S, int H, int KVH,
-                    int head_dim, int causal, float scale, void* stream);
 
 /* Ragged ("packed") rows -- SURVEY.md f-2, the var-len FlashAttention form: sequence b occupies rows
  * [row_starts[b], row_starts[b] + seqlens[b]) of q/k/v/out (total_rows rows in all) instead of [b*S, (b+1)*S), so the
@@ -317,7 +310,7 @@ int vlb200_cast_bf16_to_f32(const void* src, float* dst, uint64_t n, void* strea
  * stored float32 -> (x-mean)/std in float32 -> CHW.  image: device uint8 [in_h, in_w, 3] RGB (the decoded file).
  * coef_h/bounds_h ([new_w, ksize_h] int32, [new_w, 2] int32 = first tap, tap count) and coef_v/bounds_v
  * ([new_h, ksize_v], [new_h, 2]) are Pillow's 22-bit fixed-point resampling tables (Resample.c precompute_coeffs +
- * normalize_coeffs_8bpc), device-resident, built by vl-rlhf_b200/preprocess.py.  (top,left,crop_h,crop_w) is the output
+ * normalize_coeffs_8bpc), device-resident, built by vlrlhf_b200/preprocess.py.  (top,left,crop_h,crop_w) is the output
  * window in resized-image coordinates: the center crop for CLIP, one 336x336 cell of the zero-padded anyres canvas for
  * LLaVA-Next (LlavaNextImageProcessor get_image_patches: top/left may be negative or reach past the resized image; pixels
  * outside it are the canvas' uint8 zeros).  Only input rows [row0, row0+rows) feed the window (rows may be 0).  workspace holds the

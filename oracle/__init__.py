@@ -3,7 +3,7 @@
 CPU restatement of the reference hot path (TideDra/VL-RLHF
 `VLDPOTrainer.concatenated_forward -> get_batch_logps -> dpo_loss`, plus the
 LLaVA-1.5 forward it drives).  Nothing in the product package
-(`vl-rlhf_b200/`) may import this package: only `tests/`,
+(`vlrlhf_b200/`) may import this package: only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
 legs do, and there only as the checker.
 

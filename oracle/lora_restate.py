@@ -11,7 +11,7 @@ Follows:
   * peft lora.Linear.forward (not on disk): base(x) + lora_B(lora_A(x)) * alpha / r      (restate.lora_linear)
   * everything else: oracle/restate.py (LlavaForRL / LlavaNextForRL forward, get_batch_logps, dpo_loss).
 Adapters sit on the decoder linears only (peft's suffix match would also wrap the CLIP tower's q/k/v_proj; see
-vl-rlhf_b200/config.py).  Pinned against the reference's LlavaForRL / LlavaNextForRL run here with the adapters applied by
+vlrlhf_b200/config.py).  Pinned against the reference's LlavaForRL / LlavaNextForRL run here with the adapters applied by
 hand (tests/golden/g11_*.npz, make_fixtures.py --lora).
 """
 from __future__ import annotations

@@ -17,7 +17,7 @@ def pytest_configure(config):
 def pytest_sessionstart(session):
     """The host logic calls native host routines of libvlb200 (DDPO diff): make sure the in-tree library exists
     (nvcc cross-compiles here; on the GPU box the prebuilt .so travelled with the snapshot)."""
-    if not os.path.exists(os.path.join(ROOT, "vl-rlhf_b200", "libvlb200.so")):
+    if not os.path.exists(os.path.join(ROOT, "vlrlhf_b200", "libvlb200.so")):
         import __graft_entry__ as g
         g.build()
 

@@ -76,18 +76,18 @@ def main():
     lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
     seqlens = torch.tensor([1599, 1400, 1599, 1500, 1599, 1300, 1450, 1599], dtype=torch.int32, device=dev)
     sc = 1 / math.sqrt(dh)
-    ms = timeit(lambda: ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, seqlens, B, S, H, H, dh, True, sc))
+    ms = timeit(lambda: ops.attn_fwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, seqlens, B, S, H, H, dh, True, sc))
     fl = sum(2.0 * 2 * int(l) * int(l) / 2 * dh * H for l in seqlens.tolist())
     print(f"attn fwd  causal B=8 S=1599 H=32 dh=128  {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s (causal-half flops)", flush=True)
     dout = torch.randn(T, d, device=dev).to(bf)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    ms = timeit(lambda: ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, dout, lse, delta, dqkv[:, :d],
+    ms = timeit(lambda: ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, dout, lse, delta, dqkv[:, :d],
                                      dqkv[:, d:2 * d], dqkv[:, 2 * d:], seqlens, B, S, H, H, dh, True, sc))
     print(f"attn bwd  (2.5x fwd flops)               {ms:8.3f} ms  {2.5 * fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
     vq = torch.randn(4 * 577, 3072, device=dev).to(bf)
     vo = torch.empty(4 * 577, 1024, dtype=bf, device=dev)
-    ms = timeit(lambda: ops.attn_fwd(vq[:, :1024], vq[:, 1024:2048], vq[:, 2048:], vo, None, None, 4, 577, 16, 16, 64, False, 0.125))
+    ms = timeit(lambda: ops.attn_fwd_tc(vq[:, :1024], vq[:, 1024:2048], vq[:, 2048:], vo, None, None, 4, 577, 16, 16, 64, False, 0.125))
     print(f"attn fwd  vit B=4 S=577 H=16 dh=64        {ms:8.3f} ms  {4 * 16 * 4.0 * 577 * 577 * 64 / ms / 1e9:7.1f} TFLOP/s", flush=True)
     del qkv, dqkv, dout
 

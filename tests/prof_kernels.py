@@ -37,19 +37,6 @@ elif which == "lora":          # LoRA linear in one launch (second operand pair)
     for _ in range(4):
         ops.gemm(x, w, a2=ts[:, :r], b2=Bm, out=out[:, :ff])
         ops.gemm(dy, ts[:, :r], a_kmajor=False, b_kmajor=False, out=dB)
-elif which == "attn":
-    qkv = torch.randn(T, 3 * d, device=dev).to(bf)
-    out = torch.empty(T, d, dtype=bf, device=dev)
-    lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
-    sl = torch.tensor([1599, 1400, 1599, 1500, 1599, 1300, 1450, 1599], dtype=torch.int32, device=dev)
-    sc = 1 / math.sqrt(dh)
-    dout = torch.randn(T, d, device=dev).to(bf)
-    dqkv = torch.empty_like(qkv)
-    delta = torch.empty_like(lse)
-    for _ in range(3):
-        ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, lse, sl, B, S, H, H, dh, True, sc)
-        ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], out, dout, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
-                     dqkv[:, 2 * d:], sl, B, S, H, H, dh, True, sc)
 elif which == "attn_tc":
     qkv = torch.randn(T, 3 * d, device=dev).to(bf)
     out = torch.empty(T, d, dtype=bf, device=dev)

@@ -44,7 +44,7 @@ def test_product_package_never_imports_the_oracle():
     import os
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    pkg = os.path.join(root, "vl-rlhf_b200")
+    pkg = os.path.join(root, "vlrlhf_b200")
     offenders = []
     for dirpath, _, files in os.walk(pkg):
         for f in files:

@@ -258,10 +258,8 @@ def ref_attention(q, k, v, causal, seqlens, scale):
     (3, 130, 4, 2, 128, True, [130, 64, 1]),  # GQA, ragged
     (1, 64, 2, 2, 64, True, None),
 ])
-@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
-def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens, impl):
-    fwd = ops.attn_fwd if impl == "mma_sync" else ops.attn_fwd_tc
-    bwd = ops.attn_bwd if impl == "mma_sync" else ops.attn_bwd_tc
+def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
+    fwd, bwd = ops.attn_fwd_tc, ops.attn_bwd_tc
     torch.manual_seed(S + H)
     dev = "cuda"
     ld = (H + 2 * KV) * dh

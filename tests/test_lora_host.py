@@ -2,7 +2,7 @@
 
 * oracle/lora_restate.py against the fixtures minted from the reference's LlavaForRL / LlavaNextForRL with hand-applied
   peft-style adapters (tests/golden/g11_*.npz, oracle/make_fixtures.py --lora);
-* the engine's orchestration (vl-rlhf_b200/engine_lora.py over tests/mock_ops.py) against the fixtures and the oracle's
+* the engine's orchestration (vlrlhf_b200/engine_lora.py over tests/mock_ops.py) against the fixtures and the oracle's
   autograd: log-probs, DDPO, all loss types, adapter gradients, activation checkpointing, optimizer.
 """
 import importlib

@@ -1,4 +1,4 @@
-"""Plugin side of the LoRA-trained families (vl-rlhf_b200/plugin_lora.py) over the mock ops -- CPU tests: checkpoints in,
+"""Plugin side of the LoRA-trained families (vlrlhf_b200/plugin_lora.py) over the mock ops -- CPU tests: checkpoints in,
 PEFT-format adapters out, merge (merge_peft_model.py), LoraConfig validation, launcher flags, trainer-level calls."""
 import importlib
 import json

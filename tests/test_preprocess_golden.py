@@ -3,7 +3,7 @@
 * the oracle (oracle/image_restate.py: Pillow's 8-bit bicubic resampler + transformers' crop/rescale/normalize
   restated in numpy) against the committed fixture minted from Pillow + transformers' PIL-backend CLIP processor
   (tests/golden/g7_clip_preprocess.npz) and, when Pillow is importable, against Pillow itself on fresh sizes;
-* the product's host tables (vl-rlhf_b200/preprocess.py, vectorised) == the oracle's loop restatement, bit-exact.
+* the product's host tables (vlrlhf_b200/preprocess.py, vectorised) == the oracle's loop restatement, bit-exact.
 The CUDA kernels themselves are checked in tests/test_gpu_preprocess.py.
 """
 import hashlib

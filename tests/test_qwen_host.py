@@ -2,7 +2,7 @@
 
 * oracle/qwen_restate.py against the fixtures minted from the reference's vendored QWenLMHeadModel + VisionTransformer
   (tests/golden/g9_qwen_*.npz: policy = base + adapters, reference = adapters off);
-* the engine's orchestration (vl-rlhf_b200/engine_qwen.py over tests/mock_ops.py) against the fixtures and the oracle's
+* the engine's orchestration (vlrlhf_b200/engine_qwen.py over tests/mock_ops.py) against the fixtures and the oracle's
   autograd: log-probs, DDPO, adapter gradients, activation checkpointing, optimizer, metrics.
 """
 import importlib

@@ -1,7 +1,7 @@
 """InternLM-XComposer2-VL + PLoRA/LoRA variant (BASELINE.json configs[4]) -- CPU tests.
 
 * oracle/xc2_restate.py against the fixtures minted from the reference's InternLMXC2ForRL (tests/golden/g10_xc2_*.npz);
-* the engine's orchestration (vl-rlhf_b200/engine_xc2.py over tests/mock_ops.py) against the fixtures and the oracle's
+* the engine's orchestration (vlrlhf_b200/engine_xc2.py over tests/mock_ops.py) against the fixtures and the oracle's
   autograd: log-probs, DDPO, KTO-pair, adapter gradients, activation checkpointing, optimizer.
 """
 import importlib

@@ -73,8 +73,6 @@ SIGNATURES = {
     "vlb200_qwen_merge_index": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
-    "vlb200_attn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vlb200_attn_fwd_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vlb200_attn_delta": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -92,9 +90,6 @@ SIGNATURES = {
                                           c_void_p]),
     "vlb200_pack_merge_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
-    "vlb200_attn_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vlb200_sumsq_bf16": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_int, c_void_p]),
     "vlb200_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_float, c_float, c_float,
                              c_float, c_float, c_int, c_float, c_void_p, c_float, c_void_p]),

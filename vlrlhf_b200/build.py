@@ -1,4 +1,4 @@
-"""Build libvlb200.so (sm_100a only) in-tree with nvcc.  `python vl-rlhf_b200/build.py [--force]`.
+"""Build libvlb200.so (sm_100a only) in-tree with nvcc.  `python vlrlhf_b200/build.py [--force]`.
 
 The .so stays in-tree (git-ignored, NOT gpurun-ignored) so it travels to the GPU box.
 """

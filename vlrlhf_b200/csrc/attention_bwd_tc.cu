@@ -433,16 +433,64 @@ static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMa
     }
     const int grid = std::min(p.n_work, num_sms());
     kern<<<grid, NTHREADS, smem_bytes, s>>>(x1, x2, y1, y2, p);
-    count_launch();
+    vlb::count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
+}
+
+// ------------------------------------------------------------------ backward: delta = rowsum(dO * O)
+// row_starts (or null): first row of each sequence when the rows are ragged / packed; delta stays [B, H, S]
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
+                                  long long lddo, float* __restrict__ delta, const int* __restrict__ row_starts, size_t rows,
+                                  int B, int S, int H, int DH) {
+    const int warps_per_block = blockDim.x >> 5;
+    const size_t total = rows * H;
+    const int lane = threadIdx.x & 31;
+    for (size_t w = blockIdx.x * (size_t)warps_per_block + (threadIdx.x >> 5); w < total; w += (size_t)gridDim.x * warps_per_block) {
+        const int h = (int)(w % H);
+        const size_t row = w / H;  // b*S + t, or row_starts[b] + t
+        const __nv_bfloat16* op = o + row * ldo + (size_t)h * DH;
+        const __nv_bfloat16* dp = dout + row * lddo + (size_t)h * DH;
+        float acc = 0.f;
+        for (int c = lane * 2; c < DH; c += 64) {
+            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + c));
+            const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + c));
+            acc += a.x * d.x + a.y * d.y;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            size_t b = row / S, t = row % S;
+            if (row_starts != nullptr) {
+                b = 0;
+                while (b + 1 < (size_t)B && (size_t)row_starts[b + 1] <= row) ++b;
+                t = row - (size_t)row_starts[b];
+            }
+            if (t < (size_t)S) delta[(b * H + h) * S + t] = acc;
+        }
+    }
 }
 
 }  // namespace attn_bwd_tc
 }  // namespace vlb
 
 extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
-                                        const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream);
+                                        const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream) {
+    VLB_REQUIRE(out && dout && delta, "attn_delta: null pointer");
+    VLB_REQUIRE(row_starts == nullptr || total_rows > 0, "attn_delta: row_starts needs total_rows");
+    const size_t rows = row_starts ? (size_t)total_rows : (size_t)B * S;
+    const size_t nw = rows * H;
+    const int blocks = (int)std::min<size_t>((nw + 7) / 8, (size_t)vlb::num_sms() * 16);
+    vlb::attn_bwd_tc::attn_delta_kernel<<<blocks, 256, 0, vlb::as_stream(stream)>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo,
+                                                                  delta, row_starts, rows, B, S, H, head_dim);
+    vlb::count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B, int S, int H,
+                                 int head_dim, void* stream) {
+    return vlb200_attn_delta_varlen(out, ldo, dout, lddo, delta, nullptr, 0, B, S, H, head_dim, stream);
+}
 
 extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                          const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,

@@ -12,7 +12,7 @@
 //   * get_matching_blocks: LIFO work list, sort, merge adjacent blocks, (la, lb, 0) sentinel.
 // On top: keep blocks >= min_match_size (+ sentinel), the gaps between kept blocks that are non-empty on BOTH
 // sides are the modified spans (diff_lib.py:136-163), and the spans are mapped from the merged shifted label layout
-// back to text-level logits rows (row j-1 predicts text token j) as vl-rlhf_b200/host.py:ddpo_row_weights does.
+// back to text-level logits rows (row j-1 predicts text token j) as vlrlhf_b200/host.py:ddpo_row_weights does.
 //
 // This is a HOST function of the C ABI (plain host pointers); it needs no GPU and launches nothing.
 #include <stdint.h>

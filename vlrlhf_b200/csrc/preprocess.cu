@@ -3,7 +3,7 @@
 // transformers' CLIPImageProcessor -> Pillow `Image.resize(BICUBIC)` + numpy crop / rescale / normalize.
 //
 // Bit-exact with Pillow's 8-bit resampler (src/libImaging/Resample.c): the host builds the fixed-point (22 fractional
-// bits) coefficient tables exactly as precompute_coeffs + normalize_coeffs_8bpc do (vl-rlhf_b200/preprocess.py), and
+// bits) coefficient tables exactly as precompute_coeffs + normalize_coeffs_8bpc do (vlrlhf_b200/preprocess.py), and
 // the two passes below reproduce ImagingResampleHorizontal_8bpc / ImagingResampleVertical_8bpc: int32 accumulate
 // starting at 1<<21, arithmetic >>22, clip to [0,255], the horizontal result stored as uint8 before the vertical
 // pass.  Only the pixels that survive the center crop are computed.  The vertical pass is fused with the crop, the

@@ -503,18 +503,10 @@ def qwen_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labe
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
-def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
-             seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool, scale: float):
-    """q/k/v/out: 2-D row-major views [B*S, >= heads*head_dim] (may be column slices of one qkv buffer)."""
-    check(_L.vlb200_attn_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
-                             _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale, _stream()))
-    return out
-
-
 def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
                 seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool,
                 scale: float, row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
-    """tcgen05/TMEM/TMA forward; same contract as attn_fwd.  row_starts ([B+1] int32) + total_rows: packed rows, sequence b
+    """tcgen05/TMEM/TMA forward; q/k/v/out: 2-D row-major views [B*S, >= heads*head_dim] (may be column slices of one qkv buffer).  row_starts ([B+1] int32) + total_rows: packed rows, sequence b
     at rows [row_starts[b], row_starts[b] + seqlens[b]) (include/vlb200.h: vlb200_attn_fwd_tc_varlen)."""
     if row_starts is None:
         check(_L.vlb200_attn_fwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
@@ -527,16 +519,9 @@ def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Te
     return out
 
 
-def attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale):
-    check(_L.vlb200_attn_bwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out), out.stride(0),
-                             _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk),
-                             dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal),
-                             scale, _stream()))
-
-
 def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale,
                 row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
-    """tcgen05/TMEM/TMA backward; same contract as attn_bwd.  row_starts/total_rows: packed rows (see attn_fwd_tc)."""
+    """tcgen05/TMEM/TMA backward; same layout as attn_fwd_tc.  row_starts/total_rows: packed rows (see attn_fwd_tc)."""
     if row_starts is None:
         check(_L.vlb200_attn_bwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
                                     out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
