@@ -165,9 +165,10 @@ int vlb200_dot_f32(const float* a, const float* b, int n, float scale, float* ou
 
 /* ---- RoPE / SwiGLU / GELU (modeling_llama.py:146-184, modeling_llava.py:87-107) -----------
  * rope: rotate-half in place on the first n_rot_heads heads (q heads then k heads) of each row of qkv;
- * pos[rows] int32 indexes cos/sin tables [max_pos, head_dim/2] fp32; inverse=1 applies the transpose.   */
-int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int rows,
-                int n_rot_heads, int head_dim, int inverse, void* stream);
+ * pos[rows] int32 indexes cos/sin tables [table_rows, head_dim/2] fp32 (positions are clamped to the table: the host
+ * grows the tables before a longer sequence is run, engine.ensure_rope_len); inverse=1 applies the transpose.   */
+int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int table_rows,
+                int rows, int n_rot_heads, int head_dim, int inverse, void* stream);
 /* gate_up = [gate | up] per row (2*ff columns); act = silu(gate) * up                           */
 int vlb200_swiglu_fwd(const void* gate_up, int64_t ld_gu, void* act, int64_t ld_act, int rows, int ff, void* stream);
 int vlb200_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_dact, void* dgate_up,

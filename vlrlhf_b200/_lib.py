@@ -44,7 +44,7 @@ SIGNATURES = {
     "vlb200_colsum": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vlb200_colsum_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vlb200_dot_f32": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
-    "vlb200_rope": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vlb200_rope": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vlb200_swiglu_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "vlb200_swiglu_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "vlb200_gelu_fwd": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),

@@ -116,6 +116,34 @@ class TrainConfig:
     # are those of the padded batch; only TRL's `logits/chosen|rejected` metric changes meaning (it averages over the
     # attended positions instead of all positions).  All engines (LLaVA-1.5 / LLaVA-Next full fine-tune and LoRA, Qwen-VL, XC2).
     pack_sequences: bool = False
+    # HF TrainingArguments the reference recipes set (scripts/dpo_qwenvl.sh:4,35,42-43; scripts/dpo_llava.sh:40-41):
+    # k micro-batches are accumulated in the gradient arena before ONE reduction + AdamW step; the learning rate follows
+    # transformers.get_scheduler ("constant" | "linear" | "cosine", linear warm-up over warmup_steps or
+    # ceil(warmup_ratio * max_steps) optimizer steps; max_steps = 0: constant after the warm-up)
+    gradient_accumulation_steps: int = 1
+    lr_scheduler_type: str = "constant"
+    warmup_steps: int = 0
+    warmup_ratio: float = 0.0
+    max_steps: int = 0
+
+    def lr_at(self, optimizer_step: int) -> float:
+        """Learning rate of the optimizer step with this 0-based index == what transformers' LambdaLR schedules
+        (optimization.py: get_constant_schedule_with_warmup / get_linear_schedule_with_warmup /
+        get_cosine_schedule_with_warmup, num_cycles 0.5) hand to torch.optim.AdamW at that step."""
+        import math as _m
+        t = int(optimizer_step)
+        warm = self.warmup_steps if self.warmup_steps > 0 else int(_m.ceil(self.warmup_ratio * self.max_steps))
+        if t < warm:
+            return self.learning_rate * t / max(1, warm)
+        kind = self.lr_scheduler_type
+        if kind in ("constant", "constant_with_warmup") or self.max_steps <= 0:
+            return self.learning_rate
+        if kind == "linear":
+            return self.learning_rate * max(0.0, (self.max_steps - t) / max(1, self.max_steps - warm))
+        if kind == "cosine":
+            prog = (t - warm) / max(1, self.max_steps - warm)
+            return self.learning_rate * max(0.0, 0.5 * (1.0 + _m.cos(_m.pi * 2.0 * 0.5 * prog)))
+        raise ValueError(f"lr_scheduler_type {kind!r}: constant, linear or cosine")
 
 
 def tensor_seed(name: str, base_seed: int) -> int:

@@ -34,8 +34,8 @@ static inline int grid_for(size_t work_items, int threads) {
 // rotate-half on the first n_rot_heads heads of every row of `qkv` (q heads then k heads), in place.
 // cos/sin tables are [max_pos, dh/2] fp32 built on the host exactly like LlamaRotaryEmbedding.
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, const int* __restrict__ pos,
-                            const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int n_rot_heads,
-                            int dh, float sign) {
+                            const float* __restrict__ cos_t, const float* __restrict__ sin_t, int table_rows, int rows,
+                            int n_rot_heads, int dh, float sign) {
     const int half = dh >> 1;
     const int chunks = half >> 3;  // 8 pairs per work item
     const size_t total = (size_t)rows * n_rot_heads * chunks;
@@ -44,7 +44,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, const
         const int h = (int)((w / chunks) % n_rot_heads);
         const int r = (int)(w / ((size_t)chunks * n_rot_heads));
         __nv_bfloat16* p = qkv + (size_t)r * ld + (size_t)h * dh + c * 8;
-        const int ps = pos[r];
+        const int ps = min(max(pos[r], 0), table_rows - 1);
         const float* cp = cos_t + (size_t)ps * half + c * 8;
         const float* sp = sin_t + (size_t)ps * half + c * 8;
         float x1[8], x2[8];
@@ -621,13 +621,13 @@ using namespace vlb;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-extern "C" int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int rows,
-                           int n_rot_heads, int head_dim, int inverse, void* stream) {
-    VLB_REQUIRE(qkv && pos && cos_table && sin_table, "rope: null pointer");
+extern "C" int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int table_rows,
+                           int rows, int n_rot_heads, int head_dim, int inverse, void* stream) {
+    VLB_REQUIRE(qkv && pos && cos_table && sin_table && table_rows > 0, "rope: null pointer / empty table");
     VLB_REQUIRE(head_dim % 16 == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16, ld of 8");
     if (rows <= 0 || n_rot_heads <= 0) return VLB200_OK;
     const size_t work = (size_t)rows * n_rot_heads * (head_dim / 16);
-    rope_kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(BF(qkv), ld, pos, cos_table, sin_table, rows,
+    rope_kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(BF(qkv), ld, pos, cos_table, sin_table, table_rows, rows,
                                                                    n_rot_heads, head_dim, inverse ? -1.f : 1.f);
     count_launch();
     VLB_LAUNCH_CHECK();

@@ -199,6 +199,9 @@ class LlavaDPOEngine:
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
+        self.force_logit_means = False   # plugin: also produce TRL's logits/* means on no-grad passes (evaluation)
+        self._micro_step = 0       # train_step calls so far (gradient_accumulation_steps micro-batches per optimizer step)
+        self.last_lr = 0.0
         # VLB200_OVERLAP_ALLREDUCE=1 launches per-layer gradient buckets on the NCCL stream while backward continues.
         # Measured on 2xB200 (profiles/r1_bench_7b_2gpu_overlap.md): 697.4 ms/step overlapped vs 689.9 ms with ONE
         # all-reduce after backward -- the NCCL kernels take SMs from the persistent GEMMs' static tile schedule and
@@ -223,15 +226,22 @@ class LlavaDPOEngine:
         self._build_rope_tables()
 
     # ------------------------------------------------------------------ weights
-    def _build_rope_tables(self):
+    def _build_rope_tables(self, n_positions: Optional[int] = None):
         # identical arithmetic to LlamaRotaryEmbedding (modeling_llama.py:138-168): fp32 inv_freq, fp32 angles
         cfg = self.cfg
         dh = cfg.head_dim
         inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))
-        t = torch.arange(cfg.max_positions, dtype=torch.float32)
+        self.rope_len = int(n_positions or cfg.max_positions)
+        t = torch.arange(self.rope_len, dtype=torch.float32)
         freqs = t[:, None] * inv_freq[None, :]
         self.rope_cos = freqs.cos().contiguous().to(self.device)
         self.rope_sin = freqs.sin().contiguous().to(self.device)
+
+    def ensure_rope_len(self, n_positions: int):
+        """HF's rotary embedding grows its cos/sin cache on demand (modeling_llama.py:150-168); the tables here are rebuilt
+        when a merged sequence is longer than they are (e.g. --max_length 4096 + 575 image rows), never read out of bounds."""
+        if n_positions > self.rope_len:
+            self._build_rope_tables(max(int(n_positions), 2 * self.rope_len))
 
     def wait_optimizer(self):
         """Order the current stream after the deferred optimizer step (no host block).  Called before anything that
@@ -459,6 +469,7 @@ class LlavaDPOEngine:
         logps, per_tok, lse_v = ops.logps_fwd(logits, m.target, m.n_seq, weight=ddpo_weight)
         if save:
             self._saved = dict(m=m, feats=feats, x_last=x, lse_v=lse_v, ddpo_weight=ddpo_weight)
+        if save or self.force_logit_means:
             # TRL's `logits/chosen|rejected` = mean of the full [B,S,V] logits = dot(colsum(h), colsum(W_lm)) / (B*S*V)  (K19)
             # (packed rows: the mean runs over the attended positions only -- the reference also averages the logits of its
             # padding positions, which a packed batch never computes; the one metric that differs)
@@ -471,7 +482,7 @@ class LlavaDPOEngine:
         return logps
 
     def _head_backward(self, grad_logps: torch.Tensor, norm_w: torch.Tensor, lm_w: torch.Tensor, g_norm: torch.Tensor,
-                       g_lm: Optional[torch.Tensor]) -> torch.Tensor:
+                       g_lm: Optional[torch.Tensor], acc: bool = False) -> torch.Tensor:
         """d(log-probs) -> gradient of the last decoder layer's output (bf16 [T, d]); g_lm=None: lm_head is frozen."""
         cfg, sv = self.cfg, self._saved
         m = sv["m"]
@@ -481,26 +492,29 @@ class LlavaDPOEngine:
         dlogits = self.buf("b.dlogits", (R, cfg.vocab))
         ops.logps_bwd(logits, m.target, m.n_seq, sv["lse_v"], grad_logps, weight=sv["ddpo_weight"], out=dlogits)
         if g_lm is not None:
-            ops.gemm(dlogits, hsel, a_kmajor=False, b_kmajor=False, out=g_lm)              # dW = dlogits^T hsel
+            ops.gemm(dlogits, hsel, a_kmajor=False, b_kmajor=False, out=g_lm, accumulate=acc)   # dW = dlogits^T hsel
         dhsel = self.buf("b.dhsel", (R, d))
         ops.gemm(dlogits, lm_w, b_kmajor=False, out=dhsel)                                 # dh = dlogits W
         dxf = self.buf("b.dxf", (T, d))
         ops.zero_(dxf)
         ops.scatter_rows(dhsel, m.row_of_text, dxf)
         dx = self.buf("b.dx0", (T, d))
-        ops.rmsnorm_bwd(dxf, sv["x_last"], norm_w, self._bufs["a.rstd_f"], g_norm, out=dx)
+        ops.rmsnorm_bwd(dxf, sv["x_last"], norm_w, self._bufs["a.rstd_f"], g_norm, out=dx, dw_accumulate=acc)
         return dx
 
     # ------------------------------------------------------------------ backward of the policy copy
-    def _backward(self, grad_logps: torch.Tensor):
-        self.wait_optimizer()  # the gradient buffer is about to be overwritten
+    def _backward(self, grad_logps: torch.Tensor, accumulate: bool = False):
+        """accumulate: add this micro-batch's gradients to the gradient arena (gradient_accumulation_steps > 1) instead
+        of overwriting it -- every weight-gradient GEMM / reduction takes its `accumulate` epilogue."""
+        acc = bool(accumulate)
+        self.wait_optimizer()  # the gradient buffer is about to be written
         cfg, w, g = self.cfg, self.policy, self.g
         sv = self._saved
         m: ops.MergeIndex = sv["m"]
         d, T = cfg.hidden, m.T
         H, KV, dh = cfg.heads, cfg.kv_heads, cfg.head_dim
         hd, kvd = H * dh, KV * dh
-        dx = self._head_backward(grad_logps, w["norm"], w["lm_head"], g["norm"], g["lm_head"])
+        dx = self._head_backward(grad_logps, w["norm"], w["lm_head"], g["norm"], g["lm_head"], acc)
         dxf = self._bufs["b.dxf"]
         dx2 = self.buf("b.dx1", (T, d))
         self._reduce_bucket(self.layout.offsets["norm"], self.layout.size)          # norm + lm_head gradients are final
@@ -524,30 +538,35 @@ class LlavaDPOEngine:
             # ---- MLP
             ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h)                         # recompute h2
             ops.swiglu_fwd(gu, act)                                                           # recompute act
-            ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"])              # dWd = dx^T act
+            ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"], accumulate=acc)              # dWd = dx^T act
             ops.gemm(dx, w[f"L{i}.wd"], b_kmajor=False, out=dact)                             # dact = dx Wd
             ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
-            ops.gemm(gu, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wgu"])               # dWgu = dgu^T h2
+            ops.gemm(gu, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wgu"], accumulate=acc)               # dWgu = dgu^T h2
             ops.gemm(gu, w[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                           # dh2 = dgu Wgu
-            ops.rmsnorm_bwd(dnorm, xmid, w[f"L{i}.ln2"], rstd2, g[f"L{i}.ln2"], dres=dx, out=dx2)  # dxmid
+            ops.rmsnorm_bwd(dnorm, xmid, w[f"L{i}.ln2"], rstd2, g[f"L{i}.ln2"], dres=dx, out=dx2,
+                            dw_accumulate=acc)                                                # dxmid
             # ---- attention
-            ops.gemm(dx2, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wo"])             # dWo = dxmid^T att
+            ops.gemm(dx2, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wo"], accumulate=acc)             # dWo = dxmid^T att
             ops.gemm(dx2, w[f"L{i}.wo"], b_kmajor=False, out=datt)                            # datt = dxmid Wo
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
                          dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh,
                          True, scale, row_starts=m.starts, total_rows=m.T)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             ops.rmsnorm_fwd(x_in, w[f"L{i}.ln1"], cfg.rms_eps, out=h)                         # recompute h1
-            ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"])            # dWqkv = dqkv^T h1
+            ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"], accumulate=acc)            # dWqkv = dqkv^T h1
             ops.gemm(dqkv, w[f"L{i}.wqkv"], b_kmajor=False, out=dnorm)                        # dh1 = dqkv Wqkv
-            ops.rmsnorm_bwd(dnorm, x_in, w[f"L{i}.ln1"], rstd1, g[f"L{i}.ln1"], dres=dx2, out=dx)
+            ops.rmsnorm_bwd(dnorm, x_in, w[f"L{i}.ln1"], rstd1, g[f"L{i}.ln1"], dres=dx2, out=dx,
+                            dw_accumulate=acc)
             self._reduce_bucket(self.layout.offsets[f"L{i}.ln1"],
                                 self.layout.offsets[f"L{i + 1}.ln1"] if i + 1 < cfg.layers else self.layout.offsets["norm"])
         # ---- embedding / merge / projector
         feats = sv["feats"]
         nimg = feats.shape[0]
         dimg = self.buf("b.dimg", (nimg, d))
-        ops.zero_(self.dembed_f32)
+        if acc:   # the fp32 scatter target starts from the accumulated bf16 embedding gradient
+            ops.cast_bf16_to_f32(g["embed"].view(-1), self.dembed_f32.view(-1))
+        else:
+            ops.zero_(self.dembed_f32)
         plan = self._anyres
         if plan is None:
             ops.llava_merge_bwd(m, dx, self.dembed_f32, dimg)
@@ -558,16 +577,16 @@ class LlavaDPOEngine:
             ops.scatter_rows(dpacked, plan.scatter_index, dimg)
             dnl = self.buf("b.dnewline", (plan.newline_rows.numel(), d))
             ops.gather_rows(dpacked, plan.newline_rows, dnl)
-            ops.colsum(dnl, g["image_newline"])
+            ops.colsum(dnl, g["image_newline"], accumulate=acc)
         ops.cast_f32_to_bf16(self.dembed_f32.view(-1), g["embed"].view(-1))
         ph, z = self._bufs["p.h"], self._bufs["p.z"]
-        ops.gemm(dimg, ph, a_kmajor=False, b_kmajor=False, out=g["proj.w2"])
-        ops.colsum(dimg, g["proj.b2"])
+        ops.gemm(dimg, ph, a_kmajor=False, b_kmajor=False, out=g["proj.w2"], accumulate=acc)
+        ops.colsum(dimg, g["proj.b2"], accumulate=acc)
         dph = self.buf("b.dph", (nimg, d))
         ops.gemm(dimg, w["proj.w2"], b_kmajor=False, out=dph)
         ops.gelu_bwd(z, dph, out=dph)
-        ops.gemm(dph, feats, a_kmajor=False, b_kmajor=False, out=g["proj.w1"])
-        ops.colsum(dph, g["proj.b1"])
+        ops.gemm(dph, feats, a_kmajor=False, b_kmajor=False, out=g["proj.w1"], accumulate=acc)
+        ops.colsum(dph, g["proj.b1"], accumulate=acc)
         self._reduce_bucket(0, self.layout.offsets["L0.ln1"])                         # projector + embedding
 
     # ------------------------------------------------------------------ optimizer + data parallel
@@ -602,8 +621,13 @@ class LlavaDPOEngine:
             return torch.distributed.get_world_size(self.pg)
         return 1
 
-    def optimizer_step(self):
+    def optimizer_step(self, lr: Optional[float] = None):
+        """One clipped AdamW step over this rank's slice of the flat buffers.  `lr`: the learning rate of this step when an
+        outer scheduler owns it (plugin.B200FlatAdamW under the HF Trainer); default TrainConfig.lr_at(step index)."""
         tc = self.tc
+        if lr is None:
+            lr = tc.lr_at(self.opt_step)
+        self.last_lr = float(lr)
         self.opt_step += 1
         lo, hi = self.shard_lo, self.shard_hi
         g, p = self.grads[lo:hi], self.params[lo:hi]
@@ -612,11 +636,30 @@ class LlavaDPOEngine:
             torch.distributed.all_reduce(self.grad_sumsq, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         if self.device.type == "cuda":
             self.norm_done.record()  # the logged grad_norm is final here; AdamW only reads it
-        ops.adamw_(p, g, self.master, self.exp_avg, self.exp_avg_sq, tc.learning_rate, tc.adam_beta1,
+        ops.adamw_(p, g, self.master, self.exp_avg, self.exp_avg_sq, float(lr), tc.adam_beta1,
                    tc.adam_beta2, tc.adam_eps, tc.weight_decay, self.opt_step, grad_scale=1.0 / self.world_size(),
                    grad_sumsq=self.grad_sumsq, max_grad_norm=tc.max_grad_norm)
         if self.shard_optimizer:
             torch.distributed.all_gather_into_tensor(self.params, p, group=self.pg)
+
+    def reduce_and_step(self, lr: Optional[float] = None):
+        """Gradient reduction over the data-parallel ranks + AdamW (+ parameter all-gather when sharded); deferred to the
+        side stream when `async_optimizer` (the next step's reference pass overlaps it).  -> the device scalar that will hold
+        the squared global gradient norm (None without an optimizer)."""
+        if self.async_optimizer and self.with_optimizer:
+            main = torch.cuda.current_stream(self.device)
+            self.opt_stream.wait_stream(main)            # gradients are final
+            with torch.cuda.stream(self.opt_stream):
+                self.allreduce_grads()
+                self.optimizer_step(lr)
+                self.opt_done.record()
+            self._opt_pending = True
+            return self.grad_sumsq
+        self.allreduce_grads()
+        if self.with_optimizer:
+            self.optimizer_step(lr)
+            return self.grad_sumsq
+        return None
 
     # ------------------------------------------------------------------ the step
     def prepare_inputs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor,
@@ -632,8 +675,10 @@ class LlavaDPOEngine:
         cfg = self.cfg
         n_seq = input_ids.shape[0]
         plan = None
+        from . import host
+        host.validate_token_batch(input_ids, labels, cfg.vocab, cfg.image_token_index,
+                                  imgs_per_seq if cfg.family != "llava_next" else 1, self.tc.label_pad_token_id)
         if cfg.family == "llava_next":
-            from . import host
             if image_sizes is None:
                 raise ValueError("LLaVA-Next needs image_sizes (LlavaNext/__init__.py:211-218)")
             if image_sizes.shape[0] == n_seq:
@@ -691,6 +736,7 @@ class LlavaDPOEngine:
             if self.tc.pack_sequences:   # drop the padding rows: every kernel below runs over sum(len) rows
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+        self.ensure_rope_len(m.S)
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":
@@ -699,11 +745,14 @@ class LlavaDPOEngine:
         return self._forward(w, m, feats, which, save, ddpo_weight), m, feats
 
     def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True,
-             ref_logps: Optional[torch.Tensor] = None, seq_lens=None, imgs_per_seq: int = 1) -> StepOutput:
+             ref_logps: Optional[torch.Tensor] = None, seq_lens=None, imgs_per_seq: int = 1,
+             accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
         backward + gradient all-reduce + AdamW.  `ref_logps` ([2B] fp32, chosen then rejected) replaces the reference
         pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
-        the collator's `_logps` keys, base/collator.py:62-64)."""
+        the collator's `_logps` keys, base/collator.py:62-64).
+        Gradient accumulation: `accumulate` adds this micro-batch's gradients (scaled by `loss_scale` = 1/k) to the arena,
+        `sync=False` stops before the reduction + optimizer (HF Trainer's no_sync micro-steps)."""
         tc = self.tc
         if ref_logps is not None:
             pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, seq_lens=seq_lens,
@@ -718,28 +767,16 @@ class LlavaDPOEngine:
                                                **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
             pol, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
-                                                   1.0, want_grad=train)
+                                                   float(loss_scale), want_grad=train)
         out = StepOutput()
         out.losses, out.chosen_rewards, out.rejected_rewards, out.stats = losses, cr, rr, stats
         out.policy_logps, out.ref_logps = pol, ref
         out.loss = stats[0:1]
         out.grad_norm = None
         if train:
-            self._backward(grad)
-            if self.async_optimizer and self.with_optimizer:
-                main = torch.cuda.current_stream(self.device)
-                self.opt_stream.wait_stream(main)            # gradients are final
-                with torch.cuda.stream(self.opt_stream):
-                    self.allreduce_grads()
-                    self.optimizer_step()
-                    self.opt_done.record()
-                self._opt_pending = True
-                out.grad_norm = self.grad_sumsq
-            else:
-                self.allreduce_grads()
-                if self.with_optimizer:
-                    self.optimizer_step()
-                    out.grad_norm = self.grad_sumsq
+            self._backward(grad, accumulate=accumulate)
+            if sync:
+                out.grad_norm = self.reduce_and_step()
         return out
 
     def train_step(self, batch: Dict, train: bool = True) -> Dict[str, float]:
@@ -763,10 +800,15 @@ class LlavaDPOEngine:
         k = self.images_per_sequence(batch)
         kw = {"imgs_per_seq": k} if k != 1 else {}
         seq_lens = self.host_seq_lens(ids, am, sizes, **kw) if tc.pack_sequences else None
+        ga = max(1, int(tc.gradient_accumulation_steps)) if train else 1
+        micro = self._micro_step % ga
+        sync = micro == ga - 1
+        if train:
+            self._micro_step += 1
         out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes, **kw), train=train, ref_logps=ref_logps,
-                        seq_lens=seq_lens, **kw)
+                        seq_lens=seq_lens, accumulate=micro > 0, sync=sync, loss_scale=1.0 / ga, **kw)
         n = out.policy_logps.numel() // 2
-        if self._opt_pending:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
+        if self._opt_pending and out.grad_norm is not None:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
             torch.cuda.current_stream(self.device).wait_event(self.norm_done)
         packed = torch.cat([out.stats, out.policy_logps[:n].mean()[None], out.policy_logps[n:].mean()[None],
                             (out.grad_norm if out.grad_norm is not None else out.stats[:1] * 0),

@@ -206,7 +206,10 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         return self._head_forward(x, base["norm"], base["lm_head"], m, feats, save, ddpo_weight)
 
     # ------------------------------------------------------------------ backward: adapter gradients only
-    def _backward(self, grad_logps: torch.Tensor):
+    def _backward(self, grad_logps: torch.Tensor, accumulate: bool = False):
+        """accumulate: add this micro-batch's gradients to the gradient arena (gradient_accumulation_steps > 1) instead
+        of overwriting it -- every weight-gradient GEMM / reduction takes its `accumulate` epilogue."""
+        acc = bool(accumulate)
         self.wait_optimizer()
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
@@ -239,25 +242,25 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             xmid, gu, qkv, att = (sb[k] for k in ("xmid", "gu", "qkv", "att"))
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- down_proj
-            ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"])      # dBd = dx^T ts_d
+            ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"], accumulate=acc)      # dBd = dx^T ts_d
             ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=d1, alpha=s)                  # dt = s dx Bd
-            ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"])             # dAd = dt^T act
+            ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"], accumulate=acc)             # dAd = dt^T act
             ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
             # ---- gate | up
             ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h)                      # recompute h2
             ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
             tsg = sb["ts_gu"]
-            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.g.B"])
-            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.u.B"])
+            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.g.B"], accumulate=acc)
+            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.u.B"], accumulate=acc)
             ops.gemm(gu[:, :ff], lora[f"L{i}.g.B"], b_kmajor=False, out=d2[:, :r], alpha=s)
             ops.gemm(gu[:, ff:], lora[f"L{i}.u.B"], b_kmajor=False, out=d2[:, r:], alpha=s)
-            ops.gemm(d2, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])              # dA = dt^T h2  [2r, d]
+            ops.gemm(d2, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"], accumulate=acc)              # dA = dt^T h2  [2r, d]
             ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=d2, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- o_proj
-            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])
+            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"], accumulate=acc)
             ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=d1, alpha=s)
-            ops.gemm(d1, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])
+            ops.gemm(d1, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
                             dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale,
@@ -268,9 +271,9 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             tsq = sb["ts_qkv"]
             cols = ((0, hd, "q"), (hd, hd + kvd, "k"), (hd + kvd, hd + 2 * kvd, "v"))
             for j, (lo, hi, n) in enumerate(cols):
-                ops.gemm(dqkv[:, lo:hi], tsq[:, j * r:(j + 1) * r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.{n}.B"])
+                ops.gemm(dqkv[:, lo:hi], tsq[:, j * r:(j + 1) * r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.{n}.B"], accumulate=acc)
                 ops.gemm(dqkv[:, lo:hi], lora[f"L{i}.{n}.B"], b_kmajor=False, out=d3[:, j * r:(j + 1) * r], alpha=s)
-            ops.gemm(d3, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])             # [3r, d]
+            ops.gemm(d3, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"], accumulate=acc)             # [3r, d]
             if i > 0:  # nothing below decoder layer 0 is trainable: its input gradient is never read
                 ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=d3, b2=lora[f"L{i}.qkv.A"], out=dnorm)
                 ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)

@@ -358,7 +358,10 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         return self._head_forward(x, base["norm"], base["lm_head"], m, feats, save, ddpo_weight)
 
     # ------------------------------------------------------------------ backward: adapter gradients only
-    def _backward(self, grad_logps: torch.Tensor):
+    def _backward(self, grad_logps: torch.Tensor, accumulate: bool = False):
+        """accumulate: add this micro-batch's gradients to the gradient arena (gradient_accumulation_steps > 1) instead
+        of overwriting it -- every weight-gradient GEMM / reduction takes its `accumulate` epilogue."""
+        acc = bool(accumulate)
         self.wait_optimizer()
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
@@ -394,17 +397,17 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, out=dact)                          # dact = dx Wd
             ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
             tsg = sb["ts_gu"]
-            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w2.B"])   # dB2 = dgate^T ts2
-            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"])   # dB1 = dup^T ts1
+            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w2.B"], accumulate=acc)   # dB2 = dgate^T ts2
+            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"], accumulate=acc)   # dB1 = dup^T ts1
             ops.gemm(gu[:, :ff], lora[f"L{i}.w2.B"], b_kmajor=False, out=dt[:, :r], alpha=s)   # dt2 = s dgate B2
             ops.gemm(gu[:, ff:], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt[:, r:], alpha=s)   # dt1 = s dup B1
-            ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])              # dA = dt^T h2  [2r, d]
+            ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"], accumulate=acc)              # dA = dt^T h2  [2r, d]
             ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=dt, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- attention output projection (LoRA on attn.c_proj)
-            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])     # dBo = dxmid^T ts_o
+            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"], accumulate=acc)     # dBo = dxmid^T ts_o
             ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr, alpha=s)                 # dt = s dxmid Bo
-            ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])            # dAo = dt^T att
+            ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)            # dAo = dt^T att
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
             ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
                             dqkv[:, 2 * d:], m.seqlens, m.n_seq, m.S, H, H, dh, True, scale, row_starts=m.starts,
@@ -412,9 +415,9 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh, inverse=True)
             # ---- fused qkv projection (LoRA on attn.c_attn; the bias is frozen)
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
-            ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"])
+            ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"], accumulate=acc)
             ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr, alpha=s)
-            ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])
+            ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"], accumulate=acc)
             ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.qkv.A"], out=dnorm)   # dh1 = dqkv Wqkv + dt A
             ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)
             self._reduce_bucket(self.layout.offsets[f"L{i}.qkv.A"],
@@ -424,6 +427,8 @@ class QwenVLDPOEngine(LlavaDPOEngine):
     def prepare_inputs(self, input_ids, attention_mask, labels, pixel_values, ddpo_weight=None, image_sizes=None):
         dev = self.device
         n_seq = input_ids.shape[0]
+        from . import host
+        host.validate_token_batch(input_ids, labels, self.cfg.vocab, None, None, self.tc.label_pad_token_id)
         if pixel_values.shape[0] == n_seq:  # concatenated_inputs duplicated the images ([v, v], trainer.py:135-145)
             pixel_values = pixel_values[: n_seq // 2]
         ids = input_ids.to(dev, non_blocking=True).contiguous()
@@ -444,6 +449,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             if self.tc.pack_sequences:   # S == L here: the surviving rows are the attended tokens
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+        self.ensure_rope_len(m.S)
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":

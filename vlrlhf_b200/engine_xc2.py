@@ -306,7 +306,10 @@ class XC2DPOEngine(QwenVLDPOEngine):
         return self._head_forward(x, base["norm"], base["lm_head"], m, feats, save, ddpo_weight)
 
     # ------------------------------------------------------------------ backward: trainable-adapter gradients only
-    def _backward(self, grad_logps: torch.Tensor):
+    def _backward(self, grad_logps: torch.Tensor, accumulate: bool = False):
+        """accumulate: add this micro-batch's gradients to the gradient arena (gradient_accumulation_steps > 1) instead
+        of overwriting it -- every weight-gradient GEMM / reduction takes its `accumulate` epilogue."""
+        acc = bool(accumulate)
         self.wait_optimizer()
         cfg, base, lora, g = self.cfg, self.base, self.policy, self.g
         sv = self._saved
@@ -339,28 +342,28 @@ class XC2DPOEngine(QwenVLDPOEngine):
             xmid, gu, qkv, att = (sb[k] for k in ("xmid", "gu", "qkv", "att"))
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- down projection (LoRA + PLoRA on feed_forward.w2)
-            ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"])      # dBd = dx^T ts_d
+            ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"], accumulate=acc)      # dBd = dx^T ts_d
             ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=dr, alpha=s)
-            ops.gemm(dr, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"])             # dAd = dt^T act
+            ops.gemm(dr, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"], accumulate=acc)             # dAd = dt^T act
             ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
             self._plora_bwd([(dx, base[f"L{i}.p.d.B"], slice(0, pr))], base[f"L{i}.p.d.A"], dact)
             # ---- gate | up
             ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h)                      # recompute h2
             ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
             tsg = sb["ts_gu"]
-            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"])
-            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w3.B"])
+            ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w1.B"], accumulate=acc)
+            ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.w3.B"], accumulate=acc)
             ops.gemm(gu[:, :ff], lora[f"L{i}.w1.B"], b_kmajor=False, out=dt[:, :r], alpha=s)
             ops.gemm(gu[:, ff:], lora[f"L{i}.w3.B"], b_kmajor=False, out=dt[:, r:], alpha=s)
-            ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"])
+            ops.gemm(dt, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.gu.A"], accumulate=acc)
             ops.gemm(gu, base[f"L{i}.wgu"], b_kmajor=False, a2=dt, b2=lora[f"L{i}.gu.A"], out=dnorm)   # dh2 = dgu Wgu + dt A
             self._plora_bwd([(gu[:, :ff], base[f"L{i}.p.w1.B"], slice(0, pr)), (gu[:, ff:], base[f"L{i}.p.w3.B"], slice(pr, 2 * pr))],
                             base[f"L{i}.p.gu.A"], dnorm)
             ops.rmsnorm_bwd(dnorm, xmid, base[f"L{i}.ln2"], rstd2, self._dw_scratch, dres=dx, out=dx2)   # dxmid
             # ---- attention output projection
-            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"])
+            ops.gemm(dx2, sb["ts_o"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.B"], accumulate=acc)
             ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr, alpha=s)
-            ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"])
+            ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)
             self._plora_bwd([(dx2, base[f"L{i}.p.o.B"], slice(0, pr))], base[f"L{i}.p.o.A"], datt)
             ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
@@ -369,9 +372,9 @@ class XC2DPOEngine(QwenVLDPOEngine):
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             # ---- fused qkv projection
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
-            ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"])
+            ops.gemm(dqkv, sb["ts_qkv"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.B"], accumulate=acc)
             ops.gemm(dqkv, lora[f"L{i}.qkv.B"], b_kmajor=False, out=dr, alpha=s)
-            ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"])
+            ops.gemm(dr, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.qkv.A"], accumulate=acc)
             ops.gemm(dqkv, base[f"L{i}.wqkv"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.qkv.A"], out=dnorm)
             self._plora_bwd([(dqkv, base[f"L{i}.p.qkv.B"], slice(0, pr))], base[f"L{i}.p.qkv.A"], dnorm)
             ops.rmsnorm_bwd(dnorm, x_in, base[f"L{i}.ln1"], rstd1, self._dw_scratch, dres=dx2, out=dx)
@@ -380,6 +383,8 @@ class XC2DPOEngine(QwenVLDPOEngine):
 
     # ------------------------------------------------------------------ inputs
     def prepare_inputs(self, input_ids, attention_mask, labels, pixel_values, ddpo_weight=None, image_sizes=None):
+        from . import host
+        host.validate_token_batch(input_ids, None, self.cfg.vocab, self.cfg.image_token_index, 1)   # one image per sequence
         return QwenVLDPOEngine.prepare_inputs(self, input_ids, attention_mask, labels, pixel_values, ddpo_weight)
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
@@ -398,6 +403,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         self._img_rows = m.img_pos if m.packed else (
             m.img_pos.view(m.n_seq, -1) +
             (torch.arange(m.n_seq, dtype=torch.int32, device=m.img_pos.device) * m.S)[:, None]).reshape(-1).contiguous()
+        self.ensure_rope_len(m.S)
         if feats is None:
             feats = self.vision_features(px)
         if which == "policy":

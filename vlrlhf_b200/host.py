@@ -196,6 +196,29 @@ def right_pad_valid_tokens(input_ids: torch.Tensor, attention_mask: torch.Tensor
     return ids, am, lab
 
 
+def validate_token_batch(input_ids: torch.Tensor, labels: Optional[torch.Tensor], vocab: int, image_token_index: Optional[int] = None,
+                         imgs_per_seq: Optional[int] = None, label_pad_token_id: int = -100) -> None:
+    """Host-side checks of one concatenated batch BEFORE anything is indexed on the device (no device sync: only CPU tensors
+    are inspected; device-resident batches are the caller's responsibility).  Mirrors what the reference raises on:
+    a wrong number of <image> placeholders per sequence (Llava/__init__.py:90-94 ValueError -- prompt truncation can cut
+    the placeholder away) and token / label ids outside the embedding table (torch's embedding IndexError)."""
+    if input_ids.device.type != "cpu":
+        return
+    if input_ids.numel() and (int(input_ids.min()) < 0 or int(input_ids.max()) >= vocab):
+        raise IndexError(f"input_ids outside [0, {vocab}): min {int(input_ids.min())}, max {int(input_ids.max())}")
+    if labels is not None and labels.device.type == "cpu" and labels.numel():
+        lb = labels[labels != label_pad_token_id]
+        if lb.numel() and (int(lb.min()) < 0 or int(lb.max()) >= vocab):
+            raise IndexError(f"labels outside [0, {vocab}): min {int(lb.min())}, max {int(lb.max())}")
+    if image_token_index is not None and imgs_per_seq is not None:
+        cnt = (input_ids == image_token_index).sum(-1)
+        if bool((cnt != imgs_per_seq).any()):
+            raise ValueError(f"The input provided to the model are wrong. The number of image tokens is {int(cnt.sum())} while "
+                             f"the number of image given to the model is {int(imgs_per_seq) * input_ids.shape[0]}. This prevents "
+                             f"correct indexing and breaks batch generation. (per-sequence <image> counts {cnt.tolist()}, "
+                             f"expected {int(imgs_per_seq)} each)")
+
+
 def merged_seq_lens(input_ids: torch.Tensor, attention_mask: torch.Tensor, image_token_index: int, feat_rows) -> List[int]:
     """Merged length of every sequence's attended prefix -- what the merge kernels report as `seqlens` -- computed on the
     host so that a packed step (TrainConfig.pack_sequences) needs no device read-back: attended text tokens minus the

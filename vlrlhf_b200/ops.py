@@ -244,7 +244,7 @@ def dot_f32(a: torch.Tensor, b: torch.Tensor, scale: float, out: torch.Tensor):
 def rope_(qkv: torch.Tensor, pos: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, n_rot_heads: int, head_dim: int,
           inverse: bool = False):
     assert pos.dtype == torch.int32 and cos_t.dtype == torch.float32 and sin_t.dtype == torch.float32
-    check(_L.vlb200_rope(_ptr(qkv), _rowmajor_ld(qkv), _ptr(pos), _ptr(cos_t), _ptr(sin_t), qkv.shape[0], n_rot_heads,
+    check(_L.vlb200_rope(_ptr(qkv), _rowmajor_ld(qkv), _ptr(pos), _ptr(cos_t), _ptr(sin_t), cos_t.shape[0], qkv.shape[0], n_rot_heads,
                          head_dim, int(inverse), _stream()))
     return qkv
 
@@ -380,7 +380,7 @@ def llava_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, lab
     m.mask = torch.empty(n_seq, S, dtype=torch.int32, device=dev)
     m.pos = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
     m.seqlens = torch.empty(n_seq, dtype=torch.int32, device=dev)
-    m.img_pos = torch.empty(n_seq * imgs_per_seq * n_patches, dtype=torch.int32, device=dev)
+    m.img_pos = torch.zeros(n_seq * imgs_per_seq * n_patches, dtype=torch.int32, device=dev)
     m.row_of_text = torch.empty(n_seq * (L - 1), dtype=torch.int32, device=dev)
     m.target = torch.empty(n_seq * (L - 1), dtype=torch.int64, device=dev)
     m.status = torch.empty(1, dtype=torch.int32, device=dev)
@@ -423,7 +423,7 @@ def llavanext_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor,
     m.mask = torch.empty(n_seq, S, dtype=torch.int32, device=dev)
     m.pos = torch.empty(n_seq * S, dtype=torch.int32, device=dev)
     m.seqlens = torch.empty(n_seq, dtype=torch.int32, device=dev)
-    m.img_pos = torch.empty(m.reps * m.total_feats, dtype=torch.int32, device=dev)  # img_rows
+    m.img_pos = torch.zeros(m.reps * m.total_feats, dtype=torch.int32, device=dev)  # img_rows
     m.row_of_text = torch.empty(n_seq * (L - 1), dtype=torch.int32, device=dev)
     m.target = torch.empty(n_seq * (L - 1), dtype=torch.int64, device=dev)
     m.status = torch.empty(1, dtype=torch.int32, device=dev)

@@ -113,7 +113,91 @@ def dpo_loss(self, policy_chosen_logps: torch.Tensor, policy_rejected_logps: tor
 # --------------------------------------------------------------------------------------------
 # model wrapper + concatenated_forward
 # --------------------------------------------------------------------------------------------
-class B200LlavaForRL(nn.Module):
+class _EmbeddingHandle(nn.Module):
+    """What `get_input_embeddings()` returns: the embedding weight parameter under the usual attribute name (TRL /
+    HF Trainer only register hooks on it or read `.weight`)."""
+
+    def __init__(self, weight: Optional[nn.Parameter]):
+        super().__init__()
+        object.__setattr__(self, "weight", weight)
+
+    def forward(self, *a, **k):
+        raise RuntimeError("the embedding lookup is fused into the engine's merge kernel")
+
+
+class B200ModuleMixin:
+    """The nn.Module-side contract the HF Trainer / TRL DPOTrainer rely on, for every B200 model wrapper.
+
+    Parameters are VIEWS of the engine's flat arenas and their `.grad` are views of the flat gradient arena:
+      * `zero_grad()` keeps the views (torch's default `set_to_none=True` would drop them and every torch optimizer would
+        then skip the parameters); the gradients themselves need no zeroing -- the next backward overwrites them;
+      * `_EngineLogps.backward` re-attaches any view a foreign `zero_grad` (e.g. through a wrapper module) dropped, and
+        ACCUMULATES into the arena when the gradients of an earlier micro-batch are still live
+        (gradient_accumulation_steps > 1: HF calls zero_grad only after optimizer.step);
+      * `gradient_checkpointing_enable()` maps to TrainConfig.activation_checkpointing (every reference script passes
+        --gradient_checkpointing True); `enable_input_require_grads()` / `get_input_embeddings()` exist because TRL calls
+        them when checkpointing is on."""
+
+    _grads_live = False           # the arena holds gradients of micro-batches not yet consumed by an optimizer step
+    supports_gradient_checkpointing = True
+
+    def _register_engine_params(self, tensors: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], trainable):
+        self._hf: Dict[str, nn.Parameter] = {}
+        self._grad_views: Dict[str, torch.Tensor] = {}
+        for name, t in tensors.items():
+            tr = bool(trainable(name))
+            p = nn.Parameter(t, requires_grad=tr)
+            if tr:
+                self._grad_views[name] = grads[name]
+                p.grad = grads[name]  # gradient storage = the engine's flat reduce buffer
+            self._hf[name] = p
+            self.register_parameter(name.replace(".", "__"), p)
+
+    def hf_named_parameters(self):
+        return self._hf.items()
+
+    def _grads_attached(self) -> bool:
+        for name, gv in self._grad_views.items():
+            g = self._hf[name].grad
+            return g is not None and g.data_ptr() == gv.data_ptr()
+        return False
+
+    def _attach_grads(self):
+        for name, gv in self._grad_views.items():
+            p = self._hf[name]
+            if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
+                p.grad = gv
+
+    def zero_grad(self, set_to_none: bool = True):
+        self._attach_grads()
+        self._grads_live = False
+
+    # ---- gradient checkpointing (HF PreTrainedModel API)
+    def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None):
+        self.engine.tc.activation_checkpointing = True
+
+    def gradient_checkpointing_disable(self):
+        self.engine.tc.activation_checkpointing = False
+
+    @property
+    def is_gradient_checkpointing(self) -> bool:
+        return bool(self.engine.tc.activation_checkpointing)
+
+    def enable_input_require_grads(self):
+        pass   # the hand-written backward needs no autograd hook on the embedding output
+
+    def get_input_embeddings(self):
+        for name, p in self._hf.items():
+            if name.endswith("embed_tokens.weight") or name.endswith("wte.weight") or name.endswith("tok_embeddings.weight"):
+                return _EmbeddingHandle(p)
+        return _EmbeddingHandle(None)
+
+    def flat_optimizer(self, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                       max_grad_norm: Optional[float] = None) -> "B200FlatAdamW":
+        return B200FlatAdamW(self, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+
+
+class B200LlavaForRL(B200ModuleMixin, nn.Module):
     """Holds the engine; exposes HF-named `nn.Parameter`s that are VIEWS of the engine's flat bf16 arena (torch
     keeps a handle, the engine keeps the storage), so state_dict()/save_pretrained-style tooling, parameter
     freezing and optimizers see the usual names.  Mirrors the model-side contract of docs/CustomizedModel.md:
@@ -124,18 +208,8 @@ class B200LlavaForRL(nn.Module):
         super().__init__()
         self.engine = LlavaDPOEngine(cfg, train, device=device, with_optimizer=with_optimizer)
         self.cfg = cfg
-        grads = self.engine.hf_state("grad")
-        self._hf = {}
-        for name, t in self.engine.hf_state("policy").items():
-            trainable = not name.startswith("vision_tower.")
-            p = nn.Parameter(t, requires_grad=trainable)
-            if trainable:
-                p.grad = grads[name]  # gradient storage = the engine's flat all-reduce buffer
-            self._hf[name] = p
-            self.register_parameter(name.replace(".", "__"), p)
-
-    def hf_named_parameters(self):
-        return self._hf.items()
+        self._register_engine_params(self.engine.hf_state("policy"), self.engine.hf_state("grad"),
+                                     lambda name: not name.startswith("vision_tower."))
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, *args, config=None, torch_dtype=None,
@@ -192,28 +266,60 @@ class B200LlavaForRL(nn.Module):
 
 class _EngineLogps(torch.autograd.Function):
     """Policy log-probs as a differentiable function of the engine's parameters: backward runs the hand-written
-    backward pass and leaves the gradients in the parameters' .grad views."""
+    backward pass and leaves the gradients in the parameters' .grad views (accumulating when an earlier micro-batch's
+    gradients are still live)."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, inputs, seq_lens, imgs_per_seq=1):
-        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens,
-                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
-        ctx.engine = engine
+    def forward(ctx, anchor, owner, inputs, seq_lens, imgs_per_seq=1, shared=None):
+        engine = owner.engine
+        kw = {"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}
+        if shared is not None:
+            kw.update(feats=shared[0], m=shared[1])
+        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens, **kw)
+        ctx.owner = owner
         return logps
 
     @staticmethod
     def backward(ctx, g):
-        ctx.engine._backward(g.float().contiguous())
-        return torch.zeros(1, device=g.device), None, None, None, None
+        owner = ctx.owner
+        acc = bool(getattr(owner, "_grads_live", False)) and owner._grads_attached()
+        owner.engine._backward(g.float().contiguous(), accumulate=acc)
+        owner._attach_grads()
+        owner._grads_live = True
+        return torch.zeros(1, device=g.device), None, None, None, None, None
+
+
+def unwrap_model(model):
+    """DDP / accelerate / torch.compile wrappers -> the B200 module (or RefView) underneath."""
+    seen = 0
+    while not hasattr(model, "engine") and seen < 8:
+        inner = getattr(model, "module", None) or getattr(model, "_orig_mod", None)
+        if inner is None:
+            break
+        model, seen = inner, seen + 1
+    if not hasattr(model, "engine"):
+        raise TypeError(f"{type(model).__name__} is not a B200 model wrapper (no engine underneath)")
+    return model
 
 
 def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, torch.LongTensor]]
-                         ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """VLDPOTrainer.concatenated_forward (base/trainer.py:190-242) on the engine.  Returns
-    (chosen_logps, rejected_logps, None, None): the [B,S,V] logits the reference returns only feed a logging
-    `.mean()` and are never materialised here.  `model` is a B200LlavaForRL or the string 'ref' wrapper."""
+    (chosen_logps, rejected_logps, chosen_logits, rejected_logits) where the last two are ONE-element fp32 tensors holding
+    the mean of the [B,S,V] logits the reference returns: trl's get_batch_loss_metrics only ever takes
+    `.detach().mean()` of them (a logging metric), so the full tensors are never materialised.  `model` is a B200 model
+    wrapper (possibly under DDP/accelerate wrappers) or a RefView."""
+    model = unwrap_model(model)
     eng: LlavaDPOEngine = model.engine
     which = getattr(model, "_which", "policy")
+    owner = getattr(model, "_owner", model)
+    n = batch["chosen_labels"].shape[0]
+    stash = getattr(owner, "_ref_stash", None)
+    if which == "ref" and stash is not None and stash[0] is batch:   # computed ahead by the policy call on this batch
+        owner._ref_stash = None
+        lg = stash[1]
+        zero = lg.new_zeros(1)
+        return lg[:n], lg[n:], zero, zero.clone()
     cb = host.concatenated_inputs(batch, getattr(self, "is_encoder_decoder", False),
                                   getattr(self, "label_pad_token_id", -100), getattr(self, "padding_value", 0) or 0)
     ids, am, lb = host.right_pad_valid_tokens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
@@ -232,14 +338,32 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes, **kw)
     # TrainConfig.pack_sequences: the merged lengths come from the host batch, so the step stays free of device read-backs
     seq_lens = eng.host_seq_lens(ids, am, sizes, **kw) if eng.tc.pack_sequences else None
-    n = batch["chosen_labels"].shape[0]
-    if which == "policy" and torch.is_grad_enabled():
-        anchor = torch.zeros(1, device=eng.device, requires_grad=True)
-        logps = _EngineLogps.apply(anchor, eng, inputs, seq_lens, k)
-    else:
-        with torch.no_grad():
-            logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens, **kw)
-    return logps[:n], logps[n:], None, None
+    eng.force_logit_means = which == "policy"
+    try:
+        if which == "policy" and torch.is_grad_enabled():
+            shared = None
+            ref_model = getattr(self, "ref_model", None)
+            if (isinstance(ref_model, RefView) and ref_model._owner is owner and "reference_chosen_logps" not in batch
+                    and not getattr(self, "precompute_ref_log_probs", False)):
+                # trl calls policy first, reference second (get_batch_loss_metrics); the frozen reference pass is run HERE,
+                # ahead of the policy pass, and handed out when trl asks for it: image features and the merge index are
+                # computed once for both passes, and a deferred optimizer step of the previous batch overlaps it
+                with torch.no_grad():
+                    ref_lg, m, feats = eng.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens, **kw)
+                owner._ref_stash = (batch, ref_lg.clone())
+                shared = (feats, m)
+            anchor = torch.zeros(1, device=eng.device, requires_grad=True)
+            logps = _EngineLogps.apply(anchor, owner, inputs, seq_lens, k, shared)
+        else:
+            with torch.no_grad():
+                logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens, **kw)
+        if which == "policy":
+            means = eng.logit_means.clone()
+            return logps[:n], logps[n:], means[0:1], means[1:2]
+    finally:
+        eng.force_logit_means = False
+    zero = logps.new_zeros(1)
+    return logps[:n], logps[n:], zero, zero.clone()
 
 
 def model_pixels(model, input_ids: torch.Tensor) -> torch.Tensor:
@@ -252,7 +376,8 @@ def model_pixels(model, input_ids: torch.Tensor) -> torch.Tensor:
 class RefView(nn.Module):
     """`ref_model` handle for TRL's concatenated_forward(self.ref_model, batch) call: the same engine, reference weights
     (full fine-tuning: the frozen copy; LoRA: the shared base with the adapters off).  A parameter-less nn.Module so the
-    trainer's `.eval()` / dropout / accelerate bookkeeping accepts it without copying the engine."""
+    trainer's `.eval()` / dropout / accelerate bookkeeping accepts it without copying the engine (trl's
+    `create_reference_model(model)` would deep-copy 120 GB of arenas plus CUDA streams and events)."""
 
     def __init__(self, model):
         super().__init__()
@@ -262,6 +387,129 @@ class RefView(nn.Module):
 
     def forward(self, *a, **k):
         raise RuntimeError("RefView is consumed by concatenated_forward; it has no logits-producing forward")
+
+    def __deepcopy__(self, memo):
+        return self
+
+
+# --------------------------------------------------------------------------------------------
+# the optimizer the Trainer steps: the engine's flat fused AdamW (+ the data-parallel gradient reduction)
+# --------------------------------------------------------------------------------------------
+class B200FlatAdamW(torch.optim.Optimizer):
+    """torch.optim.Optimizer facade over the engine's flat optimizer state, for `Trainer(optimizers=(opt, sched))` /
+    `create_optimizer`: `step()` = gradient reduction over the data-parallel ranks (NCCL reduce-scatter of the flat bf16
+    gradient arena; nothing at world 1) + global-norm clipping + ONE fused AdamW launch over this rank's slice (fp32 master
+    weights and moments) + parameter all-gather.  The learning rate is read from `param_groups[0]["lr"]` at every step, so
+    any torch LR scheduler (HF get_scheduler's LambdaLR) drives it.  The parameters are not part of an autograd graph, so
+    DDP's reducer hooks would never fire for them: THIS is where replicas are kept in sync -- do not wrap the model in DDP /
+    DeepSpeed (the trainer classes built by install*() keep accelerate from doing so)."""
+
+    def __init__(self, model, lr: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_grad_norm: Optional[float] = None):
+        model = unwrap_model(model)
+        eng = model.engine
+        if not eng.with_optimizer:
+            raise ValueError("the engine was built with with_optimizer=False: no fp32 master / moment arenas to step")
+        params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=float(lr), betas=tuple(betas), eps=float(eps), weight_decay=float(weight_decay)))
+        self.model, self.engine = model, eng
+        if max_grad_norm is not None:
+            eng.tc.max_grad_norm = float(max_grad_norm)
+        eng.async_optimizer = False   # under the Trainer the next call is the policy pass: nothing to overlap with
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g, eng = self.param_groups[0], self.engine
+        tc = eng.tc
+        tc.adam_beta1, tc.adam_beta2 = (float(b) for b in g["betas"])
+        tc.adam_eps, tc.weight_decay = float(g["eps"]), float(g["weight_decay"])
+        self.grad_norm_sq = eng.reduce_and_step(lr=float(g["lr"]))
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.model.zero_grad()
+
+    def grad_norm(self) -> float:
+        """Global gradient norm of the last step (before clipping), one device read."""
+        return float(self.grad_norm_sq.item()) ** 0.5 / self.engine.world_size()
+
+    def state_dict(self):
+        sd = super().state_dict()
+        eng = self.engine
+        eng.wait_optimizer()
+        sd["b200_flat"] = {"step": eng.opt_step, "shard": (eng.shard_lo, eng.shard_hi), "master": eng.master,
+                           "exp_avg": eng.exp_avg, "exp_avg_sq": eng.exp_avg_sq}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        flat = state_dict.get("b200_flat")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "b200_flat"})
+        if flat is not None:
+            eng = self.engine
+            eng.wait_optimizer()
+            if tuple(flat["shard"]) != (eng.shard_lo, eng.shard_hi):
+                raise ValueError(f"optimizer state of shard {tuple(flat['shard'])} loaded into shard {(eng.shard_lo, eng.shard_hi)}")
+            eng.opt_step = int(flat["step"])
+            eng.master.copy_(flat["master"]); eng.exp_avg.copy_(flat["exp_avg"]); eng.exp_avg_sq.copy_(flat["exp_avg_sq"])
+
+
+def make_trainer_class(base, check_peft=None, name: str = "B200DPOTrainer"):
+    """The reference's DPO trainer class for a family (`core_mapper.dpo_trainer`, a VLDPOTrainer subclass) with the three
+    hot-path override points replaced and the Trainer-side plumbing the engine needs:
+      * `ref_model` defaults to a RefView of the same engine (the reference builds ref_model=None, utils/auto_load.py:537, and
+        trl would `create_reference_model(model)` = deep-copy every arena);
+      * `create_optimizer` returns B200FlatAdamW with the TrainingArguments' lr / betas / eps / weight decay; clipping by
+        `max_grad_norm` moves into that fused step (HF's own clip pass over 6.8 G gradient views is switched off);
+      * accelerate is kept from wrapping the model in DDP (gradient reduction happens inside the optimizer step);
+      * `training_step` without the reference's per-step empty_cache() + gc.collect() (base/trainer.py:303-308)."""
+
+    class B200DPOTrainer(base):
+        get_batch_logps = staticmethod(get_batch_logps)
+        concatenated_forward = concatenated_forward
+        dpo_loss = dpo_loss
+
+        def __init__(self, model=None, ref_model=None, *a, peft_config=None, **k):
+            if check_peft is not None:   # LoRA families: the adapters are the engine's, not peft modules
+                check_peft(model, peft_config)
+                peft_config = None
+            args = k.get("args")
+            self._b200_max_grad_norm = getattr(args, "max_grad_norm", None) if args is not None else None
+            if args is not None and self._b200_max_grad_norm:
+                args.max_grad_norm = 0.0   # clipping is fused into B200FlatAdamW.step
+            if args is not None and getattr(args, "gradient_checkpointing", False):
+                unwrap_model(model).gradient_checkpointing_enable()
+            super().__init__(model, ref_model if ref_model is not None else RefView(unwrap_model(model)), *a,
+                             peft_config=peft_config, **k)
+            acc = getattr(self, "accelerator", None)
+            if acc is not None and hasattr(acc, "prepare_model"):
+                prepare_model = acc.prepare_model
+
+                def _prepare_model(m, *pa, **pk):
+                    if hasattr(m, "engine"):   # B200 wrapper or RefView: device placement and reduction are the engine's
+                        return m
+                    return prepare_model(m, *pa, **pk)
+                acc.prepare_model = _prepare_model
+
+        def create_optimizer(self):
+            if getattr(self, "optimizer", None) is None:
+                a = self.args
+                self.optimizer = B200FlatAdamW(self.model, lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2),
+                                               eps=a.adam_epsilon, weight_decay=a.weight_decay,
+                                               max_grad_norm=self._b200_max_grad_norm)
+            return self.optimizer
+
+        def training_step(self, model, inputs, *a, **k):
+            mro = type(self).__mro__
+            for cls in mro[mro.index(B200DPOTrainer) + 1:]:
+                fn = cls.__dict__.get("training_step")
+                if fn is None or "empty_cache" in getattr(getattr(fn, "__code__", None), "co_names", ()):
+                    continue   # VLDPOTrainer's empty_cache() + gc.collect() wrapper (base/trainer.py:303-308) is skipped
+                return fn(self, model, inputs, *a, **k)
+            raise AttributeError("no training_step below the B200 trainer class")
+
+    B200DPOTrainer.__name__ = B200DPOTrainer.__qualname__ = name
+    return B200DPOTrainer
 
 
 def install():
@@ -274,13 +522,7 @@ def install():
     from vlrlhf.base.trainer import VLDPOTrainer
     from vlrlhf.models.utils import ModelCoreMapper
 
-    class LlavaB200DPOTrainer(VLDPOTrainer):
-        get_batch_logps = staticmethod(get_batch_logps)
-        concatenated_forward = concatenated_forward
-        dpo_loss = dpo_loss
-
-        def training_step(self, model, inputs):  # trainer.py:303-308 without the per-step empty_cache()/gc
-            return super(VLDPOTrainer, self).training_step(model, inputs)
+    LlavaB200DPOTrainer = make_trainer_class(VLDPOTrainer, name="LlavaB200DPOTrainer")
 
     def swap(mod):
         ref = mod.core_mapper

@@ -26,9 +26,10 @@ import torch
 import torch.nn as nn
 
 from .config import LLAVA_LORA_LINEARS, TrainConfig, XC2ModelConfig, with_lora
+from .plugin import B200ModuleMixin
 
 
-class _B200LoRAModel(nn.Module):
+class _B200LoRAModel(B200ModuleMixin, nn.Module):
     """nn.Module whose parameters are views of an adapter-training engine's arenas: adapters trainable with `.grad` = the
     engine's flat gradient buffer, base and tower frozen (peft freezes every base parameter)."""
 
@@ -36,14 +37,7 @@ class _B200LoRAModel(nn.Module):
         super().__init__()
         self.engine, self.cfg = engine, cfg
         grads = self._storage(engine.g)
-        self._hf: Dict[str, nn.Parameter] = {}
-        for name, t in {**self._base_storage(), **self._storage(engine.policy)}.items():
-            trainable = name in grads
-            p = nn.Parameter(t, requires_grad=trainable)
-            if trainable:
-                p.grad = grads[name]
-            self._hf[name] = p
-            self.register_parameter(name.replace(".", "__"), p)
+        self._register_engine_params({**self._base_storage(), **self._storage(engine.policy)}, grads, lambda n: n in grads)
         self.hf_config_dict: Optional[dict] = None
         self.base_model_name_or_path: Optional[str] = None
         self.config = None
@@ -66,9 +60,6 @@ class _B200LoRAModel(nn.Module):
             eng._store(dst, name, t)
         else:
             dst[name].copy_(t.to(eng.device, torch.bfloat16).reshape(dst[name].shape))
-
-    def hf_named_parameters(self):
-        return self._hf.items()
 
     def forward(self, *a, **k):
         raise RuntimeError(f"{type(self).__name__} is driven through concatenated_forward / engine.train_step; generation "
@@ -322,17 +313,7 @@ def lora_args_from_argv(argv: Optional[List[str]] = None) -> Optional[Dict[str, 
 
 
 def _trainer_class(base, plugin):
-    class B200LoRADPOTrainer(base):
-        get_batch_logps = staticmethod(plugin.get_batch_logps)
-        concatenated_forward = plugin.concatenated_forward
-        dpo_loss = plugin.dpo_loss
-
-        def __init__(self, model=None, ref_model=None, *a, peft_config=None, **k):
-            check_peft_config(model, peft_config)
-            # the adapters are the engine's, not peft modules; the reference pass = the same engine with them off
-            super().__init__(model, ref_model if ref_model is not None else plugin.RefView(model), *a, peft_config=None, **k)
-
-    return B200LoRADPOTrainer
+    return plugin.make_trainer_class(base, check_peft=check_peft_config, name="B200LoRADPOTrainer")
 
 
 def install_lora(families=("Llava", "LlavaNext", "InternLMXC2"), lora_args: Optional[Dict[str, float]] = None):

@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from .config import QWEN_LORA_TARGETS, QwenModelConfig, TrainConfig
 from .engine_qwen import QwenVLDPOEngine
+from .plugin import B200ModuleMixin
 
 
 def qwen_config_from_hf(hf_config, lora_r: int = 64, lora_alpha: float = 16.0) -> QwenModelConfig:
@@ -61,21 +62,15 @@ def image_paths_from_ids(input_ids: torch.Tensor, image_start_id: int) -> List[s
     return out
 
 
-class B200QwenVLForRL(nn.Module):
+class B200QwenVLForRL(B200ModuleMixin, nn.Module):
     def __init__(self, cfg: QwenModelConfig, train: Optional[TrainConfig] = None, device: str = "cuda",
                  with_optimizer: bool = True):
         super().__init__()
         self.engine = QwenVLDPOEngine(cfg, train, device=device, with_optimizer=with_optimizer)
         self.cfg = cfg
         grads = self.engine.hf_state("grad")
-        self._hf: Dict[str, nn.Parameter] = {}
-        for name, t in self.engine.hf_state("policy").items():
-            trainable = name in grads  # the adapters; the base LM is frozen under LoRA (peft freezes every base parameter)
-            p = nn.Parameter(t, requires_grad=trainable)
-            if trainable:
-                p.grad = grads[name]
-            self._hf[name] = p
-            self.register_parameter(name.replace(".", "__"), p)
+        # trainable = the adapters; the base LM is frozen under LoRA (peft freezes every base parameter)
+        self._register_engine_params(self.engine.hf_state("policy"), grads, lambda n: n in grads)
         self._preprocessor = None
         self.hf_config_dict: Optional[dict] = None
         self.base_model_name_or_path: Optional[str] = None
@@ -200,14 +195,8 @@ def install_qwen():
     from vlrlhf.models.utils import ModelCoreMapper
     ref = qwen.core_mapper
 
-    class QwenVLB200DPOTrainer(ref.dpo_trainer):  # keeps QwenVLDPOTrainer.tokenize_row (:257-347)
-        get_batch_logps = staticmethod(plugin.get_batch_logps)
-        concatenated_forward = plugin.concatenated_forward
-        dpo_loss = plugin.dpo_loss
-
-        def __init__(self, model=None, *a, peft_config=None, **k):
-            check_peft_config(model, peft_config)
-            super().__init__(model, *a, peft_config=None, **k)  # the adapters are the engine's, not peft modules
+    # keeps QwenVLDPOTrainer.tokenize_row (:257-347); the adapters are the engine's, not peft modules
+    QwenVLB200DPOTrainer = plugin.make_trainer_class(ref.dpo_trainer, check_peft=check_peft_config, name="QwenVLB200DPOTrainer")
 
     qwen.core_mapper = ModelCoreMapper(
         model=B200QwenVLForRL, processor=ref.processor, dpo_collator=ref.dpo_collator, dpo_trainer=QwenVLB200DPOTrainer,
