@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's PyTorch-CPU path (port)
+    python bench.py --impl library   [--steps K]                   # stock transformers + SDPA + fused AdamW on the same GPU
 
 Workload (BASELINE.json configs[1]): LLaVA-1.5-7B DPO, bf16, 4 pairs/GPU, text seq 1024 (+575 image
 positions -> 1599 decoder tokens/sequence), 1x336-px image per pair, full fine-tune of projector + LLM,
@@ -279,8 +280,11 @@ def run_b200(args):
         return run_b200_lora(args, cfg, world, rank, local)
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     # configs[3] (LLaVA-Next-Mistral-7B, S = 2199) keeps only the layer inputs for backward so that full-FT fits one GPU
-    eng = engine.LlavaDPOEngine(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b"),
-                                                        pack_sequences=args.pack))
+    # built through the reference-facing wrapper (plugin.B200LlavaForRL: nn.Parameters that are views of the engine's arenas)
+    from vlrlhf_b200 import plugin
+    model = plugin.B200LlavaForRL(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b"),
+                                                          pack_sequences=args.pack))
+    eng = model.engine
     eng.init_synthetic(0)  # same weights on every rank
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)  # rank-local pairs
     cb = host.concatenated_inputs(batch)
@@ -358,6 +362,45 @@ def run_b200(args):
                                           full, nseq, S, H, KV, dh, True, sc), 10)
     attn_fl = 4.0 * S * S * dh * H * nseq / 2
     del qkv, att, datt, dqkv
+    # the two long-K GEMM shapes that carry as much of the step as the forward shape: the gate|up input
+    # gradient (K = 2*ff) and weight gradient (K = T, MN-major operands), timed alone like the headline kernel
+    dgu = eng.buf("s.gu" if eng.tc.activation_checkpointing else "a.gu.0", (T, 2 * cfg.ff))
+    dh2 = eng.buf("b.dxf", (T, cfg.hidden))
+    dgrad_ms = timed(lambda: ops.gemm(dgu, wgu, b_kmajor=False, out=dh2), 10)
+    gw = eng.g["L0.wgu"]
+    wgrad_ms = timed(lambda: ops.gemm(dgu, a, a_kmajor=False, b_kmajor=False, out=gw), 10)
+    gemm_fl = 2.0 * T * 2 * cfg.ff * cfg.hidden
+
+    # the same step through the Trainer-side boundary (plugin.concatenated_forward x2 -> dpo_loss -> loss.backward() ->
+    # B200FlatAdamW.step -> zero_grad), i.e. trl's get_batch_loss_metrics + HF training_step, host batch in, metrics out
+    ms_plugin, plugin_last = None, {}
+    trainer = opt = step_plugin = None
+    if not args.skip_plugin and not args.skip_e2e:
+        from types import SimpleNamespace
+        eng.wait_optimizer()
+        trainer = SimpleNamespace(loss_type=loss_type, beta=eng.tc.beta, label_smoothing=eng.tc.label_smoothing,
+                                  reference_free=False, label_pad_token_id=-100, padding_value=0, is_encoder_decoder=False,
+                                  ref_model=plugin.RefView(model), precompute_ref_log_probs=False)
+        opt = model.flat_optimizer(lr=eng.tc.learning_rate, betas=(eng.tc.adam_beta1, eng.tc.adam_beta2), eps=eng.tc.adam_eps,
+                                   weight_decay=eng.tc.weight_decay, max_grad_norm=eng.tc.max_grad_norm)
+
+        def step_plugin():
+            pc, pr, pcl, prl = plugin.concatenated_forward(trainer, model, batch)
+            with torch.no_grad():
+                rc, rr, _, _ = plugin.concatenated_forward(trainer, trainer.ref_model, batch)
+            losses, cr, rj = plugin.dpo_loss(trainer, pc, pr, rc, rr)
+            loss = losses.mean()
+            loss.backward()
+            opt.step()
+            model.zero_grad()
+            packed = torch.stack([loss.detach(), cr.mean(), rj.mean(), (cr > rj).float().mean(), pc.detach().mean(),
+                                  pr.detach().mean(), pcl.detach().mean(), prl.detach().mean()]).cpu()   # the D2H read
+            plugin_last.update(loss=float(packed[0]), **{"rewards/chosen": float(packed[1]), "rewards/rejected": float(packed[2]),
+                               "rewards/accuracies": float(packed[3]), "logps/chosen": float(packed[4]),
+                               "logps/rejected": float(packed[5]), "logits/chosen": float(packed[6]),
+                               "logits/rejected": float(packed[7])})
+        step_plugin()
+        ms_plugin = timed(step_plugin, args.steps)
     if rank == 0:
         pairs = PAIRS_PER_GPU * world
         h2d = sum(int(t.numel() * t.element_size()) for t in (cb["concatenated_input_ids"], cb["concatenated_attention_mask"],
@@ -371,16 +414,30 @@ def run_b200(args):
                        "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
                        "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
                        "rows_per_step": (sum(seq_lens) if seq_lens else 2 * PAIRS_PER_GPU * S),
-                       "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master+moments, max_grad_norm 1.0",
+                       "parallelism": (f"dp{world}: gradients reduce-scattered (NCCL), AdamW on each rank's 1/{world} slice (ZeRO-1), "
+                                       f"parameters all-gathered; deferred to a side stream under the next reference pass")
+                       if world > 1 else "dp1 (no collective)",
+                       "optimizer": "AdamW fp32 master+moments, max_grad_norm 1.0",
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
                        "step_tflop_algorithmic": flops / 1e12,
                        "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
             "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                     "ms_per_step": ms_e2e, "last_metrics": last},
+            "e2e_plugin": {"value": (pairs / (ms_plugin / 1e3) if ms_plugin else None), "unit": UNIT, "ms_per_step": ms_plugin,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 4, "last_metrics": plugin_last,
+                           "path": "plugin.concatenated_forward(policy) + (RefView) -> plugin.dpo_loss -> losses.mean().backward() "
+                                   "-> B200FlatAdamW.step() -> model.zero_grad(): trl get_batch_loss_metrics + HF training_step"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,K-major> (tcgen05 cta_group::2, 256x256 pair tiles, gate_up fwd shape)",
                          "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
                          "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": traffic, "traffic_detail": traffic_detail},
+            "roofline_gemm_longk": [
+                {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,MN-major> gate|up input gradient dh = dgu Wgu (M=T, N=d, K=2*ff)",
+                 "achieved": gemm_fl / dgrad_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                 "frac": gemm_fl / dgrad_ms / 1e9 / pk["bf16_tflops"], "ms": dgrad_ms},
+                {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,MN-major,MN-major> gate|up weight gradient dW = dgu^T h (M=2*ff, N=d, K=T)",
+                 "achieved": gemm_fl / wgrad_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                 "frac": gemm_fl / wgrad_ms / 1e9 / pk["bf16_tflops"], "ms": wgrad_ms}],
             "roofline_attention": [
                 {"bound": "tensor", "kernel": f"attn_fwd_tc_kernel<{dh}> (tcgen05 causal FlashAttention forward, one decoder layer)",
                  "achieved": attn_fl / af_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": attn_fl / af_ms / 1e9 / pk["bf16_tflops"],
@@ -390,6 +447,22 @@ def run_b200(args):
                  "frac": 2.5 * attn_fl / ab_ms / 1e9 / pk["bf16_tflops"], "ms": ab_ms}],
             "clocks": clocks,
         }
+        if world == 1 and args.model == "7b" and not args.no_library_baseline:
+            # the stock library stack on the same GPU (bench_library.py): the engine's arenas are released first
+            try:
+                model = eng = dev_inputs = a = wgu = out = dgu = dh2 = gw = q_ = k_ = v_ = lse = delta = None   # noqa: F841
+                trainer = opt = step_dev = step_e2e = step_plugin = None                                    # noqa: F841
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                import bench_library
+                from types import SimpleNamespace
+                lib = bench_library.run_library(SimpleNamespace(steps=min(args.steps, 3), warmup=2))
+                line["gpu_library_baseline"] = {"value": lib["value"], "unit": UNIT, "ms_per_step": lib["ms_per_step"],
+                                                "e2e_value": lib["e2e"]["value"], "stack": lib["config"]["stack"],
+                                                "versions": {k: lib["config"].get(k) for k in ("transformers", "torch")}}
+            except Exception as e:  # a baseline that cannot run must not take the measurement down with it
+                line["gpu_library_baseline"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
         if world == 1 and not args.no_cpu_baseline:
             cores = host_threads()
             sec, parts = cpu_sample_seconds_per_pair(cores)
@@ -631,12 +704,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--model", default="7b", choices=["7b", "small", "tiny", "next7b", "next_small", "qwen7b", "qwen_small", "xc2_7b", "xc2_small",
                                                    "7b_lora", "next7b_lora", "small_lora", "next_small_lora"],
                     help="7b = the benchmark (configs[1]); next7b = configs[3] LLaVA-Next-Mistral-7B DDPO, qwen7b = configs[2] Qwen-VL-Chat LoRA (side measurements)")
     ap.add_argument("--loss-type", dest="loss_type", default="sigmoid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock transformers+SDPA+AdamW arm on the same GPU")
+    ap.add_argument("--skip-plugin", action="store_true", help="skip the e2e_plugin measurement (the Trainer-side boundary)")
     ap.add_argument("--checkpointing", action="store_true", help="activation checkpointing (the *_lora side measurements)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--pack", action="store_true",
@@ -644,6 +719,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "library":
+        import bench_library
+        line = bench_library.run_library(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
     else:
         run_b200(args)
 

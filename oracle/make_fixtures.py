@@ -277,6 +277,9 @@ def main():
     ap.add_argument("--config1-bf16", dest="config1_bf16", action="store_true")
     ap.add_argument("--next", action="store_true", help="only the LLaVA-Next fixtures (g6_*)")
     ap.add_argument("--config4", action="store_true", help="LLaVA-Next-Mistral-7B shapes, DDPO (BASELINE.json configs[3])")
+    ap.add_argument("--config2", action="store_true", help="LLaVA-1.5-7B at the FULL headline length: 1 pair, text 1024 -> 1599 merged")
+    ap.add_argument("--config3", action="store_true", help="Qwen-VL-Chat 7B shapes + LoRA r 64 (BASELINE.json configs[2])")
+    ap.add_argument("--config5", action="store_true", help="InternLM-XComposer2-VL-7B shapes + PLoRA/LoRA, KTO (configs[4])")
     ap.add_argument("--preprocess", action="store_true", help="only the CLIP image-preprocessing fixture (g7)")
     ap.add_argument("--qwen", action="store_true", help="only the Qwen-VL + LoRA fixtures (g9_*)")
     ap.add_argument("--xc2", action="store_true", help="only the InternLM-XComposer2 + PLoRA/LoRA fixtures (g10_*)")
@@ -298,6 +301,17 @@ def main():
         # BASELINE.json configs[3] at parity size: Mistral-7B decoder + CLIP-L/336 anyres, 1 pair, text 96, one wide
         # image (1x2 grid -> 3 crops, unpadded), DDPO token weights, fp32 CPU
         g45_llava("g8_config4_next7b", R.LLAVANEXT_MISTRAL_7B, 1, 96, 24, 0, ddpo=True, image_sizes=[(400, 640)])
+        return
+    if args.config2:
+        # BASELINE.json configs[1] at its full sequence length (the headline bench shape): ONE pair, text 1024 (+575 image
+        # rows -> 1599 merged), prompt 128, fp32 CPU -- oracle values for the shape the bench runs, not only properties
+        g45_llava("g14_config2_full_7b", R.LLAVA15_7B, 1, 1024, 128, 0, ddpo=False)
+        return
+    if args.config3:
+        g12_qwen7b()
+        return
+    if args.config5:
+        g13_xc2_7b()
         return
     if args.preprocess:
         g7_clip_preprocess()
@@ -376,11 +390,14 @@ def build_reference_qwen(qcfg, base_w):
                                 patch_size=qcfg.patch_size, width=qcfg.v_width, n_queries=qcfg.n_queries))
     m = QwenVLForRL(hc)
     sd = m.state_dict()
-    assert set(sd) == set(base_w), (sorted(set(sd) ^ set(base_w))[:8])
-    with torch.no_grad():
-        for k, v in base_w.items():
-            assert sd[k].shape == v.shape, k
+    seen = set()
+    with torch.no_grad():   # base_w: dict, or an iterator of (name, tensor) (7B shapes: one tensor in flight)
+        for k, v in (base_w.items() if isinstance(base_w, dict) else base_w):
+            assert k in sd and sd[k].shape == v.shape, k
             sd[k].copy_(v)
+            seen.add(k)
+            del v
+    assert set(sd) == seen, (sorted(set(sd) ^ seen)[:8])
         # Resampler.pos_embed is a non-trainable sincos table built in __init__ (visual.py:112-114); keep it
     # transformers 5.x dropped ModuleUtilsMixin.get_head_mask; 4.41 returns [None] * n for head_mask=None
     m.transformer.get_head_mask = lambda head_mask, n, *a, **k: [None] * n
@@ -392,13 +409,37 @@ def g9_qwen():
     """Qwen-VL + LoRA (BASELINE.json configs[2] at parity size): reference QwenVLForRL.forward with the adapters on
     (policy) and off (reference), VLDPOTrainer.get_batch_logps / dpo_loss on top."""
     from oracle import qwen_restate as Q
+    _qwen_cases((("g9_qwen_tiny", Q.TINY_QWEN, 2, 48, 24), ("g9_qwen_small", Q.SMALL_QWEN, 2, 128, 72)))
+
+
+def g12_qwen7b():
+    """BASELINE.json configs[2] at 7B SHAPES (Qwen-VL-Chat: ViT-bigG 48 x 1664 with 104-wide heads, 256-query resampler,
+    32 x 4096 LM, V = 151936, LoRA r 64 alpha 16 on c_attn / attn.c_proj / w1 / w2): the reference's vendored QwenVLForRL in
+    fp32 on the CPU, ONE pair, text 352 (prompt 272 incl. the 258-token image span), adapters off = reference pass."""
+    from oracle import qwen_restate as Q
+    _qwen_cases((("g12_config3_qwen7b", Q.QWEN_VL_CHAT, 1, 352, 272),), stream=True)
+
+
+def _stream_specs(specs, seed):
+    for n, sh, sc, sf in specs:
+        yield n, R.bf16_round(R.hash_uniform(int(np.prod(sh)), R.tensor_seed(n, seed), sc, sf)).reshape(sh)
+
+
+def _qwen_cases(cases, stream=False):
+    from oracle import qwen_restate as Q
     VLDPOTrainer, _, _ = ref_shim.reference_symbols()
-    for tag, qcfg, n_pairs, text_len, prompt_len in (("g9_qwen_tiny", Q.TINY_QWEN, 2, 48, 24),
-                                                     ("g9_qwen_small", Q.SMALL_QWEN, 2, 128, 72)):
+    for tag, qcfg, n_pairs, text_len, prompt_len in cases:
         seed = 0
-        base_w, lora_w = Q.make_weights(qcfg, seed)
-        m = build_reference_qwen(qcfg, {k: v for k, v in base_w.items()} | {
-            "transformer.visual.attn_pool.pos_embed": Q.sincos_2d(qcfg.hidden, int(qcfg.n_queries ** 0.5))})
+        t0 = time.time()
+        pos = {"transformer.visual.attn_pool.pos_embed": Q.sincos_2d(qcfg.hidden, int(qcfg.n_queries ** 0.5))}
+        if stream:   # 9.6 G fp32 parameters: never hold a second copy
+            import itertools
+            lora_w = Q._make(Q.lora_specs(qcfg), seed)
+            m = build_reference_qwen(qcfg, itertools.chain(_stream_specs(Q.weight_specs(qcfg), seed), pos.items()))
+            print(f"[{tag}] weights ready {time.time() - t0:.1f}s", flush=True)
+        else:
+            base_w, lora_w = Q.make_weights(qcfg, seed)
+            m = build_reference_qwen(qcfg, {k: v for k, v in base_w.items()} | pos)
         batch = Q.make_batch(qcfg, n_pairs, text_len, prompt_len, seed, ddpo_like=True)
         cb = R.concatenated_inputs(batch, -100, 0)
         pixels = cb["concatenated_img_input_dict"]["pixel_values"]
@@ -429,6 +470,8 @@ def g9_qwen():
                 out["policy_logits_mean_rejected"] = logits[n_pairs:].mean().numpy()
                 if logits.numel() < 2_000_000:
                     out["policy_logits"] = logits.numpy()
+            print(f"[{tag}] {who} forward done {time.time() - t0:.1f}s", flush=True)
+            del o, logits
         n = n_pairs
         for lt in ("sigmoid", "ipo", "hinge", "kto_pair", "ddpo"):
             sfx = "_ddpo" if lt == "ddpo" else ""
@@ -437,6 +480,7 @@ def g9_qwen():
             out[f"{lt}_losses"], out[f"{lt}_cr"], out[f"{lt}_rr"] = l.numpy(), c.numpy(), r.numpy()
         np.savez_compressed(os.path.join(GOLDEN, f"{tag}.npz"), **out)
         print(tag, {k: v for k, v in out.items() if k.endswith("logps") or k == "sigmoid_losses"}, flush=True)
+        del m
 
 
 class _LoraOverPLoRA(torch.nn.Module):
@@ -499,14 +543,16 @@ def build_reference_xc2(xcfg, base_w):
     m = InternLMXC2ForRL(c)
     BM.PLoRA.__init__ = orig_plora_init
     sd = m.state_dict()
-    missing = [k for k in base_w if k not in sd]
-    assert not missing, missing[:5]
-    with torch.no_grad():
-        for k, v in base_w.items():
+    seen = set()
+    with torch.no_grad():   # base_w: dict, or an iterator of (name, tensor) (7B shapes: one tensor in flight)
+        for k, v in (base_w.items() if isinstance(base_w, dict) else base_w):
+            assert k in sd, k
             assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
             sd[k].copy_(v)
+            seen.add(k)
+            del v
         for k in sd:
-            if k not in base_w:
+            if k not in seen:
                 assert "post_layernorm" in k or "position_ids" in k, k
                 if "post_layernorm" in k:
                     sd[k].fill_(1.0 if k.endswith("weight") else 0.0)
@@ -520,11 +566,30 @@ def g10_xc2():
     """InternLM-XComposer2-VL + PLoRA + LoRA (BASELINE.json configs[4] at parity size): policy = adapters on, reference =
     adapters off (the frozen PLoRA image-token adapters stay on in both), DPO / DDPO / KTO-pair losses on top."""
     from oracle import xc2_restate as X
+    _xc2_cases((("g10_xc2_tiny", X.TINY_XC2, 2, 24, 8), ("g10_xc2_small", X.SMALL_XC2, 2, 96, 24)))
+
+
+def g13_xc2_7b():
+    """BASELINE.json configs[4] at 7B SHAPES (internlm-xcomposer2-vl-7b: CLIP-L/14 at 490 px -> 1225 image rows, InternLM2-7B
+    GQA 32/8 with the per-group interleaved wqkv, PLoRA r 256 on the image rows of all five linears, trainable LoRA r 64):
+    the reference's InternLMXC2ForRL in fp32 on the CPU, ONE pair, text 96 (S = 1320), KTO-pair / DPO / DDPO losses."""
+    from oracle import xc2_restate as X
+    _xc2_cases((("g13_config5_xc2_7b", X.XC2_VL_7B, 1, 96, 24),), stream=True)
+
+
+def _xc2_cases(cases, stream=False):
+    from oracle import xc2_restate as X
     VLDPOTrainer, _, _ = ref_shim.reference_symbols()
-    for tag, xcfg, n_pairs, text_len, prompt_len in (("g10_xc2_tiny", X.TINY_XC2, 2, 24, 8), ("g10_xc2_small", X.SMALL_XC2, 2, 96, 24)):
+    for tag, xcfg, n_pairs, text_len, prompt_len in cases:
         seed = 0
-        base_w, lora_w = X.make_weights(xcfg, seed)
-        m = build_reference_xc2(xcfg, base_w)
+        t0 = time.time()
+        if stream:
+            lora_w = X._make(X.lora_specs(xcfg), seed)
+            m = build_reference_xc2(xcfg, _stream_specs(X.weight_specs(xcfg), seed))
+            print(f"[{tag}] weights ready {time.time() - t0:.1f}s", flush=True)
+        else:
+            base_w, lora_w = X.make_weights(xcfg, seed)
+            m = build_reference_xc2(xcfg, base_w)
         batch = R.make_batch(xcfg, n_pairs, text_len, prompt_len, seed, ddpo_like=True)
         cb = R.concatenated_inputs(batch, -100, 0)
         out = {"seed": seed, "n_pairs": n_pairs, "text_len": text_len, "prompt_len": prompt_len}

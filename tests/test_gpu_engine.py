@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from oracle import restate as R
+from tests import parity_log
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
@@ -80,16 +81,10 @@ def test_forward_logps_and_loss_parity(pkg, tag):
         assert np.array_equal(m.labels.cpu().numpy(), d["labels"])
         src = m.src_map.view(m.n_seq, m.S)
         assert np.array_equal(((src < 0) & (src != -(2 ** 31))).cpu().numpy(), d["image_position_map"])
-    pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
-    # golden = reference LlavaForRL.forward + get_batch_logps (fp32 CPU)
-    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
-    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
-    # margins are differences of ~1e2..1e3-sized log-probs: compare losses/rewards with an absolute slack tied
-    # to the 1e-3 relative bound on the log-probs themselves
+    # golden = reference LlavaForRL.forward + get_batch_logps + dpo_loss (fp32 CPU); log-probs 1e-3 relative, losses and
+    # rewards to the absolute error measured on a B200 x2 (tests/parity_log.py, profiles/parity_r2.md)
+    pol, ref = parity_log.check_step(tag, out, d)
     slack = 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["sigmoid_losses"], atol=slack)
-    np.testing.assert_allclose(out.chosen_rewards.cpu().numpy(), d["sigmoid_cr"], atol=slack)
-    np.testing.assert_allclose(out.rejected_rewards.cpu().numpy(), d["sigmoid_rr"], atol=slack)
     # same comparison against the oracle restatement run here (CPU fp32)
     wp, wr = R.make_policy_and_ref(rcfg, int(d["seed"]))
     with torch.no_grad():
@@ -197,17 +192,10 @@ def test_config1_7b_shapes_logps_and_loss_parity(pkg):
     ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
     out = eng.step(ids, am, lb, px, train=False)
     pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
-    print("config1 policy logps", pol, "golden", d["policy_logps"], "rel", np.abs(pol / d["policy_logps"] - 1))
-    print("config1 ref    logps", ref, "golden", d["ref_logps"], "rel", np.abs(ref / d["ref_logps"] - 1))
-    if "policy_logps_refdtype_bf16" in d.files:
-        print("reference's own bf16 path vs its fp32 path: rel", np.abs(d["policy_logps_refdtype_bf16"] / d["policy_logps"] - 1))
-    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
-    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
-    # per-pair loss / rewards: margins are differences of ~1e3-sized log-probs, each good to 1e-3 relative
-    slack = 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["sigmoid_losses"], atol=slack)
-    acc_want = (d["sigmoid_cr"] > d["sigmoid_rr"]).mean()
-    assert abs(float(out.stats[1]) - acc_want) < 1e-6
+    if "policy_logps_refdtype_bf16" in d.files:   # the noise floor of the reference's own bf16 deployment, for the table
+        parity_log.record("g5_config1_7b", "REFERENCE bf16 vs its fp32 (policy_logps)", d["policy_logps_refdtype_bf16"],
+                          d["policy_logps"], note="the reference's own bf16 path, not ours")
+    parity_log.check_step("g5_config1_7b", out, d)
     del eng
     torch.cuda.empty_cache()
 
@@ -312,8 +300,36 @@ def test_config4_next7b_shapes_ddpo_parity(pkg):
             assert (np.abs(pol - d[key]) <= 1e-3 * np.abs(d["policy_logps"])).all()
             assert (np.abs(ref - d[rkey]) <= 1e-3 * np.abs(d["ref_logps"])).all()
             assert np.abs(pol / d[key] - 1).max() < 5e-3
-    slack = 0.1 * 1e-3 * np.abs(d["policy_logps_ddpo"]).max() * 4
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["ddpo_losses"], atol=slack)
+    b = parity_log.LOSS_ABS_BOUNDS.get("g8_config4_next7b", 0.1 * 1e-3 * np.abs(d["policy_logps_ddpo"]).max() * 4)
+    parity_log.record("g8_config4_next7b", "ddpo_losses", out.losses.cpu().numpy(), d["ddpo_losses"], bound_abs=b)
+    del eng
+    torch.cuda.empty_cache()
+
+
+def test_config2_full_length_7b_parity(pkg):
+    """BASELINE.json configs[1] -- the headline bench shape -- at its FULL sequence length: LLaVA-1.5-7B shapes, ONE pair,
+    text 1024 -> 1599 merged rows, against the reference's LlavaForRL.forward + get_batch_logps + dpo_loss run in fp32 on the
+    CPU (tests/golden/g14_config2_full_7b.npz, oracle/make_fixtures.py --config2).  ~900 labelled tokens per sequence."""
+    config, engine, host, ops = pkg
+    path = os.path.join(G, "g14_config2_full_7b.npz")
+    if not os.path.exists(path):
+        pytest.skip("g14 fixture not generated yet (oracle/make_fixtures.py --config2)")
+    d = np.load(path)
+    rcfg = R.LLAVA15_7B
+    eng = engine.LlavaDPOEngine(config.LLAVA15_7B, config.TrainConfig(), with_optimizer=False)
+    eng.init_synthetic(int(d["seed"]))
+    batch = R.make_batch(rcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]))
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb, px, _ = stage(eng, host, cb, rcfg)
+    assert ids.shape[1] == 1024
+    out = eng.step(ids, am, lb, px, train=False)
+    assert eng._bufs["s.x0"].shape[0] == 2 * 1599
+    parity_log.check_step("g14_config2_full_7b", out, d)
+    # the same batch as packed rows (f-2): identical log-probs to the padded layout, still within the bound
+    eng.tc.pack_sequences = True
+    seq_lens = eng.host_seq_lens(cb["concatenated_input_ids"], cb["concatenated_attention_mask"])
+    outp = eng.step(ids, am, lb, px, train=False, seq_lens=seq_lens)
+    parity_log.record("g14_config2_full_7b", "packed policy_logps", outp.policy_logps.cpu().numpy(), d["policy_logps"], bound_rel=1e-3)
     del eng
     torch.cuda.empty_cache()
 

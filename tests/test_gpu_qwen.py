@@ -8,10 +8,14 @@ import torch
 
 from oracle import qwen_restate as Q
 from oracle import restate as R
+from tests import parity_log
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
-CASES = {"g9_qwen_tiny": ("TINY_QWEN", Q.TINY_QWEN), "g9_qwen_small": ("SMALL_QWEN", Q.SMALL_QWEN)}
+CASES = {"g9_qwen_tiny": ("TINY_QWEN", Q.TINY_QWEN), "g9_qwen_small": ("SMALL_QWEN", Q.SMALL_QWEN),
+         # BASELINE.json configs[2] at 7B shapes (ViT-bigG 48 x 1664 / dh 104, V 151936, LoRA r 64): forward parity only
+         "g12_config3_qwen7b": ("QWEN_VL_CHAT", Q.QWEN_VL_CHAT)}
+SMALL_TAGS = ["g9_qwen_tiny", "g9_qwen_small"]
 
 
 @pytest.fixture(scope="module")
@@ -24,6 +28,8 @@ def pkg():
 def build(pkg, tag, loss_type="sigmoid", with_optimizer=False, **tc):
     config, EQ, host, ops = pkg
     name, qcfg = CASES[tag]
+    if not os.path.exists(os.path.join(G, tag + ".npz")):
+        pytest.skip(f"{tag} fixture not generated yet (oracle/make_fixtures.py --config3)")
     d = np.load(os.path.join(G, tag + ".npz"))
     eng = EQ.QwenVLDPOEngine(getattr(config, name), config.TrainConfig(loss_type=loss_type, learning_rate=1e-3, **tc),
                              with_optimizer=with_optimizer)
@@ -87,7 +93,7 @@ def test_qwen_merge_kernel_matches_mock(pkg):
         eng.check_merge_status(st)
 
 
-@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("tag", SMALL_TAGS)
 def test_qwen_weights_bit_exact_and_visual_tower(pkg, tag):
     config, EQ, host, ops = pkg
     eng, qcfg, d, batch = build(pkg, tag)
@@ -114,23 +120,20 @@ def test_qwen_forward_logps_loss_and_ddpo_parity(pkg, tag):
     ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
     px = cb["concatenated_img_input_dict"]["pixel_values"]
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
-    pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
-    print(f"[{tag}] policy rel err", np.abs(pol / d["policy_logps"] - 1), "ref rel err", np.abs(ref / d["ref_logps"] - 1))
-    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
-    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
-    slack = 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["sigmoid_losses"], atol=slack)
-    np.testing.assert_allclose(out.chosen_rewards.cpu().numpy(), d["sigmoid_cr"], atol=slack)
+    parity_log.check_step(tag, out, d)
     wt = eng.ddpo_weights(ids, am, lb)
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px, wt), train=False)
     # DDPO sums a subset of the same per-token terms: absolute error bounded by the full sum's 1e-3 budget
     for got, key, full in ((out.policy_logps, "policy_logps_ddpo", "policy_logps"), (out.ref_logps, "ref_logps_ddpo", "ref_logps")):
         err = np.abs(got.cpu().numpy() - d[key])
-        print(f"[{tag}] {key} abs err", err, "budget", 1e-3 * np.abs(d[full]), "values", d[key])
+        parity_log.record(tag, key, got.cpu().numpy(), d[key], note="subset of the per-token terms; bound = 1e-3 x |full sum|")
         assert (err <= 1e-3 * np.abs(d[full])).all(), (key, err)
+    if tag.startswith("g12"):
+        del eng
+        torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("tag", list(CASES))
+@pytest.mark.parametrize("tag", SMALL_TAGS)
 def test_qwen_adapter_gradients_match_oracle_autograd(pkg, tag):
     config, EQ, host, ops = pkg
     res = {}

@@ -8,10 +8,12 @@ import torch
 
 from oracle import restate as R
 from oracle import xc2_restate as X
+from tests import parity_log
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {"g10_xc2_tiny": ("TINY_XC2", X.TINY_XC2), "g10_xc2_small": ("SMALL_XC2", X.SMALL_XC2)}
+SMALL_TAGS = list(CASES)
 
 
 @pytest.fixture(scope="module")
@@ -60,19 +62,49 @@ def test_xc2_weights_and_forward_parity(pkg, tag):
     ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
     px = cb["concatenated_img_input_dict"]["pixel_values"]
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
-    pol, ref = out.policy_logps.cpu().numpy(), out.ref_logps.cpu().numpy()
-    print(f"[{tag}] policy rel err", np.abs(pol / d["policy_logps"] - 1), "ref rel err", np.abs(ref / d["ref_logps"] - 1))
-    np.testing.assert_allclose(pol, d["policy_logps"], rtol=1e-3)
-    np.testing.assert_allclose(ref, d["ref_logps"], rtol=1e-3)
-    slack = 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["sigmoid_losses"], atol=slack)
+    parity_log.check_step(tag, out, d)
     wt = eng.ddpo_weights(ids, am, lb)
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px, wt), train=False)
     for got, key, full in ((out.policy_logps, "policy_logps_ddpo", "policy_logps"), (out.ref_logps, "ref_logps_ddpo", "ref_logps")):
         assert (np.abs(got.cpu().numpy() - d[key]) <= 1e-3 * np.abs(d[full])).all(), key
     eng.tc.loss_type = "kto_pair"
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
-    np.testing.assert_allclose(out.losses.cpu().numpy(), d["kto_pair_losses"], atol=slack)
+    b = parity_log.LOSS_ABS_BOUNDS.get(tag, 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4)
+    parity_log.record(tag, "kto_pair_losses", out.losses.cpu().numpy(), d["kto_pair_losses"], bound_abs=b)
+
+
+def test_config5_xc2_7b_shapes_parity(pkg):
+    """BASELINE.json configs[4] at 7B SHAPES: internlm-xcomposer2-vl-7b (CLIP-L/14 at 490 px -> 1225 image rows, InternLM2-7B
+    GQA 32/8 with interleaved wqkv, PLoRA r 256 on the image rows, LoRA r 64), ONE pair, text 96 -> S = 1320, KTO-pair and DDPO
+    on top -- against the reference's InternLMXC2ForRL run in fp32 on the CPU (tests/golden/g13_config5_xc2_7b.npz)."""
+    config, EX, host, ops = pkg
+    tag = "g13_config5_xc2_7b"
+    if not os.path.exists(os.path.join(G, tag + ".npz")):
+        pytest.skip("g13 fixture not generated yet (oracle/make_fixtures.py --config5)")
+    d = np.load(os.path.join(G, tag + ".npz"))
+    xcfg = X.XC2_VL_7B
+    eng = EX.XC2DPOEngine(config.XC2_VL_7B, config.TrainConfig(), with_optimizer=False)
+    eng.init_synthetic(int(d["seed"]))
+    batch = R.make_batch(xcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    px = cb["concatenated_img_input_dict"]["pixel_values"]
+    out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
+    parity_log.check_step(tag, out, d)
+    m = ops.llava_merge_index(ids.cuda(), am.cuda(), lb.cuda(), xcfg.n_patches, px.shape[0] // 2, 1, xcfg.image_token_index,
+                              xcfg.pad_token_id)
+    assert np.array_equal(m.labels.cpu().numpy(), d["labels"])                      # integer work: bit-exact
+    wt = eng.ddpo_weights(ids, am, lb)
+    outd = eng.step(*eng.prepare_inputs(ids, am, lb, px, wt), train=False)
+    for got, key, full in ((outd.policy_logps, "policy_logps_ddpo", "policy_logps"), (outd.ref_logps, "ref_logps_ddpo", "ref_logps")):
+        parity_log.record(tag, key, got.cpu().numpy(), d[key], note="subset of the per-token terms; bound = 1e-3 x |full sum|")
+        assert (np.abs(got.cpu().numpy() - d[key]) <= 1e-3 * np.abs(d[full])).all(), key
+    eng.tc.loss_type = "kto_pair"
+    out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
+    b = parity_log.LOSS_ABS_BOUNDS.get(tag, 0.1 * 1e-3 * np.abs(d["policy_logps"]).max() * 4)
+    parity_log.record(tag, "kto_pair_losses", out.losses.cpu().numpy(), d["kto_pair_losses"], bound_abs=b)
+    del eng
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("tag", list(CASES))
