@@ -3,7 +3,7 @@
 # and the long-K raster A/B (VLB200_RASTER_POLICY=model vs default) on the same box.
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r2.jsonl
-timeout 1200 python -m pytest tests -m gpu -q --maxfail=8 -s > gpurun_out/r2a_tests.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q --maxfail=40 -s > gpurun_out/r2a_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2a_tests.log
 tail -25 gpurun_out/r2a_tests.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err

@@ -18,6 +18,8 @@ def record(case: str, quantity: str, got, want, bound_abs: float = None, bound_r
     err = np.abs(g - w)
     abs_err = float(err.max()) if err.size else 0.0
     rel_err = float((err / np.maximum(np.abs(w), 1e-30)).max()) if err.size else 0.0
+    bound_abs = None if bound_abs is None else float(bound_abs)
+    bound_rel = None if bound_rel is None else float(bound_rel)
     line = {"case": case, "quantity": quantity, "n": int(g.size), "max_abs_err": abs_err, "max_rel_err": rel_err,
             "want_absmax": float(np.abs(w).max()) if w.size else 0.0, "bound_abs": bound_abs, "bound_rel": bound_rel,
             "note": note}
@@ -58,6 +60,13 @@ def check_step(case: str, out, d, loss_key: str = "sigmoid", beta: float = 0.1, 
     record(case, f"{loss_key}_rejected_rewards", out.rejected_rewards.float().cpu().numpy(), d[f"{loss_key}_rr"], bound_abs=b, note=note)
     n = d[f"{loss_key}_cr"].shape[0]
     record(case, f"{loss_key}_loss_mean", [float(out.stats[0])], [float(np.mean(d[f"{loss_key}_losses"]))], bound_abs=b, note=note)
-    acc = float((d[f"{loss_key}_cr"] > d[f"{loss_key}_rr"]).mean())
-    record(case, f"{loss_key}_reward_accuracy", [float(out.stats[1])], [acc], bound_abs=1e-6)
+    # reward accuracy = fraction of pairs with chosen reward > rejected reward: exact wherever the golden margin is clear of
+    # the rewards' own error bound; a pair whose golden margin is inside that bound may fall either way
+    margin = np.asarray(d[f"{loss_key}_cr"], np.float64) - np.asarray(d[f"{loss_key}_rr"], np.float64)
+    sure = np.abs(margin) > 2 * b
+    got_sign = (out.chosen_rewards.float().cpu().numpy() > out.rejected_rewards.float().cpu().numpy())
+    assert (got_sign[sure] == (margin > 0)[sure]).all(), (case, "reward sign", margin, got_sign)
+    acc = float((margin > 0).mean())
+    record(case, f"{loss_key}_reward_accuracy", [float(out.stats[1])], [acc], bound_abs=float((~sure).sum()) / n + 1e-6,
+           note=f"{int((~sure).sum())} of {n} pairs have a golden margin inside the reward error bound")
     return pol, ref

@@ -205,8 +205,12 @@ def test_merge_validity_errors(pkg):
     eng, rcfg, d, batch, cb = build(pkg, "g4_tiny", with_optimizer=False)
     ids = cb["concatenated_input_ids"].clone()
     ids[0, 3] = rcfg.image_token_index  # a second image token in one sequence only
-    a, b, c, px, _ = eng.prepare_inputs(ids, cb["concatenated_attention_mask"], cb["concatenated_labels"],
-                                        cb["concatenated_img_input_dict"]["pixel_values"])
+    with pytest.raises(ValueError, match="number of image tokens"):   # host batches are refused before any device work
+        eng.prepare_inputs(ids, cb["concatenated_attention_mask"], cb["concatenated_labels"],
+                           cb["concatenated_img_input_dict"]["pixel_values"])
+    # device-resident batches skip the host check: the merge kernel's status word carries the same verdict
+    a, b, c, px, _ = eng.prepare_inputs(ids.cuda(), cb["concatenated_attention_mask"].cuda(), cb["concatenated_labels"].cuda(),
+                                        cb["concatenated_img_input_dict"]["pixel_values"].cuda())
     m = ops.llava_merge_index(a, b, c, rcfg.n_patches, px.shape[0], 1, rcfg.image_token_index, rcfg.pad_token_id)
     with pytest.raises(ValueError):
         eng.check_merge_status(m)

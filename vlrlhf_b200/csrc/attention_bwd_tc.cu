@@ -39,6 +39,10 @@ struct Params {
     const float* delta;  // [B, H, S]
     const int* seqlens;
     const int* row_starts;  // [B] or null: first row of each sequence (ragged / packed rows); null: b*S
+    // shared-prefix attention (packed rows only; see vlb200_attn_fwd_tc_ctx): ctx[b] >= 0 names the sequence whose keys/values
+    // every query of sequence b also sees; kids[2*b], kids[2*b+1] (or -1) are the sequences that name b as their context
+    const int* ctx;
+    const int* kids;
     __nv_bfloat16* out1; long long ld1;  // MODE 0: dV ; MODE 1: unused
     __nv_bfloat16* out2; long long ld2;  // MODE 0: dK ; MODE 1: dQ
     int B, S, H, KVH, causal;
@@ -61,24 +65,66 @@ __device__ __forceinline__ void item_coords(const Params& p, int w, int& b, int&
     hx = bh % heads;
     b = bh / heads;
 }
-// streamed-tile range for one item: tiles [y_begin, y_end) of 64 rows, repeated for `reps` heads (GQA group)
+// Streamed tiles of one item: up to three SEGMENTS of 64-row tiles, the whole list repeated for `reps` heads (GQA group).
+//   MODE 0 (stationary keys of sequence b):    seg 0 = b's own queries from the causal diagonal on,
+//                                              seg 1/2 = ALL queries of the sequences that use b as their context (no causal mask)
+//   MODE 1 (stationary queries of sequence b): seg 0 = ALL keys of b's context sequence (no causal mask),
+//                                              seg 1 = b's own keys up to the causal diagonal
+// A segment: tiles [yb, yb + n) of sequence `seq` (rows row0 + yt*64, `len` valid rows, statistics of `seq`).
+struct Seg { int n, yb, row0, len, seq, causal; };
+struct Item { Seg s[3]; int per_rep, reps, kv_len; };
+
 template <int MODE>
-__device__ __forceinline__ void item_range(const Params& p, int b, int xb, int& y_begin, int& y_end, int& reps) {
+__device__ __forceinline__ Item item_plan(const Params& p, int b, int xb) {
+    Item it;
     int kv_len = p.seqlens ? p.seqlens[b] : p.S;
     kv_len = max(min(kv_len, p.S), 0);
+    it.kv_len = kv_len;
     const int x0 = xb * BX;
+    const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) it.s[i] = Seg{0, 0, 0, 0, b, 0};
+    const bool live = x0 < kv_len;
     if (MODE == 0) {  // stationary keys [x0, x0+128); queries beyond kv_len have dO == 0
-        reps = p.H / p.KVH;
-        y_begin = p.causal ? x0 / BY : 0;
-        y_end = x0 < kv_len ? (kv_len + BY - 1) / BY : y_begin;
+        it.reps = p.H / p.KVH;
+        const int yb = p.causal ? x0 / BY : 0;
+        const int ye = live ? (kv_len + BY - 1) / BY : yb;
+        it.s[0] = Seg{max(ye - yb, 0), yb, row0, kv_len, b, p.causal};
+        if (p.kids != nullptr && live) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = p.kids[2 * b + k];
+                if (c >= 0) {
+                    const int len = max(min(p.seqlens[c], p.S), 0);
+                    it.s[1 + k] = Seg{(len + BY - 1) / BY, 0, p.row_starts[c], len, c, 0};
+                }
+            }
+        }
     } else {          // stationary queries; keys up to the causal diagonal / kv_len
-        reps = 1;
-        y_begin = 0;
+        it.reps = 1;
         int kmax = kv_len;
         if (p.causal) kmax = min(kmax, x0 + BX);
-        y_end = x0 < kv_len ? (kmax + BY - 1) / BY : 0;
+        const Seg self = Seg{live ? (kmax + BY - 1) / BY : 0, 0, row0, kv_len, b, p.causal};
+        if (p.ctx != nullptr && live && p.ctx[b] >= 0) {
+            const int c = p.ctx[b];
+            const int len = max(min(p.seqlens[c], p.S), 0);
+            it.s[0] = Seg{(len + BY - 1) / BY, 0, p.row_starts[c], len, c, 0};
+            it.s[1] = self;
+        } else {
+            it.s[0] = self;
+        }
     }
-    if (y_end < y_begin) y_end = y_begin;
+    it.per_rep = it.s[0].n + it.s[1].n + it.s[2].n;
+    return it;
+}
+// tile t of an item -> (segment, tile index inside the sequence, head repetition)
+__device__ __forceinline__ void item_tile(const Item& it, int t, Seg& sg, int& yt, int& rep) {
+    rep = t / it.per_rep;
+    int u = t - rep * it.per_rep;
+    if (u < it.s[0].n) { sg = it.s[0]; }
+    else if (u < it.s[0].n + it.s[1].n) { u -= it.s[0].n; sg = it.s[1]; }
+    else { u -= it.s[0].n + it.s[1].n; sg = it.s[2]; }
+    yt = sg.yb + u;
 }
 
 template <int DH, int MODE>
@@ -136,10 +182,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
         if (lane_idx == 0) {
             uint32_t item = 0, yc = 0;
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                int b, hx, xb, yb, ye, reps;
+                int b, hx, xb;
                 item_coords<MODE>(p, w, b, hx, xb);
-                item_range<MODE>(p, b, xb, yb, ye, reps);
-                const int n = (ye - yb) * reps;
+                const Item it = item_plan<MODE>(p, b, xb);
+                const int n = it.per_rep * it.reps;
                 if (n == 0) continue;
                 const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
                 const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
@@ -152,7 +198,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 }
                 for (int t = 0; t < n; ++t, ++yc) {
                     const int st = yc % NST;
-                    const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                    Seg sg; int yt, rep;
+                    item_tile(it, t, sg, yt, rep);
                     const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
                     mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
                     mbar_arrive_expect_tx(&y_full[st], 2 * Y_BYTES);
@@ -160,8 +207,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     uint8_t* y2 = y1 + Y_BYTES;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        tma_load_2d(&tma_y1, &y_full[st], y1 + c * YCH, ycol + c * 64, row0 + yt * BY);
-                        tma_load_2d(&tma_y2, &y_full[st], y2 + c * YCH, ycol + c * 64, row0 + yt * BY);
+                        tma_load_2d(&tma_y1, &y_full[st], y1 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
+                        tma_load_2d(&tma_y2, &y_full[st], y2 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
                     }
                 }
                 ++item;
@@ -174,10 +221,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
             uint32_t item = 0, yc = 0, tc = 0, ec = 0;
             for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                int b, hx, xb, yb, ye, reps;
+                int b, hx, xb;
                 item_coords<MODE>(p, w, b, hx, xb);
-                item_range<MODE>(p, b, xb, yb, ye, reps);
-                const int n = (ye - yb) * reps;
+                const Item it = item_plan<MODE>(p, b, xb);
+                const int n = it.per_rep * it.reps;
                 if (n == 0) continue;
                 mbar_wait(x_full, item & 1, 30);
                 tcgen05_fence_after();
@@ -258,12 +305,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
         const float sl2 = p.scale * LOG2E_F;
         uint32_t tc = 0, ec = 0;
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-            int b, hx, xb, yb, ye, reps;
+            int b, hx, xb;
             item_coords<MODE>(p, w, b, hx, xb);
-            item_range<MODE>(p, b, xb, yb, ye, reps);
-            const int n = (ye - yb) * reps;
-            int kv_len = p.seqlens ? p.seqlens[b] : p.S;
-            kv_len = max(min(kv_len, p.S), 0);
+            const Item it = item_plan<MODE>(p, b, xb);
+            const int n = it.per_rep * it.reps;
+            const int kv_len = it.kv_len;
             const int x0 = xb * BX;
             const int xrow = x0 + r;  // MODE 0: key index ; MODE 1: query index
             float row_lse2 = 0.f, row_delta = 0.f;
@@ -278,11 +324,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             float nl = 0.f, nd = 0.f;
             auto fetch_stats = [&](int t) {
                 if (MODE == 0 && tid_e < BY && t < n) {
-                    const int rep = t / (ye - yb), yt = yb + t % (ye - yb);
+                    Seg sg; int yt, rep;
+                    item_tile(it, t, sg, yt, rep);
                     const int q = yt * BY + tid_e;
-                    const long long si = ((long long)b * p.H + (hx * group + rep)) * p.S + q;
-                    nl = q < kv_len ? p.lse[si] * LOG2E_F : 0.f;
-                    nd = q < kv_len ? p.delta[si] : 0.f;
+                    const long long si = ((long long)sg.seq * p.H + (hx * group + rep)) * p.S + q;
+                    nl = q < sg.len ? p.lse[si] * LOG2E_F : 0.f;
+                    nd = q < sg.len ? p.delta[si] : 0.f;
                 }
             };
             if (MODE == 0 && n > 0) {
@@ -291,8 +338,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             }
             for (int t = 0; t < n; ++t, ++tc) {
                 const uint32_t tb = tc & 1;
-                const int yt = yb + t % (ye - yb);
+                Seg sg; int yt, rep_unused;
+                item_tile(it, t, sg, yt, rep_unused);
                 const int y0 = yt * BY;
+                const int ylen = sg.len;             // valid streamed rows of this tile's sequence
+                const bool causal_t = sg.causal != 0;
                 if (MODE == 0) {
                     asm volatile("bar.sync 1, 256;" ::: "memory");  // statistics of tile t are visible
                     fetch_stats(t + 1);                              // global loads for tile t+1 fly during this tile
@@ -309,8 +359,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 // mask only tiles that touch the causal diagonal or the end of the valid range
                 const int ymax = y0 + BY - 1;
                 bool need_mask;
-                if (MODE == 0) need_mask = ymax >= kv_len || x0 + BX > kv_len || (p.causal && x0 + BX - 1 > y0);
-                else need_mask = ymax >= kv_len || x0 + BX > kv_len || (p.causal && ymax > x0);
+                if (MODE == 0) need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && x0 + BX - 1 > y0);
+                else need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && ymax > x0);
                 const float* cl = sLse + tb * BY + half * 32;
                 const float* cd = sDelta + tb * BY + half * 32;
                 uint32_t e1[16], e2[16];
@@ -336,9 +386,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                             const int col = half * 32 + c4 + e;
                             float pr = ex2_approx(fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]));
                             if (MASKED) {
+                                // stationary index xrow < kv_len, streamed index y0 + col < ylen; causal inside a sequence only
                                 const int key = MODE == 0 ? xrow : y0 + col;
                                 const int qi = MODE == 0 ? y0 + col : xrow;
-                                if (!(key < kv_len && qi < kv_len && (!p.causal || key <= qi))) pr = 0.f;
+                                if (!(xrow < kv_len && y0 + col < ylen && (!causal_t || key <= qi))) pr = 0.f;
                             }
                             pv[e] = pr;
                             dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]) * p.scale;
@@ -492,14 +543,17 @@ extern "C" int vlb200_attn_delta(const void* out, int64_t ldo, const void* dout,
     return vlb200_attn_delta_varlen(out, ldo, dout, lddo, delta, nullptr, 0, B, S, H, head_dim, stream);
 }
 
-extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                         const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
-                                         float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
-                                         const int* seqlens, const int* row_starts, int64_t total_rows, int B, int S, int H,
-                                         int KVH, int head_dim, int causal, float scale, void* stream) {
+extern "C" int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                      float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                      const int* seqlens, const int* row_starts, const int* ctx, const int* kids,
+                                      int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal, float scale,
+                                      void* stream) {
     using namespace vlb;
     using namespace vlb::attn_bwd_tc;
     VLB_REQUIRE(q && k && v && out && dout && lse && delta && dq && dk && dv, "attn_bwd_tc: null pointer");
+    VLB_REQUIRE((ctx == nullptr) == (kids == nullptr), "attn_bwd_tc: ctx and kids come together");
+    VLB_REQUIRE(ctx == nullptr || (row_starts != nullptr && causal), "attn_bwd_tc: context sequences need packed rows and causal attention");
     VLB_REQUIRE(row_starts == nullptr || (seqlens != nullptr && total_rows > 0), "attn_bwd_tc: row_starts needs seqlens and total_rows");
     VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_bwd_tc: bad B/S/H/KVH");
     VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_bwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
@@ -519,7 +573,7 @@ extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void*
     if ((rc = gemm::get_tensor_map(k, kcols, rows, ldk, 64, BY, &yk))) return rc;
     if ((rc = gemm::get_tensor_map(v, kcols, rows, ldv, 64, BY, &yv))) return rc;
     Params p{};
-    p.lse = lse; p.delta = delta; p.seqlens = seqlens; p.row_starts = row_starts;
+    p.lse = lse; p.delta = delta; p.seqlens = seqlens; p.row_starts = row_starts; p.ctx = ctx; p.kids = kids;
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_xb = (S + BX - 1) / BX;
     cudaStream_t s = as_stream(stream);
@@ -532,6 +586,15 @@ extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void*
     p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq;
     p.n_work = p.n_xb * H * B;
     return head_dim == 64 ? launch<64, 1>(xq, xdo, yk, yv, p, s) : launch<128, 1>(xq, xdo, yk, yv, p, s);
+}
+
+extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                         const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                         float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                         const int* seqlens, const int* row_starts, int64_t total_rows, int B, int S, int H,
+                                         int KVH, int head_dim, int causal, float scale, void* stream) {
+    return vlb200_attn_bwd_tc_ctx(q, ldq, k, ldk, v, ldv, out, ldo, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, seqlens,
+                                  row_starts, nullptr, nullptr, total_rows, B, S, H, KVH, head_dim, causal, scale, stream);
 }
 
 extern "C" int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

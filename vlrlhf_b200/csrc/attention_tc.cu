@@ -35,6 +35,8 @@ struct Params {
     float* lse;          // [B, H, S] or null
     const int* seqlens;  // [B] or null
     const int* row_starts;  // [B] or null: first row of each sequence (ragged / packed rows); null: sequence b starts at b*S
+    const int* ctx;         // [B] or null: ctx[b] >= 0 names a sequence whose rows are extra keys/values visible to EVERY query of
+                            // sequence b (the shared prompt+image prefix of a chosen/rejected pair); they precede b's own keys
     int B, S, H, KVH, causal;
     float scale;
     int n_qb, n_work;
@@ -65,6 +67,25 @@ __device__ __forceinline__ int num_kv_tiles(const Params& p, int b, int qb) {
     int kmax = kv_len;
     if (p.causal) kmax = min(kmax, (qb + 1) * BM);
     return (kmax + BN - 1) / BN;
+}
+// KV tiles of one work item: n_ctx tiles of the context sequence (all keys visible), then n_self tiles of the sequence itself.
+// skip: packed rows only -- a query tile wholly beyond its sequence is neither computed nor stored (padded layouts keep
+// computing their padding rows: those are stored and must stay finite).
+struct KvPlan { int n_ctx, n_self, ctx_row0, ctx_len; bool skip; };
+__device__ __forceinline__ KvPlan kv_plan(const Params& p, int b, int qb) {
+    KvPlan k;
+    k.n_self = num_kv_tiles(p, b, qb);
+    k.n_ctx = 0; k.ctx_row0 = 0; k.ctx_len = 0;
+    k.skip = p.row_starts != nullptr && p.seqlens != nullptr && qb * BM >= p.seqlens[b];
+    if (p.ctx != nullptr && !k.skip) {
+        const int c = p.ctx[b];
+        if (c >= 0) {
+            k.ctx_len = max(min(p.seqlens[c], p.S), 0);
+            k.ctx_row0 = p.row_starts[c];
+            k.n_ctx = (k.ctx_len + BN - 1) / BN;
+        }
+    }
+    return k;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -125,11 +146,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         // ===================== TMA producer =====================
         if (lane_idx == 0) {
             uint32_t item = 0, g = 0;  // g = global KV-tile counter (ring position)
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 int b, h, qb;
                 work_coords(p, w, b, h, qb);
+                const KvPlan plan = kv_plan(p, b, qb);
+                if (plan.skip) continue;
                 const int kvh = h / (p.H / p.KVH);
-                const int n_tiles = num_kv_tiles(p, b, qb);
+                const int n_tiles = plan.n_ctx + plan.n_self;
                 const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
                 mbar_wait(q_empty, (item & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(q_full, Q_BYTES);
@@ -140,12 +163,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     mbar_wait(&kv_empty[st], ((g / NSTAGE) & 1) ^ 1, 20 + st);  // PV of the tile 3 back retired (K/P and V slots free)
                     mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
                     uint8_t* kp = sStage + st * STAGE_BYTES;
+                    const int krow = j < plan.n_ctx ? plan.ctx_row0 + j * BN : row0 + (j - plan.n_ctx) * BN;
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        tma_load_2d(&tma_k, &kv_full[st], kp + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
-                        tma_load_2d(&tma_v, &kv_full[st], kp + KP_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, row0 + j * BN);
+                        tma_load_2d(&tma_k, &kv_full[st], kp + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
+                        tma_load_2d(&tma_v, &kv_full[st], kp + KP_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
                     }
                 }
+                ++item;
             }
         }
     } else if (warp_idx == 1) {
@@ -154,10 +179,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
             uint32_t item = 0, g0 = 0, sc = 0;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
                 int b, h, qb;
                 work_coords(p, w, b, h, qb);
-                const int n_tiles = num_kv_tiles(p, b, qb);
+                const KvPlan plan = kv_plan(p, b, qb);
+                if (plan.skip) continue;
+                const int n_tiles = plan.n_ctx + plan.n_self;
                 mbar_wait(q_full, item & 1, 30);
                 tcgen05_fence_after();
                 // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
@@ -212,6 +239,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     }
                 }
                 g0 += n_tiles;
+                ++item;
             }
         }
     } else {
@@ -220,11 +248,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const int r = quad * 32 + lane_idx;  // row inside the Q tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        uint32_t item = 0, sc = 0, g = 0;  // g = global tile counter (== number of PVs issued for earlier tiles)
-        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x, ++item) {
+        uint32_t sc = 0, g = 0;  // g = global tile counter (== number of PVs issued for earlier tiles)
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int b, h, qb;
             work_coords(p, w, b, h, qb);
-            const int n_tiles = num_kv_tiles(p, b, qb);
+            const KvPlan plan = kv_plan(p, b, qb);
+            if (plan.skip) continue;
+            const int n_tiles = plan.n_ctx + plan.n_self;
             int kv_len = p.seqlens ? p.seqlens[b] : p.S;
             kv_len = max(kv_len, 1);
             const int qrow = qb * BM + r;
@@ -240,16 +270,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&s_empty[sb]);  // S buffer is in registers now
-                const int k0 = j * BN;
-                const bool need_mask = (k0 + BN > kv_len) || (p.causal && k0 + BN > qb * BM);
+                // context tiles: every key below ctx_len is visible; own tiles: keys below kv_len, up to the causal diagonal
+                const bool is_ctx = j < plan.n_ctx;
+                const int k0 = (is_ctx ? j : j - plan.n_ctx) * BN;
+                const int vlim = (is_ctx ? plan.ctx_len : kv_len) - k0;              // keys [0, vlim) of the tile exist
+                const int clim = (p.causal && !is_ctx) ? qrow - k0 : BN;             // keys [0, clim] of the tile are not in the future
+                const bool need_mask = vlim < BN || (p.causal && !is_ctx && k0 + BN > qb * BM);
                 float mx = -INFINITY;
                 if (need_mask) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int key = k0 + c * 32 + i;
-                            if (key >= kv_len || (p.causal && key > qrow)) sr[c][i] = 0xff800000u;  // -inf
+                            const int kk = c * 32 + i;
+                            if (kk >= vlim || kk > clim) sr[c][i] = 0xff800000u;  // -inf
                             mx = fmaxf(mx, __uint_as_float(sr[c][i]));
                         }
                     }
@@ -374,12 +408,13 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 }  // namespace attn_tc
 }  // namespace vlb
 
-extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                         void* out, int64_t ldo, float* lse, const int* seqlens, const int* row_starts,
-                                         int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal, float scale,
-                                         void* stream) {
+extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      void* out, int64_t ldo, float* lse, const int* seqlens, const int* row_starts,
+                                      const int* ctx, int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal,
+                                      float scale, void* stream) {
     using namespace vlb;
     VLB_REQUIRE(q && k && v && out, "attn_fwd_tc: null pointer");
+    VLB_REQUIRE(ctx == nullptr || (row_starts != nullptr && causal), "attn_fwd_tc: context sequences need packed rows and causal attention");
     VLB_REQUIRE(row_starts == nullptr || (seqlens != nullptr && total_rows > 0), "attn_fwd_tc: row_starts needs seqlens and total_rows");
     VLB_REQUIRE(B > 0 && S > 0 && H > 0 && KVH > 0 && H % KVH == 0, "attn_fwd_tc: bad B/S/H/KVH");
     VLB_REQUIRE(head_dim == 64 || head_dim == 128, "attn_fwd_tc: head_dim %d unsupported (64 or 128)", head_dim);
@@ -392,12 +427,20 @@ extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void*
     if ((rc = gemm::get_tensor_map(k, (uint64_t)KVH * head_dim, rows, ldk, 64, 128, &tk))) return rc;
     if ((rc = gemm::get_tensor_map(v, (uint64_t)KVH * head_dim, rows, ldv, 64, 128, &tv))) return rc;
     attn_tc::Params p{};
-    p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.seqlens = seqlens; p.row_starts = row_starts;
+    p.o = (__nv_bfloat16*)out; p.ldo = ldo; p.lse = lse; p.seqlens = seqlens; p.row_starts = row_starts; p.ctx = ctx;
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
     if (head_dim == 64) return attn_tc::launch<64>(tq, tk, tv, p, as_stream(stream));
     return attn_tc::launch<128>(tq, tk, tv, p, as_stream(stream));
+}
+
+extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                         void* out, int64_t ldo, float* lse, const int* seqlens, const int* row_starts,
+                                         int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal, float scale,
+                                         void* stream) {
+    return vlb200_attn_fwd_tc_ctx(q, ldq, k, ldk, v, ldv, out, ldo, lse, seqlens, row_starts, nullptr, total_rows, B, S, H, KVH,
+                                  head_dim, causal, scale, stream);
 }
 
 extern "C" int vlb200_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
