@@ -283,7 +283,7 @@ def run_b200(args):
     # built through the reference-facing wrapper (plugin.B200LlavaForRL: nn.Parameters that are views of the engine's arenas)
     from vlrlhf_b200 import plugin
     model = plugin.B200LlavaForRL(cfg, config.TrainConfig(loss_type=loss_type, activation_checkpointing=(args.model == "next7b"),
-                                                          pack_sequences=args.pack))
+                                                          pack_sequences=args.pack, share_prefix=args.share_prefix))
     eng = model.engine
     eng.init_synthetic(0)  # same weights on every rank
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)  # rank-local pairs
@@ -316,8 +316,10 @@ def run_b200(args):
         return float(ms) / steps
 
     # --pack (side measurement, SURVEY f-2): the padding rows of the ragged synthetic batch are dropped from every kernel
-    seq_lens = eng.host_seq_lens(ids_h, am_h, sizes_h) if args.pack else None
-    step_dev = lambda: eng.step(*dev_inputs, train=True, seq_lens=seq_lens)  # noqa: E731
+    # --share-prefix: one copy of every pair's prompt + image prefix; same log-probs / losses / gradients
+    plan = eng.host_row_plan(ids_h, am_h, sizes_h)
+    seq_lens = plan.get("seq_lens")
+    step_dev = lambda: eng.step(*dev_inputs, train=True, **plan)  # noqa: E731
     last = {}
 
     def step_e2e():
@@ -413,7 +415,9 @@ def run_b200(args):
                            WORKLOAD_NEXT if args.model == "next7b" else f"{args.model} (dev config, NOT the benchmark)"),
                        "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
                        "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
-                       "rows_per_step": (sum(seq_lens) if seq_lens else 2 * PAIRS_PER_GPU * S),
+                       "share_prefix": eng.tc.share_prefix,
+                       "rows_per_step": (sum(seq_lens) - sum(plan.get("prefix_rows", [])) if seq_lens else 2 * PAIRS_PER_GPU * S),
+                       "shared_prefix_rows_per_step": sum(plan.get("prefix_rows", [])),
                        "parallelism": (f"dp{world}: gradients reduce-scattered (NCCL), AdamW on each rank's 1/{world} slice (ZeRO-1), "
                                        f"parameters all-gathered; deferred to a side stream under the next reference pass")
                        if world > 1 else "dp1 (no collective)",
@@ -582,7 +586,7 @@ def run_b200_lora(args, cfg, world, rank, local):
     loss_type = "ddpo" if (is_next and args.loss_type == "sigmoid") else args.loss_type  # configs[3] is DDPO
     eng = engine_lora.LlavaLoRADPOEngine(cfg, config.TrainConfig(loss_type=loss_type, learning_rate=1e-5,
                                                                  activation_checkpointing=args.checkpointing,
-                                                                 pack_sequences=args.pack))
+                                                                 pack_sequences=args.pack, share_prefix=args.share_prefix))
     eng.init_synthetic(0)
     batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
     cb = host.concatenated_inputs(batch)
@@ -612,8 +616,8 @@ def run_b200_lora(args, cfg, world, rank, local):
         return float(ms) / steps
 
     last = {}
-    seq_lens = eng.host_seq_lens(ids_h, am_h, sizes_h) if args.pack else None
-    step_dev = lambda: eng.step(*dev_inputs, train=True, seq_lens=seq_lens)  # noqa: E731
+    plan = eng.host_row_plan(ids_h, am_h, sizes_h)
+    step_dev = lambda: eng.step(*dev_inputs, train=True, **plan)  # noqa: E731
     step_e2e = lambda: last.update(eng.train_step(batch, train=True))  # noqa: E731
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -649,6 +653,7 @@ def run_b200_lora(args, cfg, world, rank, local):
                                         f"({S} merged), 1x336px image/pair") if full else f"{args.model} (dev config, NOT the benchmark)",
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": loss_type,
                            "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
+                           "share_prefix": eng.tc.share_prefix, "shared_prefix_rows_per_step": sum(plan.get("prefix_rows", [])),
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
                            "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
@@ -714,6 +719,9 @@ def main():
     ap.add_argument("--skip-plugin", action="store_true", help="skip the e2e_plugin measurement (the Trainer-side boundary)")
     ap.add_argument("--checkpointing", action="store_true", help="activation checkpointing (the *_lora side measurements)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--share-prefix", dest="share_prefix", action="store_true",
+                    help="TrainConfig.share_prefix: the prompt + image prefix common to the chosen and rejected sequence of a pair is "
+                         "computed once (LLaVA-1.5 family)")
     ap.add_argument("--pack", action="store_true",
                     help="TrainConfig.pack_sequences (side measurement: padding rows dropped; the headline run keeps them, as the reference does)")
     args = ap.parse_args()

@@ -232,6 +232,20 @@ int vlb200_pack_merge_rows(const int* src_map, const int* position_ids, const in
                            int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,
                            void* stream);
 
+/* Shared-prefix rows (base/trainer.py:124-146 concatenates chosen and rejected on the batch axis, so the
+ * reference computes the prompt + image prefix of every pair twice per pass): sequence b (chosen b < n_seq/2, rejected of
+ * the same pair at b + n_seq/2) keeps its first prefix_rows[b] merged rows in ONE copy per pair at prefix_starts[b] (both
+ * arrays hold equal values for the two sequences of a pair) and its remaining seq_lens[b] - prefix_rows[b] rows at
+ * suffix_starts[b].  Same outputs and in-place rewrites as vlb200_pack_merge_rows; additionally the rejected copy of an
+ * img_pos entry that lies in the shared prefix becomes -1 (the row is counted once by vlb200_llava_merge_bwd_rows);
+ * row_of_text of both sequences points at the shared row (the head gathers it twice, its gradient is scatter-ADDED).
+ * Consumed with vlb200_attn_{fwd,bwd}_tc_ctx: attention sequences = {prefixes, chosen suffixes, rejected suffixes}.       */
+int vlb200_share_prefix_rows(const int* src_map, const int* position_ids, const int* prefix_rows, const int* prefix_starts,
+                             const int* suffix_starts, const int* seq_lens, int n_seq, int merged_len, int64_t total_rows,
+                             int* src_map_shared, int* position_ids_shared, int* row_of_text, int64_t n_text_rows,
+                             int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,
+                             void* stream);
+
 /* ---- LLaVA-Next text/image merge -- models/LlavaNext/__init__.py:38-171 (_merge_input_ids_with_image_features)
  * Differences from the LLaVA-1.5 merge above: image k contributes feat_off[k+1]-feat_off[k] PACKED feature rows
  * (anyres "spatial_unpad" + image_newline, modeling_llava_next.py pack_image_features; the row gather that builds
@@ -285,6 +299,20 @@ int vlb200_attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, c
 int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                               int64_t ldo, float* lse, const int* seqlens, const int* row_starts, int64_t total_rows, int B,
                               int S, int H, int KVH, int head_dim, int causal, float scale, void* stream);
+/* Context sequences ("tree" attention with one shared trunk): ctx[b] >= 0 names a sequence whose rows are additional keys /
+ * values visible to EVERY query of sequence b, logically before b's own keys (b's own keys stay causal).  kids[2*b],
+ * kids[2*b+1] (-1: none) list the sequences that name b as their context -- the backward of b's keys gathers their queries.
+ * With {prefix, chosen suffix, rejected suffix} as three sequences per pair this computes exactly the attention of the two
+ * full sequences while the shared prefix is stored, projected and attended once.  Packed rows + causal only.  lse / delta:
+ * [B, H, S] indexed by (sequence, head, row inside the sequence).  ctx == NULL: identical to the _varlen entry points. */
+int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                           int64_t ldo, float* lse, const int* seqlens, const int* row_starts, const int* ctx,
+                           int64_t total_rows, int B, int S, int H, int KVH, int head_dim, int causal, float scale, void* stream);
+int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
+                           int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
+                           void* dk, int64_t lddk, void* dv, int64_t lddv, const int* seqlens, const int* row_starts,
+                           const int* ctx, const int* kids, int64_t total_rows, int B, int S, int H, int KVH, int head_dim,
+                           int causal, float scale, void* stream);
 int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, const int* row_starts,
                              int64_t total_rows, int B, int S, int H, int head_dim, void* stream);
 int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

@@ -308,6 +308,29 @@ class MergeIndex:
     row_starts = None
     total_feats = None
     reps = None
+    att_ctx = None
+
+    @property
+    def shared(self):
+        return self.att_ctx is not None
+
+    @property
+    def chosen_rows(self):
+        return self.range_chosen if self.shared else (0, self.T_chosen)
+
+    @property
+    def rejected_rows(self):
+        return self.range_rejected if self.shared else (self.T_chosen, self.T)
+
+    @property
+    def n_attn_seq(self):
+        return self.n_att if self.shared else self.n_seq
+
+    def attn(self):
+        if self.shared:
+            return dict(seqlens=self.att_lens, B=self.n_att, S=self.S, row_starts=self.att_starts, total_rows=self.T,
+                        ctx=self.att_ctx, kids=self.att_kids)
+        return dict(seqlens=self.seqlens, B=self.n_seq, S=self.S, row_starts=self.starts, total_rows=self.T)
 
     @property
     def packed(self):
@@ -366,6 +389,77 @@ def pack_merge_rows(m, seq_lens):
         m.img_pos = (m.img_pos.reshape(-1).long() + st[b]).to(torch.int32)
     m.row_starts = torch.tensor(starts, dtype=torch.int32)
     m.rows, m.rows_chosen = max(starts[-1], 1), starts[m.n_seq // 2]
+    _c(3)
+    return m
+
+
+def share_prefix_rows(m, seq_lens, prefix_rows):
+    """CPU mirror of vlb200_share_prefix_rows (csrc/elementwise.cu) + ops.share_prefix_rows: one copy of every pair's common
+    prefix; rows = [chosen suffixes | prefixes | rejected suffixes]; 3 * n_pairs attention sequences in that order."""
+    lens = [int(x) for x in seq_lens]
+    npair = m.n_seq // 2
+    pre = [int(x) for x in prefix_rows]
+    if len(lens) != m.n_seq or len(pre) != npair:
+        raise ValueError("share_prefix_rows: bad lengths")
+    if m.packed:
+        raise ValueError("share_prefix_rows: the index is already packed")
+    if m.total_feats is not None and m.reps is not None:
+        raise ValueError("share_prefix_rows: LLaVA-Next image rows (variable feature lengths) are not supported yet")
+    for i in range(npair):
+        if pre[i] < 0 or pre[i] > min(lens[i], lens[npair + i]):
+            raise ValueError("share_prefix_rows: prefix exceeds its sequences")
+    att_lens = [lens[i] - pre[i] for i in range(npair)] + pre + [lens[npair + i] - pre[i] for i in range(npair)]
+    att_starts = [0]
+    for n in att_lens:
+        att_starts.append(att_starts[-1] + n)
+    rows = max(att_starts[-1], 1)
+    S = m.S
+
+    def dest(b, p_):
+        if p_ >= lens[b]:
+            return -1
+        i = b % npair
+        if p_ < pre[i]:
+            return att_starts[npair + i] + p_
+        return att_starts[b if b < npair else 2 * npair + i] + (p_ - pre[i])
+
+    src_old, pos_old = m.src_map.reshape(-1), m.pos.reshape(-1)
+    src_new = torch.zeros(rows, dtype=torch.int32)
+    pos_new = torch.zeros(rows, dtype=torch.int32)
+    for b in range(m.n_seq):
+        for p_ in range(lens[b]):
+            r = dest(b, p_)
+            if p_ >= pre[b % npair] or b < npair:
+                src_new[r], pos_new[r] = src_old[b * S + p_], pos_old[b * S + p_]
+            else:   # the rejected copy of a shared row is the same computation
+                assert int(src_new[r]) == int(src_old[b * S + p_]) and int(pos_new[r]) == int(pos_old[b * S + p_])
+    m.src_map, m.pos = src_new, pos_new
+    rot = m.row_of_text.reshape(-1).clone()
+    for i, r in enumerate(rot.tolist()):
+        if r >= 0:
+            rot[i] = dest(r // S, r % S) if r // S < m.n_seq else -1
+    m.row_of_text = rot
+    if getattr(m, "img_pos", None) is not None:
+        feats = m.imgs_per_seq * m.P
+        ip = m.img_pos.reshape(-1).clone()
+        for i, p_ in enumerate(ip.tolist()):
+            b = i // feats
+            if p_ >= 0:
+                ip[i] = -1 if (p_ < pre[b % npair] and b >= npair) else dest(b, p_)
+        m.img_pos = ip
+    ctx = [npair + i if pre[i] > 0 else -1 for i in range(npair)] + [-1] * npair + [npair + i if pre[i] > 0 else -1 for i in range(npair)]
+    kids = [-1] * (6 * npair)
+    for i in range(npair):
+        if pre[i] > 0:
+            kids[2 * (npair + i)], kids[2 * (npair + i) + 1] = i, 2 * npair + i
+    m.att_starts = torch.tensor(att_starts, dtype=torch.int32)
+    m.att_lens = torch.tensor(att_lens, dtype=torch.int32)
+    m.att_ctx = torch.tensor(ctx, dtype=torch.int32)
+    m.att_kids = torch.tensor(kids, dtype=torch.int32)
+    m.row_starts, m.rows, m.rows_chosen = m.att_starts, rows, att_starts[2 * npair]
+    m.n_att = 3 * npair
+    m.range_chosen, m.range_rejected = (0, att_starts[2 * npair]), (att_starts[npair], att_starts[3 * npair])
+    m.shared_rows = sum(pre)
     _c(3)
     return m
 
@@ -686,9 +780,53 @@ def _pack_rows_into(dst, padded, row_starts, seqlens, B, S):
         dst[r0:r0 + n] = padded[b * S:b * S + n].to(dst.dtype)
 
 
-def attn_fwd_tc(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale, row_starts=None, total_rows=0):
+def _attn_ctx_core(q, k, v, seqlens, row_starts, ctx, B, H, KVH, dh, scale):
+    """Differentiable restatement of vlb200_attn_fwd_tc_ctx: sequence b's queries see ALL rows of sequence ctx[b] (if any), then
+    their own rows causally.  q/k/v: fp32 [rows, heads*dh].  -> (out [rows, H*dh], [(b, lse [H, n])])"""
+    out = torch.zeros(q.shape[0], H * dh, dtype=torch.float32)
+    stats = []
+    g = H // KVH
+    for b in range(B):
+        n, r0 = int(seqlens[b]), int(row_starts[b])
+        if n == 0:
+            stats.append(None)
+            continue
+        rows = torch.arange(r0, r0 + n)
+        c = int(ctx[b])
+        nc = 0
+        if c >= 0:
+            nc, c0 = int(seqlens[c]), int(row_starts[c])
+            rows_k = torch.cat([torch.arange(c0, c0 + nc), rows])
+        else:
+            rows_k = rows
+        qq = q[rows].view(n, H, dh).transpose(0, 1)                                 # [H, n, dh]
+        kk = k[rows_k].view(-1, KVH, dh).transpose(0, 1).repeat_interleave(g, 0)     # [H, nk, dh]
+        vv = v[rows_k].view(-1, KVH, dh).transpose(0, 1).repeat_interleave(g, 0)
+        sc = qq @ kk.transpose(1, 2) * scale
+        mask = torch.zeros(n, nc + n, dtype=torch.bool)
+        mask[:, nc:] = torch.ones(n, n, dtype=torch.bool).triu(1)
+        sc = sc.masked_fill(mask[None], float("-inf"))
+        p_ = torch.softmax(sc, -1)
+        out[rows] = (p_ @ vv).transpose(0, 1).reshape(n, H * dh)
+        stats.append(torch.logsumexp(sc, -1))
+    return out, stats
+
+
+def attn_fwd_tc(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale, row_starts=None, total_rows=0, ctx=None,
+                kids=None):
     """Same contract as the mma.sync kernels; row_starts: packed rows (only the attended prefix of every sequence is written,
     lse rows beyond it are left untouched -- as the CUDA kernel does)."""
+    if ctx is not None:
+        assert causal and row_starts is not None
+        with torch.no_grad():
+            o, stats = _attn_ctx_core(q.float(), k.float(), v.float(), seqlens, row_starts, ctx, B, H, KVH, head_dim, scale)
+        out.copy_(o.to(out.dtype))
+        if lse is not None:
+            for b, st in enumerate(stats):
+                if st is not None:
+                    lse[b, :, :st.shape[1]] = st
+        _c()
+        return out
     if row_starts is None:
         return attn_fwd(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scale)
     qp, kp, vp = (_unpack_rows(t, row_starts, seqlens, B, S) for t in (q, k, v))
@@ -703,7 +841,19 @@ def attn_fwd_tc(q, k, v, out, lse, seqlens, B, S, H, KVH, head_dim, causal, scal
 
 
 def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale, row_starts=None,
-                total_rows=0):
+                total_rows=0, ctx=None, kids=None):
+    if ctx is not None:
+        assert causal and row_starts is not None and kids is not None
+        for b in range(B):   # kids must be the inverse of ctx (the kernel's dK/dV pass walks it)
+            want = sorted(j for j in range(B) if int(ctx[j]) == b)
+            assert sorted(int(x) for x in kids[2 * b:2 * b + 2] if int(x) >= 0) == want, (b, want)
+        with torch.enable_grad():
+            qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+            o, _ = _attn_ctx_core(qf, kf, vf, seqlens, row_starts, ctx, B, H, KVH, head_dim, scale)
+            (o * dout.float()).sum().backward()
+        dq.copy_(qf.grad.to(dq.dtype)); dk.copy_(kf.grad.to(dk.dtype)); dv.copy_(vf.grad.to(dv.dtype))
+        _c(3)
+        return
     if row_starts is None:
         return attn_bwd(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale)
     qp, kp, vp, dop = (_unpack_rows(t, row_starts, seqlens, B, S) for t in (q, k, v, dout))

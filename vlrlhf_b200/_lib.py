@@ -88,6 +88,16 @@ SIGNATURES = {
                                           c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                           c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                           c_void_p]),
+    "vlb200_attn_fwd_tc_ctx": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_void_p]),
+    "vlb200_attn_bwd_tc_ctx": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                       c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_float, c_void_p]),
+    "vlb200_share_prefix_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64,
+                                         c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64,
+                                         c_void_p]),
     "vlb200_pack_merge_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                        c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "vlb200_sumsq_bf16": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_int, c_void_p]),

@@ -116,6 +116,14 @@ class TrainConfig:
     # are those of the padded batch; only TRL's `logits/chosen|rejected` metric changes meaning (it averages over the
     # attended positions instead of all positions).  All engines (LLaVA-1.5 / LLaVA-Next full fine-tune and LoRA, Qwen-VL, XC2).
     pack_sequences: bool = False
+    # the reference concatenates chosen and rejected on the batch axis (base/trainer.py:124-146), so the
+    # prompt + image prefix the two sequences of a pair have in common (identical tokens, identical image, causal attention
+    # => identical hidden states) is computed twice per pass.  With share_prefix it is laid out, projected, normed and
+    # attended ONCE per pair: rows = [chosen suffixes | prefixes | rejected suffixes], the attention kernels treat a suffix's
+    # prefix as context keys (vlb200_attn_*_tc_ctx), the backward sums both suffixes' gradients into the prefix.  Implies
+    # packed rows.  Results equal the padded step up to accumulation order (the prefix gradient is accumulated inside one
+    # attention backward instead of two).  LLaVA-1.5 family (full fine-tune and LoRA).
+    share_prefix: bool = False
     # HF TrainingArguments the reference recipes set (scripts/dpo_qwenvl.sh:4,35,42-43; scripts/dpo_llava.sh:40-41):
     # k micro-batches are accumulated in the gradient arena before ONE reduction + AdamW step; the learning rate follows
     # transformers.get_scheduler ("constant" | "linear" | "cosine", linear warm-up over warmup_steps or

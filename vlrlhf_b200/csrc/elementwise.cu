@@ -351,6 +351,7 @@ __global__ void merge_img_bwd_kernel(const int* __restrict__ img_pos, const __nv
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int b = bi; b < n_seq; b += n_img_batch) {
             const int p = img_pos[(size_t)b * feats_per_seq + f];
+            if (p < 0) continue;   // shared-prefix rows: the image rows of a pair exist once (the rejected copy is dropped)
             float v[8];
             unpack8e(*reinterpret_cast<const uint4*>(dx + ((size_t)b * S + p) * d + c * 8), v);
 #pragma unroll
@@ -391,6 +392,50 @@ __global__ void remap_rows_kernel(int* __restrict__ rows, size_t n, const int* _
 __global__ void abs_img_pos_kernel(int* __restrict__ img_pos, size_t n, int feats_per_seq, const int* __restrict__ row_starts) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         img_pos[i] += row_starts[i / feats_per_seq];
+}
+// ---- shared-prefix rows: the first pre[b] merged rows of the chosen and the rejected sequence of a pair
+// are the same computation (same prompt tokens, same image, causal attention), so they are laid out ONCE.  Padded row (b, p):
+//   p < pre[b]  -> pre_start[b] + p            (pre / pre_start are equal for the two sequences of a pair)
+//   p < len[b]  -> suf_start[b] + (p - pre[b])
+//   otherwise   -> dropped (-1)
+__device__ __forceinline__ int shared_row(int b, int p, const int* pre, const int* pre_start, const int* suf_start, const int* len) {
+    if (p >= len[b]) return -1;
+    const int q = pre[b];
+    return p < q ? pre_start[b] + p : suf_start[b] + (p - q);
+}
+__global__ void share_rows_kernel(const int* __restrict__ src_map, const int* __restrict__ pos, const int* __restrict__ pre,
+                                  const int* __restrict__ pre_start, const int* __restrict__ suf_start, const int* __restrict__ len,
+                                  int n_seq, int S, int* __restrict__ src_map_s, int* __restrict__ pos_s) {
+    const size_t total = (size_t)n_seq * S;
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < total; r += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(r / S), p = (int)(r % S);
+        const int dst = shared_row(b, p, pre, pre_start, suf_start, len);
+        // a shared row is written by both sequences of the pair with the same values; the first half (chosen) is the writer
+        if (dst >= 0 && (p >= pre[b] || b < n_seq / 2)) {
+            src_map_s[dst] = src_map[r];
+            pos_s[dst] = pos[r];
+        }
+    }
+}
+__global__ void share_remap_rows_kernel(int* __restrict__ rows, size_t n, const int* __restrict__ pre, const int* __restrict__ pre_start,
+                                        const int* __restrict__ suf_start, const int* __restrict__ len, int n_seq, int S) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = rows[i];
+        if (r < 0) continue;
+        const int b = r / S, p = r % S;
+        rows[i] = b < n_seq ? shared_row(b, p, pre, pre_start, suf_start, len) : -1;
+    }
+}
+// img_pos (position inside sequence i / feats_per_seq) -> absolute shared row; the rejected copy of a row that lies in the
+// shared prefix becomes -1 (vlb200_llava_merge_bwd_rows then counts the row once)
+__global__ void share_img_pos_kernel(int* __restrict__ img_pos, size_t n, int feats_per_seq, const int* __restrict__ pre,
+                                     const int* __restrict__ pre_start, const int* __restrict__ suf_start, const int* __restrict__ len,
+                                     int n_seq) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / feats_per_seq), p = img_pos[i];
+        if (p < 0) continue;
+        img_pos[i] = (p < pre[b] && b >= n_seq / 2) ? -1 : shared_row(b, p, pre, pre_start, suf_start, len);
+    }
 }
 
 // ---------------------------------------------------------------- LLaVA-Next merge index (LlavaNext/__init__.py:38-171)
@@ -761,6 +806,38 @@ extern "C" int vlb200_pack_merge_rows(const int* src_map, const int* position_id
     }
     if (img_pos != nullptr && n_img_pos > 0) {
         abs_img_pos_kernel<<<grid_for((size_t)n_img_pos, 256), 256, 0, s>>>(img_pos, (size_t)n_img_pos, feats_per_seq, row_starts);
+        count_launch();
+    }
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+extern "C" int vlb200_share_prefix_rows(const int* src_map, const int* position_ids, const int* prefix_rows, const int* prefix_starts,
+                                        const int* suffix_starts, const int* seq_lens, int n_seq, int merged_len, int64_t total_rows,
+                                        int* src_map_shared, int* position_ids_shared, int* row_of_text, int64_t n_text_rows,
+                                        int* img_pos, int64_t n_img_pos, int feats_per_seq, int* img_rows, int64_t n_img_rows,
+                                        void* stream) {
+    VLB_REQUIRE(src_map && position_ids && prefix_rows && prefix_starts && suffix_starts && seq_lens && src_map_shared &&
+                    position_ids_shared && n_seq > 0 && n_seq % 2 == 0 && merged_len > 0 && total_rows > 0,
+                "share_prefix_rows: bad arguments");
+    VLB_REQUIRE(img_pos == nullptr || feats_per_seq > 0, "share_prefix_rows: img_pos needs feats_per_seq");
+    cudaStream_t s = as_stream(stream);
+    share_rows_kernel<<<grid_for((size_t)n_seq * merged_len, 256), 256, 0, s>>>(src_map, position_ids, prefix_rows, prefix_starts,
+                                                                              suffix_starts, seq_lens, n_seq, merged_len,
+                                                                              src_map_shared, position_ids_shared);
+    count_launch();
+    if (row_of_text != nullptr && n_text_rows > 0) {
+        share_remap_rows_kernel<<<grid_for((size_t)n_text_rows, 256), 256, 0, s>>>(row_of_text, (size_t)n_text_rows, prefix_rows,
+                                                                                 prefix_starts, suffix_starts, seq_lens, n_seq, merged_len);
+        count_launch();
+    }
+    if (img_rows != nullptr && n_img_rows > 0) {
+        share_remap_rows_kernel<<<grid_for((size_t)n_img_rows, 256), 256, 0, s>>>(img_rows, (size_t)n_img_rows, prefix_rows,
+                                                                                prefix_starts, suffix_starts, seq_lens, n_seq, merged_len);
+        count_launch();
+    }
+    if (img_pos != nullptr && n_img_pos > 0) {
+        share_img_pos_kernel<<<grid_for((size_t)n_img_pos, 256), 256, 0, s>>>(img_pos, (size_t)n_img_pos, feats_per_seq, prefix_rows,
+                                                                            prefix_starts, suffix_starts, seq_lens, n_seq);
         count_launch();
     }
     VLB_LAUNCH_CHECK();

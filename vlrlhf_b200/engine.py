@@ -141,6 +141,19 @@ def hf_views(cfg: ModelConfig, w: Dict[str, torch.Tensor], vision: Optional[Dict
     return out
 
 
+def attn_forward(m: "ops.MergeIndex", q, k, v, out, lse, H: int, KV: int, dh: int, scale: float):
+    """Causal fused attention over the sequences of a merge index (padded, packed or shared-prefix rows)."""
+    a = m.attn()
+    return ops.attn_fwd_tc(q, k, v, out, lse, a["seqlens"], a["B"], a["S"], H, KV, dh, True, scale,
+                           **{k_: a[k_] for k_ in ("row_starts", "total_rows", "ctx", "kids") if a.get(k_) is not None})
+
+
+def attn_backward(m: "ops.MergeIndex", q, k, v, out, dout, lse, delta, dq, dk, dv, H: int, KV: int, dh: int, scale: float):
+    a = m.attn()
+    return ops.attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, a["seqlens"], a["B"], a["S"], H, KV, dh, True, scale,
+                           **{k_: a[k_] for k_ in ("row_starts", "total_rows", "ctx", "kids") if a.get(k_) is not None})
+
+
 class StepOutput:
     __slots__ = ("loss", "losses", "chosen_rewards", "rejected_rewards", "stats", "policy_logps", "ref_logps", "grad_norm")
 
@@ -166,6 +179,8 @@ class LlavaDPOEngine:
         import os as _os
         if train is None and _os.environ.get("VLB200_PACK_SEQUENCES", "0") == "1":
             self.tc.pack_sequences = True   # launcher-level switch: the reference's dpo.py builds the model without a TrainConfig
+        if train is None and _os.environ.get("VLB200_SHARE_PREFIX", "0") == "1":
+            self.tc.share_prefix = True
         # Optimizer sharding across the data-parallel ranks (ZeRO-1 style; the reference's default DeepSpeed config
         # shards optimizer state too, accelerate_config/zero2.yaml): gradients are reduce-SCATTERED, each rank runs
         # AdamW on its 1/world slice of the flat buffers (fp32 master + moments exist for that slice only) and the
@@ -373,7 +388,7 @@ class LlavaDPOEngine:
         return dict(rstd1=self.buf(f"{pre}.rstd1{sfx}", (T,), torch.float32),
                     rstd2=self.buf(f"{pre}.rstd2{sfx}", (T,), torch.float32),
                     qkv=self.buf(f"{pre}.qkv{sfx}", (T, cfg.qkv_dim)), att=self.buf(f"{pre}.att{sfx}", (T, H * dh)),
-                    lse=self.buf(f"{pre}.lse{sfx}", (m.n_seq, H, m.S), torch.float32),
+                    lse=self.buf(f"{pre}.lse{sfx}", (m.n_attn_seq, H, m.S), torch.float32),
                     xmid=self.buf(f"{pre}.xmid{sfx}", (T, cfg.hidden), torch.float32),
                     gu=self.buf(f"{pre}.gu{sfx}", (T, 2 * cfg.ff)))
 
@@ -392,8 +407,7 @@ class LlavaDPOEngine:
         ops.rmsnorm_fwd(x, w[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=b["rstd1"])
         ops.gemm(h, w[f"L{i}.wqkv"], out=qkv)
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
-        ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
+        attn_forward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], H, KV, dh, 1.0 / math.sqrt(dh))
         ops.gemm(att, w[f"L{i}.wo"], out=xmid, residual=x)
         ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
         if xn is None:
@@ -473,11 +487,11 @@ class LlavaDPOEngine:
             # TRL's `logits/chosen|rejected` = mean of the full [B,S,V] logits = dot(colsum(h), colsum(W_lm)) / (B*S*V)  (K19)
             # (packed rows: the mean runs over the attended positions only -- the reference also averages the logits of its
             # padding positions, which a packed batch never computes; the one metric that differs)
-            half = m.T_chosen
+            (c0, c1), (r0, r1) = m.chosen_rows, m.rejected_rows   # shared-prefix rows: the prefixes belong to both halves
             cs = self.buf("m.colsum", (3, d), torch.float32)
-            ops.colsum_f32(h[:half], cs[0]); ops.colsum_f32(h[half:], cs[1]); ops.colsum_f32(lm_w, cs[2])
+            ops.colsum_f32(h[c0:c1], cs[0]); ops.colsum_f32(h[r0:r1], cs[1]); ops.colsum_f32(lm_w, cs[2])
             self.logit_means = self.buf("m.logit_means", (2,), torch.float32)
-            inv_c, inv_r = 1.0 / (float(max(half, 1)) * cfg.vocab), 1.0 / (float(max(T - half, 1)) * cfg.vocab)
+            inv_c, inv_r = 1.0 / (float(max(c1 - c0, 1)) * cfg.vocab), 1.0 / (float(max(r1 - r0, 1)) * cfg.vocab)
             ops.dot_f32(cs[0], cs[2], inv_c, self.logit_means[0:1]); ops.dot_f32(cs[1], cs[2], inv_r, self.logit_means[1:2])
         return logps
 
@@ -497,7 +511,12 @@ class LlavaDPOEngine:
         ops.gemm(dlogits, lm_w, b_kmajor=False, out=dhsel)                                 # dh = dlogits W
         dxf = self.buf("b.dxf", (T, d))
         ops.zero_(dxf)
-        ops.scatter_rows(dhsel, m.row_of_text, dxf)
+        if m.shared:   # a shared prefix row feeds the heads of BOTH sequences of its pair: chosen half written, rejected half added
+            hr = R // 2
+            ops.scatter_rows(dhsel[:hr], m.row_of_text[:hr], dxf)
+            ops.scatter_add_rows(dhsel[hr:], m.row_of_text[hr:], dxf)
+        else:
+            ops.scatter_rows(dhsel, m.row_of_text, dxf)
         dx = self.buf("b.dx0", (T, d))
         ops.rmsnorm_bwd(dxf, sv["x_last"], norm_w, self._bufs["a.rstd_f"], g_norm, out=dx, dw_accumulate=acc)
         return dx
@@ -524,7 +543,7 @@ class LlavaDPOEngine:
         dnorm = dxf  # reuse: [T, d] scratch for the gradients of the normed activations
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
-        delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
+        delta = self.buf("b.delta", (m.n_attn_seq, H, m.S), torch.float32)
         scale = 1.0 / math.sqrt(dh)
         for i in reversed(range(cfg.layers)):
             x_in = self._bufs[f"x.{i}"]
@@ -548,9 +567,8 @@ class LlavaDPOEngine:
             # ---- attention
             ops.gemm(dx2, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wo"], accumulate=acc)             # dWo = dxmid^T att
             ops.gemm(dx2, w[f"L{i}.wo"], b_kmajor=False, out=datt)                            # datt = dxmid Wo
-            ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
-                         dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                         True, scale, row_starts=m.starts, total_rows=m.T)
+            attn_backward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta,
+                          dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], H, KV, dh, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             ops.rmsnorm_fwd(x_in, w[f"L{i}.ln1"], cfg.rms_eps, out=h)                         # recompute h1
             ops.gemm(dqkv, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wqkv"], accumulate=acc)            # dWqkv = dqkv^T h1
@@ -715,7 +733,7 @@ class LlavaDPOEngine:
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
                       feats: Optional[torch.Tensor] = None, m: Optional["ops.MergeIndex"] = None, seq_lens=None,
-                      imgs_per_seq: int = 1):
+                      imgs_per_seq: int = 1, prefix_rows=None):
         """`seq_lens` (host ints, merged length of every sequence; host.merged_seq_lens) is only read with
         TrainConfig.pack_sequences; without it the lengths are read back from the device (one synchronisation)."""
         cfg = self.cfg
@@ -733,7 +751,15 @@ class LlavaDPOEngine:
                     raise ValueError(f"{px.shape[0]} images do not split into groups of {imgs_per_seq}")
                 m = ops.llava_merge_index(ids, am, lb, cfg.n_patches, px.shape[0] // imgs_per_seq, imgs_per_seq,
                                           cfg.image_token_index, cfg.pad_token_id, cfg.ignore_index)
-            if self.tc.pack_sequences:   # drop the padding rows: every kernel below runs over sum(len) rows
+            if self.tc.share_prefix:     # one copy of every pair's common prefix (implies packed rows)
+                if anyres is not None:
+                    raise ValueError("share_prefix: LLaVA-Next (variable packed feature lengths) is not supported yet")
+                if seq_lens is None or prefix_rows is None:
+                    raise ValueError("share_prefix needs the host-side row plan: pass **engine.host_row_plan(ids, am) "
+                                     "(train_step and plugin.concatenated_forward do)")
+                ops.share_prefix_rows(m, seq_lens, prefix_rows)
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+            elif self.tc.pack_sequences:   # drop the padding rows: every kernel below runs over sum(len) rows
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         self.ensure_rope_len(m.S)
@@ -746,7 +772,7 @@ class LlavaDPOEngine:
 
     def step(self, ids, am, lb, px, ddpo_weight=None, anyres=None, train: bool = True,
              ref_logps: Optional[torch.Tensor] = None, seq_lens=None, imgs_per_seq: int = 1,
-             accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0) -> StepOutput:
+             accumulate: bool = False, sync: bool = True, loss_scale: float = 1.0, prefix_rows=None) -> StepOutput:
         """One DPO step on device-resident inputs: policy fwd, reference fwd (no grad), loss, and when `train`
         backward + gradient all-reduce + AdamW.  `ref_logps` ([2B] fp32, chosen then rejected) replaces the reference
         pass: TRL's precompute_ref_log_probs branch of get_batch_loss_metrics (plumbed at base/trainer.py:61,96 and
@@ -756,7 +782,8 @@ class LlavaDPOEngine:
         tc = self.tc
         if ref_logps is not None:
             pol, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, seq_lens=seq_lens,
-                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
+                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}),
+                                               **({"prefix_rows": prefix_rows} if prefix_rows is not None else {}))
             ref = ref_logps.to(self.device, torch.float32).reshape(-1).contiguous()
             if ref.numel() != pol.numel():
                 raise ValueError(f"ref_logps holds {ref.numel()} values, the batch has {pol.numel()} sequences")
@@ -764,7 +791,8 @@ class LlavaDPOEngine:
             # reference pass first: it reads none of the policy weights, so the previous step's deferred optimizer
             # (side stream) overlaps it; the policy pass below waits for `opt_done`
             ref, m, feats = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "ref", save=False, seq_lens=seq_lens,
-                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}))
+                                               **({"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}),
+                                               **({"prefix_rows": prefix_rows} if prefix_rows is not None else {}))
             pol, _, _ = self.forward_logps(ids, am, lb, px, ddpo_weight, anyres, "policy", save=train, feats=feats, m=m)
         losses, cr, rr, stats, grad = ops.dpo_loss(pol, ref, tc.beta, tc.label_smoothing, tc.loss_type, tc.reference_free,
                                                    float(loss_scale), want_grad=train)
@@ -799,14 +827,14 @@ class LlavaDPOEngine:
                                    torch.as_tensor(batch["reference_rejected_logps"], dtype=torch.float32).reshape(-1)])
         k = self.images_per_sequence(batch)
         kw = {"imgs_per_seq": k} if k != 1 else {}
-        seq_lens = self.host_seq_lens(ids, am, sizes, **kw) if tc.pack_sequences else None
+        plan = self.host_row_plan(ids, am, sizes, **kw)
         ga = max(1, int(tc.gradient_accumulation_steps)) if train else 1
         micro = self._micro_step % ga
         sync = micro == ga - 1
         if train:
             self._micro_step += 1
         out = self.step(*self.prepare_inputs(ids, am, lb, px, wt, sizes, **kw), train=train, ref_logps=ref_logps,
-                        seq_lens=seq_lens, accumulate=micro > 0, sync=sync, loss_scale=1.0 / ga, **kw)
+                        accumulate=micro > 0, sync=sync, loss_scale=1.0 / ga, **plan, **kw)
         n = out.policy_logps.numel() // 2
         if self._opt_pending and out.grad_norm is not None:  # grad_norm comes from the side stream; AdamW itself keeps running behind this read
             torch.cuda.current_stream(self.device).wait_event(self.norm_done)
@@ -847,12 +875,28 @@ class LlavaDPOEngine:
         wt = self.ddpo_weights(ids, am, lb, sizes) if tc.loss_type == "ddpo" else None
         k = self.images_per_sequence(batch)
         kw = {"imgs_per_seq": k} if k != 1 else {}
-        seq_lens = self.host_seq_lens(ids, am, sizes, **kw) if tc.pack_sequences else None
+        plan = self.host_row_plan(ids, am, sizes, **kw)
         inputs = self.prepare_inputs(ids, am, lb, batch["img_input_dict"]["pixel_values"], wt, sizes, **kw)
-        logps, _, _ = self.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens, **kw)
+        logps, _, _ = self.forward_logps(*inputs, which="ref", save=False, **plan, **kw)
         logps = logps.float().cpu()
         n = logps.numel() // 2
         return logps[:n], logps[n:]
+
+    def host_row_plan(self, ids, am, image_sizes=None, imgs_per_seq: int = 1) -> Dict:
+        """Keyword arguments for step / forward_logps that describe the row layout of one concatenated HOST batch, so the
+        step needs no device read-back: {} (padded rows), {seq_lens} (TrainConfig.pack_sequences) or {seq_lens, prefix_rows}
+        (TrainConfig.share_prefix: merged rows the chosen and rejected sequence of every pair have in common)."""
+        tc = self.tc
+        kw = {"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}
+        if not (tc.pack_sequences or tc.share_prefix):
+            return {}
+        plan = {"seq_lens": self.host_seq_lens(ids, am, image_sizes, **kw)}
+        if tc.share_prefix:
+            from . import host
+            if self.cfg.family != "llava":
+                raise ValueError(f"share_prefix is implemented for the LLaVA-1.5 family (full fine-tune and LoRA), not {self.cfg.family!r}")
+            plan["prefix_rows"] = host.shared_prefix_rows(ids, am, self.cfg.image_token_index, self.cfg.n_patches)
+        return plan
 
     def host_seq_lens(self, ids, am, image_sizes=None, imgs_per_seq: int = 1) -> List[int]:
         """Merged length of every sequence of one concatenated host batch (packed steps: the rows that survive)."""

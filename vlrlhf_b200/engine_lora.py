@@ -26,7 +26,7 @@ import torch
 
 from . import ops
 from .config import LlavaLoRAModelConfig, llava_lora_specs, tensor_seed, weight_specs
-from .engine import Arena, LlavaDPOEngine, Weights, _trainable_layout, _vision_layout, hf_views
+from .engine import Arena, LlavaDPOEngine, Weights, _trainable_layout, _vision_layout, attn_backward, attn_forward, hf_views
 
 
 def _lora_layout(cfg: LlavaLoRAModelConfig) -> Arena:
@@ -163,8 +163,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             for j, (lo, hi, n) in enumerate(((0, hd, "q"), (hd, hd + kvd, "k"), (hd + kvd, hd + 2 * kvd, "v"))):
                 ops.gemm(h, wqkv[lo:hi], a2=ts[:, j * r:(j + 1) * r], b2=lora[f"L{i}.{n}.B"], out=qkv[:, lo:hi])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
-        ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
+        attn_forward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], H, KV, dh, 1.0 / math.sqrt(dh))
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -227,7 +226,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         dnorm = dxf
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
-        delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
+        delta = self.buf("b.delta", (m.n_attn_seq, H, m.S), torch.float32)
         # dt = bf16(s * dy B) of the adapters that share an input, side by side (3r: q|k|v, 2r: gate|up, r: o, down)
         d3 = self.buf("b.d3", (T, 3 * r)); d2 = self.buf("b.d2", (T, 2 * r)); d1 = self.buf("b.d1", (T, r))
         scale = 1.0 / math.sqrt(dh)
@@ -262,9 +261,8 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
             ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=d1, alpha=s)
             ops.gemm(d1, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
-            ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
-                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale,
-                            row_starts=m.starts, total_rows=m.T)
+            attn_backward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
+                          dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], H, KV, dh, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             # ---- q | k | v
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1

@@ -240,6 +240,31 @@ def merged_seq_lens(input_ids: torch.Tensor, attention_mask: torch.Tensor, image
     return [int(v) for v in (att.sum(-1) - is_img.sum(-1) + rows)]
 
 
+def shared_prefix_rows(input_ids: torch.Tensor, attention_mask: torch.Tensor, image_token_index: int, n_patches: int,
+                       min_suffix: int = 1) -> List[int]:
+    """Merged rows the chosen and the rejected sequence of every pair have in common (TrainConfig.share_prefix), from one
+    concatenated HOST batch ([2B, L], chosen first -- base/trainer.py:124-146): the longest common token prefix of the two
+    sequences, capped so that each keeps at least `min_suffix` rows of its own, expanded to merged rows (every <image>
+    placeholder inside it stands for n_patches rows, Llava/__init__.py:44-52).  0 when nothing can be shared -- including
+    the case where an <image> placeholder lies beyond the common prefix (the image rows then stay per sequence)."""
+    ids, am = input_ids.cpu(), attention_mask.cpu()
+    n_seq, L = ids.shape
+    if n_seq % 2:
+        raise ValueError("shared_prefix_rows: a concatenated batch holds an even number of sequences")
+    B = n_seq // 2
+    lens = (am == 1).sum(-1)
+    same = (ids[:B] == ids[B:]) & (am[:B] == 1) & (am[B:] == 1)
+    lcp = torch.cumprod(same.to(torch.int64), dim=-1).sum(-1)              # first mismatch / end of the shorter sequence
+    lcp = torch.minimum(lcp, torch.minimum(lens[:B], lens[B:]) - int(min_suffix)).clamp(min=0)
+    is_img = ids[:B] == image_token_index
+    inside = torch.arange(L)[None, :] < lcp[:, None]
+    n_in = (is_img & inside).sum(-1)
+    n_all = (is_img & (am[:B] == 1)).sum(-1)
+    rows = lcp + n_in * (int(n_patches) - 1)
+    rows = torch.where(n_in == n_all, rows, torch.zeros_like(rows))       # every image of the pair inside the prefix, or no sharing
+    return [int(v) for v in rows]
+
+
 def ddpo_row_weights(input_ids: torch.Tensor, labels: torch.Tensor, image_token_index: int, n_patches,
                      label_pad_token_id: int = -100, min_match_size: int = 3,
                      attention_mask: Optional[torch.Tensor] = None, merged_len: Optional[int] = None) -> torch.Tensor:

@@ -337,7 +337,8 @@ class MergeIndex:
     """Device-side result of the integer merge pass (Llava/__init__.py:36-109)."""
     __slots__ = ("src_map", "labels", "mask", "pos", "seqlens", "img_pos", "row_of_text", "target", "status",
                  "n_seq", "L", "S", "P", "n_img_batch", "imgs_per_seq", "total_feats", "reps",
-                 "row_starts", "rows", "rows_chosen")
+                 "row_starts", "rows", "rows_chosen",
+                 "att_starts", "att_lens", "att_ctx", "att_kids", "n_att", "range_chosen", "range_rejected", "shared_rows")
 
     # Row layout of the merged activations.  Padded (default): sequence b at rows [b*S, (b+1)*S).  Packed (pack_merge_rows):
     # sequence b at rows [row_starts[b], row_starts[b] + len[b]), `rows` = sum(len) in all, `rows_chosen` of them chosen.
@@ -359,6 +360,33 @@ class MergeIndex:
     def T_chosen(self) -> int:
         """Rows of the chosen half (the first n_seq/2 sequences)."""
         return self.rows_chosen if self.packed else (self.n_seq // 2) * self.S
+
+    # Shared-prefix rows (share_prefix_rows): rows = [chosen suffixes | one prefix per pair | rejected suffixes]; attention runs
+    # over n_att = 3 * n_pairs sequences in that order (a suffix names its pair's prefix as context).
+    @property
+    def shared(self) -> bool:
+        return getattr(self, "att_ctx", None) is not None
+
+    @property
+    def chosen_rows(self):
+        """(lo, hi): the contiguous rows that make up the chosen sequences (shared: chosen suffixes + prefixes)."""
+        return self.range_chosen if self.shared else (0, self.T_chosen)
+
+    @property
+    def rejected_rows(self):
+        """(lo, hi): the contiguous rows of the rejected sequences (shared: prefixes + rejected suffixes)."""
+        return self.range_rejected if self.shared else (self.T_chosen, self.T)
+
+    @property
+    def n_attn_seq(self) -> int:
+        return self.n_att if self.shared else self.n_seq
+
+    def attn(self) -> dict:
+        """Sequence description the attention kernels take: seqlens, B, row_starts, total_rows (+ ctx / kids when shared)."""
+        if self.shared:
+            return dict(seqlens=self.att_lens, B=self.n_att, S=self.S, row_starts=self.att_starts, total_rows=self.T,
+                        ctx=self.att_ctx, kids=self.att_kids)
+        return dict(seqlens=self.seqlens, B=self.n_seq, S=self.S, row_starts=self.starts, total_rows=self.T)
 
     @property
     def row_stride(self) -> int:
@@ -474,6 +502,70 @@ def pack_merge_rows(m: MergeIndex, seq_lens) -> MergeIndex:
     return m
 
 
+def share_prefix_rows(m: MergeIndex, seq_lens, prefix_rows) -> MergeIndex:
+    """Lay the merged rows out with ONE copy of every pair's common prefix (include/vlb200.h: vlb200_share_prefix_rows).
+    `seq_lens` (host ints, one per sequence == m.seqlens) and `prefix_rows` (host ints, one per PAIR: merged rows the chosen
+    and the rejected sequence have in common; 0 = nothing shared) come from the host batch (host.shared_prefix_rows), so the step
+    needs no device read-back.  Afterwards m.T = sum(seq_lens) - sum(prefix_rows); rows = [chosen suffixes | prefixes | rejected
+    suffixes]; m.attn() describes 3 * n_pairs attention sequences."""
+    lens = [int(x) for x in seq_lens]
+    npair = m.n_seq // 2
+    pre = [int(x) for x in prefix_rows]
+    if len(lens) != m.n_seq or len(pre) != npair:
+        raise ValueError(f"share_prefix_rows: {len(lens)} lengths / {len(pre)} prefixes for {m.n_seq} sequences")
+    if m.packed:
+        raise ValueError("share_prefix_rows: the index is already packed")
+    for i in range(npair):
+        if pre[i] < 0 or pre[i] > min(lens[i], lens[npair + i]):
+            raise ValueError(f"share_prefix_rows: prefix {pre[i]} of pair {i} exceeds its sequences ({lens[i]}, {lens[npair + i]})")
+    # rows: chosen suffixes, prefixes, rejected suffixes; attention sequences in the same order
+    att_lens = [lens[i] - pre[i] for i in range(npair)] + pre + [lens[npair + i] - pre[i] for i in range(npair)]
+    att_starts = [0]
+    for n in att_lens:
+        att_starts.append(att_starts[-1] + n)
+    rows = max(att_starts[-1], 1)
+    pre_start = [att_starts[npair + i] for i in range(npair)]
+    suf_start = [att_starts[i] for i in range(npair)] + [att_starts[2 * npair + i] for i in range(npair)]
+    ctx = [npair + i if pre[i] > 0 else -1 for i in range(npair)] + [-1] * npair + \
+          [npair + i if pre[i] > 0 else -1 for i in range(npair)]
+    kids = [-1] * (2 * 3 * npair)
+    for i in range(npair):
+        if pre[i] > 0:
+            kids[2 * (npair + i)], kids[2 * (npair + i) + 1] = i, 2 * npair + i
+    dev = m.src_map.device
+    host = torch.tensor(pre + pre + pre_start + pre_start + suf_start + lens + att_starts + att_lens + ctx + kids, dtype=torch.int32)
+    d = host.to(dev, non_blocking=True)
+    n2, n3 = m.n_seq, 3 * npair
+    o = 0
+    pre_d = d[o:o + n2]; o += n2
+    pst_d = d[o:o + n2]; o += n2
+    sst_d = d[o:o + n2]; o += n2
+    len_d = d[o:o + n2]; o += n2
+    m.att_starts = d[o:o + n3 + 1]; o += n3 + 1
+    m.att_lens = d[o:o + n3]; o += n3
+    m.att_ctx = d[o:o + n3]; o += n3
+    m.att_kids = d[o:o + 2 * n3]
+    src_s = torch.empty(rows, dtype=torch.int32, device=dev)
+    pos_s = torch.empty(rows, dtype=torch.int32, device=dev)
+    next_layout = getattr(m, "total_feats", None) is not None and getattr(m, "reps", None) is not None
+    img_pos, n_img_pos, feats, img_rows, n_img_rows = None, 0, 0, None, 0
+    if getattr(m, "img_pos", None) is None:
+        pass
+    elif next_layout:
+        raise ValueError("share_prefix_rows: LLaVA-Next image rows (variable feature lengths) are not supported yet")
+    else:
+        img_pos, n_img_pos, feats = m.img_pos, m.img_pos.numel(), m.imgs_per_seq * m.P
+    check(_L.vlb200_share_prefix_rows(_ptr(m.src_map), _ptr(m.pos), _ptr(pre_d), _ptr(pst_d), _ptr(sst_d), _ptr(len_d), m.n_seq, m.S,
+                                      rows, _ptr(src_s), _ptr(pos_s), _ptr(m.row_of_text), m.row_of_text.numel(), _ptr(img_pos),
+                                      n_img_pos, feats, _ptr(img_rows), n_img_rows, _stream()))
+    m.src_map, m.pos = src_s, pos_s
+    m.row_starts, m.rows, m.rows_chosen = m.att_starts, rows, att_starts[2 * npair]
+    m.n_att = n3
+    m.range_chosen, m.range_rejected = (0, att_starts[2 * npair]), (att_starts[npair], att_starts[3 * npair])
+    m.shared_rows = sum(pre)
+    return m
+
+
 def qwen_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labels: torch.Tensor, n_queries: int,
                      n_img_batch: int, imgs_per_seq: int, image_start_id: int, ignore_index: int = -100):
     """Integer pass of QWenModel.forward's image placement (modeling_qwen.py:524-528,614-621); S == L."""
@@ -505,10 +597,16 @@ def qwen_merge_index(input_ids: torch.Tensor, attention_mask: torch.Tensor, labe
 # ------------------------------------------------------------------------------------------
 def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: Optional[torch.Tensor],
                 seqlens: Optional[torch.Tensor], B: int, S: int, H: int, KVH: int, head_dim: int, causal: bool,
-                scale: float, row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
+                scale: float, row_starts: Optional[torch.Tensor] = None, total_rows: int = 0,
+                ctx: Optional[torch.Tensor] = None, kids: Optional[torch.Tensor] = None):
     """tcgen05/TMEM/TMA forward; q/k/v/out: 2-D row-major views [B*S, >= heads*head_dim] (may be column slices of one qkv buffer).  row_starts ([B+1] int32) + total_rows: packed rows, sequence b
     at rows [row_starts[b], row_starts[b] + seqlens[b]) (include/vlb200.h: vlb200_attn_fwd_tc_varlen)."""
-    if row_starts is None:
+    if ctx is not None:
+        assert row_starts is not None and ctx.dtype == torch.int32 and ctx.numel() == B
+        check(_L.vlb200_attn_fwd_tc_ctx(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                        out.stride(0), _ptr(lse), _ptr(seqlens), _ptr(row_starts), _ptr(ctx), int(total_rows), B, S,
+                                        H, KVH, head_dim, int(causal), scale, _stream()))
+    elif row_starts is None:
         check(_L.vlb200_attn_fwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
                                     out.stride(0), _ptr(lse), _ptr(seqlens), B, S, H, KVH, head_dim, int(causal), scale,
                                     _stream()))
@@ -520,9 +618,16 @@ def attn_fwd_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Te
 
 
 def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KVH, head_dim, causal, scale,
-                row_starts: Optional[torch.Tensor] = None, total_rows: int = 0):
+                row_starts: Optional[torch.Tensor] = None, total_rows: int = 0,
+                ctx: Optional[torch.Tensor] = None, kids: Optional[torch.Tensor] = None):
     """tcgen05/TMEM/TMA backward; same layout as attn_fwd_tc.  row_starts/total_rows: packed rows (see attn_fwd_tc)."""
-    if row_starts is None:
+    if ctx is not None:
+        assert row_starts is not None and kids is not None and ctx.numel() == B and kids.numel() == 2 * B
+        check(_L.vlb200_attn_bwd_tc_ctx(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                        out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
+                                        _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), _ptr(row_starts), _ptr(ctx),
+                                        _ptr(kids), int(total_rows), B, S, H, KVH, head_dim, int(causal), scale, _stream()))
+    elif row_starts is None:
         check(_L.vlb200_attn_bwd_tc(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
                                     out.stride(0), _ptr(dout), dout.stride(0), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0),
                                     _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _ptr(seqlens), B, S, H, KVH, head_dim,

@@ -270,12 +270,12 @@ class _EngineLogps(torch.autograd.Function):
     gradients are still live)."""
 
     @staticmethod
-    def forward(ctx, anchor, owner, inputs, seq_lens, imgs_per_seq=1, shared=None):
+    def forward(ctx, anchor, owner, inputs, plan, imgs_per_seq=1, shared=None):
         engine = owner.engine
         kw = {"imgs_per_seq": imgs_per_seq} if imgs_per_seq != 1 else {}
         if shared is not None:
             kw.update(feats=shared[0], m=shared[1])
-        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, seq_lens=seq_lens, **kw)
+        logps, m, feats = engine.forward_logps(*inputs, which="policy", save=True, **(plan or {}), **kw)
         ctx.owner = owner
         return logps
 
@@ -336,8 +336,9 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
     k = eng.images_per_sequence(batch) if "img_input_dict" in batch else 1   # several <image> placeholders per sequence
     kw = {"imgs_per_seq": k} if k != 1 else {}
     inputs = eng.prepare_inputs(ids, am, lb, px, wt, sizes, **kw)
-    # TrainConfig.pack_sequences: the merged lengths come from the host batch, so the step stays free of device read-backs
-    seq_lens = eng.host_seq_lens(ids, am, sizes, **kw) if eng.tc.pack_sequences else None
+    # TrainConfig.pack_sequences / share_prefix: the row layout comes from the host batch, so the step stays free of read-backs
+    plan = eng.host_row_plan(ids, am, sizes, **kw) if hasattr(eng, "host_row_plan") else (
+        {"seq_lens": eng.host_seq_lens(ids, am, sizes, **kw)} if eng.tc.pack_sequences else {})
     eng.force_logit_means = which == "policy"
     try:
         if which == "policy" and torch.is_grad_enabled():
@@ -349,14 +350,14 @@ def concatenated_forward(self, model: nn.Module, batch: Dict[str, Union[List, to
                 # ahead of the policy pass, and handed out when trl asks for it: image features and the merge index are
                 # computed once for both passes, and a deferred optimizer step of the previous batch overlaps it
                 with torch.no_grad():
-                    ref_lg, m, feats = eng.forward_logps(*inputs, which="ref", save=False, seq_lens=seq_lens, **kw)
+                    ref_lg, m, feats = eng.forward_logps(*inputs, which="ref", save=False, **plan, **kw)
                 owner._ref_stash = (batch, ref_lg.clone())
                 shared = (feats, m)
             anchor = torch.zeros(1, device=eng.device, requires_grad=True)
-            logps = _EngineLogps.apply(anchor, owner, inputs, seq_lens, k, shared)
+            logps = _EngineLogps.apply(anchor, owner, inputs, plan, k, shared)
         else:
             with torch.no_grad():
-                logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, seq_lens=seq_lens, **kw)
+                logps, _, _ = eng.forward_logps(*inputs, which=which, save=False, **plan, **kw)
         if which == "policy":
             means = eng.logit_means.clone()
             return logps[:n], logps[n:], means[0:1], means[1:2]
