@@ -33,6 +33,7 @@ PAIRS_PER_GPU = 4
 TEXT_LEN = 1024
 PROMPT_LEN = 128
 WORKLOAD = "LLaVA-1.5-7B DPO bf16 full-FT, 4 pairs/GPU, text 1024 (1599 merged), 1x336px image/pair"
+# (bench_library.py and the CPU arm run the same workload string)
 WORKLOAD_NEXT = ("LLaVA-Next-Mistral-7B DDPO bf16 full-FT (configs[3], side measurement), 4 pairs/GPU, text 1024, 1x336px image "
                  "-> 3 anyres crops -> 1176 packed image tokens (2199 merged), activation checkpointing")
 
@@ -64,6 +65,28 @@ def step_flops(cfg, n_pairs, S, rows_lm):
     proj = cfg.n_patches * 2 * (dv * d + d * d)
     crops = getattr(cfg, "_bench_crops_per_image", 1)  # LLaVA-Next: the tower and projector run once per anyres crop
     return n_pairs * (2 * per_seq * 4 + crops * (vit + proj * 4)) + lm * 4
+
+
+def executed_flops(cfg, n_pairs, S, rows_lm, plan):
+    """FLOPs the step actually EXECUTES under a row plan (packed / shared-prefix rows): the linear layers see sum(rows), a
+    sequence of n own rows with c context rows costs 4*d*(n*n/2 + n*c) per layer and pass in attention.  No plan: step_flops."""
+    if not plan or "seq_lens" not in plan:
+        return step_flops(cfg, n_pairs, S, rows_lm)
+    d, ff, L = cfg.hidden, cfg.ff, cfg.layers
+    lens = plan["seq_lens"]
+    pre = plan.get("prefix_rows") or [0] * n_pairs
+    p_layer = cfg.qkv_dim * d + d * cfg.heads * cfg.head_dim + 3 * d * ff
+    rows, attn = 0, 0.0
+    for i in range(n_pairs):
+        p_, c, r = pre[i], lens[i] - pre[i], lens[n_pairs + i] - pre[i]
+        rows += p_ + c + r
+        attn += 4.0 * d * (p_ * p_ / 2 + c * c / 2 + c * p_ + r * r / 2 + r * p_)
+    lin = rows * 2 * p_layer * L
+    lm = rows_lm * 2 * d * cfg.vocab
+    dv, Sv = cfg.v_hidden, cfg.n_patches + 1
+    vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + cfg.n_patches * 2 * cfg.patch_k * dv
+    proj = cfg.n_patches * 2 * (dv * d + d * d)
+    return (lin + L * attn) * 4 + n_pairs * (vit + proj * 4) + lm * 4
 
 
 class ClockSampler:
@@ -274,6 +297,8 @@ def run_b200(args):
            "small_lora": config.SMALL_LORA, "next_small_lora": config.SMALL_NEXT_LORA}[args.model]
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
     is_next = cfg.family == "llava_next"
+    if cfg.family != "llava" or args.pack:
+        args.share_prefix = False
     if cfg.family in ("qwen_vl", "xc2"):
         return run_b200_qwen(args, cfg, world, rank, local)
     if getattr(cfg, "lora_r", 0):
@@ -338,6 +363,17 @@ def run_b200(args):
     launches = (ops.launch_count() - n0)
     ms_e2e = timed(step_e2e, args.steps) if not args.skip_e2e else None
     clocks = sampler.stop() if sampler else None
+    padded_layout = None
+    if eng.tc.share_prefix and not args.skip_e2e:
+        # the same step in the reference's padded [2B, S] layout (every prefix computed twice), on the same box, for reference
+        eng.tc.share_prefix = False
+        for _ in range(2):
+            eng.step(*dev_inputs, train=True)
+        ms_pad = timed(lambda: eng.step(*dev_inputs, train=True), min(args.steps, 5))
+        eng.tc.share_prefix = True
+        eng.step(*dev_inputs, train=True, **plan)
+        padded_layout = {"value": PAIRS_PER_GPU * world / (ms_pad / 1e3), "unit": UNIT, "ms_per_step": ms_pad,
+                         "rows_per_step": 2 * PAIRS_PER_GPU * S, "steps": min(args.steps, 5)}
 
     # dominant kernel live: the tcgen05 GEMM at its largest forward shape (gate_up: [T,d] x [2ff,d]^T)
     T = 2 * PAIRS_PER_GPU * S
@@ -348,7 +384,8 @@ def run_b200(args):
     pk, pk_src = peaks()
     gemm_tf = 2.0 * T * 2 * cfg.ff * cfg.hidden / gemm_ms / 1e9
     traffic, traffic_detail = _traffic()
-    flops = step_flops(cfg, PAIRS_PER_GPU, S, rows_lm)
+    flops = step_flops(cfg, PAIRS_PER_GPU, S, rows_lm)              # what the reference's padded [2B, S] formulation computes
+    flops_exec = executed_flops(cfg, PAIRS_PER_GPU, S, rows_lm, plan)   # what this step executes (shared / packed rows)
     # second kernel family of the north_star ("fraction of the attention/GEMM roofline"): the fused causal attention of one
     # decoder layer, forward and backward, on random q|k|v at the step's shape; algorithmic FLOPs = causal half of QK^T + PV
     nseq, H, KV, dh = 2 * PAIRS_PER_GPU, cfg.heads, cfg.kv_heads, cfg.head_dim
@@ -423,10 +460,13 @@ def run_b200(args):
                        if world > 1 else "dp1 (no collective)",
                        "optimizer": "AdamW fp32 master+moments, max_grad_norm 1.0",
                        "l2": "inputs>>L2 (each step streams >100 GB through HBM)",
-                       "step_tflop_algorithmic": flops / 1e12,
-                       "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                       "step_tflop_algorithmic": flops / 1e12, "step_tflop_executed": flops_exec / 1e12,
+                       "step_tensor_util_of_sustained_peak": flops_exec / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                       "step_tensor_util_note": "EXECUTED FLOPs / time / sustained cuBLAS peak (shared-prefix rows execute fewer FLOPs "
+                                                "than the padded formulation in step_tflop_algorithmic)"},
             "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                     "ms_per_step": ms_e2e, "last_metrics": last},
+            "padded_layout": padded_layout,
             "e2e_plugin": {"value": (pairs / (ms_plugin / 1e3) if ms_plugin else None), "unit": UNIT, "ms_per_step": ms_plugin,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * 4, "last_metrics": plugin_last,
                            "path": "plugin.concatenated_forward(policy) + (RefView) -> plugin.dpo_loss -> losses.mean().backward() "
@@ -719,9 +759,11 @@ def main():
     ap.add_argument("--skip-plugin", action="store_true", help="skip the e2e_plugin measurement (the Trainer-side boundary)")
     ap.add_argument("--checkpointing", action="store_true", help="activation checkpointing (the *_lora side measurements)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
-    ap.add_argument("--share-prefix", dest="share_prefix", action="store_true",
-                    help="TrainConfig.share_prefix: the prompt + image prefix common to the chosen and rejected sequence of a pair is "
-                         "computed once (LLaVA-1.5 family)")
+    ap.add_argument("--no-share-prefix", dest="share_prefix", action="store_false",
+                    help="LLaVA-1.5 family: keep the reference's padded [2B, S] row layout as the headline.  Default: "
+                         "TrainConfig.share_prefix -- the prompt + image prefix the chosen and rejected sequence of a pair have in "
+                         "common is laid out and computed ONCE (same log-probs, losses and gradients; parity tests "
+                         "tests/test_gpu_share_prefix.py); the padded layout is then measured next to it (`padded_layout`)")
     ap.add_argument("--pack", action="store_true",
                     help="TrainConfig.pack_sequences (side measurement: padding rows dropped; the headline run keeps them, as the reference does)")
     args = ap.parse_args()
