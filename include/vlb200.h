@@ -169,6 +169,14 @@ int vlb200_dot_f32(const float* a, const float* b, int n, float scale, float* ou
  * grows the tables before a longer sequence is run, engine.ensure_rope_len); inverse=1 applies the transpose.   */
 int vlb200_rope(void* qkv, int64_t ld, const int* pos, const float* cos_table, const float* sin_table, int table_rows,
                 int rows, int n_rot_heads, int head_dim, int inverse, void* stream);
+/* dact = dy Wd^T-free form: dact[M, ff] = dy[M, K] Wd[K, ff] (+ A2 B2, the LoRA term of the input gradient) with the SwiGLU
+ * BACKWARD in the epilogue (modeling_llama.py:182-184 under autograd): the [M, ff] product never reaches HBM.  gate_up
+ * [M, 2*ff] is read and overwritten IN PLACE with [dgate | dup]; act (optional, [M, ff]) receives silu(gate) * up recomputed
+ * from gate_up -- what the down projection's weight gradient needs.  Bit-identical to vlb200_gemm_bf16_ex ->
+ * vlb200_swiglu_fwd + vlb200_swiglu_bwd.  Wd is down_proj.weight [K = d_model, ff] row-major (an MN-major B operand).     */
+int vlb200_gemm_swiglu_bwd_bf16(const void* dy, int ld_dy, const void* Wd, int ld_wd, const void* A2, int lda2,
+                                const void* B2, int ldb2, int K2, void* gate_up, int ld_gu, void* act, int ld_act, int M,
+                                int ff, int K, void* stream);
 /* gate_up = [gate | up] per row (2*ff columns); act = silu(gate) * up                           */
 int vlb200_swiglu_fwd(const void* gate_up, int64_t ld_gu, void* act, int64_t ld_act, int rows, int ff, void* stream);
 int vlb200_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_dact, void* dgate_up,

@@ -863,6 +863,15 @@ def attn_bwd_tc(q, k, v, out, dout, lse, delta, dq, dk, dv, seqlens, B, S, H, KV
         _pack_rows_into(dst, src, row_starts, seqlens, B, S)
 
 
+def gemm_swiglu_bwd(dy, wd, gu, act=None, a2=None, b2=None):
+    ff = wd.shape[1]
+    dact = gemm(dy, wd, b_kmajor=False, a2=a2, b2=b2)
+    if act is not None:
+        swiglu_fwd(gu, act)
+    swiglu_bwd(gu, dact, out=gu)
+    return gu
+
+
 def colsum_f32(a, out):
     out.copy_(a.float().sum(0))
     _c(2)

@@ -24,6 +24,8 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p]),
     "vlb200_gemm_swiglu_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                         c_int, c_void_p]),
+    "vlb200_gemm_swiglu_bwd_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                            c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vlb200_set_gemm_mode": (c_int, [c_int]),
     "vlb200_set_gemm_raster_mb": (c_int, [c_double]),
     "vlb200_set_gemm_raster_policy": (c_int, [c_int]),

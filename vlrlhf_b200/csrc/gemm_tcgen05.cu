@@ -75,6 +75,8 @@ __host__ __device__ __forceinline__ void tile_coords(const Params& p, int tile, 
     }
 }
 
+constexpr int ACT_SWIGLU_BWD = 100;   // internal epilogue mode of vlb200_gemm_swiglu_bwd_bf16 (not an activation of the public API)
+
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == VLB200_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
     if (act == VLB200_ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
@@ -87,6 +89,36 @@ __device__ __forceinline__ void epilogue_store_32(const Params& p, int row, int 
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                    if (p.act == ACT_SWIGLU_BWD) {
+                        // v = dact (the product dy Wd, never stored).  gate|up at G is read and overwritten IN PLACE by
+                        // [dgate | dup]; act = silu(gate) * up goes to D when given.  dact is rounded to bf16 first and the
+                        // arithmetic is that of swiglu_fwd_kernel / swiglu_bwd_kernel (elementwise.cu), so the result equals
+                        // GEMM -> swiglu_fwd + swiglu_bwd bit for bit.
+                        __nv_bfloat16* gp = p.G + (long long)row * p.ldg + col0;
+                        __nv_bfloat16* ap = p.D != nullptr ? reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0 : nullptr;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            if (col0 + j8 * 8 < p.N) {
+                                const uint4 gb = *reinterpret_cast<const uint4*>(gp + j8 * 8);
+                                const uint4 ub = *reinterpret_cast<const uint4*>(gp + p.ff + j8 * 8);
+                                const uint32_t gw[4] = {gb.x, gb.y, gb.z, gb.w}, uw[4] = {ub.x, ub.y, ub.z, ub.w};
+                                uint32_t dgw[4], duw[4], aw[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 g = unpack_bf16x2(gw[q]), u = unpack_bf16x2(uw[q]);
+                                    const float2 d = unpack_bf16x2(pack_bf16x2(v[j8 * 8 + 2 * q], v[j8 * 8 + 2 * q + 1]));
+                                    const float sx = 1.f / (1.f + __expf(-g.x)), sy = 1.f / (1.f + __expf(-g.y));
+                                    dgw[q] = pack_bf16x2(d.x * u.x * sx * (1.f + g.x * (1.f - sx)), d.y * u.y * sy * (1.f + g.y * (1.f - sy)));
+                                    duw[q] = pack_bf16x2(d.x * g.x * sx, d.y * g.y * sy);
+                                    aw[q] = pack_bf16x2(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
+                                }
+                                *reinterpret_cast<uint4*>(gp + j8 * 8) = make_uint4(dgw[0], dgw[1], dgw[2], dgw[3]);
+                                *reinterpret_cast<uint4*>(gp + p.ff + j8 * 8) = make_uint4(duw[0], duw[1], duw[2], duw[3]);
+                                if (ap != nullptr) *reinterpret_cast<uint4*>(ap + j8 * 8) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+                            }
+                        }
+                        return;
+                    }
                     if (p.bias != nullptr) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
@@ -912,13 +944,15 @@ static int dispatch_major(bool ak, bool bk, const CUtensorMap& ta, const CUtenso
 }  // namespace gemm
 }  // namespace vlb
 
-extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
-                                   const void* A2, int lda2, const void* B2, int ldb2, int K2, void* D, int ldd,
-                                   int out_dtype, int M, int N, int K, float alpha, const void* bias, int act,
-                                   const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
+// gate_up != nullptr: the SwiGLU-backward epilogue (vlb200_gemm_swiglu_bwd_bf16); D may then be null
+static int gemm_ex_impl(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
+                        const void* A2, int lda2, const void* B2, int ldb2, int K2, void* D, int ldd,
+                        int out_dtype, int M, int N, int K, float alpha, const void* bias, int act,
+                        const void* residual, int residual_dtype, int ldr, int accumulate, void* gate_up, long long ld_gu,
+                        void* stream) {
     using namespace vlb;
     using namespace vlb::gemm;
-    VLB_REQUIRE(A && B && D, "gemm: null pointer");
+    VLB_REQUIRE(A && B && (D || gate_up), "gemm: null pointer");
     VLB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     VLB_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
     VLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda=%d / ldb=%d must be multiples of 8 elements (TMA 16 B strides)",
@@ -995,6 +1029,7 @@ extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const v
     p.alpha = alpha;
     p.splits = splits; p.kb_per_split = kb_per_split; p.ws = nullptr;
     p.ff = 0; p.G = nullptr; p.ldg = 0;
+    if (gate_up != nullptr) { p.ff = N; p.G = reinterpret_cast<__nv_bfloat16*>(gate_up); p.ldg = ld_gu; }
     if (splits > 1) {
         rc = splitk_workspace((size_t)splits * M * N * sizeof(float), &p.ws);
         if (rc) return rc;
@@ -1015,6 +1050,28 @@ extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const v
     if (use_pair) return dispatch_2cta(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
     if (big_n) return dispatch_major<256, 4>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
     return dispatch_major<128, 6>(a_kmajor != 0, b_kmajor != 0, ta, tb, ta2, tb2, p, s);
+}
+
+extern "C" int vlb200_gemm_bf16_ex(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
+                                   const void* A2, int lda2, const void* B2, int ldb2, int K2, void* D, int ldd,
+                                   int out_dtype, int M, int N, int K, float alpha, const void* bias, int act,
+                                   const void* residual, int residual_dtype, int ldr, int accumulate, void* stream) {
+    VLB_REQUIRE(act == VLB200_ACT_NONE || act == VLB200_ACT_QUICK_GELU || act == VLB200_ACT_GELU_ERF, "gemm: unknown activation %d", act);
+    return gemm_ex_impl(A, lda, a_kmajor, B, ldb, b_kmajor, A2, lda2, B2, ldb2, K2, D, ldd, out_dtype, M, N, K, alpha, bias, act,
+                        residual, residual_dtype, ldr, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int vlb200_gemm_swiglu_bwd_bf16(const void* dy, int ld_dy, const void* Wd, int ld_wd, const void* A2, int lda2,
+                                           const void* B2, int ldb2, int K2, void* gate_up, int ld_gu, void* act, int ld_act,
+                                           int M, int ff, int K, void* stream) {
+    VLB_REQUIRE(dy && Wd && gate_up, "gemm_swiglu_bwd: null pointer");
+    VLB_REQUIRE(ff % 8 == 0 && ld_gu % 8 == 0 && ld_gu >= 2 * ff && (act == nullptr || (ld_act % 8 == 0 && ld_act >= ff)),
+                "gemm_swiglu_bwd: bad leading dimensions");
+    VLB_REQUIRE((reinterpret_cast<uintptr_t>(gate_up) & 15) == 0 && (reinterpret_cast<uintptr_t>(act) & 15) == 0,
+                "gemm_swiglu_bwd: gate_up / act must be 16-byte aligned");
+    // dact[M, ff] = dy[M, K] Wd[K, ff] (Wd = down_proj.weight [d_model, ff] row-major, i.e. an MN-major B operand)
+    return gemm_ex_impl(dy, ld_dy, 1, Wd, ld_wd, 0, A2, lda2, B2, ldb2, K2, act, act ? ld_act : 8, VLB200_BF16, M, ff, K, 1.0f, nullptr,
+                        vlb::gemm::ACT_SWIGLU_BWD, nullptr, VLB200_BF16, 0, 0, gate_up, ld_gu, stream);
 }
 
 extern "C" int vlb200_gemm_bf16(const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* D,

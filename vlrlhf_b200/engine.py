@@ -214,6 +214,7 @@ class LlavaDPOEngine:
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
+        self.fuse_swiglu_bwd = _os.environ.get("VLB200_FUSE_SWIGLU_BWD", "1") != "0"
         self.force_logit_means = False   # plugin: also produce TRL's logits/* means on no-grad passes (evaluation)
         self._micro_step = 0       # train_step calls so far (gradient_accumulation_steps micro-batches per optimizer step)
         self.last_lr = 0.0
@@ -539,7 +540,7 @@ class LlavaDPOEngine:
         self._reduce_bucket(self.layout.offsets["norm"], self.layout.size)          # norm + lm_head gradients are final
         h = self.buf("s.h", (T, d))
         act = self.buf("s.act", (T, cfg.ff))
-        dact = self.buf("b.dact", (T, cfg.ff))
+        dact = None if self.fuse_swiglu_bwd else self.buf("b.dact", (T, cfg.ff))
         dnorm = dxf  # reuse: [T, d] scratch for the gradients of the normed activations
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
@@ -556,10 +557,14 @@ class LlavaDPOEngine:
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- MLP
             ops.rmsnorm_fwd(xmid, w[f"L{i}.ln2"], cfg.rms_eps, out=h)                         # recompute h2
-            ops.swiglu_fwd(gu, act)                                                           # recompute act
-            ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"], accumulate=acc)              # dWd = dx^T act
-            ops.gemm(dx, w[f"L{i}.wd"], b_kmajor=False, out=dact)                             # dact = dx Wd
-            ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
+            if self.fuse_swiglu_bwd:   # dact = dx Wd never reaches HBM: SwiGLU backward (+ the act recompute) in its epilogue
+                ops.gemm_swiglu_bwd(dx, w[f"L{i}.wd"], gu, act)                               # gu <- dgu (in place), act recomputed
+                ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"], accumulate=acc)          # dWd = dx^T act
+            else:
+                ops.swiglu_fwd(gu, act)                                                       # recompute act
+                ops.gemm(dx, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wd"], accumulate=acc)          # dWd = dx^T act
+                ops.gemm(dx, w[f"L{i}.wd"], b_kmajor=False, out=dact)                         # dact = dx Wd
+                ops.swiglu_bwd(gu, dact, out=gu)                                              # dgu (in place)
             ops.gemm(gu, h, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.wgu"], accumulate=acc)               # dWgu = dgu^T h2
             ops.gemm(gu, w[f"L{i}.wgu"], b_kmajor=False, out=dnorm)                           # dh2 = dgu Wgu
             ops.rmsnorm_bwd(dnorm, xmid, w[f"L{i}.ln2"], rstd2, g[f"L{i}.ln2"], dres=dx, out=dx2,

@@ -222,7 +222,7 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
         dx2 = self.buf("b.dx1", (T, d))
         h = self.buf("s.h", (T, d))
         act = self.buf("s.act", (T, ff))
-        dact = self.buf("b.dact", (T, ff))
+        dact = None if self.fuse_swiglu_bwd else self.buf("b.dact", (T, ff))
         dnorm = dxf
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
@@ -237,17 +237,26 @@ class LlavaLoRADPOEngine(LlavaDPOEngine):
                 self._layer_fwd(None, i, x_in, sb, m, None, lora)   # recomputes up to gu + act + ts_d
             else:
                 sb = self._layer_bufs("a", f".{i}", m)
-                ops.swiglu_fwd(sb["gu"], act)                        # recompute act
+                if not self.fuse_swiglu_bwd:
+                    ops.swiglu_fwd(sb["gu"], act)                    # recompute act
             xmid, gu, qkv, att = (sb[k] for k in ("xmid", "gu", "qkv", "att"))
             rstd1, rstd2, lse = (sb[k] for k in ("rstd1", "rstd2", "lse"))
             # ---- down_proj
             ops.gemm(dx, sb["ts_d"], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.B"], accumulate=acc)      # dBd = dx^T ts_d
             ops.gemm(dx, lora[f"L{i}.d.B"], b_kmajor=False, out=d1, alpha=s)                  # dt = s dx Bd
-            ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"], accumulate=acc)             # dAd = dt^T act
-            ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
+            if self.fuse_swiglu_bwd:
+                # dact = dx Wd + dt Ad stays in TMEM: SwiGLU backward in the epilogue (gu <- dgu in place); act is recomputed
+                # there too unless the checkpointed forward above already produced it
+                ops.gemm_swiglu_bwd(dx, base[f"L{i}.wd"], gu, None if self.tc.activation_checkpointing else act,
+                                    a2=d1, b2=lora[f"L{i}.d.A"])
+                ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"], accumulate=acc)         # dAd = dt^T act
+            else:
+                ops.gemm(d1, act, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.d.A"], accumulate=acc)         # dAd = dt^T act
+                ops.gemm(dx, base[f"L{i}.wd"], b_kmajor=False, a2=d1, b2=lora[f"L{i}.d.A"], out=dact)   # dact = dx Wd + dt Ad
             # ---- gate | up
             ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h)                      # recompute h2
-            ops.swiglu_bwd(gu, dact, out=gu)                                                  # dgu (in place)
+            if not self.fuse_swiglu_bwd:
+                ops.swiglu_bwd(gu, dact, out=gu)                                              # dgu (in place)
             tsg = sb["ts_gu"]
             ops.gemm(gu[:, :ff], tsg[:, :r], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.g.B"], accumulate=acc)
             ops.gemm(gu[:, ff:], tsg[:, r:], a_kmajor=False, b_kmajor=False, out=g[f"L{i}.u.B"], accumulate=acc)

@@ -106,6 +106,30 @@ def gemm_swiglu(a: torch.Tensor, wgu: torch.Tensor, gu: torch.Tensor, act: torch
     return act
 
 
+def gemm_swiglu_bwd(dy: torch.Tensor, wd: torch.Tensor, gu: torch.Tensor, act: Optional[torch.Tensor] = None,
+                    a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gu <- [dgate | dup] IN PLACE from dact = dy @ wd (+ a2 @ b2) without storing dact; act (optional) <- silu(gate) * up.
+    dy [M, K], wd = down_proj.weight [K, ff] (row-major), a2 [M, K2] / b2 [K2, ff]: the LoRA term of the input gradient.
+    Bit-identical to gemm(dy, wd, b_kmajor=False) -> swiglu_fwd + swiglu_bwd (include/vlb200.h)."""
+    assert dy.dtype == wd.dtype == gu.dtype == torch.bfloat16
+    M, K = dy.shape
+    ff = wd.shape[1]
+    if wd.shape[0] != K or tuple(gu.shape) != (M, 2 * ff) or (act is not None and tuple(act.shape) != (M, ff)):
+        raise ValueError("gemm_swiglu_bwd: shape mismatch")
+    if (a2 is None) != (b2 is None):
+        raise ValueError("gemm_swiglu_bwd: a2 and b2 come together")
+    K2 = 0
+    if a2 is not None:
+        K2 = a2.shape[1]
+        if a2.shape[0] != M or tuple(b2.shape) != (K2, ff):
+            raise ValueError("gemm_swiglu_bwd: second operand pair does not match")
+    check(_L.vlb200_gemm_swiglu_bwd_bf16(_ptr(dy), _rowmajor_ld(dy), _ptr(wd), _rowmajor_ld(wd), _ptr(a2),
+                                         _rowmajor_ld(a2) if a2 is not None else 0, _ptr(b2),
+                                         _rowmajor_ld(b2) if b2 is not None else 0, K2, _ptr(gu), _rowmajor_ld(gu), _ptr(act),
+                                         _rowmajor_ld(act) if act is not None else 0, M, ff, K, _stream()))
+    return gu
+
+
 def set_gemm_raster_mb(mb: float):
     """L2 budget (MB) of the tile rasterisation; <= 0 restores VLB200_RASTER_MB / the default.  Tuning only."""
     check(_L.vlb200_set_gemm_raster_mb(float(mb)))
