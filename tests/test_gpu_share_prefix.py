@@ -181,7 +181,7 @@ def test_shared_step_equals_padded_step_and_oracle(pkg, tag, cfg_name, rcfg, sha
     parity_log.record(f"{tag} share_prefix", f"{loss_type} logps vs padded step", o1.policy_logps.cpu().numpy(),
                       o0.policy_logps.cpu().numpy(), bound_rel=2e-4)
     parity_log.record(f"{tag} share_prefix", f"{loss_type} losses vs padded step", o1.losses.cpu().numpy(), o0.losses.cpu().numpy(),
-                      bound_abs=5e-3)
+                      bound_abs=1.5e-2)
     wp, wr = R.make_policy_and_ref(rcfg, seed)
     names = ["language_model.model.layers.0.self_attn.q_proj.weight", "language_model.model.layers.0.self_attn.k_proj.weight",
              "language_model.model.layers.0.self_attn.v_proj.weight", "language_model.model.layers.1.mlp.down_proj.weight",
