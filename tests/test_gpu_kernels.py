@@ -509,3 +509,22 @@ def test_pack_merge_rows_equals_mirror(ops):
     wn = mock_ops.pack_merge_rows(mock_ops.llavanext_merge_index(nids, nam, nlb, *args), nlens)
     for k in ("src_map", "pos", "row_of_text", "img_pos", "row_starts"):
         assert torch.equal(getattr(mn, k).cpu().reshape(-1), getattr(wn, k).reshape(-1)), k
+
+
+@pytest.mark.parametrize("M,K,ff,r", [(600, 512, 1024, 0), (1000, 256, 768, 16), (130, 512, 256, 0)])
+def test_gemm_swiglu_bwd_fused_is_bit_identical(ops, M, K, ff, r):
+    """vlb200_gemm_swiglu_bwd_bf16 (SwiGLU backward + act recompute in the dgrad GEMM's epilogue) == gemm -> swiglu_fwd + swiglu_bwd,
+    bit for bit, on CTA-pair, single-CTA and ragged-edge shapes, with and without the LoRA operand pair."""
+    g = torch.Generator(device="cuda").manual_seed(M + ff)
+    rn = lambda *s: (torch.randn(*s, device="cuda", generator=g) * 0.5).to(torch.bfloat16)  # noqa: E731
+    dy, wd, gu = rn(M, K), rn(K, ff), rn(M, 2 * ff)
+    a2, b2 = (rn(M, r), rn(r, ff)) if r else (None, None)
+    dact = ops.gemm(dy, wd, b_kmajor=False, a2=a2, b2=b2)
+    act_want = ops.swiglu_fwd(gu)
+    dgu_want = ops.swiglu_bwd(gu, dact)
+    gu1, act1 = gu.clone(), torch.full((M, ff), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_swiglu_bwd(dy, wd, gu1, act1, a2=a2, b2=b2)
+    assert torch.equal(gu1, dgu_want) and torch.equal(act1, act_want)
+    gu2 = gu.clone()
+    ops.gemm_swiglu_bwd(dy, wd, gu2, None, a2=a2, b2=b2)          # act not wanted (checkpointed LoRA backward)
+    assert torch.equal(gu2, dgu_want)

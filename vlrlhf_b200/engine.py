@@ -214,7 +214,11 @@ class LlavaDPOEngine:
         self.sumsq_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.opt_step = 0
-        self.fuse_swiglu_bwd = _os.environ.get("VLB200_FUSE_SWIGLU_BWD", "1") != "0"
+        # SwiGLU backward inside the down-projection dgrad GEMM's epilogue (vlb200_gemm_swiglu_bwd_bf16: dact never reaches HBM,
+        # two elementwise launches per layer fewer, bit-identical results).  Measured on a B200 (profiles/r2d_*): 551 vs 543
+        # ms/step -- the epilogue's row-per-thread gate|up reads and writes (32 rows per warp request) cost more than the two
+        # coalesced elementwise passes save, so it stays opt-in until the epilogue stages through shared memory.
+        self.fuse_swiglu_bwd = _os.environ.get("VLB200_FUSE_SWIGLU_BWD", "0") == "1"
         self.force_logit_means = False   # plugin: also produce TRL's logits/* means on no-grad passes (evaluation)
         self._micro_step = 0       # train_step calls so far (gradient_accumulation_steps micro-batches per optimizer step)
         self.last_lr = 0.0
