@@ -680,6 +680,18 @@ def run_b200_lora(args, cfg, world, rank, local):
     vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + P * 2 * cfg.patch_k * dv
     proj = P * 2 * (dv * d + d * d) * 2
     flops = PAIRS_PER_GPU * (2 * per_seq + crops * (vit + proj)) + rows_lm * 2 * d * cfg.vocab * 3
+    # shared-prefix / packed rows execute fewer FLOPs than the padded formulation above: linear work scales with the rows, the
+    # attention of a sequence with n own and c context rows with n*n/2 + n*c
+    flops_exec = flops
+    if "seq_lens" in plan:
+        lens, pre = plan["seq_lens"], plan.get("prefix_rows") or [0] * PAIRS_PER_GPU
+        rows, att = 0, 0.0
+        for i in range(PAIRS_PER_GPU):
+            p_, c_, r_ = pre[i], lens[i] - pre[i], lens[PAIRS_PER_GPU + i] - pre[i]
+            rows += p_ + c_ + r_
+            att += 4.0 * d * L * (p_ * p_ / 2 + c_ * c_ / 2 + c_ * p_ + r_ * r_ / 2 + r_ * p_)
+        flops_exec = rows * 2 * p_layer * L * 3 + 4 * att + 3 * rows * 2 * L * r * ((3 * d + cfg.qkv_dim) + (hd + d) + 2 * (d + ff) + (ff + d)) \
+            + PAIRS_PER_GPU * crops * (vit + proj) + rows_lm * 2 * d * cfg.vocab * 3
     pk, pk_src = peaks()
     if rank == 0:
         pairs = PAIRS_PER_GPU * world
@@ -695,8 +707,8 @@ def run_b200_lora(args, cfg, world, rank, local):
                            "activation_checkpointing": eng.tc.activation_checkpointing, "pack_sequences": eng.tc.pack_sequences,
                            "share_prefix": eng.tc.share_prefix, "shared_prefix_rows_per_step": sum(plan.get("prefix_rows", [])),
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
-                           "step_tflop_algorithmic": flops / 1e12,
-                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                           "step_tflop_algorithmic": flops / 1e12, "step_tflop_executed": flops_exec / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops_exec / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
                 "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
