@@ -20,21 +20,10 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 
 @pytest.fixture(scope="module")
 def cpu_plugin():
-    import vlrlhf_b200  # noqa: F401
-    from tests import mock_ops
-    names = ("vlrlhf_b200.ops", "vlrlhf_b200.engine", "vlrlhf_b200.plugin")
-    saved = {k: sys.modules.get(k) for k in names}
-    sys.modules["vlrlhf_b200.ops"] = mock_ops
-    for k in names[1:]:
-        sys.modules.pop(k, None)
-    plugin = importlib.import_module("vlrlhf_b200.plugin")
-    from vlrlhf_b200 import config
-    yield plugin, config
-    for k, v in saved.items():
-        if v is None:
-            sys.modules.pop(k, None)
-        else:
-            sys.modules[k] = v
+    from tests.conftest import mocked_ops
+    with mocked_ops("vlrlhf_b200.engine", "vlrlhf_b200.plugin") as m:
+        from vlrlhf_b200 import config
+        yield m.modules["plugin"], config
 
 
 def _model(plugin, config, seed, **tc):

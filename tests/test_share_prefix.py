@@ -17,21 +17,11 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 
 @pytest.fixture(scope="module")
 def cpu_pkg():
-    import vlrlhf_b200  # noqa: F401
+    from tests.conftest import mocked_ops
     from tests import mock_ops
-    names = ("vlrlhf_b200.ops", "vlrlhf_b200.engine", "vlrlhf_b200.engine_lora", "vlrlhf_b200.plugin")
-    saved = {k: sys.modules.get(k) for k in names}
-    sys.modules["vlrlhf_b200.ops"] = mock_ops
-    for k in names[1:]:
-        sys.modules.pop(k, None)
-    engine = importlib.import_module("vlrlhf_b200.engine")
-    from vlrlhf_b200 import config, host
-    yield config, engine, host, mock_ops
-    for k, v in saved.items():
-        if v is None:
-            sys.modules.pop(k, None)
-        else:
-            sys.modules[k] = v
+    with mocked_ops("vlrlhf_b200.engine", "vlrlhf_b200.engine_lora", "vlrlhf_b200.plugin") as m:
+        from vlrlhf_b200 import config, host
+        yield config, m.modules["engine"], host, mock_ops
 
 
 def test_shared_prefix_rows_plan(cpu_pkg):
