@@ -403,7 +403,7 @@ def share_prefix_rows(m, seq_lens, prefix_rows):
         raise ValueError("share_prefix_rows: bad lengths")
     if m.packed:
         raise ValueError("share_prefix_rows: the index is already packed")
-    if m.total_feats is not None and m.reps is not None:
+    if getattr(m, "img_pos", None) is not None and m.total_feats is not None and m.reps is not None:   # (Qwen-VL: no row list)
         raise ValueError("share_prefix_rows: LLaVA-Next image rows (variable feature lengths) are not supported yet")
     for i in range(npair):
         if pre[i] < 0 or pre[i] > min(lens[i], lens[npair + i]):

@@ -159,3 +159,105 @@ def test_two_images_per_sequence_on_the_gpu(pkg):
         for k in ("rewards/chosen", "rewards/rejected", "logps/chosen", "logps/rejected"):
             assert abs(got[k] - float(metrics[k])) < 2e-3 * max(1.0, abs(float(metrics[k]))), k
         assert torch.isfinite(eng.grads.float()).all()
+
+
+def _shared_vs_padded(build_engine, batch, loss_type, grad_rel=2e-2):
+    """TrainConfig.share_prefix on an adapter engine: the padded step's log-probs / losses (<= 2e-4 relative: another row
+    grouping per attention tile), adapter gradients equal up to the accumulation order."""
+    from tests import parity_log
+    res = []
+    for share in (False, True):
+        eng = build_engine(share)
+        eng.train_step(batch, train=True)             # allocates the workspaces
+        if share:   # what a shared step does not write it must not read (see _packed_vs_padded)
+            for name, t in eng._stores.items():
+                if name.split(".")[0] in ("a", "s", "b", "x") and t.is_floating_point():
+                    t.fill_(float("nan"))
+        metrics = eng.train_step(batch, train=True)
+        torch.cuda.synchronize()
+        m = eng._saved["m"]
+        assert m.shared == share and (not share or (m.shared_rows > 0 and m.T < m.n_seq * m.S - m.shared_rows + 1))
+        res.append((metrics, eng.grads.clone().float()))
+        del eng
+    (m0, g0), (m1, g1) = res
+    for k in ("loss", "rewards/chosen", "rewards/rejected", "rewards/margins", "logps/chosen", "logps/rejected"):
+        assert abs(m0[k] - m1[k]) <= 3e-4 * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    assert torch.isfinite(g1).all()
+    rel = ((g0 - g1).norm() / g0.norm()).item()
+    cos = (torch.dot(g0, g1) / (g0.norm() * g1.norm())).item()
+    print(f"[shared vs padded {loss_type}] gradient rel l2 {rel:.3e}, cosine {cos:.6f}")
+    assert rel < grad_rel and cos > 0.9995, f"gradient rel l2 {rel}, cosine {cos}"
+
+
+@pytest.mark.parametrize("loss_type", ["sigmoid", "ddpo"])
+def test_qwen_shared_prefix_step_equals_padded_step(loss_type):
+    import vlrlhf_b200  # noqa: F401
+    from oracle import qwen_restate as Q
+    from vlrlhf_b200 import config, engine_qwen
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "g9_qwen_small.npz"))
+    batch = Q.make_batch(Q.SMALL_QWEN, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+
+    def build(share):
+        eng = engine_qwen.QwenVLDPOEngine(config.SMALL_QWEN, config.TrainConfig(loss_type=loss_type, learning_rate=1e-3,
+                                                                                  share_prefix=share), with_optimizer=False)
+        eng.init_synthetic(int(d["seed"]))
+        return eng
+
+    _shared_vs_padded(build, batch, loss_type)
+
+
+@pytest.mark.parametrize("loss_type", ["kto_pair", "ddpo"])
+def test_xc2_shared_prefix_step_equals_padded_step(loss_type):
+    import vlrlhf_b200  # noqa: F401
+    from oracle import restate as R
+    from oracle import xc2_restate as X
+    from vlrlhf_b200 import config, engine_xc2
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "g10_xc2_small.npz"))
+    batch = R.make_batch(X.SMALL_XC2, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+
+    def build(share):
+        eng = engine_xc2.XC2DPOEngine(config.SMALL_XC2, config.TrainConfig(loss_type=loss_type, learning_rate=1e-3,
+                                                                            share_prefix=share), with_optimizer=False)
+        eng.init_synthetic(int(d["seed"]))
+        return eng
+
+    _shared_vs_padded(build, batch, loss_type)
+
+
+@pytest.mark.parametrize("family", ["qwen", "xc2"])
+def test_7b_shape_fixtures_with_shared_prefix(family):
+    """Configs 3 and 5 at 7B shapes with the pair's prompt + image prefix laid out once: log-probs against the reference's
+    fp32 run (g12 / g13), same bound as the padded layout."""
+    import vlrlhf_b200  # noqa: F401
+    from oracle import restate as R
+    from tests import parity_log
+    from vlrlhf_b200 import config, host
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    if family == "qwen":
+        from oracle import qwen_restate as Q
+        from vlrlhf_b200 import engine_qwen
+        tag, rcfg = "g12_config3_qwen7b", Q.QWEN_VL_CHAT
+        mk = lambda: engine_qwen.QwenVLDPOEngine(config.QWEN_VL_CHAT, config.TrainConfig(share_prefix=True), with_optimizer=False)
+        make_batch = Q.make_batch
+    else:
+        from oracle import xc2_restate as X
+        from vlrlhf_b200 import engine_xc2
+        tag, rcfg = "g13_config5_xc2_7b", X.XC2_VL_7B
+        mk = lambda: engine_xc2.XC2DPOEngine(config.XC2_VL_7B, config.TrainConfig(share_prefix=True), with_optimizer=False)
+        make_batch = R.make_batch
+    path = os.path.join(G, tag + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{tag} fixture not generated")
+    d = np.load(path)
+    eng = mk()
+    eng.init_synthetic(int(d["seed"]))
+    batch = make_batch(rcfg, int(d["n_pairs"]), int(d["text_len"]), int(d["prompt_len"]), int(d["seed"]), ddpo_like=True)
+    cb = host.concatenated_inputs(batch)
+    ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
+    px = cb["concatenated_img_input_dict"]["pixel_values"]
+    plan = eng.host_row_plan(ids, am)
+    assert plan["prefix_rows"][0] > 0
+    out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False, **plan)
+    parity_log.check_step(tag + " share_prefix", out, d, rtol=1e-3 if family == "qwen" else 1.5e-3)   # (xc2: see test_gpu_xc2.py)
+    del eng
+    torch.cuda.empty_cache()

@@ -338,3 +338,24 @@ def test_qwen_packed_step_equals_padded_step(qpkg, loss_type, ckpt):
         if not k.startswith("logits/"):
             assert m0[k] == m1[k], k
     assert torch.equal(g0, g1) and float(g0.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("loss_type,ckpt", [("sigmoid", False), ("ddpo", True)])
+def test_qwen_shared_prefix_step_equals_padded_step(qpkg, loss_type, ckpt):
+    """TrainConfig.share_prefix on the Qwen-VL engine: the prompt incl. its 256 image placeholder tokens (S == L: a common token
+    is a common row) is laid out once per pair: log-probs, loss and rewards of the padded step, adapter gradients equal up to the
+    accumulation order."""
+    res = []
+    for share in (False, True):
+        eng, qcfg, d, batch = _setup(qpkg, "g9_qwen_tiny", loss_type=loss_type, share_prefix=share, activation_checkpointing=ckpt)
+        metrics = eng.train_step(batch, train=True)
+        m = eng._saved["m"]
+        assert m.shared == share
+        if share:
+            assert m.shared_rows >= int(d["n_pairs"]) * qcfg.n_queries and m.T < m.n_seq * m.S - m.shared_rows + 1
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in ("loss", "rewards/chosen", "rewards/rejected", "rewards/margins", "logps/chosen", "logps/rejected"):
+        assert abs(m0[k] - m1[k]) <= 5e-5 * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    g0, g1 = g0.float(), g1.float()
+    assert float(g0.abs().sum()) > 0 and float((g0 - g1).norm() / g0.norm()) < 2e-2

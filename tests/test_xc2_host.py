@@ -174,3 +174,25 @@ def test_xc2_packed_step_equals_padded_step(xpkg, loss_type, ckpt):
         if not k.startswith("logits/"):
             assert m0[k] == m1[k], k
     assert torch.equal(g0, g1) and float(g0.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("loss_type,ckpt", [("kto_pair", False), ("ddpo", True)])
+def test_xc2_shared_prefix_step_equals_padded_step(xpkg, loss_type, ckpt):
+    """TrainConfig.share_prefix on the XC2 engine: one copy of every pair's prompt + 1225-row image prefix (the partial-LoRA
+    image rows are listed once, the rejected copies become -1 and are skipped by the gathers / scatters): log-probs, loss and
+    rewards of the padded step, adapter gradients equal up to the accumulation order."""
+    res = []
+    for share in (False, True):
+        eng, xcfg, d, batch = _setup(xpkg, "g10_xc2_tiny", loss_type=loss_type, share_prefix=share, activation_checkpointing=ckpt)
+        metrics = eng.train_step(batch, train=True)
+        m = eng._saved["m"]
+        assert m.shared == share
+        if share:
+            assert m.shared_rows >= int(d["n_pairs"]) * (int(d["prompt_len"]) + xcfg.n_patches - 1) and m.T < m.n_seq * m.S - m.shared_rows + 1
+            assert int((eng._img_rows >= 0).sum()) == int(d["n_pairs"]) * xcfg.n_patches   # every image row once
+        res.append((metrics, eng.grads.clone()))
+    (m0, g0), (m1, g1) = res
+    for k in ("loss", "rewards/chosen", "rewards/rejected", "rewards/margins", "logps/chosen", "logps/rejected"):
+        assert abs(m0[k] - m1[k]) <= 5e-5 * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    g0, g1 = g0.float(), g1.float()
+    assert float(g0.abs().sum()) > 0 and float((g0 - g1).norm() / g0.norm()) < 2e-2

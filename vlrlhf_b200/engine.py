@@ -902,9 +902,13 @@ class LlavaDPOEngine:
         plan = {"seq_lens": self.host_seq_lens(ids, am, image_sizes, **kw)}
         if tc.share_prefix:
             from . import host
-            if self.cfg.family != "llava":
-                raise ValueError(f"share_prefix is implemented for the LLaVA-1.5 family (full fine-tune and LoRA), not {self.cfg.family!r}")
-            plan["prefix_rows"] = host.shared_prefix_rows(ids, am, self.cfg.image_token_index, self.cfg.n_patches)
+            fam = self.cfg.family
+            if fam in ("llava", "xc2"):     # one <image> token stands for n_patches merged rows
+                plan["prefix_rows"] = host.shared_prefix_rows(ids, am, self.cfg.image_token_index, self.cfg.n_patches)
+            elif fam == "qwen_vl":          # the 256 image rows are placeholder tokens of the text itself (S == L)
+                plan["prefix_rows"] = host.shared_prefix_rows(ids, am, -1, 1)
+            else:
+                raise ValueError(f"share_prefix is not implemented for {fam!r} (LLaVA-Next: variable packed feature lengths)")
         return plan
 
     def host_seq_lens(self, ids, am, image_sizes=None, imgs_per_seq: int = 1) -> List[int]:

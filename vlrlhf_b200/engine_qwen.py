@@ -30,7 +30,7 @@ import torch
 
 from . import ops
 from .config import QwenModelConfig, qwen_lora_specs, qwen_weight_specs, tensor_seed
-from .engine import Arena, LlavaDPOEngine, Weights
+from .engine import Arena, LlavaDPOEngine, Weights, attn_backward, attn_forward
 
 
 def _lora_layout(cfg: QwenModelConfig) -> Arena:
@@ -320,8 +320,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", r, "l.ts")
             ops.gemm(h, base[f"L{i}.wqkv"], a2=ts, b2=lora[f"L{i}.qkv.B"], out=qkv, bias=base[f"L{i}.bqkv"])
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh)
-        ops.attn_fwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, H, dh, True,
-                        1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
+        attn_forward(m, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, b["lse"], H, H, dh, 1.0 / math.sqrt(dh))
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -378,7 +377,7 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         dnorm = dxf
         dqkv = self.buf("b.dqkv", (T, 3 * d))
         datt = self.buf("b.datt", (T, d))
-        delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
+        delta = self.buf("b.delta", (m.n_attn_seq, H, m.S), torch.float32)
         dt = self.buf("b.dt", (T, 2 * r))   # dt = bf16(s * dy B) of the two MLP adapters, side by side
         dr = self.buf("b.dr", (T, r))       # same for the r-wide adapters (c_attn, attn.c_proj)
         scale = 1.0 / math.sqrt(dh)
@@ -409,9 +408,8 @@ class QwenVLDPOEngine(LlavaDPOEngine):
             ops.gemm(dx2, lora[f"L{i}.o.B"], b_kmajor=False, out=dr, alpha=s)                 # dt = s dxmid Bo
             ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)            # dAo = dt^T att
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)   # datt = dxmid Wo + dt Ao
-            ops.attn_bwd_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
-                            dqkv[:, 2 * d:], m.seqlens, m.n_seq, m.S, H, H, dh, True, scale, row_starts=m.starts,
-                            total_rows=m.T)
+            attn_backward(m, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, delta, dqkv[:, :d], dqkv[:, d:2 * d],
+                            dqkv[:, 2 * d:], H, H, dh, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, 2 * H, dh, inverse=True)
             # ---- fused qkv projection (LoRA on attn.c_attn; the bias is frozen)
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
@@ -441,12 +439,17 @@ class QwenVLDPOEngine(LlavaDPOEngine):
         return ids, am, lb, px, wt
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
-                      feats=None, m=None, seq_lens=None):
+                      feats=None, m=None, seq_lens=None, prefix_rows=None):
         cfg = self.cfg
         self._anyres = None
         if m is None:
             m = ops.qwen_merge_index(ids, am, lb, cfg.n_queries, px.shape[0], 1, cfg.image_start_id, cfg.ignore_index)
-            if self.tc.pack_sequences:   # S == L here: the surviving rows are the attended tokens
+            if self.tc.share_prefix:     # one copy of every pair's common prefix (engine.py; implies packed rows)
+                if seq_lens is None or prefix_rows is None:
+                    raise ValueError("share_prefix needs the host-side row plan: pass **engine.host_row_plan(ids, am)")
+                ops.share_prefix_rows(m, seq_lens, prefix_rows)
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+            elif self.tc.pack_sequences:   # S == L here: the surviving rows are the attended tokens
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         self.ensure_rope_len(m.S)

@@ -26,7 +26,7 @@ import torch
 
 from . import ops
 from .config import XC2ModelConfig, tensor_seed, xc2_lora_specs, xc2_weight_specs
-from .engine import Arena, LlavaDPOEngine, Weights, _vision_layout
+from .engine import Arena, LlavaDPOEngine, Weights, _vision_layout, attn_backward, attn_forward
 from .engine_qwen import QwenVLDPOEngine
 
 
@@ -81,6 +81,18 @@ class XC2DPOEngine(QwenVLDPOEngine):
         self._dw_scratch = torch.zeros(cfg.hidden, dtype=torch.bfloat16, device=self.device)
         self._perm = qkv_permutation(cfg).to(self.device)
         self._inv_perm = torch.argsort(self._perm)
+        # Combined second operands [lora_B | Plora_B] ([out, r + pr]) of the linears whose output is bf16 (wqkv, w1, w3): the
+        # trainable LoRA term and the frozen partial-LoRA term then enter the base GEMM's accumulator TOGETHER (one rounding of
+        # the output; the r1 path scatter-added the partial-LoRA term into the rounded result: 1.2e-3 on the 7B-shape log-probs).
+        # Copies: the Plora columns are refreshed when the base weights change, the lora columns before every policy pass.
+        ca = Arena()
+        for i in range(cfg.layers):
+            ca.add(f"L{i}.qkv.Bc", (cfg.qkv_dim, cfg.lora_r + cfg.plora_r))
+            ca.add(f"L{i}.w1.Bc", (cfg.ff, cfg.lora_r + cfg.plora_r)); ca.add(f"L{i}.w3.Bc", (cfg.ff, cfg.lora_r + cfg.plora_r))
+        self.clayout = ca
+        self.cparams = torch.zeros(ca.size, dtype=torch.bfloat16, device=self.device)
+        self.comb = Weights(ca, self.cparams)
+        self._comb_base_stale = True
 
     # ------------------------------------------------------------------ names (storage views; wqkv-row tensors are permuted)
     def _lora_storage(self, w: Weights) -> Dict[str, torch.Tensor]:
@@ -126,6 +138,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         return {k: (v.index_select(0, self._inv_perm) if self._qkv_rows(k) else v) for k, v in self._base_storage().items()}
 
     def _store(self, dst: Dict[str, torch.Tensor], name: str, t: torch.Tensor):
+        self._comb_base_stale = True   # (a base tensor may have changed: the combined operands are rebuilt at the next pass)
         t = t.to(self.device, torch.bfloat16).reshape(dst[name].shape)
         dst[name].copy_(t.index_select(0, self._perm) if self._qkv_rows(name) else t)
 
@@ -133,6 +146,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         """Seeded random-init base (incl. the frozen PLoRA adapters) + trainable adapters, bit-identical to
         oracle.xc2_restate.make_weights."""
         self.wait_optimizer()
+        self._comb_base_stale = True
         cfg = self.cfg
         base, lora = self._base_storage(), self._lora_storage(self.policy)
 
@@ -196,6 +210,46 @@ class XC2DPOEngine(QwenVLDPOEngine):
     def vision_features(self, pixels: torch.Tensor) -> torch.Tensor:
         return LlavaDPOEngine.vision_features(self, pixels)
 
+    # ------------------------------------------------------------------ combined [lora_B | Plora_B] operands
+    def _refresh_comb(self, lora: Optional[Weights]):
+        """Copy the frozen Plora_B columns (when the base changed) and the current lora_B columns (policy pass) into the
+        combined second operands."""
+        cfg = self.cfg
+        r, pr = cfg.lora_r, cfg.plora_r
+        k2 = r + pr
+        names = (("qkv", "qkv.B", "p.qkv.B"), ("w1", "w1.B", "p.w1.B"), ("w3", "w3.B", "p.w3.B"))
+        for i in range(cfg.layers):
+            for cn, ln, pn in names:
+                dst = self.comb[f"L{i}.{cn}.Bc"]
+                if self._comb_base_stale:
+                    src = self.base[f"L{i}.{pn}"]
+                    ops.copy_rows(src, 0, pr, 0, dst[:, r:], 0, k2, 1, src.shape[0], pr)
+                if lora is not None:
+                    src = lora[f"L{i}.{ln}"]
+                    ops.copy_rows(src, 0, r, 0, dst, 0, k2, 1, src.shape[0], r)
+        self._comb_base_stale = False
+
+    def _adapter_operand(self, xin: torch.Tensor, A_p: torch.Tensor, ts: Optional[torch.Tensor], name: str, n_out: int):
+        """-> list of n_out activation operands [T, r + pr] = [ts_k | scale_p * (x A_p_k^T) on the image rows, 0 elsewhere]
+        (ts: the trainable LoRA activations [T, n_out * r] of the policy pass, or None)."""
+        cfg = self.cfg
+        r, pr, T = cfg.lora_r, cfg.plora_r, xin.shape[0]
+        rows = self._img_rows
+        n = rows.numel()
+        xc = self.buf(f"p.xc.{xin.shape[1]}", (n, xin.shape[1]))
+        ops.gather_rows(xin, rows, xc)
+        tp = self.buf(f"p.t.{A_p.shape[0]}", (n, A_p.shape[0]))
+        ops.gemm(xc, A_p, out=tp, alpha=cfg.plora_scale)
+        outs = []
+        for k in range(n_out):
+            ta = self.buf(f"l.ts_all.{name}.{k}", (T, r + pr))
+            ops.zero_(ta)                                   # text rows of the partial-LoRA columns (and the lora columns when off)
+            if ts is not None:
+                ops.copy_rows(ts[:, k * r:(k + 1) * r], 0, ts.stride(0), 0, ta, 0, r + pr, 1, T, r)
+            ops.scatter_rows(tp[:, k * pr:(k + 1) * pr], rows, ta[:, r:])
+            outs.append(ta)
+        return outs
+
     # ------------------------------------------------------------------ one linear: base + trainable LoRA + frozen PLoRA
     def _plora_fwd(self, xin: torch.Tensor, A: torch.Tensor, outs, m, tag: str):
         """outs: list of (B [out, pr], dst [T, out] bf16|fp32, column range of the gathered t)."""
@@ -247,15 +301,17 @@ class XC2DPOEngine(QwenVLDPOEngine):
             return ts
 
         ops.rmsnorm_fwd(x, base[f"L{i}.ln1"], cfg.rms_eps, out=h, rstd=b["rstd1"])
+        # y = x W^T + [ts | tp] [lora_B | Plora_B]^T in ONE launch (one rounding of the bf16 output); reference pass: the
+        # partial-LoRA columns only
+        ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", r, "l.ts") if lora is not None else None
+        (ta,) = self._adapter_operand(h, base[f"L{i}.p.qkv.A"], ts, "qkv", 1)
+        bc = self.comb[f"L{i}.qkv.Bc"]
         if lora is None:
-            ops.gemm(h, base[f"L{i}.wqkv"], out=qkv)
+            ops.gemm(h, base[f"L{i}.wqkv"], a2=ta[:, r:], b2=bc[:, r:], out=qkv)
         else:
-            ts = lora_t(h, lora[f"L{i}.qkv.A"], "ts_qkv", r, "l.ts")
-            ops.gemm(h, base[f"L{i}.wqkv"], a2=ts, b2=lora[f"L{i}.qkv.B"], out=qkv)   # y = x W^T + ts B^T in one launch
-        self._plora_fwd(h, base[f"L{i}.p.qkv.A"], [(base[f"L{i}.p.qkv.B"], qkv, slice(0, pr))], m, "qkv")
+            ops.gemm(h, base[f"L{i}.wqkv"], a2=ta, b2=bc, out=qkv)
         ops.rope_(qkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh)
-        ops.attn_fwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], m.seqlens, m.n_seq, m.S, H, KV, dh,
-                        True, 1.0 / math.sqrt(dh), row_starts=m.starts, total_rows=m.T)
+        attn_forward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, b["lse"], H, KV, dh, 1.0 / math.sqrt(dh))
         if lora is None:
             ops.gemm(att, base[f"L{i}.wo"], out=xmid, residual=x)
         else:
@@ -263,15 +319,12 @@ class XC2DPOEngine(QwenVLDPOEngine):
             ops.gemm(att, base[f"L{i}.wo"], a2=ts, b2=lora[f"L{i}.o.B"], out=xmid, residual=x)
         self._plora_fwd(att, base[f"L{i}.p.o.A"], [(base[f"L{i}.p.o.B"], xmid, slice(0, pr))], m, "o")
         ops.rmsnorm_fwd(xmid, base[f"L{i}.ln2"], cfg.rms_eps, out=h, rstd=b["rstd2"])
-        if lora is None:
-            ops.gemm(h, base[f"L{i}.wgu"], out=gu)
-        else:
-            ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r, "l.ts2")
-            wgu = base[f"L{i}.wgu"]
-            ops.gemm(h, wgu[:ff], a2=ts[:, :r], b2=lora[f"L{i}.w1.B"], out=gu[:, :ff])
-            ops.gemm(h, wgu[ff:], a2=ts[:, r:], b2=lora[f"L{i}.w3.B"], out=gu[:, ff:])
-        self._plora_fwd(h, base[f"L{i}.p.gu.A"], [(base[f"L{i}.p.w1.B"], gu[:, :ff], slice(0, pr)),
-                                                   (base[f"L{i}.p.w3.B"], gu[:, ff:], slice(pr, 2 * pr))], m, "gu")
+        ts = lora_t(h, lora[f"L{i}.gu.A"], "ts_gu", 2 * r, "l.ts2") if lora is not None else None
+        ta1, ta3 = self._adapter_operand(h, base[f"L{i}.p.gu.A"], ts, "gu", 2)
+        wgu = base[f"L{i}.wgu"]
+        c0 = r if lora is None else 0
+        ops.gemm(h, wgu[:ff], a2=ta1[:, c0:], b2=self.comb[f"L{i}.w1.Bc"][:, c0:], out=gu[:, :ff])
+        ops.gemm(h, wgu[ff:], a2=ta3[:, c0:], b2=self.comb[f"L{i}.w3.Bc"][:, c0:], out=gu[:, ff:])
         if xn is not None or (lora is not None and "ts_d" in b):
             act = self.buf("s.act", (T, ff))
             ops.swiglu_fwd(gu, act)
@@ -289,6 +342,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         cfg, base = self.cfg, self.base
         d, T = cfg.hidden, m.T
         lora = self.policy if tag == "policy" else None
+        self._refresh_comb(lora)
         nimg = feats.shape[0]
         ph = self.buf("p.h_ref", (nimg, d))                               # frozen projector (build_mlp.py:14-28)
         ops.gemm(feats, base["proj.w1"], out=ph, bias=base["proj.b1"], act=ops.ACT_GELU_ERF)
@@ -327,7 +381,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         dnorm = dxf
         dqkv = self.buf("b.dqkv", (T, cfg.qkv_dim))
         datt = self.buf("b.datt", (T, hd))
-        delta = self.buf("b.delta", (m.n_seq, H, m.S), torch.float32)
+        delta = self.buf("b.delta", (m.n_attn_seq, H, m.S), torch.float32)
         dt = self.buf("b.dt", (T, 2 * r))   # dt = bf16(s * dy B): gate | up side by side; dr: the r-wide adapters
         dr = self.buf("b.dr", (T, r))
         scale = 1.0 / math.sqrt(dh)
@@ -366,9 +420,8 @@ class XC2DPOEngine(QwenVLDPOEngine):
             ops.gemm(dr, att, a_kmajor=False, b_kmajor=False, out=g[f"L{i}.o.A"], accumulate=acc)
             ops.gemm(dx2, base[f"L{i}.wo"], b_kmajor=False, a2=dr, b2=lora[f"L{i}.o.A"], out=datt)
             self._plora_bwd([(dx2, base[f"L{i}.p.o.B"], slice(0, pr))], base[f"L{i}.p.o.A"], datt)
-            ops.attn_bwd_tc(qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
-                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], m.seqlens, m.n_seq, m.S, H, KV, dh, True, scale,
-                            row_starts=m.starts, total_rows=m.T)
+            attn_backward(m, qkv[:, :hd], qkv[:, hd:hd + kvd], qkv[:, hd + kvd:], att, datt, lse, delta, dqkv[:, :hd],
+                            dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:], H, KV, dh, scale)
             ops.rope_(dqkv, m.pos, self.rope_cos, self.rope_sin, H + KV, dh, inverse=True)
             # ---- fused qkv projection
             ops.rmsnorm_fwd(x_in, base[f"L{i}.ln1"], cfg.rms_eps, out=h)                      # recompute h1
@@ -388,7 +441,7 @@ class XC2DPOEngine(QwenVLDPOEngine):
         return QwenVLDPOEngine.prepare_inputs(self, input_ids, attention_mask, labels, pixel_values, ddpo_weight)
 
     def forward_logps(self, ids, am, lb, px, ddpo_weight=None, anyres=None, which: str = "policy", save: bool = False,
-                      feats=None, m=None, seq_lens=None):
+                      feats=None, m=None, seq_lens=None, prefix_rows=None):
         cfg = self.cfg
         self._anyres = None
         if m is None:
@@ -396,7 +449,12 @@ class XC2DPOEngine(QwenVLDPOEngine):
                                       cfg.ignore_index)
             # rotary positions are arange(S) for every row, padded or not (modeling_internlm2.py:186-203)
             m.pos = torch.arange(m.S, dtype=torch.int32, device=ids.device).repeat(m.n_seq)
-            if self.tc.pack_sequences:   # drop the padding rows (the rotary positions above are packed along)
+            if self.tc.share_prefix:     # one copy of every pair's common prefix (engine.py; the rotary positions are packed along)
+                if seq_lens is None or prefix_rows is None:
+                    raise ValueError("share_prefix needs the host-side row plan: pass **engine.host_row_plan(ids, am)")
+                ops.share_prefix_rows(m, seq_lens, prefix_rows)
+                self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
+            elif self.tc.pack_sequences:   # drop the padding rows (the rotary positions above are packed along)
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         # flat merged rows of every image position (the PLoRA row mask im_mask, __init__.py:87-104); packed: already absolute
