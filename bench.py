@@ -297,7 +297,7 @@ def run_b200(args):
            "small_lora": config.SMALL_LORA, "next_small_lora": config.SMALL_NEXT_LORA}[args.model]
     text_len, prompt_len = (TEXT_LEN, PROMPT_LEN) if args.model in ("7b", "next7b") else (96, 24)
     is_next = cfg.family == "llava_next"
-    if cfg.family != "llava" or args.pack:
+    if cfg.family == "llava_next" or args.pack:   # (LLaVA-Next: variable packed feature lengths, not built)
         args.share_prefix = False
     if cfg.family in ("qwen_vl", "xc2"):
         return run_b200_qwen(args, cfg, world, rank, local)
@@ -531,14 +531,14 @@ def run_b200_qwen(args, cfg, world, rank, local):
         text_len, prompt_len = (1024, 32) if full else (96, 24)
         loss_type = "kto_pair" if args.loss_type == "sigmoid" else args.loss_type
         eng = engine_xc2.XC2DPOEngine(cfg, config.TrainConfig(loss_type=loss_type, learning_rate=1e-5, weight_decay=0.1,
-                                                              pack_sequences=args.pack))
+                                                              pack_sequences=args.pack, share_prefix=args.share_prefix))
         eng.init_synthetic(0)
         batch = synthetic.make_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
         args.loss_type = loss_type
     else:
         text_len, prompt_len = (1024, 320) if full else (128, 72)
         eng = engine_qwen.QwenVLDPOEngine(cfg, config.TrainConfig(loss_type=args.loss_type, learning_rate=1e-5, weight_decay=0.05,
-                                                                  pack_sequences=args.pack))
+                                                                  pack_sequences=args.pack, share_prefix=args.share_prefix))
         eng.init_synthetic(0)
         batch = synthetic.make_qwen_batch(cfg, PAIRS_PER_GPU, text_len, prompt_len, seed=1000 + rank, pin=True)
     cb = host.concatenated_inputs(batch)
@@ -565,8 +565,8 @@ def run_b200_qwen(args, cfg, world, rank, local):
         return float(ms) / steps
 
     last = {}
-    seq_lens = eng.host_seq_lens(ids_h, am_h) if args.pack else None
-    step_dev = lambda: eng.step(*dev_inputs, train=True, seq_lens=seq_lens)  # noqa: E731
+    plan = eng.host_row_plan(ids_h, am_h)   # {} for the padded layout; seq_lens (+ prefix_rows) for packed / shared-prefix rows
+    step_dev = lambda: eng.step(*dev_inputs, train=True, **plan)  # noqa: E731
     step_e2e = lambda: last.update(eng.train_step(batch, train=True))  # noqa: E731
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -600,10 +600,12 @@ def run_b200_qwen(args, cfg, world, rank, local):
                                         "w1/w2, frozen ViT-bigG+resampler, 4 pairs/GPU, text 1024 incl. 256 image tokens, 1x448px "
                                         "image/pair") if full else f"{args.model} (dev config, NOT the benchmark)",
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": text_len, "loss_type": args.loss_type,
-                           "pack_sequences": eng.tc.pack_sequences,
+                           "pack_sequences": eng.tc.pack_sequences, "share_prefix": eng.tc.share_prefix,
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
-                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "step_tensor_util_note": "algorithmic FLOPs of the PADDED formulation / time / sustained cuBLAS peak; under "
+                                                    "share_prefix the step executes fewer (the pair's common prefix rows run once)"},
                 "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
@@ -744,10 +746,12 @@ def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, l
                                         "4 pairs/GPU, text 1024 (2248 merged), 1x490px image/pair") if args.model == "xc2_7b"
                            else f"{args.model} (dev config, NOT the benchmark)",
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": args.loss_type,
-                           "pack_sequences": eng.tc.pack_sequences,
+                           "pack_sequences": eng.tc.pack_sequences, "share_prefix": eng.tc.share_prefix,
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
                            "step_tflop_algorithmic": flops / 1e12,
-                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
+                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "step_tensor_util_note": "algorithmic FLOPs of the PADDED formulation / time / sustained cuBLAS peak; under "
+                                                    "share_prefix the step executes fewer (the pair's common prefix rows run once)"},
                 "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}

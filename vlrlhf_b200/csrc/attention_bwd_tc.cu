@@ -29,7 +29,6 @@ using namespace ptx;
 
 constexpr int BX = 128;  // stationary rows
 constexpr int BY = 64;   // streamed rows
-constexpr int NST = 3;   // streamed-tile ring depth
 constexpr int NTHREADS = 320;  // TMA warp, MMA warp, 8 elementwise warps (two per TMEM lane quadrant)
 constexpr int NEW = 8;         // elementwise warps
 constexpr float LOG2E_F = 1.4426950408889634f;
@@ -49,6 +48,10 @@ struct Params {
     float scale;
     int n_xb, n_work;
 };
+
+// diagnostics (DBG bit 8): cycles one elementwise thread per CTA spends in each phase of its loop, summed over the grid
+__device__ unsigned long long g_bwd_prof[32];   // [MODE][16]
+#define VLB_PROF(i) do { if (DBG & 8) { const long long t_ = clock64(); prof[i] += (unsigned long long)(t_ - tp); tp = t_; } } while (0)
 
 __device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -127,7 +130,15 @@ __device__ __forceinline__ void item_tile(const Item& it, int t, Seg& sg, int& y
     yt = sg.yb + u;
 }
 
-template <int DH, int MODE>
+// TS: the elementwise results (P^T / dS^T, or dS) stay in TENSOR MEMORY: each elementwise warp writes its 32 bf16 columns,
+// packed two per 32-bit column, over the first 16 columns of the 32 fp32 score columns it has just read (tcgen05.st), and the
+// accumulate MMAs take their A operand from TMEM (TS mode, one K = 16 step = 8 columns).  No E stores to / A reads from
+// shared memory (64 of 224 KB of shared-memory traffic per streamed tile), no generic->async proxy fence, and the 64 KB of E
+// buffers become two more stages of the streamed-tile ring.  A score buffer is then recycled in MMA issue order (the score
+// MMAs of tile t+2 are issued after the accumulate MMAs of tile t), not by a barrier.
+// DBG (diagnostics, wrong results, timing only), a bit mask: 1 = no MMAs are issued (barriers only), 2 = no exponentials,
+// 4 = no streamed-tile loads
+template <int DH, int MODE, bool TS, int DBG = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_constant__ CUtensorMap tma_x2,
                    const __grid_constant__ CUtensorMap tma_y1, const __grid_constant__ CUtensorMap tma_y2, const Params p) {
@@ -137,6 +148,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     constexpr int X_BYTES = NCH * XCH;       // one stationary tile
     constexpr int Y_BYTES = NCH * YCH;       // one streamed tile
     constexpr int E_BYTES = BX * 128;        // [128 rows][64 bf16]
+    constexpr int NST = TS ? 5 : 3;          // streamed-tile ring depth
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t TM_T1 = 0, TM_T2 = 128, TM_A1 = 256, TM_A2 = 384;  // T buffers: +64 per stage
 
@@ -146,7 +158,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     uint8_t* sX2 = sX1 + X_BYTES;
     uint8_t* sY = sX2 + X_BYTES;                 // NST stages of (Y1, Y2)
     uint8_t* sE = sY + NST * 2 * Y_BYTES;        // 2 buffers of (E1, E2)
-    float* sLse = reinterpret_cast<float*>(sE + 4 * E_BYTES);  // [2][64] (MODE 0)
+    float* sLse = reinterpret_cast<float*>(sE + (TS ? 0 : 4 * E_BYTES));  // [2][64] (MODE 0)
     float* sDelta = sLse + 2 * BY;                           // [2][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BY);
     uint64_t* x_full = bars + 0;
@@ -202,6 +214,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     item_tile(it, t, sg, yt, rep);
                     const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
                     mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
+                    if (DBG & 4) { mbar_arrive(&y_full[st]); continue; }
                     mbar_arrive_expect_tx(&y_full[st], 2 * Y_BYTES);
                     uint8_t* y1 = sY + st * 2 * Y_BYTES;
                     uint8_t* y2 = y1 + Y_BYTES;
@@ -237,7 +250,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     bool progressed = false;
                     if (ts < n) {
                         const uint32_t yi = y0 + ts, st = yi % NST, tb = tc & 1;
-                        if (mbar_try_wait(&y_full[st], (yi / NST) & 1) && mbar_try_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1)) {
+                        bool t_free;   // TS: the buffer holds tile ts-2's E operands until its accumulate MMAs have been issued
+                        if (TS) t_free = ts - ta < 2;
+                        else t_free = mbar_try_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1);
+                        if (t_free && mbar_try_wait(&y_full[st], (yi / NST) & 1)) {
                             tcgen05_fence_after();
                             const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
                             // descriptors: constant fields built once, only the 16-byte-granular start address advances
@@ -246,11 +262,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
                                 const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                if (DBG & 1) continue;
                                 umma_f16_ss(tmem_base + TM_T1 + tb * BY, dx1 + xo, dy1 + yo, idesc_t, k != 0);
                             }
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
                                 const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                if (DBG & 1) continue;
                                 umma_f16_ss(tmem_base + TM_T2 + tb * BY, dx2 + xo, dy2 + yo, idesc_t, k != 0);
                             }
                             umma_commit(&t_full[tb]);
@@ -270,10 +288,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                             const uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
 #pragma unroll
                             for (int k = 0; k < BY / 16; ++k) {
-                                if (MODE == 0)  // dV += P^T dO
-                                    umma_f16_ss(tmem_base + TM_A1, de1 + (uint64_t)(k * 2), by2 + (uint64_t)(k * 128), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
-                                // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
-                                umma_f16_ss(tmem_base + TM_A2, de2 + (uint64_t)(k * 2), by1 + (uint64_t)(k * 128), idesc_a, (ta != 0 || k != 0) ? 1u : 0u);
+                                const uint32_t acc = (ta != 0 || k != 0) ? 1u : 0u;
+                                if (DBG & 1) continue;
+                                if (TS) {
+                                    // streamed rows 16k..16k+15: written by elementwise half k/2 at columns half*32 + (k%2)*8 of the score buffer
+                                    const uint32_t ac = eb * BY + (k >> 1) * 32 + (k & 1) * 8;
+                                    if (MODE == 0) umma_f16_ts(tmem_base + TM_A1, tmem_base + TM_T1 + ac, by2 + (uint64_t)(k * 128), idesc_a, acc);
+                                    umma_f16_ts(tmem_base + TM_A2, tmem_base + TM_T2 + ac, by1 + (uint64_t)(k * 128), idesc_a, acc);
+                                } else {
+                                    if (MODE == 0)  // dV += P^T dO
+                                        umma_f16_ss(tmem_base + TM_A1, de1 + (uint64_t)(k * 2), by2 + (uint64_t)(k * 128), idesc_a, acc);
+                                    // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
+                                    umma_f16_ss(tmem_base + TM_A2, de2 + (uint64_t)(k * 2), by1 + (uint64_t)(k * 128), idesc_a, acc);
+                                }
                             }
                             umma_commit(&e_done[eb]);
                             umma_commit(&y_empty[st]);
@@ -304,11 +331,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
         uint32_t tc = 0, ec = 0;
+        unsigned long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tp = clock64();
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int b, hx, xb;
             item_coords<MODE>(p, w, b, hx, xb);
             const Item it = item_plan<MODE>(p, b, xb);
             const int n = it.per_rep * it.reps;
+            if (DBG & 8) { prof[8] += 1; prof[9] += n; }
             const int kv_len = it.kv_len;
             const int x0 = xb * BX;
             const int xrow = x0 + r;  // MODE 0: key index ; MODE 1: query index
@@ -336,6 +366,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 fetch_stats(0);
                 if (tid_e < BY) { sLse[(tc & 1) * BY + tid_e] = nl; sDelta[(tc & 1) * BY + tid_e] = nd; }
             }
+            VLB_PROF(0);   // item start
             for (int t = 0; t < n; ++t, ++tc) {
                 const uint32_t tb = tc & 1;
                 Seg sg; int yt, rep_unused;
@@ -347,15 +378,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     asm volatile("bar.sync 1, 256;" ::: "memory");  // statistics of tile t are visible
                     fetch_stats(t + 1);                              // global loads for tile t+1 fly during this tile
                 }
+                VLB_PROF(1);   // tile coordinates, statistics barrier + prefetch
                 mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
                 tcgen05_fence_after();
+                VLB_PROF(2);   // wait for the score tiles
                 uint32_t t1[32], t2[32];
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, t1);
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, t2);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane_idx == 0) mbar_arrive(&t_empty[tb]);
+                if (!TS && lane_idx == 0) mbar_arrive(&t_empty[tb]);
+                VLB_PROF(3);   // TMEM -> registers
                 // mask only tiles that touch the causal diagonal or the end of the valid range
                 const int ymax = y0 + BY - 1;
                 bool need_mask;
@@ -384,7 +418,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int col = half * 32 + c4 + e;
-                            float pr = ex2_approx(fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]));
+                            float pr = fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]);
+                            if (!(DBG & 2)) pr = ex2_approx(pr);
                             if (MASKED) {
                                 // stationary index xrow < kv_len, streamed index y0 + col < ylen; causal inside a sequence only
                                 const int key = MODE == 0 ? xrow : y0 + col;
@@ -400,23 +435,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 };
                 if (need_mask) tile_body(std::true_type{});
                 else tile_body(std::false_type{});
+                VLB_PROF(4);   // elementwise
                 // this E buffer is free once the accumulate MMAs of its previous use (two tiles back) have completed
                 const uint32_t eb = ec & 1;
-                if ((ec >> 1) > 0) mbar_wait(&e_done[eb], ((ec >> 1) - 1) & 1, 90 + eb);
-                uint8_t* sE1 = sE + eb * 2 * E_BYTES;
-                uint8_t* sE2 = sE1 + E_BYTES;
+                if (TS) {   // over the score columns this warp has read (its own lanes, its own 32 columns)
+                    if (MODE == 0) tmem_st_32x32_x16(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, e1);
+                    tmem_st_32x32_x16(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, e2);
+                    tmem_st_wait_all();
+                } else {
+                    if ((ec >> 1) > 0) mbar_wait(&e_done[eb], ((ec >> 1) - 1) & 1, 90 + eb);
+                    uint8_t* sE1 = sE + eb * 2 * E_BYTES;
+                    uint8_t* sE2 = sE1 + E_BYTES;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int unit = half * 4 + u;
-                    const uint32_t off = r * 128 + ((unit ^ (r & 7)) << 4);
-                    if (MODE == 0) *reinterpret_cast<uint4*>(sE1 + off) = make_uint4(e1[u * 4], e1[u * 4 + 1], e1[u * 4 + 2], e1[u * 4 + 3]);
-                    *reinterpret_cast<uint4*>(sE2 + off) = make_uint4(e2[u * 4], e2[u * 4 + 1], e2[u * 4 + 2], e2[u * 4 + 3]);
+                    for (int u = 0; u < 4; ++u) {
+                        const int unit = half * 4 + u;
+                        const uint32_t off = r * 128 + ((unit ^ (r & 7)) << 4);
+                        if (MODE == 0) *reinterpret_cast<uint4*>(sE1 + off) = make_uint4(e1[u * 4], e1[u * 4 + 1], e1[u * 4 + 2], e1[u * 4 + 3]);
+                        *reinterpret_cast<uint4*>(sE2 + off) = make_uint4(e2[u * 4], e2[u * 4 + 1], e2[u * 4 + 2], e2[u * 4 + 3]);
+                    }
+                    fence_proxy_async_smem();
                 }
-                fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&e_full[eb]);
                 ++ec;
+                VLB_PROF(5);   // E store, completion, fences, publish
                 if (MODE == 0 && tid_e < BY && t + 1 < n) {  // publish tile t+1's statistics (other buffer)
                     sLse[((tc + 1) & 1) * BY + tid_e] = nl;
                     sDelta[((tc + 1) & 1) * BY + tid_e] = nd;
@@ -461,6 +504,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(acc_free);
             }
+            VLB_PROF(7);   // epilogue
+        }
+        if ((DBG & 8) && threadIdx.x == 64) {
+            for (int i = 0; i < 10; ++i) atomicAdd(&g_bwd_prof[MODE * 16 + i], prof[i]);
         }
     }
     tcgen05_fence_before();
@@ -471,12 +518,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     }
 }
 
-template <int DH, int MODE>
+template <int DH, int MODE, bool TS, int DBG = 0>
 static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, const Params& p,
                   cudaStream_t s) {
     constexpr int NCH = DH / 64;
-    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + 4 * BX * 128 + 4 * BY * 4 + 256 + 1024;
-    auto kern = attn_bwd_tc_kernel<DH, MODE>;
+    constexpr int NST = TS ? 5 : 3;
+    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + (TS ? 0 : 4 * BX * 128) + 4 * BY * 4 + 256 + 1024;
+    auto kern = attn_bwd_tc_kernel<DH, MODE, TS, DBG>;
     static bool configured = false;
     if (!configured) {
         VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -523,6 +571,16 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 
 }  // namespace attn_bwd_tc
 }  // namespace vlb
+
+// diagnostics: read (and reset) the phase counters of the DBG-8 variants; not part of the ABI in include/vlb200.h
+extern "C" int vlbdbg_attn_bwd_profile(unsigned long long* out32, int reset) {
+    if (cudaMemcpyFromSymbol(out32, vlb::attn_bwd_tc::g_bwd_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(vlb::attn_bwd_tc::g_bwd_prof, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
 
 extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
                                         const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream) {
@@ -580,12 +638,28 @@ extern "C" int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     // pass 1: dK, dV
     p.out1 = (__nv_bfloat16*)dv; p.ld1 = lddv; p.out2 = (__nv_bfloat16*)dk; p.ld2 = lddk;
     p.n_work = p.n_xb * KVH * B;
-    rc = head_dim == 64 ? launch<64, 0>(xk, xv, yq, ydo, p, s) : launch<128, 0>(xk, xv, yq, ydo, p, s);
+    // VLB200_ATTN_BWD_TS=1: elementwise results stay in tensor memory (TS-mode accumulate MMAs)
+    static const bool ts = [] { const char* e = getenv("VLB200_ATTN_BWD_TS"); return e && e[0] == '1'; }();
+    static const int dbg = [] { const char* e = getenv("VLB200_ATTN_BWD_DBG"); return e ? atoi(e) : 0; }();
+    if (dbg && head_dim == 128) {
+        p.n_work = p.n_xb * KVH * B;
+        switch (dbg) {
+#define VLB_DBG_CASE(D) case D: rc = launch<128, 0, true, D>(xk, xv, yq, ydo, p, s); if (rc) return rc; \
+            p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq; p.n_work = p.n_xb * H * B; \
+            return launch<128, 1, true, D>(xq, xdo, yk, yv, p, s);
+            VLB_DBG_CASE(1) VLB_DBG_CASE(2) VLB_DBG_CASE(3) VLB_DBG_CASE(4) VLB_DBG_CASE(7) VLB_DBG_CASE(8)
+#undef VLB_DBG_CASE
+            default: break;
+        }
+    }
+    if (ts) rc = head_dim == 64 ? launch<64, 0, true>(xk, xv, yq, ydo, p, s) : launch<128, 0, true>(xk, xv, yq, ydo, p, s);
+    else rc = head_dim == 64 ? launch<64, 0, false>(xk, xv, yq, ydo, p, s) : launch<128, 0, false>(xk, xv, yq, ydo, p, s);
     if (rc) return rc;
     // pass 2: dQ
     p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq;
     p.n_work = p.n_xb * H * B;
-    return head_dim == 64 ? launch<64, 1>(xq, xdo, yk, yv, p, s) : launch<128, 1>(xq, xdo, yk, yv, p, s);
+    if (ts) return head_dim == 64 ? launch<64, 1, true>(xq, xdo, yk, yv, p, s) : launch<128, 1, true>(xq, xdo, yk, yv, p, s);
+    return head_dim == 64 ? launch<64, 1, false>(xq, xdo, yk, yv, p, s) : launch<128, 1, false>(xq, xdo, yk, yv, p, s);
 }
 
 extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

@@ -88,6 +88,10 @@ __device__ __forceinline__ KvPlan kv_plan(const Params& p, int b, int qb) {
     return k;
 }
 
+// diagnostics (DBG bit 8): cycles one softmax thread per CTA spends in each phase of its loop, summed over the grid
+__device__ unsigned long long g_fwd_prof[16];
+#define VLB_PROF(i) do { if (DBG & 8) { const long long t_ = clock64(); prof[i] += (unsigned long long)(t_ - tp); tp = t_; } } while (0)
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -96,7 +100,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 constexpr int NSTAGE = 3;  // K/V ring depth
 
-template <int DH>
+// VAR 0: P goes through shared memory (SS-mode PV).  VAR 1: P stays in TENSOR MEMORY -- the softmax threads write bf16 P over
+// the first 64 columns of the S buffer they just read (tcgen05.st) and PV runs with its A operand from TMEM (TS mode): 64 KB
+// less shared-memory traffic per tile (32 KB of P stores + 32 KB of A reads out of 224 KB; the kernel is bound by the 128 B/clk
+// shared-memory port, profiles/r2_attention_analysis.md).  VAR 2: Q is copied to TMEM once per query tile as well (S = Q K^T in
+// TS mode): another 32 KB per tile.
+template <int DH, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                    const __grid_constant__ CUtensorMap tma_v, const Params p) {
@@ -105,10 +114,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     constexpr int Q_BYTES = NCH * CHUNK_BYTES;
     constexpr int KV_BYTES = NCH * CHUNK_BYTES;  // one K or V tile
     constexpr int P_BYTES = 2 * CHUNK_BYTES;     // [128 q][128 keys] bf16
-    constexpr int KP_BYTES = KV_BYTES > P_BYTES ? KV_BYTES : P_BYTES;  // K_j slot, reused for P_j once S_j has retired
+    constexpr bool TS = (VAR % 10) >= 1, QT = (VAR % 10) >= 2;
+    // diagnostics (wrong results, timing only), a bit mask: 1 = the MMA thread issues no MMAs (barriers only), 2 = the softmax
+    // threads skip the exponentials, 4 = the producer loads no K/V tiles (stale shared memory)
+    constexpr int DBG = VAR / 10;
+    constexpr int KP_BYTES = TS ? KV_BYTES : (KV_BYTES > P_BYTES ? KV_BYTES : P_BYTES);  // K_j slot (VAR 0: reused for P_j once S_j has retired)
     constexpr int STAGE_BYTES = KP_BYTES + KV_BYTES;
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t TM_S = 0, TM_O = 256;     // S buffers at columns 0 / 128, O at 256
+    constexpr uint32_t TM_S = 0, TM_O = 256, TM_Q = 384;  // S buffers at columns 0 / 128 (TS: P_j over the first 64 columns of S_j), O at 256, Q (QT) at 384
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,13 +137,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     uint64_t* s_empty = s_full + 2;            // [2]
     uint64_t* pv_done = s_empty + 2;
     uint64_t* o_free = pv_done + 1;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+    uint64_t* qt_full = o_free + 1;            // QT: Q tile copied to tensor memory by the 4 softmax warps
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(qt_full + 1);
 
     const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
 
     if (warp_idx == 0 && lane_idx == 0) {
         prefetch_tensormap(&tma_q); prefetch_tensormap(&tma_k); prefetch_tensormap(&tma_v);
-        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        mbar_init(q_full, 1); mbar_init(q_empty, QT ? 4 : 1); mbar_init(qt_full, 4);
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&p_full[i], 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
         mbar_init(pv_done, 1); mbar_init(o_free, 4);
@@ -161,6 +175,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 for (int j = 0; j < n_tiles; ++j, ++g) {
                     const uint32_t st = g % NSTAGE;
                     mbar_wait(&kv_empty[st], ((g / NSTAGE) & 1) ^ 1, 20 + st);  // PV of the tile 3 back retired (K/P and V slots free)
+                    if (DBG & 4) { mbar_arrive(&kv_full[st]); continue; }
                     mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
                     uint8_t* kp = sStage + st * STAGE_BYTES;
                     const int krow = j < plan.n_ctx ? plan.ctx_row0 + j * BN : row0 + (j - plan.n_ctx) * BN;
@@ -185,8 +200,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 const KvPlan plan = kv_plan(p, b, qb);
                 if (plan.skip) continue;
                 const int n_tiles = plan.n_ctx + plan.n_self;
-                mbar_wait(q_full, item & 1, 30);
+                if (QT) mbar_wait(qt_full, item & 1, 31);
+                else mbar_wait(q_full, item & 1, 30);
                 tcgen05_fence_after();
+                const uint32_t sc0 = sc;
                 // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
                 // published -- neither blocks the other (a blocked in-order loop exposed the full TMA latency per tile)
                 int js = 0, jp = 0;
@@ -195,17 +212,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     bool progressed = false;
                     if (js < n_tiles) {
                         const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
-                        if (mbar_try_wait(&kv_full[st], (g / NSTAGE) & 1) && mbar_try_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1)) {
+                        // S buffer free: VAR 0 -- the softmax threads have read it; TS -- P_j lives in S_j's buffer until PV_j
+                        // has consumed it: the MMAs of this thread execute in issue order, so S_{j+2} may be issued once PV_j has
+                        bool s_free;
+                        if (TS) s_free = js - jp < 2;
+                        else s_free = mbar_try_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
+                        if (s_free && mbar_try_wait(&kv_full[st], (g / NSTAGE) & 1)) {
                             tcgen05_fence_after();
                             const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 0);
                             const uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0);
 #pragma unroll
                             for (int k = 0; k < DH / 16; ++k) {
                                 const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
-                                umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
+                                if (DBG & 1) continue;
+                                if (QT) umma_f16_ts(tmem_base + TM_S + sb * BN, tmem_base + TM_Q + k * 8, dk + off, idesc_s, k != 0);
+                                else umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
                             }
                             umma_commit(&s_full[sb]);
-                            if (js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
+                            if (!QT && js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
                             ++sc; ++js;
                             progressed = true;
                         }
@@ -219,8 +243,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                             const uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
 #pragma unroll
                             for (int k = 0; k < BN / 16; ++k) {
-                                umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
-                                            dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                                if (DBG & 1) continue;
+                                if (TS)
+                                    umma_f16_ts(tmem_base + TM_O, tmem_base + TM_S + ((sc0 + jp) & 1) * BN + k * 8,
+                                                dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                                else
+                                    umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
+                                                dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
                             }
                             umma_commit(pv_done);
                             umma_commit(&kv_empty[st]);
@@ -248,28 +277,57 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         const int r = quad * 32 + lane_idx;  // row inside the Q tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        uint32_t sc = 0, g = 0;  // g = global tile counter (== number of PVs issued for earlier tiles)
+        uint32_t sc = 0, g = 0, item = 0;  // g = global tile counter (== number of PVs issued for earlier tiles)
+        unsigned long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tp = clock64();
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int b, h, qb;
             work_coords(p, w, b, h, qb);
             const KvPlan plan = kv_plan(p, b, qb);
             if (plan.skip) continue;
             const int n_tiles = plan.n_ctx + plan.n_self;
+            if (DBG & 8) { prof[8] += 1; prof[9] += n_tiles; }
+            if (QT) {
+                // Q tile: smem (TMA, 128B-swizzled) -> this thread's TMEM lane, two bf16 per column (the K-major A operand of
+                // S = Q K^T).  Every MMA of the previous item has retired (its epilogue waited for the last PV).
+                mbar_wait(q_full, item & 1, 70);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t qw[16];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(sQ + c * CHUNK_BYTES + r * 128 + (((hh * 4 + u) ^ (r & 7)) << 4));
+                            qw[u * 4 + 0] = v.x; qw[u * 4 + 1] = v.y; qw[u * 4 + 2] = v.z; qw[u * 4 + 3] = v.w;
+                        }
+                        tmem_st_32x32_x16(tmem_base + lane_addr + TM_Q + c * 32 + hh * 16, qw);
+                    }
+                }
+                tmem_st_wait_all();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) { mbar_arrive(qt_full); mbar_arrive(q_empty); }
+                ++item;
+            }
             int kv_len = p.seqlens ? p.seqlens[b] : p.S;
             kv_len = max(kv_len, 1);
             const int qrow = qb * BM + r;
             float m_run = -INFINITY, l_run = 0.f;
+            VLB_PROF(0);   // item start (plan, Q copy)
             for (int j = 0; j < n_tiles; ++j, ++sc, ++g) {
                 const uint32_t sb = sc & 1, st = g % NSTAGE;
                 mbar_wait(&s_full[sb], (sc >> 1) & 1, 80 + sb);
                 tcgen05_fence_after();
+                VLB_PROF(1);   // wait for S
                 uint32_t sr[4][32];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_base + lane_addr + TM_S + sb * BN + c * 32, sr[c]);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane_idx == 0) mbar_arrive(&s_empty[sb]);  // S buffer is in registers now
+                if (!TS && lane_idx == 0) mbar_arrive(&s_empty[sb]);  // S buffer is in registers now
+                VLB_PROF(2);   // TMEM -> registers
                 // context tiles: every key below ctx_len is visible; own tiles: keys below kv_len, up to the causal diagonal
                 const bool is_ctx = j < plan.n_ctx;
                 const int k0 = (is_ctx ? j : j - plan.n_ctx) * BN;
@@ -304,32 +362,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     m_run = m_new;
                 }
                 const float neg_m = m_run == -INFINITY ? 0.f : -m_run;
+                VLB_PROF(3);   // mask + row max
                 // P = exp2(s*c - m) (bf16) into the K slot of this stage (K_j is dead: S_j has retired), laid out as a
                 // K-major 128B-swizzled A operand: chunk = 64 keys, row pitch 128 B
                 uint8_t* sP = sStage + st * STAGE_BYTES;
                 float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    uint32_t wt[16];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         uint32_t w4[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][u * 8 + 2 * e]), sl2, neg_m));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c][u * 8 + 2 * e + 1]), sl2, neg_m));
+                            float p0 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e]), sl2, neg_m);
+                            float p1 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e + 1]), sl2, neg_m);
+                            if (!(DBG & 2)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
                             rs0 += p0;
                             rs1 += p1;
                             w4[e] = pack_bf16x2(p0, p1);
                         }
-                        const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 64-key chunk (c >> 1)
-                        *reinterpret_cast<uint4*>(sP + (c >> 1) * CHUNK_BYTES + r * 128 + ((unit ^ (r & 7)) << 4)) =
-                            make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        if (TS) {   // P_j over S_j's first 64 columns: keys 2i | 2i+1 in column i of this thread's lane
+                            wt[u * 4 + 0] = w4[0]; wt[u * 4 + 1] = w4[1]; wt[u * 4 + 2] = w4[2]; wt[u * 4 + 3] = w4[3];
+                        } else {
+                            const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 64-key chunk (c >> 1)
+                            *reinterpret_cast<uint4*>(sP + (c >> 1) * CHUNK_BYTES + r * 128 + ((unit ^ (r & 7)) << 4)) =
+                                make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
                     }
+                    if (TS) tmem_st_32x32_x16(tmem_base + lane_addr + TM_S + sb * BN + c * 16, wt);
                 }
                 l_run = l_run * corr + (rs0 + rs1);
+                VLB_PROF(4);   // exponentials, row sum, pack, P store issue
                 // publish P only after PV of the previous tile has retired: keeps the pv_done phase bookkeeping exact
                 // (a waiter never runs two phases ahead) and orders the (rare) O correction before the next PV
                 if (j > 0) mbar_wait(pv_done, (g - 1) & 1, 90);
+                VLB_PROF(5);   // wait for the previous PV
                 if (j > 0 && __any_sync(0xffffffffu, need)) {  // warp-uniform: tcgen05.ld/st are warp collectives
                     tcgen05_fence_after();
 #pragma unroll
@@ -343,10 +411,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     }
                     tmem_st_wait();
                 }
-                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                if (TS) tmem_st_wait_all();   // P_j is in tensor memory
+                else fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&p_full[st]);
+                VLB_PROF(6);   // O correction (rare), store completion, fences, publish
             }
             // ---- epilogue: wait for the last PV, normalise, store O and LSE
             mbar_wait(pv_done, (g - 1) & 1, 95);
@@ -377,6 +447,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             tcgen05_fence_before();
             __syncwarp();
             if (lane_idx == 0) mbar_arrive(o_free);
+            VLB_PROF(7);   // epilogue
+        }
+        if ((DBG & 8) && threadIdx.x == 64) {
+            for (int i = 0; i < 10; ++i) atomicAdd(&g_fwd_prof[i], prof[i]);
         }
     }
     tcgen05_fence_before();
@@ -387,12 +461,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     }
 }
 
-template <int DH>
+template <int DH, int VAR>
 static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t s) {
     constexpr int kv_bytes = (DH / 64) * 128 * 128;
-    constexpr int kp_bytes = kv_bytes > 2 * 128 * 128 ? kv_bytes : 2 * 128 * 128;
+    constexpr int kp_bytes = (VAR % 10) >= 1 ? kv_bytes : (kv_bytes > 2 * 128 * 128 ? kv_bytes : 2 * 128 * 128);
     constexpr int smem_bytes = kv_bytes + NSTAGE * (kp_bytes + kv_bytes) + 256 + 1024;
-    auto kern = attn_fwd_tc_kernel<DH>;
+    auto kern = attn_fwd_tc_kernel<DH, VAR>;
     static bool configured = false;
     if (!configured) {
         VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -407,6 +481,16 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 
 }  // namespace attn_tc
 }  // namespace vlb
+
+// diagnostics: read (and reset) the phase counters of the DBG-8 variants; not part of the ABI in include/vlb200.h
+extern "C" int vlbdbg_attn_fwd_profile(unsigned long long* out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, vlb::attn_tc::g_fwd_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(vlb::attn_tc::g_fwd_prof, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
 
 extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                       void* out, int64_t ldo, float* lse, const int* seqlens, const int* row_starts,
@@ -431,8 +515,24 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
-    if (head_dim == 64) return attn_tc::launch<64>(tq, tk, tv, p, as_stream(stream));
-    return attn_tc::launch<128>(tq, tk, tv, p, as_stream(stream));
+    // VLB200_ATTN_FWD_VARIANT: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory
+    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    cudaStream_t st = as_stream(stream);
+    if (head_dim == 64) {
+        if (variant == 1) return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
+        if (variant == 2) return attn_tc::launch<64, 2>(tq, tk, tv, p, st);
+        return attn_tc::launch<64, 0>(tq, tk, tv, p, st);
+    }
+    if (variant == 1) return attn_tc::launch<128, 1>(tq, tk, tv, p, st);
+    if (variant == 2) return attn_tc::launch<128, 2>(tq, tk, tv, p, st);
+    switch (variant) {
+#define VLB_DBG_CASE(V) case V: return attn_tc::launch<128, V>(tq, tk, tv, p, st);
+        VLB_DBG_CASE(10) VLB_DBG_CASE(12) VLB_DBG_CASE(20) VLB_DBG_CASE(22) VLB_DBG_CASE(30) VLB_DBG_CASE(32)
+        VLB_DBG_CASE(40) VLB_DBG_CASE(42) VLB_DBG_CASE(70) VLB_DBG_CASE(72) VLB_DBG_CASE(80) VLB_DBG_CASE(82)
+#undef VLB_DBG_CASE
+        default: break;
+    }
+    return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
 }
 
 extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

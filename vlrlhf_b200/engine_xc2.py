@@ -458,9 +458,14 @@ class XC2DPOEngine(QwenVLDPOEngine):
                 ops.pack_merge_rows(m, seq_lens if seq_lens is not None else m.seqlens.cpu().tolist())
                 self._pad_rows, self._cur_rows = m.n_seq * m.S, m.T
         # flat merged rows of every image position (the PLoRA row mask im_mask, __init__.py:87-104); packed: already absolute
-        self._img_rows = m.img_pos if m.packed else (
-            m.img_pos.view(m.n_seq, -1) +
-            (torch.arange(m.n_seq, dtype=torch.int32, device=m.img_pos.device) * m.S)[:, None]).reshape(-1).contiguous()
+        if getattr(self, "_img_rows_of", None) is not m:
+            self._img_rows = m.img_pos if m.packed else (
+                m.img_pos.view(m.n_seq, -1) +
+                (torch.arange(m.n_seq, dtype=torch.int32, device=m.img_pos.device) * m.S)[:, None]).reshape(-1).contiguous()
+            if m.shared and prefix_rows is not None and all(int(p) > 0 for p in prefix_rows):
+                # every pair shares its image rows: the rejected half of the list is all -1 (skipped rows) -- drop it
+                self._img_rows = m.img_pos[: m.img_pos.numel() // 2]
+            self._img_rows_of = m
         self.ensure_rope_len(m.S)
         if feats is None:
             feats = self.vision_features(px)
