@@ -2,15 +2,15 @@
 //
 //   MODE 0 (dK, dV): a CTA keeps a 128-key tile (K_j, V_j) in smem and streams 64-query tiles (Q_i, dO_i):
 //        S^T = K Q^T, dP^T = V dO^T            tcgen05.mma 128x64x16 (scores transposed: TMEM lane = key)
-//        P^T = exp2(S^T*c - lse[q]),  dS^T = scale * P^T o (dP^T - delta[q])      (bf16 -> swizzled smem)
+//        P^T = exp2(S^T*c - lse[q]),  dS^T = scale * P^T o (dP^T - delta[q])      (bf16, written back over the scores in TMEM)
 //        dV += P^T dO,  dK += dS^T Q           tcgen05.mma 128xDHx16, B = streamed tile read MN-major
 //   MODE 1 (dQ):     a CTA keeps a 128-query tile (Q_i, dO_i) and streams 64-key tiles (K_j, V_j):
 //        S = Q K^T, dP = dO V^T;  dS = scale * P o (dP - delta[row]);  dQ += dS K
 //
 // dQ is produced by a second pass (7 tile-GEMMs instead of 5) so no atomics are needed and results are
-// deterministic.  Persistent CTAs, warp 0 = TMA producer (stationary tiles + 3-stage ring of streamed tiles),
-// warp 1 = MMA issuer, warps 2-5 = elementwise/epilogue (one stationary row per thread).  Score tiles are
-// double buffered in TMEM; dK/dV (or dQ) accumulate in TMEM over the whole loop (GQA: over the group's heads).
+// deterministic.  Persistent CTAs, warp 0 = TMA producer (stationary tiles + 4-stage ring of streamed tiles),
+// warp 1 = MMA issuer, warps 2-9 = elementwise/epilogue (one stationary row per thread, two warps per TMEM lane quadrant).
+// Score tiles are double buffered in TMEM; dK/dV (or dQ) accumulate in TMEM over the whole loop (GQA: over the group's heads).
 //
 // Replaces the autograd backward of LlamaAttention (modeling_llama.py:199-290).
 #include <algorithm>
@@ -29,6 +29,7 @@ using namespace ptx;
 
 constexpr int BX = 128;  // stationary rows
 constexpr int BY = 64;   // streamed rows
+constexpr int NST = 4;   // streamed-tile ring depth
 constexpr int NTHREADS = 320;  // TMA warp, MMA warp, 8 elementwise warps (two per TMEM lane quadrant)
 constexpr int NEW = 8;         // elementwise warps
 constexpr float LOG2E_F = 1.4426950408889634f;
@@ -130,15 +131,17 @@ __device__ __forceinline__ void item_tile(const Item& it, int t, Seg& sg, int& y
     yt = sg.yb + u;
 }
 
-// TS: the elementwise results (P^T / dS^T, or dS) stay in TENSOR MEMORY: each elementwise warp writes its 32 bf16 columns,
-// packed two per 32-bit column, over the first 16 columns of the 32 fp32 score columns it has just read (tcgen05.st), and the
-// accumulate MMAs take their A operand from TMEM (TS mode, one K = 16 step = 8 columns).  No E stores to / A reads from
-// shared memory (64 of 224 KB of shared-memory traffic per streamed tile), no generic->async proxy fence, and the 64 KB of E
-// buffers become two more stages of the streamed-tile ring.  A score buffer is then recycled in MMA issue order (the score
-// MMAs of tile t+2 are issued after the accumulate MMAs of tile t), not by a barrier.
+// The elementwise results (P^T / dS^T, or dS) stay in TENSOR MEMORY: each elementwise warp writes its 32 bf16 columns, packed
+// two per 32-bit column, over the first 16 columns of the 32 fp32 score columns it has just read (tcgen05.st), and the
+// accumulate MMAs take their A operand from TMEM (TS mode, one K = 16 step = 8 columns): no E stores to / A reads from shared
+// memory, no generic->async proxy fence.  A score buffer is recycled in MMA issue order (the score MMAs of tile t+2 are issued
+// after the accumulate MMAs of tile t), not by a barrier.  The MMA warp runs CONVERGED (all lanes poll the barriers, votes
+// make the branches warp-uniform) and one elected lane issues the MMAs: with the role under `if (lane == 0)` ptxas wraps every
+// tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall, ~10 instructions per MMA -- at 20-24 MMAs of 32 tensor-cycles per
+// 64-row tile the issue thread was the bound of the dQ pass (profiles/r2j_attn_phases.log: 1260 cycles per tile waiting for scores).
 // DBG (diagnostics, wrong results, timing only), a bit mask: 1 = no MMAs are issued (barriers only), 2 = no exponentials,
-// 4 = no streamed-tile loads
-template <int DH, int MODE, bool TS, int DBG = 0>
+// 4 = no streamed-tile loads, 8 = per-phase cycle counters
+template <int DH, int MODE, int DBG = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_constant__ CUtensorMap tma_x2,
                    const __grid_constant__ CUtensorMap tma_y1, const __grid_constant__ CUtensorMap tma_y2, const Params p) {
@@ -147,38 +150,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     constexpr int YCH = BY * 128;            // bytes of one [64 x 128 B] chunk
     constexpr int X_BYTES = NCH * XCH;       // one stationary tile
     constexpr int Y_BYTES = NCH * YCH;       // one streamed tile
-    constexpr int E_BYTES = BX * 128;        // [128 rows][64 bf16]
-    constexpr int NST = TS ? 5 : 3;          // streamed-tile ring depth
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t TM_T1 = 0, TM_T2 = 128, TM_A1 = 256, TM_A2 = 384;  // T buffers: +64 per stage
+    // MODE 1 has one accumulator (dQ): the stationary Q and dO tiles live in the other accumulator's columns, two bf16 per
+    // column, and the score MMAs run in TS mode.  An M = 128, N = 64 SS-mode MMA reads 6 KB of operands per 32 tensor cycles
+    // -- 192 B/clk against the 128 B/clk shared-memory port (the dQ pass waited 900 cycles per tile for its scores); with A in
+    // tensor memory only the 2 KB of the streamed tile are read.
+    constexpr uint32_t TM_X1 = 256, TM_X2 = 320;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX1 = smem;
     uint8_t* sX2 = sX1 + X_BYTES;
     uint8_t* sY = sX2 + X_BYTES;                 // NST stages of (Y1, Y2)
-    uint8_t* sE = sY + NST * 2 * Y_BYTES;        // 2 buffers of (E1, E2)
-    float* sLse = reinterpret_cast<float*>(sE + (TS ? 0 : 4 * E_BYTES));  // [2][64] (MODE 0)
-    float* sDelta = sLse + 2 * BY;                           // [2][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * BY);
+    float* sStat = reinterpret_cast<float*>(sY + NST * 2 * Y_BYTES);  // MODE 0: [NST stages][lse2 x64 | delta x64] of the streamed queries
+    uint8_t* sOut = reinterpret_cast<uint8_t*>(sStat + NST * 128);   // [NEW warps][32 rows][64 B]: epilogue staging (coalesced stores)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + NEW * 2048);
     uint64_t* x_full = bars + 0;
     uint64_t* x_empty = bars + 1;
     uint64_t* y_full = bars + 2;             // [NST]
     uint64_t* y_empty = bars + 2 + NST;      // [NST]
     uint64_t* t_full = bars + 2 + 2 * NST;   // [2]
-    uint64_t* t_empty = t_full + 2;          // [2]
-    uint64_t* e_full = t_empty + 2;          // [2]
+    uint64_t* e_full = t_full + 2;           // [2]
     uint64_t* e_done = e_full + 2;           // [2]
     uint64_t* acc_free = e_done + 2;
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_free + 1);
+    uint64_t* xt_full = acc_free + 1;        // MODE 1: stationary tiles copied to tensor memory by the 8 elementwise warps
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(xt_full + 1);
 
     const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
     if (warp_idx == 0 && lane_idx == 0) {
         prefetch_tensormap(&tma_x1); prefetch_tensormap(&tma_x2); prefetch_tensormap(&tma_y1); prefetch_tensormap(&tma_y2);
-        mbar_init(x_full, 1); mbar_init(x_empty, 1);
-        for (int i = 0; i < NST; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NEW); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&e_full[i], NEW); mbar_init(&e_done[i], 1); }
+        mbar_init(x_full, 1); mbar_init(x_empty, MODE == 1 ? NEW : 1); mbar_init(xt_full, NEW);
+        for (int i = 0; i < NST; ++i) { mbar_init(&y_full[i], MODE == 0 ? 2 : 1); mbar_init(&y_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&e_full[i], NEW); mbar_init(&e_done[i], 1); }
         mbar_init(acc_free, NEW);
         fence_barrier_init();
     }
@@ -190,17 +194,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     const int group = p.H / p.KVH;
 
     if (warp_idx == 0) {
-        // ===================== TMA producer =====================
-        if (lane_idx == 0) {
-            uint32_t item = 0, yc = 0;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                int b, hx, xb;
-                item_coords<MODE>(p, w, b, hx, xb);
-                const Item it = item_plan<MODE>(p, b, xb);
-                const int n = it.per_rep * it.reps;
-                if (n == 0) continue;
-                const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
-                const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
+        // ===================== TMA producer (lane 0) + per-column statistics of the streamed tiles (whole warp, MODE 0) =====
+        uint32_t item = 0, yc = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, hx, xb;
+            item_coords<MODE>(p, w, b, hx, xb);
+            const Item it = item_plan<MODE>(p, b, xb);
+            const int n = __shfl_sync(0xffffffffu, it.per_rep * it.reps, 0);
+            if (n == 0) continue;
+            const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
+            const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
+            if (lane_idx == 0) {
                 mbar_wait(x_empty, (item & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(x_full, 2 * X_BYTES);
 #pragma unroll
@@ -208,129 +212,164 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     tma_load_2d(&tma_x1, x_full, sX1 + c * XCH, xcol + c * 64, row0 + xb * BX);
                     tma_load_2d(&tma_x2, x_full, sX2 + c * XCH, xcol + c * 64, row0 + xb * BX);
                 }
-                for (int t = 0; t < n; ++t, ++yc) {
-                    const int st = yc % NST;
+            }
+            // MODE 0: lane l holds log-sum-exp (log2 domain) and delta of queries l and 32 + l of the NEXT tile to publish (the
+            // global loads fly while the warp waits for a free stage)
+            float sl_[2] = {0.f, 0.f}, sd_[2] = {0.f, 0.f};
+            auto load_stats = [&](int t) {
+                if (MODE == 0 && t < n) {
                     Seg sg; int yt, rep;
                     item_tile(it, t, sg, yt, rep);
-                    const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
-                    mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
-                    if (DBG & 4) { mbar_arrive(&y_full[st]); continue; }
-                    mbar_arrive_expect_tx(&y_full[st], 2 * Y_BYTES);
-                    uint8_t* y1 = sY + st * 2 * Y_BYTES;
-                    uint8_t* y2 = y1 + Y_BYTES;
+                    const long long sbase = ((long long)sg.seq * p.H + (hx * group + rep)) * p.S;
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        tma_load_2d(&tma_y1, &y_full[st], y1 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
-                        tma_load_2d(&tma_y2, &y_full[st], y2 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int q = yt * BY + hh * 32 + lane_idx;
+                        const bool ok = q < sg.len;
+                        sl_[hh] = ok ? p.lse[sbase + q] : 0.f;
+                        sd_[hh] = ok ? p.delta[sbase + q] : 0.f;
                     }
                 }
-                ++item;
-            }
-        }
-    } else if (warp_idx == 1) {
-        // ===================== MMA issuer =====================
-        if (lane_idx == 0) {
-            constexpr uint32_t idesc_t = make_idesc_bf16_f32(BX, BY, false, false);
-            constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
-            uint32_t item = 0, yc = 0, tc = 0, ec = 0;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                int b, hx, xb;
-                item_coords<MODE>(p, w, b, hx, xb);
-                const Item it = item_plan<MODE>(p, b, xb);
-                const int n = it.per_rep * it.reps;
-                if (n == 0) continue;
-                mbar_wait(x_full, item & 1, 30);
-                tcgen05_fence_after();
-                const uint32_t y0 = yc;
-                // dynamic issue order (see attention_tc.cu): score MMAs for tile ts as soon as its streamed tile and a
-                // TMEM score buffer are ready, otherwise the accumulate MMAs of tile ta once its E operands are published
-                int ts = 0, ta = 0;
-                long long t_spin = 0;
-                while (ta < n) {
-                    bool progressed = false;
-                    if (ts < n) {
-                        const uint32_t yi = y0 + ts, st = yi % NST, tb = tc & 1;
-                        bool t_free;   // TS: the buffer holds tile ts-2's E operands until its accumulate MMAs have been issued
-                        if (TS) t_free = ts - ta < 2;
-                        else t_free = mbar_try_wait(&t_empty[tb], ((tc >> 1) & 1) ^ 1);
-                        if (t_free && mbar_try_wait(&y_full[st], (yi / NST) & 1)) {
-                            tcgen05_fence_after();
-                            const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
-                            // descriptors: constant fields built once, only the 16-byte-granular start address advances
-                            const uint64_t dx1 = make_smem_desc_sw128(smem_u32(sX1), 1024, 0), dx2 = make_smem_desc_sw128(smem_u32(sX2), 1024, 0);
-                            const uint64_t dy1 = make_smem_desc_sw128(y1, 1024, 0), dy2 = make_smem_desc_sw128(y2, 1024, 0);
+            };
+            load_stats(0);
+            for (int t = 0; t < n; ++t, ++yc) {
+                const int st = yc % NST;
+                Seg sg; int yt, rep;
+                item_tile(it, t, sg, yt, rep);
+                const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
+                mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
+                __syncwarp();
+                if (lane_idx == 0) {
+                    if (DBG & 4) {
+                        mbar_arrive(&y_full[st]);
+                    } else {
+                        mbar_arrive_expect_tx(&y_full[st], 2 * Y_BYTES);
+                        uint8_t* y1 = sY + st * 2 * Y_BYTES;
+                        uint8_t* y2 = y1 + Y_BYTES;
 #pragma unroll
-                            for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
-                                if (DBG & 1) continue;
-                                umma_f16_ss(tmem_base + TM_T1 + tb * BY, dx1 + xo, dy1 + yo, idesc_t, k != 0);
-                            }
-#pragma unroll
-                            for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
-                                if (DBG & 1) continue;
-                                umma_f16_ss(tmem_base + TM_T2 + tb * BY, dx2 + xo, dy2 + yo, idesc_t, k != 0);
-                            }
-                            umma_commit(&t_full[tb]);
-                            if (ts == n - 1) umma_commit(x_empty);
-                            ++tc; ++ts;
-                            progressed = true;
+                        for (int c = 0; c < NCH; ++c) {
+                            tma_load_2d(&tma_y1, &y_full[st], y1 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
+                            tma_load_2d(&tma_y2, &y_full[st], y2 + c * YCH, ycol + c * 64, sg.row0 + yt * BY);
                         }
                     }
-                    if (!progressed && ta < ts) {
-                        const uint32_t yi = y0 + ta, st = yi % NST, eb = ec & 1;
-                        if (mbar_try_wait(&e_full[eb], (ec >> 1) & 1)) {
-                            if (ta == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);
-                            tcgen05_fence_after();
-                            const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
-                            const uint32_t e1 = smem_u32(sE + eb * 2 * E_BYTES), e2 = e1 + E_BYTES;
-                            const uint64_t de1 = make_smem_desc_sw128(e1, 1024, 0), de2 = make_smem_desc_sw128(e2, 1024, 0);
-                            const uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
+                }
+                if (MODE == 0) {
+                    // statistics of the tile's 64 queries -> the stage's slot; the second arrival on y_full publishes them (the
+                    // elementwise warps read them as broadcast float4s: one warp loads what eight warps used to load redundantly,
+                    // 840 cycles per tile in profiles/r2k_attn.log)
+                    float* slot = sStat + st * 128;
 #pragma unroll
-                            for (int k = 0; k < BY / 16; ++k) {
-                                const uint32_t acc = (ta != 0 || k != 0) ? 1u : 0u;
-                                if (DBG & 1) continue;
-                                if (TS) {
+                    for (int hh = 0; hh < 2; ++hh) {
+                        slot[hh * 32 + lane_idx] = sl_[hh] * LOG2E_F;
+                        slot[64 + hh * 32 + lane_idx] = sd_[hh];
+                    }
+                    __syncwarp();
+                    if (lane_idx == 0) mbar_arrive(&y_full[st]);
+                    load_stats(t + 1);
+                }
+            }
+            ++item;
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+        constexpr uint32_t idesc_t = make_idesc_bf16_f32(BX, BY, false, false);
+        constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
+        const uint64_t dx1 = make_smem_desc_sw128(smem_u32(sX1), 1024, 0), dx2 = make_smem_desc_sw128(smem_u32(sX2), 1024, 0);
+        uint32_t item = 0, yc = 0, tc = 0, ec = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, hx, xb;
+            item_coords<MODE>(p, w, b, hx, xb);
+            const Item it = item_plan<MODE>(p, b, xb);
+            const int n = __shfl_sync(0xffffffffu, it.per_rep * it.reps, 0);
+            if (n == 0) continue;
+            if (MODE == 1) mbar_wait(xt_full, item & 1, 31);
+            else mbar_wait(x_full, item & 1, 30);
+            __syncwarp();
+            tcgen05_fence_after();
+            const uint32_t y0 = yc;
+            // dynamic issue order (see attention_tc.cu): the score MMAs of tile ts as soon as its streamed tile has landed and
+            // the accumulate MMAs of tile ts-2 have been issued (they read the E operands that live in ts's score buffer),
+            // otherwise the accumulate MMAs of tile ta once its E operands are published
+            int ts = 0, ta = 0;
+            long long t_spin = 0;
+            while (ta < n) {
+                bool progressed = false;
+                if (ts < n && ts - ta < 2) {
+                    const uint32_t yi = y0 + ts, st = yi % NST, tb = tc & 1;
+                    if (__all_sync(0xffffffffu, mbar_test_wait(&y_full[st], (yi / NST) & 1))) {
+                        tcgen05_fence_after();
+                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                        const uint64_t dy1 = make_smem_desc_sw128(y1, 1024, 0), dy2 = make_smem_desc_sw128(y2, 1024, 0);
+                        if (elect_one_sync()) {
+                            if (!(DBG & 1)) {
+#pragma unroll
+                                for (int k = 0; k < DH / 16; ++k) {
+                                    const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                    if (MODE == 1) umma_f16_ts(tmem_base + TM_T1 + tb * BY, tmem_base + TM_X1 + k * 8, dy1 + yo, idesc_t, k != 0);
+                                    else umma_f16_ss(tmem_base + TM_T1 + tb * BY, dx1 + xo, dy1 + yo, idesc_t, k != 0);
+                                }
+#pragma unroll
+                                for (int k = 0; k < DH / 16; ++k) {
+                                    const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                                    if (MODE == 1) umma_f16_ts(tmem_base + TM_T2 + tb * BY, tmem_base + TM_X2 + k * 8, dy2 + yo, idesc_t, k != 0);
+                                    else umma_f16_ss(tmem_base + TM_T2 + tb * BY, dx2 + xo, dy2 + yo, idesc_t, k != 0);
+                                }
+                            }
+                            umma_commit(&t_full[tb]);
+                            if (MODE == 0 && ts == n - 1) umma_commit(x_empty);
+                        }
+                        __syncwarp();
+                        ++tc; ++ts;
+                        progressed = true;
+                    }
+                }
+                if (!progressed && ta < ts) {
+                    const uint32_t yi = y0 + ta, st = yi % NST, eb = ec & 1;
+                    if (__all_sync(0xffffffffu, mbar_test_wait(&e_full[eb], (ec >> 1) & 1))) {
+                        if (ta == 0) { mbar_wait(acc_free, (item & 1) ^ 1, 60); __syncwarp(); }
+                        tcgen05_fence_after();
+                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                        const uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
+                        if (elect_one_sync()) {
+                            if (!(DBG & 1)) {
+#pragma unroll
+                                for (int k = 0; k < BY / 16; ++k) {
+                                    const uint32_t acc = (ta != 0 || k != 0) ? 1u : 0u;
                                     // streamed rows 16k..16k+15: written by elementwise half k/2 at columns half*32 + (k%2)*8 of the score buffer
                                     const uint32_t ac = eb * BY + (k >> 1) * 32 + (k & 1) * 8;
+                                    // MODE 0: dV += P^T dO, dK += dS^T Q ; MODE 1: dQ += dS K
                                     if (MODE == 0) umma_f16_ts(tmem_base + TM_A1, tmem_base + TM_T1 + ac, by2 + (uint64_t)(k * 128), idesc_a, acc);
                                     umma_f16_ts(tmem_base + TM_A2, tmem_base + TM_T2 + ac, by1 + (uint64_t)(k * 128), idesc_a, acc);
-                                } else {
-                                    if (MODE == 0)  // dV += P^T dO
-                                        umma_f16_ss(tmem_base + TM_A1, de1 + (uint64_t)(k * 2), by2 + (uint64_t)(k * 128), idesc_a, acc);
-                                    // MODE 0: dK += dS^T Q ; MODE 1: dQ += dS K
-                                    umma_f16_ss(tmem_base + TM_A2, de2 + (uint64_t)(k * 2), by1 + (uint64_t)(k * 128), idesc_a, acc);
                                 }
                             }
                             umma_commit(&e_done[eb]);
                             umma_commit(&y_empty[st]);
-                            ++ec; ++ta;
-                            progressed = true;
                         }
-                    }
-                    if (!progressed) {
-                        if (t_spin == 0) t_spin = clock64();
-                        else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
-                            printf("[vlb200] attn_bwd_tc MMA watchdog: block %d mode %d ts %d ta %d n %d\n", blockIdx.x, MODE, ts, ta, n);
-                            __trap();
-                        }
-                    } else {
-                        t_spin = 0;
+                        __syncwarp();
+                        ++ec; ++ta;
+                        progressed = true;
                     }
                 }
-                yc += n;
-                ++item;
+                if (!progressed) {
+                    if (t_spin == 0) t_spin = clock64();
+                    else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
+                        if (lane_idx == 0) printf("[vlb200] attn_bwd_tc MMA watchdog: block %d mode %d ts %d ta %d n %d\n", blockIdx.x, MODE, ts, ta, n);
+                        __trap();
+                    }
+                } else {
+                    t_spin = 0;
+                }
             }
+            yc += n;
+            ++item;
         }
     } else {
         // ===================== elementwise + epilogue (8 warps: row = TMEM lane, two warps split the columns) ==========
         const int quad = warp_idx & 3;
         const int half = (warp_idx - 2) >> 2;  // 0: columns [0,32) of a score tile, 1: columns [32,64)
         const int r = quad * 32 + lane_idx;
-        const int tid_e = threadIdx.x - 64;    // 0..255 inside the elementwise group
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        uint32_t tc = 0, ec = 0;
+        uint32_t tc = 0, xitem = 0;
         unsigned long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         long long tp = clock64();
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
@@ -350,21 +389,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 row_lse2 = p.lse[si] * LOG2E_F;
                 row_delta = p.delta[si];
             }
-            // MODE 0: per-column (query) statistics are staged through smem one tile ahead
-            float nl = 0.f, nd = 0.f;
-            auto fetch_stats = [&](int t) {
-                if (MODE == 0 && tid_e < BY && t < n) {
-                    Seg sg; int yt, rep;
-                    item_tile(it, t, sg, yt, rep);
-                    const int q = yt * BY + tid_e;
-                    const long long si = ((long long)sg.seq * p.H + (hx * group + rep)) * p.S + q;
-                    nl = q < sg.len ? p.lse[si] * LOG2E_F : 0.f;
-                    nd = q < sg.len ? p.delta[si] : 0.f;
+            if (MODE == 1 && n > 0) {
+                // stationary tiles: smem (TMA, 128B-swizzled) -> this thread's TMEM lane, two bf16 per column (the K-major A
+                // operand of the score MMAs).  half 0 copies Q, half 1 copies dO.  Every MMA of the previous item has retired (its
+                // epilogue waited for the last accumulate).
+                mbar_wait(x_full, xitem & 1, 70);
+                const uint8_t* sx = half == 0 ? sX1 : sX2;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t qw[16];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(sx + c * XCH + r * 128 + (((hh * 4 + u) ^ (r & 7)) << 4));
+                            qw[u * 4 + 0] = v.x; qw[u * 4 + 1] = v.y; qw[u * 4 + 2] = v.z; qw[u * 4 + 3] = v.w;
+                        }
+                        tmem_st_32x32_x16(tmem_base + lane_addr + (half == 0 ? TM_X1 : TM_X2) + c * 32 + hh * 16, qw);
+                    }
                 }
-            };
-            if (MODE == 0 && n > 0) {
-                fetch_stats(0);
-                if (tid_e < BY) { sLse[(tc & 1) * BY + tid_e] = nl; sDelta[(tc & 1) * BY + tid_e] = nd; }
+                tmem_st_wait_all();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) { mbar_arrive(xt_full); mbar_arrive(x_empty); }
+                ++xitem;
             }
             VLB_PROF(0);   // item start
             for (int t = 0; t < n; ++t, ++tc) {
@@ -374,11 +422,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 const int y0 = yt * BY;
                 const int ylen = sg.len;             // valid streamed rows of this tile's sequence
                 const bool causal_t = sg.causal != 0;
-                if (MODE == 0) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");  // statistics of tile t are visible
-                    fetch_stats(t + 1);                              // global loads for tile t+1 fly during this tile
-                }
-                VLB_PROF(1);   // tile coordinates, statistics barrier + prefetch
+                if (MODE == 0) mbar_wait(&y_full[tc % NST], (tc / NST) & 1, 75);   // acquires the producer's statistics (long complete)
+                VLB_PROF(1);   // tile coordinates
                 mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
                 tcgen05_fence_after();
                 VLB_PROF(2);   // wait for the score tiles
@@ -386,17 +431,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, t1);
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, t2);
                 tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (!TS && lane_idx == 0) mbar_arrive(&t_empty[tb]);
                 VLB_PROF(3);   // TMEM -> registers
                 // mask only tiles that touch the causal diagonal or the end of the valid range
                 const int ymax = y0 + BY - 1;
                 bool need_mask;
                 if (MODE == 0) need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && x0 + BX - 1 > y0);
                 else need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && ymax > x0);
-                const float* cl = sLse + tb * BY + half * 32;
-                const float* cd = sDelta + tb * BY + half * 32;
+                const float* cl = sStat + (tc % NST) * 128 + half * 32;   // MODE 0: statistics of this warp's 32 columns
+                const float* cd = cl + 64;
                 uint32_t e1[16], e2[16];
                 // two straight-line copies of the tile body (masked / unmasked): a per-element `if (need_mask)` costs a
                 // divergence region per element (seen in the r1 SASS: 33 BSSY/BSYNC pairs, 134 ISETP per 32 elements)
@@ -427,7 +469,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                                 if (!(xrow < kv_len && y0 + col < ylen && (!causal_t || key <= qi))) pr = 0.f;
                             }
                             pv[e] = pr;
-                            dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]) * p.scale;
+                            dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]);   // (x scale in the epilogue: dK / dQ are linear in dS)
                         }
                         e1[c4 >> 1] = pack_bf16x2(pv[0], pv[1]); e1[(c4 >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
                         e2[c4 >> 1] = pack_bf16x2(dv[0], dv[1]); e2[(c4 >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
@@ -436,45 +478,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 if (need_mask) tile_body(std::true_type{});
                 else tile_body(std::false_type{});
                 VLB_PROF(4);   // elementwise
-                // this E buffer is free once the accumulate MMAs of its previous use (two tiles back) have completed
-                const uint32_t eb = ec & 1;
-                if (TS) {   // over the score columns this warp has read (its own lanes, its own 32 columns)
-                    if (MODE == 0) tmem_st_32x32_x16(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, e1);
-                    tmem_st_32x32_x16(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, e2);
-                    tmem_st_wait_all();
-                } else {
-                    if ((ec >> 1) > 0) mbar_wait(&e_done[eb], ((ec >> 1) - 1) & 1, 90 + eb);
-                    uint8_t* sE1 = sE + eb * 2 * E_BYTES;
-                    uint8_t* sE2 = sE1 + E_BYTES;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int unit = half * 4 + u;
-                        const uint32_t off = r * 128 + ((unit ^ (r & 7)) << 4);
-                        if (MODE == 0) *reinterpret_cast<uint4*>(sE1 + off) = make_uint4(e1[u * 4], e1[u * 4 + 1], e1[u * 4 + 2], e1[u * 4 + 3]);
-                        *reinterpret_cast<uint4*>(sE2 + off) = make_uint4(e2[u * 4], e2[u * 4 + 1], e2[u * 4 + 2], e2[u * 4 + 3]);
-                    }
-                    fence_proxy_async_smem();
-                }
+                // E operands over the score columns this warp has read (its own lanes, its own 32 columns)
+                if (MODE == 0) tmem_st_32x32_x16(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, e1);
+                tmem_st_32x32_x16(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, e2);
+                tmem_st_wait_all();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane_idx == 0) mbar_arrive(&e_full[eb]);
-                ++ec;
+                if (lane_idx == 0) mbar_arrive(&e_full[tb]);
                 VLB_PROF(5);   // E store, completion, fences, publish
-                if (MODE == 0 && tid_e < BY && t + 1 < n) {  // publish tile t+1's statistics (other buffer)
-                    sLse[((tc + 1) & 1) * BY + tid_e] = nl;
-                    sDelta[((tc + 1) & 1) * BY + tid_e] = nd;
-                }
             }
             // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work); columns split by `half`
             if (n > 0) {  // the commit of the last tile's accumulate MMAs covers every earlier tcgen05 op of the MMA thread
-                mbar_wait(&e_done[(ec - 1) & 1], ((ec - 1) >> 1) & 1, 95);
+                mbar_wait(&e_done[(tc - 1) & 1], ((tc - 1) >> 1) & 1, 95);
                 tcgen05_fence_after();
             }
-            const bool valid = xrow < (p.row_starts ? kv_len : p.S);  // packed rows: the tile may run into the next sequence
-            const long long grow = (p.row_starts ? (long long)p.row_starts[b] : (long long)b * p.S) + xrow;
+            // Each warp owns a [32 rows x 64 columns] block of every accumulator.  A thread holds one ROW of a 32-column chunk
+            // (TMEM lane = row): storing it directly scatters every warp-wide 16-byte store over 32 cache lines (the epilogue cost
+            // 8 230 cycles per item in the dK/dV pass, profiles/r2k_attn.log).  The chunk goes through a swizzled 2 KB staging
+            // block of the warp instead and leaves as 64-byte row segments, 8 rows per store instruction.
+            const int row_lim = p.row_starts ? kv_len : p.S;   // packed rows: the tile may run into the next sequence
+            const long long grow0 = (p.row_starts ? (long long)p.row_starts[b] : (long long)b * p.S) + x0 + quad * 32;
+            uint8_t* stg = sOut + (warp_idx - 2) * 2048;
 #pragma unroll
             for (int a = (MODE == 0 ? 0 : 1); a < 2; ++a) {
-                __nv_bfloat16* dst = (a == 0 ? p.out1 + grow * p.ld1 : p.out2 + grow * p.ld2) + (long long)hx * DH;
+                __nv_bfloat16* dst0 = (a == 0 ? p.out1 : p.out2) + (long long)hx * DH;
+                const long long ldd = a == 0 ? p.ld1 : p.ld2;
+                const float osc = a == 0 ? 1.f : p.scale;   // dK / dQ: the softmax scale folded out of dS
 #pragma unroll
                 for (int cc = 0; cc < DH / 64; ++cc) {
                     const int c = half * (DH / 64) + cc;
@@ -486,17 +515,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
 #pragma unroll
                         for (int i = 0; i < 32; ++i) acc[i] = 0u;
                     }
-                    if (valid) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            uint4 v;
-                            v.x = pack_bf16x2(__uint_as_float(acc[u * 8 + 0]), __uint_as_float(acc[u * 8 + 1]));
-                            v.y = pack_bf16x2(__uint_as_float(acc[u * 8 + 2]), __uint_as_float(acc[u * 8 + 3]));
-                            v.z = pack_bf16x2(__uint_as_float(acc[u * 8 + 4]), __uint_as_float(acc[u * 8 + 5]));
-                            v.w = pack_bf16x2(__uint_as_float(acc[u * 8 + 6]), __uint_as_float(acc[u * 8 + 7]));
-                            *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = v;
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 v;
+                        v.x = pack_bf16x2(__uint_as_float(acc[u * 8 + 0]) * osc, __uint_as_float(acc[u * 8 + 1]) * osc);
+                        v.y = pack_bf16x2(__uint_as_float(acc[u * 8 + 2]) * osc, __uint_as_float(acc[u * 8 + 3]) * osc);
+                        v.z = pack_bf16x2(__uint_as_float(acc[u * 8 + 4]) * osc, __uint_as_float(acc[u * 8 + 5]) * osc);
+                        v.w = pack_bf16x2(__uint_as_float(acc[u * 8 + 6]) * osc, __uint_as_float(acc[u * 8 + 7]) * osc);
+                        *reinterpret_cast<uint4*>(stg + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4)) = v;
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + (lane_idx >> 2), u = lane_idx & 3;
+                        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+                        if (x0 + quad * 32 + rr < row_lim)
+                            *reinterpret_cast<uint4*>(dst0 + (grow0 + rr) * ldd + c * 32 + u * 8) = v;
+                    }
+                    __syncwarp();
                 }
             }
             if (n > 0) {
@@ -518,13 +554,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
     }
 }
 
-template <int DH, int MODE, bool TS, int DBG = 0>
+template <int DH, int MODE, int DBG = 0>
 static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, const Params& p,
                   cudaStream_t s) {
     constexpr int NCH = DH / 64;
-    constexpr int NST = TS ? 5 : 3;
-    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + (TS ? 0 : 4 * BX * 128) + 4 * BY * 4 + 256 + 1024;
-    auto kern = attn_bwd_tc_kernel<DH, MODE, TS, DBG>;
+    constexpr int smem_bytes = 2 * NCH * BX * 128 + NST * 2 * NCH * BY * 128 + NST * 128 * 4 + NEW * 2048 + 256 + 1024;
+    auto kern = attn_bwd_tc_kernel<DH, MODE, DBG>;
     static bool configured = false;
     if (!configured) {
         VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -638,28 +673,23 @@ extern "C" int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     // pass 1: dK, dV
     p.out1 = (__nv_bfloat16*)dv; p.ld1 = lddv; p.out2 = (__nv_bfloat16*)dk; p.ld2 = lddk;
     p.n_work = p.n_xb * KVH * B;
-    // VLB200_ATTN_BWD_TS=1: elementwise results stay in tensor memory (TS-mode accumulate MMAs)
-    static const bool ts = [] { const char* e = getenv("VLB200_ATTN_BWD_TS"); return e && e[0] == '1'; }();
     static const int dbg = [] { const char* e = getenv("VLB200_ATTN_BWD_DBG"); return e ? atoi(e) : 0; }();
     if (dbg && head_dim == 128) {
-        p.n_work = p.n_xb * KVH * B;
         switch (dbg) {
-#define VLB_DBG_CASE(D) case D: rc = launch<128, 0, true, D>(xk, xv, yq, ydo, p, s); if (rc) return rc; \
+#define VLB_DBG_CASE(D) case D: rc = launch<128, 0, D>(xk, xv, yq, ydo, p, s); if (rc) return rc; \
             p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq; p.n_work = p.n_xb * H * B; \
-            return launch<128, 1, true, D>(xq, xdo, yk, yv, p, s);
+            return launch<128, 1, D>(xq, xdo, yk, yv, p, s);
             VLB_DBG_CASE(1) VLB_DBG_CASE(2) VLB_DBG_CASE(3) VLB_DBG_CASE(4) VLB_DBG_CASE(7) VLB_DBG_CASE(8)
 #undef VLB_DBG_CASE
             default: break;
         }
     }
-    if (ts) rc = head_dim == 64 ? launch<64, 0, true>(xk, xv, yq, ydo, p, s) : launch<128, 0, true>(xk, xv, yq, ydo, p, s);
-    else rc = head_dim == 64 ? launch<64, 0, false>(xk, xv, yq, ydo, p, s) : launch<128, 0, false>(xk, xv, yq, ydo, p, s);
+    rc = head_dim == 64 ? launch<64, 0>(xk, xv, yq, ydo, p, s) : launch<128, 0>(xk, xv, yq, ydo, p, s);
     if (rc) return rc;
     // pass 2: dQ
     p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq;
     p.n_work = p.n_xb * H * B;
-    if (ts) return head_dim == 64 ? launch<64, 1, true>(xq, xdo, yk, yv, p, s) : launch<128, 1, true>(xq, xdo, yk, yv, p, s);
-    return head_dim == 64 ? launch<64, 1, false>(xq, xdo, yk, yv, p, s) : launch<128, 1, false>(xq, xdo, yk, yv, p, s);
+    return head_dim == 64 ? launch<64, 1>(xq, xdo, yk, yv, p, s) : launch<128, 1>(xq, xdo, yk, yv, p, s);
 }
 
 extern "C" int vlb200_attn_bwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

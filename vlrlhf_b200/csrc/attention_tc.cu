@@ -189,87 +189,94 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             }
         }
     } else if (warp_idx == 1) {
-        // ===================== MMA issuer =====================
-        if (lane_idx == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
-            constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
-            uint32_t item = 0, g0 = 0, sc = 0;
-            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
-                int b, h, qb;
-                work_coords(p, w, b, h, qb);
-                const KvPlan plan = kv_plan(p, b, qb);
-                if (plan.skip) continue;
-                const int n_tiles = plan.n_ctx + plan.n_self;
-                if (QT) mbar_wait(qt_full, item & 1, 31);
-                else mbar_wait(q_full, item & 1, 30);
-                tcgen05_fence_after();
-                const uint32_t sc0 = sc;
-                // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
-                // published -- neither blocks the other (a blocked in-order loop exposed the full TMA latency per tile)
-                int js = 0, jp = 0;
-                long long t_spin = 0;
-                while (jp < n_tiles) {
-                    bool progressed = false;
-                    if (js < n_tiles) {
-                        const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
-                        // S buffer free: VAR 0 -- the softmax threads have read it; TS -- P_j lives in S_j's buffer until PV_j
-                        // has consumed it: the MMAs of this thread execute in issue order, so S_{j+2} may be issued once PV_j has
-                        bool s_free;
-                        if (TS) s_free = js - jp < 2;
-                        else s_free = mbar_try_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
-                        if (s_free && mbar_try_wait(&kv_full[st], (g / NSTAGE) & 1)) {
-                            tcgen05_fence_after();
-                            const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 0);
-                            const uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0);
+        // ===================== MMA issuer (whole warp converged; one elected lane issues: attention_bwd_tc.cu) ==========
+        constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
+        constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
+        const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ), 1024, 0);
+        uint32_t item = 0, g0 = 0, sc = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, h, qb;
+            work_coords(p, w, b, h, qb);
+            const KvPlan plan = kv_plan(p, b, qb);
+            if (__shfl_sync(0xffffffffu, (int)plan.skip, 0)) continue;
+            const int n_tiles = __shfl_sync(0xffffffffu, plan.n_ctx + plan.n_self, 0);
+            if (QT) mbar_wait(qt_full, item & 1, 31);
+            else mbar_wait(q_full, item & 1, 30);
+            __syncwarp();
+            tcgen05_fence_after();
+            const uint32_t sc0 = sc;
+            // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
+            // published -- neither blocks the other (a blocked in-order loop exposed the full TMA latency per tile)
+            int js = 0, jp = 0;
+            long long t_spin = 0;
+            while (jp < n_tiles) {
+                bool progressed = false;
+                if (js < n_tiles) {
+                    const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
+                    // S buffer free: VAR 0 -- the softmax threads have read it; TS -- P_j lives in S_j's buffer until PV_j
+                    // has consumed it: the MMAs of one thread execute in issue order, so S_{j+2} may be issued once PV_j has
+                    bool s_free;
+                    if (TS) s_free = js - jp < 2;
+                    else s_free = __all_sync(0xffffffffu, mbar_test_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1));
+                    if (s_free && __all_sync(0xffffffffu, mbar_test_wait(&kv_full[st], (g / NSTAGE) & 1))) {
+                        tcgen05_fence_after();
+                        const uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0);
+                        if (elect_one_sync()) {
+                            if (!(DBG & 1)) {
 #pragma unroll
-                            for (int k = 0; k < DH / 16; ++k) {
-                                const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
-                                if (DBG & 1) continue;
-                                if (QT) umma_f16_ts(tmem_base + TM_S + sb * BN, tmem_base + TM_Q + k * 8, dk + off, idesc_s, k != 0);
-                                else umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
+                                for (int k = 0; k < DH / 16; ++k) {
+                                    const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
+                                    if (QT) umma_f16_ts(tmem_base + TM_S + sb * BN, tmem_base + TM_Q + k * 8, dk + off, idesc_s, k != 0);
+                                    else umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
+                                }
                             }
                             umma_commit(&s_full[sb]);
                             if (!QT && js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
-                            ++sc; ++js;
-                            progressed = true;
                         }
+                        __syncwarp();
+                        ++sc; ++js;
+                        progressed = true;
                     }
-                    if (!progressed && jp < js) {
-                        const uint32_t g = g0 + jp, st = g % NSTAGE;
-                        if (mbar_try_wait(&p_full[st], (g / NSTAGE) & 1)) {
-                            if (jp == 0) mbar_wait(o_free, (item & 1) ^ 1, 60);  // epilogue of the previous item has read O
-                            tcgen05_fence_after();
-                            const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
-                            const uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
+                }
+                if (!progressed && jp < js) {
+                    const uint32_t g = g0 + jp, st = g % NSTAGE;
+                    if (__all_sync(0xffffffffu, mbar_test_wait(&p_full[st], (g / NSTAGE) & 1))) {
+                        if (jp == 0) { mbar_wait(o_free, (item & 1) ^ 1, 60); __syncwarp(); }  // epilogue of the previous item has read O
+                        tcgen05_fence_after();
+                        const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
+                        const uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
+                        if (elect_one_sync()) {
+                            if (!(DBG & 1)) {
 #pragma unroll
-                            for (int k = 0; k < BN / 16; ++k) {
-                                if (DBG & 1) continue;
-                                if (TS)
-                                    umma_f16_ts(tmem_base + TM_O, tmem_base + TM_S + ((sc0 + jp) & 1) * BN + k * 8,
-                                                dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
-                                else
-                                    umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
-                                                dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                                for (int k = 0; k < BN / 16; ++k) {
+                                    if (TS)
+                                        umma_f16_ts(tmem_base + TM_O, tmem_base + TM_S + ((sc0 + jp) & 1) * BN + k * 8,
+                                                    dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                                    else
+                                        umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
+                                                    dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                                }
                             }
                             umma_commit(pv_done);
                             umma_commit(&kv_empty[st]);
-                            ++jp;
-                            progressed = true;
                         }
-                    }
-                    if (!progressed) {
-                        if (t_spin == 0) t_spin = clock64();
-                        else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
-                            printf("[vlb200] attn_fwd_tc MMA watchdog: block %d js %d jp %d n %d\n", blockIdx.x, js, jp, n_tiles);
-                            __trap();
-                        }
-                    } else {
-                        t_spin = 0;
+                        __syncwarp();
+                        ++jp;
+                        progressed = true;
                     }
                 }
-                g0 += n_tiles;
-                ++item;
+                if (!progressed) {
+                    if (t_spin == 0) t_spin = clock64();
+                    else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
+                        if (lane_idx == 0) printf("[vlb200] attn_fwd_tc MMA watchdog: block %d js %d jp %d n %d\n", blockIdx.x, js, jp, n_tiles);
+                        __trap();
+                    }
+                } else {
+                    t_spin = 0;
+                }
             }
+            g0 += n_tiles;
+            ++item;
         }
     } else {
         // ===================== softmax + epilogue (4 warps, one row per thread) =====================
@@ -334,7 +341,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 const int vlim = (is_ctx ? plan.ctx_len : kv_len) - k0;              // keys [0, vlim) of the tile exist
                 const int clim = (p.causal && !is_ctx) ? qrow - k0 : BN;             // keys [0, clim] of the tile are not in the future
                 const bool need_mask = vlim < BN || (p.causal && !is_ctx && k0 + BN > qb * BM);
-                float mx = -INFINITY;
+                // row max over 8 independent chains (one dependent chain of 64 3-input max instructions cost 538 cycles per
+                // tile: profiles/r2j_attn_phases.log)
+                float mxp[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mxp[i] = -INFINITY;
                 if (need_mask) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -342,16 +353,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                         for (int i = 0; i < 32; ++i) {
                             const int kk = c * 32 + i;
                             if (kk >= vlim || kk > clim) sr[c][i] = 0xff800000u;  // -inf
-                            mx = fmaxf(mx, __uint_as_float(sr[c][i]));
+                            mxp[(c & 1) * 4 + (i & 3)] = fmaxf(mxp[(c & 1) * 4 + (i & 3)], __uint_as_float(sr[c][i]));
                         }
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
+                        for (int i = 0; i < 32; ++i)
+                            mxp[(c & 1) * 4 + (i & 3)] = fmaxf(mxp[(c & 1) * 4 + (i & 3)], __uint_as_float(sr[c][i]));
                     }
                 }
+                float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
                 mx *= sl2;  // scale > 0: max commutes with the scaling (log2 domain from here on)
                 // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^RESCALE_THRESHOLD
                 float corr = 1.f;
@@ -366,7 +379,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 // P = exp2(s*c - m) (bf16) into the K slot of this stage (K_j is dead: S_j has retired), laid out as a
                 // K-major 128B-swizzled A operand: chunk = 64 keys, row pitch 128 B
                 uint8_t* sP = sStage + st * STAGE_BYTES;
-                float rs0 = 0.f, rs1 = 0.f;
+                float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t wt[16];
@@ -378,8 +391,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                             float p0 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e]), sl2, neg_m);
                             float p1 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e + 1]), sl2, neg_m);
                             if (!(DBG & 2)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
-                            rs0 += p0;
-                            rs1 += p1;
+                            if (e & 1) { rs2 += p0; rs3 += p1; }
+                            else { rs0 += p0; rs1 += p1; }
                             w4[e] = pack_bf16x2(p0, p1);
                         }
                         if (TS) {   // P_j over S_j's first 64 columns: keys 2i | 2i+1 in column i of this thread's lane
@@ -392,7 +405,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                     }
                     if (TS) tmem_st_32x32_x16(tmem_base + lane_addr + TM_S + sb * BN + c * 16, wt);
                 }
-                l_run = l_run * corr + (rs0 + rs1);
+                l_run = l_run * corr + ((rs0 + rs1) + (rs2 + rs3));
                 VLB_PROF(4);   // exponentials, row sum, pack, P store issue
                 // publish P only after PV of the previous tile has retired: keeps the pv_done phase bookkeeping exact
                 // (a waiter never runs two phases ahead) and orders the (rare) O correction before the next PV

@@ -35,6 +35,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking test (mbarrier.try_wait may SUSPEND the thread up to a system time limit when the phase is incomplete: wrong
+// tool for a polling loop that has other work to issue)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Blocking wait with a watchdog: code identifies the waiter in the trap message.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
@@ -63,6 +76,17 @@ __device__ __forceinline__ void tma_load_3d(const void* map, uint64_t* bar, void
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// one lane of a CONVERGED warp (deterministic for the full mask): the issue predicate of the tcgen05 instructions
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- tcgen05 / TMEM --------------------------------------------------------------------
