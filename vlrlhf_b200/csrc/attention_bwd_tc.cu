@@ -30,7 +30,7 @@ using namespace ptx;
 constexpr int BX = 128;  // stationary rows
 constexpr int BY = 64;   // streamed rows
 constexpr int NST = 4;   // streamed-tile ring depth
-constexpr int NTHREADS = 320;  // TMA warp, MMA warp, 8 elementwise warps (two per TMEM lane quadrant)
+constexpr int NTHREADS = 352;  // TMA warp, score-MMA warp, 8 elementwise warps (two per TMEM lane quadrant), accumulate-MMA warp
 constexpr int NEW = 8;         // elementwise warps
 constexpr float LOG2E_F = 1.4426950408889634f;
 
@@ -52,6 +52,11 @@ struct Params {
 
 // diagnostics (DBG bit 8): cycles one elementwise thread per CTA spends in each phase of its loop, summed over the grid
 __device__ unsigned long long g_bwd_prof[32];   // [MODE][16]
+// DBG bit 16: clock64 timestamps of CTA 0's first 64 tile iterations (one SM: the clocks of its warps are comparable):
+// [MODE][event][tile]; events: 0 elementwise starts waiting for the scores, 1 scores seen, 2 E published (arrive issued),
+// 3 MMA warp sees E, 4 accumulate MMAs issued, 5 MMA warp sees the streamed tile of the next score pair, 6 score MMAs issued
+__device__ long long g_bwd_trace[2 * 32 * 64];   // events 8+w / 16+w: elementwise warp w publishes E / sees the scores
+#define VLB_TRACE(ev, idx) do { if ((DBG & 16) && blockIdx.x == 0 && (idx) < 64 && lane_idx == 0) g_bwd_trace[(MODE * 32 + (ev)) * 64 + (idx)] = clock64(); } while (0)
 #define VLB_PROF(i) do { if (DBG & 8) { const long long t_ = clock64(); prof[i] += (unsigned long long)(t_ - tp); tp = t_; } } while (0)
 
 __device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
@@ -270,11 +275,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             ++item;
         }
     } else if (warp_idx == 1) {
-        // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+        // ===================== score MMAs (whole warp converged; one elected lane issues) =====================
+        // The MMAs are issued by TWO warps in a fixed order -- this one: S / dP of tile t once its streamed tile has landed and
+        // the accumulate MMAs of tile t-2 have COMPLETED (they read the E operands that live in t's score buffer); warp 10:
+        // the accumulate MMAs of tile t once its E operands are published.  One warp doing both spent ~1 700 of its ~2 400
+        // cycles per tile in scalar control code between the two issue blocks (barrier polls, fences, descriptor set-up,
+        // commits: profiles/r2o2_bwd_trace.log), which made it the bound of both passes.  The tile counter runs across items:
+        // the first score tiles of the next item are issued while the elementwise warps write the previous item's epilogue.
         constexpr uint32_t idesc_t = make_idesc_bf16_f32(BX, BY, false, false);
-        constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
         const uint64_t dx1 = make_smem_desc_sw128(smem_u32(sX1), 1024, 0), dx2 = make_smem_desc_sw128(smem_u32(sX2), 1024, 0);
-        uint32_t item = 0, yc = 0, tc = 0, ec = 0;
+        uint32_t item = 0, tc = 0;
         for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
             int b, hx, xb;
             item_coords<MODE>(p, w, b, hx, xb);
@@ -284,82 +294,84 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             if (MODE == 1) mbar_wait(xt_full, item & 1, 31);
             else mbar_wait(x_full, item & 1, 30);
             __syncwarp();
-            tcgen05_fence_after();
-            const uint32_t y0 = yc;
-            // dynamic issue order (see attention_tc.cu): the score MMAs of tile ts as soon as its streamed tile has landed and
-            // the accumulate MMAs of tile ts-2 have been issued (they read the E operands that live in ts's score buffer),
-            // otherwise the accumulate MMAs of tile ta once its E operands are published
-            int ts = 0, ta = 0;
-            long long t_spin = 0;
-            while (ta < n) {
-                bool progressed = false;
-                if (ts < n && ts - ta < 2) {
-                    const uint32_t yi = y0 + ts, st = yi % NST, tb = tc & 1;
-                    if (__all_sync(0xffffffffu, mbar_test_wait(&y_full[st], (yi / NST) & 1))) {
-                        tcgen05_fence_after();
-                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
-                        const uint64_t dy1 = make_smem_desc_sw128(y1, 1024, 0), dy2 = make_smem_desc_sw128(y2, 1024, 0);
-                        if (elect_one_sync()) {
-                            if (!(DBG & 1)) {
+            for (int ts = 0; ts < n; ++ts, ++tc) {
+                const uint32_t st = tc % NST, tb = tc & 1;
+                mbar_wait(&y_full[st], (tc / NST) & 1, 40);
+                if (tc >= 2) mbar_wait(&e_done[tb], ((tc - 2) >> 1) & 1, 44);
+                __syncwarp();
+                VLB_TRACE(5, tc);
+                tcgen05_fence_after();
+                const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                uint64_t dy1 = make_smem_desc_sw128(y1, 1024, 0), dy2 = make_smem_desc_sw128(y2, 1024, 0);
+                uint64_t ax1 = dx1, ax2 = dx2;
+                // (opaque copies: the per-k descriptors are derived HERE by immediate adds on the uniform datapath; hoisted out
+                // of the loop they lived in vector registers and cost two R2UR each)
+                asm volatile("" : "+l"(dy1), "+l"(dy2), "+l"(ax1), "+l"(ax2));
+                if (elect_one_sync()) {
+                    VLB_TRACE(26, tc);
+                    if (!(DBG & 1)) {
 #pragma unroll
-                                for (int k = 0; k < DH / 16; ++k) {
-                                    const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
-                                    if (MODE == 1) umma_f16_ts(tmem_base + TM_T1 + tb * BY, tmem_base + TM_X1 + k * 8, dy1 + yo, idesc_t, k != 0);
-                                    else umma_f16_ss(tmem_base + TM_T1 + tb * BY, dx1 + xo, dy1 + yo, idesc_t, k != 0);
-                                }
-#pragma unroll
-                                for (int k = 0; k < DH / 16; ++k) {
-                                    const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
-                                    if (MODE == 1) umma_f16_ts(tmem_base + TM_T2 + tb * BY, tmem_base + TM_X2 + k * 8, dy2 + yo, idesc_t, k != 0);
-                                    else umma_f16_ss(tmem_base + TM_T2 + tb * BY, dx2 + xo, dy2 + yo, idesc_t, k != 0);
-                                }
-                            }
-                            umma_commit(&t_full[tb]);
-                            if (MODE == 0 && ts == n - 1) umma_commit(x_empty);
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                            if (MODE == 1) umma_f16_ts(tmem_base + TM_T1 + tb * BY, tmem_base + TM_X1 + k * 8, dy1 + yo, idesc_t, k != 0);
+                            else umma_f16_ss(tmem_base + TM_T1 + tb * BY, ax1 + xo, dy1 + yo, idesc_t, k != 0);
                         }
-                        __syncwarp();
-                        ++tc; ++ts;
-                        progressed = true;
-                    }
-                }
-                if (!progressed && ta < ts) {
-                    const uint32_t yi = y0 + ta, st = yi % NST, eb = ec & 1;
-                    if (__all_sync(0xffffffffu, mbar_test_wait(&e_full[eb], (ec >> 1) & 1))) {
-                        if (ta == 0) { mbar_wait(acc_free, (item & 1) ^ 1, 60); __syncwarp(); }
-                        tcgen05_fence_after();
-                        const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
-                        const uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
-                        if (elect_one_sync()) {
-                            if (!(DBG & 1)) {
 #pragma unroll
-                                for (int k = 0; k < BY / 16; ++k) {
-                                    const uint32_t acc = (ta != 0 || k != 0) ? 1u : 0u;
-                                    // streamed rows 16k..16k+15: written by elementwise half k/2 at columns half*32 + (k%2)*8 of the score buffer
-                                    const uint32_t ac = eb * BY + (k >> 1) * 32 + (k & 1) * 8;
-                                    // MODE 0: dV += P^T dO, dK += dS^T Q ; MODE 1: dQ += dS K
-                                    if (MODE == 0) umma_f16_ts(tmem_base + TM_A1, tmem_base + TM_T1 + ac, by2 + (uint64_t)(k * 128), idesc_a, acc);
-                                    umma_f16_ts(tmem_base + TM_A2, tmem_base + TM_T2 + ac, by1 + (uint64_t)(k * 128), idesc_a, acc);
-                                }
-                            }
-                            umma_commit(&e_done[eb]);
-                            umma_commit(&y_empty[st]);
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t xo = ((k >> 2) * XCH + (k & 3) * 32) >> 4, yo = ((k >> 2) * YCH + (k & 3) * 32) >> 4;
+                            if (MODE == 1) umma_f16_ts(tmem_base + TM_T2 + tb * BY, tmem_base + TM_X2 + k * 8, dy2 + yo, idesc_t, k != 0);
+                            else umma_f16_ss(tmem_base + TM_T2 + tb * BY, ax2 + xo, dy2 + yo, idesc_t, k != 0);
                         }
-                        __syncwarp();
-                        ++ec; ++ta;
-                        progressed = true;
                     }
+                    VLB_TRACE(27, tc);
+                    umma_commit(&t_full[tb]);
+                    if (MODE == 0 && ts == n - 1) umma_commit(x_empty);
                 }
-                if (!progressed) {
-                    if (t_spin == 0) t_spin = clock64();
-                    else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
-                        if (lane_idx == 0) printf("[vlb200] attn_bwd_tc MMA watchdog: block %d mode %d ts %d ta %d n %d\n", blockIdx.x, MODE, ts, ta, n);
-                        __trap();
-                    }
-                } else {
-                    t_spin = 0;
-                }
+                __syncwarp();
+                VLB_TRACE(6, tc);
             }
-            yc += n;
+            ++item;
+        }
+    } else if (warp_idx == 10) {
+        // ===================== accumulate MMAs (whole warp converged; one elected lane issues) =====================
+        constexpr uint32_t idesc_a = make_idesc_bf16_f32(BX, DH, false, true);  // B = streamed tile, MN-major
+        uint32_t item = 0, ec = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, hx, xb;
+            item_coords<MODE>(p, w, b, hx, xb);
+            const Item it = item_plan<MODE>(p, b, xb);
+            const int n = __shfl_sync(0xffffffffu, it.per_rep * it.reps, 0);
+            if (n == 0) continue;
+            for (int ta = 0; ta < n; ++ta, ++ec) {
+                const uint32_t st = ec % NST, eb = ec & 1;
+                mbar_wait(&e_full[eb], (ec >> 1) & 1, 41);
+                if (ta == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);   // the previous item's epilogue has read the accumulators
+                __syncwarp();
+                VLB_TRACE(3, ec);
+                tcgen05_fence_after();
+                const uint32_t y1 = smem_u32(sY + st * 2 * Y_BYTES), y2 = y1 + Y_BYTES;
+                uint64_t by1 = make_smem_desc_sw128(y1, 1024, YCH), by2 = make_smem_desc_sw128(y2, 1024, YCH);
+                asm volatile("" : "+l"(by1), "+l"(by2));
+                if (elect_one_sync()) {
+                    VLB_TRACE(24, ec);
+                    if (!(DBG & 1)) {
+#pragma unroll
+                        for (int k = 0; k < BY / 16; ++k) {
+                            const uint32_t acc = (ta != 0 || k != 0) ? 1u : 0u;
+                            // streamed rows 16k..16k+15: written by elementwise half k/2 at columns half*32 + (k%2)*8 of the score buffer
+                            const uint32_t ac = eb * BY + (k >> 1) * 32 + (k & 1) * 8;
+                            // MODE 0: dV += P^T dO, dK += dS^T Q ; MODE 1: dQ += dS K
+                            if (MODE == 0) umma_f16_ts(tmem_base + TM_A1, tmem_base + TM_T1 + ac, by2 + (uint64_t)(k * 128), idesc_a, acc);
+                            umma_f16_ts(tmem_base + TM_A2, tmem_base + TM_T2 + ac, by1 + (uint64_t)(k * 128), idesc_a, acc);
+                        }
+                    }
+                    VLB_TRACE(25, ec);
+                    umma_commit(&e_done[eb]);
+                    umma_commit(&y_empty[st]);
+                }
+                __syncwarp();
+                VLB_TRACE(4, ec);
+            }
             ++item;
         }
     } else {
@@ -424,9 +436,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 const bool causal_t = sg.causal != 0;
                 if (MODE == 0) mbar_wait(&y_full[tc % NST], (tc / NST) & 1, 75);   // acquires the producer's statistics (long complete)
                 VLB_PROF(1);   // tile coordinates
+                if (warp_idx == 2) VLB_TRACE(0, tc);
                 mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
                 tcgen05_fence_after();
+                if (warp_idx == 2) VLB_TRACE(1, tc);
+                VLB_TRACE(16 + warp_idx - 2, tc);
                 VLB_PROF(2);   // wait for the score tiles
+                if (DBG & 32) {   // handshake only: the tensor side alone
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane_idx == 0) mbar_arrive(&e_full[tb]);
+                    continue;
+                }
                 uint32_t t1[32], t2[32];
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T1 + tb * BY + half * 32, t1);
                 tmem_ld_32x32b(tmem_base + lane_addr + TM_T2 + tb * BY + half * 32, t2);
@@ -485,6 +506,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane_idx == 0) mbar_arrive(&e_full[tb]);
+                if (warp_idx == 2) VLB_TRACE(2, tc);
+                VLB_TRACE(8 + warp_idx - 2, tc);
                 VLB_PROF(5);   // E store, completion, fences, publish
             }
             // ---- epilogue: accumulators -> bf16 -> global (zeros when the item had no work); columns split by `half`
@@ -617,6 +640,10 @@ extern "C" int vlbdbg_attn_bwd_profile(unsigned long long* out32, int reset) {
     return 0;
 }
 
+extern "C" int vlbdbg_attn_bwd_trace(long long* out3072) {
+    return cudaMemcpyFromSymbol(out3072, vlb::attn_bwd_tc::g_bwd_trace, 2 * 32 * 64 * sizeof(long long)) != cudaSuccess;
+}
+
 extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
                                         const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream) {
     VLB_REQUIRE(out && dout && delta, "attn_delta: null pointer");
@@ -679,7 +706,7 @@ extern "C" int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k,
 #define VLB_DBG_CASE(D) case D: rc = launch<128, 0, D>(xk, xv, yq, ydo, p, s); if (rc) return rc; \
             p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq; p.n_work = p.n_xb * H * B; \
             return launch<128, 1, D>(xq, xdo, yk, yv, p, s);
-            VLB_DBG_CASE(1) VLB_DBG_CASE(2) VLB_DBG_CASE(3) VLB_DBG_CASE(4) VLB_DBG_CASE(7) VLB_DBG_CASE(8)
+            VLB_DBG_CASE(1) VLB_DBG_CASE(2) VLB_DBG_CASE(3) VLB_DBG_CASE(4) VLB_DBG_CASE(7) VLB_DBG_CASE(8) VLB_DBG_CASE(9) VLB_DBG_CASE(16) VLB_DBG_CASE(32) VLB_DBG_CASE(36)
 #undef VLB_DBG_CASE
             default: break;
         }

@@ -205,74 +205,82 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             __syncwarp();
             tcgen05_fence_after();
             const uint32_t sc0 = sc;
-            // dynamic issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is
-            // published -- neither blocks the other (a blocked in-order loop exposed the full TMA latency per tile)
+            // Issue order: S_js as soon as its K tile and an S buffer are ready, else PV_jp once P_jp is published.  When only
+            // one of the two can come next the warp BLOCKS on that barrier (mbarrier.try_wait suspends it; a spinning warp takes
+            // issue slots from the softmax warp of its scheduler: attention_bwd_tc.cu, profiles/r2m_bwd_trace.log).
             int js = 0, jp = 0;
+            auto issue_s = [&]() {
+                const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
+                tcgen05_fence_after();
+                uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0), aq = dq;
+                asm volatile("" : "+l"(dk), "+l"(aq));   // opaque bases: per-k descriptors by immediate adds (attention_bwd_tc.cu)
+                if (elect_one_sync()) {
+                    if (!(DBG & 1)) {
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) {
+                            const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
+                            if (QT) umma_f16_ts(tmem_base + TM_S + sb * BN, tmem_base + TM_Q + k * 8, dk + off, idesc_s, k != 0);
+                            else umma_f16_ss(tmem_base + TM_S + sb * BN, aq + off, dk + off, idesc_s, k != 0);
+                        }
+                    }
+                    umma_commit(&s_full[sb]);
+                    if (!QT && js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
+                }
+                __syncwarp();
+                ++sc; ++js;
+            };
+            auto issue_pv = [&]() {
+                const uint32_t g = g0 + jp, st = g % NSTAGE;
+                if (jp == 0) { mbar_wait(o_free, (item & 1) ^ 1, 60); __syncwarp(); }  // epilogue of the previous item has read O
+                tcgen05_fence_after();
+                const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
+                uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
+                asm volatile("" : "+l"(dp), "+l"(dvv));
+                if (elect_one_sync()) {
+                    if (!(DBG & 1)) {
+#pragma unroll
+                        for (int k = 0; k < BN / 16; ++k) {
+                            if (TS)
+                                umma_f16_ts(tmem_base + TM_O, tmem_base + TM_S + ((sc0 + jp) & 1) * BN + k * 8,
+                                            dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                            else
+                                umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
+                                            dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(pv_done);
+                    umma_commit(&kv_empty[st]);
+                }
+                __syncwarp();
+                ++jp;
+            };
             long long t_spin = 0;
             while (jp < n_tiles) {
-                bool progressed = false;
-                if (js < n_tiles) {
-                    const uint32_t g = g0 + js, st = g % NSTAGE, sb = sc & 1;
-                    // S buffer free: VAR 0 -- the softmax threads have read it; TS -- P_j lives in S_j's buffer until PV_j
-                    // has consumed it: the MMAs of one thread execute in issue order, so S_{j+2} may be issued once PV_j has
-                    bool s_free;
-                    if (TS) s_free = js - jp < 2;
-                    else s_free = __all_sync(0xffffffffu, mbar_test_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1));
-                    if (s_free && __all_sync(0xffffffffu, mbar_test_wait(&kv_full[st], (g / NSTAGE) & 1))) {
-                        tcgen05_fence_after();
-                        const uint64_t dk = make_smem_desc_sw128(smem_u32(sStage + st * STAGE_BYTES), 1024, 0);
-                        if (elect_one_sync()) {
-                            if (!(DBG & 1)) {
-#pragma unroll
-                                for (int k = 0; k < DH / 16; ++k) {
-                                    const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
-                                    if (QT) umma_f16_ts(tmem_base + TM_S + sb * BN, tmem_base + TM_Q + k * 8, dk + off, idesc_s, k != 0);
-                                    else umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
-                                }
-                            }
-                            umma_commit(&s_full[sb]);
-                            if (!QT && js == n_tiles - 1) umma_commit(q_empty);  // Q tile free once the last S retires
-                        }
-                        __syncwarp();
-                        ++sc; ++js;
-                        progressed = true;
-                    }
+                // S buffer free: VAR 0 -- the softmax threads have read it (s_empty); TS -- P_j lives in S_j's buffer until PV_j
+                // has consumed it: the MMAs of one thread execute in issue order, so S_{j+2} may be issued once PV_j has
+                const bool s_wanted = js < n_tiles && (!TS || js - jp < 2);
+                if (!s_wanted) {                 // PV_jp is the only thing that can come next
+                    const uint32_t g = g0 + jp;
+                    mbar_wait(&p_full[g % NSTAGE], (g / NSTAGE) & 1, 42);
+                    __syncwarp();
+                    issue_pv();
+                    continue;
                 }
-                if (!progressed && jp < js) {
-                    const uint32_t g = g0 + jp, st = g % NSTAGE;
-                    if (__all_sync(0xffffffffu, mbar_test_wait(&p_full[st], (g / NSTAGE) & 1))) {
-                        if (jp == 0) { mbar_wait(o_free, (item & 1) ^ 1, 60); __syncwarp(); }  // epilogue of the previous item has read O
-                        tcgen05_fence_after();
-                        const uint32_t pbase = smem_u32(sStage + st * STAGE_BYTES), vbase = pbase + KP_BYTES;
-                        const uint64_t dp = make_smem_desc_sw128(pbase, 1024, 0), dvv = make_smem_desc_sw128(vbase, 1024, CHUNK_BYTES);
-                        if (elect_one_sync()) {
-                            if (!(DBG & 1)) {
-#pragma unroll
-                                for (int k = 0; k < BN / 16; ++k) {
-                                    if (TS)
-                                        umma_f16_ts(tmem_base + TM_O, tmem_base + TM_S + ((sc0 + jp) & 1) * BN + k * 8,
-                                                    dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
-                                    else
-                                        umma_f16_ss(tmem_base + TM_O, dp + (uint64_t)(((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4),
-                                                    dvv + (uint64_t)(k * 128), idesc_o, (jp != 0 || k != 0) ? 1u : 0u);
-                                }
-                            }
-                            umma_commit(pv_done);
-                            umma_commit(&kv_empty[st]);
-                        }
-                        __syncwarp();
-                        ++jp;
-                        progressed = true;
-                    }
+                const uint32_t gs = g0 + js, gp = g0 + jp;
+                bool s_ready = __all_sync(0xffffffffu, mbar_test_wait(&kv_full[gs % NSTAGE], (gs / NSTAGE) & 1));
+                if (s_ready && !TS) s_ready = __all_sync(0xffffffffu, mbar_test_wait(&s_empty[sc & 1], ((sc >> 1) & 1) ^ 1));
+                if (s_ready) { issue_s(); t_spin = 0; continue; }
+                if (jp < js && __all_sync(0xffffffffu, mbar_test_wait(&p_full[gp % NSTAGE], (gp / NSTAGE) & 1))) { issue_pv(); t_spin = 0; continue; }
+                if (jp == js && TS) {            // nothing to multiply by V yet: the K tile is the only thing to wait for
+                    mbar_wait(&kv_full[gs % NSTAGE], (gs / NSTAGE) & 1, 43);
+                    __syncwarp();
+                    continue;
                 }
-                if (!progressed) {
-                    if (t_spin == 0) t_spin = clock64();
-                    else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
-                        if (lane_idx == 0) printf("[vlb200] attn_fwd_tc MMA watchdog: block %d js %d jp %d n %d\n", blockIdx.x, js, jp, n_tiles);
-                        __trap();
-                    }
-                } else {
-                    t_spin = 0;
+                __nanosleep(32);
+                if (t_spin == 0) t_spin = clock64();
+                else if (clock64() - t_spin > VLB_WATCHDOG_CYCLES) {
+                    if (lane_idx == 0) printf("[vlb200] attn_fwd_tc MMA watchdog: block %d js %d jp %d n %d\n", blockIdx.x, js, jp, n_tiles);
+                    __trap();
                 }
             }
             g0 += n_tiles;
@@ -541,7 +549,7 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     switch (variant) {
 #define VLB_DBG_CASE(V) case V: return attn_tc::launch<128, V>(tq, tk, tv, p, st);
         VLB_DBG_CASE(10) VLB_DBG_CASE(12) VLB_DBG_CASE(20) VLB_DBG_CASE(22) VLB_DBG_CASE(30) VLB_DBG_CASE(32)
-        VLB_DBG_CASE(40) VLB_DBG_CASE(42) VLB_DBG_CASE(70) VLB_DBG_CASE(72) VLB_DBG_CASE(80) VLB_DBG_CASE(82)
+        VLB_DBG_CASE(40) VLB_DBG_CASE(42) VLB_DBG_CASE(70) VLB_DBG_CASE(72) VLB_DBG_CASE(80) VLB_DBG_CASE(81) VLB_DBG_CASE(82)
 #undef VLB_DBG_CASE
         default: break;
     }
