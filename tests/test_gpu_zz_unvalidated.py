@@ -263,6 +263,6 @@ def test_7b_shape_fixtures_with_shared_prefix(family):
     plan = eng.host_row_plan(ids, am)
     assert plan["prefix_rows"][0] > 0
     out = eng.step(*eng.prepare_inputs(ids, am, lb, px), train=False, **plan)
-    parity_log.check_step(tag + " share_prefix", out, d, rtol=1e-3 if family == "qwen" else 1.5e-3)   # (xc2: see test_gpu_xc2.py)
+    parity_log.check_step(tag + " share_prefix", out, d, rtol=parity_log.RTOL_7B)
     del eng
     torch.cuda.empty_cache()

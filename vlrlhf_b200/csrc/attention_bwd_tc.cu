@@ -434,11 +434,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 const int y0 = yt * BY;
                 const int ylen = sg.len;             // valid streamed rows of this tile's sequence
                 const bool causal_t = sg.causal != 0;
-                if (MODE == 0) mbar_wait(&y_full[tc % NST], (tc / NST) & 1, 75);   // acquires the producer's statistics (long complete)
                 VLB_PROF(1);   // tile coordinates
                 if (warp_idx == 2) VLB_TRACE(0, tc);
                 mbar_wait(&t_full[tb], (tc >> 1) & 1, 80 + tb);
                 tcgen05_fence_after();
+                if (MODE == 0) mbar_wait(&y_full[tc % NST], (tc / NST) & 1, 75);   // acquires the producer's statistics (complete: the scores are)
                 if (warp_idx == 2) VLB_TRACE(1, tc);
                 VLB_TRACE(16 + warp_idx - 2, tc);
                 VLB_PROF(2);   // wait for the score tiles
@@ -458,8 +458,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 bool need_mask;
                 if (MODE == 0) need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && x0 + BX - 1 > y0);
                 else need_mask = ymax >= ylen || x0 + BX > kv_len || (causal_t && ymax > x0);
-                const float* cl = sStat + (tc % NST) * 128 + half * 32;   // MODE 0: statistics of this warp's 32 columns
-                const float* cd = cl + 64;
+                // MODE 0: statistics of this warp's 32 columns (explicit ld.shared: through a pointer the compiler emitted
+                // generic LD.E.128, whose latency sat at the head of every tile)
+                const uint32_t cl = smem_u32(sStat) + (((tc % NST) * 128 + half * 32) << 2);
+                const uint32_t cd = cl + 256;
                 uint32_t e1[16], e2[16];
                 // two straight-line copies of the tile body (masked / unmasked): a per-element `if (need_mask)` costs a
                 // divergence region per element (seen in the r1 SASS: 33 BSSY/BSYNC pairs, 134 ISETP per 32 elements)
@@ -469,10 +471,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     for (int c4 = 0; c4 < 32; c4 += 4) {
                         float l4[4], d4[4];
                         if (MODE == 0) {
-                            const float4 a = *reinterpret_cast<const float4*>(cl + c4);
-                            const float4 d = *reinterpret_cast<const float4*>(cd + c4);
-                            l4[0] = a.x; l4[1] = a.y; l4[2] = a.z; l4[3] = a.w;
-                            d4[0] = d.x; d4[1] = d.y; d4[2] = d.z; d4[3] = d.w;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l4[0]), "=f"(l4[1]), "=f"(l4[2]), "=f"(l4[3]) : "r"(cl + c4 * 4));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d4[0]), "=f"(d4[1]), "=f"(d4[2]), "=f"(d4[3]) : "r"(cd + c4 * 4));
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) { l4[e] = row_lse2; d4[e] = row_delta; }

@@ -97,6 +97,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// (a polynomial 2^x on the FMA pipe for every fourth element -- Cody-Waite reduction + degree-3 minimax, 7.5e-5 relative --
+// was measured SLOWER, 1390 vs 1202 cycles per tile for the exponential phase: one softmax warp per scheduler is bound by
+// instruction issue, not by the MUFU: profiles/r2s_attn.log)
 
 constexpr int NSTAGE = 3;  // K/V ring depth
 
@@ -114,7 +117,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     constexpr int Q_BYTES = NCH * CHUNK_BYTES;
     constexpr int KV_BYTES = NCH * CHUNK_BYTES;  // one K or V tile
     constexpr int P_BYTES = 2 * CHUNK_BYTES;     // [128 q][128 keys] bf16
-    constexpr bool TS = (VAR % 10) >= 1, QT = (VAR % 10) >= 2;
+    constexpr bool TS = (VAR % 10) >= 1, QT = (VAR % 10) == 2;
     // diagnostics (wrong results, timing only), a bit mask: 1 = the MMA thread issues no MMAs (barriers only), 2 = the softmax
     // threads skip the exponentials, 4 = the producer loads no K/V tiles (stale shared memory)
     constexpr int DBG = VAR / 10;
@@ -351,9 +354,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                 const bool need_mask = vlim < BN || (p.causal && !is_ctx && k0 + BN > qb * BM);
                 // row max over 8 independent chains (one dependent chain of 64 3-input max instructions cost 538 cycles per
                 // tile: profiles/r2j_attn_phases.log)
-                float mxp[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) mxp[i] = -INFINITY;
                 if (need_mask) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -361,18 +361,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                         for (int i = 0; i < 32; ++i) {
                             const int kk = c * 32 + i;
                             if (kk >= vlim || kk > clim) sr[c][i] = 0xff800000u;  // -inf
-                            mxp[(c & 1) * 4 + (i & 3)] = fmaxf(mxp[(c & 1) * 4 + (i & 3)], __uint_as_float(sr[c][i]));
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            mxp[(c & 1) * 4 + (i & 3)] = fmaxf(mxp[(c & 1) * 4 + (i & 3)], __uint_as_float(sr[c][i]));
-                    }
                 }
-                float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])), fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+                // four independent chains of 3-input max (FMNMX3): 64 instructions, dependent depth 16
+                float mxp[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    mxp[c] = fmaxf(__uint_as_float(sr[c][0]), __uint_as_float(sr[c][1]));
+#pragma unroll
+                    for (int i = 2; i < 32; i += 2) mxp[c] = fmaxf(fmaxf(mxp[c], __uint_as_float(sr[c][i])), __uint_as_float(sr[c][i + 1]));
+                }
+                float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
                 mx *= sl2;  // scale > 0: max commutes with the scaling (log2 domain from here on)
                 // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^RESCALE_THRESHOLD
                 float corr = 1.f;
@@ -398,10 +398,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
                         for (int e = 0; e < 4; ++e) {
                             float p0 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e]), sl2, neg_m);
                             float p1 = fmaf(__uint_as_float(sr[c][u * 8 + 2 * e + 1]), sl2, neg_m);
-                            if (!(DBG & 2)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
+                            if (!(DBG & 2)) {
+                                p0 = ex2_approx(p0);
+                                p1 = ex2_approx(p1);
+                            }
+                            w4[e] = pack_bf16x2(p0, p1);
                             if (e & 1) { rs2 += p0; rs3 += p1; }
                             else { rs0 += p0; rs1 += p1; }
-                            w4[e] = pack_bf16x2(p0, p1);
                         }
                         if (TS) {   // P_j over S_j's first 64 columns: keys 2i | 2i+1 in column i of this thread's lane
                             wt[u * 4 + 0] = w4[0]; wt[u * 4 + 1] = w4[1]; wt[u * 4 + 2] = w4[2]; wt[u * 4 + 3] = w4[3];
@@ -536,15 +539,15 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
-    // VLB200_ATTN_FWD_VARIANT: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory
-    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 0; }();
+    // VLB200_ATTN_FWD_VARIANT: 0 = P through shared memory, 1 (default) = P in tensor memory, 2 = P and Q in tensor memory
+    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 1; }();
     cudaStream_t st = as_stream(stream);
     if (head_dim == 64) {
-        if (variant == 1) return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
+        if (variant == 0) return attn_tc::launch<64, 0>(tq, tk, tv, p, st);
         if (variant == 2) return attn_tc::launch<64, 2>(tq, tk, tv, p, st);
-        return attn_tc::launch<64, 0>(tq, tk, tv, p, st);
+        return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
     }
-    if (variant == 1) return attn_tc::launch<128, 1>(tq, tk, tv, p, st);
+    if (variant == 0) return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
     if (variant == 2) return attn_tc::launch<128, 2>(tq, tk, tv, p, st);
     switch (variant) {
 #define VLB_DBG_CASE(V) case V: return attn_tc::launch<128, V>(tq, tk, tv, p, st);
@@ -553,7 +556,7 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
 #undef VLB_DBG_CASE
         default: break;
     }
-    return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
+    return attn_tc::launch<128, 1>(tq, tk, tv, p, st);
 }
 
 extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
