@@ -126,6 +126,13 @@ __device__ __forceinline__ Item item_plan(const Params& p, int b, int xb) {
     it.per_rep = it.s[0].n + it.s[1].n + it.s[2].n;
     return it;
 }
+// tile u of one head repetition of an item -> (segment, tile index inside the sequence)
+__device__ __forceinline__ void item_tile_u(const Item& it, int u, Seg& sg, int& yt) {
+    if (u < it.s[0].n) { sg = it.s[0]; }
+    else if (u < it.s[0].n + it.s[1].n) { u -= it.s[0].n; sg = it.s[1]; }
+    else { u -= it.s[0].n + it.s[1].n; sg = it.s[2]; }
+    yt = sg.yb + u;
+}
 // tile t of an item -> (segment, tile index inside the sequence, head repetition)
 __device__ __forceinline__ void item_tile(const Item& it, int t, Seg& sg, int& yt, int& rep) {
     rep = t / it.per_rep;
@@ -427,10 +434,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 ++xitem;
             }
             VLB_PROF(0);   // item start
+            int tu = 0;   // tile index inside the current head repetition (no division per tile)
             for (int t = 0; t < n; ++t, ++tc) {
                 const uint32_t tb = tc & 1;
-                Seg sg; int yt, rep_unused;
-                item_tile(it, t, sg, yt, rep_unused);
+                Seg sg; int yt;
+                item_tile_u(it, tu, sg, yt);
+                if (++tu == it.per_rep) tu = 0;
                 const int y0 = yt * BY;
                 const int ylen = sg.len;             // valid streamed rows of this tile's sequence
                 const bool causal_t = sg.causal != 0;
@@ -600,22 +609,33 @@ static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMa
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
                                   long long lddo, float* __restrict__ delta, const int* __restrict__ row_starts, size_t rows,
                                   int B, int S, int H, int DH) {
+    // 16-byte loads: DH / 8 lanes cover one (row, head) -- 16 lanes at head_dim 128, 8 at 64 -- so a warp reduces 2 or 4 pairs
+    // per pass (4-byte loads, one pair per warp, reached 29 % of the HBM bandwidth: profiles/r1b_ncu_summary.md)
+    const int lanes = DH >> 3;                  // lanes per (row, head)
+    const int per_warp = 32 / lanes;
     const int warps_per_block = blockDim.x >> 5;
     const size_t total = rows * H;
     const int lane = threadIdx.x & 31;
-    for (size_t w = blockIdx.x * (size_t)warps_per_block + (threadIdx.x >> 5); w < total; w += (size_t)gridDim.x * warps_per_block) {
-        const int h = (int)(w % H);
-        const size_t row = w / H;  // b*S + t, or row_starts[b] + t
-        const __nv_bfloat16* op = o + row * ldo + (size_t)h * DH;
-        const __nv_bfloat16* dp = dout + row * lddo + (size_t)h * DH;
+    const int sub = lane / lanes, li = lane % lanes;
+    for (size_t w0 = (blockIdx.x * (size_t)warps_per_block + (threadIdx.x >> 5)) * per_warp; w0 < total;
+         w0 += (size_t)gridDim.x * warps_per_block * per_warp) {
+        const size_t w = w0 + sub;
+        const bool live = w < total;
+        const int h = live ? (int)(w % H) : 0;
+        const size_t row = live ? w / H : 0;  // b*S + t, or row_starts[b] + t
         float acc = 0.f;
-        for (int c = lane * 2; c < DH; c += 64) {
-            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + c));
-            const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + c));
-            acc += a.x * d.x + a.y * d.y;
+        if (live) {
+            const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + (size_t)h * DH + li * 8);
+            const uint4 d = *reinterpret_cast<const uint4*>(dout + row * lddo + (size_t)h * DH + li * 8);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 x = unpack_bf16x2(av[i]), y = unpack_bf16x2(dv[i]);
+                acc += x.x * y.x + x.y * y.y;
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
+        for (int off = lanes >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (live && li == 0) {
             size_t b = row / S, t = row % S;
             if (row_starts != nullptr) {
                 b = 0;
@@ -647,10 +667,12 @@ extern "C" int vlbdbg_attn_bwd_trace(long long* out3072) {
 extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta,
                                         const int* row_starts, int64_t total_rows, int B, int S, int H, int head_dim, void* stream) {
     VLB_REQUIRE(out && dout && delta, "attn_delta: null pointer");
+    VLB_REQUIRE(head_dim >= 8 && head_dim <= 256 && (head_dim & (head_dim - 1)) == 0 && ldo % 8 == 0 && lddo % 8 == 0,
+                "attn_delta: head_dim must be a power of two in [8, 256], row strides multiples of 8");
     VLB_REQUIRE(row_starts == nullptr || total_rows > 0, "attn_delta: row_starts needs total_rows");
     const size_t rows = row_starts ? (size_t)total_rows : (size_t)B * S;
-    const size_t nw = rows * H;
-    const int blocks = (int)std::min<size_t>((nw + 7) / 8, (size_t)vlb::num_sms() * 16);
+    const size_t nw = rows * H;   // (row, head) pairs; a warp takes 32 / (head_dim / 8) of them per pass
+    const int blocks = (int)std::min<size_t>((nw * (head_dim / 8) / 32 + 7) / 8, (size_t)vlb::num_sms() * 16);
     vlb::attn_bwd_tc::attn_delta_kernel<<<blocks, 256, 0, vlb::as_stream(stream)>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo,
                                                                   delta, row_starts, rows, B, S, H, head_dim);
     vlb::count_launch();
