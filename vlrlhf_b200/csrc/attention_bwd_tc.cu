@@ -728,7 +728,7 @@ extern "C" int vlb200_attn_bwd_tc_ctx(const void* q, int64_t ldq, const void* k,
 #define VLB_DBG_CASE(D) case D: rc = launch<128, 0, D>(xk, xv, yq, ydo, p, s); if (rc) return rc; \
             p.out1 = nullptr; p.ld1 = 0; p.out2 = (__nv_bfloat16*)dq; p.ld2 = lddq; p.n_work = p.n_xb * H * B; \
             return launch<128, 1, D>(xq, xdo, yk, yv, p, s);
-            VLB_DBG_CASE(1) VLB_DBG_CASE(2) VLB_DBG_CASE(3) VLB_DBG_CASE(4) VLB_DBG_CASE(7) VLB_DBG_CASE(8) VLB_DBG_CASE(9) VLB_DBG_CASE(16) VLB_DBG_CASE(32) VLB_DBG_CASE(36)
+            VLB_DBG_CASE(8) VLB_DBG_CASE(16) VLB_DBG_CASE(32)
 #undef VLB_DBG_CASE
             default: break;
         }

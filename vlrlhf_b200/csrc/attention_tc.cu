@@ -891,26 +891,26 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
-    // VLB200_ATTN_FWD_VARIANT: 0 = P through shared memory, 1 (default) = P in tensor memory, 2 = P and Q in tensor memory
-    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 1; }();
+    // VLB200_ATTN_FWD_VARIANT: 4 (default) = second-generation kernel (attn_fwd_tc2_kernel); first generation: 0 = P through
+    // shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory; 80 / 81 / 84 = variants 0 / 1 / 4 with per-phase cycle
+    // counters (tests/attn_phase_probe.py)
+    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 4; }();
     cudaStream_t st = as_stream(stream);
-    if (variant == 4) return head_dim == 64 ? attn_tc::launch2<64, 0>(tq, tk, tv, p, st) : attn_tc::launch2<128, 0>(tq, tk, tv, p, st);
-    if (variant == 84 && head_dim == 128) return attn_tc::launch2<128, 8>(tq, tk, tv, p, st);
     if (head_dim == 64) {
         if (variant == 0) return attn_tc::launch<64, 0>(tq, tk, tv, p, st);
+        if (variant == 1) return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
         if (variant == 2) return attn_tc::launch<64, 2>(tq, tk, tv, p, st);
-        return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
+        return attn_tc::launch2<64, 0>(tq, tk, tv, p, st);
     }
-    if (variant == 0) return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
-    if (variant == 2) return attn_tc::launch<128, 2>(tq, tk, tv, p, st);
     switch (variant) {
-#define VLB_DBG_CASE(V) case V: return attn_tc::launch<128, V>(tq, tk, tv, p, st);
-        VLB_DBG_CASE(10) VLB_DBG_CASE(12) VLB_DBG_CASE(20) VLB_DBG_CASE(22) VLB_DBG_CASE(30) VLB_DBG_CASE(32)
-        VLB_DBG_CASE(40) VLB_DBG_CASE(42) VLB_DBG_CASE(70) VLB_DBG_CASE(72) VLB_DBG_CASE(80) VLB_DBG_CASE(81) VLB_DBG_CASE(82)
-#undef VLB_DBG_CASE
-        default: break;
+        case 0: return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
+        case 1: return attn_tc::launch<128, 1>(tq, tk, tv, p, st);
+        case 2: return attn_tc::launch<128, 2>(tq, tk, tv, p, st);
+        case 80: return attn_tc::launch<128, 80>(tq, tk, tv, p, st);
+        case 81: return attn_tc::launch<128, 81>(tq, tk, tv, p, st);
+        case 84: return attn_tc::launch2<128, 8>(tq, tk, tv, p, st);
+        default: return attn_tc::launch2<128, 0>(tq, tk, tv, p, st);
     }
-    return attn_tc::launch<128, 1>(tq, tk, tv, p, st);
 }
 
 extern "C" int vlb200_attn_fwd_tc_varlen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
