@@ -89,6 +89,21 @@ def executed_flops(cfg, n_pairs, S, rows_lm, plan):
     return (lin + L * attn) * 4 + n_pairs * (vit + proj * 4) + lm * 4
 
 
+def plan_ratios(plan, n_pairs, S):
+    """(rows executed / padded rows, attention work executed / padded) of a row plan (packed or shared-prefix rows)."""
+    if not plan or "seq_lens" not in plan:
+        return 1.0, 1.0, 1.0
+    lens = plan["seq_lens"]
+    pre = plan.get("prefix_rows") or [0] * n_pairs
+    rows, attn = 0, 0.0
+    for i in range(n_pairs):
+        p_, c, r = pre[i], lens[i] - pre[i], lens[n_pairs + i] - pre[i]
+        rows += p_ + c + r
+        attn += p_ * p_ / 2 + c * c / 2 + c * p_ + r * r / 2 + r * p_
+    shared_pairs = sum(1 for x in pre if x > 0)
+    return rows / (2.0 * n_pairs * S), attn / (2.0 * n_pairs * S * S / 2), 1.0 - 0.5 * shared_pairs / n_pairs
+
+
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -402,12 +417,17 @@ def run_b200(args):
     attn_f = lambda: ops.attn_fwd_tc(q_, k_, v_, att, lse, full, nseq, S, H, KV, dh, True, sc)  # noqa: E731
     attn_b = lambda: ops.attn_bwd_tc(q_, k_, v_, att, datt, lse, delta, dqkv[:, :hd], dqkv[:, hd:hd + kvd], dqkv[:, hd + kvd:],  # noqa: E731
                                      full, nseq, S, H, KV, dh, True, sc)
-    for _ in range(40):
-        attn_f()
-    af_ms = timed(attn_f, 20)
-    for _ in range(15):
-        attn_b()
-    ab_ms = timed(attn_b, 20)
+    def timed_alone(fn, untimed, n):
+        """-> (ms per launch, median SM clock during the loop): `untimed` launches first (~0.1 s: the clock leaves the step's
+        power-capped level), then n timed ones with the nvidia-smi sampler running (200 ms period)."""
+        for _ in range(untimed):
+            fn()
+        smp = ClockSampler(local) if rank == 0 else None
+        ms = timed(fn, n)
+        clk = smp.stop() if smp else {}
+        return ms, clk.get("sm_mhz")
+    af_ms, af_mhz = timed_alone(attn_f, 300, 1500)
+    ab_ms, ab_mhz = timed_alone(attn_b, 120, 600)
     attn_fl = 4.0 * S * S * dh * H * nseq / 2
     del qkv, att, datt, dqkv
     # the two long-K GEMM shapes that carry as much of the step as the forward shape (VERDICT r1 weak #7): the gate|up input
@@ -494,10 +514,10 @@ def run_b200(args):
             "roofline_attention": [
                 {"bound": "tensor", "kernel": f"attn_fwd_tc_kernel<{dh}> (tcgen05 causal FlashAttention forward, one decoder layer)",
                  "achieved": attn_fl / af_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": attn_fl / af_ms / 1e9 / pk["bf16_tflops"],
-                 "ms": af_ms},
+                 "ms": af_ms, "sm_mhz": af_mhz},
                 {"bound": "tensor", "kernel": f"attn_delta_kernel + attn_bwd_tc_kernel<{dh},dKdV> + <{dh},dQ> (backward of the same layer)",
                  "achieved": 2.5 * attn_fl / ab_ms / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                 "frac": 2.5 * attn_fl / ab_ms / 1e9 / pk["bf16_tflops"], "ms": ab_ms}],
+                 "frac": 2.5 * attn_fl / ab_ms / 1e9 / pk["bf16_tflops"], "ms": ab_ms, "sm_mhz": ab_mhz}],
             "clocks": clocks,
         }
         if world == 1 and args.model == "7b" and not args.no_library_baseline:
@@ -598,6 +618,8 @@ def run_b200_qwen(args, cfg, world, rank, local):
     vit = cfg.v_layers * (P * 2 * (4 * w * w + 2 * w * cfg.v_mlp) + 4 * P * P * w) + P * 2 * cfg.patch_k * w
     resampler = P * 2 * (w * d + 2 * d * d) + 4 * cfg.n_queries * P * d + cfg.n_queries * 2 * 2 * d * d
     flops = PAIRS_PER_GPU * (2 * (per_seq + lora_seq * 3) + vit + resampler) + rows_lm * 2 * d * cfg.vocab * 3
+    rr, ra, _ = plan_ratios(plan, PAIRS_PER_GPU, S)   # shared-prefix / packed rows execute fewer FLOPs than the padded formulation
+    flops_exec = PAIRS_PER_GPU * (2 * (3 * lin_seq * rr + 4 * attn_seq * ra + lora_seq * 3 * rr) + vit + resampler) + rows_lm * 2 * d * cfg.vocab * 3
     pk, pk_src = peaks()
     if rank == 0:
         pairs = PAIRS_PER_GPU * world
@@ -611,10 +633,10 @@ def run_b200_qwen(args, cfg, world, rank, local):
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": text_len, "loss_type": args.loss_type,
                            "pack_sequences": eng.tc.pack_sequences, "share_prefix": eng.tc.share_prefix,
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
-                           "step_tflop_algorithmic": flops / 1e12,
-                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
-                           "step_tensor_util_note": "algorithmic FLOPs of the PADDED formulation / time / sustained cuBLAS peak; under "
-                                                    "share_prefix the step executes fewer (the pair's common prefix rows run once)"},
+                           "step_tflop_algorithmic": flops / 1e12, "step_tflop_executed": flops_exec / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops_exec / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "step_tensor_util_note": "EXECUTED FLOPs / time / sustained cuBLAS peak (shared-prefix rows execute fewer FLOPs "
+                                                    "than the padded formulation, step_tflop_algorithmic)"},
                 "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}
@@ -743,6 +765,9 @@ def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, l
     vit = cfg.v_used_layers * (Sv * 2 * (4 * dv * dv + 2 * dv * cfg.v_ff) + 4 * Sv * Sv * dv) + P * 2 * cfg.patch_k * dv
     proj = P * 2 * (dv * d + d * d) * 2
     flops = PAIRS_PER_GPU * (2 * per_seq + vit + proj) + rows_lm * 2 * d * cfg.vocab * 3
+    plan = eng.host_row_plan(ids_h, am_h)
+    rr, ra, ri = plan_ratios(plan, PAIRS_PER_GPU, S)   # ri: image rows (partial LoRA) executed / padded
+    flops_exec = PAIRS_PER_GPU * (2 * (3 * (lin_seq * rr + plora_seq * ri) + 4 * attn_seq * ra + 3 * lora_seq * rr) + vit + proj) + rows_lm * 2 * d * cfg.vocab * 3
     pk, pk_src = peaks()
     if rank == 0:
         pairs = PAIRS_PER_GPU * world
@@ -757,10 +782,10 @@ def _finish_xc2(args, cfg, eng, world, rank, ms_dev, ms_e2e, launches, clocks, l
                            "pairs_per_gpu": PAIRS_PER_GPU, "text_len": text_len, "merged_len": S, "loss_type": args.loss_type,
                            "pack_sequences": eng.tc.pack_sequences, "share_prefix": eng.tc.share_prefix,
                            "parallelism": f"dp{world}", "optimizer": "AdamW on the adapters only (fp32 master+moments)",
-                           "step_tflop_algorithmic": flops / 1e12,
-                           "step_tensor_util_of_sustained_peak": flops / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
-                           "step_tensor_util_note": "algorithmic FLOPs of the PADDED formulation / time / sustained cuBLAS peak; under "
-                                                    "share_prefix the step executes fewer (the pair's common prefix rows run once)"},
+                           "step_tflop_algorithmic": flops / 1e12, "step_tflop_executed": flops_exec / 1e12,
+                           "step_tensor_util_of_sustained_peak": flops_exec / (ms_dev / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "step_tensor_util_note": "EXECUTED FLOPs / time / sustained cuBLAS peak (shared-prefix rows execute fewer FLOPs "
+                                                    "than the padded formulation, step_tflop_algorithmic)"},
                 "e2e": {"value": (pairs / (ms_e2e / 1e3) if ms_e2e else None), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 11 * 4,
                         "ms_per_step": ms_e2e, "last_metrics": last},
                 "gpu_launches": launches, "clocks": clocks}

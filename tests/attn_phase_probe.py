@@ -50,18 +50,20 @@ def run(fn, reader, width, names, reps=5):
         items, tiles = vals[8], vals[9]
         if tiles == 0:
             continue
-        extra = [buf[base + i] / reps for i in (10, 11)]
+        extra = [buf[base + i] / reps for i in (10, 11, 12, 13, 14, 15)]
         tot = sum(vals[:8]) + sum(extra)
         print(f"  [{names[base // 16]}] {ms:.3f} ms/launch-set; per CTA: {items / 148:.1f} items, {tiles / 148:.1f} tiles, {tot / 148:.0f} cycles in the loop")
         if any(extra):
             print(f"      item: wait for S of the first tile {extra[0] / items:8.0f} cycles per item; wait for the last PV {extra[1] / items:8.0f} cycles per item")
+            if extra[2] or extra[3]:
+                print(f"      item: epilogue: row-sum exchange + set-up {extra[2] / items:8.0f}; O chunks: TMEM load {extra[4] / items:6.0f}, scale/pack/staging {extra[5] / items:6.0f}, staging load + global store {extra[3] / items:6.0f} cycles per item")
         for i, nm in enumerate(names[-1]):
             if vals[i]:
                 per = vals[i] / (items if nm.startswith("item:") else tiles)
                 print(f"      {nm:52s} {per:8.0f} cycles per {'item' if nm.startswith('item:') else 'tile'}   ({100 * vals[i] / tot:4.1f} %)")
 
 
-if os.environ.get("VLB200_ATTN_FWD_VARIANT", "0") in ("80", "81", "82", "84"):
+if os.environ.get("VLB200_ATTN_FWD_VARIANT", "0") in ("80", "81", "82", "84", "85", "125"):
     run(fwd, lib.vlbdbg_attn_fwd_profile, 16, ["forward", ["item: start (plan, Q copy)", "wait for S", "TMEM -> registers (S)", "mask + row max",
                                                           "exp2, row sum, pack, P store issue", "wait for the previous PV",
                                                           "O correction, store completion, fences, publish", "item: epilogue"]])

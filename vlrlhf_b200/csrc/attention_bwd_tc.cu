@@ -268,11 +268,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                     // statistics of the tile's 64 queries -> the stage's slot; the second arrival on y_full publishes them (the
                     // elementwise warps read them as broadcast float4s: one warp loads what eight warps used to load redundantly,
                     // 840 cycles per tile in profiles/r2k_attn.log)
-                    float* slot = sStat + st * 128;
+                    const uint32_t slot_a = smem_u32(sStat + st * 128);
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        slot[hh * 32 + lane_idx] = sl_[hh] * LOG2E_F;
-                        slot[64 + hh * 32 + lane_idx] = sd_[hh];
+                        sts_f32(slot_a + ((hh * 32 + lane_idx) << 2), sl_[hh] * LOG2E_F);
+                        sts_f32(slot_a + ((64 + hh * 32 + lane_idx) << 2), sd_[hh]);
                     }
                     __syncwarp();
                     if (lane_idx == 0) mbar_arrive(&y_full[st]);
@@ -413,7 +413,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 // operand of the score MMAs).  half 0 copies Q, half 1 copies dO.  Every MMA of the previous item has retired (its
                 // epilogue waited for the last accumulate).
                 mbar_wait(x_full, xitem & 1, 70);
-                const uint8_t* sx = half == 0 ? sX1 : sX2;
+                const uint32_t sx_a = smem_u32(half == 0 ? sX1 : sX2);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
 #pragma unroll
@@ -421,7 +421,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                         uint32_t qw[16];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(sx + c * XCH + r * 128 + (((hh * 4 + u) ^ (r & 7)) << 4));
+                            const uint4 v = lds128(sx_a + c * XCH + r * 128 + (((hh * 4 + u) ^ (r & 7)) << 4));
                             qw[u * 4 + 0] = v.x; qw[u * 4 + 1] = v.y; qw[u * 4 + 2] = v.z; qw[u * 4 + 3] = v.w;
                         }
                         tmem_st_32x32_x16(tmem_base + lane_addr + (half == 0 ? TM_X1 : TM_X2) + c * 32 + hh * 16, qw);
@@ -530,7 +530,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             // block of the warp instead and leaves as 64-byte row segments, 8 rows per store instruction.
             const int row_lim = p.row_starts ? kv_len : p.S;   // packed rows: the tile may run into the next sequence
             const long long grow0 = (p.row_starts ? (long long)p.row_starts[b] : (long long)b * p.S) + x0 + quad * 32;
-            uint8_t* stg = sOut + (warp_idx - 2) * 2048;
+            const uint32_t stg_a = smem_u32(sOut + (warp_idx - 2) * 2048);
 #pragma unroll
             for (int a = (MODE == 0 ? 0 : 1); a < 2; ++a) {
                 __nv_bfloat16* dst0 = (a == 0 ? p.out1 : p.out2) + (long long)hx * DH;
@@ -554,13 +554,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                         v.y = pack_bf16x2(__uint_as_float(acc[u * 8 + 2]) * osc, __uint_as_float(acc[u * 8 + 3]) * osc);
                         v.z = pack_bf16x2(__uint_as_float(acc[u * 8 + 4]) * osc, __uint_as_float(acc[u * 8 + 5]) * osc);
                         v.w = pack_bf16x2(__uint_as_float(acc[u * 8 + 6]) * osc, __uint_as_float(acc[u * 8 + 7]) * osc);
-                        *reinterpret_cast<uint4*>(stg + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4)) = v;
+                        sts128(stg_a + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4), v);
                     }
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + (lane_idx >> 2), u = lane_idx & 3;
-                        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+                        const uint4 v = lds128(stg_a + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
                         if (x0 + quad * 32 + rr < row_lim)
                             *reinterpret_cast<uint4*>(dst0 + (grow0 + rr) * ldd + c * 32 + u * 8) = v;
                     }

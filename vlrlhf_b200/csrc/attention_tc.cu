@@ -97,7 +97,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// (a polynomial 2^x on the FMA pipe for every fourth element -- Cody-Waite reduction + degree-3 minimax, 7.5e-5 relative --
+// 2^x on the FMA / ALU pipes (no MUFU): n = round(x) by the 1.5 * 2^23 trick, 2^f on [-0.5, 0.5] by a degree-3 minimax
+// polynomial (7.5e-5 relative: far inside bf16's 4e-3), n added to the exponent field.  x <= ~100; anything below -126
+// (incl. -inf) gives ~1e-38.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.f);
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(0.0551716685f, f, 0.2426111251f);
+    p = fmaf(p, f, 0.6932609677f);
+    p = fmaf(p, f, 0.9999280572f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// (in the one-softmax-warp-per-scheduler kernels the polynomial for every fourth element -- Cody-Waite reduction + degree-3 minimax, 7.5e-5 relative --
 // was measured SLOWER, 1390 vs 1202 cycles per tile for the exponential phase: one softmax warp per scheduler is bound by
 // instruction issue, not by the MUFU: profiles/r2s_attn.log)
 
@@ -655,7 +667,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         const int r = quad * 32 + lane_idx;  // row inside the Q tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sl2 = p.scale * LOG2E_F;
-        uint8_t* stg = sOut + quad * 4096;
+        const uint32_t stg_a = smem_u32(sOut + quad * 4096);
         uint32_t g = 0;
         unsigned long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         long long tp = clock64();
@@ -786,7 +798,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                         v.y = pack_bf16x2(__uint_as_float(orow[hh][u * 8 + 2]) * inv, __uint_as_float(orow[hh][u * 8 + 3]) * inv);
                         v.z = pack_bf16x2(__uint_as_float(orow[hh][u * 8 + 4]) * inv, __uint_as_float(orow[hh][u * 8 + 5]) * inv);
                         v.w = pack_bf16x2(__uint_as_float(orow[hh][u * 8 + 6]) * inv, __uint_as_float(orow[hh][u * 8 + 7]) * inv);
-                        *reinterpret_cast<uint4*>(stg + hh * 2048 + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4)) = v;
+                        sts128(stg_a + hh * 2048 + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4), v);
                     }
                 }
                 __syncwarp();
@@ -795,7 +807,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + (lane_idx >> 2), u = lane_idx & 3;
-                        const uint4 v = *reinterpret_cast<const uint4*>(stg + hh * 2048 + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+                        const uint4 v = lds128(stg_a + hh * 2048 + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
                         if (qb * BM + quad * 32 + rr < row_lim)
                             *reinterpret_cast<uint4*>(obase + (long long)rr * p.ldo + c2 * 64 + hh * 32 + u * 8) = v;
                     }
@@ -832,6 +844,375 @@ static int launch2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     }
     const int grid = std::min(p.n_work, num_sms());
     kern<<<grid, NTHREADS2, smem_bytes, s>>>(tq, tk, tv, p);
+    count_launch();
+    VLB_LAUNCH_CHECK();
+    return VLB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Third-generation forward (VLB200_ATTN_FWD_VARIANT=5): the second generation with EIGHT softmax warps -- two per TMEM lane
+// quadrant, each thread owning 64 of its row's 128 score columns.  One softmax warp per scheduler issues 452 instructions per
+// tile at 2.6 cycles each (profiles/r2s_attn.log); two warps per scheduler interleave.  The pair exchanges its partial row
+// maxima through shared memory behind a 64-thread named barrier (so both keep the SAME running max and take the same lazy
+// rescale decisions), keeps partial row sums that meet only in the epilogue, and splits the O columns for the (rare)
+// correction and for the epilogue.
+// (second generation, for reference:) VLB200_ATTN_FWD_VARIANT=4.  Same arithmetic as VAR 1 (P in tensor memory, TS-mode PV); what
+// changes is the plumbing around the softmax warps, whose serial per-tile chain bounds the kernel (profiles/r2s_attn.log:
+// the per-item epilogue cost 4 000 cycles and the pipeline refill ~1 600 per query tile):
+//   * K and V tiles travel through SEPARATE two-slot rings (a K slot is free as soon as S_j has retired, long before V_j's):
+//     128 KB instead of 192 KB, which pays for a second Q buffer and an epilogue staging block;
+//   * Q is double buffered and the tile counter runs ACROSS query tiles: the S warp issues S_0 / S_1 of the next query tile
+//     while the softmax warps are still in the epilogue of the previous one;
+//   * S = Q K^T and O += P V are issued by two converged warps in a fixed order (one elected lane each; attention_bwd_tc.cu);
+//     an S buffer is recycled when the PV that read its P has COMPLETED (pv_done[buffer]);
+//   * the epilogue leaves through a swizzled 2 KB staging block per warp as 64-byte row segments (8 rows per store
+//     instruction instead of 32 scattered 16-byte pieces).
+constexpr int NTHREADS3 = 352;  // TMA producer, S-MMA warp, 8 softmax warps, PV-MMA warp
+
+template <int DH, int DBG>
+__global__ void __launch_bounds__(NTHREADS3, 1)
+attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                    const __grid_constant__ CUtensorMap tma_v, const Params p) {
+    constexpr int NCH = DH / 64;
+    constexpr int CHUNK_BYTES = 128 * 128;
+    constexpr int T_BYTES = NCH * CHUNK_BYTES;   // one Q, K or V tile
+    constexpr uint32_t TMEM_COLS = 512;
+    // S buffers at columns 0 / 128, O at 256, bf16 P buffers (two keys per column) at 384 / 448.  P has its OWN columns: with
+    // P_g written over S_g, S_{g+2} had to wait for the COMPLETION of PV_g (another warp issues it) and that chain -- publish,
+    // PV warp wake-up, 8 MMAs, commit, S warp wake-up, 8 MMAs -- was as long as a softmax tile (200 cycles of waiting per tile)
+    constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 384;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                          // [2]
+    uint8_t* sK = sQ + 2 * T_BYTES;              // [NKS]
+    uint8_t* sV = sK + NKS * T_BYTES;            // [NVS]
+    uint8_t* sOut = sV + NVS * T_BYTES;          // [8 warps][32 rows][64 B]
+    float* sMx = reinterpret_cast<float*>(sOut + 8 * 2048);   // [2 tile parities][2 halves][128 rows]: partial row maxima
+    float* sL = sMx + 2 * 2 * 128;                            // [2 halves][128 rows]: partial row sums (epilogue)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 2 * 128);
+    uint64_t* q_full = bars;                     // [2]
+    uint64_t* q_empty = q_full + 2;              // [2]
+    uint64_t* k_full = q_empty + 2;              // [NKS]
+    uint64_t* k_empty = k_full + NKS;            // [NKS]
+    uint64_t* v_full = k_empty + NKS;            // [NVS]
+    uint64_t* v_empty = v_full + NVS;            // [NVS]
+    uint64_t* s_full = v_empty + NVS;            // [2]
+    uint64_t* s_empty = s_full + 2;              // [2]
+    uint64_t* p_full = s_empty + 2;              // [2]
+    uint64_t* pv_done = p_full + 2;              // [2]
+    uint64_t* o_free = pv_done + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_free + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane_idx = threadIdx.x & 31;
+    if (warp_idx == 0 && lane_idx == 0) {
+        prefetch_tensormap(&tma_q); prefetch_tensormap(&tma_k); prefetch_tensormap(&tma_v);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); mbar_init(&p_full[i], 8);
+            mbar_init(&pv_done[i], 1);
+        }
+        for (int i = 0; i < NKS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < NVS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(o_free, 8);
+        fence_barrier_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_base_smem, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp_idx == 0) {
+        // ===================== TMA producer =====================
+        if (lane_idx == 0) {
+            uint32_t item = 0, g = 0;  // g = global KV-tile counter
+            for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+                int b, h, qb;
+                work_coords(p, w, b, h, qb);
+                const KvPlan plan = kv_plan(p, b, qb);
+                if (plan.skip) continue;
+                const int kvh = h / (p.H / p.KVH);
+                const int n_tiles = plan.n_ctx + plan.n_self;
+                const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
+                const uint32_t qs = item & 1;
+                mbar_wait(&q_empty[qs], ((item >> 1) & 1) ^ 1, 10);
+                mbar_arrive_expect_tx(&q_full[qs], T_BYTES);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_q, &q_full[qs], sQ + qs * T_BYTES + c * CHUNK_BYTES, h * DH + c * 64, row0 + qb * BM);
+                for (int j = 0; j < n_tiles; ++j, ++g) {
+                    const int krow = j < plan.n_ctx ? plan.ctx_row0 + j * BN : row0 + (j - plan.n_ctx) * BN;
+                    const uint32_t ks = g % NKS, vs = g % NVS;
+                    mbar_wait(&k_empty[ks], ((g / NKS) & 1) ^ 1, 20);   // S of the tile two back has retired
+                    mbar_arrive_expect_tx(&k_full[ks], T_BYTES);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_k, &k_full[ks], sK + ks * T_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
+                    mbar_wait(&v_empty[vs], ((g / NVS) & 1) ^ 1, 21);   // PV of the tile two back has retired
+                    mbar_arrive_expect_tx(&v_full[vs], T_BYTES);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_v, &v_full[vs], sV + vs * T_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
+                }
+                ++item;
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== S = Q K^T (whole warp converged; one elected lane issues) =====================
+        constexpr uint32_t idesc_s = make_idesc_bf16_f32(BM, BN, false, false);
+        uint32_t item = 0, g = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, h, qb;
+            work_coords(p, w, b, h, qb);
+            const KvPlan plan = kv_plan(p, b, qb);
+            if (__shfl_sync(0xffffffffu, (int)plan.skip, 0)) continue;
+            const int n_tiles = __shfl_sync(0xffffffffu, plan.n_ctx + plan.n_self, 0);
+            const uint32_t qs = item & 1;
+            mbar_wait(&q_full[qs], (item >> 1) & 1, 30);
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                const uint32_t sb = g & 1, ks = g % NKS;
+                mbar_wait(&k_full[ks], (g / NKS) & 1, 31);
+                mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 32);   // the softmax warps have S_{g-2} in registers
+                __syncwarp();
+                tcgen05_fence_after();
+                uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + qs * T_BYTES), 1024, 0);
+                uint64_t dk = make_smem_desc_sw128(smem_u32(sK + ks * T_BYTES), 1024, 0);
+                asm volatile("" : "+l"(dq), "+l"(dk));   // opaque bases: per-k descriptors by immediate adds on the uniform datapath
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < DH / 16; ++k) {
+                        const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
+                        umma_f16_ss(tmem_base + TM_S + sb * BN, dq + off, dk + off, idesc_s, k != 0);
+                    }
+                    umma_commit(&s_full[sb]);
+                    umma_commit(&k_empty[ks]);
+                    if (j == n_tiles - 1) umma_commit(&q_empty[qs]);  // Q tile free once the last S retires
+                }
+                __syncwarp();
+            }
+            ++item;
+        }
+    } else if (warp_idx == 10) {
+        // ===================== O += P V (whole warp converged; one elected lane issues) =====================
+        constexpr uint32_t idesc_o = make_idesc_bf16_f32(BM, DH, false, true);  // B = V is MN-major
+        uint32_t item = 0, g = 0;
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, h, qb;
+            work_coords(p, w, b, h, qb);
+            const KvPlan plan = kv_plan(p, b, qb);
+            if (__shfl_sync(0xffffffffu, (int)plan.skip, 0)) continue;
+            const int n_tiles = __shfl_sync(0xffffffffu, plan.n_ctx + plan.n_self, 0);
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                const uint32_t sb = g & 1, vs = g % NVS;
+                mbar_wait(&p_full[sb], (g >> 1) & 1, 40);
+                mbar_wait(&v_full[vs], (g / NVS) & 1, 41);
+                if (j == 0) mbar_wait(o_free, (item & 1) ^ 1, 42);   // the epilogue of the previous query tile has read O
+                __syncwarp();
+                tcgen05_fence_after();
+                uint64_t dvv = make_smem_desc_sw128(smem_u32(sV + vs * T_BYTES), 1024, CHUNK_BYTES);
+                asm volatile("" : "+l"(dvv));
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < BN / 16; ++k)
+                        umma_f16_ts(tmem_base + TM_O, tmem_base + TM_P + sb * 64 + k * 8, dvv + (uint64_t)(k * 128), idesc_o,
+                                    (j != 0 || k != 0) ? 1u : 0u);
+                    umma_commit(&pv_done[sb]);
+                    umma_commit(&v_empty[vs]);
+                }
+                __syncwarp();
+            }
+            ++item;
+        }
+    } else {
+        // ===================== softmax + epilogue (8 warps: row = TMEM lane, two warps split the 128 score columns) ==========
+        const int quad = warp_idx & 3;
+        const int half = (warp_idx - 2) >> 2;   // 0: score columns [0, 64), 1: [64, 128)
+        const int r = quad * 32 + lane_idx;     // row inside the Q tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float sl2 = p.scale * LOG2E_F;
+        const uint32_t stg_a = smem_u32(sOut + (warp_idx - 2) * 2048);
+        constexpr int OC = DH / 2;              // O columns of this warp: [half * OC, half * OC + OC)
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+        const uint32_t smx_a = smem_u32(sMx), sl_a = smem_u32(sL);
+        uint32_t g = 0;
+        unsigned long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tp = clock64();
+        for (int w = blockIdx.x; w < p.n_work; w += gridDim.x) {
+            int b, h, qb;
+            work_coords(p, w, b, h, qb);
+            const KvPlan plan = kv_plan(p, b, qb);
+            if (plan.skip) continue;
+            const int n_tiles = plan.n_ctx + plan.n_self;
+            if (DBG & 8) { prof[8] += 1; prof[9] += n_tiles; }
+            int kv_len = p.seqlens ? p.seqlens[b] : p.S;
+            kv_len = max(kv_len, 1);
+            const int qrow = qb * BM + r;
+            float m_run = -INFINITY, l_part = 0.f;   // l_part: this warp's 64 columns only
+            VLB_PROF(0);   // item start
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                const uint32_t sb = g & 1;
+                mbar_wait(&s_full[sb], (g >> 1) & 1, 80 + sb);
+                tcgen05_fence_after();
+                if ((DBG & 8) && j == 0) { const long long t_ = clock64(); prof[10] += (unsigned long long)(t_ - tp); tp = t_; }   // first tile of a query tile
+                VLB_PROF(1);   // wait for S
+                uint32_t sr[2][32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) tmem_ld_32x32(tmem_base + lane_addr + TM_S + sb * BN + half * 64 + c * 32, sr[c]);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(&s_empty[sb]);   // this warp's half of S_g is in registers
+                VLB_PROF(2);   // TMEM -> registers
+                // context tiles: every key below ctx_len is visible; own tiles: keys below kv_len, up to the causal diagonal
+                const bool is_ctx = j < plan.n_ctx;
+                const int k0 = (is_ctx ? j : j - plan.n_ctx) * BN;
+                const int vlim = (is_ctx ? plan.ctx_len : kv_len) - k0;              // keys [0, vlim) of the tile exist
+                const int clim = (p.causal && !is_ctx) ? qrow - k0 : BN;             // keys [0, clim] of the tile are not in the future
+                const bool need_mask = vlim < BN || (p.causal && !is_ctx && k0 + BN > qb * BM);
+                if (need_mask) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kk = half * 64 + c * 32 + i;
+                            if (kk >= vlim || kk > clim) sr[c][i] = 0xff800000u;  // -inf
+                        }
+                    }
+                }
+                float mxp[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    mxp[c] = fmaxf(__uint_as_float(sr[c][0]), __uint_as_float(sr[c][1]));
+#pragma unroll
+                    for (int i = 2; i < 32; i += 2) mxp[c] = fmaxf(fmaxf(mxp[c], __uint_as_float(sr[c][i])), __uint_as_float(sr[c][i + 1]));
+                }
+                // the row maximum over all 128 columns: partial maxima meet through shared memory (slot by tile parity: the
+                // partner reads slot g before it can pass the barrier of tile g + 1, so tile g + 2 may overwrite it)
+                float mx = fmaxf(mxp[0], mxp[1]);
+                sts_f32(smx_a + (((sb * 2 + half) * 128 + r) << 2), mx);
+                pair_sync();
+                mx = fmaxf(mx, lds_f32(smx_a + (((sb * 2 + (half ^ 1)) * 128 + r) << 2)));
+                mx *= sl2;  // scale > 0: max commutes with the scaling (log2 domain from here on)
+                // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^RESCALE_THRESHOLD
+                float corr = 1.f;
+                bool need = false;
+                if (mx > m_run + RESCALE_THRESHOLD || m_run == -INFINITY) {
+                    const float m_new = mx == -INFINITY ? m_run : mx;
+                    if (m_run != -INFINITY && m_new != m_run) { corr = ex2_approx(m_run - m_new); need = true; }
+                    m_run = m_new;
+                }
+                const float neg_m = m_run == -INFINITY ? 0.f : -m_run;
+                VLB_PROF(3);   // mask + row max
+                // P = exp2(s*c - m) (bf16) into P buffer g & 1, this warp's 32 columns (keys 2i | 2i+1 of its half in column i)
+                float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t wt[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * u]), sl2, neg_m));
+                        const float x1 = fmaf(__uint_as_float(sr[c][2 * u + 1]), sl2, neg_m);
+                        // DBG bit 4 (variant 45): every fourth exponential on the FMA pipe -- with two softmax warps per scheduler
+                        // the exponential phase is MUFU-bound (1095 cycles against a floor of 1024: profiles/r2aa_attn.log)
+                        const float p1 = ((DBG & 4) && (u & 1)) ? ex2_poly(x1) : ex2_approx(x1);
+                        wt[u] = pack_bf16x2(p0, p1);
+                        if (u & 1) { rs2 += p0; rs3 += p1; }
+                        else { rs0 += p0; rs1 += p1; }
+                    }
+                    tmem_st_32x32_x16(tmem_base + lane_addr + TM_P + sb * 64 + half * 32 + c * 16, wt);
+                }
+                l_part = l_part * corr + ((rs0 + rs1) + (rs2 + rs3));
+                VLB_PROF(4);   // exponentials, row sum, pack, P store issue
+                // the (rare) O correction needs the previous PV retired; waiting for it every tile also keeps the pv_done phase
+                // bookkeeping exact (a waiter never falls two phases behind)
+                if (j > 0) mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 90);
+                VLB_PROF(5);   // wait for the previous PV
+                if (j > 0 && __any_sync(0xffffffffu, need)) {  // warp-uniform (and equal in both warps of the pair: same rows, same max)
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int c = 0; c < OC / 32; ++c) {
+                        uint32_t orow[32];
+                        tmem_ld_32x32(tmem_base + lane_addr + TM_O + half * OC + c * 32, orow);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * corr);
+                        tmem_st_32x32(tmem_base + lane_addr + TM_O + half * OC + c * 32, orow);
+                    }
+                }
+                tmem_st_wait_all();   // P_g (and the corrected O) are in tensor memory
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane_idx == 0) mbar_arrive(&p_full[sb]);
+                VLB_PROF(6);   // O correction (rare), store completion, fences, publish
+            }
+            // ---- epilogue: wait for the last PV, normalise, store this warp's O columns (through its staging block) and LSE
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 95);
+            tcgen05_fence_after();
+            if (DBG & 8) { const long long t_ = clock64(); prof[11] += (unsigned long long)(t_ - tp); tp = t_; }   // wait for the last PV
+            sts_f32(sl_a + ((half * 128 + r) << 2), l_part);
+            pair_sync();
+            const float l_run = l_part + lds_f32(sl_a + (((half ^ 1) * 128 + r) << 2));
+            pair_sync();   // (the partner has read this item's value before the next item overwrites it)
+            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            // packed rows: the tile may run into the next sequence's rows, so only the attended prefix is stored
+            const int row_lim = (p.row_starts && p.seqlens) ? min(p.seqlens[b], p.S) : p.S;
+            const long long row0 = p.row_starts ? p.row_starts[b] : (long long)b * p.S;
+            __nv_bfloat16* obase = p.o + (row0 + qb * BM + quad * 32) * p.ldo + (long long)h * DH + half * OC;
+            if (DBG & 8) { const long long t_ = clock64(); prof[12] += (unsigned long long)(t_ - tp); tp = t_; }   // row-sum exchange, 1/l, addresses
+#pragma unroll
+            for (int c = 0; c < OC / 32; ++c) {
+                uint32_t orow[32];
+                tmem_ld_32x32(tmem_base + lane_addr + TM_O + half * OC + c * 32, orow);
+                tmem_ld_wait();
+                if (DBG & 8) { const long long t_ = clock64(); prof[14] += (unsigned long long)(t_ - tp); tp = t_; }   // O chunk: TMEM load
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 v;
+                    v.x = pack_bf16x2(__uint_as_float(orow[u * 8 + 0]) * inv, __uint_as_float(orow[u * 8 + 1]) * inv);
+                    v.y = pack_bf16x2(__uint_as_float(orow[u * 8 + 2]) * inv, __uint_as_float(orow[u * 8 + 3]) * inv);
+                    v.z = pack_bf16x2(__uint_as_float(orow[u * 8 + 4]) * inv, __uint_as_float(orow[u * 8 + 5]) * inv);
+                    v.w = pack_bf16x2(__uint_as_float(orow[u * 8 + 6]) * inv, __uint_as_float(orow[u * 8 + 7]) * inv);
+                    sts128(stg_a + lane_idx * 64 + ((u ^ ((lane_idx >> 1) & 3)) << 4), v);
+                }
+                __syncwarp();
+                if (DBG & 8) { const long long t_ = clock64(); prof[15] += (unsigned long long)(t_ - tp); tp = t_; }   // O chunk: scale, pack, staging store
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = i * 8 + (lane_idx >> 2), u = lane_idx & 3;
+                    const uint4 v = lds128(stg_a + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+                    if (qb * BM + quad * 32 + rr < row_lim) *reinterpret_cast<uint4*>(obase + (long long)rr * p.ldo + c * 32 + u * 8) = v;
+                }
+                __syncwarp();
+                if (DBG & 8) { const long long t_ = clock64(); prof[13] += (unsigned long long)(t_ - tp); tp = t_; }   // O chunk: staging load, global store
+            }
+            if (half == 0 && qrow < row_lim && p.lse)
+                p.lse[((long long)b * p.H + h) * p.S + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * LN2_F : -INFINITY;
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane_idx == 0) mbar_arrive(o_free);
+            VLB_PROF(7);   // epilogue
+        }
+        if ((DBG & 8) && threadIdx.x == 64) {
+            for (int i = 0; i < 16; ++i) atomicAdd(&g_fwd_prof[i], prof[i]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int DH, int DBG>
+static int launch3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t s) {
+    constexpr int t_bytes = (DH / 64) * 128 * 128;
+    constexpr int smem_bytes = (2 + NKS + NVS) * t_bytes + 8 * 2048 + (2 * 2 * 128 + 2 * 128) * 4 + 256 + 1024;
+    auto kern = attn_fwd_tc3_kernel<DH, DBG>;
+    static bool configured = false;
+    if (!configured) {
+        VLB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int grid = std::min(p.n_work, num_sms());
+    kern<<<grid, NTHREADS3, smem_bytes, s>>>(tq, tk, tv, p);
     count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
@@ -891,16 +1272,18 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     p.B = B; p.S = S; p.H = H; p.KVH = KVH; p.causal = causal; p.scale = scale;
     p.n_qb = (S + attn_tc::BM - 1) / attn_tc::BM;
     p.n_work = p.n_qb * H * B;
-    // VLB200_ATTN_FWD_VARIANT: 4 (default) = second-generation kernel (attn_fwd_tc2_kernel); first generation: 0 = P through
-    // shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory; 80 / 81 / 84 = variants 0 / 1 / 4 with per-phase cycle
-    // counters (tests/attn_phase_probe.py)
-    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 4; }();
+    // VLB200_ATTN_FWD_VARIANT: 5 (default) = third-generation kernel (attn_fwd_tc3_kernel, eight softmax warps), 4 = second
+    // generation (attn_fwd_tc2_kernel, four); first generation: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q
+    // in tensor memory; 45 = variant 5 with every fourth exponential as a polynomial; 80 / 81 / 84 / 85 / 125 = variants
+    // 0 / 1 / 4 / 5 / 45 with per-phase cycle counters (tests/attn_phase_probe.py)
+    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 5; }();
     cudaStream_t st = as_stream(stream);
     if (head_dim == 64) {
         if (variant == 0) return attn_tc::launch<64, 0>(tq, tk, tv, p, st);
         if (variant == 1) return attn_tc::launch<64, 1>(tq, tk, tv, p, st);
         if (variant == 2) return attn_tc::launch<64, 2>(tq, tk, tv, p, st);
-        return attn_tc::launch2<64, 0>(tq, tk, tv, p, st);
+        if (variant == 4) return attn_tc::launch2<64, 0>(tq, tk, tv, p, st);
+        return attn_tc::launch3<64, 0>(tq, tk, tv, p, st);
     }
     switch (variant) {
         case 0: return attn_tc::launch<128, 0>(tq, tk, tv, p, st);
@@ -909,7 +1292,11 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
         case 80: return attn_tc::launch<128, 80>(tq, tk, tv, p, st);
         case 81: return attn_tc::launch<128, 81>(tq, tk, tv, p, st);
         case 84: return attn_tc::launch2<128, 8>(tq, tk, tv, p, st);
-        default: return attn_tc::launch2<128, 0>(tq, tk, tv, p, st);
+        case 4: return attn_tc::launch2<128, 0>(tq, tk, tv, p, st);
+        case 85: return attn_tc::launch3<128, 8>(tq, tk, tv, p, st);
+        case 45: return attn_tc::launch3<128, 4>(tq, tk, tv, p, st);
+        case 125: return attn_tc::launch3<128, 12>(tq, tk, tv, p, st);
+        default: return attn_tc::launch3<128, 0>(tq, tk, tv, p, st);
     }
 }
 

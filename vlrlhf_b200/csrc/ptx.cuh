@@ -61,6 +61,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     }
 }
 
+// ---- explicit shared-memory accesses ---------------------------------------------------------------------------------
+// Through a C++ pointer into the dynamic shared-memory block the compiler emits GENERIC loads / stores (LD.E / ST.E): slower,
+// and a generic load cannot be hoisted over a global store it might alias -- the attention epilogues ran
+// load, store, load, store ... at ~130 cycles per pair (profiles/r2ac: 1152 of 2300 cycles per query tile).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // ---- TMA -------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
