@@ -36,6 +36,10 @@ int vlb200_abi_version(void);
 const char* vlb200_last_error(void);
 /* number of kernels this library has launched since load (bench.py's "gpu_launches") */
 uint64_t vlb200_launch_count(void);
+/* Which generation of the attention forward kernel vlb200_attn_fwd_tc* launches: 5 (default; environment VLB200_ATTN_FWD_VARIANT)
+ * = eight softmax warps, 4 = four, 1 / 0 / 2 = first generation (P in tensor memory / through shared memory / P and Q in
+ * tensor memory).  All give the same results up to accumulation order; returns the previous value, -1 = query only. */
+int vlb200_set_attn_fwd_variant(int variant);
 
 /* ---- dtype tags ---------------------------------------------------------------------- */
 #define VLB200_BF16 0

@@ -258,7 +258,17 @@ def ref_attention(q, k, v, causal, seqlens, scale):
     (3, 130, 4, 2, 128, True, [130, 64, 1]),  # GQA, ragged
     (1, 64, 2, 2, 64, True, None),
 ])
-def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
+@pytest.mark.parametrize("fwd_variant", [5, 4, 1, 0])
+def test_attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens, fwd_variant):
+    """fwd_variant: every generation of the forward kernel the library ships (include/vlb200.h vlb200_set_attn_fwd_variant)."""
+    prev = ops.set_attn_fwd_variant(fwd_variant)
+    try:
+        _attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens)
+    finally:
+        ops.set_attn_fwd_variant(prev)
+
+
+def _attention_fwd_bwd(ops, B, S, H, KV, dh, causal, lens):
     fwd, bwd = ops.attn_fwd_tc, ops.attn_bwd_tc
     torch.manual_seed(S + H)
     dev = "cuda"
@@ -404,7 +414,16 @@ def test_adamw_matches_torch(ops):
     (3, 300, 4, 4, 64, [256, 300, 128]),      # lengths on tile boundaries
     (2, 96, 2, 2, 64, [0, 96]),               # an empty sequence
 ])
-def test_attention_varlen_equals_padded(ops, B, S, H, KV, dh, lens):
+@pytest.mark.parametrize("fwd_variant", [5, 4])
+def test_attention_varlen_equals_padded(ops, B, S, H, KV, dh, lens, fwd_variant):
+    prev = ops.set_attn_fwd_variant(fwd_variant)
+    try:
+        _attention_varlen_equals_padded(ops, B, S, H, KV, dh, lens)
+    finally:
+        ops.set_attn_fwd_variant(prev)
+
+
+def _attention_varlen_equals_padded(ops, B, S, H, KV, dh, lens):
     """The var-len entry points (packed rows: sequence b at row_starts[b]) give, on every attended row, what the padded entry
     points give (same tiles relative to the sequence start, masked neighbours contribute exact zeros: at most an ulp apart),
     and write nothing else."""

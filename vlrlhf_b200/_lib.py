@@ -15,6 +15,7 @@ SIGNATURES = {
     "vlb200_abi_version": (c_int, []),
     "vlb200_last_error": (c_char_p, []),
     "vlb200_launch_count": (c_uint64, []),
+    "vlb200_set_attn_fwd_variant": (c_int, [c_int]),
     "vlb200_init_uniform": (c_int, [c_void_p, c_int, c_uint64, c_uint32, c_float, c_float, c_void_p]),
     "vlb200_perturb_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_float, c_float, c_void_p]),
     "vlb200_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,

@@ -1239,6 +1239,16 @@ static int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 }  // namespace attn_tc
 }  // namespace vlb
 
+static int& attn_fwd_variant() {
+    static int v = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 5; }();
+    return v;
+}
+extern "C" int vlb200_set_attn_fwd_variant(int variant) {
+    const int prev = attn_fwd_variant();
+    if (variant >= 0) attn_fwd_variant() = variant;
+    return prev;
+}
+
 // diagnostics: read (and reset) the phase counters of the DBG-8 variants; not part of the ABI in include/vlb200.h
 extern "C" int vlbdbg_attn_fwd_profile(unsigned long long* out16, int reset) {
     if (cudaMemcpyFromSymbol(out16, vlb::attn_tc::g_fwd_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return 1;
@@ -1276,7 +1286,7 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
     // generation (attn_fwd_tc2_kernel, four); first generation: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q
     // in tensor memory; 45 = variant 5 with every fourth exponential as a polynomial; 80 / 81 / 84 / 85 / 125 = variants
     // 0 / 1 / 4 / 5 / 45 with per-phase cycle counters (tests/attn_phase_probe.py)
-    static const int variant = [] { const char* e = getenv("VLB200_ATTN_FWD_VARIANT"); return e ? atoi(e) : 5; }();
+    const int variant = attn_fwd_variant();
     cudaStream_t st = as_stream(stream);
     if (head_dim == 64) {
         if (variant == 0) return attn_tc::launch<64, 0>(tq, tk, tv, p, st);

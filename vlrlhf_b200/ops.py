@@ -44,6 +44,11 @@ def launch_count() -> int:
     return int(_L.vlb200_launch_count())
 
 
+def set_attn_fwd_variant(variant: int) -> int:
+    """Select the attention forward kernel generation (include/vlb200.h); returns the previous one (-1: query only)."""
+    return int(_L.vlb200_set_attn_fwd_variant(int(variant)))
+
+
 def init_uniform_(t: torch.Tensor, seed: int, scale: float, shift: float = 0.0) -> torch.Tensor:
     assert t.is_contiguous()
     check(_L.vlb200_init_uniform(_ptr(t), _dt(t), t.numel(), seed & 0xFFFFFFFF, scale, shift, _stream()))
