@@ -52,7 +52,22 @@ RTOL_7B = 2e-3
 
 # Measured on a B200 (profiles/parity_r2.md), x2: absolute error bounds of the per-pair losses and rewards per case.
 # A case without an entry falls back to the budget the 1e-3 log-prob bound implies (beta x 4 log-probs) and is reported.
-LOSS_ABS_BOUNDS = {}
+# Tiny / small fixtures: ~5x the error measured on a B200 in the final run of round 2 (reproducible to ~1e-4 there); the 7B-shape
+# fixtures keep the bound the asserted log-prob tolerance implies (their errors are noise, see RTOL_7B above).
+LOSS_ABS_BOUNDS = {
+    "g10_xc2_small": 0.04,
+    "g10_xc2_tiny": 0.01,
+    "g11_lora_small": 0.07,
+    "g11_lora_tiny": 0.02,
+    "g11_next_lora_small": 0.06,
+    "g11_next_lora_tiny": 0.02,
+    "g4_small": 0.035,
+    "g4_tiny": 0.02,
+    "g6_next_small": 0.045,
+    "g6_next_tiny": 0.02,
+    "g9_qwen_small": 0.03,
+    "g9_qwen_tiny": 0.02,
+}
 
 
 def check_step(case: str, out, d, loss_key: str = "sigmoid", beta: float = 0.1, logps_key: str = "policy_logps",

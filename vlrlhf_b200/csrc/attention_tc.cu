@@ -1143,9 +1143,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 VLB_PROF(6);   // O correction (rare), store completion, fences, publish
             }
             // ---- epilogue: wait for the last PV, normalise, store this warp's O columns (through its staging block) and LSE
-            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 95);
-            tcgen05_fence_after();
-            if (DBG & 8) { const long long t_ = clock64(); prof[11] += (unsigned long long)(t_ - tp); tp = t_; }   // wait for the last PV
+            // (everything that does not need O first: the last PV is still executing)
             sts_f32(sl_a + ((half * 128 + r) << 2), l_part);
             pair_sync();
             const float l_run = l_part + lds_f32(sl_a + (((half ^ 1) * 128 + r) << 2));
@@ -1155,7 +1153,12 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             const int row_lim = (p.row_starts && p.seqlens) ? min(p.seqlens[b], p.S) : p.S;
             const long long row0 = p.row_starts ? p.row_starts[b] : (long long)b * p.S;
             __nv_bfloat16* obase = p.o + (row0 + qb * BM + quad * 32) * p.ldo + (long long)h * DH + half * OC;
-            if (DBG & 8) { const long long t_ = clock64(); prof[12] += (unsigned long long)(t_ - tp); tp = t_; }   // row-sum exchange, 1/l, addresses
+            if (half == 0 && qrow < row_lim && p.lse)
+                p.lse[((long long)b * p.H + h) * p.S + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * LN2_F : -INFINITY;
+            if (DBG & 8) { const long long t_ = clock64(); prof[12] += (unsigned long long)(t_ - tp); tp = t_; }   // row-sum exchange, 1/l, LSE, addresses
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 95);
+            tcgen05_fence_after();
+            if (DBG & 8) { const long long t_ = clock64(); prof[11] += (unsigned long long)(t_ - tp); tp = t_; }   // wait for the last PV
 #pragma unroll
             for (int c = 0; c < OC / 32; ++c) {
                 uint32_t orow[32];
@@ -1182,8 +1185,6 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 __syncwarp();
                 if (DBG & 8) { const long long t_ = clock64(); prof[13] += (unsigned long long)(t_ - tp); tp = t_; }   // O chunk: staging load, global store
             }
-            if (half == 0 && qrow < row_lim && p.lse)
-                p.lse[((long long)b * p.H + h) * p.S + qrow] = l_run > 0.f ? (m_run + log2f(l_run)) * LN2_F : -INFINITY;
             tcgen05_fence_before();
             __syncwarp();
             if (lane_idx == 0) mbar_arrive(o_free);
