@@ -63,7 +63,7 @@ def run(fn, reader, width, names, reps=5):
                 print(f"      {nm:52s} {per:8.0f} cycles per {'item' if nm.startswith('item:') else 'tile'}   ({100 * vals[i] / tot:4.1f} %)")
 
 
-if os.environ.get("VLB200_ATTN_FWD_VARIANT", "0") in ("80", "81", "82", "84", "85", "125"):
+if os.environ.get("VLB200_ATTN_FWD_VARIANT", "0") in ("80", "81", "82", "84", "85", "125", "105", "245", "265"):
     run(fwd, lib.vlbdbg_attn_fwd_profile, 16, ["forward", ["item: start (plan, Q copy)", "wait for S", "TMEM -> registers (S)", "mask + row max",
                                                           "exp2, row sum, pack, P store issue", "wait for the previous PV",
                                                           "O correction, store completion, fences, publish", "item: epilogue"]])

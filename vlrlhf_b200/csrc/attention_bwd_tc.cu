@@ -217,7 +217,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
             const int xcol = hx * DH;  // MODE 0: kv head; MODE 1: q head
             if (lane_idx == 0) {
-                mbar_wait(x_empty, (item & 1) ^ 1, 10);
+                mbar_wait_relaxed(x_empty, (item & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(x_full, 2 * X_BYTES);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
@@ -248,7 +248,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 Seg sg; int yt, rep;
                 item_tile(it, t, sg, yt, rep);
                 const int ycol = (MODE == 0 ? (hx * group + rep) : (hx / group)) * DH;
-                mbar_wait(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
+                mbar_wait_relaxed(&y_empty[st], ((yc / NST) & 1) ^ 1, 20 + st);
                 __syncwarp();
                 if (lane_idx == 0) {
                     if (DBG & 4) {
@@ -298,13 +298,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             const Item it = item_plan<MODE>(p, b, xb);
             const int n = __shfl_sync(0xffffffffu, it.per_rep * it.reps, 0);
             if (n == 0) continue;
-            if (MODE == 1) mbar_wait(xt_full, item & 1, 31);
-            else mbar_wait(x_full, item & 1, 30);
+            if (MODE == 1) mbar_wait_relaxed(xt_full, item & 1, 31);
+            else mbar_wait_relaxed(x_full, item & 1, 30);
             __syncwarp();
             for (int ts = 0; ts < n; ++ts, ++tc) {
                 const uint32_t st = tc % NST, tb = tc & 1;
-                mbar_wait(&y_full[st], (tc / NST) & 1, 40);
-                if (tc >= 2) mbar_wait(&e_done[tb], ((tc - 2) >> 1) & 1, 44);
+                mbar_wait_relaxed(&y_full[st], (tc / NST) & 1, 40);
+                if (tc >= 2) mbar_wait_relaxed(&e_done[tb], ((tc - 2) >> 1) & 1, 44);
                 __syncwarp();
                 VLB_TRACE(5, tc);
                 tcgen05_fence_after();
@@ -351,8 +351,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
             if (n == 0) continue;
             for (int ta = 0; ta < n; ++ta, ++ec) {
                 const uint32_t st = ec % NST, eb = ec & 1;
-                mbar_wait(&e_full[eb], (ec >> 1) & 1, 41);
-                if (ta == 0) mbar_wait(acc_free, (item & 1) ^ 1, 60);   // the previous item's epilogue has read the accumulators
+                mbar_wait_relaxed(&e_full[eb], (ec >> 1) & 1, 41);
+                if (ta == 0) mbar_wait_relaxed(acc_free, (item & 1) ^ 1, 60);   // the previous item's epilogue has read the accumulators
                 __syncwarp();
                 VLB_TRACE(3, ec);
                 tcgen05_fence_after();
@@ -476,6 +476,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                 // divergence region per element (seen in the r1 SASS: 33 BSSY/BSYNC pairs, 134 ISETP per 32 elements)
                 auto tile_body = [&](auto masked_tag) {
                     constexpr bool MASKED = decltype(masked_tag)::value;
+                    const uint64_t sl2p = pack_f32x2(sl2, sl2);
 #pragma unroll
                     for (int c4 = 0; c4 < 32; c4 += 4) {
                         float l4[4], d4[4];
@@ -487,19 +488,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_x1, const __grid_cons
                             for (int e = 0; e < 4; ++e) { l4[e] = row_lse2; d4[e] = row_delta; }
                         }
                         float pv[4], dv[4];
+                        if (!MASKED) {
+                            // two elements per instruction (FFMA2 / FADD2 / FMUL2): the phase costs (non-MUFU instructions) + (MUFU
+                            // instructions), serialised (profiles/r2ah_experiment.log)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int col = half * 32 + c4 + e;
-                            float pr = fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]);
-                            if (!(DBG & 2)) pr = ex2_approx(pr);
-                            if (MASKED) {
+                            for (int e = 0; e < 4; e += 2) {
+                                const uint64_t xp = fma_f32x2(pack_f32x2(__uint_as_float(t1[c4 + e]), __uint_as_float(t1[c4 + e + 1])), sl2p,
+                                                              pack_f32x2(-l4[e], -l4[e + 1]));
+                                float x0, x1;
+                                unpack_f32x2(xp, x0, x1);
+                                if (!(DBG & 2)) { x0 = ex2_approx(x0); x1 = ex2_approx(x1); }
+                                pv[e] = x0; pv[e + 1] = x1;
+                                const uint64_t dd = add_f32x2(pack_f32x2(__uint_as_float(t2[c4 + e]), __uint_as_float(t2[c4 + e + 1])),
+                                                              pack_f32x2(-d4[e], -d4[e + 1]));
+                                unpack_f32x2(mul_f32x2(pack_f32x2(x0, x1), dd), dv[e], dv[e + 1]);   // (x scale in the epilogue)
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int col = half * 32 + c4 + e;
+                                float pr = fmaf(__uint_as_float(t1[c4 + e]), sl2, -l4[e]);
+                                if (!(DBG & 2)) pr = ex2_approx(pr);
                                 // stationary index xrow < kv_len, streamed index y0 + col < ylen; causal inside a sequence only
                                 const int key = MODE == 0 ? xrow : y0 + col;
                                 const int qi = MODE == 0 ? y0 + col : xrow;
                                 if (!(xrow < kv_len && y0 + col < ylen && (!causal_t || key <= qi))) pr = 0.f;
+                                pv[e] = pr;
+                                dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]);   // (x scale in the epilogue: dK / dQ are linear in dS)
                             }
-                            pv[e] = pr;
-                            dv[e] = pr * (__uint_as_float(t2[c4 + e]) - d4[e]);   // (x scale in the epilogue: dK / dQ are linear in dS)
                         }
                         e1[c4 >> 1] = pack_bf16x2(pv[0], pv[1]); e1[(c4 >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
                         e2[c4 >> 1] = pack_bf16x2(dv[0], dv[1]); e2[(c4 >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);

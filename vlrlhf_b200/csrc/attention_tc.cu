@@ -935,18 +935,18 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 const int n_tiles = plan.n_ctx + plan.n_self;
                 const int row0 = p.row_starts ? p.row_starts[b] : b * p.S;
                 const uint32_t qs = item & 1;
-                mbar_wait(&q_empty[qs], ((item >> 1) & 1) ^ 1, 10);
+                mbar_wait_relaxed(&q_empty[qs], ((item >> 1) & 1) ^ 1, 10);
                 mbar_arrive_expect_tx(&q_full[qs], T_BYTES);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_q, &q_full[qs], sQ + qs * T_BYTES + c * CHUNK_BYTES, h * DH + c * 64, row0 + qb * BM);
                 for (int j = 0; j < n_tiles; ++j, ++g) {
                     const int krow = j < plan.n_ctx ? plan.ctx_row0 + j * BN : row0 + (j - plan.n_ctx) * BN;
                     const uint32_t ks = g % NKS, vs = g % NVS;
-                    mbar_wait(&k_empty[ks], ((g / NKS) & 1) ^ 1, 20);   // S of the tile two back has retired
+                    mbar_wait_relaxed(&k_empty[ks], ((g / NKS) & 1) ^ 1, 20);   // S of the tile two back has retired
                     mbar_arrive_expect_tx(&k_full[ks], T_BYTES);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_k, &k_full[ks], sK + ks * T_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
-                    mbar_wait(&v_empty[vs], ((g / NVS) & 1) ^ 1, 21);   // PV of the tile two back has retired
+                    mbar_wait_relaxed(&v_empty[vs], ((g / NVS) & 1) ^ 1, 21);   // PV of the tile two back has retired
                     mbar_arrive_expect_tx(&v_full[vs], T_BYTES);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) tma_load_2d(&tma_v, &v_full[vs], sV + vs * T_BYTES + c * CHUNK_BYTES, kvh * DH + c * 64, krow);
@@ -965,11 +965,11 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             if (__shfl_sync(0xffffffffu, (int)plan.skip, 0)) continue;
             const int n_tiles = __shfl_sync(0xffffffffu, plan.n_ctx + plan.n_self, 0);
             const uint32_t qs = item & 1;
-            mbar_wait(&q_full[qs], (item >> 1) & 1, 30);
+            mbar_wait_relaxed(&q_full[qs], (item >> 1) & 1, 30);
             for (int j = 0; j < n_tiles; ++j, ++g) {
                 const uint32_t sb = g & 1, ks = g % NKS;
-                mbar_wait(&k_full[ks], (g / NKS) & 1, 31);
-                mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 32);   // the softmax warps have S_{g-2} in registers
+                mbar_wait_relaxed(&k_full[ks], (g / NKS) & 1, 31);
+                mbar_wait_relaxed(&s_empty[sb], ((g >> 1) & 1) ^ 1, 32);   // the softmax warps have S_{g-2} in registers
                 __syncwarp();
                 tcgen05_fence_after();
                 uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + qs * T_BYTES), 1024, 0);
@@ -1001,9 +1001,9 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             const int n_tiles = __shfl_sync(0xffffffffu, plan.n_ctx + plan.n_self, 0);
             for (int j = 0; j < n_tiles; ++j, ++g) {
                 const uint32_t sb = g & 1, vs = g % NVS;
-                mbar_wait(&p_full[sb], (g >> 1) & 1, 40);
-                mbar_wait(&v_full[vs], (g / NVS) & 1, 41);
-                if (j == 0) mbar_wait(o_free, (item & 1) ^ 1, 42);   // the epilogue of the previous query tile has read O
+                mbar_wait_relaxed(&p_full[sb], (g >> 1) & 1, 40);
+                mbar_wait_relaxed(&v_full[vs], (g / NVS) & 1, 41);
+                if (j == 0) mbar_wait_relaxed(o_free, (item & 1) ^ 1, 42);   // the epilogue of the previous query tile has read O
                 __syncwarp();
                 tcgen05_fence_after();
                 uint64_t dvv = make_smem_desc_sw128(smem_u32(sV + vs * T_BYTES), 1024, CHUNK_BYTES);
@@ -1101,23 +1101,30 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 const float neg_m = m_run == -INFINITY ? 0.f : -m_run;
                 VLB_PROF(3);   // mask + row max
                 // P = exp2(s*c - m) (bf16) into P buffer g & 1, this warp's 32 columns (keys 2i | 2i+1 of its half in column i)
-                float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+                // two elements per instruction where the pipe allows it (FFMA2 for the scale + shift, FADD2 for the row sum): the
+                // phase costs (non-MUFU instructions) + (MUFU instructions), serialised -- 399 + 732 cycles, profiles/r2ah
+                const uint64_t sl2p = pack_f32x2(sl2, sl2), negp = pack_f32x2(neg_m, neg_m);
+                uint64_t rsa = pack_f32x2(0.f, 0.f), rsb = rsa;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t wt[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * u]), sl2, neg_m));
-                        const float x1 = fmaf(__uint_as_float(sr[c][2 * u + 1]), sl2, neg_m);
-                        // DBG bit 4 (variant 45): every fourth exponential on the FMA pipe -- with two softmax warps per scheduler
-                        // the exponential phase is MUFU-bound (1095 cycles against a floor of 1024: profiles/r2aa_attn.log)
-                        const float p1 = ((DBG & 4) && (u & 1)) ? ex2_poly(x1) : ex2_approx(x1);
-                        wt[u] = pack_bf16x2(p0, p1);
-                        if (u & 1) { rs2 += p0; rs3 += p1; }
-                        else { rs0 += p0; rs1 += p1; }
+                        const uint64_t xp = fma_f32x2(pack_f32x2(__uint_as_float(sr[c][2 * u]), __uint_as_float(sr[c][2 * u + 1])), sl2p, negp);
+                        float x0, x1;
+                        unpack_f32x2(xp, x0, x1);
+                        const float p0 = (DBG & 2) ? x0 : ex2_approx(x0);   // (DBG 2 / 16: timing diagnostics without ex2 / without the bf16 pack)
+                        // DBG bit 4 (variant 45): every fourth exponential on the FMA pipe
+                        const float p1 = (DBG & 2) ? x1 : ((DBG & 4) && (u & 1)) ? ex2_poly(x1) : ex2_approx(x1);
+                        wt[u] = (DBG & 16) ? (__float_as_uint(p0) ^ (__float_as_uint(p1) >> 16)) : pack_bf16x2(p0, p1);
+                        if (u & 1) rsb = add_f32x2(rsb, pack_f32x2(p0, p1));
+                        else rsa = add_f32x2(rsa, pack_f32x2(p0, p1));
                     }
                     tmem_st_32x32_x16(tmem_base + lane_addr + TM_P + sb * 64 + half * 32 + c * 16, wt);
                 }
+                float rs0, rs1, rs2, rs3;
+                unpack_f32x2(rsa, rs0, rs1);
+                unpack_f32x2(rsb, rs2, rs3);
                 l_part = l_part * corr + ((rs0 + rs1) + (rs2 + rs3));
                 VLB_PROF(4);   // exponentials, row sum, pack, P store issue
                 // the (rare) O correction needs the previous PV retired; waiting for it every tile also keeps the pv_done phase
@@ -1307,6 +1314,9 @@ extern "C" int vlb200_attn_fwd_tc_ctx(const void* q, int64_t ldq, const void* k,
         case 85: return attn_tc::launch3<128, 8>(tq, tk, tv, p, st);
         case 45: return attn_tc::launch3<128, 4>(tq, tk, tv, p, st);
         case 125: return attn_tc::launch3<128, 12>(tq, tk, tv, p, st);
+        case 105: return attn_tc::launch3<128, 10>(tq, tk, tv, p, st);
+        case 245: return attn_tc::launch3<128, 24>(tq, tk, tv, p, st);
+        case 265: return attn_tc::launch3<128, 26>(tq, tk, tv, p, st);
         default: return attn_tc::launch3<128, 0>(tq, tk, tv, p, st);
     }
 }

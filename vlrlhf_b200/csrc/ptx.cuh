@@ -61,6 +61,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int co
     }
 }
 
+// Blocking wait for the single-warp roles (TMA producer, MMA issuers): backs off with nanosleep between polls.  The plain
+// spin above re-polls every few cycles (try_wait's suspension is short), and the role warps share their scheduler with two
+// softmax / elementwise warps: ~15 % of all issue-slot samples of the attention forward were these `@P0 BRA` spin loops
+// (profiles/r2ae ncu source page).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if (clock64() - t0 > VLB_WATCHDOG_CYCLES) {
+            printf("[vlb200] mbarrier watchdog: block %d thread %d waiter %d parity %u\n", blockIdx.x, threadIdx.x, code,
+                   parity);
+            __trap();
+        }
+    }
+}
+
 // ---- explicit shared-memory accesses ---------------------------------------------------------------------------------
 // Through a C++ pointer into the dynamic shared-memory block the compiler emits GENERIC loads / stores (LD.E / ST.E): slower,
 // and a generic load cannot be hoisted over a global store it might alias -- the attention epilogues ran
@@ -80,6 +97,29 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two floats per 64-bit register pair and instruction) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 // ---- TMA -------------------------------------------------------------------------------
