@@ -623,26 +623,27 @@ static int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMa
 // ------------------------------------------------------------------ backward: delta = rowsum(dO * O)
 // row_starts (or null): first row of each sequence when the rows are ragged / packed; delta stays [B, H, S]
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout,
-                                  long long lddo, float* __restrict__ delta, const int* __restrict__ row_starts, size_t rows,
+                                  long long lddo, float* __restrict__ delta, const int* __restrict__ row_starts, uint32_t rows,
                                   int B, int S, int H, int DH) {
     // 16-byte loads: DH / 8 lanes cover one (row, head) -- 16 lanes at head_dim 128, 8 at 64 -- so a warp reduces 2 or 4 pairs
-    // per pass (4-byte loads, one pair per warp, reached 29 % of the HBM bandwidth: profiles/r1b_ncu_summary.md)
-    const int lanes = DH >> 3;                  // lanes per (row, head)
-    const int per_warp = 32 / lanes;
-    const int warps_per_block = blockDim.x >> 5;
-    const size_t total = rows * H;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / lanes, li = lane % lanes;
-    for (size_t w0 = (blockIdx.x * (size_t)warps_per_block + (threadIdx.x >> 5)) * per_warp; w0 < total;
-         w0 += (size_t)gridDim.x * warps_per_block * per_warp) {
-        const size_t w = w0 + sub;
+    // per pass (4-byte loads, one pair per warp, reached 29 % of the HBM bandwidth: profiles/r1b_ncu_summary.md); 32-bit index
+    // arithmetic (with 64-bit divisions per pair the kernel was ALU-bound: 72 % ALU, profiles/r2ae_ncu_summary.md).
+    const uint32_t lanes = (uint32_t)DH >> 3;   // lanes per (row, head)
+    const uint32_t per_warp = 32u / lanes;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t total = rows * (uint32_t)H;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sub = lane / lanes, li = lane % lanes;
+    for (uint32_t w0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * per_warp; w0 < total;
+         w0 += gridDim.x * warps_per_block * per_warp) {
+        const uint32_t w = w0 + sub;
         const bool live = w < total;
-        const int h = live ? (int)(w % H) : 0;
-        const size_t row = live ? w / H : 0;  // b*S + t, or row_starts[b] + t
+        const uint32_t row = live ? w / (uint32_t)H : 0u;   // b*S + t, or row_starts[b] + t
+        const uint32_t h = live ? w - row * (uint32_t)H : 0u;
         float acc = 0.f;
         if (live) {
-            const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + (size_t)h * DH + li * 8);
-            const uint4 d = *reinterpret_cast<const uint4*>(dout + row * lddo + (size_t)h * DH + li * 8);
+            const uint4 a = *reinterpret_cast<const uint4*>(o + (size_t)row * ldo + (size_t)h * DH + li * 8);
+            const uint4 d = *reinterpret_cast<const uint4*>(dout + (size_t)row * lddo + (size_t)h * DH + li * 8);
             const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -650,15 +651,15 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
                 acc += x.x * y.x + x.y * y.y;
             }
         }
-        for (int off = lanes >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        for (uint32_t off = lanes >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (live && li == 0) {
-            size_t b = row / S, t = row % S;
+            uint32_t b = row / (uint32_t)S, t = row - b * (uint32_t)S;
             if (row_starts != nullptr) {
                 b = 0;
-                while (b + 1 < (size_t)B && (size_t)row_starts[b + 1] <= row) ++b;
-                t = row - (size_t)row_starts[b];
+                while (b + 1 < (uint32_t)B && (uint32_t)row_starts[b + 1] <= row) ++b;
+                t = row - (uint32_t)row_starts[b];
             }
-            if (t < (size_t)S) delta[(b * H + h) * S + t] = acc;
+            if (t < (uint32_t)S) delta[((size_t)b * H + h) * S + t] = acc;
         }
     }
 }
@@ -687,10 +688,11 @@ extern "C" int vlb200_attn_delta_varlen(const void* out, int64_t ldo, const void
                 "attn_delta: head_dim must be a power of two in [8, 256], row strides multiples of 8");
     VLB_REQUIRE(row_starts == nullptr || total_rows > 0, "attn_delta: row_starts needs total_rows");
     const size_t rows = row_starts ? (size_t)total_rows : (size_t)B * S;
+    VLB_REQUIRE(rows * (size_t)H < (1ull << 31), "attn_delta: rows x heads must be below 2^31");
     const size_t nw = rows * H;   // (row, head) pairs; a warp takes 32 / (head_dim / 8) of them per pass
     const int blocks = (int)std::min<size_t>((nw * (head_dim / 8) / 32 + 7) / 8, (size_t)vlb::num_sms() * 16);
     vlb::attn_bwd_tc::attn_delta_kernel<<<blocks, 256, 0, vlb::as_stream(stream)>>>((const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)dout, lddo,
-                                                                  delta, row_starts, rows, B, S, H, head_dim);
+                                                                  delta, row_starts, (uint32_t)rows, B, S, H, head_dim);
     vlb::count_launch();
     VLB_LAUNCH_CHECK();
     return VLB200_OK;
