@@ -68,8 +68,17 @@ def _worker(rank, world, port, out_dir):
     eng4.init_synthetic(0)
     eng4.step(*a[:4], train=True)
     packed_rows = eng4._saved["m"].T
+    # shared-prefix rows (TrainConfig.share_prefix) under the sharded step: every rank lays out its own pairs' common prefixes
+    # once -- again a rank-local row count no collective depends on; the reduced gradient slice equals the padded step's up to
+    # the accumulation order of the rows
+    eng5 = engine.LlavaDPOEngine(config.TINY, config.TrainConfig(learning_rate=1e-3, share_prefix=True), device="cpu")
+    eng5.init_synthetic(0)
+    plan = eng5.host_row_plan(cb["concatenated_input_ids"], cb["concatenated_attention_mask"])
+    eng5.step(*a[:4], train=True, **plan)
+    shared_rows = eng5._saved["m"].T
     n = eng.params.numel()
-    torch.save({"params_packed": eng4.params[:n].clone(), "packed_rows": packed_rows,
+    torch.save({"params_packed": eng4.params[:n].clone(), "packed_rows": packed_rows, "shared_rows": shared_rows,
+                "params_shared": eng5.params[:n].clone(), "grads_shared_own": eng5.grads[eng5.shard_lo:eng5.shard_hi].clone(),
                 "padded_rows": eng4._saved["m"].n_seq * eng4._saved["m"].S, "local": local, "summed": summed, "params": eng.params.clone(), "world": eng.world_size(),
                 "sumsq": eng.grad_sumsq.clone(), "params_overlap": eng2.params.clone(), "grads_overlap": eng2.grads.clone(),
                 "params_sharded": eng3.params[:n].clone(), "sumsq_sharded": eng3.grad_sumsq.clone(),
@@ -116,6 +125,13 @@ def test_two_rank_data_parallel_step(tmp_path):
     # packed rows: identical replicas, identical to the padded sharded step
     assert torch.equal(r0["params_packed"], r1["params_packed"]) and torch.equal(r0["params_packed"], r0["params_sharded"])
     assert r0["packed_rows"] < r0["padded_rows"] or r1["packed_rows"] < r1["padded_rows"]
+    # shared-prefix rows: identical replicas after the all-gather; each rank's reduced gradient slice is the padded step's up to
+    # the accumulation order (fewer rows: the common prefix of every pair once)
+    assert torch.equal(r0["params_shared"], r1["params_shared"])
+    assert r0["shared_rows"] < r0["packed_rows"] and r1["shared_rows"] < r1["packed_rows"]
+    for r in (r0, r1):
+        g_s, g_p = r["grads_shared_own"].float(), r["grads_sharded_own"].float()
+        assert float((g_s - g_p).norm() / g_p.norm().clamp_min(1e-12)) < 2e-2
 
 
 def _qwen_worker(rank, world, port, out_dir):
@@ -142,6 +158,14 @@ def _qwen_worker(rank, world, port, out_dir):
         eng.train_step(batch, train=True)
         out[f"params{shard}"] = eng.params[: eng.layout.size].clone()
         out[f"base{shard}"] = eng.bparams.clone()
+        if shard == "1":   # the same sharded step with shared-prefix rows (rank-local row plan from the host batch)
+            out["grads_own"] = eng.grads[eng.shard_lo:eng.shard_hi].clone()
+            eng_s = EQ.QwenVLDPOEngine(config.TINY_QWEN, config.TrainConfig(learning_rate=1e-3, share_prefix=True), device="cpu")
+            eng_s.init_synthetic(0)
+            eng_s.train_step(batch, train=True)
+            assert eng_s._saved["m"].shared and eng_s._saved["m"].shared_rows > 0
+            out["params_shared"] = eng_s.params[: eng_s.layout.size].clone()
+            out["grads_shared_own"] = eng_s.grads[eng_s.shard_lo:eng_s.shard_hi].clone()
     torch.save(out, os.path.join(out_dir, f"qrank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -158,3 +182,9 @@ def test_two_rank_qwen_lora_step(tmp_path):
         assert torch.equal(r0[f"params{s}"], r1[f"params{s}"])
         assert torch.equal(r0[f"base{s}"], r1[f"base{s}"])
     assert (r0["params0"] == r0["params1"]).float().mean().item() > 0.9999
+    # shared-prefix rows under the sharded step: identical replicas; the rank's reduced gradient slice is the padded step's up to
+    # the accumulation order
+    assert torch.equal(r0["params_shared"], r1["params_shared"])
+    for r in (r0, r1):
+        g_s, g_p = r["grads_shared_own"].float(), r["grads_own"].float()
+        assert float((g_s - g_p).norm() / g_p.norm().clamp_min(1e-12)) < 2e-2
