@@ -501,6 +501,8 @@ def run_b200(args):
                            "path": "plugin.concatenated_forward(policy) + (RefView) -> plugin.dpo_loss -> losses.mean().backward() "
                                    "-> B200FlatAdamW.step() -> model.zero_grad(): trl get_batch_loss_metrics + HF training_step"},
             "gpu_launches": launches,
+            "hbm_gb": {"peak_allocated": torch.cuda.max_memory_allocated() / 1e9, "peak_reserved": torch.cuda.max_memory_reserved() / 1e9,
+                       "device_total": torch.cuda.get_device_properties(local).total_memory / 1e9},
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_2cta_kernel<6,K-major,K-major> (tcgen05 cta_group::2, 256x256 pair tiles, gate_up fwd shape)",
                          "achieved": gemm_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
                          "peak_source": f"{pk_src} (burst; kernel timed alone)", "traffic": traffic, "traffic_detail": traffic_detail},
